@@ -1,0 +1,145 @@
+/*
+ * spiral_b200.h - C-ABI of libspiral_b200.so: the B200 (sm_100a) implementation of Spiral's
+ * server-side query answering.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * tree menonsamir/spiral).  The reference has no FFI: its path sits behind C++ free functions
+ * with external linkage, so a maintainer binds these symbols from thin definitions of those
+ * functions (INTEGRATION.md shows the stubs; spiral_b200/csrc/host_mirror.cpp is that file).
+ *
+ * Three tiers:
+ *   sb200_dev_*     device pointers + stream: the kernels, for callers that keep data in HBM
+ *   sb200_<refname> host pointers in the REFERENCE's layouts: one call = H2D, kernels, D2H
+ *   sb200_server_*  a resident server: database + public parameters live in HBM, one query in,
+ *                   one response out
+ *
+ * Layouts.  "ref-NTT": uint64_t data[(r*cols+c)*2*2048 + n*2048 + z], n = 0 mod p / 1 mod b
+ * (reference include/poly.h:24-64).  "raw": uint64_t data[(r*cols+c)*2048 + z] in [0,Q].
+ * "dev-NTT": uint32_t with the same index order (residues are 28-bit).  "PB64": one uint64_t =
+ * residue mod p | residue mod b << 32 (reference src/spiral.cpp:429).
+ *
+ * All functions return 0 on success and a negative code on failure; sb200_last_error() gives the
+ * text.  There is NO CPU fallback: without a CUDA device every compute entry fails with
+ * SB200_ERR_NO_DEVICE.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef SPIRAL_B200_H
+#define SPIRAL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_OK 0
+#define SB200_ERR_NO_DEVICE (-1)
+#define SB200_ERR_CUDA (-2)
+#define SB200_ERR_ARG (-3)
+#define SB200_ERR_STATE (-4)
+
+#define SB200_POLY_LEN 2048
+
+/* Scheme parameters: the reference's compile-time -D values (include/values.h:78-93) at run time. */
+typedef struct sb200_params {
+    uint32_t nu1;          /* num_expansions (argv[1])   */
+    uint32_t nu2;          /* further_dims   (argv[2])   */
+    uint32_t t_gsw;        /* TGSW      */
+    uint32_t t_conv;       /* TCONV     */
+    uint32_t t_exp;        /* TEXP      */
+    uint32_t t_exp_right;  /* TEXPRIGHT */
+    uint32_t qp_bits;      /* QPBITS    */
+    uint32_t out_n;        /* OUTN (Pack variants) */
+    uint64_t p_db;         /* PVALUE    */
+} sb200_params;
+
+/* ---- library -------------------------------------------------------------------------- */
+int sb200_init(int device);                 /* cudaSetDevice + twiddle tables for that device */
+const char *sb200_last_error(void);
+int sb200_abi_version(void);
+uint64_t sb200_arb_qprime(uint32_t qp_bits);           /* include/values.h:74-76 */
+/* kernels launched by this process since load (our own launches only) */
+uint64_t sb200_launch_count(void);
+
+/* ---- tier 1: device pointers ---------------------------------------------------------- */
+int sb200_dev_ntt_from_ref(uint32_t *out, const uint64_t *in_ref_ntt, size_t npolys, void *stream);
+int sb200_dev_ntt_to_ref(uint64_t *out_ref_ntt, const uint32_t *in, size_t npolys, void *stream);
+int sb200_dev_to_ntt(uint32_t *out, const uint64_t *raw, size_t npolys, void *stream);          /* src/poly.cpp:291-329 */
+int sb200_dev_from_ntt(uint64_t *raw, const uint32_t *in, size_t npolys, void *stream);        /* src/poly.cpp:357-377 */
+int sb200_dev_multiply(uint32_t *out, const uint32_t *a, const uint32_t *b, int rs, int ms, int cs, void *stream); /* src/poly.cpp:34-78 */
+int sb200_dev_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t t, void *stream);   /* src/poly.cpp:240-261 */
+int sb200_dev_gadget_ntt(uint32_t *out, const uint64_t *raw, int mx, int rdim, int cols, void *stream); /* src/util.cpp:114-150 + to_ntt */
+int sb200_dev_rescale(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod, void *stream); /* src/poly.cpp:578-601 */
+/* database: plaintext items (u16 coefficients < p_db, [item][m*2+c][2048]) -> scan layout (load_db, src/spiral.cpp:1028-1172) */
+int sb200_dev_db_build(uint64_t *db, const uint16_t *pts, uint32_t nu1, uint32_t nu2, uint32_t p_db,
+                       size_t item_begin, size_t item_count, void *stream);
+/* database already in the reference layout B[z][ii][c][j][m] (src/spiral.cpp:1139-1153), z_count slices at B_chunk */
+int sb200_dev_db_from_reference(uint64_t *db, const uint64_t *B_chunk, size_t dim0, size_t num_per,
+                                size_t z_begin, size_t z_count, void *stream);
+size_t sb200_db_words(uint32_t nu1, uint32_t nu2);       /* uint64 words of the scan-layout database */
+int sb200_dev_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, void *stream);   /* src/spiral.cpp:410-433 */
+int sb200_dev_first_dim(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, void *stream); /* src/spiral.cpp:628-999 */
+size_t sb200_fold_scratch_words(size_t num_per_after, uint32_t t_gsw);   /* uint32 words */
+int sb200_dev_fold_round(uint64_t *cts, size_t num_per_after, const uint32_t *q, const uint32_t *q_neg,
+                         uint32_t t_gsw, uint32_t *scratch, void *stream);                      /* src/spiral.cpp:1349-1410 */
+
+/* ---- tier 2: host pointers, reference layouts (what the interposed reference functions call) */
+int sb200_to_ntt(uint64_t *out_ref_ntt, const uint64_t *raw, size_t npolys);
+int sb200_from_ntt(uint64_t *raw, const uint64_t *in_ref_ntt, size_t npolys);
+int sb200_ntt_forward(uint64_t *io_ref_ntt, size_t npolys);     /* ntt_forward, src/core.cpp:247 (values mod q) */
+int sb200_ntt_inverse(uint64_t *io_ref_ntt, size_t npolys);     /* ntt_inverse, src/core.cpp:419 */
+int sb200_multiply(uint64_t *out, const uint64_t *a, const uint64_t *b, int rs, int ms, int cs);
+int sb200_automorph(uint64_t *out_raw, const uint64_t *in_raw, size_t npolys, uint32_t t);
+int sb200_gadget_invert(uint64_t *out_raw, const uint64_t *in_raw, int mx, int rdim, int cols);   /* src/util.cpp:114-150 */
+int sb200_getRescaled(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod);
+/* load_db: pts = total_n items of n0*n2 polys, u64 coefficients < p_db (reference generate_random_pt); B in reference layout */
+int sb200_load_db(uint64_t *B_ref_layout, const uint64_t *pts, uint32_t nu1, uint32_t nu2, uint64_t p_db);
+int sb200_reorientCiphertexts(uint64_t *out, const uint64_t *inp_ref_ntt, size_t dim0, size_t n1_padded);
+int sb200_multiplyQueryByDatabase(uint64_t *out_ref_ntt, const uint64_t *reoriented, const uint64_t *database,
+                                  size_t dim0, size_t num_per);
+int sb200_nttInvAndCrtLiftCiphertexts(uint64_t *cts_raw, const uint64_t *scratch_ref_ntt, size_t num_per);
+int sb200_split_and_crt(uint64_t *out_ref_ntt, const uint64_t *in_raw, size_t num_per, uint32_t t_gsw);   /* src/spiral.cpp:270-341 */
+/* q / q_neg: the reference's reoriented GSW buffers (reorient_Q layout, stride n1*m2*2*2048 words per dimension) */
+int sb200_foldOneFurtherDimension(size_t cur_dim, size_t num_per, const uint64_t *q, const uint64_t *q_neg,
+                                  uint64_t *cts_raw, uint32_t t_gsw);
+/* cv: 2^g cts (2x1 ref-NTT); W_left: g x (2 x t_exp); W_right: g x (2 x t_exp_right) */
+int sb200_expandImproved(uint64_t *cv, size_t g, uint32_t t_exp, const uint64_t *W_left, const uint64_t *W_right,
+                         uint32_t t_exp_right, size_t max_bits_right, size_t stopround);            /* src/spiral.cpp:1664-1743 */
+int sb200_scalToMat(uint64_t *out_reg, const uint64_t *cv, const uint64_t *W, uint32_t t_conv);     /* src/spiral.cpp:1850-1885 */
+int sb200_regevToGSW(uint64_t *out, const uint64_t *cv_v, uint32_t t_conv, uint32_t t, const uint64_t *W,
+                     const uint64_t *V);                                                            /* src/spiral.cpp:1985-2025 */
+
+/* ---- tier 3: resident server ----------------------------------------------------------- */
+typedef struct sb200_server sb200_server;
+/* shard `rank` of `world` owns second-dimension indices ii = rank (mod world); world = 1 -> whole database */
+int sb200_server_create(sb200_server **out, const sb200_params *prm, int device, int rank, int world);
+void sb200_server_destroy(sb200_server *srv);
+/* database from plaintext items (u16 coefficients, this shard's items only, order j-major: item = j*local_num_per + ii_local) */
+int sb200_server_load_db_items(sb200_server *srv, const uint16_t *pts_host, size_t item_begin, size_t item_count);
+/* database handed over in the reference's layout (the WHOLE B of load_db); the shard's rows are extracted */
+int sb200_server_load_db_reference(sb200_server *srv, const uint64_t *B_host);
+uint64_t *sb200_server_db_ptr(sb200_server *srv);          /* device pointer of the scan-layout shard */
+/* public parameters, ref-NTT host buffers: W_exp_left g x (2 x t_exp), W_exp_right (stopround+1 or g) x (2 x t_exp_right),
+ * W_conv 3 x 2*t_conv, V_conv 3 x 2*t_conv  (runConversionImproved, src/spiral.cpp:2093-2300) */
+int sb200_server_set_public_params(sb200_server *srv, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
+                                   const uint64_t *W_conv, const uint64_t *V_conv);
+/* one query end to end: H2D of the packed query ciphertext (2x1 ref-NTT, 64 KiB), all server stages, D2H of the
+ * modulus-switched response (3x2 raw, 96 KiB).  world == 1 only. */
+int sb200_server_answer(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream);
+/* staged variants (device-resident between stages; used by bench.py and the multi-GPU path) */
+int sb200_server_upload_query(sb200_server *srv, const uint64_t *query_cv_host, void *stream);
+int sb200_server_expand_and_convert(sb200_server *srv, void *stream);      /* expansion + ScalToMat + RegevToGSW (+negation) */
+int sb200_server_first_dim(sb200_server *srv, void *stream);               /* scan + INTT + CRT lift */
+int sb200_server_fold_local(sb200_server *srv, void *stream);              /* local fold rounds; leaves 1 ct per shard */
+uint64_t *sb200_server_partial_ct(sb200_server *srv);                      /* device ptr: this shard's surviving ct (3x2 raw) */
+/* rank 0: `gathered` = world cts (device, order = rank); runs the last log2(world) folds + modulus switch */
+int sb200_server_fold_tail(sb200_server *srv, uint64_t *gathered_dev, uint64_t *total_resp_dev, void *stream);
+int sb200_server_download(sb200_server *srv, uint64_t *dst_host, const uint64_t *src_dev, size_t words, void *stream);
+/* debug taps (device pointers): raw cts after the first dimension; final ct before modulus switch */
+uint64_t *sb200_server_first_dim_cts(sb200_server *srv);
+size_t sb200_server_query_bytes(const sb200_server *srv);
+size_t sb200_server_response_bytes(const sb200_server *srv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPIRAL_B200_H */

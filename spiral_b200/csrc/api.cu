@@ -1,0 +1,555 @@
+// api.cu - the C-ABI of libspiral_b200.so (include/spiral_b200.h).
+#include "../../include/spiral_b200.h"
+#include "kernels.cuh"
+#include "common.cuh"
+#include "ntt.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sb200;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? SB200_ERR_NO_DEVICE : SB200_ERR_CUDA, \
+                                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CHECK_LAUNCH() CU(cudaGetLastError())
+
+static int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SB200_ERR_NO_DEVICE, "no CUDA device: libspiral_b200 has no CPU fallback (%s)", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    }
+    int rc = init_tables();
+    if (rc != 0) return fail(SB200_ERR_CUDA, "twiddle-table initialisation failed (%d)", rc);
+    return SB200_OK;
+}
+#define NEED_DEVICE() do { int rc_ = ensure_device(); if (rc_) return rc_; } while (0)
+
+extern "C" const char *sb200_last_error(void) { return g_err.c_str(); }
+extern "C" int sb200_abi_version(void) { return 1; }
+extern "C" uint64_t sb200_launch_count(void) { return launch_count(); }
+extern "C" uint64_t sb200_arb_qprime(uint32_t qp_bits) {     // reference include/values.h:74-76
+    static const uint64_t qprime_mods[37] = {
+        0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 12289, 12289, 61441, 65537, 65537, 520193, 786433,
+        786433, 3604481, 7340033, 16515073, 33292289, 67043329, 132120577, 268369921, 469762049,
+        1073479681, 2013265921, 4293918721ull, 8588886017ull, 17175674881ull, 34359214081ull, 68718428161ull};
+    return qp_bits < 37 ? qprime_mods[qp_bits] : 0;
+}
+extern "C" int sb200_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(SB200_ERR_NO_DEVICE, "no CUDA device: libspiral_b200 has no CPU fallback"); }
+    if (device < 0 || device >= n) return fail(SB200_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    CU(cudaSetDevice(device));
+    return ensure_device();
+}
+
+// ---------------------------------------------------------------------------------------------
+// tier 1: device pointers
+// ---------------------------------------------------------------------------------------------
+static inline cudaStream_t S(void *s) { return (cudaStream_t)s; }
+
+extern "C" int sb200_dev_ntt_from_ref(uint32_t *out, const uint64_t *in, size_t npolys, void *stream) {
+    NEED_DEVICE(); launch_ntt_u64_to_dev(out, in, npolys, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_ntt_to_ref(uint64_t *out, const uint32_t *in, size_t npolys, void *stream) {
+    NEED_DEVICE(); launch_ntt_dev_to_u64(out, in, npolys, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_to_ntt(uint32_t *out, const uint64_t *raw, size_t npolys, void *stream) {
+    NEED_DEVICE(); launch_to_ntt(out, raw, npolys, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_from_ntt(uint64_t *raw, const uint32_t *in, size_t npolys, void *stream) {
+    NEED_DEVICE(); launch_from_ntt(raw, in, npolys, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_multiply(uint32_t *out, const uint32_t *a, const uint32_t *b, int rs, int ms, int cs, void *stream) {
+    NEED_DEVICE(); launch_matmul(out, a, b, rs, ms, cs, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t t, void *stream) {
+    NEED_DEVICE(); launch_automorph(out, in, npolys, t, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_gadget_ntt(uint32_t *out, const uint64_t *raw, int mx, int rdim, int cols, void *stream) {
+    NEED_DEVICE();
+    if (rdim <= 0 || mx % rdim) return fail(SB200_ERR_ARG, "gadget_ntt: mx %% rdim != 0");
+    launch_gadget_ntt(out, raw, mx, rdim, cols, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_rescale(uint64_t *out, const uint64_t *in, size_t n, uint64_t inp_mod, uint64_t out_mod, void *stream) {
+    NEED_DEVICE(); launch_rescale(out, in, n, inp_mod, out_mod, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" size_t sb200_db_words(uint32_t nu1, uint32_t nu2) { return ((size_t)kN << (nu1 + nu2)) * kN0 * kN2; }
+extern "C" int sb200_dev_db_build(uint64_t *db, const uint16_t *pts, uint32_t nu1, uint32_t nu2, uint32_t p_db,
+                                  size_t item_begin, size_t item_count, void *stream) {
+    NEED_DEVICE();
+    if (p_db == 0 || p_db > 65536) return fail(SB200_ERR_ARG, "db_build: p_db must be in [1, 65536]");
+    launch_db_build_spiral(db, pts, (int)nu1, (int)nu2, p_db, item_begin, item_count, S(stream));
+    CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_db_from_reference(uint64_t *db, const uint64_t *B_chunk, size_t dim0, size_t num_per,
+                                           size_t z_begin, size_t z_count, void *stream) {
+    NEED_DEVICE(); launch_db_from_reference(db, B_chunk, dim0, num_per * kN2, z_begin, z_count, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, void *stream) {
+    NEED_DEVICE(); launch_reorient_query(out, cts, dim0, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_first_dim(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, void *stream) {
+    NEED_DEVICE();
+    if (!dim0 || !num_per || (dim0 & (dim0 - 1)) || (num_per & (num_per - 1))) return fail(SB200_ERR_ARG, "first_dim: dim0 and num_per must be powers of two");
+    launch_scan_spiral(out, query, db, dim0, num_per, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" size_t sb200_fold_scratch_words(size_t num_per_after, uint32_t t_gsw) { return fold_scratch_words(num_per_after, (int)t_gsw); }
+extern "C" int sb200_dev_fold_round(uint64_t *cts, size_t num_per_after, const uint32_t *q, const uint32_t *q_neg,
+                                    uint32_t t_gsw, uint32_t *scratch, void *stream) {
+    NEED_DEVICE(); launch_fold_round(cts, num_per_after, q, q_neg, (int)t_gsw, scratch, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tier 2: host pointers in the reference's layouts.  Small RAII device buffers + sync copies.
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <typename T>
+struct DBuf {
+    T *p = nullptr; size_t n = 0;
+    DBuf() {}
+    explicit DBuf(size_t count) { alloc(count); }
+    ~DBuf() { if (p) cudaFree(p); }
+    DBuf(const DBuf &) = delete; DBuf &operator=(const DBuf &) = delete;
+    cudaError_t alloc(size_t count) { n = count; return cudaMalloc(&p, (count ? count : 1) * sizeof(T)); }
+    cudaError_t up(const T *h, size_t count) { return cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice); }
+    cudaError_t down(T *h, size_t count) const { return cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost); }
+};
+constexpr size_t PLW = 2 * (size_t)kN;   // words of one NTT-form polynomial
+
+// ref-NTT host buffer -> dev-NTT device buffer
+int up_ntt(DBuf<uint32_t> &dst, const uint64_t *host, size_t npolys) {
+    DBuf<uint64_t> tmp;
+    CU(tmp.alloc(npolys * PLW)); CU(tmp.up(host, npolys * PLW));
+    CU(dst.alloc(npolys * PLW));
+    launch_ntt_u64_to_dev(dst.p, tmp.p, npolys, 0); CHECK_LAUNCH();
+    CU(cudaDeviceSynchronize());
+    return SB200_OK;
+}
+int down_ntt(uint64_t *host, const uint32_t *dev, size_t npolys) {
+    DBuf<uint64_t> tmp;
+    CU(tmp.alloc(npolys * PLW));
+    launch_ntt_dev_to_u64(tmp.p, dev, npolys, 0); CHECK_LAUNCH();
+    CU(tmp.down(host, npolys * PLW));
+    return SB200_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+}  // namespace
+
+extern "C" int sb200_to_ntt(uint64_t *out, const uint64_t *raw, size_t npolys) {
+    NEED_DEVICE();
+    DBuf<uint64_t> d_raw; DBuf<uint32_t> d_out;
+    CU(d_raw.alloc(npolys * kN)); CU(d_raw.up(raw, npolys * kN)); CU(d_out.alloc(npolys * PLW));
+    launch_to_ntt(d_out.p, d_raw.p, npolys, 0); CHECK_LAUNCH();
+    return down_ntt(out, d_out.p, npolys);
+}
+extern "C" int sb200_from_ntt(uint64_t *raw, const uint64_t *in, size_t npolys) {
+    NEED_DEVICE();
+    DBuf<uint32_t> d_in; DBuf<uint64_t> d_raw;
+    TRY(up_ntt(d_in, in, npolys)); CU(d_raw.alloc(npolys * kN));
+    launch_from_ntt(d_raw.p, d_in.p, npolys, 0); CHECK_LAUNCH();
+    CU(d_raw.down(raw, npolys * kN));
+    return SB200_OK;
+}
+// ntt_forward / ntt_inverse on ref-NTT buffers: forward = to_ntt of the plane values; inverse without CRT.
+// Implemented through the raw path: forward treats each plane as a raw polynomial reduced mod its own prime.
+__global__ void __launch_bounds__(sb200::kNttThreads) k_ntt_only(uint32_t *io, int inverse) {
+    __shared__ __align__(16) uint32_t sm[2][sb200::kPlaneWords];
+    const int n = sb200::plane_of_thread(), lt = sb200::lane_in_plane();
+    uint32_t *pl = io + ((size_t)blockIdx.x * 2 + n) * sb200::kN;
+    uint32_t v[16];
+    if (!inverse) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = pl[sb200::nat_pos(lt, k)];
+        sb200::ntt_forward_plane(v, sm[n], lt, n);
+        sb200::plane_sync(n);
+        sb200::store_ntt_regs(v, pl, lt);
+    } else {
+        sb200::load_ntt_regs(v, pl, lt);
+        sb200::ntt_inverse_plane(v, sm[n], lt, n);
+        sb200::plane_sync(n);
+#pragma unroll
+        for (int k = 0; k < 16; k++) pl[sb200::nat_pos(lt, k)] = v[k];
+    }
+}
+static int ntt_only(uint64_t *io, size_t npolys, int inverse) {
+    NEED_DEVICE();
+    DBuf<uint32_t> d;
+    TRY(up_ntt(d, io, npolys));
+    if (npolys) { count_launch(); k_ntt_only<<<(unsigned)npolys, kNttThreads>>>(d.p, inverse); }
+    CHECK_LAUNCH();
+    return down_ntt(io, d.p, npolys);
+}
+extern "C" int sb200_ntt_forward(uint64_t *io, size_t npolys) { return ntt_only(io, npolys, 0); }
+extern "C" int sb200_ntt_inverse(uint64_t *io, size_t npolys) { return ntt_only(io, npolys, 1); }
+
+extern "C" int sb200_multiply(uint64_t *out, const uint64_t *a, const uint64_t *b, int rs, int ms, int cs) {
+    NEED_DEVICE();
+    DBuf<uint32_t> da, db, dout;
+    TRY(up_ntt(da, a, (size_t)rs * ms)); TRY(up_ntt(db, b, (size_t)ms * cs)); CU(dout.alloc((size_t)rs * cs * PLW));
+    launch_matmul(dout.p, da.p, db.p, rs, ms, cs, 0); CHECK_LAUNCH();
+    return down_ntt(out, dout.p, (size_t)rs * cs);
+}
+extern "C" int sb200_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t t) {
+    NEED_DEVICE();
+    DBuf<uint64_t> di(npolys * kN), dout(npolys * kN);
+    CU(di.up(in, npolys * kN));
+    launch_automorph(dout.p, di.p, npolys, t, 0); CHECK_LAUNCH();
+    CU(dout.down(out, npolys * kN));
+    return SB200_OK;
+}
+extern "C" int sb200_gadget_invert(uint64_t *out, const uint64_t *in, int mx, int rdim, int cols) {
+    NEED_DEVICE();
+    if (rdim <= 0 || mx % rdim) return fail(SB200_ERR_ARG, "gadget_invert: mx %% rdim != 0");
+    DBuf<uint64_t> di((size_t)rdim * cols * kN), dout((size_t)mx * cols * kN);
+    CU(di.up(in, (size_t)rdim * cols * kN));
+    launch_gadget_raw(dout.p, di.p, mx, rdim, cols, 0); CHECK_LAUNCH();
+    CU(dout.down(out, (size_t)mx * cols * kN));
+    return SB200_OK;
+}
+extern "C" int sb200_getRescaled(uint64_t *out, const uint64_t *in, size_t n, uint64_t inp_mod, uint64_t out_mod) {
+    NEED_DEVICE();
+    DBuf<uint64_t> di(n), dout(n);
+    CU(di.up(in, n));
+    launch_rescale(dout.p, di.p, n, inp_mod, out_mod, 0); CHECK_LAUNCH();
+    CU(dout.down(out, n));
+    return SB200_OK;
+}
+extern "C" int sb200_load_db(uint64_t *B, const uint64_t *pts, uint32_t nu1, uint32_t nu2, uint64_t p_db) {
+    NEED_DEVICE();
+    if (p_db == 0 || p_db > 65536) return fail(SB200_ERR_ARG, "load_db: p_db must be in [1, 65536]");
+    const size_t total_n = (size_t)1 << (nu1 + nu2), words = sb200_db_words(nu1, nu2);
+    std::vector<uint16_t> h16(total_n * 4 * kN);
+    for (size_t i = 0; i < h16.size(); i++) h16[i] = (uint16_t)pts[i];
+    DBuf<uint16_t> dp(h16.size()); DBuf<uint64_t> ddb(words), dref(words);
+    CU(dp.up(h16.data(), h16.size()));
+    launch_db_build_spiral(ddb.p, dp.p, (int)nu1, (int)nu2, (uint32_t)p_db, 0, total_n, 0); CHECK_LAUNCH();
+    launch_db_to_reference(dref.p, ddb.p, (size_t)1 << nu1, ((size_t)1 << nu2) * kN2, 0); CHECK_LAUNCH();
+    CU(dref.down(B, words));
+    return SB200_OK;
+}
+extern "C" int sb200_reorientCiphertexts(uint64_t *out, const uint64_t *inp, size_t dim0, size_t n1_padded) {
+    NEED_DEVICE();
+    if (n1_padded != 4) return fail(SB200_ERR_ARG, "reorientCiphertexts: n1_padded must be 4");
+    DBuf<uint32_t> din; DBuf<uint64_t> dout(dim0 * 2 * 4 * kN);
+    TRY(up_ntt(din, inp, dim0 * kN1 * 2));
+    launch_reorient_query(dout.p, din.p, dim0, 0); CHECK_LAUNCH();
+    CU(dout.down(out, dim0 * 2 * 4 * kN));
+    return SB200_OK;
+}
+extern "C" int sb200_multiplyQueryByDatabase(uint64_t *out, const uint64_t *reoriented, const uint64_t *database,
+                                             size_t dim0, size_t num_per) {
+    NEED_DEVICE();
+    const size_t qwords = dim0 * 2 * 4 * kN, dbwords = dim0 * num_per * 4 * kN, opolys = num_per * 6;
+    DBuf<uint64_t> dq(qwords), dref(dbwords), ddb(dbwords); DBuf<uint32_t> dout(opolys * PLW);
+    CU(dq.up(reoriented, qwords)); CU(dref.up(database, dbwords));
+    launch_db_from_reference(ddb.p, dref.p, dim0, num_per * kN2, 0, kN, 0); CHECK_LAUNCH();
+    launch_scan_spiral(dout.p, dq.p, ddb.p, dim0, num_per, 0); CHECK_LAUNCH();
+    return down_ntt(out, dout.p, opolys);
+}
+extern "C" int sb200_nttInvAndCrtLiftCiphertexts(uint64_t *cts_raw, const uint64_t *scratch, size_t num_per) {
+    return sb200_from_ntt(cts_raw, scratch, num_per * 6);
+}
+extern "C" int sb200_foldOneFurtherDimension(size_t cur_dim, size_t num_per, const uint64_t *q, const uint64_t *q_neg,
+                                             uint64_t *cts_raw, uint32_t t_gsw) {
+    NEED_DEVICE();
+    const int rm = 3 * 3 * (int)t_gsw;
+    const size_t stride = (size_t)rm * 2 * kN;              // reference stride between dimensions (n1*m2*crt_count*poly_len)
+    DBuf<uint64_t> dq((size_t)rm * kN), dqn((size_t)rm * kN), dcts(2 * num_per * 6 * kN);
+    DBuf<uint32_t> q_dev((size_t)rm * PLW), qn_dev((size_t)rm * PLW), scratch(fold_scratch_words(num_per, (int)t_gsw));
+    CU(dq.up(q + cur_dim * stride, (size_t)rm * kN)); CU(dqn.up(q_neg + cur_dim * stride, (size_t)rm * kN));
+    CU(dcts.up(cts_raw, 2 * num_per * 6 * kN));
+    launch_unreorient_q(q_dev.p, dq.p, rm, 0); launch_unreorient_q(qn_dev.p, dqn.p, rm, 0); CHECK_LAUNCH();
+    launch_fold_round(dcts.p, num_per, q_dev.p, qn_dev.p, (int)t_gsw, scratch.p, 0); CHECK_LAUNCH();
+    CU(dcts.down(cts_raw, num_per * 6 * kN));
+    return SB200_OK;
+}
+extern "C" int sb200_split_and_crt(uint64_t *out, const uint64_t *in_raw, size_t num_per, uint32_t t_gsw) {
+    NEED_DEVICE();
+    // the decomposition kernel of the fold, run on num_per ciphertexts; scratch layout == reference's (i, m, c, n, z)
+    DBuf<uint64_t> dcts(num_per * 6 * kN); DBuf<uint32_t> scratch(num_per * 3 * t_gsw * 2 * PLW);
+    CU(dcts.up(in_raw, num_per * 6 * kN));
+    launch_fold_decomp_only(scratch.p, dcts.p, num_per, (int)t_gsw, 0); CHECK_LAUNCH();
+    return down_ntt(out, scratch.p, num_per * 3 * t_gsw * 2);
+}
+
+extern "C" int sb200_expandImproved(uint64_t *cv, size_t g, uint32_t t_exp, const uint64_t *W_left, const uint64_t *W_right,
+                                    uint32_t t_exp_right, size_t max_bits_right, size_t stopround) {
+    NEED_DEVICE();
+    ExpandPlan plan{(int)g, (int)t_exp, (int)t_exp_right, (int)stopround, (int)max_bits_right};
+    const size_t ncts = (size_t)1 << g;
+    const size_t n_right = stopround > 0 ? stopround + 1 : g;
+    std::vector<int> list(expand_active_total(plan)), offs(g), cnt(g);
+    const int maxcnt = expand_build_lists(plan, list.data(), offs.data(), cnt.data());
+    const int tmax = plan.t_left > plan.t_right ? plan.t_left : plan.t_right;
+    DBuf<uint32_t> dcv, dWl, dWr, neg1(g * PLW), c1((size_t)maxcnt * PLW), ginv((size_t)maxcnt * tmax * PLW);
+    DBuf<uint64_t> c0((size_t)maxcnt * kN); DBuf<int> dlist(list.size());
+    TRY(up_ntt(dcv, cv, ncts * 2)); TRY(up_ntt(dWl, W_left, g * 2 * t_exp)); TRY(up_ntt(dWr, W_right, n_right * 2 * t_exp_right));
+    CU(dlist.up(list.data(), list.size()));
+    build_neg1(neg1.p, (int)g, 0);
+    launch_expand(dcv.p, plan, dWl.p, dWr.p, neg1.p, c0.p, c1.p, ginv.p, dlist.p, offs.data(), cnt.data(), 0); CHECK_LAUNCH();
+    return down_ntt(cv, dcv.p, ncts * 2);
+}
+extern "C" int sb200_scalToMat(uint64_t *out_reg, const uint64_t *cv, const uint64_t *W, uint32_t t_conv) {
+    NEED_DEVICE();
+    DBuf<uint32_t> dcv, dW, dout(6 * PLW), sntt((size_t)t_conv * PLW); DBuf<uint64_t> sraw(kN); DBuf<int> idx(2);
+    TRY(up_ntt(dcv, cv, 2)); TRY(up_ntt(dW, W, 3 * 2 * (size_t)t_conv));
+    const int h[2] = {0, 0};
+    CU(idx.up(h, 2));
+    launch_scal_to_mat_ntt(dout.p, dcv.p, idx.p, idx.p + 1, 1, dW.p, (int)t_conv, sraw.p, sntt.p, 0); CHECK_LAUNCH();
+    return down_ntt(out_reg, dout.p, 6);
+}
+extern "C" int sb200_regevToGSW(uint64_t *out, const uint64_t *cv_v, uint32_t t_conv, uint32_t t, const uint64_t *W, const uint64_t *V) {
+    NEED_DEVICE();
+    const int nbits = (int)t;
+    DBuf<uint32_t> dcv, dW, dV, dout((size_t)3 * 3 * t * PLW), sntt((size_t)2 * t_conv * nbits * PLW);
+    DBuf<uint64_t> sraw((size_t)2 * nbits * kN); DBuf<int> ct_idx(nbits), poly_idx(2 * nbits);
+    TRY(up_ntt(dcv, cv_v, (size_t)t * 2)); TRY(up_ntt(dW, W, 3 * 2 * (size_t)t_conv)); TRY(up_ntt(dV, V, 3 * 2 * (size_t)t_conv));
+    std::vector<int> hc(nbits), hp(2 * nbits);
+    for (int b = 0; b < nbits; b++) { hc[b] = b; hp[b] = 2 * b; hp[nbits + b] = 2 * b + 1; }
+    CU(ct_idx.up(hc.data(), nbits)); CU(poly_idx.up(hp.data(), 2 * nbits));
+    launch_regev_to_gsw(dout.p, nullptr, dcv.p, ct_idx.p, poly_idx.p, 1, (int)t, dW.p, dV.p, (int)t_conv, sraw.p, sntt.p, 0); CHECK_LAUNCH();
+    return down_ntt(out, dout.p, (size_t)3 * 3 * t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tier 3: resident server
+// ---------------------------------------------------------------------------------------------
+struct sb200_server {
+    sb200_params prm;
+    int device = 0, rank = 0, world = 1, log_world = 0;
+    size_t dim0 = 0, num_per = 0, local_num_per = 0;
+    size_t g = 0, stopround = 0;
+    ExpandPlan plan{};
+    std::vector<int> offs, cnt;
+    int maxcnt = 0, tmax = 0;
+    bool have_db = false, have_params = false;
+    // device memory
+    DBuf<uint64_t> db;                                  // scan layout shard
+    DBuf<uint32_t> W_left, W_right, W_conv, V_conv, neg1;
+    DBuf<uint64_t> q_stage;                             // uploaded query (ref-NTT)
+    DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, gsw_neg, scan_out, fold_scratch;
+    DBuf<uint64_t> c0, conv_raw, query, cts, resp, final_ct;
+    DBuf<int> lists, ct_idx_first, poly_idx_first, ct_idx_bits, poly_idx_bits;
+};
+
+static size_t ceil_log2(size_t x) { size_t g = 0; while (((size_t)1 << g) < x) g++; return g; }
+
+extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, int device, int rank, int world) {
+    if (!out || !prm) return fail(SB200_ERR_ARG, "server_create: null argument");
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(SB200_ERR_ARG, "server_create: world must be a power of two and 0 <= rank < world");
+    if (((size_t)1 << prm->nu2) < (size_t)world) return fail(SB200_ERR_ARG, "server_create: 2^nu2 < world");
+    if (prm->t_gsw == 0 || prm->t_conv == 0 || prm->t_exp == 0 || prm->t_exp_right == 0) return fail(SB200_ERR_ARG, "server_create: zero gadget length");
+    int rc = sb200_init(device);
+    if (rc) return rc;
+    sb200_server *s = new sb200_server();
+    s->prm = *prm; s->device = device; s->rank = rank; s->world = world; s->log_world = (int)ceil_log2((size_t)world);
+    s->dim0 = (size_t)1 << prm->nu1; s->num_per = (size_t)1 << prm->nu2; s->local_num_per = s->num_per / world;
+    // expansion shape exactly as runConversionImproved derives it (reference src/spiral.cpp:2076-2085, qe_rest == 0)
+    const size_t ell = prm->t_gsw, nbits = ell * prm->nu2;
+    s->g = ceil_log2(nbits + s->dim0);
+    s->stopround = ceil_log2(nbits);
+    if (nbits > s->dim0) s->stopround = 0;
+    s->plan = ExpandPlan{(int)s->g, (int)prm->t_exp, (int)prm->t_exp_right, (int)s->stopround, (int)nbits};
+    std::vector<int> list(expand_active_total(s->plan));
+    s->offs.resize(s->g); s->cnt.resize(s->g);
+    s->maxcnt = expand_build_lists(s->plan, list.data(), s->offs.data(), s->cnt.data());
+    s->tmax = s->plan.t_left > s->plan.t_right ? s->plan.t_left : s->plan.t_right;
+
+    const size_t ncts = (size_t)1 << s->g, m2 = 3 * ell, n_right = s->stopround > 0 ? s->stopround + 1 : s->g;
+    const size_t conv_cols = std::max(s->dim0, 2 * nbits);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc(n_right * 2 * prm->t_exp_right * PLW));
+    A(s->W_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->V_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
+    A(s->q_stage.alloc(2 * PLW)); A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW));
+    A(s->ginv.alloc((size_t)s->maxcnt * s->tmax * PLW)); A(s->c0.alloc((size_t)s->maxcnt * kN));
+    A(s->conv_raw.alloc(conv_cols * kN)); A(s->conv_ntt.alloc(conv_cols * prm->t_conv * PLW));
+    A(s->gsw.alloc(prm->nu2 * 3 * m2 * PLW)); A(s->gsw_neg.alloc(prm->nu2 * 3 * m2 * PLW));
+    A(s->query.alloc(s->dim0 * 2 * 4 * kN)); A(s->scan_out.alloc(s->local_num_per * 6 * PLW));
+    const size_t cts_n = std::max(s->local_num_per, (size_t)world);
+    A(s->cts.alloc(cts_n * 6 * kN)); A(s->final_ct.alloc(6 * kN)); A(s->resp.alloc(6 * kN));
+    const size_t fold_np = std::max(s->local_num_per / 2, (size_t)world / 2);
+    A(s->fold_scratch.alloc(fold_scratch_words(fold_np ? fold_np : 1, (int)ell)));
+    A(s->lists.alloc(list.size())); A(s->ct_idx_first.alloc(s->dim0)); A(s->poly_idx_first.alloc(s->dim0));
+    A(s->ct_idx_bits.alloc(nbits ? nbits : 1)); A(s->poly_idx_bits.alloc(nbits ? 2 * nbits : 1));
+    if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "server_create: device allocation failed: %s", cudaGetErrorString(e)); }
+    // index lists (reorderFromStopround, reference src/spiral.cpp:2027-2036)
+    std::vector<int> cf(s->dim0), pf(s->dim0), cb(nbits), pb(2 * nbits);
+    for (size_t j = 0; j < s->dim0; j++) { cf[j] = (int)(s->stopround ? 2 * j : j); pf[j] = 2 * cf[j]; }
+    for (size_t b = 0; b < nbits; b++) { cb[b] = (int)(s->stopround ? 2 * b + 1 : s->dim0 + b); pb[b] = 2 * cb[b]; pb[nbits + b] = 2 * cb[b] + 1; }
+    A(s->lists.up(list.data(), list.size())); A(s->ct_idx_first.up(cf.data(), cf.size())); A(s->poly_idx_first.up(pf.data(), pf.size()));
+    if (nbits) { A(s->ct_idx_bits.up(cb.data(), cb.size())); A(s->poly_idx_bits.up(pb.data(), pb.size())); }
+    build_neg1(s->neg1.p, (int)s->g, 0);
+    A(cudaDeviceSynchronize());
+    if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "server_create: setup failed: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return SB200_OK;
+}
+extern "C" void sb200_server_destroy(sb200_server *s) { delete s; }
+
+static int server_alloc_db(sb200_server *s) {
+    if (s->db.p) return SB200_OK;
+    CU(s->db.alloc(s->dim0 * s->local_num_per * 4 * kN));
+    return SB200_OK;
+}
+extern "C" int sb200_server_load_db_items(sb200_server *s, const uint16_t *pts, size_t item_begin, size_t item_count) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    CU(cudaSetDevice(s->device));
+    TRY(server_alloc_db(s));
+    const size_t total_local = s->dim0 * s->local_num_per;
+    if (item_begin + item_count > total_local) return fail(SB200_ERR_ARG, "load_db_items: range exceeds the shard (%zu items)", total_local);
+    const size_t chunk = 4096;                                           // items per staging buffer (64 MiB)
+    DBuf<uint16_t> stage(std::min(chunk, item_count ? item_count : 1) * 4 * kN);
+    uint32_t nu2_local = (uint32_t)ceil_log2(s->local_num_per);
+    for (size_t o = 0; o < item_count; o += chunk) {
+        const size_t n = std::min(chunk, item_count - o);
+        CU(stage.up(pts + o * 4 * kN, n * 4 * kN));
+        launch_db_build_spiral(s->db.p, stage.p, (int)s->prm.nu1, (int)nu2_local, (uint32_t)s->prm.p_db, item_begin + o, n, 0);
+        CHECK_LAUNCH();
+        CU(cudaDeviceSynchronize());
+    }
+    s->have_db = true;
+    return SB200_OK;
+}
+extern "C" int sb200_server_load_db_reference(sb200_server *s, const uint64_t *B) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    CU(cudaSetDevice(s->device));
+    TRY(server_alloc_db(s));
+    // per z-slice the reference holds num_per rows (ii) of n2*dim0*n0 words; the shard takes rows ii = rank (mod world)
+    const size_t row_words = kN2 * s->dim0 * kN0, zc = 16;
+    DBuf<uint64_t> stage(zc * s->local_num_per * row_words);
+    for (size_t z0 = 0; z0 < (size_t)kN; z0 += zc) {
+        if (s->world == 1) {
+            CU(stage.up(B + z0 * s->num_per * row_words, zc * s->num_per * row_words));
+        } else {
+            for (size_t z = 0; z < zc; z++)
+                CU(cudaMemcpy2D(stage.p + z * s->local_num_per * row_words, row_words * 8,
+                                B + ((z0 + z) * s->num_per + s->rank) * row_words, (size_t)s->world * row_words * 8,
+                                row_words * 8, s->local_num_per, cudaMemcpyHostToDevice));
+        }
+        launch_db_from_reference(s->db.p, stage.p, s->dim0, s->local_num_per * kN2, z0, zc, 0);
+        CHECK_LAUNCH();
+        CU(cudaDeviceSynchronize());
+    }
+    s->have_db = true;
+    return SB200_OK;
+}
+extern "C" uint64_t *sb200_server_db_ptr(sb200_server *s) { return s ? s->db.p : nullptr; }
+
+static int server_up_ntt(sb200_server *s, DBuf<uint32_t> &dst, const uint64_t *host, size_t npolys) {
+    (void)s;
+    const size_t chunk = 1024;
+    DBuf<uint64_t> tmp(std::min(chunk, npolys ? npolys : 1) * PLW);
+    for (size_t o = 0; o < npolys; o += chunk) {
+        const size_t n = std::min(chunk, npolys - o);
+        CU(tmp.up(host + o * PLW, n * PLW));
+        launch_ntt_u64_to_dev(dst.p + o * PLW, tmp.p, n, 0); CHECK_LAUNCH();
+        CU(cudaDeviceSynchronize());
+    }
+    return SB200_OK;
+}
+extern "C" int sb200_server_set_public_params(sb200_server *s, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
+                                              const uint64_t *W_conv, const uint64_t *V_conv) {
+    if (!s || !W_exp_left || !W_exp_right || !W_conv || !V_conv) return fail(SB200_ERR_ARG, "set_public_params: null argument");
+    CU(cudaSetDevice(s->device));
+    const size_t n_right = s->stopround > 0 ? s->stopround + 1 : s->g;
+    TRY(server_up_ntt(s, s->W_left, W_exp_left, s->g * 2 * s->prm.t_exp));
+    TRY(server_up_ntt(s, s->W_right, W_exp_right, n_right * 2 * s->prm.t_exp_right));
+    TRY(server_up_ntt(s, s->W_conv, W_conv, 3 * 2 * (size_t)s->prm.t_conv));
+    TRY(server_up_ntt(s, s->V_conv, V_conv, 3 * 2 * (size_t)s->prm.t_conv));
+    s->have_params = true;
+    return SB200_OK;
+}
+
+extern "C" int sb200_server_upload_query(sb200_server *s, const uint64_t *query_cv_host, void *stream) {
+    if (!s || !query_cv_host) return fail(SB200_ERR_ARG, "upload_query: null argument");
+    CU(cudaMemcpyAsync(s->q_stage.p, query_cv_host, 2 * PLW * sizeof(uint64_t), cudaMemcpyHostToDevice, S(stream)));
+    launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, S(stream)); CHECK_LAUNCH();
+    return SB200_OK;
+}
+extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (!s->have_params) return fail(SB200_ERR_STATE, "expand_and_convert: public parameters not set");
+    cudaStream_t st = S(stream);
+    launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
+                  s->offs.data(), s->cnt.data(), st);
+    launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
+                                  (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+    launch_regev_to_gsw(s->gsw.p, s->gsw_neg.p, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
+                        s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+extern "C" int sb200_server_first_dim(sb200_server *s, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (!s->have_db) return fail(SB200_ERR_STATE, "first_dim: database not loaded");
+    launch_scan_spiral(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, S(stream));
+    launch_from_ntt(s->cts.p, s->scan_out.p, s->local_num_per * 6, S(stream));
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+static void fold_rounds(sb200_server *s, uint64_t *cts, size_t count, size_t first_dim, cudaStream_t st) {
+    const size_t per = 3 * 3 * (size_t)s->prm.t_gsw * PLW;
+    size_t np = count, d = first_dim;
+    while (np >= 2) {
+        np /= 2;
+        launch_fold_round(cts, np, s->gsw.p + d * per, s->gsw_neg.p + d * per, (int)s->prm.t_gsw, s->fold_scratch.p, st);
+        d++;
+    }
+}
+extern "C" int sb200_server_fold_local(sb200_server *s, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    fold_rounds(s, s->cts.p, s->local_num_per, 0, S(stream));
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+extern "C" uint64_t *sb200_server_partial_ct(sb200_server *s) { return s ? s->cts.p : nullptr; }
+extern "C" uint64_t *sb200_server_first_dim_cts(sb200_server *s) { return s ? s->cts.p : nullptr; }
+extern "C" int sb200_server_fold_tail(sb200_server *s, uint64_t *gathered, uint64_t *resp_dev, void *stream) {
+    if (!s || !gathered || !resp_dev) return fail(SB200_ERR_ARG, "fold_tail: null argument");
+    cudaStream_t st = S(stream);
+    fold_rounds(s, gathered, (size_t)s->world, s->prm.nu2 - s->log_world, st);
+    // modulus switch (check_final, reference src/spiral.cpp:1441-1447): row 0 -> arb_qprime, rows 1.. -> 4*p_db
+    launch_rescale(resp_dev, gathered, 2 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
+    launch_rescale(resp_dev + 2 * kN, gathered + 2 * kN, 4 * (size_t)kN, kQ, 4 * s->prm.p_db, st);
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+extern "C" int sb200_server_download(sb200_server *s, uint64_t *dst, const uint64_t *src, size_t words, void *stream) {
+    (void)s;
+    CU(cudaMemcpyAsync(dst, src, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, S(stream)));
+    CU(cudaStreamSynchronize(S(stream)));
+    return SB200_OK;
+}
+extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer: single-shard call on a sharded server (use the staged API)");
+    TRY(sb200_server_upload_query(s, query_cv_host, stream));
+    TRY(sb200_server_expand_and_convert(s, stream));
+    TRY(sb200_server_first_dim(s, stream));
+    TRY(sb200_server_fold_local(s, stream));
+    TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
+    return sb200_server_download(s, total_resp_host, s->resp.p, 6 * kN, stream);
+}
+extern "C" size_t sb200_server_query_bytes(const sb200_server *) { return 2 * PLW * sizeof(uint64_t); }
+extern "C" size_t sb200_server_response_bytes(const sb200_server *) { return 6 * (size_t)kN * sizeof(uint64_t); }

@@ -1,0 +1,82 @@
+// kernels.cuh - launch wrappers for every CUDA kernel of the Spiral server path.
+// Device data formats:
+//   NTT form ("dev-NTT") : uint32_t [poly][2][2048]  plane 0 = residues mod p, plane 1 = mod b
+//                          (the reference's [n][z] layout narrowed to the 28-bit residues)
+//   raw form             : uint64_t [poly][2048] in [0, Q]
+//   packed ("PB64")      : uint64_t, low 32 bits = residue mod p, high 32 bits = residue mod b
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sb200 {
+
+void count_launch(int n = 1);        // our own kernel launches since load (sb200_launch_count)
+uint64_t launch_count();
+int init_tables();   // builds twiddle tables on the current device (idempotent, per device)
+
+// ---- format conversion at the boundary (reference u64-per-residue NTT layout <-> dev-NTT)
+void launch_ntt_u64_to_dev(uint32_t *out, const uint64_t *in, size_t npolys, cudaStream_t s);
+void launch_ntt_dev_to_u64(uint64_t *out, const uint32_t *in, size_t npolys, cudaStream_t s);
+
+// ---- MatPoly primitives (reference src/poly.cpp) on batches of polynomials
+void launch_to_ntt(uint32_t *out, const uint64_t *raw, size_t npolys, cudaStream_t s);          // to_ntt / to_ntt_no_reduce
+void launch_from_ntt(uint64_t *raw, const uint32_t *in, size_t npolys, cudaStream_t s);        // from_ntt (INTT + CRT lift)
+void launch_matmul(uint32_t *out, const uint32_t *a, const uint32_t *b, int rs, int ms, int cs, cudaStream_t s);
+void launch_add(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t npolys, cudaStream_t s);
+void launch_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t t, cudaStream_t s);
+// raw (rdim x cols) -> NTT'd digits (mx x cols), row j + k*rdim  (gadget_invert + to_ntt)
+void launch_gadget_ntt(uint32_t *out, const uint64_t *raw, int mx, int rdim, int cols, cudaStream_t s);
+void launch_gadget_raw(uint64_t *out, const uint64_t *raw, int mx, int rdim, int cols, cudaStream_t s);
+void launch_rescale(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod, cudaStream_t s);
+
+// ---- database preprocessing
+// plaintext items (values < p_db, one u16 per coefficient, item-major [item][n0*n2][2048]) ->
+// scan layout DB'[z][j][ic][m] PB64 with ic = ii*n2 + c, item = j*num_per + ii.
+void launch_db_build_spiral(uint64_t *db, const uint16_t *pts, int nu1, int nu2, uint32_t p_db,
+                            size_t item_begin, size_t item_count, cudaStream_t s);
+// reference layout B[z][ii][c][j][m] (src/spiral.cpp:1139-1153) -> scan layout, rows_z z-slices at a time
+void launch_db_from_reference(uint64_t *db, const uint64_t *B_ref, size_t dim0, size_t ic, size_t z_begin,
+                              size_t z_count, cudaStream_t s);
+
+void launch_db_to_reference(uint64_t *B_ref, const uint64_t *db, size_t dim0, size_t ic, cudaStream_t s);
+void launch_unreorient_q(uint32_t *out, const uint64_t *q_reor, int rm_count, cudaStream_t s);
+
+// ---- first dimension
+// query: [z][j][m][4] PB64 (reference reorientCiphertexts layout);  db: scan layout;
+// out: dev-NTT [i][r][c] (num_per x 3 x 2 polys)
+void launch_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, cudaStream_t s);
+void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s);
+
+// ---- folding (Spiral): cts raw [2*num_per][3][2][2048] -> first num_per folded in place.
+// q_dev / qneg_dev: dev-NTT (3 x 3*t_gsw) GSW ciphertext of THIS round.
+void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,
+                       int t_gsw, uint32_t *scratch, cudaStream_t s);
+size_t fold_scratch_words(size_t num_per_half, int t_gsw);
+void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t count, int t_gsw, cudaStream_t s);
+
+// ---- expansion (reference expandImproved / coefficientExpansion)
+struct ExpandPlan { int g, t_left, t_right, stopround, max_bits_right; };
+size_t expand_active_total(const ExpandPlan &p);
+int expand_build_lists(const ExpandPlan &p, int *list, int *offs, int *cnt);   // host arrays; returns max count
+// cv: dev-NTT [2^g][2]; W_left: [g][2][t_left]; W_right: [g or stopround+1][2][t_right]; neg1: [g] polys
+// c0_raw: maxcnt*2048 u64; c1_ntt: maxcnt polys; ginv: maxcnt*max(t) polys; list_dev: device copy of list
+void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
+                   const uint32_t *neg1, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s);
+void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s);   // neg1[r] = NTT(-x^(N-2^r)), r < count
+
+// ---- conversion
+void launch_from_ntt_indexed(uint64_t *raw, const uint32_t *in, const int *poly_idx, size_t count, cudaStream_t s);
+// ct_idx[j] = ciphertext index inside cv, poly_idx[j] = 2*ct_idx[j] (row-0 polynomial)
+void launch_scal_to_mat_reoriented(uint64_t *query_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t dim0,
+                                   const uint32_t *W, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s);
+void launch_scal_to_mat_ntt(uint32_t *out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t count,
+                            const uint32_t *W, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s);
+// poly_idx: 2*nbits entries (row-0 polys of the nu2*t_gsw bit ciphertexts, then their row-1 polys)
+void launch_regev_to_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx,
+                         int nu2, int t_gsw, const uint32_t *W, const uint32_t *V, int t_conv,
+                         uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s);
+void launch_gsw_negate(uint32_t *neg, const uint32_t *gsw, int count, int ell, int rows, cudaStream_t s);
+
+}  // namespace sb200

@@ -1,0 +1,393 @@
+// query_kernels.cu - database-independent part of query answering: coefficient expansion of the
+// packed query, ScalToMat / RegevToGSW conversion and GSW negation, all on the device so that
+// only the single query ciphertext crosses PCIe per query.
+//
+// Reference functions replaced:
+//   expandImproved / coefficientExpansion   src/spiral.cpp:1664-1743, src/testing.cpp:40-105
+//   scalToMat (+special_distribute)         src/spiral.cpp:1834-1885
+//   regevToGSW                              src/spiral.cpp:1985-2025
+//   GSW negation, cpu_crt_to_ucompressed_and_ntt   src/spiral.cpp:2361-2378, :597-609
+//   regevToSimpleGsw, GSW negation (Pack)   src/testing.cpp:108-140, :1027-1032
+#include "kernels.cuh"
+#include "ntt.cuh"
+
+namespace sb200 {
+
+__device__ __forceinline__ uint64_t pack_pb2(uint32_t p, uint32_t b) { return (uint64_t)p | ((uint64_t)b << 32); }
+
+// ============================================================================================
+// Expansion, one round = three kernels over the round's ACTIVE ciphertexts (host-built list):
+//   k_expand_prep   : (slot,row) cv[i] (or x^(-2^r) * cv[i - 2^r], stored) -> INTT -> CRT ->
+//                     automorph (negation as Q - a, 0 -> Q kept) -> row 0: raw to c0_raw[slot]
+//                                                                  row 1: NTT to c1_ntt[slot]
+//   k_expand_digits : (slot,k)   digit k of c0_raw[slot] -> NTT -> ginv[slot][k]
+//   k_expand_accum  : cv[i][row] += sum_k W[row][k] * ginv[slot][k] + row * c1_ntt[slot]
+// ============================================================================================
+__global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restrict__ cv, const int *__restrict__ active, int num_in,
+                                                             const uint32_t *__restrict__ neg1, uint32_t tpow,
+                                                             uint64_t *__restrict__ c0_raw, uint32_t *__restrict__ c1_ntt) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    __shared__ __align__(16) uint32_t au[2][kN];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const int slot = blockIdx.x, row = blockIdx.y, i = active[slot];
+    uint32_t v[16];
+    if (i < num_in) {
+        load_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
+    } else {
+        uint32_t a[16], w[16];
+        load_ntt_regs(a, cv + (((size_t)(i - num_in) * 2 + row) * 2 + n) * kN, lt);
+        load_ntt_regs(w, neg1 + n * kN, lt);
+#pragma unroll
+        for (int e = 0; e < 16; e++) v[e] = mulmod(a[e], w[e], n);
+        store_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
+    }
+    ntt_inverse_plane(v, sm[n], lt, n);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int z = threadIdx.x + 256 * k;
+        uint64_t val = crt_compose(sm[0][z], sm[1][z]);
+        const uint32_t it = (uint32_t)z * tpow;
+        const int rem = (int)(it & (kN - 1));
+        if ((it >> kLogN) & 1) val = kQ - val;                 // 0 -> Q on purpose (reference src/poly.cpp:256)
+        if (row == 0) {
+            c0_raw[(size_t)slot * kN + rem] = val;
+        } else {
+            au[0][rem] = raw_to_res(val, 0);
+            au[1][rem] = raw_to_res(val, 1);
+        }
+    }
+    if (row == 1) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = au[n][nat_pos(lt, k)];
+        ntt_forward_plane(v, sm[n], lt, n);
+        store_ntt_regs(v, c1_ntt + ((size_t)slot * 2 + n) * kN, lt);
+    }
+}
+
+__global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restrict__ ginv, const uint64_t *__restrict__ c0_raw,
+                                                               const int *__restrict__ active, int t_left, int t_right, int tmax) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const int slot = blockIdx.x, k = blockIdx.y, i = active[slot];
+    const int gd = (i & 1) ? t_right : t_left;
+    if (k >= gd) return;
+    const uint32_t bits_per = get_bits_per(gd);
+    const uint64_t mask = (1ull << bits_per) - 1;
+    const uint64_t *src = c0_raw + (size_t)slot * kN;
+    uint32_t v[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const uint64_t d = gadget_digit(__ldg(src + nat_pos(lt, e)), k, bits_per, mask);
+        v[e] = bits_per >= 28 ? raw_to_res(d, n) : (uint32_t)d;
+    }
+    ntt_forward_plane(v, sm[n], lt, n);
+    store_ntt_regs(v, ginv + (((size_t)slot * tmax + k) * 2 + n) * kN, lt);
+}
+
+__global__ void k_expand_accum(uint32_t *__restrict__ cv, const int *__restrict__ active, const uint32_t *__restrict__ ginv,
+                               const uint32_t *__restrict__ c1_ntt, const uint32_t *__restrict__ W_left,
+                               const uint32_t *__restrict__ W_right, int t_left, int t_right, int tmax) {
+    // grid (slot, row*4 + quarter); 256 threads x uint4
+    const int slot = blockIdx.x, row = blockIdx.y >> 2, quarter = blockIdx.y & 3, i = active[slot];
+    const int w4 = quarter * 256 + threadIdx.x, n = w4 >= 512;
+    const int gd = (i & 1) ? t_right : t_left;
+    const uint32_t *W = ((i & 1) ? W_right : W_left) + (size_t)row * gd * 2 * kN;
+    uint64_t acc[4] = {0, 0, 0, 0};
+    for (int k = 0; k < gd; k++) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(W + (size_t)k * 2 * kN) + w4);
+        const uint4 y = __ldg(reinterpret_cast<const uint4 *>(ginv + ((size_t)slot * tmax + k) * 2 * kN) + w4);
+        acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
+        acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(cv + ((size_t)i * 2 + row) * 2 * kN) + w4;
+    const uint4 cur = *dst;
+    uint4 add = make_uint4(0, 0, 0, 0);
+    if (row == 1) add = __ldg(reinterpret_cast<const uint4 *>(c1_ntt + (size_t)slot * 2 * kN) + w4);
+    uint4 o;
+    o.x = reduce_u64(acc[0] + cur.x + add.x, n); o.y = reduce_u64(acc[1] + cur.y + add.y, n);
+    o.z = reduce_u64(acc[2] + cur.z + add.z, n); o.w = reduce_u64(acc[3] + cur.w + add.w, n);
+    *dst = o;
+}
+
+// neg1[r] = NTT(invert(x^(N - 2^r))) = NTT(-x^(N-2^r))   (reference src/spiral.cpp:184-192)
+__global__ void __launch_bounds__(kNttThreads) k_build_neg1(uint32_t *__restrict__ neg1) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    const int n = plane_of_thread(), lt = lane_in_plane(), r = blockIdx.x;
+    const uint32_t q = modulus(n);
+    const int idx = kN - (1 << r);
+    uint32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = (nat_pos(lt, k) == idx) ? q - 1 : 0;
+    ntt_forward_plane(v, sm[n], lt, n);
+    store_ntt_regs(v, neg1 + ((size_t)r * 2 + n) * kN, lt);
+}
+void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s) {
+    if (count) { count_launch(); k_build_neg1<<<count, kNttThreads, 0, s>>>(neg1_dev); }
+}
+
+// host side: per-round active lists, exactly the reference's skip rules (src/spiral.cpp:1701-1702)
+static int build_active(int *dst, int r, int stopround, int max_bits_right) {
+    const int num_out = 2 << r;
+    int cnt = 0;
+    for (int i = 0; i < num_out; i++) {
+        if (stopround > 0 && r > stopround && (i % 2) == 1) continue;
+        if (stopround > 0 && r == stopround && (i % 2) == 1 && i / 2 > max_bits_right) continue;
+        dst[cnt++] = i;
+    }
+    return cnt;
+}
+size_t expand_active_total(const ExpandPlan &p) {
+    size_t total = 0;
+    for (int r = 0; r < p.g; r++) total += (size_t)2 << r;
+    return total;
+}
+// fills host arrays: list (concatenated), offs[r], cnt[r]; returns the max count
+int expand_build_lists(const ExpandPlan &p, int *list, int *offs, int *cnt) {
+    int o = 0, mx = 0;
+    for (int r = 0; r < p.g; r++) {
+        offs[r] = o;
+        cnt[r] = build_active(list + o, r, p.stopround, p.max_bits_right);
+        if (cnt[r] > mx) mx = cnt[r];
+        o += cnt[r];
+    }
+    return mx;
+}
+
+void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
+                   const uint32_t *neg1, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s) {
+    const int tmax = p.t_left > p.t_right ? p.t_left : p.t_right;
+    for (int r = 0; r < p.g; r++) {
+        if (!cnt[r]) continue;
+        const int *act = list_dev + offs[r];
+        const uint32_t tpow = (uint32_t)(kN >> r) + 1;
+        const uint32_t *Wl = W_left + (size_t)r * 2 * p.t_left * 2 * kN;
+        const uint32_t *Wr = W_right + (size_t)r * 2 * p.t_right * 2 * kN;
+        // digits needed this round: t_right only if some odd ciphertext is active
+        const bool any_odd = !(p.stopround > 0 && r > p.stopround);
+        const int ty = any_odd ? tmax : p.t_left;
+        count_launch(); k_expand_prep<<<dim3(cnt[r], 2), kNttThreads, 0, s>>>(cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, c0_raw, c1_ntt);
+        count_launch(); k_expand_digits<<<dim3(cnt[r], ty), kNttThreads, 0, s>>>(ginv, c0_raw, act, p.t_left, p.t_right, tmax);
+        count_launch(); k_expand_accum<<<dim3(cnt[r], 8), 256, 0, s>>>(cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, tmax);
+    }
+}
+
+// ============================================================================================
+// Conversion.  Shared front end: INTT+CRT of selected polynomials, then NTT'd gadget digits.
+// ============================================================================================
+// raw[slot] = from_ntt(poly src[poly_idx[slot]])
+__global__ void __launch_bounds__(kNttThreads) k_from_ntt_indexed(uint64_t *__restrict__ raw, const uint32_t *__restrict__ in,
+                                                                  const int *__restrict__ poly_idx) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    uint32_t v[16];
+    load_ntt_regs(v, in + ((size_t)poly_idx[blockIdx.x] * 2 + n) * kN, lt);
+    ntt_inverse_plane(v, sm[n], lt, n);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
+    __syncthreads();
+    uint64_t *dst = raw + (size_t)blockIdx.x * kN;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int z = threadIdx.x + 256 * k;
+        dst[z] = crt_compose(sm[0][z], sm[1][z]);
+    }
+}
+void launch_from_ntt_indexed(uint64_t *raw, const uint32_t *in, const int *poly_idx, size_t count, cudaStream_t s) {
+    if (count) { count_launch(); k_from_ntt_indexed<<<(unsigned)count, kNttThreads, 0, s>>>(raw, in, poly_idx); }
+}
+
+// scalToMat for dim0 ciphertexts, written straight into the scan's query layout
+// query[z][j][m=c][r] (reorientCiphertexts fused):   out[r][c] = sum_k W[r][2k+c]*ginv[k][j] + [r == c+1] cv1
+// ginv: [t_conv][dim0] polys ; cv row 1 taken from cv[ct_idx[j]]
+__global__ void k_scal_to_mat_accum(uint64_t *__restrict__ query, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
+                                    const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int t_conv, int dim0) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (j, z), z fastest
+    if (idx >= (size_t)dim0 * kN) return;
+    const int z = (int)(idx % kN), j = (int)(idx / kN);
+    uint64_t acc[3][2][2];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) acc[r][c][0] = acc[r][c][1] = 0;
+    const int wc = 2 * t_conv;
+    for (int k = 0; k < t_conv; k++) {
+        const uint32_t *g = ginv + ((size_t)k * dim0 + j) * 2 * kN;
+        const uint32_t gp = g[z], gb = g[kN + z];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint32_t *w = W + ((size_t)r * wc + 2 * k + c) * 2 * kN;
+                acc[r][c][0] += (uint64_t)w[z] * gp;
+                acc[r][c][1] += (uint64_t)w[kN + z] * gb;
+            }
+        if ((k & 127) == 127) {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) { acc[r][c][0] = reduce_u64(acc[r][c][0], 0); acc[r][c][1] = reduce_u64(acc[r][c][1], 1); }
+        }
+    }
+    const uint32_t *cv1 = cv + ((size_t)ct_idx[j] * 2 + 1) * 2 * kN;
+    const uint32_t c1p = cv1[z], c1b = cv1[kN + z];
+    acc[1][0][0] += c1p; acc[1][0][1] += c1b;     // place(cv_1, 1, 0)
+    acc[2][1][0] += c1p; acc[2][1][1] += c1b;     // place(cv_1, 2, 1)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        uint64_t w[4];
+#pragma unroll
+        for (int r = 0; r < 3; r++) w[r] = pack_pb2(reduce_u64(acc[r][c][0], 0), reduce_u64(acc[r][c][1], 1));
+        w[3] = 0;
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(query + (((size_t)z * dim0 + j) * 2 + c) * 4);
+        dst[0] = make_ulonglong2(w[0], w[1]);
+        dst[1] = make_ulonglong2(w[2], w[3]);
+    }
+}
+// same product but emitted as dev-NTT MatPoly (3 x 2) per ciphertext - the reference's scalToMat output
+__global__ void k_scal_to_mat_ntt(uint32_t *__restrict__ out, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
+                                  const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int t_conv, int count) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (j, n, z)
+    if (idx >= (size_t)count * 2 * kN) return;
+    const int nz = (int)(idx % (2 * kN)), j = (int)(idx / (2 * kN)), n = nz >= kN;
+    const int wc = 2 * t_conv;
+    uint64_t acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int k = 0; k < t_conv; k++) {
+        const uint32_t g = ginv[((size_t)k * count + j) * 2 * kN + nz];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) acc[r][c] += (uint64_t)W[((size_t)r * wc + 2 * k + c) * 2 * kN + nz] * g;
+        if ((k & 127) == 127) {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) acc[r][c] = reduce_u64(acc[r][c], n);
+        }
+    }
+    const uint32_t c1 = cv[((size_t)ct_idx[j] * 2 + 1) * 2 * kN + nz];
+    acc[1][0] += c1; acc[2][1] += c1;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) out[(((size_t)j * 3 + r) * 2 + c) * 2 * kN + nz] = reduce_u64(acc[r][c], n);
+}
+
+// regevToGSW accumulate: for GSW ciphertext d (stored at slot dslot = nu2-1-d) and digit index jj < ell
+//   col 3jj     = sum_k V[r][k]*g0[k] + V[r][t_conv+k]*g1[k]
+//   col 3jj+1+c = sum_k W[r][2k+c]*g0[k] + [r == c+1] cv1
+// g0/g1: NTT'd digits of rows 0/1 of cv (bit index b = d*ell + jj): ginv[row][k][b]
+__global__ void k_regev_to_gsw_accum(uint32_t *__restrict__ gsw, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
+                                     const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, const uint32_t *__restrict__ V,
+                                     int t_conv, int ell, int nu2) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b, n, z)
+    const int nbits = ell * nu2;
+    if (idx >= (size_t)nbits * 2 * kN) return;
+    const int nz = (int)(idx % (2 * kN)), b = (int)(idx / (2 * kN)), n = nz >= kN;
+    const int d = b / ell, jj = b % ell, wc = 2 * t_conv, m2 = 3 * ell;
+    uint64_t s2m[3][2] = {{0, 0}, {0, 0}, {0, 0}}, pr[3] = {0, 0, 0};
+    for (int k = 0; k < t_conv; k++) {
+        const uint32_t g0 = ginv[(((size_t)0 * t_conv + k) * nbits + b) * 2 * kN + nz];
+        const uint32_t g1 = ginv[(((size_t)1 * t_conv + k) * nbits + b) * 2 * kN + nz];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            pr[r] += (uint64_t)V[((size_t)r * wc + k) * 2 * kN + nz] * g0 + (uint64_t)V[((size_t)r * wc + t_conv + k) * 2 * kN + nz] * g1;
+#pragma unroll
+            for (int c = 0; c < 2; c++) s2m[r][c] += (uint64_t)W[((size_t)r * wc + 2 * k + c) * 2 * kN + nz] * g0;
+        }
+        if ((k & 63) == 63) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                pr[r] = reduce_u64(pr[r], n);
+#pragma unroll
+                for (int c = 0; c < 2; c++) s2m[r][c] = reduce_u64(s2m[r][c], n);
+            }
+        }
+    }
+    const uint32_t c1 = cv[((size_t)ct_idx[b] * 2 + 1) * 2 * kN + nz];
+    s2m[1][0] += c1; s2m[2][1] += c1;
+    uint32_t *o = gsw + (size_t)(nu2 - 1 - d) * 3 * m2 * 2 * kN;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        o[((size_t)r * m2 + 3 * jj) * 2 * kN + nz] = reduce_u64(pr[r], n);
+        o[((size_t)r * m2 + 3 * jj + 1) * 2 * kN + nz] = reduce_u64(s2m[r][0], n);
+        o[((size_t)r * m2 + 3 * jj + 2) * 2 * kN + nz] = reduce_u64(s2m[r][1], n);
+    }
+}
+
+// GSW negation: Qneg = NTT(G2 - from_ntt(Q))  per polynomial (d, r, m); G2 = buildGadget(n1, m2)
+// (reference src/spiral.cpp:2361-2378; `long` subtraction, +Q when negative)
+__global__ void __launch_bounds__(kNttThreads) k_gsw_negate(uint32_t *__restrict__ neg, const uint32_t *__restrict__ gsw, int ell, int rows) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    __shared__ __align__(16) uint32_t au[2][kN];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const int m2 = rows * ell;
+    const int poly = blockIdx.x, rm = poly % (rows * m2), r = rm / m2, m = rm % m2;
+    uint32_t v[16];
+    load_ntt_regs(v, gsw + ((size_t)poly * 2 + n) * kN, lt);
+    ntt_inverse_plane(v, sm[n], lt, n);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
+    __syncthreads();
+    const uint32_t bits_per = get_bits_per(ell);
+    const int kk = m / rows;
+    uint64_t gad = 0;                                              // buildGadget: G[r][r + kk*rows] = 2^(bits_per*kk)
+    if ((m % rows) == r && (uint64_t)bits_per * kk < 64) gad = 1ull << (bits_per * kk);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int z = threadIdx.x + 256 * k;
+        const uint64_t val = crt_compose(sm[0][z], sm[1][z]);
+        long long d = (long long)(z == 0 ? gad : 0) - (long long)val;
+        if (d < 0) d += (long long)kQ;
+        au[0][z] = raw_to_res((uint64_t)d, 0);
+        au[1][z] = raw_to_res((uint64_t)d, 1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = au[n][nat_pos(lt, k)];
+    ntt_forward_plane(v, sm[n], lt, n);
+    store_ntt_regs(v, neg + ((size_t)poly * 2 + n) * kN, lt);
+}
+void launch_gsw_negate(uint32_t *neg, const uint32_t *gsw, int count, int ell, int rows, cudaStream_t s) {
+    const int polys = count * rows * rows * ell;
+    if (polys) { count_launch(); k_gsw_negate<<<polys, kNttThreads, 0, s>>>(neg, gsw, ell, rows); }
+}
+
+void launch_scal_to_mat_reoriented(uint64_t *query_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t dim0,
+                                   const uint32_t *W, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
+    launch_from_ntt_indexed(scratch_raw, cv, poly_idx, dim0, s);
+    launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, (int)dim0, s);
+    const size_t n = dim0 * kN;
+    count_launch(); k_scal_to_mat_accum<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
+}
+void launch_scal_to_mat_ntt(uint32_t *out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t count,
+                            const uint32_t *W, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
+    launch_from_ntt_indexed(scratch_raw, cv, poly_idx, count, s);
+    launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, (int)count, s);
+    const size_t n = count * 2 * kN;
+    count_launch(); k_scal_to_mat_ntt<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, cv, ct_idx, scratch_ntt, W, t_conv, (int)count);
+}
+// poly_idx: 2*nbits entries - first nbits = row-0 polys of the bit ciphertexts, next nbits = row-1 polys
+void launch_regev_to_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx,
+                         int nu2, int t_gsw, const uint32_t *W, const uint32_t *V, int t_conv,
+                         uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
+    const int nbits = nu2 * t_gsw;
+    if (!nbits) return;
+    launch_from_ntt_indexed(scratch_raw, cv, poly_idx, 2 * (size_t)nbits, s);
+    // raw viewed as (rdim = 1) x (2*nbits) -> digits [k][2*nbits]; reinterpret as [row][k][nbits] needs row-major
+    // split, so run the two rows separately: ginv[row][k][b]
+    launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, nbits, s);
+    launch_gadget_ntt(scratch_ntt + (size_t)t_conv * nbits * 2 * kN, scratch_raw + (size_t)nbits * kN, t_conv, 1, nbits, s);
+    const size_t n = (size_t)nbits * 2 * kN;
+    count_launch(); k_regev_to_gsw_accum<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gsw_out, cv, ct_idx, scratch_ntt, W, V, t_conv, t_gsw, nu2);
+    if (gsw_neg_out) launch_gsw_negate(gsw_neg_out, gsw_out, nu2, t_gsw, 3, s);
+}
+
+}  // namespace sb200

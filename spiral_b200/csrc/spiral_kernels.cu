@@ -1,0 +1,344 @@
+// spiral_kernels.cu - database preprocessing, first-dimension scan, folding, query expansion and
+// Regev->GSW conversion kernels of the Spiral (matrix-Regev, n = 2) server path.
+//
+// Reference functions replaced (paths relative to the reference tree):
+//   load_db                       src/spiral.cpp:1028-1172   -> k_db_build_spiral / k_db_from_reference
+//   reorientCiphertexts           src/spiral.cpp:410-433     -> k_reorient_query (and fused in k_scal_to_mat_accum)
+//   multiplyQueryByDatabase       src/spiral.cpp:628-999     -> k_scan_spiral
+//   nttInvAndCrtLiftCiphertexts   src/spiral.cpp:437-453     -> k_from_ntt (ntt_kernels.cu)
+//   foldOneFurtherDimension       src/spiral.cpp:1349-1410   -> k_fold_decomp_ntt + k_fold_mac_intt
+//   expandImproved                src/spiral.cpp:1664-1743   -> k_expand_prep + k_expand_digits + k_expand_accum
+//   scalToMat / regevToGSW        src/spiral.cpp:1850-2025   -> k_from_ntt_indexed + k_gadget_ntt + *_accum
+//   GSW negation                  src/spiral.cpp:2361-2378   -> k_gsw_negate
+#include "kernels.cuh"
+#include "ntt.cuh"
+
+namespace sb200 {
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack_pb(uint32_t p, uint32_t b) { return (uint64_t)p | ((uint64_t)b << 32); }
+
+// ============================================================================================
+// Database preprocessing.
+// Scan layout: DB'[z][j][ic][m] PB64, ic = ii*n2 + c, database item i = j*num_per + ii, plaintext
+// entry (m, c).  One (z, j) row is IC*16 bytes; consecutive threads of the scan read consecutive
+// 16-byte (m=0, m=1) pairs -> fully coalesced 128-bit loads.
+// ============================================================================================
+constexpr int kDbStashWords = 4 * 2 * kN;   // 4 polys x 2 planes
+
+__global__ void __launch_bounds__(kNttThreads) k_db_build_spiral(uint64_t *__restrict__ db, const uint16_t *__restrict__ pts,
+                                                                 int nu1, int nu2, uint32_t p_db, size_t item_begin) {
+    extern __shared__ __align__(16) uint32_t dyn[];
+    uint32_t(*sm)[kPlaneWords] = reinterpret_cast<uint32_t(*)[kPlaneWords]>(dyn);
+    uint32_t *stash = dyn + 2 * kPlaneWords;                       // [poly][n][z]
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const uint32_t q = modulus(n);
+    const size_t item = item_begin + blockIdx.x;
+    const size_t num_per = (size_t)1 << nu2, dim0 = (size_t)1 << nu1;
+    const uint16_t *src = pts + (size_t)blockIdx.x * 4 * kN;
+    for (int poly = 0; poly < 4; poly++) {
+        uint32_t v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            // centre-lift: v >= p_db/2 -> v - p_db (+Q)   (reference src/spiral.cpp:1116-1127); Q = 0 mod p, b
+            uint32_t c = src[poly * kN + nat_pos(lt, k)];
+            v[k] = (c >= p_db / 2) ? (q - ((p_db - c) % q)) % q : c % q;
+        }
+        ntt_forward_plane(v, sm[n], lt, n);
+        store_ntt_regs(v, stash + (poly * 2 + n) * kN, lt);
+    }
+    __syncthreads();
+    const size_t ii = item % num_per, j = item / num_per, IC = num_per * 2;
+    for (int z = threadIdx.x; z < kN; z += kNttThreads) {
+        // 32 contiguous bytes: (c=0: m=0, m=1), (c=1: m=0, m=1); poly index = m*n2 + c
+        ulonglong2 c0, c1;
+        c0.x = pack_pb(stash[(0 * 2 + 0) * kN + z], stash[(0 * 2 + 1) * kN + z]);   // m=0,c=0
+        c0.y = pack_pb(stash[(2 * 2 + 0) * kN + z], stash[(2 * 2 + 1) * kN + z]);   // m=1,c=0
+        c1.x = pack_pb(stash[(1 * 2 + 0) * kN + z], stash[(1 * 2 + 1) * kN + z]);   // m=0,c=1
+        c1.y = pack_pb(stash[(3 * 2 + 0) * kN + z], stash[(3 * 2 + 1) * kN + z]);   // m=1,c=1
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(db + (((size_t)z * dim0 + j) * IC + ii * 2) * 2);
+        dst[0] = c0;
+        dst[1] = c1;
+    }
+}
+void launch_db_build_spiral(uint64_t *db, const uint16_t *pts, int nu1, int nu2, uint32_t p_db,
+                            size_t item_begin, size_t item_count, cudaStream_t s) {
+    const size_t smem = (2 * kPlaneWords + kDbStashWords) * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_db_build_spiral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (item_count) { count_launch(); k_db_build_spiral<<<(unsigned)item_count, kNttThreads, smem, s>>>(db, pts, nu1, nu2, p_db, item_begin); }
+}
+
+// reference layout B[z][ii][c][j][m] -> DB'[z][j][ic][m]: per z a (IC x dim0) -> (dim0 x IC) transpose of 16-byte elements
+__global__ void k_db_from_reference(uint64_t *__restrict__ db, const uint64_t *__restrict__ Bref, size_t dim0, size_t IC, size_t z_begin) {
+    // per z: src is (IC rows x dim0 cols) of 16-byte elements, dst is (dim0 x IC)
+    __shared__ ulonglong2 tile[32][33];
+    const size_t z = blockIdx.z;      // z relative to the chunk for Bref, absolute z_begin + z for db
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(Bref) + z * IC * dim0;
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(db) + (z_begin + z) * IC * dim0;
+    const size_t j0 = (size_t)blockIdx.x * 32, ic0 = (size_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        size_t ic = ic0 + r, j = j0 + threadIdx.x;
+        if (ic < IC && j < dim0) tile[r][threadIdx.x] = src[ic * dim0 + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        size_t j = j0 + r, ic = ic0 + threadIdx.x;
+        if (ic < IC && j < dim0) dst[j * IC + ic] = tile[threadIdx.x][r];
+    }
+}
+void launch_db_from_reference(uint64_t *db, const uint64_t *B_ref, size_t dim0, size_t ic, size_t z_begin,
+                              size_t z_count, cudaStream_t s) {
+    if (!z_count) return;
+    dim3 grid((unsigned)((dim0 + 31) / 32), (unsigned)((ic + 31) / 32), (unsigned)z_count);
+    count_launch(); k_db_from_reference<<<grid, dim3(32, 8), 0, s>>>(db, B_ref, dim0, ic, z_begin);
+}
+
+void launch_db_to_reference(uint64_t *B_ref, const uint64_t *db, size_t dim0, size_t ic, cudaStream_t s) {
+    // the same 16-byte transpose with the roles of (ic, j) swapped
+    dim3 grid((unsigned)((ic + 31) / 32), (unsigned)((dim0 + 31) / 32), (unsigned)kN);
+    count_launch(); k_db_from_reference<<<grid, dim3(32, 8), 0, s>>>(B_ref, db, ic, dim0, 0);
+}
+
+// ============================================================================================
+// reorientCiphertexts: dev-NTT cts [j][r][m][n][z] -> query[z][j][m][4] PB64 (r = 3 lane zero)
+// ============================================================================================
+__global__ void k_reorient_query(uint64_t *__restrict__ out, const uint32_t *__restrict__ cts, size_t dim0) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (jm, z), z fastest
+    if (idx >= dim0 * 2 * kN) return;
+    const size_t z = idx % kN, jm = idx / kN, j = jm >> 1, m = jm & 1;
+    uint64_t w[4];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const uint32_t *p = cts + (((j * kN1 + r) * 2 + m) * 2) * (size_t)kN;
+        w[r] = pack_pb(p[z], p[kN + z]);
+    }
+    w[3] = 0;
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out + ((z * dim0 + j) * 2 + m) * 4);
+    dst[0] = make_ulonglong2(w[0], w[1]);
+    dst[1] = make_ulonglong2(w[2], w[3]);
+}
+void launch_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, cudaStream_t s) {
+    size_t n = dim0 * 2 * kN;
+    count_launch(); k_reorient_query<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, cts, dim0);
+}
+
+// ============================================================================================
+// First-dimension scan  (multiplyQueryByDatabase, src/spiral.cpp:628-999)
+//   out[i][r][c][n][z] = sum_{j,m} query[z][j][m][r]_n * DB[z][i][c][j][m]_n  mod prime_n
+// HBM-bound: every database byte is read exactly once per query; 6 32x32->64 MACs per 8 bytes.
+// CTA = 128 threads covering ZT z-slices x ICT ic-columns; each thread owns U ic-columns of one z
+// and streams its 16-byte (m=0,m=1) pairs down the j axis with 128-bit no-allocate loads, while
+// the query slice for those z sits in shared memory and is broadcast to the warp.
+// Accumulators are unreduced u64 (products < 2^56); they are folded to < 2^61 every 64 j
+// (128 products) with one 32x32 multiply, and Barrett-reduced once at the end.
+// ============================================================================================
+constexpr int kScanThreads = 128;
+constexpr int kScanFoldEvery = 64;
+
+__device__ __forceinline__ uint64_t fold_acc(uint64_t a, uint32_t c32) {      // a mod q preserved, result < 2^61
+    return (a & 0xffffffffull) + (uint64_t)(uint32_t)(a >> 32) * c32;
+}
+
+template <int U>
+__global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
+                                                             const uint64_t *__restrict__ db, int dim0, int IC, int ICT,
+                                                             int ZT, int JC) {
+    extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4 = 64 bytes per (z, j)
+    const int tid = threadIdx.x;
+    const int zl = (U == 1) ? tid / ICT : 0;
+    const int icl = (U == 1) ? tid % ICT : tid;
+    const int z0 = blockIdx.x * ZT, z = z0 + zl;
+    const int ic0 = blockIdx.y * ICT + icl;            // first owned column
+    const bool active = (U == 2) || tid < ZT * ICT;   // tiny IC: surplus threads only help staging
+    const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+
+    uint64_t acc[U][3][2];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) acc[u][r][0] = acc[u][r][1] = 0;
+
+    const uint4 *dbz = reinterpret_cast<const uint4 *>(db) + ((size_t)z * dim0) * IC + ic0;
+    const uint4 *qg = reinterpret_cast<const uint4 *>(query);
+
+    for (int jc0 = 0; jc0 < dim0; jc0 += JC) {
+        __syncthreads();
+        // stage the query rows [z0 .. z0+ZT) x [jc0 .. jc0+JC) : 4 uint4 per (z, j)
+        for (int e = tid; e < ZT * JC * 4; e += kScanThreads) {
+            const int zz = e / (JC * 4), rem = e % (JC * 4);
+            qs[e] = __ldg(qg + ((size_t)(z0 + zz) * dim0 + jc0) * 4 + rem);
+        }
+        __syncthreads();
+        const uint4 *qz = qs + (size_t)zl * JC * 4;
+        if (active)
+#pragma unroll 4
+        for (int jj = 0; jj < JC; jj++) {
+            const int j = jc0 + jj;
+            uint4 d[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) d[u] = ld_stream_u4(dbz + (size_t)j * IC + u * kScanThreads);
+            const uint4 q0 = qz[jj * 4 + 0], q1 = qz[jj * 4 + 1], q2 = qz[jj * 4 + 2], q3 = qz[jj * 4 + 3];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                // d = (m0.p, m0.b, m1.p, m1.b); q0 = m0:(r0.p r0.b r1.p r1.b) q1 = m0:(r2.p r2.b - -) q2,q3 = m1
+                acc[u][0][0] += (uint64_t)q0.x * d[u].x;  acc[u][0][1] += (uint64_t)q0.y * d[u].y;
+                acc[u][1][0] += (uint64_t)q0.z * d[u].x;  acc[u][1][1] += (uint64_t)q0.w * d[u].y;
+                acc[u][2][0] += (uint64_t)q1.x * d[u].x;  acc[u][2][1] += (uint64_t)q1.y * d[u].y;
+                acc[u][0][0] += (uint64_t)q2.x * d[u].z;  acc[u][0][1] += (uint64_t)q2.y * d[u].w;
+                acc[u][1][0] += (uint64_t)q2.z * d[u].z;  acc[u][1][1] += (uint64_t)q2.w * d[u].w;
+                acc[u][2][0] += (uint64_t)q3.x * d[u].z;  acc[u][2][1] += (uint64_t)q3.y * d[u].w;
+            }
+            if ((jj & (kScanFoldEvery - 1)) == kScanFoldEvery - 1) {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        acc[u][r][0] = fold_acc(acc[u][r][0], c32p);
+                        acc[u][r][1] = fold_acc(acc[u][r][1], c32b);
+                    }
+            }
+        }
+    }
+    if (active)
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int ic = ic0 + u * kScanThreads;
+        const int i = ic >> 1, c = ic & 1;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            uint32_t *o = out + ((((size_t)i * kN1 + r) * kN2 + c) * 2) * kN + z;
+            o[0] = reduce_u64(acc[u][r][0], 0);
+            o[kN] = reduce_u64(acc[u][r][1], 1);
+        }
+    }
+}
+
+void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
+    const int IC = (int)num_per * 2;
+    const int U = IC >= 256 ? 2 : 1;
+    const int ICT = IC < kScanThreads * U ? IC : kScanThreads * U;
+    int ZT = (kScanThreads * U) / ICT;
+    if (ZT > 8) ZT = 8;
+    int JC = (int)dim0;
+    while ((size_t)ZT * JC * 64 > 32768 && JC > kScanFoldEvery) JC >>= 1;
+    const size_t smem = (size_t)ZT * JC * 64;
+    dim3 grid(kN / ZT, IC / ICT);
+    if (U == 2) { count_launch(); k_scan_spiral<2><<<grid, kScanThreads, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC); }
+    else { count_launch(); k_scan_spiral<1><<<grid, kScanThreads, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC); }
+}
+
+// ============================================================================================
+// Folding  (foldOneFurtherDimension, src/spiral.cpp:1349-1410)
+//   C'[i] = Qneg (x) G^-1(C[i]) + Q (x) G^-1(C[num_per + i])
+// k_fold_decomp_ntt : signed base-2^bits_per digits with the reference's per-half carry chain
+//                     (split_and_crt, :270-341) -> forward NTT -> scratch[ct][m][c]
+// k_fold_mac_intt   : 2*m2-term pointwise dot product (cpu_mul_query_by_ct, :464-582), add,
+//                     inverse NTT and CRT lift (:1374-1407) fused; writes the folded ct in place.
+// ============================================================================================
+__device__ __forceinline__ uint64_t signed_digit(uint64_t val, int k, int t, uint32_t bits_per) {
+    const uint64_t mask = (1ull << bits_per) - 1;
+    const uint64_t halfv = (uint64_t)((1 << bits_per) / 2);
+    const int half_elems = t / 2;
+    const int k0 = k < half_elems ? 0 : half_elems;
+    uint64_t carry = 0, piece = 0;
+    for (int kk = k0; kk <= k; kk++) {
+        uint32_t off = min((uint32_t)kk * bits_per, 64u);
+        piece = ((val >> (off & 63)) & mask) + carry;
+        carry = 0;
+        const bool guard = (k < half_elems) ? (kk + 1 < half_elems) : true;   // first half: k < num_elems/2 - 1
+        if (piece > halfv && guard) { piece += kQ - (1ull << bits_per); carry = 1; }
+    }
+    return piece;
+}
+__global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, int t_gsw) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const int ctpoly = blockIdx.x, k = blockIdx.y;          // ctpoly = ct*6 + r*2 + c
+    const int ct = ctpoly / 6, r = (ctpoly % 6) >> 1, c = ctpoly & 1;
+    const uint32_t bits_per = get_bits_per(t_gsw);
+    const uint64_t *src = cts + (size_t)ctpoly * kN;
+    uint32_t v[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = raw_to_res(signed_digit(__ldg(src + nat_pos(lt, e)), k, t_gsw, bits_per), n);
+    ntt_forward_plane(v, sm[n], lt, n);
+    const int m2 = kN1 * t_gsw, row = r + k * kN1;
+    store_ntt_regs(v, scratch + ((((size_t)ct * m2 + row) * kN2 + c) * 2 + n) * kN, lt);
+}
+__global__ void __launch_bounds__(kNttThreads) k_fold_mac_intt(uint64_t *__restrict__ cts, const uint32_t *__restrict__ scratch,
+                                                               const uint32_t *__restrict__ q_dev, const uint32_t *__restrict__ qneg_dev,
+                                                               int num_per, int t_gsw) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const int i = blockIdx.x / 6, r = (blockIdx.x % 6) >> 1, c = blockIdx.x & 1;
+    const int m2 = kN1 * t_gsw;
+    uint64_t acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) acc[e] = 0;
+    for (int h = 0; h < 2; h++) {
+        const int ct = h == 0 ? i : num_per + i;
+        const uint32_t *Qm = (h == 0 ? qneg_dev : q_dev) + ((size_t)r * m2 * 2 + n) * kN;
+        const uint32_t *Cm = scratch + ((((size_t)ct * m2) * kN2 + c) * 2 + n) * kN;
+        for (int m = 0; m < m2; m++) {
+            uint32_t a[16], b[16];
+            load_ntt_regs(a, Qm + (size_t)m * 2 * kN, lt);
+            load_ntt_regs(b, Cm + (size_t)m * kN2 * 2 * kN, lt);
+#pragma unroll
+            for (int e = 0; e < 16; e++) acc[e] += (uint64_t)a[e] * b[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc[e] = reduce_u64(acc[e], n);     // keeps 2*m2 > 256 safe
+    }
+    uint32_t v[16];
+    const uint32_t q = modulus(n);
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = csub((uint32_t)acc[e], q);       // acc < 2q after the two partial reductions
+    // (the h = 0 partial result was already < q and h = 1 adds products before reducing again, so acc < q)
+    // inverse NTT + CRT lift, written over ciphertext i
+    {
+        ntt_inverse_plane(v, sm[n], lt, n);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
+        __syncthreads();
+        uint64_t *dst = cts + ((size_t)i * 6 + r * 2 + c) * kN;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int z = threadIdx.x + 256 * k;
+            dst[z] = crt_compose(sm[0][z], sm[1][z]);
+        }
+    }
+}
+// reference reorient_Q layout (packed [z][r*m2 + m], src/spiral.cpp:388-400) -> dev-NTT [r*m2 + m][n][z]
+__global__ void k_unreorient_q(uint32_t *__restrict__ out, const uint64_t *__restrict__ q_reor, int rm_count) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // (rm, z), z fastest
+    if (idx >= (size_t)rm_count * kN) return;
+    const int z = (int)(idx % kN), rm = (int)(idx / kN);
+    const uint64_t w = q_reor[(size_t)z * rm_count + rm];
+    out[((size_t)rm * 2) * kN + z] = (uint32_t)w % kP;
+    out[((size_t)rm * 2 + 1) * kN + z] = (uint32_t)(w >> 32) % kB;
+}
+void launch_unreorient_q(uint32_t *out, const uint64_t *q_reor, int rm_count, cudaStream_t s) {
+    const size_t n = (size_t)rm_count * kN;
+    count_launch(); k_unreorient_q<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, q_reor, rm_count);
+}
+// scan layout -> reference layout (inverse of launch_db_from_reference), whole database
+void launch_db_to_reference(uint64_t *B_ref, const uint64_t *db, size_t dim0, size_t ic, cudaStream_t s);
+
+size_t fold_scratch_words(size_t num_per_half, int t_gsw) { return 2 * num_per_half * (size_t)kN1 * t_gsw * kN2 * 2 * kN; }
+// split_and_crt alone (reference src/spiral.cpp:270-341) on `count` ciphertexts: scratch[ct][m][c] dev-NTT
+void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t count, int t_gsw, cudaStream_t s) {
+    if (count) { count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(count * 6), t_gsw), kNttThreads, 0, s>>>(scratch, cts, t_gsw); }
+}
+void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,
+                       int t_gsw, uint32_t *scratch, cudaStream_t s) {
+    count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(2 * num_per * 6), t_gsw), kNttThreads, 0, s>>>(scratch, cts, t_gsw);
+    count_launch(); k_fold_mac_intt<<<(unsigned)(num_per * 6), kNttThreads, 0, s>>>(cts, scratch, q_dev, qneg_dev, (int)num_per, t_gsw);
+}
+
+}  // namespace sb200

@@ -1,0 +1,138 @@
+"""Loader for oracle/liboracle.so - the CPU restatement of the reference.  TEST INFRASTRUCTURE:
+imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg, as the checker."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+N = 2048
+P = 268369921
+B = 249561089
+Q = P * B
+
+CONFIGS = {
+    "cfg1": dict(t_gsw=8, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=20, out_n=2, p_db=256),
+    "cfg3": dict(t_gsw=8, t_conv=4, t_exp=16, t_exp_right=56, qp_bits=20, out_n=4, p_db=256),
+    "cfg4": dict(t_gsw=3, t_conv=56, t_exp=56, t_exp_right=56, qp_bits=27, out_n=5, p_db=65536),
+    "cfg5": dict(t_gsw=9, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=21, out_n=2, p_db=256),
+}
+SO_CASE_MAX_IN = 4
+KIND_RAW, KIND_NTT, KIND_PACKED = 0, 1, 2
+
+
+class SoParams(C.Structure):
+    _fields_ = [("nu1", C.c_uint32), ("nu2", C.c_uint32), ("t_gsw", C.c_uint32), ("t_conv", C.c_uint32),
+                ("t_exp", C.c_uint32), ("t_exp_right", C.c_uint32), ("qp_bits", C.c_uint32),
+                ("out_n", C.c_uint32), ("p_db", C.c_uint64)]
+
+
+class SoCaseIO(C.Structure):
+    _fields_ = [("inp", C.POINTER(C.c_uint64) * SO_CASE_MAX_IN), ("in_words", C.c_size_t * SO_CASE_MAX_IN),
+                ("out", C.POINTER(C.c_uint64)), ("out_words", C.c_size_t), ("out_kind", C.c_int)]
+
+
+class SoShape(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("npolys", "dim0", "num_per", "g", "stopround", "max_bits_right", "cur_dim")]
+
+
+def make_params(cfg, nu1=0, nu2=0):
+    d = CONFIGS[cfg] if isinstance(cfg, str) else cfg
+    return SoParams(nu1, nu2, d["t_gsw"], d["t_conv"], d["t_exp"], d["t_exp_right"], d["qp_bits"], d["out_n"], d["p_db"])
+
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        build()
+    lib = C.CDLL(LIB)
+    u64p, sz = C.POINTER(C.c_uint64), C.c_size_t
+    lib.so_case_count.restype = C.c_int
+    lib.so_case_name.restype = C.c_char_p
+    lib.so_case_name.argtypes = [C.c_int]
+    lib.so_case_shape.argtypes = [C.c_int, C.POINTER(SoParams), C.POINTER(SoShape)]
+    lib.so_case_make_inputs.argtypes = [C.c_int, C.POINTER(SoParams), C.c_uint64, C.POINTER(SoCaseIO)]
+    lib.so_case_run_oracle.argtypes = [C.c_int, C.POINTER(SoParams), C.POINTER(SoCaseIO)]
+    lib.so_case_digest.restype = C.c_uint64
+    lib.so_case_digest.argtypes = [C.POINTER(SoCaseIO)]
+    lib.so_digest_kind.restype = C.c_uint64
+    lib.so_digest_kind.argtypes = [u64p, sz, C.c_int]
+    lib.so_case_free.argtypes = [C.POINTER(SoCaseIO)]
+    lib.so_tables.restype = u64p
+    lib.so_fnv1a64.restype = C.c_uint64
+    lib.so_fnv1a64.argtypes = [u64p, sz]
+    lib.so_arb_qprime.restype = C.c_uint64
+    lib.so_arb_qprime.argtypes = [C.c_uint32]
+    lib.so_spiral_expansion_shape.argtypes = [C.POINTER(SoParams), C.POINTER(sz), C.POINTER(sz)]
+    lib.so_spiral_answer.restype = C.c_int
+    lib.so_spiral_answer.argtypes = [C.POINTER(SoParams)] + [u64p] * 9
+    lib.so_load_db.argtypes = [u64p, u64p, C.c_uint32, C.c_uint32, C.c_uint64]
+    lib.so_multiply_query_by_database.argtypes = [u64p, u64p, u64p, sz, sz]
+    lib.so_reorient_ciphertexts.argtypes = [u64p, u64p, sz, sz]
+    lib.so_ntt_inv_and_crt_lift.argtypes = [u64p, u64p, sz]
+    lib.so_fold_one_further_dimension.argtypes = [sz, sz, u64p, u64p, u64p, C.c_uint32]
+    lib.so_to_ntt.argtypes = [u64p, u64p, sz]
+    lib.so_from_ntt.argtypes = [u64p, u64p, sz]
+    lib.so_get_rescaled.argtypes = [u64p, u64p, sz, C.c_uint64, C.c_uint64]
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def golden(cfg):
+    with open(os.path.join(GOLDEN_DIR, f"ref_digests_{cfg}.json")) as f:
+        return json.load(f)
+
+
+class Case:
+    """One parity case: seeded inputs + the oracle's output, as numpy arrays."""
+
+    def __init__(self, lib, case_id, prm, seed):
+        self.lib, self.id, self.prm = lib, case_id, prm
+        self.io = SoCaseIO()
+        lib.so_case_make_inputs(case_id, C.byref(prm), seed, C.byref(self.io))
+        lib.so_case_run_oracle(case_id, C.byref(prm), C.byref(self.io))
+        self.name = lib.so_case_name(case_id).decode()
+        self.shape = SoShape()
+        lib.so_case_shape(case_id, C.byref(prm), C.byref(self.shape))
+        self.inputs = [np.ctypeslib.as_array(self.io.inp[k], shape=(self.io.in_words[k],)).copy()
+                       if self.io.in_words[k] else None for k in range(SO_CASE_MAX_IN)]
+        self.out = np.ctypeslib.as_array(self.io.out, shape=(self.io.out_words,)).copy()
+        self.kind = self.io.out_kind
+        self.digest = lib.so_case_digest(C.byref(self.io))
+        lib.so_case_free(C.byref(self.io))
+
+
+def canon(a, kind):
+    """Canonical form for comparison: raw exact; NTT / packed residues reduced modulo their prime."""
+    a = np.asarray(a, dtype=np.uint64)
+    if kind == KIND_RAW:
+        return a
+    if kind == KIND_NTT:
+        v = a.reshape(-1, 2, N).copy()
+        v[:, 0, :] %= np.uint64(P)
+        v[:, 1, :] %= np.uint64(B)
+        return v.reshape(-1)
+    lo = (a & np.uint64(0xFFFFFFFF)) % np.uint64(P)
+    hi = (a >> np.uint64(32)) % np.uint64(B)
+    return lo | (hi << np.uint64(32))
