@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py - Spiral server-side query answering on B200: ms/query and database GB/s scanned.
+
+One "step" = one query answered against the resident database (expansion + conversion +
+first-dimension scan + folding + modulus switch), BASELINE.json's metric.
+
+  python bench.py --gpus 1 --steps K --warmup W            our CUDA path   (config.workload = cfg1)
+  python bench.py --impl reference ...                      the UNMODIFIED reference (oracle/_ref) on host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...         second dimension sharded over N GPUs (weak scaling:
+                                                            every GPU keeps a 2^20-record shard, nu_2 grows by log2 N)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG1 = dict(t_gsw=8, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=20, out_n=2, p_db=256)   # SURVEY 8d, `./spiral 8 7`
+N_POLY = 2048
+
+
+def host_isa():
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return "avx2"
+    return "avx512" if " avx512f" in flags and " avx512dq" in flags and " avx512bw" in flags and " avx512vl" in flags else "avx2"
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference through its own harness (oracle/ref_bench.cpp)
+# ------------------------------------------------------------------------------------------------
+STAGE_RE = {
+    "expansion": r"Main expansion\s+\(CPU.us\):\s+(\d+)",
+    "conversion": r"Conversion \(CPU.us\):\s+(\d+)",
+    "first_dim": r"First dimension multiply \(CPU.us\):\s+(\d+)",
+    "folding": r"Folding \(CPU.us\):\s+(\d+)",
+}
+
+
+def run_reference(nu1, nu2, queries, timeout=1500):
+    """Returns per-query stage times (ms) parsed from the reference's own print_summary
+    (src/spiral.cpp:239-263).  `Main expansion` and `Conversion` accumulate across queries in the
+    reference (+=, src/spiral.cpp:2180,2256), so they are differenced; the other two are per query."""
+    isa = host_isa()
+    exe = os.path.join(ROOT, "oracle", "_ref", f"ref_bench_cfg1_{isa}")
+    if not os.path.exists(exe):
+        return None, f"{exe} not built"
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "oracle", "_ref") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    try:
+        out = subprocess.run([exe, str(nu1), str(nu2), "1234", str(queries)], capture_output=True, text=True, timeout=timeout, env=env)
+    except Exception as e:  # noqa: BLE001
+        return None, f"reference run failed: {e}"
+    if out.returncode != 0:
+        return None, f"reference exited {out.returncode}: {out.stderr[-200:]}"
+    chunks = out.stdout.split("=== ref_bench query")[1:]
+    res, prev = [], dict(expansion=0, conversion=0)
+    for ch in chunks:
+        st = {}
+        for k, rx in STAGE_RE.items():
+            m = re.search(rx, ch)
+            if not m:
+                return None, f"could not parse '{k}' from the reference output"
+            st[k] = int(m.group(1))
+        correct = re.search(r"Is correct\?:\s*(\d)", ch)
+        q = dict(expansion=(st["expansion"] - prev["expansion"]) / 1e3, conversion=(st["conversion"] - prev["conversion"]) / 1e3,
+                 first_dim=st["first_dim"] / 1e3, folding=st["folding"] / 1e3, correct=bool(correct and correct.group(1) == "1"))
+        q["total"] = q["expansion"] + q["conversion"] + q["first_dim"] + q["folding"]
+        prev = dict(expansion=st["expansion"], conversion=st["conversion"])
+        res.append(q)
+    return res, isa
+
+
+def oracle_port_baseline(nu1, nu2):
+    """Fallback CPU baseline when oracle/_ref is absent: the oracle port (scalar C) on one core."""
+    import ctypes as C
+    import numpy as np
+    from tests import oracle_lib as ol
+    lib = ol.load()
+    s = ol.SpiralSession(lib, "cfg1", nu1, nu2, seed=1)
+    Bbuf = s.reference_db()
+    q = s.query(3)
+    t0 = time.perf_counter()
+    s.oracle_answer(q, Bbuf)
+    dt = (time.perf_counter() - t0) * 1e3
+    s.close()
+    return dt
+
+
+def workload_name(nu1, nu2):
+    return f"Spiral 2^{nu1 + nu2 + 5} records x 256 B (./spiral {nu1} {nu2}; TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256), explicit DB"
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nu1, nu2 = args.nu1, args.nu2          # the reference is single-process: it always runs the N=1 workload
+    res, info = run_reference(nu1, nu2, args.steps + args.warmup)
+    base = {"impl": "reference", "metric": "server_ms_per_query", "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": {"workload": workload_name(nu1, nu2)}}
+    if res is None:
+        kind = "port"
+        try:
+            ms = oracle_port_baseline(6, 4)
+            sample = "oracle port (scalar C restatement), ONE query at ./spiral 6 4 (1/32 of the records), 1 core: " + info
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps(dict(base, unavailable=f"{info}; oracle port failed: {e}")))
+            return 0
+        line = dict(base, value=ms, ms_per_step=ms, cpu_baseline={"value": ms, "unit": "ms", "cores": 1, "kind": kind, "sample": sample},
+                    e2e={"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return 0
+    timed = res[args.warmup:] if len(res) > args.warmup else res
+    ms = sum(q["total"] for q in timed) / len(timed)
+    stages = {k: sum(q[k] for q in timed) / len(timed) for k in ("expansion", "conversion", "first_dim", "folding")}
+    db_bytes = 8 * N_POLY * 4 << (nu1 + nu2)
+    sample = (f"unmodified reference (oracle/_ref, g++ -O3 -march=x86-64-{'v4' if info == 'avx512' else 'v3'}, {info} scan path), "
+              f"{len(timed)} full queries at the same workload after {args.warmup} warm-up, single thread (the reference is single-threaded, "
+              f"src/spiral.cpp:1231) on {cpu_model()}; all queries decoded correctly: {all(q['correct'] for q in res)}")
+    line = dict(base, value=ms, ms_per_step=ms, stages_ms=stages, db_gbs_scanned=db_bytes / (stages["first_dim"] * 1e-3) / 1e9,
+                cpu_baseline={"value": ms, "unit": "ms", "cores": 1, "kind": "reference", "sample": sample},
+                e2e={"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (recipe in /opt/skills/guides/B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def b200_main(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from spiral_b200 import SpiralParams
+    from spiral_b200.lib import load_library
+    from spiral_b200.server import SpiralServer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = load_library()
+
+    log_w = world.bit_length() - 1
+    nu1, nu2 = args.nu1, args.nu2 + log_w                    # weak scaling: fixed 2^(nu1+args.nu2) items per GPU
+    prm = SpiralParams(nu1, nu2, CFG1["t_gsw"], CFG1["t_conv"], CFG1["t_exp"], CFG1["t_exp_right"], CFG1["qp_bits"], CFG1["out_n"], CFG1["p_db"])
+    srv = SpiralServer(prm, device=local_rank, rank=rank, world=world)
+    srv.load_db_random(seed=1000 + rank)
+
+    # synthetic public parameters and query: uniform ring elements of the right shape (ref-NTT layout)
+    rng = np.random.default_rng(7)                           # same on every rank (the query is replicated)
+    PL = 2 * N_POLY
+    ell_bits = CFG1["t_gsw"] * nu2
+    g = int(np.ceil(np.log2(ell_bits + (1 << nu1))))
+    stop = int(np.ceil(np.log2(ell_bits))) if ell_bits <= (1 << nu1) else 0
+    n_right = stop + 1 if stop else g
+
+    def rnd_ntt(npolys):
+        a = rng.integers(0, 249561089, size=(npolys, 2, N_POLY), dtype=np.uint64)
+        return np.ascontiguousarray(a.reshape(-1))
+    srv.set_public_params(rnd_ntt(g * 2 * CFG1["t_exp"]), rnd_ntt(n_right * 2 * CFG1["t_exp_right"]),
+                          rnd_ntt(3 * 2 * CFG1["t_conv"]), rnd_ntt(3 * 2 * CFG1["t_conv"]))
+    q_host = torch.from_numpy(rnd_ntt(2).view(np.int64)).pin_memory()
+    resp_host = torch.empty(6 * N_POLY, dtype=torch.int64).pin_memory()
+    gathered = torch.empty(world * 6 * N_POLY, dtype=torch.int64, device="cuda")
+    part = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
+    resp_dev = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(timed_events=None, e2e=False):
+        """One query.  e2e=True includes the H2D of the query and the D2H of the response."""
+        if e2e or timed_events is None:
+            srv.upload_query_ptr(q_host.data_ptr(), stream)
+        marks = []
+        if timed_events is not None:
+            marks.append(ev()); marks[-1].record()
+        srv.expand_and_convert(stream)
+        if timed_events is not None:
+            marks.append(ev()); marks[-1].record()
+        srv.scan(stream)
+        if timed_events is not None:
+            marks.append(ev()); marks[-1].record()
+        srv.lift(stream)
+        srv.fold_local(stream)
+        if world > 1:
+            srv.copy_partial(part.data_ptr(), stream)
+            dist.all_gather_into_tensor(gathered, part)       # one 96 KiB ciphertext per GPU over NVLink (NCCL)
+            if rank == 0:
+                srv.fold_tail(gathered.data_ptr(), resp_dev.data_ptr(), stream)
+        else:
+            srv.fold_tail(srv.partial_ct_ptr(), resp_dev.data_ptr(), stream)
+        if timed_events is not None:
+            marks.append(ev()); marks[-1].record()
+            timed_events.append(marks)
+        if e2e and rank == 0:
+            resp_host.copy_(resp_dev, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # resident upload once for the device-timed loop
+    srv.upload_query_ptr(q_host.data_ptr(), stream)
+    for _ in range(max(args.warmup, 3)):
+        step(timed_events=[])
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.sb200_launch_count()
+    events = []
+    t_begin, t_end = ev(), ev()
+    barrier()
+    t_begin.record()
+    for _ in range(args.steps):
+        step(timed_events=events)
+    t_end.record()
+    barrier()
+    launches = lib.sb200_launch_count() - launches0
+    total_ms = t_begin.elapsed_time(t_end)
+
+    # end to end through the host-buffer call path (H2D query + D2H response inside the timed region)
+    e_begin, e_end = ev(), ev()
+    barrier()
+    e_begin.record()
+    for _ in range(args.steps):
+        step(timed_events=None, e2e=True)
+        torch.cuda.current_stream().synchronize()             # the caller holds the response before the next query
+    e_end.record()
+    barrier()
+    e2e_ms = e_begin.elapsed_time(e_end)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    scan_ms = sorted(m[1].elapsed_time(m[2]) for m in events)
+    exp_ms = sum(m[0].elapsed_time(m[1]) for m in events) / len(events)
+    rest_ms = sum(m[2].elapsed_time(m[3]) for m in events) / len(events)
+    scan_avg = sum(scan_ms) / len(scan_ms)
+    sc = torch.tensor([scan_avg], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sc, op=dist.ReduceOp.MAX)
+    scan_max = float(sc[0])
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        db_bytes_gpu = srv.db_bytes                            # algorithmic bytes per launch: 8 B x 2048 x 4 x items on this GPU
+        achieved = db_bytes_gpu / (scan_avg * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        ms_per_query = total_ms / args.steps
+        line = {
+            "metric": "server_ms_per_query", "value": ms_per_query, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_query, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (28-bit CRT residues, 32x32->64 MAC)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(nu1, nu2), "sharding": f"second dimension strided over {world} GPU(s), {srv.db_bytes / 2**30:.2f} GiB shard per GPU",
+                       "l2": "database shard (2 GiB) is 16x the 126 MB L2 and is streamed once per query - no flush needed"},
+            "stages_ms": {"expansion_conversion": exp_ms, "first_dim_scan": scan_avg, "lift_fold_modswitch": rest_ms},
+            "db_gbs_scanned": world * db_bytes_gpu / (scan_max * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_scan_spiral", "peak_source": peak_src, "scan_ms_min_med_max": [scan_ms[0], scan_ms[len(scan_ms) // 2], scan_ms[-1]]},
+            "e2e": {"value": e2e_ms / args.steps, "unit": "ms", "h2d_bytes_per_step": int(q_host.numel() * 8), "d2h_bytes_per_step": int(resp_host.numel() * 8)},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res, info = run_reference(args.nu1, args.nu2, 2)
+            if res is not None:
+                qd = res[-1]
+                line["cpu_baseline"] = {"value": qd["total"], "unit": "ms", "cores": 1, "kind": "reference",
+                                        "stages_ms": {k: qd[k] for k in ("expansion", "conversion", "first_dim", "folding")},
+                                        "sample": f"unmodified reference (oracle/_ref, {info}), 2nd of 2 full queries at the same workload, 1 thread on {cpu_model()}, decoded correctly: {qd['correct']}"}
+            else:
+                try:
+                    ms = oracle_port_baseline(6, 4)
+                    line["cpu_baseline"] = {"value": ms, "unit": "ms", "cores": 1, "kind": "port",
+                                            "sample": f"oracle port, one query at ./spiral 6 4 (1/32 of the records), 1 core ({info})"}
+                except Exception as e:  # noqa: BLE001
+                    line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+        print(json.dumps(line))
+    srv.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nu1", type=int, default=8)
+    ap.add_argument("--nu2", type=int, default=7)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 8:
+            args.steps = 8                                    # ~3 s per CPU query; keep the whole run within minutes
+        return reference_main(args)
+    return b200_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

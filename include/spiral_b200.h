@@ -129,6 +129,10 @@ int sb200_server_answer(sb200_server *srv, const uint64_t *query_cv_host, uint64
 int sb200_server_upload_query(sb200_server *srv, const uint64_t *query_cv_host, void *stream);
 int sb200_server_expand_and_convert(sb200_server *srv, void *stream);      /* expansion + ScalToMat + RegevToGSW (+negation) */
 int sb200_server_first_dim(sb200_server *srv, void *stream);               /* scan + INTT + CRT lift */
+int sb200_server_scan(sb200_server *srv, void *stream);                    /* multiplyQueryByDatabase only (src/spiral.cpp:628) */
+int sb200_server_lift(sb200_server *srv, void *stream);                    /* nttInvAndCrtLiftCiphertexts only (src/spiral.cpp:437) */
+int sb200_server_copy_partial(sb200_server *srv, uint64_t *dst_dev, void *stream);   /* D2D copy of the shard's surviving ct */
+int sb200_server_load_db_random(sb200_server *srv, uint64_t seed);         /* synthetic uniform database (benchmarks) */
 int sb200_server_fold_local(sb200_server *srv, void *stream);              /* local fold rounds; leaves 1 ct per shard */
 uint64_t *sb200_server_partial_ct(sb200_server *srv);                      /* device ptr: this shard's surviving ct (3x2 raw) */
 /* rank 0: `gathered` = world cts (device, order = rank); runs the last log2(world) folds + modulus switch */

@@ -1,0 +1,246 @@
+/*
+ * client_sim.c - a minimal Spiral CLIENT (key generation, public parameters, query, decoding).
+ *
+ * TEST INFRASTRUCTURE ONLY (part of liboracle.so).  The client is out of scope for the product
+ * (SURVEY section 2); this restatement exists so the tests can drive the CUDA server with REAL
+ * encryptions and check the one end-to-end property the reference itself checks: the decoded
+ * record equals the planted record ("Is correct?: 1", src/spiral.cpp:1494).  Randomness comes
+ * from a seeded splitmix64 instead of the reference's unseeded std::random_device.
+ *
+ * Restates: keygen src/client.cpp:23-47, getRegevSample :141-157, encryptSimpleRegev :170-186,
+ * encryptSimpleRegevMatrix :209-227, get_fresh_public_key_raw :49-68, getPublicEncryptions
+ * :271-290, W / V generation src/spiral.cpp:2207-2290, query encoding :2098-2157, decoding
+ * (check_final) :1428-1476, discrete Gaussian src/core.cpp:182-207.
+ */
+#include "client_sim.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define N SO_N
+#define PL (2 * (size_t)SO_N)
+typedef unsigned __int128 u128;
+
+struct so_client {
+    so_params prm;
+    so_rng rng;
+    int nonoise;
+    uint64_t *Sp;       /* n0 x 1 raw */
+    uint64_t *sr;       /* 1 x 1 raw  */
+    double cdf[2 * 64 + 1];
+};
+
+static uint64_t *xalloc(size_t words) {
+    uint64_t *p = (uint64_t *)calloc(words ? words : 1, sizeof(uint64_t));
+    if (!p) abort();
+    return p;
+}
+
+/* discrete Gaussian, width 6.4, support [-64, 64]  (src/core.cpp:182-207) */
+static void build_cdf(so_client *c) {
+    double total = 0, acc = 0;
+    for (int i = -64; i <= 64; i++) total += exp(-M_PI * (double)i * i / (6.4 * 6.4));
+    for (int i = -64; i <= 64; i++) { acc += exp(-M_PI * (double)i * i / (6.4 * 6.4)) / total; c->cdf[i + 64] = acc; }
+}
+static uint64_t sample_u64(so_client *c) {                 /* src/client.cpp:7-10 */
+    if (c->nonoise) return 0;
+    double u = (double)(so_rng_next(&c->rng) >> 11) / 9007199254740992.0;
+    int k = 0;
+    while (k < 128 && c->cdf[k] < u) k++;
+    int64_t v = k - 64;
+    return (uint64_t)((v + (int64_t)SO_Q) % (int64_t)SO_Q);
+}
+static void noise(so_client *c, uint64_t *E, size_t npolys) { for (size_t i = 0; i < npolys * N; i++) E[i] = sample_u64(c); }
+
+so_client *so_client_new(const so_params *prm, uint64_t seed, int nonoise) {
+    so_client *c = (so_client *)calloc(1, sizeof(so_client));
+    c->prm = *prm; c->rng.s = seed; c->nonoise = nonoise;
+    build_cdf(c);
+    c->Sp = xalloc(SO_N0 * N); c->sr = xalloc(N);
+    /* keygen draws the key from the error distribution even under --nonoise; keep it non-trivial */
+    int saved = c->nonoise; c->nonoise = 0;
+    for (size_t m = 0; m < N; m++) c->sr[m] = sample_u64(c) % SO_Q;
+    for (size_t r = 0; r < SO_N0; r++) for (size_t m = 0; m < N; m++) c->Sp[r * N + m] = sample_u64(c) % SO_Q;
+    c->nonoise = saved;
+    return c;
+}
+void so_client_free(so_client *c) { if (c) { free(c->Sp); free(c->sr); free(c); } }
+
+/* P (2x1 NTT) = [to_ntt(Q - a) ; a*s + e]   (getRegevSample) */
+static void regev_sample(so_client *c, uint64_t *P_ntt) {
+    uint64_t *a = xalloc(N), *e = xalloc(N), *a_inv = xalloc(N);
+    uint64_t *a_ntt = xalloc(PL), *s_ntt = xalloc(PL), *e_ntt = xalloc(PL), *b = xalloc(PL);
+    so_fill_uniform_raw(a, N, &c->rng);
+    noise(c, e, 1);
+    so_invert(a_inv, a, 1);
+    so_to_ntt(a_ntt, a, 1); so_to_ntt(s_ntt, c->sr, 1); so_to_ntt(e_ntt, e, 1);
+    so_multiply(b, a_ntt, s_ntt, 1, 1, 1);
+    so_add(b, b, e_ntt, 1);
+    so_to_ntt(P_ntt, a_inv, 1);
+    memcpy(P_ntt + PL, b, PL * sizeof(uint64_t));
+    free(a); free(e); free(a_inv); free(a_ntt); free(s_ntt); free(e_ntt); free(b);
+}
+/* encryptSimpleRegev(sigma): 2x1 NTT */
+static void encrypt_simple_regev(so_client *c, uint64_t *out_ntt, const uint64_t *sigma_raw) {
+    uint64_t *sig_ntt = xalloc(PL);
+    regev_sample(c, out_ntt);
+    so_to_ntt(sig_ntt, sigma_raw, 1);
+    so_add(out_ntt + PL, out_ntt + PL, sig_ntt, 1);
+    free(sig_ntt);
+}
+/* encryptSimpleRegevMatrix(s, mat_to_enc (1 x m NTT)) -> 2 x m NTT */
+static void encrypt_simple_regev_matrix(so_client *c, uint64_t *out, const uint64_t *mat_ntt, size_t m) {
+    uint64_t P[2 * 2 * SO_N];
+    for (size_t i = 0; i < m; i++) {
+        regev_sample(c, P);
+        memcpy(&out[(0 * m + i) * PL], P, PL * sizeof(uint64_t));
+        so_add(&out[(1 * m + i) * PL], P + PL, &mat_ntt[i * PL], 1);
+    }
+}
+/* get_fresh_public_key_raw(Sp, m) -> to_ntt(P), P = [Q - A ; Sp*A + E]  (n1 x m) */
+static void fresh_public_key_ntt(so_client *c, uint64_t *P_ntt, size_t m) {
+    uint64_t *A = xalloc(m * N), *E = xalloc(SO_N0 * m * N), *A_ntt = xalloc(m * PL), *E_ntt = xalloc(SO_N0 * m * PL);
+    uint64_t *Sp_ntt = xalloc(SO_N0 * PL), *Bp = xalloc(SO_N0 * m * PL), *P_raw = xalloc(SO_N1 * m * N);
+    so_fill_uniform_raw(A, m * N, &c->rng);
+    noise(c, E, SO_N0 * m);
+    so_to_ntt(A_ntt, A, m); so_to_ntt(E_ntt, E, SO_N0 * m); so_to_ntt(Sp_ntt, c->Sp, SO_N0);
+    so_multiply(Bp, Sp_ntt, A_ntt, SO_N0, 1, m);
+    so_add(Bp, E_ntt, Bp, SO_N0 * m);
+    uint64_t *A_back = xalloc(m * N);
+    so_from_ntt(A_back, A_ntt, m);
+    so_invert(P_raw, A_back, m);
+    so_from_ntt(P_raw + m * N, Bp, SO_N0 * m);
+    so_to_ntt(P_ntt, P_raw, SO_N1 * m);
+    free(A); free(E); free(A_ntt); free(E_ntt); free(Sp_ntt); free(Bp); free(P_raw); free(A_back);
+}
+
+size_t so_client_w_exp_right_count(const so_params *prm) {
+    size_t g, stop; so_spiral_expansion_shape(prm, &g, &stop);
+    return stop > 0 ? stop + 1 : g;
+}
+
+static void expansion_keys(so_client *c, uint64_t *W, size_t count, uint32_t t) {   /* getPublicEncryptions */
+    uint64_t *G = xalloc((size_t)t * N), *G_ntt = xalloc((size_t)t * PL), *tau = xalloc(N), *tau_ntt = xalloc(PL), *prod = xalloc((size_t)t * PL);
+    so_build_gadget(G, 1, t);
+    so_to_ntt(G_ntt, G, t);
+    for (size_t i = 0; i < count; i++) {
+        so_automorph(tau, c->sr, 1, (N >> i) + 1);
+        so_to_ntt(tau_ntt, tau, 1);
+        so_multiply(prod, tau_ntt, G_ntt, 1, 1, t);
+        encrypt_simple_regev_matrix(c, &W[i * 2 * t * PL], prod, t);
+    }
+    free(G); free(G_ntt); free(tau); free(tau_ntt); free(prod);
+}
+
+void so_client_spiral_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *W_conv, uint64_t *V_conv) {
+    const so_params *p = &c->prm;
+    size_t g, stop; so_spiral_expansion_shape(p, &g, &stop);
+    expansion_keys(c, W_exp_right, so_client_w_exp_right_count(p), p->t_exp_right);   /* order as :2093-2094 */
+    expansion_keys(c, W_exp_left, g, p->t_exp);
+
+    size_t mc = p->t_conv, m = 2 * mc;
+    uint64_t *s0_ntt = xalloc(PL), *Sp_ntt = xalloc(SO_N0 * PL);
+    so_to_ntt(s0_ntt, c->sr, 1); so_to_ntt(Sp_ntt, c->Sp, SO_N0);
+    {   /* W = P + [0 ; s0 * G_scale]   (:2207-2217) */
+        uint64_t *G = xalloc(SO_N0 * m * N), *G_ntt = xalloc(SO_N0 * m * PL), *s0G = xalloc(SO_N0 * m * PL), *P = xalloc(SO_N1 * m * PL);
+        so_build_gadget(G, SO_N0, m);
+        so_to_ntt(G_ntt, G, SO_N0 * m);
+        so_mul_by_const(s0G, s0_ntt, G_ntt, SO_N0 * m);
+        fresh_public_key_ntt(c, P, m);
+        memcpy(W_conv, P, m * PL * sizeof(uint64_t));
+        so_add(W_conv + m * PL, P + m * PL, s0G, SO_N0 * m);
+        free(G); free(G_ntt); free(s0G); free(P);
+    }
+    {   /* V = P + [0 ; Sp * [s0*gv | gv]]   (:2274-2290) */
+        uint64_t *gv = xalloc(mc * N), *gv_ntt = xalloc(mc * PL), *tog = xalloc(m * PL), *res = xalloc(SO_N0 * m * PL), *P = xalloc(SO_N1 * m * PL);
+        so_build_gadget(gv, 1, mc);
+        so_to_ntt(gv_ntt, gv, mc);
+        so_mul_by_const(tog, s0_ntt, gv_ntt, mc);
+        memcpy(tog + mc * PL, gv_ntt, mc * PL * sizeof(uint64_t));
+        so_multiply(res, Sp_ntt, tog, SO_N0, 1, m);
+        fresh_public_key_ntt(c, P, m);
+        memcpy(V_conv, P, m * PL * sizeof(uint64_t));
+        so_add(V_conv + m * PL, P + m * PL, res, SO_N0 * m);
+        free(gv); free(gv_ntt); free(tog); free(res); free(P);
+    }
+    free(s0_ntt); free(Sp_ntt);
+}
+
+static int64_t inv_mod(int64_t a, int64_t b) {             /* src/util.cpp:272-286 */
+    int64_t b0 = b, t, q, x0 = 0, x1 = 1;
+    if (b == 1) return 1;
+    while (a > 1) { q = a / b; t = b; b = a % b; a = t; t = x0; x0 = x1 - q * x0; x1 = t; }
+    if (x1 < 0) x1 += b0;
+    return x1;
+}
+
+void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv) {   /* :2098-2157 */
+    const so_params *p = &c->prm;
+    size_t g, stop; so_spiral_expansion_shape(p, &g, &stop);
+    size_t fd = p->nu2, ell = p->t_gsw, dim0 = (size_t)1 << p->nu1;
+    size_t idx_dim0 = idx_target >> fd, idx_further = idx_target & (((size_t)1 << fd) - 1);
+    uint32_t bits_per = so_get_bits_per((uint32_t)ell);
+    uint64_t scale_k = SO_Q / p->p_db;
+    uint64_t *sigma = xalloc(N);
+    if (stop != 0) {
+        sigma[2 * idx_dim0] = scale_k % SO_Q;
+        for (size_t i = 0; i < fd; i++) {
+            uint64_t bit = (idx_further >> i) & 1;
+            for (size_t j = 0; j < ell; j++) sigma[2 * (i * ell + j) + 1] = ((uint64_t)1 << (bits_per * j)) * bit % SO_Q;
+        }
+        uint64_t inv_first = (uint64_t)inv_mod((int64_t)1 << g, (int64_t)SO_Q), inv_rest = (uint64_t)inv_mod((int64_t)1 << (stop + 1), (int64_t)SO_Q);
+        for (size_t i = 0; i < N / 2; i++) {
+            sigma[2 * i] = (uint64_t)((u128)sigma[2 * i] * inv_first % SO_Q);
+            sigma[2 * i + 1] = (uint64_t)((u128)sigma[2 * i + 1] * inv_rest % SO_Q);
+        }
+    } else {
+        sigma[idx_dim0] = scale_k % SO_Q;
+        size_t ctr = 0;
+        for (size_t i = 0; i < fd; i++) {
+            uint64_t bit = (idx_further >> i) & 1;
+            for (size_t j = 0; j < ell; j++) sigma[dim0 + ctr++] = ((uint64_t)1 << (bits_per * j)) * bit % SO_Q;
+        }
+        uint64_t inv = (uint64_t)inv_mod((int64_t)1 << g, (int64_t)SO_Q);
+        for (size_t i = 0; i < N; i++) sigma[i] = (uint64_t)((u128)sigma[i] * inv % SO_Q);
+    }
+    encrypt_simple_regev(c, query_cv, sigma);
+    free(sigma);
+}
+
+/* negacyclic product over Z_q' (what to_ntt_qprime / mul_over_qprime / from_ntt_qprime compute) */
+static void negacyclic_mul_acc(uint64_t *res, const uint64_t *a, const uint64_t *b, uint64_t q) {
+    for (size_t i = 0; i < N; i++) {
+        if (!a[i]) continue;
+        for (size_t j = 0; j < N; j++) {
+            uint64_t prod = (uint64_t)((u128)a[i] * b[j] % q);
+            size_t k = i + j;
+            if (k < N) res[k] = (res[k] + prod) % q; else res[k - N] = (res[k - N] + q - prod) % q;
+        }
+    }
+}
+
+void so_client_spiral_decode(so_client *c, const uint64_t *total_resp, uint64_t *out_pt) {   /* :1428-1476 */
+    const so_params *p = &c->prm;
+    uint64_t qp = so_arb_qprime(p->qp_bits), q_1 = 4 * p->p_db;
+    uint64_t *Sp_q = xalloc(SO_N0 * N), *s_prod = xalloc(SO_N0 * SO_N2 * N);
+    for (size_t i = 0; i < SO_N0 * N; i++) {               /* to_ntt_qprime's recentering, src/util.cpp:224-229 */
+        int64_t a = (int64_t)c->Sp[i];
+        if (a >= (int64_t)(SO_Q / 2)) a -= (int64_t)SO_Q;
+        Sp_q[i] = (uint64_t)((a + (int64_t)((SO_Q / qp) * qp) + 2 * (int64_t)qp) % (int64_t)qp);
+    }
+    for (size_t r = 0; r < SO_N0; r++)
+        for (size_t cc = 0; cc < SO_N2; cc++)
+            negacyclic_mul_acc(&s_prod[(r * SO_N2 + cc) * N], &Sp_q[r * N], &total_resp[cc * N], qp);
+    const uint64_t *rest = total_resp + SO_N2 * N;
+    for (size_t i = 0; i < SO_N0 * SO_N2 * N; i++) {
+        int64_t vf = (int64_t)s_prod[i]; if (vf >= (int64_t)(qp / 2)) vf -= (int64_t)qp;
+        int64_t vr = (int64_t)rest[i];   if (vr >= (int64_t)(q_1 / 2)) vr -= (int64_t)q_1;
+        uint64_t denom = qp * (q_1 / p->p_db);
+        int64_t r = vf * (int64_t)q_1 + vr * (int64_t)qp;
+        int64_t sign = r >= 0 ? 1 : -1;
+        __int128 res = ((__int128)r + sign * ((int64_t)denom / 2)) / (__int128)denom;
+        res = (res + (denom / p->p_db) * p->p_db + 2 * p->p_db) % p->p_db;
+        out_pt[i] = (uint64_t)res;
+    }
+    free(Sp_q); free(s_prod);
+}

@@ -1,0 +1,17 @@
+/* client_sim.h - minimal Spiral client for end-to-end tests.  TEST INFRASTRUCTURE ONLY (see client_sim.c). */
+#pragma once
+#include "spiral_oracle.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct so_client so_client;
+so_client *so_client_new(const so_params *prm, uint64_t seed, int nonoise);
+void so_client_free(so_client *c);
+size_t so_client_w_exp_right_count(const so_params *prm);
+/* W_exp_left: g x (2 x t_exp); W_exp_right: count x (2 x t_exp_right); W_conv, V_conv: 3 x 2*t_conv (all ref-NTT) */
+void so_client_spiral_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *W_conv, uint64_t *V_conv);
+void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv);
+void so_client_spiral_decode(so_client *c, const uint64_t *total_resp, uint64_t *out_pt);
+#ifdef __cplusplus
+}
+#endif

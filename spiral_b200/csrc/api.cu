@@ -500,12 +500,44 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
     CHECK_LAUNCH();
     return SB200_OK;
 }
-extern "C" int sb200_server_first_dim(sb200_server *s, void *stream) {
+extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    if (!s->have_db) return fail(SB200_ERR_STATE, "first_dim: database not loaded");
+    if (!s->have_db) return fail(SB200_ERR_STATE, "scan: database not loaded");
     launch_scan_spiral(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, S(stream));
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+extern "C" int sb200_server_lift(sb200_server *s, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
     launch_from_ntt(s->cts.p, s->scan_out.p, s->local_num_per * 6, S(stream));
     CHECK_LAUNCH();
+    return SB200_OK;
+}
+extern "C" int sb200_server_first_dim(sb200_server *s, void *stream) {
+    TRY(sb200_server_scan(s, stream));
+    return sb200_server_lift(s, stream);
+}
+extern "C" int sb200_server_copy_partial(sb200_server *s, uint64_t *dst_dev, void *stream) {
+    if (!s || !dst_dev) return fail(SB200_ERR_ARG, "copy_partial: null argument");
+    CU(cudaMemcpyAsync(dst_dev, s->cts.p, 6 * (size_t)kN * sizeof(uint64_t), cudaMemcpyDeviceToDevice, S(stream)));
+    return SB200_OK;
+}
+extern "C" int sb200_server_load_db_random(sb200_server *s, uint64_t seed) {
+    // synthetic database for benchmarks: uniform plaintext coefficients generated on the host in chunks
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    const size_t total_local = s->dim0 * s->local_num_per, chunk = 2048;
+    std::vector<uint16_t> h(chunk * 4 * kN);
+    uint64_t x = seed * 0x9e3779b97f4a7c15ull + 0x1234567ull;
+    const uint32_t p_db = (uint32_t)s->prm.p_db;
+    for (size_t o = 0; o < total_local; o += chunk) {
+        const size_t n = std::min(chunk, total_local - o);
+        for (size_t i = 0; i < n * 4 * kN; i += 4) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;                    // xorshift64
+            h[i] = (uint16_t)((x & 0xffff) % p_db); h[i + 1] = (uint16_t)(((x >> 16) & 0xffff) % p_db);
+            h[i + 2] = (uint16_t)(((x >> 32) & 0xffff) % p_db); h[i + 3] = (uint16_t)((x >> 48) % p_db);
+        }
+        TRY(sb200_server_load_db_items(s, h.data(), o, n));
+    }
     return SB200_OK;
 }
 static void fold_rounds(sb200_server *s, uint64_t *cts, size_t count, size_t first_dim, cudaStream_t st) {

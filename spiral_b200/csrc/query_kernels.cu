@@ -32,14 +32,21 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
     const int slot = blockIdx.x, row = blockIdx.y, i = active[slot];
     uint32_t v[16];
     if (i < num_in) {
+        // the reference writes cv[2^r + i] = x^(-2^r) * cv[i] whenever i is processed, even if 2^r + i
+        // itself is skipped later in the round (src/spiral.cpp:1709) - so the producer stores it
+        uint32_t w[16], nb[16];
         load_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
+        load_ntt_regs(w, neg1 + n * kN, lt);
+#pragma unroll
+        for (int e = 0; e < 16; e++) nb[e] = mulmod(v[e], w[e], n);
+        store_ntt_regs(nb, cv + (((size_t)(i + num_in) * 2 + row) * 2 + n) * kN, lt);
     } else {
+        // same product recomputed locally: no dependence on the producer CTA of this launch
         uint32_t a[16], w[16];
         load_ntt_regs(a, cv + (((size_t)(i - num_in) * 2 + row) * 2 + n) * kN, lt);
         load_ntt_regs(w, neg1 + n * kN, lt);
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = mulmod(a[e], w[e], n);
-        store_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
     }
     ntt_inverse_plane(v, sm[n], lt, n);
     __syncthreads();

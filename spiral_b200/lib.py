@@ -108,6 +108,10 @@ def load_library():
         "sb200_server_expand_and_convert": (C.c_int, [vp, vp]),
         "sb200_server_first_dim": (C.c_int, [vp, vp]),
         "sb200_server_fold_local": (C.c_int, [vp, vp]),
+        "sb200_server_scan": (C.c_int, [vp, vp]),
+        "sb200_server_lift": (C.c_int, [vp, vp]),
+        "sb200_server_copy_partial": (C.c_int, [vp, vp, vp]),
+        "sb200_server_load_db_random": (C.c_int, [vp, C.c_uint64]),
         "sb200_server_partial_ct": (vp, [vp]),
         "sb200_server_fold_tail": (C.c_int, [vp, vp, vp, vp]),
         "sb200_server_download": (C.c_int, [vp, vp, vp, sz, vp]),

@@ -1,0 +1,117 @@
+"""Host-side mirror of the reference's server entry points for the Spiral path.
+
+`SpiralServer` keeps the database and the client's public parameters resident in HBM and answers
+queries; it is a thin Python face over the tier-3 C-ABI (sb200_server_*), which is the same code a
+C++ host (spiral_b200/csrc/host_mirror.cpp) drives.  Names follow the reference:
+process_query_fast (src/spiral.cpp:1584) = first_dim + fold; runConversionImproved (:2040) =
+expand_and_convert.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .lib import SpiralParams, check, load_library
+
+N = 2048
+_P64 = C.POINTER(C.c_uint64)
+_P16 = C.POINTER(C.c_uint16)
+
+
+def _p64(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_P64)
+
+
+class SpiralServer:
+    def __init__(self, params: SpiralParams, device=0, rank=0, world=1):
+        self.lib = load_library()
+        self.params = params
+        self.rank, self.world = rank, world
+        self.dim0, self.num_per = 1 << params.nu1, 1 << params.nu2
+        self.local_num_per = self.num_per // world
+        h = C.c_void_p()
+        check(self.lib.sb200_server_create(C.byref(h), C.byref(params), device, rank, world), self.lib)
+        self.h = h
+
+    # ---- database -----------------------------------------------------------------------
+    def load_db_items(self, pts_u16, item_begin=0):
+        """pts_u16: (items, 4, 2048) uint16, this shard's items in j-major order (load_db, src/spiral.cpp:1028)."""
+        pts_u16 = np.ascontiguousarray(pts_u16, dtype=np.uint16)
+        check(self.lib.sb200_server_load_db_items(self.h, pts_u16.ctypes.data_as(_P16), item_begin, pts_u16.shape[0]), self.lib)
+
+    def load_db_reference(self, B):
+        """B: the reference's own database buffer (layout of src/spiral.cpp:1139-1153)."""
+        check(self.lib.sb200_server_load_db_reference(self.h, _p64(B)), self.lib)
+
+    def shard_items(self, pts):
+        """Select + order this shard's items from the full item-major plaintext array."""
+        idx = [j * self.num_per + ii for j in range(self.dim0) for ii in range(self.rank, self.num_per, self.world)]
+        return pts[idx]
+
+    # ---- public parameters --------------------------------------------------------------
+    def set_public_params(self, W_exp_left, W_exp_right, W_conv, V_conv):
+        check(self.lib.sb200_server_set_public_params(self.h, _p64(W_exp_left), _p64(W_exp_right), _p64(W_conv), _p64(V_conv)), self.lib)
+
+    # ---- query answering -----------------------------------------------------------------
+    def answer(self, query_cv, stream=None):
+        """Host query (2x1 ref-NTT, 64 KiB) -> host response (3x2 raw, row 0 mod q', rows 1-2 mod 4p)."""
+        resp = np.empty(6 * N, dtype=np.uint64)
+        check(self.lib.sb200_server_answer(self.h, query_cv.ctypes.data, resp.ctypes.data, stream), self.lib)
+        return resp
+
+    def upload_query(self, query_cv, stream=None):
+        check(self.lib.sb200_server_upload_query(self.h, query_cv.ctypes.data, stream), self.lib)
+
+    def upload_query_ptr(self, host_ptr, stream=None):
+        """host_ptr: address of a (preferably pinned) 64 KiB ref-NTT query ciphertext."""
+        check(self.lib.sb200_server_upload_query(self.h, host_ptr, stream), self.lib)
+
+    def expand_and_convert(self, stream=None):
+        check(self.lib.sb200_server_expand_and_convert(self.h, stream), self.lib)
+
+    def first_dim(self, stream=None):
+        check(self.lib.sb200_server_first_dim(self.h, stream), self.lib)
+
+    def scan(self, stream=None):
+        check(self.lib.sb200_server_scan(self.h, stream), self.lib)
+
+    def lift(self, stream=None):
+        check(self.lib.sb200_server_lift(self.h, stream), self.lib)
+
+    def copy_partial(self, dst_ptr, stream=None):
+        check(self.lib.sb200_server_copy_partial(self.h, dst_ptr, stream), self.lib)
+
+    def load_db_random(self, seed=1):
+        check(self.lib.sb200_server_load_db_random(self.h, seed), self.lib)
+
+    def fold_local(self, stream=None):
+        check(self.lib.sb200_server_fold_local(self.h, stream), self.lib)
+
+    def partial_ct_ptr(self):
+        return self.lib.sb200_server_partial_ct(self.h)
+
+    def fold_tail(self, gathered_ptr, resp_ptr, stream=None):
+        check(self.lib.sb200_server_fold_tail(self.h, gathered_ptr, resp_ptr, stream), self.lib)
+
+    def download(self, dev_ptr, words, stream=None):
+        out = np.empty(words, dtype=np.uint64)
+        check(self.lib.sb200_server_download(self.h, out.ctypes.data, dev_ptr, words, stream), self.lib)
+        return out
+
+    def first_dim_cts(self, stream=None):
+        return self.download(self.lib.sb200_server_first_dim_cts(self.h), self.local_num_per * 6 * N, stream)
+
+    @property
+    def db_bytes(self):
+        return self.dim0 * self.local_num_per * 4 * N * 8
+
+    def close(self):
+        if self.h:
+            self.lib.sb200_server_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

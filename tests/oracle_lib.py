@@ -90,6 +90,14 @@ def load():
     lib.so_to_ntt.argtypes = [u64p, u64p, sz]
     lib.so_from_ntt.argtypes = [u64p, u64p, sz]
     lib.so_get_rescaled.argtypes = [u64p, u64p, sz, C.c_uint64, C.c_uint64]
+    lib.so_client_new.restype = C.c_void_p
+    lib.so_client_new.argtypes = [C.POINTER(SoParams), C.c_uint64, C.c_int]
+    lib.so_client_free.argtypes = [C.c_void_p]
+    lib.so_client_w_exp_right_count.restype = sz
+    lib.so_client_w_exp_right_count.argtypes = [C.POINTER(SoParams)]
+    lib.so_client_spiral_pub_params.argtypes = [C.c_void_p, u64p, u64p, u64p, u64p]
+    lib.so_client_spiral_query.argtypes = [C.c_void_p, sz, u64p]
+    lib.so_client_spiral_decode.argtypes = [C.c_void_p, u64p, u64p]
     _lib = lib
     return lib
 
@@ -136,3 +144,53 @@ def canon(a, kind):
     lo = (a & np.uint64(0xFFFFFFFF)) % np.uint64(P)
     hi = (a >> np.uint64(32)) % np.uint64(B)
     return lo | (hi << np.uint64(32))
+
+
+class SpiralSession:
+    """Test-side client + CPU reference pipeline for one parameter set (small sizes only)."""
+
+    def __init__(self, lib, cfg, nu1, nu2, seed=1, nonoise=False):
+        self.lib, self.prm = lib, make_params(cfg, nu1, nu2)
+        p = self.prm
+        g, stop = C.c_size_t(), C.c_size_t()
+        lib.so_spiral_expansion_shape(C.byref(p), C.byref(g), C.byref(stop))
+        self.g, self.stopround = g.value, stop.value
+        self.dim0, self.num_per = 1 << nu1, 1 << nu2
+        self.total_n = self.dim0 * self.num_per
+        self.client = lib.so_client_new(C.byref(p), seed, int(nonoise))
+        PL = 2 * N
+        n_right = lib.so_client_w_exp_right_count(C.byref(p))
+        self.W_left = np.zeros(self.g * 2 * p.t_exp * PL, dtype=np.uint64)
+        self.W_right = np.zeros(n_right * 2 * p.t_exp_right * PL, dtype=np.uint64)
+        self.W_conv = np.zeros(3 * 2 * p.t_conv * PL, dtype=np.uint64)
+        self.V_conv = np.zeros(3 * 2 * p.t_conv * PL, dtype=np.uint64)
+        lib.so_client_spiral_pub_params(self.client, ptr(self.W_left), ptr(self.W_right), ptr(self.W_conv), ptr(self.V_conv))
+        rng = np.random.default_rng(seed + 1000)
+        self.pts = rng.integers(0, p.p_db, size=(self.total_n, 4, N), dtype=np.uint64)   # item-major plaintext matrices
+
+    def reference_db(self):
+        Bbuf = np.zeros(self.total_n * 4 * N, dtype=np.uint64)
+        self.lib.so_load_db(ptr(Bbuf), ptr(np.ascontiguousarray(self.pts.reshape(-1))), self.prm.nu1, self.prm.nu2, self.prm.p_db)
+        return Bbuf
+
+    def query(self, idx):
+        q = np.zeros(2 * 2 * N, dtype=np.uint64)
+        self.lib.so_client_spiral_query(self.client, idx, ptr(q))
+        return q
+
+    def oracle_answer(self, q, Bbuf):
+        final_ct = np.zeros(6 * N, dtype=np.uint64)
+        resp = np.zeros(6 * N, dtype=np.uint64)
+        first = np.zeros(self.num_per * 6 * N, dtype=np.uint64)
+        rc = self.lib.so_spiral_answer(C.byref(self.prm), ptr(q), ptr(self.W_left), ptr(self.W_right), ptr(self.W_conv),
+                                       ptr(self.V_conv), ptr(Bbuf), ptr(final_ct), ptr(resp), ptr(first))
+        assert rc == 0
+        return resp, final_ct, first
+
+    def decode(self, resp):
+        out = np.zeros(4 * N, dtype=np.uint64)
+        self.lib.so_client_spiral_decode(self.client, ptr(np.ascontiguousarray(resp)), ptr(out))
+        return out.reshape(4, N)
+
+    def close(self):
+        self.lib.so_client_free(self.client)

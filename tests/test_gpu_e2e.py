@@ -1,0 +1,83 @@
+"""GPU suite: the resident server (tier-3 C-ABI) on real encryptions.
+  * response bit-exact with the oracle's whole pipeline (and the intermediate first-dimension cts)
+  * decoded record == planted record (the reference's "Is correct?: 1" gate)
+  * both database ingest paths (plaintext items, reference-layout buffer) give the same answers
+  * edge indices (first / last record), stopround == 0 and != 0 shapes, odd t_GSW."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from spiral_b200 import SpiralParams
+from spiral_b200.server import SpiralServer
+from tests import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def sb_params(so):
+    return SpiralParams(so.nu1, so.nu2, so.t_gsw, so.t_conv, so.t_exp, so.t_exp_right, so.qp_bits, so.out_n, so.p_db)
+
+
+@pytest.mark.parametrize("cfg,nu1,nu2", [("cfg1", 2, 2), ("cfg1", 4, 1), ("cfg5", 3, 2), ("cfg1", 5, 3), ("cfg1", 6, 2)])
+def test_server_matches_oracle_and_decodes(sb, oracle, cfg, nu1, nu2):
+    s = ol.SpiralSession(oracle, cfg, nu1, nu2, seed=11)
+    Bbuf = s.reference_db()
+    srv = SpiralServer(sb_params(s.prm))
+    srv.load_db_items(s.pts.astype(np.uint16))
+    srv.set_public_params(s.W_left, s.W_right, s.W_conv, s.V_conv)
+    for idx in (0, s.total_n - 1, s.total_n // 3):
+        q = s.query(idx)
+        want_resp, _, want_first = s.oracle_answer(q, Bbuf)
+        got = srv.answer(q)
+        assert np.array_equal(got, want_resp), f"response differs at idx {idx}"
+        assert np.array_equal(s.decode(got), s.pts[idx]), f"decode failed at idx {idx}"
+    srv.close()
+    s.close()
+
+
+def test_first_dim_tap_and_reference_layout_ingest(sb, oracle):
+    s = ol.SpiralSession(oracle, "cfg1", 4, 2, seed=5)
+    Bbuf = s.reference_db()
+    q = s.query(9)
+    want_resp, _, want_first = s.oracle_answer(q, Bbuf)
+    a = SpiralServer(sb_params(s.prm))
+    a.load_db_reference(Bbuf)                      # the reference's own B buffer
+    a.set_public_params(s.W_left, s.W_right, s.W_conv, s.V_conv)
+    a.upload_query(q)
+    a.expand_and_convert()
+    a.first_dim()
+    assert np.array_equal(a.first_dim_cts(), want_first), "raw cts after the first dimension differ"
+    assert np.array_equal(a.answer(q), want_resp)
+    a.close()
+    s.close()
+
+
+def test_sharded_servers_reproduce_single_gpu_answer(sb, oracle):
+    """world = 2 and 4 on ONE device: strided shards + gather + tail folds == unsharded response."""
+    import torch
+    s = ol.SpiralSession(oracle, "cfg1", 3, 3, seed=9)
+    Bbuf = s.reference_db()
+    q = s.query(41)
+    want_resp, _, _ = s.oracle_answer(q, Bbuf)
+    for world in (2, 4):
+        servers = [SpiralServer(sb_params(s.prm), rank=r, world=world) for r in range(world)]
+        gathered = torch.empty(world * 6 * ol.N, dtype=torch.int64, device="cuda")
+        resp = torch.empty(6 * ol.N, dtype=torch.int64, device="cuda")
+        for r, srv in enumerate(servers):
+            if r % 2 == 0:
+                srv.load_db_items(srv.shard_items(s.pts).astype(np.uint16))
+            else:
+                srv.load_db_reference(Bbuf)
+            srv.set_public_params(s.W_left, s.W_right, s.W_conv, s.V_conv)
+            srv.upload_query(q); srv.expand_and_convert(); srv.first_dim(); srv.fold_local()
+            torch.cuda.synchronize()
+            part = torch.from_numpy(srv.download(srv.partial_ct_ptr(), 6 * ol.N).view(np.int64)).cuda()
+            gathered[r * 6 * ol.N:(r + 1) * 6 * ol.N] = part
+        servers[0].fold_tail(gathered.data_ptr(), resp.data_ptr())
+        torch.cuda.synchronize()
+        got = resp.cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, want_resp), f"world={world}"
+        for srv in servers:
+            srv.close()
+    s.close()
