@@ -53,6 +53,10 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
 void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,
                        int t_gsw, uint32_t *scratch, cudaStream_t s);
 size_t fold_scratch_words(size_t num_per_half, int t_gsw);
+size_t fold_scratch_words_generic(size_t cts_in, int R, int Cc, int t);
+// R x Cc ciphertexts, `planes` independent planes (plane p's ciphertexts start at p*plane_stride), signed (Spiral) or unsigned (Pack) digits
+void launch_fold_round_generic(uint64_t *cts, int R, int Cc, int t, int is_signed, size_t np_after, size_t planes, size_t plane_stride,
+                               const uint32_t *q_dev, const uint32_t *qneg_dev, uint32_t *scratch, cudaStream_t s);
 void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t count, int t_gsw, cudaStream_t s);
 
 // ---- expansion (reference expandImproved / coefficientExpansion)

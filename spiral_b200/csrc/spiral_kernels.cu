@@ -256,63 +256,89 @@ __device__ __forceinline__ uint64_t signed_digit(uint64_t val, int k, int t, uin
     }
     return piece;
 }
-__global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, int t_gsw) {
+// Generic over the ciphertext shape so the Pack variant (foldCiphertextsDim1, src/testing.cpp:596-624:
+// 2x1 ciphertexts, UNSIGNED gadget_invert digits, out_n^2 planes batched) shares the kernels:
+//   R x Cc ciphertext, GSW is R x (R*t), digit k of input row r lands in row r + k*R.
+struct FoldShape {
+    int R, Cc, t, is_signed;
+    int np;              // ciphertexts per plane AFTER this round
+    int planes;          // independent planes folded by the same GSW ciphertext
+    int plane_stride;    // ciphertexts between consecutive planes in `cts`
+};
+__global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, FoldShape fs, int cts_per_plane) {
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
-    const int ctpoly = blockIdx.x, k = blockIdx.y;          // ctpoly = ct*6 + r*2 + c
-    const int ct = ctpoly / 6, r = (ctpoly % 6) >> 1, c = ctpoly & 1;
-    const uint32_t bits_per = get_bits_per(t_gsw);
-    const uint64_t *src = cts + (size_t)ctpoly * kN;
+    const int RC = fs.R * fs.Cc;
+    const int ctpoly = blockIdx.x, k = blockIdx.y;          // ctpoly = (plane*cts_per_plane + ct)*RC + r*Cc + c
+    const int ctd = ctpoly / RC, rc = ctpoly % RC, r = rc / fs.Cc, c = rc % fs.Cc;
+    const int plane = ctd / cts_per_plane, ctl = ctd % cts_per_plane;
+    const uint32_t bits_per = get_bits_per(fs.t);
+    const uint64_t mask = (1ull << bits_per) - 1;
+    const uint64_t *src = cts + ((size_t)(plane * fs.plane_stride + ctl) * RC + rc) * kN;
     uint32_t v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = raw_to_res(signed_digit(__ldg(src + nat_pos(lt, e)), k, t_gsw, bits_per), n);
+    for (int e = 0; e < 16; e++) {
+        const uint64_t val = __ldg(src + nat_pos(lt, e));
+        const uint64_t d = fs.is_signed ? signed_digit(val, k, fs.t, bits_per) : gadget_digit(val, k, bits_per, mask);
+        v[e] = raw_to_res(d, n);
+    }
     ntt_forward_plane(v, sm[n], lt, n);
-    const int m2 = kN1 * t_gsw, row = r + k * kN1;
-    store_ntt_regs(v, scratch + ((((size_t)ct * m2 + row) * kN2 + c) * 2 + n) * kN, lt);
+    const int m2 = fs.R * fs.t, row = r + k * fs.R;
+    store_ntt_regs(v, scratch + ((((size_t)ctd * m2 + row) * fs.Cc + c) * 2 + n) * kN, lt);
 }
 __global__ void __launch_bounds__(kNttThreads) k_fold_mac_intt(uint64_t *__restrict__ cts, const uint32_t *__restrict__ scratch,
                                                                const uint32_t *__restrict__ q_dev, const uint32_t *__restrict__ qneg_dev,
-                                                               int num_per, int t_gsw) {
+                                                               FoldShape fs) {
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
-    const int i = blockIdx.x / 6, r = (blockIdx.x % 6) >> 1, c = blockIdx.x & 1;
-    const int m2 = kN1 * t_gsw;
+    const int RC = fs.R * fs.Cc;
+    const int id = blockIdx.x / RC, rc = blockIdx.x % RC, r = rc / fs.Cc, c = rc % fs.Cc;
+    const int plane = id / fs.np, i = id % fs.np;
+    const int m2 = fs.R * fs.t;
     uint64_t acc[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) acc[e] = 0;
     for (int h = 0; h < 2; h++) {
-        const int ct = h == 0 ? i : num_per + i;
+        const int ctd = plane * 2 * fs.np + (h == 0 ? i : fs.np + i);      // dense index used by the decomposition
         const uint32_t *Qm = (h == 0 ? qneg_dev : q_dev) + ((size_t)r * m2 * 2 + n) * kN;
-        const uint32_t *Cm = scratch + ((((size_t)ct * m2) * kN2 + c) * 2 + n) * kN;
+        const uint32_t *Cm = scratch + ((((size_t)ctd * m2) * fs.Cc + c) * 2 + n) * kN;
         for (int m = 0; m < m2; m++) {
             uint32_t a[16], b[16];
             load_ntt_regs(a, Qm + (size_t)m * 2 * kN, lt);
-            load_ntt_regs(b, Cm + (size_t)m * kN2 * 2 * kN, lt);
+            load_ntt_regs(b, Cm + (size_t)m * fs.Cc * 2 * kN, lt);
 #pragma unroll
             for (int e = 0; e < 16; e++) acc[e] += (uint64_t)a[e] * b[e];
+            if ((m & 127) == 127) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) acc[e] = reduce_u64(acc[e], n);
+            }
         }
 #pragma unroll
-        for (int e = 0; e < 16; e++) acc[e] = reduce_u64(acc[e], n);     // keeps 2*m2 > 256 safe
+        for (int e = 0; e < 16; e++) acc[e] = reduce_u64(acc[e], n);     // < q: the two halves never overflow together
     }
     uint32_t v[16];
-    const uint32_t q = modulus(n);
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = csub((uint32_t)acc[e], q);       // acc < 2q after the two partial reductions
-    // (the h = 0 partial result was already < q and h = 1 adds products before reducing again, so acc < q)
-    // inverse NTT + CRT lift, written over ciphertext i
-    {
-        ntt_inverse_plane(v, sm[n], lt, n);
-        __syncthreads();
+    for (int e = 0; e < 16; e++) v[e] = (uint32_t)acc[e];
+    // inverse NTT + CRT lift, written over ciphertext i of this plane
+    ntt_inverse_plane(v, sm[n], lt, n);
+    __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
-        __syncthreads();
-        uint64_t *dst = cts + ((size_t)i * 6 + r * 2 + c) * kN;
+    for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
+    __syncthreads();
+    uint64_t *dst = cts + ((size_t)(plane * fs.plane_stride + i) * RC + rc) * kN;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int z = threadIdx.x + 256 * k;
-            dst[z] = crt_compose(sm[0][z], sm[1][z]);
-        }
+    for (int k = 0; k < 8; k++) {
+        int z = threadIdx.x + 256 * k;
+        dst[z] = crt_compose(sm[0][z], sm[1][z]);
     }
+}
+size_t fold_scratch_words_generic(size_t cts_in, int R, int Cc, int t) { return cts_in * (size_t)R * t * Cc * 2 * kN; }
+void launch_fold_round_generic(uint64_t *cts, int R, int Cc, int t, int is_signed, size_t np_after, size_t planes, size_t plane_stride,
+                               const uint32_t *q_dev, const uint32_t *qneg_dev, uint32_t *scratch, cudaStream_t s) {
+    FoldShape fs{R, Cc, t, is_signed, (int)np_after, (int)planes, (int)plane_stride};
+    const int RC = R * Cc, cpp = (int)(2 * np_after);
+    count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(planes * cpp * RC), t), kNttThreads, 0, s>>>(scratch, cts, fs, cpp);
+    count_launch(); k_fold_mac_intt<<<(unsigned)(planes * np_after * RC), kNttThreads, 0, s>>>(cts, scratch, q_dev, qneg_dev, fs);
 }
 // reference reorient_Q layout (packed [z][r*m2 + m], src/spiral.cpp:388-400) -> dev-NTT [r*m2 + m][n][z]
 __global__ void k_unreorient_q(uint32_t *__restrict__ out, const uint64_t *__restrict__ q_reor, int rm_count) {
@@ -330,15 +356,15 @@ void launch_unreorient_q(uint32_t *out, const uint64_t *q_reor, int rm_count, cu
 // scan layout -> reference layout (inverse of launch_db_from_reference), whole database
 void launch_db_to_reference(uint64_t *B_ref, const uint64_t *db, size_t dim0, size_t ic, cudaStream_t s);
 
-size_t fold_scratch_words(size_t num_per_half, int t_gsw) { return 2 * num_per_half * (size_t)kN1 * t_gsw * kN2 * 2 * kN; }
+size_t fold_scratch_words(size_t num_per_half, int t_gsw) { return fold_scratch_words_generic(2 * num_per_half, kN1, kN2, t_gsw); }
 // split_and_crt alone (reference src/spiral.cpp:270-341) on `count` ciphertexts: scratch[ct][m][c] dev-NTT
 void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t count, int t_gsw, cudaStream_t s) {
-    if (count) { count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(count * 6), t_gsw), kNttThreads, 0, s>>>(scratch, cts, t_gsw); }
+    FoldShape fs{kN1, kN2, t_gsw, 1, (int)count, 1, (int)count};
+    if (count) { count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(count * 6), t_gsw), kNttThreads, 0, s>>>(scratch, cts, fs, (int)count); }
 }
 void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,
                        int t_gsw, uint32_t *scratch, cudaStream_t s) {
-    count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(2 * num_per * 6), t_gsw), kNttThreads, 0, s>>>(scratch, cts, t_gsw);
-    count_launch(); k_fold_mac_intt<<<(unsigned)(num_per * 6), kNttThreads, 0, s>>>(cts, scratch, q_dev, qneg_dev, (int)num_per, t_gsw);
+    launch_fold_round_generic(cts, kN1, kN2, t_gsw, 1, num_per, 1, 2 * num_per, q_dev, qneg_dev, scratch, s);
 }
 
 }  // namespace sb200
