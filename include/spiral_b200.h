@@ -108,6 +108,17 @@ int sb200_scalToMat(uint64_t *out_reg, const uint64_t *cv, const uint64_t *W, ui
 int sb200_regevToGSW(uint64_t *out, const uint64_t *cv_v, uint32_t t_conv, uint32_t t, const uint64_t *W,
                      const uint64_t *V);                                                            /* src/spiral.cpp:1985-2025 */
 
+/* SpiralPack / SpiralStreamPack leaves (src/testing.cpp) */
+int sb200_convertDb(uint64_t *db_buf, const uint64_t *db_ref_ntt, size_t count, size_t dim0, size_t num_per);          /* :316-340 */
+int sb200_reorientCiphertextsDim1(uint64_t *out, const uint64_t *v_firstdim, size_t count, size_t dim0, size_t idx_factor); /* :342-362 */
+int sb200_fastMultiplyQueryByDatabaseDim1(uint64_t *out_ref_ntt, const uint64_t *db, const uint64_t *v_firstdim,
+                                          size_t dim0, size_t num_per);                                                   /* :364-593 */
+/* v_cts: count cts (2x1 raw), result left in v_cts[0]; v_folding / v_folding_neg: log2(count) x (2 x 2*ell) ref-NTT */
+int sb200_foldCiphertextsDim1(uint64_t *v_cts, size_t count, const uint64_t *v_folding, const uint64_t *v_folding_neg, uint32_t ell); /* :596-624 */
+int sb200_regevToSimpleGsw(uint64_t *v_gsw, const uint64_t *v_inp, size_t count_inp, const uint64_t *V, uint32_t t_conv,
+                           uint32_t ell, uint32_t further_dims, size_t idx_factor, size_t idx_offset);                  /* :108-140 */
+int sb200_pack(uint64_t *result_ref_ntt, uint32_t out_n, uint32_t t_conv, const uint64_t *v_ct_raw, const uint64_t *v_W); /* :198-241 */
+
 /* ---- tier 3: resident server ----------------------------------------------------------- */
 typedef struct sb200_server sb200_server;
 /* shard `rank` of `world` owns second-dimension indices ii = rank (mod world); world = 1 -> whole database */
@@ -142,6 +153,27 @@ int sb200_server_download(sb200_server *srv, uint64_t *dst_host, const uint64_t 
 uint64_t *sb200_server_first_dim_cts(sb200_server *srv);
 size_t sb200_server_query_bytes(const sb200_server *srv);
 size_t sb200_server_response_bytes(const sb200_server *srv);
+
+
+/* ---- tier 3, Pack variants (testHighRate, src/testing.cpp:777-1155; server statements :1007-1081) ---- */
+typedef struct sb200_pack_server sb200_pack_server;
+int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device);
+void sb200_pack_server_destroy(sb200_pack_server *srv);
+/* one of the out_n^2 database planes: 2^(nu1+nu2) items of one polynomial each (u16 coefficients < p_db) */
+int sb200_pack_server_load_plane_items(sb200_pack_server *srv, size_t plane, const uint16_t *pts_host);
+int sb200_pack_server_load_plane_reference(sb200_pack_server *srv, size_t plane, const uint64_t *db_buf_host);   /* convertDb layout */
+int sb200_pack_server_load_random(sb200_pack_server *srv, uint64_t seed);
+/* W_exp_left g x (2 x t_exp), W_exp_right (stopround+1) x (2 x t_exp_right), V 2 x 2*t_conv (all three may be NULL for
+ * direct-upload clients), v_W out_n x ((out_n+1) x t_conv); ref-NTT host buffers */
+int sb200_pack_server_set_public_params(sb200_pack_server *srv, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
+                                        const uint64_t *V, const uint64_t *v_W);
+/* total_resp: (out_n+1) x out_n raw; result_cts (optional): out_n^2 folded cts (2x1 raw) before packing */
+int sb200_pack_server_answer(sb200_pack_server *srv, const uint64_t *query_cv_host, uint64_t *total_resp_host,
+                             uint64_t *result_cts_host, void *stream);
+int sb200_pack_server_answer_direct(sb200_pack_server *srv, const uint64_t *v_firstdim_host, const uint64_t *v_folding_host,
+                                    uint64_t *total_resp_host, uint64_t *result_cts_host, void *stream);
+size_t sb200_pack_server_db_bytes(const sb200_pack_server *srv);
+size_t sb200_pack_server_response_words(const sb200_pack_server *srv);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,241 @@
+// pack_kernels.cu - SpiralPack / SpiralStreamPack server path (reference src/testing.cpp): 2x1 Regev
+// ciphertexts, 1x1 plaintexts, out_n^2 database planes, packing into one (out_n+1) x out_n response.
+//
+// Reference functions replaced:
+//   convertDb                         src/testing.cpp:316-340  -> k_db_build_pack / transpose from the reference layout
+//   reorientCiphertextsDim1           src/testing.cpp:342-362  -> k_reorient_dim1
+//   fastMultiplyQueryByDatabaseDim1   src/testing.cpp:364-593  -> k_scan_pack
+//   foldCiphertextsDim1               src/testing.cpp:596-624  -> generic fold kernels (spiral_kernels.cu), unsigned digits
+//   regevToSimpleGsw + negation       src/testing.cpp:108-140, 1027-1032 -> k_simple_gsw_accum + k_gsw_negate
+//   pack                              src/testing.cpp:198-241  -> k_pack_accum
+#include "kernels.cuh"
+#include "ntt.cuh"
+
+namespace sb200 {
+
+__device__ __forceinline__ uint4 ld_stream_u4p(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack_pb3(uint32_t p, uint32_t b) { return (uint64_t)p | ((uint64_t)b << 32); }
+
+// ============================================================================================
+// Database.  Scan layout per plane: DBP[z][jp][i][s] PB64, jp = j/2, s = j&1, item = j*num_per + i.
+// Consecutive threads (i) read consecutive 16-byte (j even, j odd) pairs.
+// ============================================================================================
+__global__ void __launch_bounds__(kNttThreads) k_db_build_pack(uint64_t *__restrict__ db, const uint16_t *__restrict__ pts,
+                                                               int dim0, int num_per, uint32_t p_db) {
+    extern __shared__ __align__(16) uint32_t dyn[];
+    uint32_t(*sm)[kPlaneWords] = reinterpret_cast<uint32_t(*)[kPlaneWords]>(dyn);
+    uint32_t *stash = dyn + 2 * kPlaneWords;                       // [s*2 + ipar][n][z]
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const uint32_t q = modulus(n);
+    const int ih = blockIdx.x, jp = blockIdx.y;                    // i = 2*ih + ipar, j = 2*jp + s
+    for (int poly = 0; poly < 4; poly++) {
+        const int s = poly >> 1, ipar = poly & 1;
+        const size_t item = (size_t)(2 * jp + s) * num_per + (2 * ih + ipar);
+        const uint16_t *src = pts + item * kN;
+        uint32_t v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint32_t c = src[nat_pos(lt, k)];                      // centre-lift as src/testing.cpp:857-868
+            v[k] = (c >= p_db / 2) ? (q - ((p_db - c) % q)) % q : c % q;
+        }
+        ntt_forward_plane(v, sm[n], lt, n);
+        store_ntt_regs(v, stash + (poly * 2 + n) * kN, lt);
+    }
+    __syncthreads();
+    const size_t JP = dim0 / 2;
+    for (int z = threadIdx.x; z < kN; z += kNttThreads) {
+        ulonglong2 a, b;        // i even: (s=0, s=1) ; i odd: (s=0, s=1)
+        a.x = pack_pb3(stash[(0 * 2 + 0) * kN + z], stash[(0 * 2 + 1) * kN + z]);
+        a.y = pack_pb3(stash[(2 * 2 + 0) * kN + z], stash[(2 * 2 + 1) * kN + z]);
+        b.x = pack_pb3(stash[(1 * 2 + 0) * kN + z], stash[(1 * 2 + 1) * kN + z]);
+        b.y = pack_pb3(stash[(3 * 2 + 0) * kN + z], stash[(3 * 2 + 1) * kN + z]);
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(db) + ((size_t)z * JP + jp) * num_per + 2 * ih;
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+void launch_db_build_pack(uint64_t *db_plane, const uint16_t *pts_plane, size_t dim0, size_t num_per, uint32_t p_db, cudaStream_t s) {
+    const size_t smem = (2 * kPlaneWords + 4 * 2 * kN) * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_db_build_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    count_launch(); k_db_build_pack<<<dim3((unsigned)(num_per / 2), (unsigned)(dim0 / 2)), kNttThreads, smem, s>>>(db_plane, pts_plane, (int)dim0, (int)num_per, p_db);
+}
+
+// ============================================================================================
+// reorientCiphertextsDim1: selected 2x1 dev-NTT cts -> query[z][j][r] PB64
+// ============================================================================================
+__global__ void k_reorient_dim1(uint64_t *__restrict__ out, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx, int dim0) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (j, z), z fastest
+    if (idx >= (size_t)dim0 * kN) return;
+    const int z = (int)(idx % kN), j = (int)(idx / kN);
+    const uint32_t *ct = cv + (size_t)ct_idx[j] * 2 * 2 * kN;
+    ulonglong2 w;
+    w.x = pack_pb3(ct[z], ct[kN + z]);
+    w.y = pack_pb3(ct[2 * kN + z], ct[3 * kN + z]);
+    reinterpret_cast<ulonglong2 *>(out)[(size_t)z * dim0 + j] = w;
+}
+void launch_reorient_dim1(uint64_t *out, const uint32_t *cv, const int *ct_idx, size_t dim0, cudaStream_t s) {
+    const size_t n = dim0 * kN;
+    count_launch(); k_reorient_dim1<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, cv, ct_idx, (int)dim0);
+}
+
+// ============================================================================================
+// First-dimension scan, Pack variant (fastMultiplyQueryByDatabaseDim1):
+//   out[plane][i][r][n][z] = sum_j query[z][j][r]_n * DBP[plane][z][j][i]_n      (4 MACs per 8 bytes)
+// CTA = 256 threads on one (plane, z): thread = (js, i) with i the fast index; with few i-columns
+// (SpiralStreamPack: num_per = 8) the j axis is split over JS = 256/ICT thread groups and the partial
+// sums are combined through shared memory, so every lane still streams 16-byte pairs.
+// ============================================================================================
+constexpr int kPackScanThreads = 256;
+__global__ void __launch_bounds__(kPackScanThreads) k_scan_pack(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
+                                                                const uint64_t *__restrict__ db, int dim0, int IC, int ICT, int JC,
+                                                                size_t plane_words, size_t out_plane_polys) {
+    extern __shared__ __align__(16) uint4 qs[];        // [JC pairs][2] uint4, later reused for the reduction
+    const int tid = threadIdx.x, JS = kPackScanThreads / ICT;
+    const int i = tid % ICT, js = tid / ICT;
+    const int z = blockIdx.x, i0 = blockIdx.y * ICT, plane = blockIdx.z;
+    const int JP = dim0 / 2;
+    const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+    uint64_t acc[2][2] = {{0, 0}, {0, 0}};
+    const uint4 *dbz = reinterpret_cast<const uint4 *>(db + plane * plane_words) + ((size_t)z * JP) * IC + i0 + i;
+    const uint4 *qg = reinterpret_cast<const uint4 *>(query) + (size_t)z * JP * 2;
+    int since_fold = 0;
+    for (int jc0 = 0; jc0 < JP; jc0 += JC) {
+        __syncthreads();
+        for (int e = tid; e < JC * 2; e += kPackScanThreads) qs[e] = __ldg(qg + (size_t)jc0 * 2 + e);
+        __syncthreads();
+#pragma unroll 8
+        for (int jj = js; jj < JC; jj += JS) {
+            const uint4 d = ld_stream_u4p(dbz + (size_t)(jc0 + jj) * IC);      // (j0.p, j0.b, j1.p, j1.b)
+            const uint4 q0 = qs[jj * 2], q1 = qs[jj * 2 + 1];                  // j0:(r0.p r0.b r1.p r1.b), j1
+            acc[0][0] += (uint64_t)q0.x * d.x;  acc[0][1] += (uint64_t)q0.y * d.y;
+            acc[1][0] += (uint64_t)q0.z * d.x;  acc[1][1] += (uint64_t)q0.w * d.y;
+            acc[0][0] += (uint64_t)q1.x * d.z;  acc[0][1] += (uint64_t)q1.y * d.w;
+            acc[1][0] += (uint64_t)q1.z * d.z;  acc[1][1] += (uint64_t)q1.w * d.w;
+            if (++since_fold == 60) {
+                since_fold = 0;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    acc[r][0] = (acc[r][0] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[r][0] >> 32) * c32p;
+                    acc[r][1] = (acc[r][1] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[r][1] >> 32) * c32b;
+                }
+            }
+        }
+    }
+    uint32_t red[4] = {reduce_u64(acc[0][0], 0), reduce_u64(acc[0][1], 1), reduce_u64(acc[1][0], 0), reduce_u64(acc[1][1], 1)};
+    if (JS > 1) {
+        __syncthreads();
+        uint4 *rs = qs;                               // [js][i]
+        rs[js * ICT + i] = make_uint4(red[0], red[1], red[2], red[3]);
+        __syncthreads();
+        if (js == 0) {
+            uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (int k = 0; k < JS; k++) { const uint4 v = rs[k * ICT + i]; s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w; }
+            red[0] = reduce_u64(s0, 0); red[1] = reduce_u64(s1, 1); red[2] = reduce_u64(s2, 0); red[3] = reduce_u64(s3, 1);
+        }
+    }
+    if (js == 0) {
+        uint32_t *o = out + ((size_t)plane * out_plane_polys + (size_t)(i0 + i) * 2) * 2 * kN + z;
+        o[0] = red[0]; o[kN] = red[1];                // row 0: planes p, b
+        o[2 * kN] = red[2]; o[3 * kN] = red[3];       // row 1
+    }
+}
+void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, size_t planes,
+                      size_t db_plane_words, size_t out_plane_polys, cudaStream_t s) {
+    const int IC = (int)num_per;
+    const int ICT = IC < kPackScanThreads ? IC : kPackScanThreads;
+    const int JP = (int)dim0 / 2, JS = kPackScanThreads / ICT;
+    int JC = JP;
+    while ((size_t)JC * 32 > 32768) JC >>= 1;
+    size_t smem = (size_t)JC * 32;
+    const size_t red = (size_t)JS * ICT * 16;
+    if (red > smem) smem = red;
+    dim3 grid(kN, IC / ICT, (unsigned)planes);
+    count_launch(); k_scan_pack<<<grid, kPackScanThreads, smem, s>>>(out, query, db, (int)dim0, IC, ICT, JC, db_plane_words, out_plane_polys);
+}
+
+// ============================================================================================
+// regevToSimpleGsw accumulate:  gsw[d] (2 x 2*ell):  col 2j+1 = c_inp ; col 2j = V (2 x 2*t_conv) * ginv
+// ginv: [2*t_conv][nbits] polys (row jj + 2k), bit index b = d*ell + j
+// ============================================================================================
+__global__ void k_simple_gsw_accum(uint32_t *__restrict__ gsw, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
+                                   const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ V, int t_conv, int ell, int nu2) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b, n, z)
+    const int nbits = ell * nu2;
+    if (idx >= (size_t)nbits * 2 * kN) return;
+    const int nz = (int)(idx % (2 * kN)), b = (int)(idx / (2 * kN)), n = nz >= kN;
+    const int d = b / ell, j = b % ell, mc2 = 2 * t_conv, cols = 2 * ell;
+    uint64_t acc[2] = {0, 0};
+    for (int m = 0; m < mc2; m++) {
+        const uint32_t g = ginv[((size_t)m * nbits + b) * 2 * kN + nz];
+        acc[0] += (uint64_t)V[((size_t)0 * mc2 + m) * 2 * kN + nz] * g;
+        acc[1] += (uint64_t)V[((size_t)1 * mc2 + m) * 2 * kN + nz] * g;
+        if ((m & 127) == 127) { acc[0] = reduce_u64(acc[0], n); acc[1] = reduce_u64(acc[1], n); }
+    }
+    const uint32_t *cin = cv + (size_t)ct_idx[b] * 2 * 2 * kN;
+    uint32_t *o = gsw + (size_t)d * 2 * cols * 2 * kN;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        o[((size_t)r * cols + 2 * j) * 2 * kN + nz] = reduce_u64(acc[r], n);
+        o[((size_t)r * cols + 2 * j + 1) * 2 * kN + nz] = cin[(size_t)r * 2 * kN + nz];
+    }
+}
+// poly_idx: 2*nbits entries (row-0 polys of the bit ciphertexts, then their row-1 polys)
+void launch_regev_to_simple_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx,
+                                int nu2, int ell, const uint32_t *V, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
+    const int nbits = nu2 * ell;
+    if (!nbits) return;
+    launch_from_ntt_indexed(scratch_raw, cv, poly_idx, 2 * (size_t)nbits, s);             // raw as (rdim = 2) x nbits
+    launch_gadget_ntt(scratch_ntt, scratch_raw, 2 * t_conv, 2, nbits, s);
+    const size_t n = (size_t)nbits * 2 * kN;
+    count_launch(); k_simple_gsw_accum<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gsw_out, cv, ct_idx, scratch_ntt, V, t_conv, ell, nu2);
+    if (gsw_neg_out) launch_gsw_negate(gsw_neg_out, gsw_out, nu2, ell, 2, s);
+}
+
+// ============================================================================================
+// pack:  result[row][c] = sum_r ( W_r[row][:] * NTT(G^-1(ct_{r,c} row 0)) ) + [row >= 1] NTT(ct_{row-1,c} row 1)
+// ginv: [t_conv][n*n] polys ; ct2: [n*n] polys (NTT of the second rows) ; v_W: [n][(n+1) x t_conv]
+// ============================================================================================
+__global__ void k_pack_accum(uint32_t *__restrict__ result, const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ ct2,
+                             const uint32_t *__restrict__ vW, int out_n, int t_conv) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row, c, n, z)
+    const int rows = out_n + 1, nn = out_n * out_n;
+    if (idx >= (size_t)rows * out_n * 2 * kN) return;
+    const int nz = (int)(idx % (2 * kN)), rc = (int)(idx / (2 * kN)), n = nz >= kN;
+    const int row = rc / out_n, c = rc % out_n;
+    uint64_t acc = 0;
+    int cnt = 0;
+    for (int r = 0; r < out_n; r++) {
+        const uint32_t *W = vW + ((size_t)r * rows + row) * t_conv * 2 * kN;
+        for (int k = 0; k < t_conv; k++) {
+            acc += (uint64_t)W[(size_t)k * 2 * kN + nz] * ginv[((size_t)k * nn + r * out_n + c) * 2 * kN + nz];
+            if (++cnt == 128) { cnt = 0; acc = reduce_u64(acc, n); }
+        }
+    }
+    if (row >= 1) acc += ct2[((size_t)(row - 1) * out_n + c) * 2 * kN + nz];
+    result[idx] = reduce_u64(acc, n);
+}
+// v_ct_raw: n*n cts (2 polys each: row 0, row 1) raw ; scratch_raw: 2*n*n polys ; scratch_ntt: (t_conv + 1) * n*n polys
+__global__ void k_split_rows(uint64_t *__restrict__ rows01, const uint64_t *__restrict__ cts, int count) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (ct, row, z)
+    if (idx >= (size_t)count * 2 * kN) return;
+    const int z = (int)(idx % kN), row = (int)((idx / kN) & 1), ct = (int)(idx / (2 * kN));
+    rows01[((size_t)row * count + ct) * kN + z] = cts[idx];
+}
+void launch_pack(uint32_t *result, const uint64_t *v_ct_raw, const uint32_t *vW, int out_n, int t_conv,
+                 uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
+    const int nn = out_n * out_n;
+    const size_t n1 = (size_t)nn * 2 * kN;
+    count_launch(); k_split_rows<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(scratch_raw, v_ct_raw, nn);
+    launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, nn, s);                                   // digits of the first rows
+    launch_to_ntt(scratch_ntt + (size_t)t_conv * nn * 2 * kN, scratch_raw + (size_t)nn * kN, nn, s);  // second rows
+    const size_t n2 = (size_t)(out_n + 1) * out_n * 2 * kN;
+    count_launch(); k_pack_accum<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(result, scratch_ntt, scratch_ntt + (size_t)t_conv * nn * 2 * kN, vW, out_n, t_conv);
+}
+
+}  // namespace sb200

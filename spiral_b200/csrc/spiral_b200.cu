@@ -2,4 +2,6 @@
 #include "ntt_kernels.cu"
 #include "spiral_kernels.cu"
 #include "query_kernels.cu"
+#include "pack_kernels.cu"
 #include "api.cu"
+#include "api_pack.cu"

@@ -96,7 +96,23 @@ def load_library():
         "sb200_expandImproved": (C.c_int, [u64p, sz, C.c_uint32, u64p, u64p, C.c_uint32, sz, sz]),
         "sb200_scalToMat": (C.c_int, [u64p, u64p, u64p, C.c_uint32]),
         "sb200_regevToGSW": (C.c_int, [u64p, u64p, C.c_uint32, C.c_uint32, u64p, u64p]),
+        "sb200_convertDb": (C.c_int, [u64p, u64p, sz, sz, sz]),
+        "sb200_reorientCiphertextsDim1": (C.c_int, [u64p, u64p, sz, sz, sz]),
+        "sb200_fastMultiplyQueryByDatabaseDim1": (C.c_int, [u64p, u64p, u64p, sz, sz]),
+        "sb200_foldCiphertextsDim1": (C.c_int, [u64p, sz, u64p, u64p, C.c_uint32]),
+        "sb200_regevToSimpleGsw": (C.c_int, [u64p, u64p, sz, u64p, C.c_uint32, C.c_uint32, C.c_uint32, sz, sz]),
+        "sb200_pack": (C.c_int, [u64p, C.c_uint32, C.c_uint32, u64p, u64p]),
         # tier 3
+        "sb200_pack_server_create": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int]),
+        "sb200_pack_server_destroy": (None, [vp]),
+        "sb200_pack_server_load_plane_items": (C.c_int, [vp, sz, u16p]),
+        "sb200_pack_server_load_plane_reference": (C.c_int, [vp, sz, u64p]),
+        "sb200_pack_server_load_random": (C.c_int, [vp, C.c_uint64]),
+        "sb200_pack_server_set_public_params": (C.c_int, [vp, u64p, u64p, u64p, u64p]),
+        "sb200_pack_server_answer": (C.c_int, [vp, vp, vp, vp, vp]),
+        "sb200_pack_server_answer_direct": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "sb200_pack_server_db_bytes": (sz, [vp]),
+        "sb200_pack_server_response_words": (sz, [vp]),
         "sb200_server_create": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int, C.c_int, C.c_int]),
         "sb200_server_destroy": (None, [vp]),
         "sb200_server_load_db_items": (C.c_int, [vp, u16p, sz, sz]),

@@ -90,6 +90,11 @@ def load():
     lib.so_to_ntt.argtypes = [u64p, u64p, sz]
     lib.so_from_ntt.argtypes = [u64p, u64p, sz]
     lib.so_get_rescaled.argtypes = [u64p, u64p, sz, C.c_uint64, C.c_uint64]
+    lib.so_pack_answer.restype = C.c_int
+    lib.so_pack_answer.argtypes = [C.POINTER(SoParams), C.c_int] + [u64p] * 10
+    lib.so_pack_expansion_shape.argtypes = [C.POINTER(SoParams), C.POINTER(sz), C.POINTER(sz)]
+    lib.so_convert_db.argtypes = [u64p, u64p, sz, sz, sz]
+    lib.so_encode_plaintext.argtypes = [u64p, u64p, sz, C.c_uint64]
     lib.so_client_new.restype = C.c_void_p
     lib.so_client_new.argtypes = [C.POINTER(SoParams), C.c_uint64, C.c_int]
     lib.so_client_free.argtypes = [C.c_void_p]

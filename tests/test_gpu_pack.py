@@ -1,0 +1,92 @@
+"""GPU suite: SpiralPack / SpiralStreamPack resident server against the oracle's whole Pack pipeline
+(so_pack_answer = testHighRate's server statements).  Inputs are uniform ring elements of the right
+shapes: the arithmetic is exact, so equality on arbitrary inputs is the strongest parity statement;
+both database ingest paths and both query modes (packed + expansion, direct upload) are covered."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from spiral_b200 import SpiralParams
+from spiral_b200.lib import check
+from tests import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+N, PL = ol.N, 2 * ol.N
+P64 = C.POINTER(C.c_uint64)
+P16 = C.POINTER(C.c_uint16)
+
+
+def p(a):
+    return a.ctypes.data_as(P64)
+
+
+def rnd_ntt(rng, npolys):
+    a = np.empty((npolys, 2, N), dtype=np.uint64)
+    a[:, 0, :] = rng.integers(0, ol.P, size=(npolys, N), dtype=np.uint64)
+    a[:, 1, :] = rng.integers(0, ol.B, size=(npolys, N), dtype=np.uint64)
+    return np.ascontiguousarray(a.reshape(-1))
+
+
+def build_planes(oracle, prm, rng, dim0, num_per, planes):
+    """Plaintext planes (u16) + the reference-layout db_buf the oracle consumes."""
+    items = dim0 * num_per
+    pts = rng.integers(0, prm.p_db, size=(planes, items, N), dtype=np.uint64)
+    db = np.zeros(planes * items * N, dtype=np.uint64)
+    for pl in range(planes):
+        enc = np.zeros(items * N, dtype=np.uint64)
+        oracle.so_encode_plaintext(p(enc), p(np.ascontiguousarray(pts[pl].reshape(-1))), items * N, prm.p_db)
+        ntt = np.zeros(items * PL, dtype=np.uint64)
+        oracle.so_to_ntt(p(ntt), p(enc), items)
+        view = db[pl * items * N:(pl + 1) * items * N]
+        oracle.so_convert_db(p(view), p(ntt), items, dim0, num_per)
+    return pts, db
+
+
+@pytest.mark.parametrize("cfg,nu1,nu2,mode", [("cfg1", 5, 2, "expand"), ("cfg3", 4, 1, "expand"), ("cfg4", 5, 2, "direct"),
+                                              ("cfg4", 6, 3, "direct"), ("cfg1", 5, 3, "direct"), ("cfg5", 5, 1, "expand")])
+def test_pack_server_matches_oracle(sb, oracle, cfg, nu1, nu2, mode):
+    prm = ol.make_params(cfg, nu1, nu2)
+    rng = np.random.default_rng(nu1 * 100 + nu2)
+    dim0, num_per, n = 1 << nu1, 1 << nu2, prm.out_n
+    planes, ell, fd = n * n, prm.t_gsw, nu2
+    pts, db = build_planes(oracle, prm, rng, dim0, num_per, planes)
+    g, stop = C.c_size_t(), C.c_size_t()
+    oracle.so_pack_expansion_shape(C.byref(prm), C.byref(g), C.byref(stop))
+    g, stop = g.value, stop.value
+    vW = rnd_ntt(rng, n * (n + 1) * prm.t_conv)
+    W_left = rnd_ntt(rng, g * 2 * prm.t_exp)
+    W_right = rnd_ntt(rng, (stop + 1) * 2 * prm.t_exp_right)
+    V = rnd_ntt(rng, 2 * 2 * prm.t_conv)
+    query = rnd_ntt(rng, 2)
+    v_first = rnd_ntt(rng, dim0 * 2)
+    v_fold = rnd_ntt(rng, max(fd, 1) * 2 * 2 * ell)
+    want = np.zeros((n + 1) * n * N, dtype=np.uint64)
+    want_cts = np.zeros(planes * 2 * N, dtype=np.uint64)
+    rc = oracle.so_pack_answer(C.byref(prm), int(mode == "expand"), p(query), p(W_left), p(W_right), p(V), p(v_first), p(v_fold),
+                               p(vW), p(db), p(want), p(want_cts))
+    assert rc == 0
+
+    h = C.c_void_p()
+    sp = SpiralParams(nu1, nu2, prm.t_gsw, prm.t_conv, prm.t_exp, prm.t_exp_right, prm.qp_bits, prm.out_n, prm.p_db)
+    check(sb.sb200_pack_server_create(C.byref(h), C.byref(sp), 0), sb)
+    items = dim0 * num_per
+    for pl in range(planes):
+        if pl % 2 == 0:
+            a = np.ascontiguousarray(pts[pl].astype(np.uint16))
+            check(sb.sb200_pack_server_load_plane_items(h, pl, a.ctypes.data_as(P16)), sb)
+        else:
+            view = np.ascontiguousarray(db[pl * items * N:(pl + 1) * items * N])
+            check(sb.sb200_pack_server_load_plane_reference(h, pl, p(view)), sb)
+    got = np.zeros_like(want)
+    got_cts = np.zeros_like(want_cts)
+    if mode == "expand":
+        check(sb.sb200_pack_server_set_public_params(h, p(W_left), p(W_right), p(V), p(vW)), sb)
+        check(sb.sb200_pack_server_answer(h, query.ctypes.data, got.ctypes.data, got_cts.ctypes.data, None), sb)
+    else:
+        check(sb.sb200_pack_server_set_public_params(h, None, None, None, p(vW)), sb)
+        check(sb.sb200_pack_server_answer_direct(h, v_first.ctypes.data, v_fold.ctypes.data, got.ctypes.data, got_cts.ctypes.data, None), sb)
+    assert sb.sb200_pack_server_response_words(h) == want.size
+    sb.sb200_pack_server_destroy(h)
+    assert np.array_equal(got_cts, want_cts), "folded per-plane ciphertexts differ"
+    assert np.array_equal(got, want), "packed + modulus-switched response differs"

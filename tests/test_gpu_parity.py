@@ -67,6 +67,20 @@ def run_case(sb, case, prm):
     elif name == "load_db":
         nu1, nu2 = int(s.dim0).bit_length() - 1, int(s.num_per).bit_length() - 1
         ok(sb, sb.sb200_load_db(p(out), p(i[0]), nu1, nu2, prm.p_db))
+    elif name == "convert_db":
+        ok(sb, sb.sb200_convertDb(p(out), p(i[0]), s.dim0 * s.num_per, s.dim0, s.num_per))
+    elif name == "reorient_dim1":
+        ok(sb, sb.sb200_reorientCiphertextsDim1(p(out), p(i[0]), 2 * s.dim0, s.dim0, 2))
+    elif name == "first_dim_pack":
+        ok(sb, sb.sb200_fastMultiplyQueryByDatabaseDim1(p(out), p(i[1]), p(i[0]), s.dim0, s.num_per))
+    elif name == "fold_dim1":
+        cts = i[0].copy()
+        ok(sb, sb.sb200_foldCiphertextsDim1(p(cts), s.num_per, p(i[1]), p(i[2]), prm.t_gsw))
+        out = cts[: 2 * N]
+    elif name == "regev_to_simple_gsw":
+        ok(sb, sb.sb200_regevToSimpleGsw(p(out), p(i[0]), 4 * prm.t_gsw + 2, p(i[1]), prm.t_conv, prm.t_gsw, 2, 2, 1))
+    elif name == "pack":
+        ok(sb, sb.sb200_pack(p(out), prm.out_n, prm.t_conv, p(i[0]), p(i[1])))
     else:
         return None
     return out
@@ -74,7 +88,12 @@ def run_case(sb, case, prm):
 
 SPIRAL_CASES = ["ntt_forward", "ntt_inverse", "to_ntt", "to_ntt_no_reduce", "from_ntt", "multiply", "automorph",
                 "gadget_invert", "rescale", "reorient_ciphertexts", "first_dim", "ntt_inv_crt_lift", "split_and_crt",
-                "fold_one", "expand_full", "expand_stopround", "scal_to_mat", "regev_to_gsw", "load_db"]
+                "fold_one", "expand_full", "expand_stopround", "scal_to_mat", "regev_to_gsw", "load_db",
+                "convert_db", "reorient_dim1", "first_dim_pack", "fold_dim1", "regev_to_simple_gsw", "pack"]
+
+
+def test_every_golden_case_is_dispatched(oracle):
+    assert sorted(SPIRAL_CASES) == sorted(ol.golden("cfg1")["cases"])
 
 
 @pytest.mark.parametrize("cfg", ["cfg1", "cfg5", "cfg4", "cfg3"])
