@@ -142,6 +142,8 @@ int sb200_server_expand_and_convert(sb200_server *srv, void *stream);      /* ex
 int sb200_server_first_dim(sb200_server *srv, void *stream);               /* scan + INTT + CRT lift */
 int sb200_server_scan(sb200_server *srv, void *stream);                    /* multiplyQueryByDatabase only (src/spiral.cpp:628) */
 int sb200_server_lift(sb200_server *srv, void *stream);                    /* nttInvAndCrtLiftCiphertexts only (src/spiral.cpp:437) */
+/* interposed multiplyQueryByDatabase: host reoriented query in, ref-NTT host ciphertexts out, database stays resident */
+int sb200_server_scan_host(sb200_server *srv, const uint64_t *reoriented_host, uint64_t *out_ref_ntt_host);
 int sb200_server_copy_partial(sb200_server *srv, uint64_t *dst_dev, void *stream);   /* D2D copy of the shard's surviving ct */
 int sb200_server_load_db_random(sb200_server *srv, uint64_t seed);         /* synthetic uniform database (benchmarks) */
 int sb200_server_fold_local(sb200_server *srv, void *stream);              /* local fold rounds; leaves 1 ct per shard */

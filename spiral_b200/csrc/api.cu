@@ -517,6 +517,14 @@ extern "C" int sb200_server_first_dim(sb200_server *s, void *stream) {
     TRY(sb200_server_scan(s, stream));
     return sb200_server_lift(s, stream);
 }
+extern "C" int sb200_server_scan_host(sb200_server *s, const uint64_t *reoriented_host, uint64_t *out_ref_ntt_host) {
+    // multiplyQueryByDatabase against the resident database with a host-side reoriented query (interposed reference call)
+    if (!s || !reoriented_host || !out_ref_ntt_host) return fail(SB200_ERR_ARG, "scan_host: null argument");
+    if (!s->have_db) return fail(SB200_ERR_STATE, "scan_host: database not loaded");
+    CU(cudaMemcpy(s->query.p, reoriented_host, s->dim0 * 2 * 4 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    launch_scan_spiral(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, 0); CHECK_LAUNCH();
+    return down_ntt(out_ref_ntt_host, s->scan_out.p, s->local_num_per * 6);
+}
 extern "C" int sb200_server_copy_partial(sb200_server *s, uint64_t *dst_dev, void *stream) {
     if (!s || !dst_dev) return fail(SB200_ERR_ARG, "copy_partial: null argument");
     CU(cudaMemcpyAsync(dst_dev, s->cts.p, 6 * (size_t)kN * sizeof(uint64_t), cudaMemcpyDeviceToDevice, S(stream)));

@@ -127,6 +127,7 @@ def load_library():
         "sb200_server_scan": (C.c_int, [vp, vp]),
         "sb200_server_lift": (C.c_int, [vp, vp]),
         "sb200_server_copy_partial": (C.c_int, [vp, vp, vp]),
+        "sb200_server_scan_host": (C.c_int, [vp, u64p, u64p]),
         "sb200_server_load_db_random": (C.c_int, [vp, C.c_uint64]),
         "sb200_server_partial_ct": (vp, [vp]),
         "sb200_server_fold_tail": (C.c_int, [vp, vp, vp, vp]),
