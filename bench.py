@@ -234,7 +234,10 @@ def b200_main(args):
     gathered = torch.empty(world * 6 * N_POLY, dtype=torch.int64, device="cuda")
     part = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
     resp_dev = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-legacy) stream: kernels, graph replays, events, NCCL and copies all run on it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def ev():
         return torch.cuda.Event(enable_timing=True)

@@ -334,6 +334,48 @@ extern "C" int sb200_regevToGSW(uint64_t *out, const uint64_t *cv_v, uint32_t t_
 // ---------------------------------------------------------------------------------------------
 // tier 3: resident server
 // ---------------------------------------------------------------------------------------------
+// A query is ~60 dependent kernel launches on fixed buffers: each stage is captured once into a CUDA
+// graph and replayed, which removes the per-launch gaps of the latency-bound expansion / fold chains.
+// SB200_NO_GRAPH=1 falls back to plain launches (same kernels, same results).
+namespace {
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    const void *key0 = nullptr, *key1 = nullptr;
+    ~GraphSlot() { if (exec) cudaGraphExecDestroy(exec); }
+};
+bool graphs_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SB200_NO_GRAPH"); v = (e && *e == '1') ? 0 : 1; }
+    return v == 1;
+}
+template <typename F>
+int run_stage(GraphSlot &slot, cudaStream_t st, const void *k0, const void *k1, F &&body) {
+    if (!graphs_enabled()) { body(st); CHECK_LAUNCH(); return SB200_OK; }
+    if (slot.exec && (slot.key0 != k0 || slot.key1 != k1)) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+    if (!slot.exec) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs != cudaStreamCaptureStatusNone) { body(st); CHECK_LAUNCH(); return SB200_OK; }   // caller is capturing: just enqueue
+        const uint64_t before = launch_count();
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        body(st);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (e != cudaSuccess || !graph) { cudaGetLastError(); return fail(SB200_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e)); }
+        slot.launches = (int)(launch_count() - before);
+        count_launch(-slot.launches);                       // capture enqueues nothing; replays are counted below
+        e = cudaGraphInstantiate(&slot.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { slot.exec = nullptr; return fail(SB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+        slot.key0 = k0; slot.key1 = k1;
+    }
+    CU(cudaGraphLaunch(slot.exec, st));
+    count_launch(slot.launches);
+    return SB200_OK;
+}
+}  // namespace
+
 struct sb200_server {
     sb200_params prm;
     int device = 0, rank = 0, world = 1, log_world = 0;
@@ -350,7 +392,13 @@ struct sb200_server {
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, gsw_neg, scan_out, fold_scratch;
     DBuf<uint64_t> c0, conv_raw, query, cts, resp, final_ct;
     DBuf<int> lists, ct_idx_first, poly_idx_first, ct_idx_bits, poly_idx_bits;
+    GraphSlot g_convert, g_lift_fold, g_tail;
+    // stream = NULL means "the legacy default stream", which cannot be captured: such calls run on this
+    // BLOCKING stream instead (implicitly ordered with legacy-default-stream work, e.g. torch's default stream)
+    cudaStream_t own_stream = nullptr;
+    ~sb200_server() { if (own_stream) cudaStreamDestroy(own_stream); }
 };
+static inline cudaStream_t ES(sb200_server *s, void *stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
 
 static size_t ceil_log2(size_t x) { size_t g = 0; while (((size_t)1 << g) < x) g++; return g; }
 
@@ -400,6 +448,7 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     A(s->lists.up(list.data(), list.size())); A(s->ct_idx_first.up(cf.data(), cf.size())); A(s->poly_idx_first.up(pf.data(), pf.size()));
     if (nbits) { A(s->ct_idx_bits.up(cb.data(), cb.size())); A(s->poly_idx_bits.up(pb.data(), pb.size())); }
     build_neg1(s->neg1.p, (int)s->g, 0);
+    A(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamDefault));
     A(cudaDeviceSynchronize());
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "server_create: setup failed: %s", cudaGetErrorString(e)); }
     *out = s;
@@ -483,33 +532,32 @@ extern "C" int sb200_server_set_public_params(sb200_server *s, const uint64_t *W
 
 extern "C" int sb200_server_upload_query(sb200_server *s, const uint64_t *query_cv_host, void *stream) {
     if (!s || !query_cv_host) return fail(SB200_ERR_ARG, "upload_query: null argument");
-    CU(cudaMemcpyAsync(s->q_stage.p, query_cv_host, 2 * PLW * sizeof(uint64_t), cudaMemcpyHostToDevice, S(stream)));
-    launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, S(stream)); CHECK_LAUNCH();
-    return SB200_OK;
+    CU(cudaMemcpyAsync(s->q_stage.p, query_cv_host, 2 * PLW * sizeof(uint64_t), cudaMemcpyHostToDevice, ES(s, stream)));
+    return SB200_OK;      // the narrowing into cv[0] is the first node of the expand_and_convert stage
 }
 extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!s->have_params) return fail(SB200_ERR_STATE, "expand_and_convert: public parameters not set");
-    cudaStream_t st = S(stream);
-    launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
-                  s->offs.data(), s->cnt.data(), st);
-    launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
-                                  (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
-    launch_regev_to_gsw(s->gsw.p, s->gsw_neg.p, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
-                        s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
-    CHECK_LAUNCH();
-    return SB200_OK;
+    return run_stage(s->g_convert, ES(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
+        launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, st);       // uploaded query (ref-NTT) -> cv[0]
+        launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
+                      s->offs.data(), s->cnt.data(), st);
+        launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
+                                      (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+        launch_regev_to_gsw(s->gsw.p, s->gsw_neg.p, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
+                            s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+    });
 }
 extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!s->have_db) return fail(SB200_ERR_STATE, "scan: database not loaded");
-    launch_scan_spiral(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, S(stream));
+    launch_scan_spiral(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, ES(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
 }
 extern "C" int sb200_server_lift(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    launch_from_ntt(s->cts.p, s->scan_out.p, s->local_num_per * 6, S(stream));
+    launch_from_ntt(s->cts.p, s->scan_out.p, s->local_num_per * 6, ES(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
 }
@@ -527,7 +575,7 @@ extern "C" int sb200_server_scan_host(sb200_server *s, const uint64_t *reoriente
 }
 extern "C" int sb200_server_copy_partial(sb200_server *s, uint64_t *dst_dev, void *stream) {
     if (!s || !dst_dev) return fail(SB200_ERR_ARG, "copy_partial: null argument");
-    CU(cudaMemcpyAsync(dst_dev, s->cts.p, 6 * (size_t)kN * sizeof(uint64_t), cudaMemcpyDeviceToDevice, S(stream)));
+    CU(cudaMemcpyAsync(dst_dev, s->cts.p, 6 * (size_t)kN * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ES(s, stream)));
     return SB200_OK;
 }
 extern "C" int sb200_server_load_db_random(sb200_server *s, uint64_t seed) {
@@ -559,26 +607,23 @@ static void fold_rounds(sb200_server *s, uint64_t *cts, size_t count, size_t fir
 }
 extern "C" int sb200_server_fold_local(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    fold_rounds(s, s->cts.p, s->local_num_per, 0, S(stream));
-    CHECK_LAUNCH();
-    return SB200_OK;
+    return run_stage(s->g_lift_fold, ES(s, stream), nullptr, nullptr, [&](cudaStream_t st) { fold_rounds(s, s->cts.p, s->local_num_per, 0, st); });
 }
 extern "C" uint64_t *sb200_server_partial_ct(sb200_server *s) { return s ? s->cts.p : nullptr; }
 extern "C" uint64_t *sb200_server_first_dim_cts(sb200_server *s) { return s ? s->cts.p : nullptr; }
 extern "C" int sb200_server_fold_tail(sb200_server *s, uint64_t *gathered, uint64_t *resp_dev, void *stream) {
     if (!s || !gathered || !resp_dev) return fail(SB200_ERR_ARG, "fold_tail: null argument");
-    cudaStream_t st = S(stream);
-    fold_rounds(s, gathered, (size_t)s->world, s->prm.nu2 - s->log_world, st);
-    // modulus switch (check_final, reference src/spiral.cpp:1441-1447): row 0 -> arb_qprime, rows 1.. -> 4*p_db
-    launch_rescale(resp_dev, gathered, 2 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
-    launch_rescale(resp_dev + 2 * kN, gathered + 2 * kN, 4 * (size_t)kN, kQ, 4 * s->prm.p_db, st);
-    CHECK_LAUNCH();
-    return SB200_OK;
+    return run_stage(s->g_tail, ES(s, stream), gathered, resp_dev, [&](cudaStream_t st) {
+        fold_rounds(s, gathered, (size_t)s->world, s->prm.nu2 - s->log_world, st);
+        // modulus switch (check_final, reference src/spiral.cpp:1441-1447): row 0 -> arb_qprime, rows 1.. -> 4*p_db
+        launch_rescale(resp_dev, gathered, 2 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
+        launch_rescale(resp_dev + 2 * kN, gathered + 2 * kN, 4 * (size_t)kN, kQ, 4 * s->prm.p_db, st);
+    });
 }
 extern "C" int sb200_server_download(sb200_server *s, uint64_t *dst, const uint64_t *src, size_t words, void *stream) {
-    (void)s;
-    CU(cudaMemcpyAsync(dst, src, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, S(stream)));
-    CU(cudaStreamSynchronize(S(stream)));
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    CU(cudaMemcpyAsync(dst, src, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ES(s, stream)));
+    CU(cudaStreamSynchronize(ES(s, stream)));
     return SB200_OK;
 }
 extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream) {

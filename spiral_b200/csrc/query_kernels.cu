@@ -105,6 +105,7 @@ __global__ void k_expand_accum(uint32_t *__restrict__ cv, const int *__restrict_
     const int gd = (i & 1) ? t_right : t_left;
     const uint32_t *W = ((i & 1) ? W_right : W_left) + (size_t)row * gd * 2 * kN;
     uint64_t acc[4] = {0, 0, 0, 0};
+#pragma unroll 8
     for (int k = 0; k < gd; k++) {
         const uint4 x = __ldg(reinterpret_cast<const uint4 *>(W + (size_t)k * 2 * kN) + w4);
         const uint4 y = __ldg(reinterpret_cast<const uint4 *>(ginv + ((size_t)slot * tmax + k) * 2 * kN) + w4);

@@ -241,20 +241,25 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
 // k_fold_mac_intt   : 2*m2-term pointwise dot product (cpu_mul_query_by_ct, :464-582), add,
 //                     inverse NTT and CRT lift (:1374-1407) fused; writes the folded ct in place.
 // ============================================================================================
-__device__ __forceinline__ uint64_t signed_digit(uint64_t val, int k, int t, uint32_t bits_per) {
+// Signed digit k of `val` as a residue modulo q (lazy, < 4q), following split_and_crt's carry chain
+// (reference src/spiral.cpp:282-329).  The digit is either a small value d <= 2^bp or d + Q - 2^bp;
+// Q = 0 (mod p, b), so for bp <= 27 the residue is d or d + q - 2^bp with no 64-bit reduction.
+__device__ __forceinline__ uint32_t signed_digit_res(uint64_t val, int k, int t, uint32_t bits_per, uint32_t q, int n) {
     const uint64_t mask = (1ull << bits_per) - 1;
     const uint64_t halfv = (uint64_t)((1 << bits_per) / 2);
     const int half_elems = t / 2;
     const int k0 = k < half_elems ? 0 : half_elems;
     uint64_t carry = 0, piece = 0;
+    bool wrapped = false;
     for (int kk = k0; kk <= k; kk++) {
         uint32_t off = min((uint32_t)kk * bits_per, 64u);
         piece = ((val >> (off & 63)) & mask) + carry;
-        carry = 0;
         const bool guard = (k < half_elems) ? (kk + 1 < half_elems) : true;   // first half: k < num_elems/2 - 1
-        if (piece > halfv && guard) { piece += kQ - (1ull << bits_per); carry = 1; }
+        wrapped = piece > halfv && guard;
+        carry = wrapped ? 1 : 0;
     }
-    return piece;
+    if (bits_per <= 27) return wrapped ? (uint32_t)piece + q - (1u << bits_per) : (uint32_t)piece;
+    return raw_to_res(wrapped ? piece + kQ - (1ull << bits_per) : piece, n);
 }
 // Generic over the ciphertext shape so the Pack variant (foldCiphertextsDim1, src/testing.cpp:596-624:
 // 2x1 ciphertexts, UNSIGNED gadget_invert digits, out_n^2 planes batched) shares the kernels:
@@ -279,47 +284,54 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         const uint64_t val = __ldg(src + nat_pos(lt, e));
-        const uint64_t d = fs.is_signed ? signed_digit(val, k, fs.t, bits_per) : gadget_digit(val, k, bits_per, mask);
-        v[e] = raw_to_res(d, n);
+        v[e] = fs.is_signed ? signed_digit_res(val, k, fs.t, bits_per, modulus(n), n)
+                            : (bits_per <= 29 ? (uint32_t)gadget_digit(val, k, bits_per, mask) : raw_to_res(gadget_digit(val, k, bits_per, mask), n));
     }
     ntt_forward_plane(v, sm[n], lt, n);
     const int m2 = fs.R * fs.t, row = r + k * fs.R;
     store_ntt_regs(v, scratch + ((((size_t)ctd * m2 + row) * fs.Cc + c) * 2 + n) * kN, lt);
 }
-__global__ void __launch_bounds__(kNttThreads) k_fold_mac_intt(uint64_t *__restrict__ cts, const uint32_t *__restrict__ scratch,
-                                                               const uint32_t *__restrict__ q_dev, const uint32_t *__restrict__ qneg_dev,
-                                                               FoldShape fs) {
-    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
-    const int n = plane_of_thread(), lt = lane_in_plane();
+// Pointwise 2*m2-term dot product for every output polynomial, z-parallel: blockIdx.x = output poly * 4 + quarter,
+// 256 threads x 4 coefficients.  All loads of the unrolled batch are independent, so a late round with a handful
+// of ciphertexts still keeps 8-16 128-bit loads in flight per thread instead of a serial load->MAC chain.
+__global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, const uint32_t *__restrict__ scratch,
+                                                  const uint32_t *__restrict__ q_dev, const uint32_t *__restrict__ qneg_dev, FoldShape fs) {
     const int RC = fs.R * fs.Cc;
-    const int id = blockIdx.x / RC, rc = blockIdx.x % RC, r = rc / fs.Cc, c = rc % fs.Cc;
+    const int op = blockIdx.x >> 2, quarter = blockIdx.x & 3;
+    const int id = op / RC, rc = op % RC, r = rc / fs.Cc, c = rc % fs.Cc;
     const int plane = id / fs.np, i = id % fs.np;
     const int m2 = fs.R * fs.t;
-    uint64_t acc[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) acc[e] = 0;
+    const int w4 = quarter * 256 + threadIdx.x, n = w4 >= 512;
+    uint64_t acc[4] = {0, 0, 0, 0};
     for (int h = 0; h < 2; h++) {
-        const int ctd = plane * 2 * fs.np + (h == 0 ? i : fs.np + i);      // dense index used by the decomposition
-        const uint32_t *Qm = (h == 0 ? qneg_dev : q_dev) + ((size_t)r * m2 * 2 + n) * kN;
-        const uint32_t *Cm = scratch + ((((size_t)ctd * m2) * fs.Cc + c) * 2 + n) * kN;
+        const int ctd = plane * 2 * fs.np + (h == 0 ? i : fs.np + i);
+        const uint4 *Qm = reinterpret_cast<const uint4 *>((h == 0 ? qneg_dev : q_dev) + (size_t)r * m2 * 2 * kN) + w4;
+        const uint4 *Cm = reinterpret_cast<const uint4 *>(scratch + (((size_t)ctd * m2) * fs.Cc + c) * 2 * kN) + w4;
+        const size_t qs = 2 * kN / 4, cs = (size_t)fs.Cc * 2 * kN / 4;
+#pragma unroll 8
         for (int m = 0; m < m2; m++) {
-            uint32_t a[16], b[16];
-            load_ntt_regs(a, Qm + (size_t)m * 2 * kN, lt);
-            load_ntt_regs(b, Cm + (size_t)m * fs.Cc * 2 * kN, lt);
-#pragma unroll
-            for (int e = 0; e < 16; e++) acc[e] += (uint64_t)a[e] * b[e];
+            const uint4 x = __ldg(Qm + m * qs), y = __ldg(Cm + m * cs);
+            acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
+            acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
             if ((m & 127) == 127) {
 #pragma unroll
-                for (int e = 0; e < 16; e++) acc[e] = reduce_u64(acc[e], n);
+                for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
             }
         }
 #pragma unroll
-        for (int e = 0; e < 16; e++) acc[e] = reduce_u64(acc[e], n);     // < q: the two halves never overflow together
+        for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
     }
+    reinterpret_cast<uint4 *>(out + (size_t)op * 2 * kN)[w4] = make_uint4((uint32_t)acc[0], (uint32_t)acc[1], (uint32_t)acc[2], (uint32_t)acc[3]);
+}
+// inverse NTT + CRT lift of the dense MAC outputs back into the (strided) ciphertext array
+__global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict__ cts, const uint32_t *__restrict__ macout, FoldShape fs) {
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const int RC = fs.R * fs.Cc;
+    const int id = blockIdx.x / RC, rc = blockIdx.x % RC;
+    const int plane = id / fs.np, i = id % fs.np;
     uint32_t v[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = (uint32_t)acc[e];
-    // inverse NTT + CRT lift, written over ciphertext i of this plane
+    load_ntt_regs(v, macout + ((size_t)blockIdx.x * 2 + n) * kN, lt);
     ntt_inverse_plane(v, sm[n], lt, n);
     __syncthreads();
 #pragma unroll
@@ -332,13 +344,16 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_mac_intt(uint64_t *__restr
         dst[z] = crt_compose(sm[0][z], sm[1][z]);
     }
 }
-size_t fold_scratch_words_generic(size_t cts_in, int R, int Cc, int t) { return cts_in * (size_t)R * t * Cc * 2 * kN; }
+// digits of every input ciphertext + the dense MAC outputs (one per output polynomial)
+size_t fold_scratch_words_generic(size_t cts_in, int R, int Cc, int t) { return cts_in * (size_t)R * t * Cc * 2 * kN + (cts_in / 2 + 1) * (size_t)R * Cc * 2 * kN; }
 void launch_fold_round_generic(uint64_t *cts, int R, int Cc, int t, int is_signed, size_t np_after, size_t planes, size_t plane_stride,
                                const uint32_t *q_dev, const uint32_t *qneg_dev, uint32_t *scratch, cudaStream_t s) {
     FoldShape fs{R, Cc, t, is_signed, (int)np_after, (int)planes, (int)plane_stride};
     const int RC = R * Cc, cpp = (int)(2 * np_after);
     count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(planes * cpp * RC), t), kNttThreads, 0, s>>>(scratch, cts, fs, cpp);
-    count_launch(); k_fold_mac_intt<<<(unsigned)(planes * np_after * RC), kNttThreads, 0, s>>>(cts, scratch, q_dev, qneg_dev, fs);
+    uint32_t *macout = scratch + (size_t)planes * cpp * R * t * Cc * 2 * kN;
+    count_launch(); k_fold_mac<<<(unsigned)(planes * np_after * RC * 4), 256, 0, s>>>(macout, scratch, q_dev, qneg_dev, fs);
+    count_launch(); k_fold_lift<<<(unsigned)(planes * np_after * RC), kNttThreads, 0, s>>>(cts, macout, fs);
 }
 // reference reorient_Q layout (packed [z][r*m2 + m], src/spiral.cpp:388-400) -> dev-NTT [r*m2 + m][n][z]
 __global__ void k_unreorient_q(uint32_t *__restrict__ out, const uint64_t *__restrict__ q_reor, int rm_count) {
