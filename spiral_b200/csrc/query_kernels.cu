@@ -96,21 +96,35 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restr
     store_ntt_regs(v, ginv + (((size_t)slot * tmax + k) * 2 + n) * kN, lt);
 }
 
-__global__ void k_expand_accum(uint32_t *__restrict__ cv, const int *__restrict__ active, const uint32_t *__restrict__ ginv,
+__global__ void __launch_bounds__(256) k_expand_accum(uint32_t *__restrict__ cv, const int *__restrict__ active, const uint32_t *__restrict__ ginv,
                                const uint32_t *__restrict__ c1_ntt, const uint32_t *__restrict__ W_left,
                                const uint32_t *__restrict__ W_right, int t_left, int t_right, int tmax) {
-    // grid (slot, row*4 + quarter); 256 threads x uint4
-    const int slot = blockIdx.x, row = blockIdx.y >> 2, quarter = blockIdx.y & 3, i = active[slot];
-    const int w4 = quarter * 256 + threadIdx.x, n = w4 >= 512;
+    // grid (slot, row*16 + segment); CTA = 64 uint4 columns x 4 digit groups (same split as k_fold_mac: every
+    // thread's loads are independent, partial sums meet in shared memory)
+    __shared__ ulonglong2 part[3][64][2];
+    const int slot = blockIdx.x, row = blockIdx.y >> 4, seg = blockIdx.y & 15, i = active[slot];
+    const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int w4 = seg * 64 + col, n = w4 >= 512;
     const int gd = (i & 1) ? t_right : t_left;
-    const uint32_t *W = ((i & 1) ? W_right : W_left) + (size_t)row * gd * 2 * kN;
+    const uint4 *W = reinterpret_cast<const uint4 *>(((i & 1) ? W_right : W_left) + (size_t)row * gd * 2 * kN) + w4;
+    const uint4 *G = reinterpret_cast<const uint4 *>(ginv + (size_t)slot * tmax * 2 * kN) + w4;
     uint64_t acc[4] = {0, 0, 0, 0};
-#pragma unroll 8
-    for (int k = 0; k < gd; k++) {
-        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(W + (size_t)k * 2 * kN) + w4);
-        const uint4 y = __ldg(reinterpret_cast<const uint4 *>(ginv + ((size_t)slot * tmax + k) * 2 * kN) + w4);
+#pragma unroll 4
+    for (int k = grp; k < gd; k += 4) {
+        const uint4 x = __ldg(W + (size_t)k * (2 * kN / 4)), y = __ldg(G + (size_t)k * (2 * kN / 4));
         acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
         acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
+    }
+    if (grp > 0) {
+        part[grp - 1][col][0] = make_ulonglong2(acc[0], acc[1]);
+        part[grp - 1][col][1] = make_ulonglong2(acc[2], acc[3]);
+    }
+    __syncthreads();
+    if (grp != 0) return;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        const ulonglong2 a = part[g][col][0], b = part[g][col][1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
     }
     uint4 *dst = reinterpret_cast<uint4 *>(cv + ((size_t)i * 2 + row) * 2 * kN) + w4;
     const uint4 cur = *dst;
@@ -181,7 +195,7 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         const int ty = any_odd ? tmax : p.t_left;
         count_launch(); k_expand_prep<<<dim3(cnt[r], 2), kNttThreads, 0, s>>>(cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, c0_raw, c1_ntt);
         count_launch(); k_expand_digits<<<dim3(cnt[r], ty), kNttThreads, 0, s>>>(ginv, c0_raw, act, p.t_left, p.t_right, tmax);
-        count_launch(); k_expand_accum<<<dim3(cnt[r], 8), 256, 0, s>>>(cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, tmax);
+        count_launch(); k_expand_accum<<<dim3(cnt[r], 32), 256, 0, s>>>(cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, tmax);
     }
 }
 

@@ -245,19 +245,26 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
 // (reference src/spiral.cpp:282-329).  The digit is either a small value d <= 2^bp or d + Q - 2^bp;
 // Q = 0 (mod p, b), so for bp <= 27 the residue is d or d + q - 2^bp with no 64-bit reduction.
 __device__ __forceinline__ uint32_t signed_digit_res(uint64_t val, int k, int t, uint32_t bits_per, uint32_t q, int n) {
-    const uint64_t mask = (1ull << bits_per) - 1;
-    const uint64_t halfv = (uint64_t)((1 << bits_per) / 2);
+    // The carry chain "piece > 2^(bp-1) -> carry" is ordinary carry propagation of adding the constant
+    // K = sum_j (2^(bp-1) - 1) * 2^(j*bp) to the lower digits, so the carry into digit k is one bit of (L + K):
+    // no loop.  The first half restarts at digit 0, the second at digit t/2 (carry reset, reference :282,312).
     const int half_elems = t / 2;
     const int k0 = k < half_elems ? 0 : half_elems;
-    uint64_t carry = 0, piece = 0;
-    bool wrapped = false;
-    for (int kk = k0; kk <= k; kk++) {
-        uint32_t off = min((uint32_t)kk * bits_per, 64u);
-        piece = ((val >> (off & 63)) & mask) + carry;
-        const bool guard = (k < half_elems) ? (kk + 1 < half_elems) : true;   // first half: k < num_elems/2 - 1
-        wrapped = piece > halfv && guard;
-        carry = wrapped ? 1 : 0;
+    const uint32_t lowbits = (uint32_t)(k - k0) * bits_per;                 // <= 28 * ... < 64 for every surveyed t
+    const uint64_t mask = (1ull << bits_per) - 1;
+    const uint32_t off0 = min((uint32_t)k0 * bits_per, 64u), offk = min((uint32_t)k * bits_per, 64u);
+    const uint64_t x = val >> (off0 & 63);
+    uint64_t carry = 0;
+    if (lowbits) {
+        const uint64_t L = x & ((1ull << lowbits) - 1);
+        uint64_t K = 0;
+        const uint64_t hm1 = (1ull << (bits_per - 1)) - 1;
+        for (uint32_t j = 0; j < lowbits; j += bits_per) K |= hm1 << j;     // k - k0 <= t/2 iterations on CTA-uniform values
+        carry = ((L + K) >> lowbits) & 1;
     }
+    const uint64_t piece = ((val >> (offk & 63)) & mask) + carry;
+    const bool guard = (k < half_elems) ? (k + 1 < half_elems) : true;       // first half: k < num_elems/2 - 1
+    const bool wrapped = piece > (1ull << (bits_per - 1)) && guard;
     if (bits_per <= 27) return wrapped ? (uint32_t)piece + q - (1u << bits_per) : (uint32_t)piece;
     return raw_to_res(wrapped ? piece + kQ - (1ull << bits_per) : piece, n);
 }
@@ -291,37 +298,56 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
     const int m2 = fs.R * fs.t, row = r + k * fs.R;
     store_ntt_regs(v, scratch + ((((size_t)ctd * m2 + row) * fs.Cc + c) * 2 + n) * kN, lt);
 }
-// Pointwise 2*m2-term dot product for every output polynomial, z-parallel: blockIdx.x = output poly * 4 + quarter,
-// 256 threads x 4 coefficients.  All loads of the unrolled batch are independent, so a late round with a handful
-// of ciphertexts still keeps 8-16 128-bit loads in flight per thread instead of a serial load->MAC chain.
+// Pointwise 2*m2-term dot product for every output polynomial.  CTA = 64 uint4 columns (256 coefficients) x 4 term
+// groups: each thread owns every 4th term, so its <= 12 (t_GSW = 8) 128-bit load pairs are all independent and in
+// flight together; the four partial sums meet in shared memory.  16 CTAs per output polynomial keep late rounds
+// (a handful of ciphertexts) spread over the chip instead of serialising a 48-step load->MAC chain.
+constexpr int kMacCols = 64, kMacGroups = 4;
 __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, const uint32_t *__restrict__ scratch,
                                                   const uint32_t *__restrict__ q_dev, const uint32_t *__restrict__ qneg_dev, FoldShape fs) {
+    __shared__ ulonglong2 part[kMacGroups - 1][kMacCols][2];
     const int RC = fs.R * fs.Cc;
-    const int op = blockIdx.x >> 2, quarter = blockIdx.x & 3;
+    const int op = blockIdx.x >> 4, seg = blockIdx.x & 15;
     const int id = op / RC, rc = op % RC, r = rc / fs.Cc, c = rc % fs.Cc;
     const int plane = id / fs.np, i = id % fs.np;
     const int m2 = fs.R * fs.t;
-    const int w4 = quarter * 256 + threadIdx.x, n = w4 >= 512;
+    const int col = threadIdx.x & (kMacCols - 1), grp = threadIdx.x >> 6;
+    const int w4 = seg * kMacCols + col, n = w4 >= 512;
+    const size_t qs = 2 * kN / 4, cs = (size_t)fs.Cc * 2 * kN / 4;
+    const uint4 *Qn = reinterpret_cast<const uint4 *>(qneg_dev + (size_t)r * m2 * 2 * kN) + w4;
+    const uint4 *Qp = reinterpret_cast<const uint4 *>(q_dev + (size_t)r * m2 * 2 * kN) + w4;
+    const uint4 *C0 = reinterpret_cast<const uint4 *>(scratch + (((size_t)(plane * 2 * fs.np + i) * m2) * fs.Cc + c) * 2 * kN) + w4;
+    const uint4 *C1 = reinterpret_cast<const uint4 *>(scratch + (((size_t)(plane * 2 * fs.np + fs.np + i) * m2) * fs.Cc + c) * 2 * kN) + w4;
     uint64_t acc[4] = {0, 0, 0, 0};
-    for (int h = 0; h < 2; h++) {
-        const int ctd = plane * 2 * fs.np + (h == 0 ? i : fs.np + i);
-        const uint4 *Qm = reinterpret_cast<const uint4 *>((h == 0 ? qneg_dev : q_dev) + (size_t)r * m2 * 2 * kN) + w4;
-        const uint4 *Cm = reinterpret_cast<const uint4 *>(scratch + (((size_t)ctd * m2) * fs.Cc + c) * 2 * kN) + w4;
-        const size_t qs = 2 * kN / 4, cs = (size_t)fs.Cc * 2 * kN / 4;
-#pragma unroll 8
-        for (int m = 0; m < m2; m++) {
-            const uint4 x = __ldg(Qm + m * qs), y = __ldg(Cm + m * cs);
-            acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
-            acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
-            if ((m & 127) == 127) {
+    int cnt = 0;
+#pragma unroll 4
+    for (int tm = grp; tm < 2 * m2; tm += kMacGroups) {
+        const int h = tm >= m2, m = h ? tm - m2 : tm;
+        const uint4 x = __ldg((h ? Qp : Qn) + m * qs), y = __ldg((h ? C1 : C0) + m * cs);
+        acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
+        acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
+        if (++cnt == 120) {
+            cnt = 0;
 #pragma unroll
-                for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
-            }
+            for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
         }
-#pragma unroll
-        for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
     }
-    reinterpret_cast<uint4 *>(out + (size_t)op * 2 * kN)[w4] = make_uint4((uint32_t)acc[0], (uint32_t)acc[1], (uint32_t)acc[2], (uint32_t)acc[3]);
+#pragma unroll
+    for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
+    if (grp > 0) {
+        part[grp - 1][col][0] = make_ulonglong2(acc[0], acc[1]);
+        part[grp - 1][col][1] = make_ulonglong2(acc[2], acc[3]);
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+        for (int g = 0; g < kMacGroups - 1; g++) {
+            const ulonglong2 a = part[g][col][0], b = part[g][col][1];
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        }
+        reinterpret_cast<uint4 *>(out + (size_t)op * 2 * kN)[w4] =
+            make_uint4(reduce_u64(acc[0], n), reduce_u64(acc[1], n), reduce_u64(acc[2], n), reduce_u64(acc[3], n));
+    }
 }
 // inverse NTT + CRT lift of the dense MAC outputs back into the (strided) ciphertext array
 __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict__ cts, const uint32_t *__restrict__ macout, FoldShape fs) {
@@ -352,7 +378,7 @@ void launch_fold_round_generic(uint64_t *cts, int R, int Cc, int t, int is_signe
     const int RC = R * Cc, cpp = (int)(2 * np_after);
     count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(planes * cpp * RC), t), kNttThreads, 0, s>>>(scratch, cts, fs, cpp);
     uint32_t *macout = scratch + (size_t)planes * cpp * R * t * Cc * 2 * kN;
-    count_launch(); k_fold_mac<<<(unsigned)(planes * np_after * RC * 4), 256, 0, s>>>(macout, scratch, q_dev, qneg_dev, fs);
+    count_launch(); k_fold_mac<<<(unsigned)(planes * np_after * RC * 16), 256, 0, s>>>(macout, scratch, q_dev, qneg_dev, fs);
     count_launch(); k_fold_lift<<<(unsigned)(planes * np_after * RC), kNttThreads, 0, s>>>(cts, macout, fs);
 }
 // reference reorient_Q layout (packed [z][r*m2 + m], src/spiral.cpp:388-400) -> dev-NTT [r*m2 + m][n][z]
