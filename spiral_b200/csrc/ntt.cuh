@@ -53,6 +53,16 @@ __device__ __forceinline__ void bf_inv(uint32_t &u, uint32_t &v, uint2 w, uint32
     v = mul_shoup_lazy(t, w.x, w.y, q);
 }
 
+// Warm the twiddles of the later passes while the first pass computes (each is an L2 round trip otherwise).
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_twiddles(const uint2 *tw, int lt) {
+    const int blk = lt >> 3;
+    prefetch_l1(tw + 16 + blk); prefetch_l1(tw + 32 + 2 * blk); prefetch_l1(tw + 64 + 4 * blk); prefetch_l1(tw + 128 + 8 * blk);
+    prefetch_l1(tw + 256 + lt); prefetch_l1(tw + 256 + 128 + lt);
+    prefetch_l1(tw + 512 + 2 * lt); prefetch_l1(tw + 512 + 256 + 2 * lt);
+    prefetch_l1(tw + 1024 + 4 * lt); prefetch_l1(tw + 1024 + 512 + 4 * lt);
+}
+
 // Forward NTT of one prime plane.
 //   in : v[k] = a[lt + 128*k]  (natural coefficient order), any value < 4q
 //   out: v[k] = A[8*lt + k] for k < 8, A[1024 + 8*lt + (k-8)] for k >= 8  (reference NTT order), canonical
@@ -60,6 +70,7 @@ __device__ __forceinline__ void bf_inv(uint32_t &u, uint32_t &v, uint2 w, uint32
 __device__ __forceinline__ void ntt_forward_plane(uint32_t (&v)[16], uint32_t *pl, int lt, int n) {
     const uint32_t q = modulus(n), q2 = 2 * q;
     const uint2 *__restrict__ tw = c_ntt.fwd[n];
+    prefetch_twiddles(tw, lt);
     // pass A: stages 0..3, distances 1024,512,256,128 = 8,4,2,1 register steps
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -114,6 +125,7 @@ __device__ __forceinline__ void ntt_forward_plane(uint32_t (&v)[16], uint32_t *p
 __device__ __forceinline__ void ntt_inverse_plane(uint32_t (&v)[16], uint32_t *pl, int lt, int n) {
     const uint32_t q = modulus(n), q2 = 2 * q;
     const uint2 *__restrict__ tw = c_ntt.inv[n];
+    prefetch_twiddles(tw, lt);
     // pass C': distances 1,2,4
 #pragma unroll
     for (int h = 0; h < 2; h++) {

@@ -244,29 +244,36 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
 // Signed digit k of `val` as a residue modulo q (lazy, < 4q), following split_and_crt's carry chain
 // (reference src/spiral.cpp:282-329).  The digit is either a small value d <= 2^bp or d + Q - 2^bp;
 // Q = 0 (mod p, b), so for bp <= 27 the residue is d or d + q - 2^bp with no 64-bit reduction.
-__device__ __forceinline__ uint32_t signed_digit_res(uint64_t val, int k, int t, uint32_t bits_per, uint32_t q, int n) {
+struct SignedDigitPlan {          // everything that depends only on (k, t): built once per CTA
+    uint32_t off0, offk, lowbits, bits_per;
+    uint64_t K, lowmask, mask, half;
+    bool guard;
+};
+__device__ __forceinline__ SignedDigitPlan make_signed_digit_plan(int k, int t, uint32_t bits_per) {
     // The carry chain "piece > 2^(bp-1) -> carry" is ordinary carry propagation of adding the constant
     // K = sum_j (2^(bp-1) - 1) * 2^(j*bp) to the lower digits, so the carry into digit k is one bit of (L + K):
-    // no loop.  The first half restarts at digit 0, the second at digit t/2 (carry reset, reference :282,312).
+    // no loop per coefficient.  The first half restarts at digit 0, the second at digit t/2 (carry reset, :282,312).
+    SignedDigitPlan p;
     const int half_elems = t / 2;
     const int k0 = k < half_elems ? 0 : half_elems;
-    const uint32_t lowbits = (uint32_t)(k - k0) * bits_per;                 // <= 28 * ... < 64 for every surveyed t
-    const uint64_t mask = (1ull << bits_per) - 1;
-    const uint32_t off0 = min((uint32_t)k0 * bits_per, 64u), offk = min((uint32_t)k * bits_per, 64u);
-    const uint64_t x = val >> (off0 & 63);
-    uint64_t carry = 0;
-    if (lowbits) {
-        const uint64_t L = x & ((1ull << lowbits) - 1);
-        uint64_t K = 0;
-        const uint64_t hm1 = (1ull << (bits_per - 1)) - 1;
-        for (uint32_t j = 0; j < lowbits; j += bits_per) K |= hm1 << j;     // k - k0 <= t/2 iterations on CTA-uniform values
-        carry = ((L + K) >> lowbits) & 1;
-    }
-    const uint64_t piece = ((val >> (offk & 63)) & mask) + carry;
-    const bool guard = (k < half_elems) ? (k + 1 < half_elems) : true;       // first half: k < num_elems/2 - 1
-    const bool wrapped = piece > (1ull << (bits_per - 1)) && guard;
-    if (bits_per <= 27) return wrapped ? (uint32_t)piece + q - (1u << bits_per) : (uint32_t)piece;
-    return raw_to_res(wrapped ? piece + kQ - (1ull << bits_per) : piece, n);
+    p.bits_per = bits_per;
+    p.lowbits = (uint32_t)(k - k0) * bits_per;
+    p.mask = (1ull << bits_per) - 1;
+    p.off0 = min((uint32_t)k0 * bits_per, 64u) & 63;
+    p.offk = min((uint32_t)k * bits_per, 64u) & 63;
+    p.lowmask = p.lowbits ? ((1ull << p.lowbits) - 1) : 0;
+    p.half = 1ull << (bits_per - 1);
+    p.K = 0;
+    for (uint32_t j = 0; j < p.lowbits; j += bits_per) p.K |= (p.half - 1) << j;
+    p.guard = (k < half_elems) ? (k + 1 < half_elems) : true;                 // first half: k < num_elems/2 - 1
+    return p;
+}
+__device__ __forceinline__ uint32_t signed_digit_res(uint64_t val, const SignedDigitPlan &p, uint32_t q, int n) {
+    const uint64_t carry = (((val >> p.off0) & p.lowmask) + p.K) >> p.lowbits;   // 0 or 1 (K = 0, lowmask = 0 when lowbits = 0)
+    const uint64_t piece = ((val >> p.offk) & p.mask) + (p.lowbits ? carry : 0);
+    const bool wrapped = piece > p.half && p.guard;
+    if (p.bits_per <= 27) return wrapped ? (uint32_t)piece + q - (1u << p.bits_per) : (uint32_t)piece;
+    return raw_to_res(wrapped ? piece + kQ - (1ull << p.bits_per) : piece, n);
 }
 // Generic over the ciphertext shape so the Pack variant (foldCiphertextsDim1, src/testing.cpp:596-624:
 // 2x1 ciphertexts, UNSIGNED gadget_invert digits, out_n^2 planes batched) shares the kernels:
@@ -287,11 +294,12 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
     const uint32_t bits_per = get_bits_per(fs.t);
     const uint64_t mask = (1ull << bits_per) - 1;
     const uint64_t *src = cts + ((size_t)(plane * fs.plane_stride + ctl) * RC + rc) * kN;
+    const SignedDigitPlan plan = make_signed_digit_plan(k, fs.t, bits_per);
     uint32_t v[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         const uint64_t val = __ldg(src + nat_pos(lt, e));
-        v[e] = fs.is_signed ? signed_digit_res(val, k, fs.t, bits_per, modulus(n), n)
+        v[e] = fs.is_signed ? signed_digit_res(val, plan, modulus(n), n)
                             : (bits_per <= 29 ? (uint32_t)gadget_digit(val, k, bits_per, mask) : raw_to_res(gadget_digit(val, k, bits_per, mask), n));
     }
     ntt_forward_plane(v, sm[n], lt, n);
