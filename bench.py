@@ -200,6 +200,10 @@ def b200_main(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner) write to fd 1: keep the real stdout for the single JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
@@ -365,7 +369,8 @@ def b200_main(args):
                                             "sample": f"oracle port, one query at ./spiral 6 4 (1/32 of the records), 1 core ({info})"}
                 except Exception as e:  # noqa: BLE001
                     line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     srv.close()
     if world > 1:
         dist.destroy_process_group()
