@@ -432,7 +432,7 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     A(s->q_stage.alloc(2 * PLW)); A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW));
     A(s->ginv.alloc((size_t)s->maxcnt * s->tmax * PLW)); A(s->c0.alloc((size_t)s->maxcnt * kN));
     A(s->conv_raw.alloc(conv_cols * kN)); A(s->conv_ntt.alloc(conv_cols * prm->t_conv * PLW));
-    A(s->gsw.alloc(prm->nu2 * 3 * m2 * PLW)); A(s->gsw_neg.alloc(prm->nu2 * 3 * m2 * PLW));
+    A(s->gsw.alloc(prm->nu2 * 3 * m2 * PLW));
     A(s->query.alloc(s->dim0 * 2 * 4 * kN)); A(s->scan_out.alloc(s->local_num_per * 6 * PLW));
     const size_t cts_n = std::max(s->local_num_per, (size_t)world);
     A(s->cts.alloc(cts_n * 6 * kN)); A(s->final_ct.alloc(6 * kN)); A(s->resp.alloc(6 * kN));
@@ -544,7 +544,8 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
                       s->offs.data(), s->cnt.data(), st);
         launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
                                       (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
-        launch_regev_to_gsw(s->gsw.p, s->gsw_neg.p, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
+        // no GSW negation on the resident path: the fold uses the CMux form (launch_fold_round_generic)
+        launch_regev_to_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
                             s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
     });
 }
@@ -601,7 +602,7 @@ static void fold_rounds(sb200_server *s, uint64_t *cts, size_t count, size_t fir
     size_t np = count, d = first_dim;
     while (np >= 2) {
         np /= 2;
-        launch_fold_round(cts, np, s->gsw.p + d * per, s->gsw_neg.p + d * per, (int)s->prm.t_gsw, s->fold_scratch.p, st);
+        launch_fold_round(cts, np, s->gsw.p + d * per, nullptr, (int)s->prm.t_gsw, s->fold_scratch.p, st);   // CMux form
         d++;
     }
 }

@@ -145,7 +145,7 @@ extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_par
     const size_t conv_polys = std::max(2 * nbits, s->planes * 2);
     A(s->conv_raw.alloc(std::max(conv_polys, (size_t)1) * kN));
     A(s->conv_ntt.alloc(std::max((size_t)2 * prm->t_conv * nbits, (prm->t_conv + 1) * s->planes) * PLW));
-    A(s->gsw.alloc(std::max(prm->nu2, 1u) * 2 * 2 * ell * PLW)); A(s->gsw_neg.alloc(std::max(prm->nu2, 1u) * 2 * 2 * ell * PLW));
+    A(s->gsw.alloc(std::max(prm->nu2, 1u) * 2 * 2 * ell * PLW));
     A(s->query.alloc(s->dim0 * 2 * kN)); A(s->scan_out.alloc(s->planes * s->num_per * 2 * PLW));
     A(s->cts.alloc(s->planes * s->num_per * 2 * kN)); A(s->result_cts.alloc(s->planes * 2 * kN));
     A(s->fold_scratch.alloc(fold_scratch_words_generic(std::max(s->planes * s->num_per, (size_t)2), 2, 1, (int)ell)));
@@ -229,7 +229,7 @@ static int pack_process(sb200_pack_server *s, uint64_t *resp_host, uint64_t *res
         np /= 2;
         const size_t d = fd - 1 - cur;
         launch_fold_round_generic(s->cts.p, 2, 1, (int)ell, 0, np, s->planes, s->num_per, s->gsw.p + d * gsw_polys * PLW,
-                                  s->gsw_neg.p + d * gsw_polys * PLW, s->fold_scratch.p, st);
+                                  nullptr, s->fold_scratch.p, st);            // CMux form, no negated GSW needed
     }
     CU(cudaMemcpy2DAsync(s->result_cts.p, 2 * kN * 8, s->cts.p, s->num_per * 2 * kN * 8, 2 * kN * 8, s->planes, cudaMemcpyDeviceToDevice, st));
     launch_pack(s->packed.p, s->result_cts.p, s->vW.p, (int)out_n, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
@@ -259,7 +259,7 @@ extern "C" int sb200_pack_server_answer(sb200_pack_server *s, const uint64_t *qu
     launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
     launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p, s->offs.data(), s->cnt.data(), st);
     launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_first.p, s->dim0, st);
-    launch_regev_to_simple_gsw(s->gsw.p, s->gsw_neg.p, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)ell, s->V.p,
+    launch_regev_to_simple_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)ell, s->V.p,
                                (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
     CHECK_LAUNCH();
     CU(cudaStreamSynchronize(st));          // host index vectors go out of scope
@@ -279,7 +279,6 @@ extern "C" int sb200_pack_server_answer_direct(sb200_pack_server *s, const uint6
     if (fd) {
         if (!v_folding_host) return fail(SB200_ERR_ARG, "pack answer_direct: GSW ciphertexts missing");
         TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st));
-        launch_gsw_negate(s->gsw_neg.p, s->gsw.p, (int)fd, (int)ell, 2, st);
     }
     CHECK_LAUNCH();
     CU(cudaStreamSynchronize(st));

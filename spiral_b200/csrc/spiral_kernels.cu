@@ -138,14 +138,13 @@ void launch_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, cuda
 // Accumulators are unreduced u64 (products < 2^56); they are folded to < 2^61 every 64 j
 // (128 products) with one 32x32 multiply, and Barrett-reduced once at the end.
 // ============================================================================================
-constexpr int kScanThreads = 128;
 constexpr int kScanFoldEvery = 64;
 
 __device__ __forceinline__ uint64_t fold_acc(uint64_t a, uint32_t c32) {      // a mod q preserved, result < 2^61
     return (a & 0xffffffffull) + (uint64_t)(uint32_t)(a >> 32) * c32;
 }
 
-template <int U>
+template <int U, int kScanThreads, int UNR>
 __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
                                                              const uint64_t *__restrict__ db, int dim0, int IC, int ICT,
                                                              int ZT, int JC) {
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
         __syncthreads();
         const uint4 *qz = qs + (size_t)zl * JC * 4;
         if (active)
-#pragma unroll 4
+#pragma unroll UNR
         for (int jj = 0; jj < JC; jj++) {
             const int j = jc0 + jj;
             uint4 d[U];
@@ -219,18 +218,33 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
     }
 }
 
+static int scan_variant() {          // tuning knob (SB200_SCAN_VARIANT): 0 = 128 threads x 2 columns, 1 = 256 threads x 1 column
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SB200_SCAN_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
     const int IC = (int)num_per * 2;
-    const int U = IC >= 256 ? 2 : 1;
-    const int ICT = IC < kScanThreads * U ? IC : kScanThreads * U;
-    int ZT = (kScanThreads * U) / ICT;
+    const int variant = scan_variant();
+    const int T = ((variant & 1) && IC >= 256) ? 256 : 128;
+    const int U = (T == 128 && IC >= 256) ? 2 : 1;
+    const int ICT = IC < T * U ? IC : T * U;
+    int ZT = (T * U) / ICT;
     if (ZT > 8) ZT = 8;
     int JC = (int)dim0;
     while ((size_t)ZT * JC * 64 > 32768 && JC > kScanFoldEvery) JC >>= 1;
-    const size_t smem = (size_t)ZT * JC * 64;
+    size_t smem = (size_t)ZT * JC * 64;
     dim3 grid(kN / ZT, IC / ICT);
-    if (U == 2) { count_launch(); k_scan_spiral<2><<<grid, kScanThreads, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC); }
-    else { count_launch(); k_scan_spiral<1><<<grid, kScanThreads, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC); }
+    // Wave quantisation: 2048 CTAs at 8 resident CTAs/SM (1184 slots) is 1.73 waves - the second wave runs 27 % empty.
+    // Padding the dynamic shared memory to 32 KiB caps residency at 7 CTAs/SM = 1036 slots = 1.98 waves.
+    if (variant >= 4 && grid.x * grid.y == 2048 && smem < 32768) smem = 32768;
+    count_launch();
+    const bool deep = variant == 2 || variant == 3;
+    if (T == 256 && deep)    k_scan_spiral<1, 256, 8><<<grid, 256, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (T == 256)       k_scan_spiral<1, 256, 4><<<grid, 256, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2 && deep) k_scan_spiral<2, 128, 8><<<grid, 128, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2)         k_scan_spiral<2, 128, 4><<<grid, 128, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else                     k_scan_spiral<1, 128, 4><<<grid, 128, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
 }
 
 // ============================================================================================
@@ -283,6 +297,7 @@ struct FoldShape {
     int np;              // ciphertexts per plane AFTER this round
     int planes;          // independent planes folded by the same GSW ciphertext
     int plane_stride;    // ciphertexts between consecutive planes in `cts`
+    int cmux;            // 1: resident path, C_lo + Q (x) (G^-1(C_hi) - G^-1(C_lo)); 0: the reference's two-product form
 };
 __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, FoldShape fs, int cts_per_plane) {
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
@@ -295,12 +310,26 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
     const uint64_t mask = (1ull << bits_per) - 1;
     const uint64_t *src = cts + ((size_t)(plane * fs.plane_stride + ctl) * RC + rc) * kN;
     const SignedDigitPlan plan = make_signed_digit_plan(k, fs.t, bits_per);
+    const uint32_t q = modulus(n);
     uint32_t v[16];
+    if (!fs.cmux) {
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const uint64_t val = __ldg(src + nat_pos(lt, e));
-        v[e] = fs.is_signed ? signed_digit_res(val, plan, modulus(n), n)
-                            : (bits_per <= 29 ? (uint32_t)gadget_digit(val, k, bits_per, mask) : raw_to_res(gadget_digit(val, k, bits_per, mask), n));
+        for (int e = 0; e < 16; e++) {
+            const uint64_t val = __ldg(src + nat_pos(lt, e));
+            v[e] = fs.is_signed ? signed_digit_res(val, plan, q, n)
+                                : (bits_per <= 29 ? (uint32_t)gadget_digit(val, k, bits_per, mask) : raw_to_res(gadget_digit(val, k, bits_per, mask), n));
+        }
+    } else {
+        // CMux form: ctl < np is the LOW ciphertext i, its partner is np + i; one NTT of the digit difference
+        const uint64_t *hi = src + (size_t)fs.np * RC * kN;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const uint64_t a = __ldg(src + nat_pos(lt, e)), b = __ldg(hi + nat_pos(lt, e));
+            uint32_t da, db;
+            if (fs.is_signed) { da = signed_digit_res(a, plan, q, n); db = signed_digit_res(b, plan, q, n); }
+            else { da = raw_to_res(gadget_digit(a, k, bits_per, mask), n); db = raw_to_res(gadget_digit(b, k, bits_per, mask), n); }
+            v[e] = db + 2 * q - da;          // in (0, 4q): a valid lazy NTT input
+        }
     }
     ntt_forward_plane(v, sm[n], lt, n);
     const int m2 = fs.R * fs.t, row = r + k * fs.R;
@@ -328,6 +357,20 @@ __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, co
     const uint4 *C1 = reinterpret_cast<const uint4 *>(scratch + (((size_t)(plane * 2 * fs.np + fs.np + i) * m2) * fs.Cc + c) * 2 * kN) + w4;
     uint64_t acc[4] = {0, 0, 0, 0};
     int cnt = 0;
+    if (fs.cmux) {        // scratch holds one difference-digit set per OUTPUT ciphertext (dense index plane*np + i)
+        const uint4 *Cd = reinterpret_cast<const uint4 *>(scratch + (((size_t)(plane * fs.np + i) * m2) * fs.Cc + c) * 2 * kN) + w4;
+#pragma unroll 4
+        for (int m = grp; m < m2; m += kMacGroups) {
+            const uint4 x = __ldg(Qp + m * qs), y = __ldg(Cd + m * cs);
+            acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
+            acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
+            if (++cnt == 120) {
+                cnt = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
+            }
+        }
+    } else
 #pragma unroll 4
     for (int tm = grp; tm < 2 * m2; tm += kMacGroups) {
         const int h = tm >= m2, m = h ? tm - m2 : tm;
@@ -375,15 +418,26 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict_
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int z = threadIdx.x + 256 * k;
-        dst[z] = crt_compose(sm[0][z], sm[1][z]);
+        uint64_t val = crt_compose(sm[0][z], sm[1][z]);
+        if (fs.cmux) {                      // + C_lo (G * G^-1(C_lo) = C_lo mod Q), canonical result
+            uint64_t lo = dst[z];
+            lo = lo >= kQ ? lo - kQ : lo;
+            val += lo;
+            val = val >= kQ ? val - kQ : val;
+        }
+        dst[z] = val;
     }
 }
 // digits of every input ciphertext + the dense MAC outputs (one per output polynomial)
 size_t fold_scratch_words_generic(size_t cts_in, int R, int Cc, int t) { return cts_in * (size_t)R * t * Cc * 2 * kN + (cts_in / 2 + 1) * (size_t)R * Cc * 2 * kN; }
 void launch_fold_round_generic(uint64_t *cts, int R, int Cc, int t, int is_signed, size_t np_after, size_t planes, size_t plane_stride,
                                const uint32_t *q_dev, const uint32_t *qneg_dev, uint32_t *scratch, cudaStream_t s) {
-    FoldShape fs{R, Cc, t, is_signed, (int)np_after, (int)planes, (int)plane_stride};
-    const int RC = R * Cc, cpp = (int)(2 * np_after);
+    // qneg_dev == nullptr selects the CMux form (resident servers): with Qneg = G - Q (mod Q) and an exact gadget
+    // decomposition,  Qneg (x) G^-1(C_lo) + Q (x) G^-1(C_hi) = C_lo + Q (x) (G^-1(C_hi) - G^-1(C_lo))  (mod Q),
+    // and the output is the canonical representative either way - bit-identical, half the NTTs and MAC traffic.
+    const int cmux = qneg_dev == nullptr;
+    FoldShape fs{R, Cc, t, is_signed, (int)np_after, (int)planes, (int)plane_stride, cmux};
+    const int RC = R * Cc, cpp = (int)((cmux ? 1 : 2) * np_after);
     count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(planes * cpp * RC), t), kNttThreads, 0, s>>>(scratch, cts, fs, cpp);
     uint32_t *macout = scratch + (size_t)planes * cpp * R * t * Cc * 2 * kN;
     count_launch(); k_fold_mac<<<(unsigned)(planes * np_after * RC * 16), 256, 0, s>>>(macout, scratch, q_dev, qneg_dev, fs);
@@ -408,7 +462,7 @@ void launch_db_to_reference(uint64_t *B_ref, const uint64_t *db, size_t dim0, si
 size_t fold_scratch_words(size_t num_per_half, int t_gsw) { return fold_scratch_words_generic(2 * num_per_half, kN1, kN2, t_gsw); }
 // split_and_crt alone (reference src/spiral.cpp:270-341) on `count` ciphertexts: scratch[ct][m][c] dev-NTT
 void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t count, int t_gsw, cudaStream_t s) {
-    FoldShape fs{kN1, kN2, t_gsw, 1, (int)count, 1, (int)count};
+    FoldShape fs{kN1, kN2, t_gsw, 1, (int)count, 1, (int)count, 0};
     if (count) { count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(count * 6), t_gsw), kNttThreads, 0, s>>>(scratch, cts, fs, (int)count); }
 }
 void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,
