@@ -306,7 +306,9 @@ extern "C" int sb200_expandImproved(uint64_t *cv, size_t g, uint32_t t_exp, cons
     TRY(up_ntt(dcv, cv, ncts * 2)); TRY(up_ntt(dWl, W_left, g * 2 * t_exp)); TRY(up_ntt(dWr, W_right, n_right * 2 * t_exp_right));
     CU(dlist.up(list.data(), list.size()));
     build_neg1(neg1.p, (int)g, 0);
-    launch_expand(dcv.p, plan, dWl.p, dWr.p, neg1.p, c0.p, c1.p, ginv.p, dlist.p, offs.data(), cnt.data(), 0); CHECK_LAUNCH();
+    std::vector<uint16_t> hperm(g * kN); build_automorph_perms(hperm.data(), (int)g);
+    DBuf<uint16_t> dperm(hperm.size()); CU(dperm.up(hperm.data(), hperm.size()));
+    launch_expand(dcv.p, plan, dWl.p, dWr.p, neg1.p, dperm.p, c0.p, c1.p, ginv.p, dlist.p, offs.data(), cnt.data(), 0); CHECK_LAUNCH();
     return down_ntt(cv, dcv.p, ncts * 2);
 }
 extern "C" int sb200_scalToMat(uint64_t *out_reg, const uint64_t *cv, const uint64_t *W, uint32_t t_conv) {
@@ -392,11 +394,20 @@ struct sb200_server {
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, gsw_neg, scan_out, fold_scratch;
     DBuf<uint64_t> c0, conv_raw, query, cts, resp, final_ct;
     DBuf<int> lists, ct_idx_first, poly_idx_first, ct_idx_bits, poly_idx_bits;
+    DBuf<uint16_t> perms;
     GraphSlot g_convert, g_lift_fold, g_tail;
     // stream = NULL means "the legacy default stream", which cannot be captured: such calls run on this
     // BLOCKING stream instead (implicitly ordered with legacy-default-stream work, e.g. torch's default stream)
-    cudaStream_t own_stream = nullptr;
-    ~sb200_server() { if (own_stream) cudaStreamDestroy(own_stream); }
+    cudaStream_t own_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DBuf<uint64_t> conv_raw2;
+    DBuf<uint32_t> conv_ntt2;
+    ~sb200_server() {
+        if (own_stream) cudaStreamDestroy(own_stream);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+    }
 };
 static inline cudaStream_t ES(sb200_server *s, void *stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
 
@@ -447,8 +458,13 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     for (size_t b = 0; b < nbits; b++) { cb[b] = (int)(s->stopround ? 2 * b + 1 : s->dim0 + b); pb[b] = 2 * cb[b]; pb[nbits + b] = 2 * cb[b] + 1; }
     A(s->lists.up(list.data(), list.size())); A(s->ct_idx_first.up(cf.data(), cf.size())); A(s->poly_idx_first.up(pf.data(), pf.size()));
     if (nbits) { A(s->ct_idx_bits.up(cb.data(), cb.size())); A(s->poly_idx_bits.up(pb.data(), pb.size())); }
+    { std::vector<uint16_t> hperm(s->g * kN); build_automorph_perms(hperm.data(), (int)s->g);
+      A(s->perms.alloc(hperm.size())); A(s->perms.up(hperm.data(), hperm.size())); }
     build_neg1(s->neg1.p, (int)s->g, 0);
     A(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamDefault));
+    A(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)); A(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    A(s->conv_raw2.alloc(std::max((size_t)1, 2 * nbits) * kN)); A(s->conv_ntt2.alloc(std::max((size_t)1, 2 * nbits) * prm->t_conv * PLW));
     A(cudaDeviceSynchronize());
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "server_create: setup failed: %s", cudaGetErrorString(e)); }
     *out = s;
@@ -540,13 +556,23 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
     if (!s->have_params) return fail(SB200_ERR_STATE, "expand_and_convert: public parameters not set");
     return run_stage(s->g_convert, ES(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
         launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, st);       // uploaded query (ref-NTT) -> cv[0]
-        launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
-                      s->offs.data(), s->cnt.data(), st);
-        launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
-                                      (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+        // The GSW bits live in the odd ciphertexts, which are final after round `stopround`; the remaining rounds
+        // only touch even ones.  Fork: RegevToGSW runs on a side stream while the last expansion rounds and
+        // ScalToMat continue on the main one (a fork/join pair inside the captured graph).
+        const int fork_round = s->stopround > 0 ? (int)s->stopround + 1 : (int)s->g;
+        launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
+                      s->offs.data(), s->cnt.data(), st, 0, fork_round);
+        cudaEventRecord(s->ev_fork, st);
+        cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0);
         // no GSW negation on the resident path: the fold uses the CMux form (launch_fold_round_generic)
         launch_regev_to_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
-                            s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+                            s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, s->aux_stream);
+        cudaEventRecord(s->ev_join, s->aux_stream);
+        launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
+                      s->offs.data(), s->cnt.data(), st, fork_round, (int)s->g);
+        launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
+                                      (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+        cudaStreamWaitEvent(st, s->ev_join, 0);
     });
 }
 extern "C" int sb200_server_scan(sb200_server *s, void *stream) {

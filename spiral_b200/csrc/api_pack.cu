@@ -112,6 +112,7 @@ struct sb200_pack_server {
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, gsw_neg, scan_out, fold_scratch, packed;
     DBuf<uint64_t> c0, conv_raw, query, cts, result_cts, packed_raw, resp;
     DBuf<int> lists, ct_idx_first, ct_idx_bits, poly_idx_bits;
+    DBuf<uint16_t> perms;
 };
 
 extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device) {
@@ -153,6 +154,8 @@ extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_par
     A(s->lists.alloc(list.size())); A(s->ct_idx_first.alloc(s->dim0)); A(s->ct_idx_bits.alloc(nbits ? nbits : 1)); A(s->poly_idx_bits.alloc(nbits ? 2 * nbits : 1));
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "pack_server_create: device allocation failed: %s", cudaGetErrorString(e)); }
     A(s->lists.up(list.data(), list.size()));
+    { std::vector<uint16_t> hperm(s->g * kN); build_automorph_perms(hperm.data(), (int)s->g);
+      A(s->perms.alloc(hperm.size())); A(s->perms.up(hperm.data(), hperm.size())); }
     build_neg1(s->neg1.p, (int)s->g, 0);
     A(cudaDeviceSynchronize());
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "pack_server_create: setup failed: %s", cudaGetErrorString(e)); }
@@ -257,7 +260,7 @@ extern "C" int sb200_pack_server_answer(sb200_pack_server *s, const uint64_t *qu
                  CU(cudaMemcpyAsync(s->poly_idx_bits.p, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, st)); }
     CU(cudaMemcpyAsync(s->stage.p, query_cv_host, 2 * PLW * 8, cudaMemcpyHostToDevice, st));
     launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
-    launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p, s->offs.data(), s->cnt.data(), st);
+    launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p, s->offs.data(), s->cnt.data(), st);
     launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_first.p, s->dim0, st);
     launch_regev_to_simple_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)ell, s->V.p,
                                (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);

@@ -65,9 +65,10 @@ size_t expand_active_total(const ExpandPlan &p);
 int expand_build_lists(const ExpandPlan &p, int *list, int *offs, int *cnt);   // host arrays; returns max count
 // cv: dev-NTT [2^g][2]; W_left: [g][2][t_left]; W_right: [g or stopround+1][2][t_right]; neg1: [g] polys
 // c0_raw: maxcnt*2048 u64; c1_ntt: maxcnt polys; ginv: maxcnt*max(t) polys; list_dev: device copy of list
+void build_automorph_perms(uint16_t *perm_host, int g);      // host: g x 2048 slot permutations (one per round)
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
-                   const uint32_t *neg1, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
-                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s);
+                   const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin = 0, int r_end = -1);
 void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s);   // neg1[r] = NTT(-x^(N-2^r)), r < count
 
 // ---- conversion

@@ -10,6 +10,7 @@
 //   regevToSimpleGsw, GSW negation (Pack)   src/testing.cpp:108-140, :1027-1032
 #include "kernels.cuh"
 #include "ntt.cuh"
+#include <vector>
 
 namespace sb200 {
 
@@ -24,10 +25,9 @@ __device__ __forceinline__ uint64_t pack_pb2(uint32_t p, uint32_t b) { return (u
 //   k_expand_accum  : cv[i][row] += sum_k W[row][k] * ginv[slot][k] + row * c1_ntt[slot]
 // ============================================================================================
 __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restrict__ cv, const int *__restrict__ active, int num_in,
-                                                             const uint32_t *__restrict__ neg1, uint32_t tpow,
+                                                             const uint32_t *__restrict__ neg1, uint32_t tpow, const uint16_t *__restrict__ perm,
                                                              uint64_t *__restrict__ c0_raw, uint32_t *__restrict__ c1_ntt) {
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
-    __shared__ __align__(16) uint32_t au[2][kN];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const int slot = blockIdx.x, row = blockIdx.y, i = active[slot];
     uint32_t v[16];
@@ -48,6 +48,17 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = mulmod(a[e], w[e], n);
     }
+    if (row == 1) {
+        // NTT(automorph(c_1)) is a permutation of the NTT slots of c_1 (x -> x^t maps evaluation point
+        // psi^e to psi^(e*t)): no inverse / forward transform needed, identical values modulo q.
+        plane_sync(n);
+#pragma unroll
+        for (int k = 0; k < 16; k++) sm[n][ntt_pos(lt, k)] = v[k];
+        plane_sync(n);
+        uint32_t *dst = c1_ntt + ((size_t)slot * 2 + n) * kN;
+        for (int pos = lt; pos < kN; pos += kPlaneThreads) dst[pos] = sm[n][perm[pos]];
+        return;
+    }
     ntt_inverse_plane(v, sm[n], lt, n);
     __syncthreads();
 #pragma unroll
@@ -60,19 +71,7 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
         const uint32_t it = (uint32_t)z * tpow;
         const int rem = (int)(it & (kN - 1));
         if ((it >> kLogN) & 1) val = kQ - val;                 // 0 -> Q on purpose (reference src/poly.cpp:256)
-        if (row == 0) {
-            c0_raw[(size_t)slot * kN + rem] = val;
-        } else {
-            au[0][rem] = raw_to_res(val, 0);
-            au[1][rem] = raw_to_res(val, 1);
-        }
-    }
-    if (row == 1) {
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = au[n][nat_pos(lt, k)];
-        ntt_forward_plane(v, sm[n], lt, n);
-        store_ntt_regs(v, c1_ntt + ((size_t)slot * 2 + n) * kN, lt);
+        c0_raw[(size_t)slot * kN + rem] = val;
     }
 }
 
@@ -180,11 +179,46 @@ int expand_build_lists(const ExpandPlan &p, int *list, int *offs, int *cnt) {
     return mx;
 }
 
+// perm[r][pos] = NTT slot whose value lands in slot `pos` after the round-r automorphism x -> x^(N/2^r + 1).
+// Host-side: slot `pos` of the reference NTT order holds the evaluation at psi^e(pos); e() is read off a
+// transform of the polynomial x computed with the same butterfly network as ntt.cuh.
+void build_automorph_perms(uint16_t *perm_host, int g) {
+    const uint64_t q = kP, psi = kPsiP;
+    auto mulm = [&](uint64_t a, uint64_t b) { return (uint64_t)((unsigned __int128)a * b % q); };
+    std::vector<uint64_t> pw(2 * kN);
+    pw[0] = 1;
+    for (int i = 1; i < 2 * kN; i++) pw[i] = mulm(pw[i - 1], psi);
+    auto brev = [](uint32_t x) { uint32_t r = 0; for (int i = 0; i < kLogN; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; };
+    // forward transform of a(x) = x, Cooley-Tukey with w[m + i] = psi^bitrev11(m + i) (reference src/core.cpp:254-270)
+    std::vector<uint64_t> a(kN, 0);
+    a[1] = 1;
+    for (int mm = 0; mm < kLogN; mm++) {
+        const int m = 1 << mm, t = kN >> (mm + 1);
+        for (int i = 0; i < m; i++) {
+            const uint64_t w = pw[brev((uint32_t)(m + i))];
+            for (int j = 0; j < t; j++) {
+                uint64_t &x = a[2 * i * t + j], &y = a[2 * i * t + t + j];
+                const uint64_t wy = mulm(w, y), nx = (x + wy) % q, ny = (x + q - wy) % q;
+                x = nx; y = ny;
+            }
+        }
+    }
+    std::vector<int> expo_of_slot(kN), slot_of_expo(2 * kN, -1);
+    for (int e = 1; e < 2 * kN; e += 2) {
+        for (int pos = 0; pos < kN; pos++) if (a[pos] == pw[e]) { expo_of_slot[pos] = e; slot_of_expo[e] = pos; break; }
+    }
+    for (int r = 0; r < g; r++) {
+        const uint32_t t = (uint32_t)(kN >> r) + 1;
+        for (int pos = 0; pos < kN; pos++) perm_host[(size_t)r * kN + pos] = (uint16_t)slot_of_expo[(expo_of_slot[pos] * (uint64_t)t) % (2 * kN)];
+    }
+}
+
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
-                   const uint32_t *neg1, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
-                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s) {
+                   const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end) {
     const int tmax = p.t_left > p.t_right ? p.t_left : p.t_right;
-    for (int r = 0; r < p.g; r++) {
+    if (r_end < 0 || r_end > p.g) r_end = p.g;
+    for (int r = r_begin; r < r_end; r++) {
         if (!cnt[r]) continue;
         const int *act = list_dev + offs[r];
         const uint32_t tpow = (uint32_t)(kN >> r) + 1;
@@ -193,7 +227,7 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         // digits needed this round: t_right only if some odd ciphertext is active
         const bool any_odd = !(p.stopround > 0 && r > p.stopround);
         const int ty = any_odd ? tmax : p.t_left;
-        count_launch(); k_expand_prep<<<dim3(cnt[r], 2), kNttThreads, 0, s>>>(cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, c0_raw, c1_ntt);
+        count_launch(); k_expand_prep<<<dim3(cnt[r], 2), kNttThreads, 0, s>>>(cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
         count_launch(); k_expand_digits<<<dim3(cnt[r], ty), kNttThreads, 0, s>>>(ginv, c0_raw, act, p.t_left, p.t_right, tmax);
         count_launch(); k_expand_accum<<<dim3(cnt[r], 32), 256, 0, s>>>(cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, tmax);
     }
