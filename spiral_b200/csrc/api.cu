@@ -173,6 +173,7 @@ extern "C" int sb200_from_ntt(uint64_t *raw, const uint64_t *in, size_t npolys) 
 // ntt_forward / ntt_inverse on ref-NTT buffers: forward = to_ntt of the plane values; inverse without CRT.
 // Implemented through the raw path: forward treats each plane as a raw polynomial reduced mod its own prime.
 __global__ void __launch_bounds__(sb200::kNttThreads) k_ntt_only(uint32_t *io, int inverse) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][sb200::kPlaneWords];
     const int n = sb200::plane_of_thread(), lt = sb200::lane_in_plane();
     uint32_t *pl = io + ((size_t)blockIdx.x * 2 + n) * sb200::kN;
@@ -195,7 +196,7 @@ static int ntt_only(uint64_t *io, size_t npolys, int inverse) {
     NEED_DEVICE();
     DBuf<uint32_t> d;
     TRY(up_ntt(d, io, npolys));
-    if (npolys) { count_launch(); k_ntt_only<<<(unsigned)npolys, kNttThreads>>>(d.p, inverse); }
+    if (npolys) { count_launch(); launch_pdl(k_ntt_only, dim3((unsigned)npolys), dim3(kNttThreads), 0, 0, d.p, inverse); }
     CHECK_LAUNCH();
     return down_ntt(io, d.p, npolys);
 }

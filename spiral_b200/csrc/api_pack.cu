@@ -14,6 +14,7 @@ void launch_pack(uint32_t *result, const uint64_t *v_ct_raw, const uint32_t *vW,
 
 // dev-NTT 1x1 plaintexts -> the reference's convertDb layout db_buf[z][ii][j] (pure relayout)
 __global__ void k_convert_db_ref(uint64_t *__restrict__ out, const uint32_t *__restrict__ in, size_t count, size_t dim0, size_t num_per) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // (item, z)
     if (idx >= count * sb200::kN) return;
     const size_t z = idx % sb200::kN, i = idx / sb200::kN, ii = i % num_per, j = i / num_per;
@@ -26,7 +27,7 @@ extern "C" int sb200_convertDb(uint64_t *db_buf, const uint64_t *db_ntt, size_t 
     DBuf<uint32_t> din; DBuf<uint64_t> dout(count * kN);
     TRY(up_ntt(din, db_ntt, count));
     const size_t n = count * kN;
-    count_launch(); k_convert_db_ref<<<(unsigned)((n + 255) / 256), 256>>>(dout.p, din.p, count, dim0, num_per); CHECK_LAUNCH();
+    count_launch(); launch_pdl(k_convert_db_ref, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, 0, dout.p, din.p, count, dim0, num_per); CHECK_LAUNCH();
     CU(dout.down(db_buf, count * kN));
     return SB200_OK;
 }

@@ -73,4 +73,13 @@ __device__ __forceinline__ uint64_t gadget_digit(uint64_t val, int k, uint32_t b
     return (val >> (off & 63)) & mask;
 }
 
+// ---- programmatic dependent launch (sm_90+): every kernel of the query path starts with pdl_prologue().
+// launch_dependents lets the NEXT kernel of the stream / graph be scheduled while this one is still running;
+// wait blocks until the PREVIOUS kernel has completed and its writes are visible, so nothing is consumed early.
+// The dozens of short dependent kernels of one query thereby overlap their launch + ramp-up latencies.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 }  // namespace sb200

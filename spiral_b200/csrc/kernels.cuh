@@ -13,6 +13,17 @@ namespace sb200 {
 
 void count_launch(int n = 1);        // our own kernel launches since load (sb200_launch_count)
 uint64_t launch_count();
+bool pdl_enabled();                    // SB200_NO_PDL=1 disables programmatic dependent launch
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 int init_tables();   // builds twiddle tables on the current device (idempotent, per device)
 
 // ---- format conversion at the boundary (reference u64-per-residue NTT layout <-> dev-NTT)

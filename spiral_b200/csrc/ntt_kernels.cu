@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 #include "ntt.cuh"
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -29,6 +30,8 @@ static uint2 h_shoup(uint64_t w, uint64_t q) {
 static std::atomic<uint64_t> g_launch_count{0};
 void count_launch(int n) { g_launch_count.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launch_count.load(); }
+
+bool pdl_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("SB200_NO_PDL"); v = (e && *e == '1') ? 0 : 1; } return v == 1; }
 
 static std::mutex g_tab_mutex;
 static bool g_tab_ready[64] = {false};
@@ -76,22 +79,24 @@ int init_tables() {
 // boundary format conversion
 // --------------------------------------------------------------------------------------------
 __global__ void k_ntt_u64_to_dev(uint32_t *__restrict__ out, const uint64_t *__restrict__ in, size_t nwords) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nwords) return;
     int n = (int)((i / kN) & 1);
     out[i] = reduce_u64(in[i], n);       // the reference may hand over q for 0 (and lazy digits) - canonicalise
 }
 __global__ void k_ntt_dev_to_u64(uint64_t *__restrict__ out, const uint32_t *__restrict__ in, size_t nwords) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nwords) out[i] = in[i];
 }
 void launch_ntt_u64_to_dev(uint32_t *out, const uint64_t *in, size_t npolys, cudaStream_t s) {
     size_t n = npolys * 2 * kN;
-    if (n) { count_launch(); k_ntt_u64_to_dev<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, in, n); }
+    if (n) { count_launch(); launch_pdl(k_ntt_u64_to_dev, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, in, n); }
 }
 void launch_ntt_dev_to_u64(uint64_t *out, const uint32_t *in, size_t npolys, cudaStream_t s) {
     size_t n = npolys * 2 * kN;
-    if (n) { count_launch(); k_ntt_dev_to_u64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, in, n); }
+    if (n) { count_launch(); launch_pdl(k_ntt_dev_to_u64, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, in, n); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -99,6 +104,7 @@ void launch_ntt_dev_to_u64(uint64_t *out, const uint32_t *in, size_t npolys, cud
 // variant is the same map modulo q).  One CTA per polynomial.
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNttThreads) k_to_ntt(uint32_t *__restrict__ out, const uint64_t *__restrict__ raw) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const uint64_t *src = raw + (size_t)blockIdx.x * kN;
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(kNttThreads) k_to_ntt(uint32_t *__restrict__ o
     store_ntt_regs(v, out + ((size_t)blockIdx.x * 2 + n) * kN, lt);
 }
 void launch_to_ntt(uint32_t *out, const uint64_t *raw, size_t npolys, cudaStream_t s) {
-    if (npolys) { count_launch(); k_to_ntt<<<(unsigned)npolys, kNttThreads, 0, s>>>(out, raw); }
+    if (npolys) { count_launch(); launch_pdl(k_to_ntt, dim3((unsigned)npolys), dim3(kNttThreads), 0, s, out, raw); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -130,6 +136,7 @@ __device__ __forceinline__ void intt_crt_store(uint32_t (&v)[16], uint32_t (*sm)
     }
 }
 __global__ void __launch_bounds__(kNttThreads) k_from_ntt(uint64_t *__restrict__ raw, const uint32_t *__restrict__ in) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     uint32_t v[16];
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(kNttThreads) k_from_ntt(uint64_t *__restrict__
     intt_crt_store(v, sm, raw + (size_t)blockIdx.x * kN);
 }
 void launch_from_ntt(uint64_t *raw, const uint32_t *in, size_t npolys, cudaStream_t s) {
-    if (npolys) { count_launch(); k_from_ntt<<<(unsigned)npolys, kNttThreads, 0, s>>>(raw, in); }
+    if (npolys) { count_launch(); launch_pdl(k_from_ntt, dim3((unsigned)npolys), dim3(kNttThreads), 0, s, raw, in); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -145,6 +152,7 @@ void launch_from_ntt(uint64_t *raw, const uint32_t *in, size_t npolys, cudaStrea
 // --------------------------------------------------------------------------------------------
 __global__ void k_matmul(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
                          int rs, int ms, int cs) {
+    pdl_prologue();
     // blockIdx.x = (r*cs + c)*4 + quarter ; 256 threads x uint4 = 1024 words = quarter of a dev-NTT poly
     const int rc = blockIdx.x >> 2, quarter = blockIdx.x & 3;
     const int r = rc / cs, c = rc % cs;
@@ -165,10 +173,11 @@ __global__ void k_matmul(uint32_t *__restrict__ out, const uint32_t *__restrict_
     reinterpret_cast<uint4 *>(out + (size_t)rc * 2 * kN)[w4] = o;
 }
 void launch_matmul(uint32_t *out, const uint32_t *a, const uint32_t *b, int rs, int ms, int cs, cudaStream_t s) {
-    if (rs * cs) { count_launch(); k_matmul<<<rs * cs * 4, 256, 0, s>>>(out, a, b, rs, ms, cs); }
+    if (rs * cs) { count_launch(); launch_pdl(k_matmul, dim3(rs * cs * 4), dim3(256), 0, s, out, a, b, rs, ms, cs); }
 }
 
 __global__ void k_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, size_t nwords) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nwords) return;
     const uint32_t q = modulus((int)((i / kN) & 1));
@@ -176,7 +185,7 @@ __global__ void k_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ a
 }
 void launch_add(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t npolys, cudaStream_t s) {
     size_t n = npolys * 2 * kN;
-    if (n) { count_launch(); k_add<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, a, b, n); }
+    if (n) { count_launch(); launch_pdl(k_add, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, a, b, n); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -189,6 +198,7 @@ __device__ __forceinline__ void automorph_target(int i, uint32_t t, int &rem, bo
     neg = (it >> kLogN) & 1;
 }
 __global__ void k_automorph(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, uint32_t t) {
+    pdl_prologue();
     const uint64_t *src = in + (size_t)blockIdx.x * kN;
     uint64_t *dst = out + (size_t)blockIdx.x * kN;
     for (int i = threadIdx.x; i < kN; i += blockDim.x) {
@@ -199,7 +209,7 @@ __global__ void k_automorph(uint64_t *__restrict__ out, const uint64_t *__restri
     }
 }
 void launch_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t t, cudaStream_t s) {
-    if (npolys) { count_launch(); k_automorph<<<(unsigned)npolys, 256, 0, s>>>(out, in, t); }
+    if (npolys) { count_launch(); launch_pdl(k_automorph, dim3((unsigned)npolys), dim3(256), 0, s, out, in, t); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -209,6 +219,7 @@ void launch_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNttThreads) k_gadget_ntt(uint32_t *__restrict__ out, const uint64_t *__restrict__ raw,
                                                             int mx, int rdim, int cols) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const int col = blockIdx.x, row = blockIdx.y;
@@ -226,9 +237,10 @@ __global__ void __launch_bounds__(kNttThreads) k_gadget_ntt(uint32_t *__restrict
     store_ntt_regs(v, out + (((size_t)row * cols + col) * 2 + n) * kN, lt);
 }
 void launch_gadget_ntt(uint32_t *out, const uint64_t *raw, int mx, int rdim, int cols, cudaStream_t s) {
-    if (mx * cols) { count_launch(); k_gadget_ntt<<<dim3(cols, mx), kNttThreads, 0, s>>>(out, raw, mx, rdim, cols); }
+    if (mx * cols) { count_launch(); launch_pdl(k_gadget_ntt, dim3(dim3(cols, mx)), dim3(kNttThreads), 0, s, out, raw, mx, rdim, cols); }
 }
 __global__ void k_gadget_raw(uint64_t *__restrict__ out, const uint64_t *__restrict__ raw, int mx, int rdim, int cols) {
+    pdl_prologue();
     const int col = blockIdx.x, row = blockIdx.y;
     const int j = row % rdim, k = row / rdim;
     const uint32_t bits_per = get_bits_per(mx / rdim);
@@ -238,7 +250,7 @@ __global__ void k_gadget_raw(uint64_t *__restrict__ out, const uint64_t *__restr
     for (int z = threadIdx.x; z < kN; z += blockDim.x) dst[z] = gadget_digit(src[z], k, bits_per, mask);
 }
 void launch_gadget_raw(uint64_t *out, const uint64_t *raw, int mx, int rdim, int cols, cudaStream_t s) {
-    if (mx * cols) { count_launch(); k_gadget_raw<<<dim3(cols, mx), 256, 0, s>>>(out, raw, mx, rdim, cols); }
+    if (mx * cols) { count_launch(); launch_pdl(k_gadget_raw, dim3(dim3(cols, mx)), dim3(256), 0, s, out, raw, mx, rdim, cols); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -272,11 +284,12 @@ __device__ __forceinline__ uint64_t rescale_one(uint64_t a, uint64_t inp_mod, ui
     return (negv && r != 0) ? out_mod - r : r;
 }
 __global__ void k_rescale(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, size_t n, uint64_t inp_mod, uint64_t out_mod) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = rescale_one(in[i] % kQ, inp_mod, out_mod);
 }
 void launch_rescale(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod, cudaStream_t s) {
-    if (ncoeffs) { count_launch(); k_rescale<<<(unsigned)((ncoeffs + 255) / 256), 256, 0, s>>>(out, in, ncoeffs, inp_mod, out_mod); }
+    if (ncoeffs) { count_launch(); launch_pdl(k_rescale, dim3((unsigned)((ncoeffs + 255) / 256)), dim3(256), 0, s, out, in, ncoeffs, inp_mod, out_mod); }
 }
 
 }  // namespace sb200

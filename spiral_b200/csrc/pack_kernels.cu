@@ -27,6 +27,7 @@ __device__ __forceinline__ uint64_t pack_pb3(uint32_t p, uint32_t b) { return (u
 // ============================================================================================
 __global__ void __launch_bounds__(kNttThreads) k_db_build_pack(uint64_t *__restrict__ db, const uint16_t *__restrict__ pts,
                                                                int dim0, int num_per, uint32_t p_db) {
+    pdl_prologue();
     extern __shared__ __align__(16) uint32_t dyn[];
     uint32_t(*sm)[kPlaneWords] = reinterpret_cast<uint32_t(*)[kPlaneWords]>(dyn);
     uint32_t *stash = dyn + 2 * kPlaneWords;                       // [s*2 + ipar][n][z]
@@ -63,13 +64,14 @@ void launch_db_build_pack(uint64_t *db_plane, const uint16_t *pts_plane, size_t 
     const size_t smem = (2 * kPlaneWords + 4 * 2 * kN) * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_db_build_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    count_launch(); k_db_build_pack<<<dim3((unsigned)(num_per / 2), (unsigned)(dim0 / 2)), kNttThreads, smem, s>>>(db_plane, pts_plane, (int)dim0, (int)num_per, p_db);
+    count_launch(); launch_pdl(k_db_build_pack, dim3(dim3((unsigned)(num_per / 2), (unsigned)(dim0 / 2))), dim3(kNttThreads), smem, s, db_plane, pts_plane, (int)dim0, (int)num_per, p_db);
 }
 
 // ============================================================================================
 // reorientCiphertextsDim1: selected 2x1 dev-NTT cts -> query[z][j][r] PB64
 // ============================================================================================
 __global__ void k_reorient_dim1(uint64_t *__restrict__ out, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx, int dim0) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (j, z), z fastest
     if (idx >= (size_t)dim0 * kN) return;
     const int z = (int)(idx % kN), j = (int)(idx / kN);
@@ -81,7 +83,7 @@ __global__ void k_reorient_dim1(uint64_t *__restrict__ out, const uint32_t *__re
 }
 void launch_reorient_dim1(uint64_t *out, const uint32_t *cv, const int *ct_idx, size_t dim0, cudaStream_t s) {
     const size_t n = dim0 * kN;
-    count_launch(); k_reorient_dim1<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, cv, ct_idx, (int)dim0);
+    count_launch(); launch_pdl(k_reorient_dim1, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, cv, ct_idx, (int)dim0);
 }
 
 // ============================================================================================
@@ -95,6 +97,7 @@ constexpr int kPackScanThreads = 256;
 __global__ void __launch_bounds__(kPackScanThreads) k_scan_pack(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
                                                                 const uint64_t *__restrict__ db, int dim0, int IC, int ICT, int JC,
                                                                 size_t plane_words, size_t out_plane_polys) {
+    pdl_prologue();
     extern __shared__ __align__(16) uint4 qs[];        // [JC pairs][2] uint4, later reused for the reduction
     const int tid = threadIdx.x, JS = kPackScanThreads / ICT;
     const int i = tid % ICT, js = tid / ICT;
@@ -156,7 +159,7 @@ void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, 
     const size_t red = (size_t)JS * ICT * 16;
     if (red > smem) smem = red;
     dim3 grid(kN, IC / ICT, (unsigned)planes);
-    count_launch(); k_scan_pack<<<grid, kPackScanThreads, smem, s>>>(out, query, db, (int)dim0, IC, ICT, JC, db_plane_words, out_plane_polys);
+    count_launch(); launch_pdl(k_scan_pack, dim3(grid), dim3(kPackScanThreads), smem, s, out, query, db, (int)dim0, IC, ICT, JC, db_plane_words, out_plane_polys);
 }
 
 // ============================================================================================
@@ -165,6 +168,7 @@ void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, 
 // ============================================================================================
 __global__ void k_simple_gsw_accum(uint32_t *__restrict__ gsw, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
                                    const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ V, int t_conv, int ell, int nu2) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b, n, z)
     const int nbits = ell * nu2;
     if (idx >= (size_t)nbits * 2 * kN) return;
@@ -193,7 +197,7 @@ void launch_regev_to_simple_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const 
     launch_from_ntt_indexed(scratch_raw, cv, poly_idx, 2 * (size_t)nbits, s);             // raw as (rdim = 2) x nbits
     launch_gadget_ntt(scratch_ntt, scratch_raw, 2 * t_conv, 2, nbits, s);
     const size_t n = (size_t)nbits * 2 * kN;
-    count_launch(); k_simple_gsw_accum<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gsw_out, cv, ct_idx, scratch_ntt, V, t_conv, ell, nu2);
+    count_launch(); launch_pdl(k_simple_gsw_accum, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, gsw_out, cv, ct_idx, scratch_ntt, V, t_conv, ell, nu2);
     if (gsw_neg_out) launch_gsw_negate(gsw_neg_out, gsw_out, nu2, ell, 2, s);
 }
 
@@ -203,6 +207,7 @@ void launch_regev_to_simple_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const 
 // ============================================================================================
 __global__ void k_pack_accum(uint32_t *__restrict__ result, const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ ct2,
                              const uint32_t *__restrict__ vW, int out_n, int t_conv) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row, c, n, z)
     const int rows = out_n + 1, nn = out_n * out_n;
     if (idx >= (size_t)rows * out_n * 2 * kN) return;
@@ -222,6 +227,7 @@ __global__ void k_pack_accum(uint32_t *__restrict__ result, const uint32_t *__re
 }
 // v_ct_raw: n*n cts (2 polys each: row 0, row 1) raw ; scratch_raw: 2*n*n polys ; scratch_ntt: (t_conv + 1) * n*n polys
 __global__ void k_split_rows(uint64_t *__restrict__ rows01, const uint64_t *__restrict__ cts, int count) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (ct, row, z)
     if (idx >= (size_t)count * 2 * kN) return;
     const int z = (int)(idx % kN), row = (int)((idx / kN) & 1), ct = (int)(idx / (2 * kN));
@@ -231,11 +237,11 @@ void launch_pack(uint32_t *result, const uint64_t *v_ct_raw, const uint32_t *vW,
                  uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
     const int nn = out_n * out_n;
     const size_t n1 = (size_t)nn * 2 * kN;
-    count_launch(); k_split_rows<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(scratch_raw, v_ct_raw, nn);
+    count_launch(); launch_pdl(k_split_rows, dim3((unsigned)((n1 + 255) / 256)), dim3(256), 0, s, scratch_raw, v_ct_raw, nn);
     launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, nn, s);                                   // digits of the first rows
     launch_to_ntt(scratch_ntt + (size_t)t_conv * nn * 2 * kN, scratch_raw + (size_t)nn * kN, nn, s);  // second rows
     const size_t n2 = (size_t)(out_n + 1) * out_n * 2 * kN;
-    count_launch(); k_pack_accum<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(result, scratch_ntt, scratch_ntt + (size_t)t_conv * nn * 2 * kN, vW, out_n, t_conv);
+    count_launch(); launch_pdl(k_pack_accum, dim3((unsigned)((n2 + 255) / 256)), dim3(256), 0, s, result, scratch_ntt, scratch_ntt + (size_t)t_conv * nn * 2 * kN, vW, out_n, t_conv);
 }
 
 }  // namespace sb200

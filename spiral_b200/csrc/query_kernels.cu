@@ -27,6 +27,7 @@ __device__ __forceinline__ uint64_t pack_pb2(uint32_t p, uint32_t b) { return (u
 __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restrict__ cv, const int *__restrict__ active, int num_in,
                                                              const uint32_t *__restrict__ neg1, uint32_t tpow, const uint16_t *__restrict__ perm,
                                                              uint64_t *__restrict__ c0_raw, uint32_t *__restrict__ c1_ntt) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const int slot = blockIdx.x, row = blockIdx.y, i = active[slot];
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
 
 __global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restrict__ ginv, const uint64_t *__restrict__ c0_raw,
                                                                const int *__restrict__ active, int t_left, int t_right, int tmax) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const int slot = blockIdx.x, k = blockIdx.y, i = active[slot];
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restr
 __global__ void __launch_bounds__(256) k_expand_accum(uint32_t *__restrict__ cv, const int *__restrict__ active, const uint32_t *__restrict__ ginv,
                                const uint32_t *__restrict__ c1_ntt, const uint32_t *__restrict__ W_left,
                                const uint32_t *__restrict__ W_right, int t_left, int t_right, int tmax) {
+    pdl_prologue();
     // grid (slot, row*16 + segment); CTA = 64 uint4 columns x 4 digit groups (same split as k_fold_mac: every
     // thread's loads are independent, partial sums meet in shared memory)
     __shared__ ulonglong2 part[3][64][2];
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(256) k_expand_accum(uint32_t *__restrict__ cv,
 
 // neg1[r] = NTT(invert(x^(N - 2^r))) = NTT(-x^(N-2^r))   (reference src/spiral.cpp:184-192)
 __global__ void __launch_bounds__(kNttThreads) k_build_neg1(uint32_t *__restrict__ neg1) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane(), r = blockIdx.x;
     const uint32_t q = modulus(n);
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(kNttThreads) k_build_neg1(uint32_t *__restrict
     store_ntt_regs(v, neg1 + ((size_t)r * 2 + n) * kN, lt);
 }
 void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s) {
-    if (count) { count_launch(); k_build_neg1<<<count, kNttThreads, 0, s>>>(neg1_dev); }
+    if (count) { count_launch(); launch_pdl(k_build_neg1, dim3(count), dim3(kNttThreads), 0, s, neg1_dev); }
 }
 
 // host side: per-round active lists, exactly the reference's skip rules (src/spiral.cpp:1701-1702)
@@ -227,9 +231,9 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         // digits needed this round: t_right only if some odd ciphertext is active
         const bool any_odd = !(p.stopround > 0 && r > p.stopround);
         const int ty = any_odd ? tmax : p.t_left;
-        count_launch(); k_expand_prep<<<dim3(cnt[r], 2), kNttThreads, 0, s>>>(cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
-        count_launch(); k_expand_digits<<<dim3(cnt[r], ty), kNttThreads, 0, s>>>(ginv, c0_raw, act, p.t_left, p.t_right, tmax);
-        count_launch(); k_expand_accum<<<dim3(cnt[r], 32), 256, 0, s>>>(cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, tmax);
+        count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
+        count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, tmax);
+        count_launch(); launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, tmax);
     }
 }
 
@@ -239,6 +243,7 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
 // raw[slot] = from_ntt(poly src[poly_idx[slot]])
 __global__ void __launch_bounds__(kNttThreads) k_from_ntt_indexed(uint64_t *__restrict__ raw, const uint32_t *__restrict__ in,
                                                                   const int *__restrict__ poly_idx) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     uint32_t v[16];
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(kNttThreads) k_from_ntt_indexed(uint64_t *__re
     }
 }
 void launch_from_ntt_indexed(uint64_t *raw, const uint32_t *in, const int *poly_idx, size_t count, cudaStream_t s) {
-    if (count) { count_launch(); k_from_ntt_indexed<<<(unsigned)count, kNttThreads, 0, s>>>(raw, in, poly_idx); }
+    if (count) { count_launch(); launch_pdl(k_from_ntt_indexed, dim3((unsigned)count), dim3(kNttThreads), 0, s, raw, in, poly_idx); }
 }
 
 // scalToMat for dim0 ciphertexts, written straight into the scan's query layout
@@ -264,6 +269,7 @@ void launch_from_ntt_indexed(uint64_t *raw, const uint32_t *in, const int *poly_
 // ginv: [t_conv][dim0] polys ; cv row 1 taken from cv[ct_idx[j]]
 __global__ void k_scal_to_mat_accum(uint64_t *__restrict__ query, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
                                     const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int t_conv, int dim0) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (j, z), z fastest
     if (idx >= (size_t)dim0 * kN) return;
     const int z = (int)(idx % kN), j = (int)(idx / kN);
@@ -309,6 +315,7 @@ __global__ void k_scal_to_mat_accum(uint64_t *__restrict__ query, const uint32_t
 // same product but emitted as dev-NTT MatPoly (3 x 2) per ciphertext - the reference's scalToMat output
 __global__ void k_scal_to_mat_ntt(uint32_t *__restrict__ out, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
                                   const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int t_conv, int count) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (j, n, z)
     if (idx >= (size_t)count * 2 * kN) return;
     const int nz = (int)(idx % (2 * kN)), j = (int)(idx / (2 * kN)), n = nz >= kN;
@@ -342,6 +349,7 @@ __global__ void k_scal_to_mat_ntt(uint32_t *__restrict__ out, const uint32_t *__
 __global__ void k_regev_to_gsw_accum(uint32_t *__restrict__ gsw, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
                                      const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, const uint32_t *__restrict__ V,
                                      int t_conv, int ell, int nu2) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b, n, z)
     const int nbits = ell * nu2;
     if (idx >= (size_t)nbits * 2 * kN) return;
@@ -380,6 +388,7 @@ __global__ void k_regev_to_gsw_accum(uint32_t *__restrict__ gsw, const uint32_t 
 // GSW negation: Qneg = NTT(G2 - from_ntt(Q))  per polynomial (d, r, m); G2 = buildGadget(n1, m2)
 // (reference src/spiral.cpp:2361-2378; `long` subtraction, +Q when negative)
 __global__ void __launch_bounds__(kNttThreads) k_gsw_negate(uint32_t *__restrict__ neg, const uint32_t *__restrict__ gsw, int ell, int rows) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     __shared__ __align__(16) uint32_t au[2][kN];
     const int n = plane_of_thread(), lt = lane_in_plane();
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(kNttThreads) k_gsw_negate(uint32_t *__restrict
 }
 void launch_gsw_negate(uint32_t *neg, const uint32_t *gsw, int count, int ell, int rows, cudaStream_t s) {
     const int polys = count * rows * rows * ell;
-    if (polys) { count_launch(); k_gsw_negate<<<polys, kNttThreads, 0, s>>>(neg, gsw, ell, rows); }
+    if (polys) { count_launch(); launch_pdl(k_gsw_negate, dim3(polys), dim3(kNttThreads), 0, s, neg, gsw, ell, rows); }
 }
 
 void launch_scal_to_mat_reoriented(uint64_t *query_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t dim0,
@@ -421,14 +430,14 @@ void launch_scal_to_mat_reoriented(uint64_t *query_out, const uint32_t *cv, cons
     launch_from_ntt_indexed(scratch_raw, cv, poly_idx, dim0, s);
     launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, (int)dim0, s);
     const size_t n = dim0 * kN;
-    count_launch(); k_scal_to_mat_accum<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
+    count_launch(); launch_pdl(k_scal_to_mat_accum, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
 }
 void launch_scal_to_mat_ntt(uint32_t *out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t count,
                             const uint32_t *W, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
     launch_from_ntt_indexed(scratch_raw, cv, poly_idx, count, s);
     launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, (int)count, s);
     const size_t n = count * 2 * kN;
-    count_launch(); k_scal_to_mat_ntt<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, cv, ct_idx, scratch_ntt, W, t_conv, (int)count);
+    count_launch(); launch_pdl(k_scal_to_mat_ntt, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, cv, ct_idx, scratch_ntt, W, t_conv, (int)count);
 }
 // poly_idx: 2*nbits entries - first nbits = row-0 polys of the bit ciphertexts, next nbits = row-1 polys
 void launch_regev_to_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx,
@@ -442,7 +451,7 @@ void launch_regev_to_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const uint32_
     launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, nbits, s);
     launch_gadget_ntt(scratch_ntt + (size_t)t_conv * nbits * 2 * kN, scratch_raw + (size_t)nbits * kN, t_conv, 1, nbits, s);
     const size_t n = (size_t)nbits * 2 * kN;
-    count_launch(); k_regev_to_gsw_accum<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gsw_out, cv, ct_idx, scratch_ntt, W, V, t_conv, t_gsw, nu2);
+    count_launch(); launch_pdl(k_regev_to_gsw_accum, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, gsw_out, cv, ct_idx, scratch_ntt, W, V, t_conv, t_gsw, nu2);
     if (gsw_neg_out) launch_gsw_negate(gsw_neg_out, gsw_out, nu2, t_gsw, 3, s);
 }
 

@@ -33,6 +33,7 @@ constexpr int kDbStashWords = 4 * 2 * kN;   // 4 polys x 2 planes
 
 __global__ void __launch_bounds__(kNttThreads) k_db_build_spiral(uint64_t *__restrict__ db, const uint16_t *__restrict__ pts,
                                                                  int nu1, int nu2, uint32_t p_db, size_t item_begin) {
+    pdl_prologue();
     extern __shared__ __align__(16) uint32_t dyn[];
     uint32_t(*sm)[kPlaneWords] = reinterpret_cast<uint32_t(*)[kPlaneWords]>(dyn);
     uint32_t *stash = dyn + 2 * kPlaneWords;                       // [poly][n][z]
@@ -71,11 +72,12 @@ void launch_db_build_spiral(uint64_t *db, const uint16_t *pts, int nu1, int nu2,
     const size_t smem = (2 * kPlaneWords + kDbStashWords) * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_db_build_spiral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    if (item_count) { count_launch(); k_db_build_spiral<<<(unsigned)item_count, kNttThreads, smem, s>>>(db, pts, nu1, nu2, p_db, item_begin); }
+    if (item_count) { count_launch(); launch_pdl(k_db_build_spiral, dim3((unsigned)item_count), dim3(kNttThreads), smem, s, db, pts, nu1, nu2, p_db, item_begin); }
 }
 
 // reference layout B[z][ii][c][j][m] -> DB'[z][j][ic][m]: per z a (IC x dim0) -> (dim0 x IC) transpose of 16-byte elements
 __global__ void k_db_from_reference(uint64_t *__restrict__ db, const uint64_t *__restrict__ Bref, size_t dim0, size_t IC, size_t z_begin) {
+    pdl_prologue();
     // per z: src is (IC rows x dim0 cols) of 16-byte elements, dst is (dim0 x IC)
     __shared__ ulonglong2 tile[32][33];
     const size_t z = blockIdx.z;      // z relative to the chunk for Bref, absolute z_begin + z for db
@@ -96,19 +98,20 @@ void launch_db_from_reference(uint64_t *db, const uint64_t *B_ref, size_t dim0, 
                               size_t z_count, cudaStream_t s) {
     if (!z_count) return;
     dim3 grid((unsigned)((dim0 + 31) / 32), (unsigned)((ic + 31) / 32), (unsigned)z_count);
-    count_launch(); k_db_from_reference<<<grid, dim3(32, 8), 0, s>>>(db, B_ref, dim0, ic, z_begin);
+    count_launch(); launch_pdl(k_db_from_reference, dim3(grid), dim3(dim3(32, 8)), 0, s, db, B_ref, dim0, ic, z_begin);
 }
 
 void launch_db_to_reference(uint64_t *B_ref, const uint64_t *db, size_t dim0, size_t ic, cudaStream_t s) {
     // the same 16-byte transpose with the roles of (ic, j) swapped
     dim3 grid((unsigned)((ic + 31) / 32), (unsigned)((dim0 + 31) / 32), (unsigned)kN);
-    count_launch(); k_db_from_reference<<<grid, dim3(32, 8), 0, s>>>(B_ref, db, ic, dim0, 0);
+    count_launch(); launch_pdl(k_db_from_reference, dim3(grid), dim3(dim3(32, 8)), 0, s, B_ref, db, ic, dim0, 0);
 }
 
 // ============================================================================================
 // reorientCiphertexts: dev-NTT cts [j][r][m][n][z] -> query[z][j][m][4] PB64 (r = 3 lane zero)
 // ============================================================================================
 __global__ void k_reorient_query(uint64_t *__restrict__ out, const uint32_t *__restrict__ cts, size_t dim0) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (jm, z), z fastest
     if (idx >= dim0 * 2 * kN) return;
     const size_t z = idx % kN, jm = idx / kN, j = jm >> 1, m = jm & 1;
@@ -125,7 +128,7 @@ __global__ void k_reorient_query(uint64_t *__restrict__ out, const uint32_t *__r
 }
 void launch_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, cudaStream_t s) {
     size_t n = dim0 * 2 * kN;
-    count_launch(); k_reorient_query<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, cts, dim0);
+    count_launch(); launch_pdl(k_reorient_query, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, cts, dim0);
 }
 
 // ============================================================================================
@@ -148,6 +151,7 @@ template <int U, int kScanThreads, int UNR>
 __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
                                                              const uint64_t *__restrict__ db, int dim0, int IC, int ICT,
                                                              int ZT, int JC) {
+    pdl_prologue();
     extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4 = 64 bytes per (z, j)
     const int tid = threadIdx.x;
     const int zl = (U == 1) ? tid / ICT : 0;
@@ -240,11 +244,11 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
     if (variant >= 4 && grid.x * grid.y == 2048 && smem < 32768) smem = 32768;
     count_launch();
     const bool deep = variant == 2 || variant == 3;
-    if (T == 256 && deep)    k_scan_spiral<1, 256, 8><<<grid, 256, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (T == 256)       k_scan_spiral<1, 256, 4><<<grid, 256, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2 && deep) k_scan_spiral<2, 128, 8><<<grid, 128, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2)         k_scan_spiral<2, 128, 4><<<grid, 128, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else                     k_scan_spiral<1, 128, 4><<<grid, 128, smem, s>>>(out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    if (T == 256 && deep)    launch_pdl(k_scan_spiral<1, 256, 8>, dim3(grid), dim3(256), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (T == 256)       launch_pdl(k_scan_spiral<1, 256, 4>, dim3(grid), dim3(256), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2 && deep) launch_pdl(k_scan_spiral<2, 128, 8>, dim3(grid), dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2)         launch_pdl(k_scan_spiral<2, 128, 4>, dim3(grid), dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else                     launch_pdl(k_scan_spiral<1, 128, 4>, dim3(grid), dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
 }
 
 // ============================================================================================
@@ -300,6 +304,7 @@ struct FoldShape {
     int cmux;            // 1: resident path, C_lo + Q (x) (G^-1(C_hi) - G^-1(C_lo)); 0: the reference's two-product form
 };
 __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, FoldShape fs, int cts_per_plane) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const int RC = fs.R * fs.Cc;
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
 constexpr int kMacCols = 64, kMacGroups = 4;
 __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, const uint32_t *__restrict__ scratch,
                                                   const uint32_t *__restrict__ q_dev, const uint32_t *__restrict__ qneg_dev, FoldShape fs) {
+    pdl_prologue();
     __shared__ ulonglong2 part[kMacGroups - 1][kMacCols][2];
     const int RC = fs.R * fs.Cc;
     const int op = blockIdx.x >> 4, seg = blockIdx.x & 15;
@@ -402,6 +408,7 @@ __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, co
 }
 // inverse NTT + CRT lift of the dense MAC outputs back into the (strided) ciphertext array
 __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict__ cts, const uint32_t *__restrict__ macout, FoldShape fs) {
+    pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const int RC = fs.R * fs.Cc;
@@ -438,13 +445,14 @@ void launch_fold_round_generic(uint64_t *cts, int R, int Cc, int t, int is_signe
     const int cmux = qneg_dev == nullptr;
     FoldShape fs{R, Cc, t, is_signed, (int)np_after, (int)planes, (int)plane_stride, cmux};
     const int RC = R * Cc, cpp = (int)((cmux ? 1 : 2) * np_after);
-    count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(planes * cpp * RC), t), kNttThreads, 0, s>>>(scratch, cts, fs, cpp);
+    count_launch(); launch_pdl(k_fold_decomp_ntt, dim3(dim3((unsigned)(planes * cpp * RC), t)), dim3(kNttThreads), 0, s, scratch, cts, fs, cpp);
     uint32_t *macout = scratch + (size_t)planes * cpp * R * t * Cc * 2 * kN;
-    count_launch(); k_fold_mac<<<(unsigned)(planes * np_after * RC * 16), 256, 0, s>>>(macout, scratch, q_dev, qneg_dev, fs);
-    count_launch(); k_fold_lift<<<(unsigned)(planes * np_after * RC), kNttThreads, 0, s>>>(cts, macout, fs);
+    count_launch(); launch_pdl(k_fold_mac, dim3((unsigned)(planes * np_after * RC * 16)), dim3(256), 0, s, macout, scratch, q_dev, qneg_dev, fs);
+    count_launch(); launch_pdl(k_fold_lift, dim3((unsigned)(planes * np_after * RC)), dim3(kNttThreads), 0, s, cts, macout, fs);
 }
 // reference reorient_Q layout (packed [z][r*m2 + m], src/spiral.cpp:388-400) -> dev-NTT [r*m2 + m][n][z]
 __global__ void k_unreorient_q(uint32_t *__restrict__ out, const uint64_t *__restrict__ q_reor, int rm_count) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // (rm, z), z fastest
     if (idx >= (size_t)rm_count * kN) return;
     const int z = (int)(idx % kN), rm = (int)(idx / kN);
@@ -454,7 +462,7 @@ __global__ void k_unreorient_q(uint32_t *__restrict__ out, const uint64_t *__res
 }
 void launch_unreorient_q(uint32_t *out, const uint64_t *q_reor, int rm_count, cudaStream_t s) {
     const size_t n = (size_t)rm_count * kN;
-    count_launch(); k_unreorient_q<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, q_reor, rm_count);
+    count_launch(); launch_pdl(k_unreorient_q, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, out, q_reor, rm_count);
 }
 // scan layout -> reference layout (inverse of launch_db_from_reference), whole database
 void launch_db_to_reference(uint64_t *B_ref, const uint64_t *db, size_t dim0, size_t ic, cudaStream_t s);
@@ -463,7 +471,7 @@ size_t fold_scratch_words(size_t num_per_half, int t_gsw) { return fold_scratch_
 // split_and_crt alone (reference src/spiral.cpp:270-341) on `count` ciphertexts: scratch[ct][m][c] dev-NTT
 void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t count, int t_gsw, cudaStream_t s) {
     FoldShape fs{kN1, kN2, t_gsw, 1, (int)count, 1, (int)count, 0};
-    if (count) { count_launch(); k_fold_decomp_ntt<<<dim3((unsigned)(count * 6), t_gsw), kNttThreads, 0, s>>>(scratch, cts, fs, (int)count); }
+    if (count) { count_launch(); launch_pdl(k_fold_decomp_ntt, dim3(dim3((unsigned)(count * 6), t_gsw)), dim3(kNttThreads), 0, s, scratch, cts, fs, (int)count); }
 }
 void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,
                        int t_gsw, uint32_t *scratch, cudaStream_t s) {
