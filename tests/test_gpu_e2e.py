@@ -19,7 +19,7 @@ def sb_params(so):
     return SpiralParams(so.nu1, so.nu2, so.t_gsw, so.t_conv, so.t_exp, so.t_exp_right, so.qp_bits, so.out_n, so.p_db)
 
 
-@pytest.mark.parametrize("cfg,nu1,nu2", [("cfg1", 2, 2), ("cfg1", 4, 1), ("cfg5", 3, 2), ("cfg1", 5, 3), ("cfg1", 6, 2)])
+@pytest.mark.parametrize("cfg,nu1,nu2", [("cfg1", 2, 2), ("cfg1", 4, 1), ("cfg5", 3, 2), ("cfg1", 5, 3), ("cfg1", 6, 2), ("cfg1", 1, 1), ("cfg4", 2, 2), ("cfg3", 4, 2), ("cfg1", 7, 4)])
 def test_server_matches_oracle_and_decodes(sb, oracle, cfg, nu1, nu2):
     s = ol.SpiralSession(oracle, cfg, nu1, nu2, seed=11)
     Bbuf = s.reference_db()
@@ -31,7 +31,8 @@ def test_server_matches_oracle_and_decodes(sb, oracle, cfg, nu1, nu2):
         want_resp, _, want_first = s.oracle_answer(q, Bbuf)
         got = srv.answer(q)
         assert np.array_equal(got, want_resp), f"response differs at idx {idx}"
-        assert np.array_equal(s.decode(got), s.pts[idx]), f"decode failed at idx {idx}"
+        if cfg != "cfg4":      # cfg4's parameters are a Pack-variant set: as a Spiral query they exceed the noise budget
+            assert np.array_equal(s.decode(got), s.pts[idx]), f"decode failed at idx {idx}"
     srv.close()
     s.close()
 
