@@ -403,15 +403,6 @@ struct sb200_server {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DBuf<uint64_t> conv_raw2;
     DBuf<uint32_t> conv_ntt2;
-    // whole-expansion dataflow kernel (mega_kernels.cu): two segments (before / after the RegevToGSW fork)
-    bool use_mega = false;
-    int n_sm = 148;
-    MegaArgs mega[2];
-    DBuf<MegaItem> mega_items[2];
-    DBuf<uint8_t> mega_store_partner;
-    DBuf<int> mega_partner_slot, mega_counters;
-    DBuf<uint64_t> mega_c0;
-    DBuf<uint32_t> mega_c1, mega_ginv;
     ~sb200_server() {
         if (own_stream) cudaStreamDestroy(own_stream);
         if (aux_stream) cudaStreamDestroy(aux_stream);
@@ -477,43 +468,6 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     A(s->conv_raw2.alloc(std::max((size_t)1, 2 * nbits) * kN)); A(s->conv_ntt2.alloc(std::max((size_t)1, 2 * nbits) * prm->t_conv * PLW));
     A(cudaDeviceSynchronize());
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "server_create: setup failed: %s", cudaGetErrorString(e)); }
-    {   // dataflow expansion (SB200_NO_MEGA=1 keeps the per-phase kernels)
-        const char *nm = getenv("SB200_NO_MEGA");
-        s->use_mega = !(nm && *nm == '1') && s->g <= (size_t)kMegaMaxRounds;
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->n_sm = prop.multiProcessorCount;
-        if (s->use_mega) {
-            const int fork_round = s->stopround > 0 ? (int)s->stopround + 1 : (int)s->g;
-            const int n_cts = 1 << s->g;
-            const size_t cnt_ints = 3 * s->g * n_cts + 8;
-            MegaPlan mp[2];
-            build_mega_plan(mp[0], s->plan, list.data(), s->offs.data(), s->cnt.data(), 0, fork_round);
-            build_mega_plan(mp[1], s->plan, list.data(), s->offs.data(), s->cnt.data(), fork_round, (int)s->g);
-            std::vector<uint8_t> sp(mp[0].store_partner);
-            std::vector<int> ps(mp[0].partner_slot);
-            for (size_t i = 0; i < sp.size(); i++) { sp[i] |= mp[1].store_partner[i]; if (mp[1].partner_slot[i] >= 0) ps[i] = mp[1].partner_slot[i]; }
-            cudaError_t e2 = cudaSuccess;
-            auto A2 = [&](cudaError_t r) { if (e2 == cudaSuccess) e2 = r; };
-            A2(s->mega_store_partner.alloc(sp.size())); A2(s->mega_store_partner.up(sp.data(), sp.size()));
-            A2(s->mega_partner_slot.alloc(ps.size())); A2(s->mega_partner_slot.up(ps.data(), ps.size()));
-            A2(s->mega_counters.alloc(cnt_ints));
-            A2(s->mega_c0.alloc(mp[0].c_slots * kN)); A2(s->mega_c1.alloc(mp[0].c_slots * PLW)); A2(s->mega_ginv.alloc(mp[0].g_polys * PLW));
-            for (int k = 0; k < 2; k++) {
-                A2(s->mega_items[k].alloc(mp[k].items.size() ? mp[k].items.size() : 1));
-                if (!mp[k].items.empty()) A2(s->mega_items[k].up(mp[k].items.data(), mp[k].items.size()));
-                MegaArgs &m = s->mega[k];
-                m.cv = s->cv.p; m.W_left = s->W_left.p; m.W_right = s->W_right.p; m.neg1 = s->neg1.p; m.perms = s->perms.p;
-                m.c0 = s->mega_c0.p; m.c1 = s->mega_c1.p; m.ginv = s->mega_ginv.p; m.active = s->lists.p;
-                m.store_partner = s->mega_store_partner.p; m.partner_slot = s->mega_partner_slot.p;
-                m.items = s->mega_items[k].p; m.n_items = (int)mp[k].items.size();
-                m.t_left = s->plan.t_left; m.t_right = s->plan.t_right; m.n_cts = n_cts;
-                m.prep_done = s->mega_counters.p; m.digit_done = m.prep_done + s->g * n_cts; m.accum_done = m.digit_done + s->g * n_cts;
-                m.next = m.accum_done + s->g * n_cts + k;
-                for (size_t r = 0; r < s->g; r++) m.rounds[r] = mp[k].rounds[r];
-            }
-            if (e2 != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "server_create: dataflow-expansion setup failed: %s", cudaGetErrorString(e2)); }
-        }
-    }
     *out = s;
     return SB200_OK;
 }
@@ -607,10 +561,6 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
         // only touch even ones.  Fork: RegevToGSW runs on a side stream while the last expansion rounds and
         // ScalToMat continue on the main one (a fork/join pair inside the captured graph).
         const int fork_round = s->stopround > 0 ? (int)s->stopround + 1 : (int)s->g;
-        if (s->use_mega) {
-            cudaMemsetAsync(s->mega_counters.p, 0, s->mega_counters.n * sizeof(int), st);
-            launch_expand_mega(s->mega[0], s->n_sm, st);
-        } else
         launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
                       s->offs.data(), s->cnt.data(), st, 0, fork_round);
         cudaEventRecord(s->ev_fork, st);
@@ -619,8 +569,6 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
         launch_regev_to_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
                             s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, s->aux_stream);
         cudaEventRecord(s->ev_join, s->aux_stream);
-        if (s->use_mega) { if (s->mega[1].n_items) launch_expand_mega(s->mega[1], s->n_sm, st); }
-        else
         launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
                       s->offs.data(), s->cnt.data(), st, fork_round, (int)s->g);
         launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,

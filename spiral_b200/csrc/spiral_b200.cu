@@ -3,6 +3,5 @@
 #include "spiral_kernels.cu"
 #include "query_kernels.cu"
 #include "pack_kernels.cu"
-#include "mega_kernels.cu"
 #include "api.cu"
 #include "api_pack.cu"
