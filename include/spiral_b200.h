@@ -150,6 +150,15 @@ int sb200_server_fold_local(sb200_server *srv, void *stream);              /* lo
 uint64_t *sb200_server_partial_ct(sb200_server *srv);                      /* device ptr: this shard's surviving ct (3x2 raw) */
 /* rank 0: `gathered` = world cts (device, order = rank); runs the last log2(world) folds + modulus switch */
 int sb200_server_fold_tail(sb200_server *srv, uint64_t *gathered_dev, uint64_t *total_resp_dev, void *stream);
+/* the exchange step over NVLink peer memory (no NCCL, no host round trip): every rank stores its surviving ciphertext
+ * straight into rank 0's HBM and publishes a flag; rank 0 waits, runs the tail folds + modulus switch.
+ * Setup once: each rank exports a handle, all ranks connect with the world handles in rank order. */
+size_t sb200_server_xchg_handle_bytes(void);
+int sb200_server_xchg_export(sb200_server *srv, void *handle_out);
+int sb200_server_xchg_connect(sb200_server *srv, const void *all_handles);                 /* one process per GPU (cudaIpc) */
+int sb200_server_xchg_connect_local(sb200_server *srv, sb200_server *const *all_servers);  /* shards inside one process */
+int sb200_server_exchange_and_tail(sb200_server *srv, uint64_t *total_resp_dev, void *stream);
+int sb200_server_xchg_error(sb200_server *srv, void *stream);      /* 0 ok; 1/2 = a bounded spin timed out (4 s) */
 int sb200_server_download(sb200_server *srv, uint64_t *dst_host, const uint64_t *src_dev, size_t words, void *stream);
 /* debug taps (device pointers): raw cts after the first dimension; final ct before modulus switch */
 uint64_t *sb200_server_first_dim_cts(sb200_server *srv);

@@ -334,6 +334,12 @@ extern "C" int sb200_regevToGSW(uint64_t *out, const uint64_t *cv_v, uint32_t t_
     return down_ntt(out, dout.p, (size_t)3 * 3 * t);
 }
 
+namespace sb200 {
+void launch_xchg_push(void *target, void *mine, const uint64_t *ct, unsigned int *epoch, int rank, int world, unsigned int *error, cudaStream_t s);
+void launch_xchg_wait(void *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch, int world, unsigned int *error, cudaStream_t s);
+size_t xchg_buffer_bytes(int world);
+size_t xchg_ack_offset();
+}
 // ---------------------------------------------------------------------------------------------
 // tier 3: resident server
 // ---------------------------------------------------------------------------------------------
@@ -403,11 +409,21 @@ struct sb200_server {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DBuf<uint64_t> conv_raw2;
     DBuf<uint32_t> conv_ntt2;
+    // peer-memory exchange (xchg_kernels.cu)
+    DBuf<uint8_t> xchg;                       // this rank's XchgBuf (+ slots)
+    DBuf<unsigned int> xchg_state;            // [0] epoch, [1] error
+    DBuf<unsigned int *> xchg_acks;           // rank 0: device array of pointers to every rank's ack word
+    DBuf<uint64_t> gathered;                  // rank 0: private copy of the world surviving ciphertexts
+    void *xchg_target = nullptr;              // rank 0's XchgBuf as seen from this rank
+    std::vector<void *> ipc_opened;
+    bool xchg_connected = false;
+    GraphSlot g_xchg;
     ~sb200_server() {
         if (own_stream) cudaStreamDestroy(own_stream);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
     }
 };
 static inline cudaStream_t ES(sb200_server *s, void *stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
@@ -466,6 +482,11 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     A(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)); A(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     A(s->conv_raw2.alloc(std::max((size_t)1, 2 * nbits) * kN)); A(s->conv_ntt2.alloc(std::max((size_t)1, 2 * nbits) * prm->t_conv * PLW));
+    if (world > 1) {
+        if (world > 16) { delete s; return fail(SB200_ERR_ARG, "server_create: world > 16 not supported by the peer exchange"); }
+        A(s->xchg.alloc(xchg_buffer_bytes(world))); A(s->xchg_state.alloc(2)); A(s->xchg_acks.alloc(world)); A(s->gathered.alloc((size_t)world * 6 * kN));
+        if (e == cudaSuccess) { A(cudaMemset(s->xchg.p, 0, xchg_buffer_bytes(world))); A(cudaMemset(s->xchg_state.p, 0, 2 * sizeof(unsigned int))); }
+    }
     A(cudaDeviceSynchronize());
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "server_create: setup failed: %s", cudaGetErrorString(e)); }
     *out = s;
@@ -648,6 +669,85 @@ extern "C" int sb200_server_fold_tail(sb200_server *s, uint64_t *gathered, uint6
         launch_rescale(resp_dev + 2 * kN, gathered + 2 * kN, 4 * (size_t)kN, kQ, 4 * s->prm.p_db, st);
     });
 }
+// ---- peer-memory exchange: setup -----------------------------------------------------------------
+extern "C" size_t sb200_server_xchg_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+extern "C" int sb200_server_xchg_export(sb200_server *s, void *handle_out) {
+    if (!s || !handle_out || s->world < 2) return fail(SB200_ERR_ARG, "xchg_export: needs a sharded server");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->xchg.p));
+    memcpy(handle_out, &h, sizeof h);
+    return SB200_OK;
+}
+static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs) {
+    s->xchg_target = bufs[0];
+    if (s->rank == 0) {
+        std::vector<unsigned int *> acks(s->world);
+        for (int r = 0; r < s->world; r++) acks[r] = reinterpret_cast<unsigned int *>(reinterpret_cast<uint8_t *>(bufs[r]) + xchg_ack_offset());
+        CU(s->xchg_acks.up(acks.data(), s->world));
+    }
+    s->xchg_connected = true;
+    return SB200_OK;
+}
+// all_handles: world handles in rank order (each rank's sb200_server_xchg_export), one process per GPU
+extern "C" int sb200_server_xchg_connect(sb200_server *s, const void *all_handles) {
+    if (!s || !all_handles || s->world < 2) return fail(SB200_ERR_ARG, "xchg_connect: needs a sharded server");
+    std::vector<void *> bufs(s->world, nullptr);
+    for (int r = 0; r < s->world; r++) {
+        if (r == s->rank) { bufs[r] = s->xchg.p; continue; }
+        if (s->rank != 0 && r != 0) continue;                     // non-root ranks only need rank 0's buffer
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const uint8_t *>(all_handles) + (size_t)r * sizeof h, sizeof h);
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_opened.push_back(p);
+        bufs[r] = p;
+    }
+    return xchg_finish_connect(s, bufs);
+}
+// same-process variant (several shards driven from one process, e.g. tests on one device): direct pointers
+extern "C" int sb200_server_xchg_connect_local(sb200_server *s, sb200_server *const *all_servers) {
+    if (!s || !all_servers || s->world < 2) return fail(SB200_ERR_ARG, "xchg_connect_local: needs a sharded server");
+    std::vector<void *> bufs(s->world, nullptr);
+    for (int r = 0; r < s->world; r++) {
+        if (!all_servers[r] || all_servers[r]->world != s->world || all_servers[r]->rank != r) return fail(SB200_ERR_ARG, "xchg_connect_local: server %d mismatched", r);
+        bufs[r] = all_servers[r]->xchg.p;
+        if (all_servers[r]->device != s->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, s->device, all_servers[r]->device));
+            if (!can) return fail(SB200_ERR_CUDA, "xchg_connect_local: no peer access %d -> %d", s->device, all_servers[r]->device);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(all_servers[r]->device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CU(pe);
+            cudaGetLastError();
+        }
+    }
+    return xchg_finish_connect(s, bufs);
+}
+// every rank: push the surviving ciphertext into rank 0's HBM; rank 0 additionally waits for all shards, runs the
+// tail folds and the modulus switch into resp_dev (ignored on other ranks)
+extern "C" int sb200_server_exchange_and_tail(sb200_server *s, uint64_t *resp_dev, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->world < 2) return sb200_server_fold_tail(s, s->cts.p, resp_dev, stream);
+    if (!s->xchg_connected) return fail(SB200_ERR_STATE, "exchange_and_tail: peers not connected (sb200_server_xchg_connect)");
+    if (s->rank == 0 && !resp_dev) return fail(SB200_ERR_ARG, "exchange_and_tail: rank 0 needs a response buffer");
+    return run_stage(s->g_xchg, ES(s, stream), resp_dev, nullptr, [&](cudaStream_t st) {
+        launch_xchg_push(s->xchg_target, s->xchg.p, s->cts.p, s->xchg_state.p, s->rank, s->world, s->xchg_state.p + 1, st);
+        if (s->rank == 0) {
+            launch_xchg_wait(s->xchg.p, s->xchg_acks.p, s->gathered.p, s->xchg_state.p, s->world, s->xchg_state.p + 1, st);
+            fold_rounds(s, s->gathered.p, (size_t)s->world, s->prm.nu2 - s->log_world, st);
+            launch_rescale(resp_dev, s->gathered.p, 2 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
+            launch_rescale(resp_dev + 2 * kN, s->gathered.p + 2 * kN, 4 * (size_t)kN, kQ, 4 * s->prm.p_db, st);
+        }
+    });
+}
+// 0 = ok, 1 = push timed out waiting for a free slot, 2 = rank 0 timed out waiting for a shard (synchronises the stream)
+extern "C" int sb200_server_xchg_error(sb200_server *s, void *stream) {
+    if (!s || s->world < 2) return 0;
+    unsigned int st[2] = {0, 0};
+    if (cudaStreamSynchronize(ES(s, stream)) != cudaSuccess) return -1;
+    if (cudaMemcpy(st, s->xchg_state.p, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)st[1];
+}
+
 extern "C" int sb200_server_download(sb200_server *s, uint64_t *dst, const uint64_t *src, size_t words, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     CU(cudaMemcpyAsync(dst, src, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ES(s, stream)));

@@ -3,5 +3,6 @@
 #include "spiral_kernels.cu"
 #include "query_kernels.cu"
 #include "pack_kernels.cu"
+#include "xchg_kernels.cu"
 #include "api.cu"
 #include "api_pack.cu"

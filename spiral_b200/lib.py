@@ -132,6 +132,12 @@ def load_library():
         "sb200_server_partial_ct": (vp, [vp]),
         "sb200_server_fold_tail": (C.c_int, [vp, vp, vp, vp]),
         "sb200_server_download": (C.c_int, [vp, vp, vp, sz, vp]),
+        "sb200_server_xchg_handle_bytes": (sz, []),
+        "sb200_server_xchg_export": (C.c_int, [vp, vp]),
+        "sb200_server_xchg_connect": (C.c_int, [vp, vp]),
+        "sb200_server_xchg_connect_local": (C.c_int, [vp, C.POINTER(vp)]),
+        "sb200_server_exchange_and_tail": (C.c_int, [vp, vp, vp]),
+        "sb200_server_xchg_error": (C.c_int, [vp, vp]),
         "sb200_server_first_dim_cts": (vp, [vp]),
         "sb200_server_query_bytes": (sz, [vp]),
         "sb200_server_response_bytes": (sz, [vp]),

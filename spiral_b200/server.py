@@ -93,6 +93,27 @@ class SpiralServer:
     def fold_tail(self, gathered_ptr, resp_ptr, stream=None):
         check(self.lib.sb200_server_fold_tail(self.h, gathered_ptr, resp_ptr, stream), self.lib)
 
+    # ---- exchange over NVLink peer memory (sharded servers) ----------------------------------
+    def xchg_export(self):
+        buf = C.create_string_buffer(self.lib.sb200_server_xchg_handle_bytes())
+        check(self.lib.sb200_server_xchg_export(self.h, buf), self.lib)
+        return buf.raw
+
+    def xchg_connect(self, handles):
+        """handles: list of world byte strings (every rank's xchg_export()), rank order; one process per GPU."""
+        blob = b"".join(handles)
+        check(self.lib.sb200_server_xchg_connect(self.h, blob), self.lib)
+
+    def xchg_connect_local(self, servers):
+        arr = (C.c_void_p * len(servers))(*[s.h for s in servers])
+        check(self.lib.sb200_server_xchg_connect_local(self.h, arr), self.lib)
+
+    def exchange_and_tail(self, resp_ptr, stream=None):
+        check(self.lib.sb200_server_exchange_and_tail(self.h, resp_ptr, stream), self.lib)
+
+    def xchg_error(self, stream=None):
+        return self.lib.sb200_server_xchg_error(self.h, stream)
+
     def download(self, dev_ptr, words, stream=None):
         out = np.empty(words, dtype=np.uint64)
         check(self.lib.sb200_server_download(self.h, out.ctypes.data, dev_ptr, words, stream), self.lib)

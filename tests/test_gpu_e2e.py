@@ -78,7 +78,24 @@ def test_sharded_servers_reproduce_single_gpu_answer(sb, oracle):
         servers[0].fold_tail(gathered.data_ptr(), resp.data_ptr())
         torch.cuda.synchronize()
         got = resp.cpu().numpy().view(np.uint64)
-        assert np.array_equal(got, want_resp), f"world={world}"
+        assert np.array_equal(got, want_resp), f"world={world} (host-side gather)"
+        # the same exchange through the peer-memory kernels (flags + stores into rank 0's buffer), three queries in a
+        # row so the slot / epoch / ack protocol wraps around; non-root shards push first, rank 0 last
+        for srv in servers:
+            srv.xchg_connect_local(servers)
+        for idx in (41, 7, 60, 41):
+            q2 = s.query(idx)
+            want2, _, _ = s.oracle_answer(q2, Bbuf)
+            for srv in servers:
+                srv.upload_query(q2); srv.expand_and_convert(); srv.first_dim(); srv.fold_local()
+            resp.zero_()
+            torch.cuda.synchronize()
+            for srv in reversed(servers):
+                srv.exchange_and_tail(resp.data_ptr() if srv.rank == 0 else None)
+            assert all(srv.xchg_error() == 0 for srv in servers)
+            torch.cuda.synchronize()
+            got2 = resp.cpu().numpy().view(np.uint64)
+            assert np.array_equal(got2, want2), f"world={world} idx={idx} (peer-memory exchange)"
         for srv in servers:
             srv.close()
     s.close()
