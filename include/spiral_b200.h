@@ -124,6 +124,8 @@ typedef struct sb200_server sb200_server;
 /* shard `rank` of `world` owns second-dimension indices ii = rank (mod world); world = 1 -> whole database */
 int sb200_server_create(sb200_server **out, const sb200_params *prm, int device, int rank, int world);
 void sb200_server_destroy(sb200_server *srv);
+/* another server over the SAME resident database (own workspaces, keys, graphs): one per concurrent client */
+int sb200_server_create_view(sb200_server **out, sb200_server *parent);
 /* database from plaintext items (u16 coefficients, this shard's items only, order j-major: item = j*local_num_per + ii_local) */
 int sb200_server_load_db_items(sb200_server *srv, const uint16_t *pts_host, size_t item_begin, size_t item_count);
 /* database handed over in the reference's layout (the WHOLE B of load_db); the shard's rows are extracted */

@@ -394,6 +394,7 @@ struct sb200_server {
     std::vector<int> offs, cnt;
     int maxcnt = 0, tmax = 0;
     bool have_db = false, have_params = false;
+    const sb200_server *db_owner = nullptr;           // views (sb200_server_create_view) scan another server's resident database
     // device memory
     DBuf<uint64_t> db;                                  // scan layout shard
     DBuf<uint32_t> W_left, W_right, W_conv, V_conv, neg1;
@@ -493,8 +494,21 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     return SB200_OK;
 }
 extern "C" void sb200_server_destroy(sb200_server *s) { delete s; }
+// A second server over the SAME resident database (own workspaces, own public parameters, own streams / graphs):
+// one per concurrent client, so several queries can be in flight on one GPU.  The parent must outlive its views.
+extern "C" int sb200_server_create_view(sb200_server **out, sb200_server *parent) {
+    if (!out || !parent) return fail(SB200_ERR_ARG, "create_view: null argument");
+    const sb200_server *owner = parent->db_owner ? parent->db_owner : parent;
+    int rc = sb200_server_create(out, &parent->prm, parent->device, parent->rank, parent->world);
+    if (rc) return rc;
+    (*out)->db_owner = owner;
+    return SB200_OK;
+}
 
+static inline const uint64_t *server_db(const sb200_server *s) { return s->db_owner ? s->db_owner->db.p : s->db.p; }
+static inline bool server_has_db(const sb200_server *s) { return s->db_owner ? s->db_owner->have_db : s->have_db; }
 static int server_alloc_db(sb200_server *s) {
+    if (s->db_owner) return fail(SB200_ERR_STATE, "this server is a view: load the database through its parent");
     if (s->db.p) return SB200_OK;
     CU(s->db.alloc(s->dim0 * s->local_num_per * 4 * kN));
     return SB200_OK;
@@ -541,7 +555,7 @@ extern "C" int sb200_server_load_db_reference(sb200_server *s, const uint64_t *B
     s->have_db = true;
     return SB200_OK;
 }
-extern "C" uint64_t *sb200_server_db_ptr(sb200_server *s) { return s ? s->db.p : nullptr; }
+extern "C" uint64_t *sb200_server_db_ptr(sb200_server *s) { return s ? const_cast<uint64_t *>(server_db(s)) : nullptr; }
 
 static int server_up_ntt(sb200_server *s, DBuf<uint32_t> &dst, const uint64_t *host, size_t npolys) {
     (void)s;
@@ -599,8 +613,8 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
 }
 extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    if (!s->have_db) return fail(SB200_ERR_STATE, "scan: database not loaded");
-    launch_scan_spiral(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, ES(s, stream));
+    if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan: database not loaded");
+    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, ES(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
 }
@@ -617,9 +631,9 @@ extern "C" int sb200_server_first_dim(sb200_server *s, void *stream) {
 extern "C" int sb200_server_scan_host(sb200_server *s, const uint64_t *reoriented_host, uint64_t *out_ref_ntt_host) {
     // multiplyQueryByDatabase against the resident database with a host-side reoriented query (interposed reference call)
     if (!s || !reoriented_host || !out_ref_ntt_host) return fail(SB200_ERR_ARG, "scan_host: null argument");
-    if (!s->have_db) return fail(SB200_ERR_STATE, "scan_host: database not loaded");
+    if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan_host: database not loaded");
     CU(cudaMemcpy(s->query.p, reoriented_host, s->dim0 * 2 * 4 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    launch_scan_spiral(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, 0); CHECK_LAUNCH();
+    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, 0); CHECK_LAUNCH();
     return down_ntt(out_ref_ntt_host, s->scan_out.p, s->local_num_per * 6);
 }
 extern "C" int sb200_server_copy_partial(sb200_server *s, uint64_t *dst_dev, void *stream) {

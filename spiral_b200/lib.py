@@ -115,6 +115,7 @@ def load_library():
         "sb200_pack_server_response_words": (sz, [vp]),
         "sb200_server_create": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int, C.c_int, C.c_int]),
         "sb200_server_destroy": (None, [vp]),
+        "sb200_server_create_view": (C.c_int, [C.POINTER(vp), vp]),
         "sb200_server_load_db_items": (C.c_int, [vp, u16p, sz, sz]),
         "sb200_server_load_db_reference": (C.c_int, [vp, u64p]),
         "sb200_server_db_ptr": (vp, [vp]),

@@ -23,15 +23,23 @@ def _p64(a):
 
 
 class SpiralServer:
-    def __init__(self, params: SpiralParams, device=0, rank=0, world=1):
+    def __init__(self, params: SpiralParams, device=0, rank=0, world=1, _view_of=None):
         self.lib = load_library()
         self.params = params
         self.rank, self.world = rank, world
         self.dim0, self.num_per = 1 << params.nu1, 1 << params.nu2
         self.local_num_per = self.num_per // world
         h = C.c_void_p()
-        check(self.lib.sb200_server_create(C.byref(h), C.byref(params), device, rank, world), self.lib)
+        if _view_of is None:
+            check(self.lib.sb200_server_create(C.byref(h), C.byref(params), device, rank, world), self.lib)
+        else:
+            check(self.lib.sb200_server_create_view(C.byref(h), _view_of.h), self.lib)
         self.h = h
+        self._parent = _view_of                    # keeps the database owner alive
+
+    def view(self):
+        """A server for another concurrent client over the same resident database."""
+        return SpiralServer(self.params, rank=self.rank, world=self.world, _view_of=self)
 
     # ---- database -----------------------------------------------------------------------
     def load_db_items(self, pts_u16, item_begin=0):

@@ -99,3 +99,38 @@ def test_sharded_servers_reproduce_single_gpu_answer(sb, oracle):
         for srv in servers:
             srv.close()
     s.close()
+
+
+def test_views_share_the_database_and_run_concurrently(sb, oracle):
+    """Two clients (different keys) in flight on one GPU: a view scans its parent's resident database."""
+    import torch
+    a = ol.SpiralSession(oracle, "cfg1", 4, 3, seed=21)
+    b = ol.SpiralSession(oracle, "cfg1", 4, 3, seed=22)
+    b.pts = a.pts                                   # same database, different client keys
+    Bbuf = a.reference_db()
+    srv = SpiralServer(sb_params(a.prm))
+    srv.load_db_items(a.pts.astype(np.uint16))
+    view = srv.view()
+    srv.set_public_params(a.W_left, a.W_right, a.W_conv, a.V_conv)
+    view.set_public_params(b.W_left, b.W_right, b.W_conv, b.V_conv)
+    with pytest.raises(Exception):
+        view.load_db_items(a.pts.astype(np.uint16))  # a view never owns a database
+    qa, qb = a.query(100), b.query(23)
+    want_a, _, _ = a.oracle_answer(qa, Bbuf)
+    want_b, _, _ = b.oracle_answer(qb, Bbuf)
+    sa, sb_ = torch.cuda.Stream(), torch.cuda.Stream()
+    ra = torch.empty(6 * ol.N, dtype=torch.int64, device="cuda")
+    rb = torch.empty(6 * ol.N, dtype=torch.int64, device="cuda")
+    for _ in range(3):                               # interleave the stages of the two clients on two streams
+        srv.upload_query(qa, sa.cuda_stream); view.upload_query(qb, sb_.cuda_stream)
+        srv.expand_and_convert(sa.cuda_stream); view.expand_and_convert(sb_.cuda_stream)
+        view.first_dim(sb_.cuda_stream); srv.first_dim(sa.cuda_stream)
+        srv.fold_local(sa.cuda_stream); view.fold_local(sb_.cuda_stream)
+        view.fold_tail(view.partial_ct_ptr(), rb.data_ptr(), sb_.cuda_stream)
+        srv.fold_tail(srv.partial_ct_ptr(), ra.data_ptr(), sa.cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(ra.cpu().numpy().view(np.uint64), want_a)
+        assert np.array_equal(rb.cpu().numpy().view(np.uint64), want_b)
+    assert np.array_equal(a.decode(ra.cpu().numpy().view(np.uint64)), a.pts[100])
+    assert np.array_equal(b.decode(rb.cpu().numpy().view(np.uint64)), a.pts[23])
+    view.close(); srv.close(); a.close(); b.close()
