@@ -399,7 +399,7 @@ struct sb200_server {
     DBuf<uint64_t> db;                                  // scan layout shard
     DBuf<uint32_t> W_left, W_right, W_conv, V_conv, neg1;
     DBuf<uint64_t> q_stage;                             // uploaded query (ref-NTT)
-    DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, gsw_neg, scan_out, fold_scratch;
+    DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch;
     DBuf<uint64_t> c0, conv_raw, query, cts, resp, final_ct;
     DBuf<int> lists, ct_idx_first, poly_idx_first, ct_idx_bits, poly_idx_bits;
     DBuf<uint16_t> perms;

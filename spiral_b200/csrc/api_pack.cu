@@ -110,7 +110,7 @@ struct sb200_pack_server {
     DBuf<uint64_t> db;
     DBuf<uint32_t> W_left, W_right, V, vW, neg1;
     DBuf<uint64_t> stage;
-    DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, gsw_neg, scan_out, fold_scratch, packed;
+    DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch, packed;
     DBuf<uint64_t> c0, conv_raw, query, cts, result_cts, packed_raw, resp;
     DBuf<int> lists, ct_idx_first, ct_idx_bits, poly_idx_bits;
     DBuf<uint16_t> perms;

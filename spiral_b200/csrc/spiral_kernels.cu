@@ -222,33 +222,22 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
     }
 }
 
-static int scan_variant() {          // tuning knob (SB200_SCAN_VARIANT): 0 = 128 threads x 2 columns, 1 = 256 threads x 1 column
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("SB200_SCAN_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
-}
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
+    // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
+    // best of {128x2, 256x1} x {unroll 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
     const int IC = (int)num_per * 2;
-    const int variant = scan_variant();
-    const int T = ((variant & 1) && IC >= 256) ? 256 : 128;
-    const int U = (T == 128 && IC >= 256) ? 2 : 1;
+    const int T = 128;
+    const int U = IC >= 256 ? 2 : 1;
     const int ICT = IC < T * U ? IC : T * U;
     int ZT = (T * U) / ICT;
     if (ZT > 8) ZT = 8;
     int JC = (int)dim0;
     while ((size_t)ZT * JC * 64 > 32768 && JC > kScanFoldEvery) JC >>= 1;
-    size_t smem = (size_t)ZT * JC * 64;
+    const size_t smem = (size_t)ZT * JC * 64;
     dim3 grid(kN / ZT, IC / ICT);
-    // Wave quantisation: 2048 CTAs at 8 resident CTAs/SM (1184 slots) is 1.73 waves - the second wave runs 27 % empty.
-    // Padding the dynamic shared memory to 32 KiB caps residency at 7 CTAs/SM = 1036 slots = 1.98 waves.
-    if (variant >= 4 && grid.x * grid.y == 2048 && smem < 32768) smem = 32768;
     count_launch();
-    const bool deep = variant == 2 || variant == 3;
-    if (T == 256 && deep)    launch_pdl(k_scan_spiral<1, 256, 8>, dim3(grid), dim3(256), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (T == 256)       launch_pdl(k_scan_spiral<1, 256, 4>, dim3(grid), dim3(256), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2 && deep) launch_pdl(k_scan_spiral<2, 128, 8>, dim3(grid), dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2)         launch_pdl(k_scan_spiral<2, 128, 4>, dim3(grid), dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else                     launch_pdl(k_scan_spiral<1, 128, 4>, dim3(grid), dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    if (U == 2) launch_pdl(k_scan_spiral<2, 128, 4>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else        launch_pdl(k_scan_spiral<1, 128, 4>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
 }
 
 // ============================================================================================
