@@ -358,6 +358,50 @@ def b200_main(args):
         pipelined = {"clients": len(clients), "queries": nq, "ms_per_query_amortised": wall_ms / nq, "queries_per_s": nq / (wall_ms * 1e-3),
                      "db_gbs_scanned": srv.db_bytes * nq / (wall_ms * 1e-3) / 1e9,
                      "note": "host wall clock around all streams; every query includes its H2D query upload and D2H response"}
+        # batched first dimension: the clients' expansions run concurrently, ONE database pass serves all of them
+        # (sb200_server_scan_batched), then their folds run concurrently again
+        if len(clients) in (2, 4):
+            evs = [torch.cuda.Event() for _ in clients]
+            ev_scan = torch.cuda.Event()
+
+            def batch_round():
+                for ci, (c, st) in enumerate(zip(clients, streams)):
+                    with torch.cuda.stream(st):
+                        c.upload_query_ptr(q_host.data_ptr(), st.cuda_stream)
+                        c.expand_and_convert(st.cuda_stream)
+                        evs[ci].record(st)
+                with torch.cuda.stream(streams[0]):
+                    for ci in range(1, len(clients)):
+                        streams[0].wait_event(evs[ci])
+                    SpiralServer.scan_batched(clients, streams[0].cuda_stream)
+                    ev_scan.record(streams[0])
+                for ci, (c, st) in enumerate(zip(clients, streams)):
+                    with torch.cuda.stream(st):
+                        st.wait_event(ev_scan)
+                        c.lift(st.cuda_stream); c.fold_local(st.cuda_stream)
+                        c.fold_tail(c.partial_ct_ptr(), resp_devs[ci].data_ptr(), st.cuda_stream)
+                        resp_hosts[ci].copy_(resp_devs[ci], non_blocking=True)
+            for _ in range(3):
+                batch_round()
+            torch.cuda.synchronize()
+            sb0, sb1 = ev(), ev()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                batch_round()
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            # the batched scan alone, bracketed by events
+            torch.cuda.synchronize()
+            with torch.cuda.stream(streams[0]):
+                sb0.record(streams[0])
+                for _ in range(5):
+                    SpiralServer.scan_batched(clients, streams[0].cuda_stream)
+                sb1.record(streams[0])
+            torch.cuda.synchronize()
+            nq = args.steps * len(clients)
+            pipelined["batched_scan"] = {"queries_per_pass": len(clients), "ms_per_query_amortised": wall_ms / nq, "queries_per_s": nq / (wall_ms * 1e-3),
+                                         "scan_pass_ms": sb0.elapsed_time(sb1) / 5,
+                                         "effective_db_gbs_per_query_stream": srv.db_bytes * len(clients) / (sb0.elapsed_time(sb1) / 5 * 1e-3) / 1e9}
         for c in clients[1:]:
             c.close()
         torch.cuda.set_stream(tstream)

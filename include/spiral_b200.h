@@ -143,7 +143,11 @@ int sb200_server_upload_query(sb200_server *srv, const uint64_t *query_cv_host, 
 int sb200_server_expand_and_convert(sb200_server *srv, void *stream);      /* expansion + ScalToMat + RegevToGSW (+negation) */
 int sb200_server_first_dim(sb200_server *srv, void *stream);               /* scan + INTT + CRT lift */
 int sb200_server_scan(sb200_server *srv, void *stream);                    /* multiplyQueryByDatabase only (src/spiral.cpp:628) */
+/* batched first dimension: `count` (2 or 4) servers sharing one database answered in ONE database pass */
+int sb200_server_scan_batched(sb200_server *const *servers, int count, void *stream);
 int sb200_server_lift(sb200_server *srv, void *stream);                    /* nttInvAndCrtLiftCiphertexts only (src/spiral.cpp:437) */
+/* batched first dimension: `count` (2 or 4) servers sharing one database answered in ONE database pass */
+int sb200_server_scan_batched(sb200_server *const *servers, int count, void *stream);
 /* interposed multiplyQueryByDatabase: host reoriented query in, ref-NTT host ciphertexts out, database stays resident */
 int sb200_server_scan_host(sb200_server *srv, const uint64_t *reoriented_host, uint64_t *out_ref_ntt_host);
 int sb200_server_copy_partial(sb200_server *srv, uint64_t *dst_dev, void *stream);   /* D2D copy of the shard's surviving ct */

@@ -618,6 +618,22 @@ extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     CHECK_LAUNCH();
     return SB200_OK;
 }
+// One pass over the database for `count` (2 or 4) servers that share it (a parent and its views): every server's own
+// converted query is scanned, every server's own ciphertext buffer is filled.  Launched on `stream`.
+extern "C" int sb200_server_scan_batched(sb200_server *const *servers, int count, void *stream) {
+    if (!servers || (count != 2 && count != 4)) return fail(SB200_ERR_ARG, "scan_batched: count must be 2 or 4");
+    sb200_server *s0 = servers[0];
+    if (!s0 || !server_has_db(s0)) return fail(SB200_ERR_STATE, "scan_batched: database not loaded");
+    const uint64_t *q[4]; uint32_t *o[4];
+    for (int b = 0; b < count; b++) {
+        if (!servers[b] || server_db(servers[b]) != server_db(s0)) return fail(SB200_ERR_ARG, "scan_batched: servers must share one database");
+        q[b] = servers[b]->query.p; o[b] = servers[b]->scan_out.p;
+    }
+    if (launch_scan_spiral_batched(o, q, count, server_db(s0), s0->dim0, s0->local_num_per, ES(s0, stream)) != 0)
+        return fail(SB200_ERR_ARG, "scan_batched: needs 2 * num_per to be a multiple of 128");
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
 extern "C" int sb200_server_lift(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     launch_from_ntt(s->cts.p, s->scan_out.p, s->local_num_per * 6, ES(s, stream));

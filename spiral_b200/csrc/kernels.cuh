@@ -59,6 +59,9 @@ void launch_unreorient_q(uint32_t *out, const uint64_t *q_reor, int rm_count, cu
 void launch_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, cudaStream_t s);
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s);
 
+int launch_scan_spiral_batched(uint32_t *const *out, const uint64_t *const *query, int count, const uint64_t *db, size_t dim0,
+                               size_t num_per, cudaStream_t s);   // count in {2,4}: queries sharing one database pass
+
 // ---- folding (Spiral): cts raw [2*num_per][3][2][2048] -> first num_per folded in place.
 // q_dev / qneg_dev: dev-NTT (3 x 3*t_gsw) GSW ciphertext of THIS round.
 void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,

@@ -240,6 +240,93 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
     else        launch_pdl(k_scan_spiral<1, 128, 4>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
 }
 
+// ---- batched first dimension: BQ queries answered in ONE pass over the database ------------------------------
+// (SURVEY 8f, rank 1).  The single-query scan uses ~30 % of the FMA pipe at full HBM bandwidth, so several queries can
+// share every 16-byte database load: per load 12*BQ MACs against BQ query slices in shared memory.  CTA = 128 threads,
+// one column each, on one (z, 128-column tile); accumulators BQ x 6 u64 per thread.
+struct ScanBatchArgs {
+    const uint64_t *query[8];
+    uint32_t *out[8];
+};
+template <int BQ>
+__global__ void __launch_bounds__(128) k_scan_spiral_batched(const __grid_constant__ ScanBatchArgs a, const uint64_t *__restrict__ db,
+                                                             int dim0, int IC, int JC) {
+    pdl_prologue();
+    extern __shared__ __align__(16) uint4 qs[];        // [BQ][JC][4]
+    const int tid = threadIdx.x, z = blockIdx.x, ic = blockIdx.y * 128 + tid;
+    const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+    uint64_t acc[BQ][3][2];
+#pragma unroll
+    for (int b = 0; b < BQ; b++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) acc[b][r][0] = acc[b][r][1] = 0;
+    const uint4 *dbz = reinterpret_cast<const uint4 *>(db) + ((size_t)z * dim0) * IC + ic;
+    for (int jc0 = 0; jc0 < dim0; jc0 += JC) {
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < BQ; b++) {
+            const uint4 *qg = reinterpret_cast<const uint4 *>(a.query[b]) + ((size_t)z * dim0 + jc0) * 4;
+            for (int e = tid; e < JC * 4; e += 128) qs[(size_t)b * JC * 4 + e] = __ldg(qg + e);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int jj = 0; jj < JC; jj++) {
+            const uint4 d = ld_stream_u4(dbz + (size_t)(jc0 + jj) * IC);
+#pragma unroll
+            for (int b = 0; b < BQ; b++) {
+                const uint4 *q = qs + ((size_t)b * JC + jj) * 4;
+                const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+                acc[b][0][0] += (uint64_t)q0.x * d.x;  acc[b][0][1] += (uint64_t)q0.y * d.y;
+                acc[b][1][0] += (uint64_t)q0.z * d.x;  acc[b][1][1] += (uint64_t)q0.w * d.y;
+                acc[b][2][0] += (uint64_t)q1.x * d.x;  acc[b][2][1] += (uint64_t)q1.y * d.y;
+                acc[b][0][0] += (uint64_t)q2.x * d.z;  acc[b][0][1] += (uint64_t)q2.y * d.w;
+                acc[b][1][0] += (uint64_t)q2.z * d.z;  acc[b][1][1] += (uint64_t)q2.w * d.w;
+                acc[b][2][0] += (uint64_t)q3.x * d.z;  acc[b][2][1] += (uint64_t)q3.y * d.w;
+            }
+            if ((jj & (kScanFoldEvery - 1)) == kScanFoldEvery - 1) {
+#pragma unroll
+                for (int b = 0; b < BQ; b++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        acc[b][r][0] = fold_acc(acc[b][r][0], c32p);
+                        acc[b][r][1] = fold_acc(acc[b][r][1], c32b);
+                    }
+            }
+        }
+    }
+    const int i = ic >> 1, c = ic & 1;
+#pragma unroll
+    for (int b = 0; b < BQ; b++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            uint32_t *o = a.out[b] + ((((size_t)i * kN1 + r) * kN2 + c) * 2) * kN + z;
+            o[0] = reduce_u64(acc[b][r][0], 0);
+            o[kN] = reduce_u64(acc[b][r][1], 1);
+        }
+}
+// count in {2, 4}; requires IC = 2 * num_per to be a multiple of 128
+int launch_scan_spiral_batched(uint32_t *const *out, const uint64_t *const *query, int count, const uint64_t *db, size_t dim0,
+                               size_t num_per, cudaStream_t s) {
+    const int IC = (int)num_per * 2;
+    if ((count != 2 && count != 4) || IC % 128) return -1;
+    ScanBatchArgs a;
+    for (int b = 0; b < count; b++) { a.query[b] = query[b]; a.out[b] = out[b]; }
+    int JC = (int)dim0;
+    while ((size_t)count * JC * 64 > 65536 && JC > kScanFoldEvery) JC >>= 1;
+    const size_t smem = (size_t)count * JC * 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_scan_spiral_batched<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        cudaFuncSetAttribute(k_scan_spiral_batched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        attr_set = true;
+    }
+    dim3 grid(kN, IC / 128);
+    count_launch();
+    if (count == 2) launch_pdl(k_scan_spiral_batched<2>, grid, dim3(128), smem, s, a, db, (int)dim0, IC, JC);
+    else            launch_pdl(k_scan_spiral_batched<4>, grid, dim3(128), smem, s, a, db, (int)dim0, IC, JC);
+    return 0;
+}
+
 // ============================================================================================
 // Folding  (foldOneFurtherDimension, src/spiral.cpp:1349-1410)
 //   C'[i] = Qneg (x) G^-1(C[i]) + Q (x) G^-1(C[num_per + i])

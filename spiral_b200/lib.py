@@ -127,6 +127,7 @@ def load_library():
         "sb200_server_fold_local": (C.c_int, [vp, vp]),
         "sb200_server_scan": (C.c_int, [vp, vp]),
         "sb200_server_lift": (C.c_int, [vp, vp]),
+        "sb200_server_scan_batched": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
         "sb200_server_copy_partial": (C.c_int, [vp, vp, vp]),
         "sb200_server_scan_host": (C.c_int, [vp, u64p, u64p]),
         "sb200_server_load_db_random": (C.c_int, [vp, C.c_uint64]),

@@ -83,6 +83,12 @@ class SpiralServer:
     def scan(self, stream=None):
         check(self.lib.sb200_server_scan(self.h, stream), self.lib)
 
+    @staticmethod
+    def scan_batched(servers, stream=None):
+        """One database pass for 2 or 4 servers sharing a database (a parent and its views)."""
+        arr = (C.c_void_p * len(servers))(*[s.h for s in servers])
+        check(servers[0].lib.sb200_server_scan_batched(arr, len(servers), stream), servers[0].lib)
+
     def lift(self, stream=None):
         check(self.lib.sb200_server_lift(self.h, stream), self.lib)
 

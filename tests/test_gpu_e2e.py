@@ -134,3 +134,40 @@ def test_views_share_the_database_and_run_concurrently(sb, oracle):
     assert np.array_equal(a.decode(ra.cpu().numpy().view(np.uint64)), a.pts[100])
     assert np.array_equal(b.decode(rb.cpu().numpy().view(np.uint64)), a.pts[23])
     view.close(); srv.close(); a.close(); b.close()
+
+
+@pytest.mark.parametrize("count", [2, 4])
+def test_batched_scan_equals_individual_scans(sb, count):
+    """SURVEY 8f #1: several queries answered in one database pass give exactly the single-query ciphertexts."""
+    import torch
+    from spiral_b200 import SpiralParams
+    nu1, nu2 = 4, 6                                   # 2 * num_per = 128 columns
+    prm = SpiralParams(nu1, nu2, 8, 4, 8, 56, 20, 2, 256)
+    rng = np.random.default_rng(77)
+    N = ol.N
+
+    def rnd(npolys):
+        a = np.empty((npolys, 2, N), dtype=np.uint64)
+        a[:, 0, :] = rng.integers(0, ol.P, size=(npolys, N), dtype=np.uint64)
+        a[:, 1, :] = rng.integers(0, ol.B, size=(npolys, N), dtype=np.uint64)
+        return np.ascontiguousarray(a.reshape(-1))
+    srv = SpiralServer(prm)
+    srv.load_db_items(rng.integers(0, 256, size=(1 << (nu1 + nu2), 4, N), dtype=np.uint16))
+    servers = [srv] + [srv.view() for _ in range(count - 1)]
+    nbits = 8 * nu2
+    g = int(np.ceil(np.log2(nbits + (1 << nu1))))
+    n_right = g                                       # nbits > dim0 -> stopround = 0
+    single = []
+    for s_ in servers:
+        s_.set_public_params(rnd(g * 2 * 8), rnd(n_right * 2 * 56), rnd(3 * 2 * 4), rnd(3 * 2 * 4))
+        s_.upload_query(rnd(2)); s_.expand_and_convert(); s_.first_dim()
+        single.append(s_.first_dim_cts())
+    torch.cuda.synchronize()
+    SpiralServer.scan_batched(servers)
+    for s_ in servers:
+        s_.lift()
+    for k, s_ in enumerate(servers):
+        assert np.array_equal(s_.first_dim_cts(), single[k]), f"query {k} of {count}"
+    assert len({c.tobytes() for c in single}) == count, "the queries must differ for the test to mean anything"
+    for s_ in reversed(servers):
+        s_.close()
