@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
 
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
-    // best of {128x2, 256x1} x {unroll 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
+    // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
     const int IC = (int)num_per * 2;
     const int T = 128;
     const int U = IC >= 256 ? 2 : 1;
