@@ -24,6 +24,21 @@ sys.path.insert(0, ROOT)
 
 CFG1 = dict(t_gsw=8, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=20, out_n=2, p_db=256)   # SURVEY 8d, `./spiral 8 7`
 N_POLY = 2048
+# BASELINE.json configs.  cfg1/cfg2 share one shape (the explicit database is the harder, honest one);
+# cfg1 is the default and the headline; the others are selected with --workload.
+WORKLOADS = {
+    "cfg1": dict(kind="spiral", nu1=8, nu2=7, scaling="weak", prm=CFG1, flags="",
+                 macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256"),
+    "cfg5": dict(kind="spiral", nu1=9, nu2=8, scaling="strong", flags="",
+                 prm=dict(t_gsw=9, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=21, out_n=2, p_db=256),
+                 macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=9 QPBITS=21 PVALUE=256"),
+    "cfg3": dict(kind="pack", nu1=10, nu2=8, scaling="strong", direct=False, flags="--high-rate",
+                 prm=dict(t_gsw=8, t_conv=4, t_exp=16, t_exp_right=56, qp_bits=20, out_n=4, p_db=256),
+                 macros="TEXP=16 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256 OUTN=4", sample=(8, 5)),
+    "cfg4": dict(kind="pack", nu1=11, nu2=3, scaling="strong", direct=True, flags="--high-rate --direct-upload",
+                 prm=dict(t_gsw=3, t_conv=56, t_exp=56, t_exp_right=56, qp_bits=27, out_n=5, p_db=65536),
+                 macros="TEXP=56 TEXPRIGHT=56 TCONV=56 TGSW=3 QPBITS=27 PVALUE=65536 OUTN=5", sample=(9, 3)),
+}
 
 
 def host_isa():

@@ -146,8 +146,6 @@ int sb200_server_scan(sb200_server *srv, void *stream);                    /* mu
 /* batched first dimension: `count` (2 or 4) servers sharing one database answered in ONE database pass */
 int sb200_server_scan_batched(sb200_server *const *servers, int count, void *stream);
 int sb200_server_lift(sb200_server *srv, void *stream);                    /* nttInvAndCrtLiftCiphertexts only (src/spiral.cpp:437) */
-/* batched first dimension: `count` (2 or 4) servers sharing one database answered in ONE database pass */
-int sb200_server_scan_batched(sb200_server *const *servers, int count, void *stream);
 /* interposed multiplyQueryByDatabase: host reoriented query in, ref-NTT host ciphertexts out, database stays resident */
 int sb200_server_scan_host(sb200_server *srv, const uint64_t *reoriented_host, uint64_t *out_ref_ntt_host);
 int sb200_server_copy_partial(sb200_server *srv, uint64_t *dst_dev, void *stream);   /* D2D copy of the shard's surviving ct */
@@ -175,21 +173,38 @@ size_t sb200_server_response_bytes(const sb200_server *srv);
 /* ---- tier 3, Pack variants (testHighRate, src/testing.cpp:777-1155; server statements :1007-1081) ---- */
 typedef struct sb200_pack_server sb200_pack_server;
 int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device);
+/* shard `rank` of `world`: second-dimension indices ii = rank (mod world) of every plane */
+int sb200_pack_server_create_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world);
 void sb200_pack_server_destroy(sb200_pack_server *srv);
-/* one of the out_n^2 database planes: 2^(nu1+nu2) items of one polynomial each (u16 coefficients < p_db) */
+/* one of the out_n^2 database planes: this shard's 2^nu1 * (2^nu2 / world) items of one polynomial each (u16 coefficients
+ * < p_db), j-major: item = j * local_num_per + ii_local */
 int sb200_pack_server_load_plane_items(sb200_pack_server *srv, size_t plane, const uint16_t *pts_host);
-int sb200_pack_server_load_plane_reference(sb200_pack_server *srv, size_t plane, const uint64_t *db_buf_host);   /* convertDb layout */
-int sb200_pack_server_load_random(sb200_pack_server *srv, uint64_t seed);
+/* the WHOLE plane in the reference's convertDb layout (src/testing.cpp:316-340); the shard's rows are extracted */
+int sb200_pack_server_load_plane_reference(sb200_pack_server *srv, size_t plane, const uint64_t *db_buf_host);
+int sb200_pack_server_load_random(sb200_pack_server *srv, uint64_t seed);     /* synthetic plaintexts generated on the device */
 /* W_exp_left g x (2 x t_exp), W_exp_right (stopround+1) x (2 x t_exp_right), V 2 x 2*t_conv (all three may be NULL for
  * direct-upload clients), v_W out_n x ((out_n+1) x t_conv); ref-NTT host buffers */
 int sb200_pack_server_set_public_params(sb200_pack_server *srv, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
                                         const uint64_t *V, const uint64_t *v_W);
-/* total_resp: (out_n+1) x out_n raw; result_cts (optional): out_n^2 folded cts (2x1 raw) before packing */
+/* total_resp: (out_n+1) x out_n raw; result_cts (optional): out_n^2 folded cts (2x1 raw) before packing.  world == 1 only. */
 int sb200_pack_server_answer(sb200_pack_server *srv, const uint64_t *query_cv_host, uint64_t *total_resp_host,
                              uint64_t *result_cts_host, void *stream);
 int sb200_pack_server_answer_direct(sb200_pack_server *srv, const uint64_t *v_firstdim_host, const uint64_t *v_folding_host,
                                     uint64_t *total_resp_host, uint64_t *result_cts_host, void *stream);
-size_t sb200_pack_server_db_bytes(const sb200_pack_server *srv);
+/* staged variants (device-resident between stages; bench.py and the multi-GPU path) */
+int sb200_pack_server_upload_query(sb200_pack_server *srv, const uint64_t *query_cv_host, void *stream);
+int sb200_pack_server_expand_and_convert(sb200_pack_server *srv, void *stream);   /* coefficientExpansion + reorientCiphertextsDim1 + regevToSimpleGsw */
+int sb200_pack_server_upload_direct(sb200_pack_server *srv, const uint64_t *v_firstdim_host, const uint64_t *v_folding_host, void *stream);
+int sb200_pack_server_scan(sb200_pack_server *srv, void *stream);                 /* fastMultiplyQueryByDatabaseDim1, all planes (src/testing.cpp:364) */
+int sb200_pack_server_fold_local(sb200_pack_server *srv, void *stream);           /* from_ntt + local fold rounds: out_n^2 surviving cts */
+uint64_t *sb200_pack_server_partial_cts(sb200_pack_server *srv);                  /* device ptr: [plane] 2x1 raw cts of this shard */
+size_t sb200_pack_server_partial_words(const sb200_pack_server *srv);
+int sb200_pack_server_copy_partial(sb200_pack_server *srv, uint64_t *dst_dev, void *stream);
+/* rank 0: gathered = [world][plane] cts (device, rank order); last log2(world) folds + pack + modulus switch */
+int sb200_pack_server_fold_tail(sb200_pack_server *srv, const uint64_t *gathered_dev, uint64_t *total_resp_dev, void *stream);
+uint64_t *sb200_pack_server_result_cts(sb200_pack_server *srv);                   /* device ptr: folded per-plane cts after fold_tail */
+int sb200_pack_server_download(sb200_pack_server *srv, uint64_t *dst_host, const uint64_t *src_dev, size_t words, void *stream);
+size_t sb200_pack_server_db_bytes(const sb200_pack_server *srv);                  /* this shard */
 size_t sb200_pack_server_response_words(const sb200_pack_server *srv);
 
 #ifdef __cplusplus

@@ -96,11 +96,36 @@ extern "C" int sb200_pack(uint64_t *result, uint32_t out_n, uint32_t t_conv, con
 
 // ---------------------------------------------------------------------------------------------
 // resident Pack server (testHighRate's server statements, src/testing.cpp:1007-1081)
+//
+// Sharding: rank g of `world` owns the second-dimension indices ii = g (mod world) of EVERY plane, so all
+// fold rounds for bits >= log2(world) pair ciphertexts on the same GPU; one exchange of `planes` surviving 2x1
+// ciphertexts per GPU (32 KiB each) precedes the last log2(world) rounds, the packing and the modulus switch on rank 0.
 // ---------------------------------------------------------------------------------------------
+// synthetic plaintext coefficients, uniform in [0, p_db): counter-based (splitmix64), 4 values per thread
+__global__ void k_fill_random_u16(uint16_t *__restrict__ dst, size_t n4, uint32_t p_db, uint64_t seed) {
+    pdl_prologue();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    uint64_t x = seed + (i + 1) * 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull; x ^= x >> 31;
+    ushort4 o;
+    o.x = (uint16_t)((x & 0xffff) % p_db); o.y = (uint16_t)(((x >> 16) & 0xffff) % p_db);
+    o.z = (uint16_t)(((x >> 32) & 0xffff) % p_db); o.w = (uint16_t)((x >> 48) % p_db);
+    reinterpret_cast<ushort4 *>(dst)[i] = o;
+}
+// gathered [world][planes] ciphertexts (2 x 2048 u64 each) -> [planes][world]: the fold kernels want a plane's ciphertexts contiguous
+__global__ void k_transpose_cts(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, int world, int planes) {
+    pdl_prologue();
+    const int ct = blockIdx.x, r = ct / planes, p = ct % planes;          // input ciphertext (r, p)
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(in) + (size_t)ct * sb200::kN;
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out) + ((size_t)p * world + r) * sb200::kN;
+    for (int i = threadIdx.x; i < sb200::kN; i += blockDim.x) dst[i] = src[i];
+}
+
 struct sb200_pack_server {
     sb200_params prm;
-    int device = 0;
-    size_t dim0 = 0, num_per = 0, planes = 0, plane_words = 0;
+    int device = 0, rank = 0, world = 1, log_world = 0;
+    size_t dim0 = 0, num_per = 0, local_num_per = 0, planes = 0, plane_words = 0;
     size_t g = 0, stopround = 0;
     ExpandPlan plan{};
     std::vector<int> offs, cnt;
@@ -111,20 +136,27 @@ struct sb200_pack_server {
     DBuf<uint32_t> W_left, W_right, V, vW, neg1;
     DBuf<uint64_t> stage;
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch, packed;
-    DBuf<uint64_t> c0, conv_raw, query, cts, result_cts, packed_raw, resp;
-    DBuf<int> lists, ct_idx_first, ct_idx_bits, poly_idx_bits;
+    DBuf<uint64_t> c0, conv_raw, query, cts, result_cts, tail_cts, packed_raw, resp;
+    DBuf<int> lists, ct_idx_first, ct_idx_direct, ct_idx_bits, poly_idx_bits;
     DBuf<uint16_t> perms;
+    GraphSlot g_convert, g_fold, g_tail;
+    cudaStream_t own_stream = nullptr;
+    ~sb200_pack_server() { if (own_stream) cudaStreamDestroy(own_stream); }
 };
+static inline cudaStream_t PS(sb200_pack_server *s, void *stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
 
-extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device) {
+extern "C" int sb200_pack_server_create_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world) {
     if (!out || !prm) return fail(SB200_ERR_ARG, "pack_server_create: null argument");
     if (prm->out_n == 0 || prm->nu1 < 1) return fail(SB200_ERR_ARG, "pack_server_create: out_n >= 1 and nu1 >= 1 required");
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(SB200_ERR_ARG, "pack_server_create: world must be a power of two and 0 <= rank < world");
+    if (((size_t)1 << prm->nu2) < (size_t)world) return fail(SB200_ERR_ARG, "pack_server_create: 2^nu2 < world");
     int rc = sb200_init(device);
     if (rc) return rc;
     sb200_pack_server *s = new sb200_pack_server();
-    s->prm = *prm; s->device = device;
-    s->dim0 = (size_t)1 << prm->nu1; s->num_per = (size_t)1 << prm->nu2; s->planes = (size_t)prm->out_n * prm->out_n;
-    s->plane_words = s->dim0 * s->num_per * kN;
+    s->prm = *prm; s->device = device; s->rank = rank; s->world = world; s->log_world = (int)ceil_log2((size_t)world);
+    s->dim0 = (size_t)1 << prm->nu1; s->num_per = (size_t)1 << prm->nu2; s->local_num_per = s->num_per / world;
+    s->planes = (size_t)prm->out_n * prm->out_n;
+    s->plane_words = s->dim0 * s->local_num_per * kN;
     s->plane_loaded.assign(s->planes, false);
     const size_t ell = prm->t_gsw, nbits = ell * prm->nu2;
     // expansion shape (testHighRate :795-798)
@@ -141,61 +173,89 @@ extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_par
     A(s->db.alloc(s->planes * s->plane_words));
     A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc((s->stopround + 1) * 2 * prm->t_exp_right * PLW));
     A(s->V.alloc(2 * 2 * prm->t_conv * PLW)); A(s->vW.alloc(prm->out_n * rows * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
-    A(s->stage.alloc(std::max((size_t)2, (size_t)1024) * PLW));
+    A(s->stage.alloc((size_t)1024 * PLW));
     A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW)); A(s->ginv.alloc((size_t)s->maxcnt * s->tmax * PLW));
     A(s->c0.alloc((size_t)s->maxcnt * kN));
     const size_t conv_polys = std::max(2 * nbits, s->planes * 2);
     A(s->conv_raw.alloc(std::max(conv_polys, (size_t)1) * kN));
     A(s->conv_ntt.alloc(std::max((size_t)2 * prm->t_conv * nbits, (prm->t_conv + 1) * s->planes) * PLW));
     A(s->gsw.alloc(std::max(prm->nu2, 1u) * 2 * 2 * ell * PLW));
-    A(s->query.alloc(s->dim0 * 2 * kN)); A(s->scan_out.alloc(s->planes * s->num_per * 2 * PLW));
-    A(s->cts.alloc(s->planes * s->num_per * 2 * kN)); A(s->result_cts.alloc(s->planes * 2 * kN));
-    A(s->fold_scratch.alloc(fold_scratch_words_generic(std::max(s->planes * s->num_per, (size_t)2), 2, 1, (int)ell)));
+    A(s->query.alloc(s->dim0 * 2 * kN)); A(s->scan_out.alloc(s->planes * s->local_num_per * 2 * PLW));
+    A(s->cts.alloc(s->planes * s->local_num_per * 2 * kN)); A(s->result_cts.alloc(s->planes * 2 * kN));
+    A(s->tail_cts.alloc(s->planes * (size_t)world * 2 * kN));
+    A(s->fold_scratch.alloc(fold_scratch_words_generic(std::max(s->planes * std::max(s->local_num_per, (size_t)world), (size_t)2), 2, 1, (int)ell)));
     A(s->packed.alloc(rows * prm->out_n * PLW)); A(s->packed_raw.alloc(rows * prm->out_n * kN)); A(s->resp.alloc(rows * prm->out_n * kN));
-    A(s->lists.alloc(list.size())); A(s->ct_idx_first.alloc(s->dim0)); A(s->ct_idx_bits.alloc(nbits ? nbits : 1)); A(s->poly_idx_bits.alloc(nbits ? 2 * nbits : 1));
+    A(s->lists.alloc(list.size())); A(s->ct_idx_first.alloc(s->dim0)); A(s->ct_idx_direct.alloc(s->dim0));
+    A(s->ct_idx_bits.alloc(nbits ? nbits : 1)); A(s->poly_idx_bits.alloc(nbits ? 2 * nbits : 1));
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "pack_server_create: device allocation failed: %s", cudaGetErrorString(e)); }
     A(s->lists.up(list.data(), list.size()));
+    // ciphertext selections: packed query = reorientCiphertextsDim1(..., 2) and regevToSimpleGsw(..., 2, 1) (:1018, :1024);
+    // direct upload = the 2^nu1 first-dimension ciphertexts as they arrive
+    std::vector<int> cf(s->dim0), cd(s->dim0), cb(nbits), pb(2 * nbits);
+    for (size_t j = 0; j < s->dim0; j++) { cf[j] = (int)(2 * j); cd[j] = (int)j; }
+    for (size_t b = 0; b < nbits; b++) { cb[b] = (int)(2 * b + 1); pb[b] = 2 * cb[b]; pb[nbits + b] = 2 * cb[b] + 1; }
+    A(s->ct_idx_first.up(cf.data(), cf.size())); A(s->ct_idx_direct.up(cd.data(), cd.size()));
+    if (nbits) { A(s->ct_idx_bits.up(cb.data(), cb.size())); A(s->poly_idx_bits.up(pb.data(), pb.size())); }
     { std::vector<uint16_t> hperm(s->g * kN); build_automorph_perms(hperm.data(), (int)s->g);
       A(s->perms.alloc(hperm.size())); A(s->perms.up(hperm.data(), hperm.size())); }
     build_neg1(s->neg1.p, (int)s->g, 0);
+    A(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamDefault));
     A(cudaDeviceSynchronize());
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "pack_server_create: setup failed: %s", cudaGetErrorString(e)); }
     *out = s;
     return SB200_OK;
 }
+extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device) {
+    return sb200_pack_server_create_sharded(out, prm, device, 0, 1);
+}
 extern "C" void sb200_pack_server_destroy(sb200_pack_server *s) { delete s; }
 
+// pts: this shard's items of the plane, j-major: item = j * local_num_per + ii_local (ii = rank + world * ii_local)
 extern "C" int sb200_pack_server_load_plane_items(sb200_pack_server *s, size_t plane, const uint16_t *pts) {
     if (!s || !pts || plane >= s->planes) return fail(SB200_ERR_ARG, "load_plane_items: bad argument");
-    if (s->num_per < 2) return fail(SB200_ERR_ARG, "load_plane_items: num_per >= 2 required (use load_plane_reference)");
-    const size_t items = s->dim0 * s->num_per;
+    CU(cudaSetDevice(s->device));
+    const size_t items = s->dim0 * s->local_num_per;
     DBuf<uint16_t> d(items * kN);
     CU(d.up(pts, items * kN));
-    launch_db_build_pack(s->db.p + plane * s->plane_words, d.p, s->dim0, s->num_per, (uint32_t)s->prm.p_db, 0); CHECK_LAUNCH();
+    launch_db_build_pack(s->db.p + plane * s->plane_words, d.p, s->dim0, s->local_num_per, (uint32_t)s->prm.p_db, 0); CHECK_LAUNCH();
     CU(cudaDeviceSynchronize());
     s->plane_loaded[plane] = true;
     return SB200_OK;
 }
+// db_buf: the WHOLE plane in the reference's convertDb layout db_buf[z][ii][j]; the shard's rows ii = rank (mod world) are taken
 extern "C" int sb200_pack_server_load_plane_reference(sb200_pack_server *s, size_t plane, const uint64_t *db_buf) {
     if (!s || !db_buf || plane >= s->planes) return fail(SB200_ERR_ARG, "load_plane_reference: bad argument");
-    const size_t zc = 64, row = s->num_per * s->dim0;
+    CU(cudaSetDevice(s->device));
+    const size_t zc = 64, row = s->local_num_per * s->dim0;
     DBuf<uint64_t> stage(zc * row);
     for (size_t z0 = 0; z0 < (size_t)kN; z0 += zc) {
-        CU(stage.up(db_buf + z0 * row, zc * row));
-        launch_db_from_reference(s->db.p + plane * s->plane_words, stage.p, s->dim0 / 2, s->num_per, z0, zc, 0); CHECK_LAUNCH();
+        if (s->world == 1) {
+            CU(stage.up(db_buf + z0 * row, zc * row));
+        } else {
+            for (size_t z = 0; z < zc; z++)
+                CU(cudaMemcpy2D(stage.p + z * row, s->dim0 * 8, db_buf + ((z0 + z) * s->num_per + s->rank) * s->dim0,
+                                (size_t)s->world * s->dim0 * 8, s->dim0 * 8, s->local_num_per, cudaMemcpyHostToDevice));
+        }
+        launch_db_from_reference(s->db.p + plane * s->plane_words, stage.p, s->dim0 / 2, s->local_num_per, z0, zc, 0); CHECK_LAUNCH();
         CU(cudaDeviceSynchronize());
     }
     s->plane_loaded[plane] = true;
     return SB200_OK;
 }
+// synthetic database (benchmarks): plaintext coefficients generated ON THE DEVICE, then the normal preprocessing
+// (centre-lift, CRT, NTT, scan layout) - a 64 GiB cfg3 database is built in well under a second of GPU time
 extern "C" int sb200_pack_server_load_random(sb200_pack_server *s, uint64_t seed) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    const size_t items = s->dim0 * s->num_per;
-    std::vector<uint16_t> h(items * kN);
-    uint64_t x = seed * 0x9e3779b97f4a7c15ull + 99;
+    CU(cudaSetDevice(s->device));
+    const size_t items = s->dim0 * s->local_num_per, n4 = items * kN / 4;
+    DBuf<uint16_t> d;
+    CU(d.alloc(items * kN));
     for (size_t p = 0; p < s->planes; p++) {
-        for (size_t i = 0; i < h.size(); i++) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; h[i] = (uint16_t)((x >> 20) % s->prm.p_db); }
-        TRY(sb200_pack_server_load_plane_items(s, p, h.data()));
+        count_launch(); launch_pdl(k_fill_random_u16, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 0, d.p, n4, (uint32_t)s->prm.p_db,
+                                   seed * 0x100000001b3ull + p * 0x632be59bd9b4e019ull);
+        launch_db_build_pack(s->db.p + p * s->plane_words, d.p, s->dim0, s->local_num_per, (uint32_t)s->prm.p_db, 0); CHECK_LAUNCH();
+        CU(cudaDeviceSynchronize());
+        s->plane_loaded[p] = true;
     }
     return SB200_OK;
 }
@@ -205,7 +265,7 @@ static int pack_up(sb200_pack_server *s, DBuf<uint32_t> &dst, size_t dst_off_pol
         const size_t n = std::min(chunk, npolys - o);
         CU(cudaMemcpyAsync(s->stage.p, host + o * PLW, n * PLW * 8, cudaMemcpyHostToDevice, st));
         launch_ntt_u64_to_dev(dst.p + (dst_off_polys + o) * PLW, s->stage.p, n, st); CHECK_LAUNCH();
-        CU(cudaStreamSynchronize(st));
+        if (o + chunk < npolys) CU(cudaStreamSynchronize(st));        // the staging buffer is reused by the next chunk
     }
     return SB200_OK;
 }
@@ -214,79 +274,132 @@ static int pack_up(sb200_pack_server *s, DBuf<uint32_t> &dst, size_t dst_off_pol
 extern "C" int sb200_pack_server_set_public_params(sb200_pack_server *s, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
                                                    const uint64_t *V, const uint64_t *v_W) {
     if (!s || !v_W) return fail(SB200_ERR_ARG, "pack set_public_params: null argument");
-    if (W_exp_left) TRY(pack_up(s, s->W_left, 0, W_exp_left, s->g * 2 * s->prm.t_exp, 0));
-    if (W_exp_right) TRY(pack_up(s, s->W_right, 0, W_exp_right, (s->stopround + 1) * 2 * s->prm.t_exp_right, 0));
-    if (V) TRY(pack_up(s, s->V, 0, V, 2 * 2 * (size_t)s->prm.t_conv, 0));
-    TRY(pack_up(s, s->vW, 0, v_W, (size_t)s->prm.out_n * (s->prm.out_n + 1) * s->prm.t_conv, 0));
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = s->own_stream;
+    if (W_exp_left) { TRY(pack_up(s, s->W_left, 0, W_exp_left, s->g * 2 * s->prm.t_exp, st)); CU(cudaStreamSynchronize(st)); }
+    if (W_exp_right) { TRY(pack_up(s, s->W_right, 0, W_exp_right, (s->stopround + 1) * 2 * s->prm.t_exp_right, st)); CU(cudaStreamSynchronize(st)); }
+    if (V) { TRY(pack_up(s, s->V, 0, V, 2 * 2 * (size_t)s->prm.t_conv, st)); CU(cudaStreamSynchronize(st)); }
+    TRY(pack_up(s, s->vW, 0, v_W, (size_t)s->prm.out_n * (s->prm.out_n + 1) * s->prm.t_conv, st)); CU(cudaStreamSynchronize(st));
     s->have_params = (W_exp_left && W_exp_right && V);
     return SB200_OK;
 }
 
-static int pack_process(sb200_pack_server *s, uint64_t *resp_host, uint64_t *result_cts_host, cudaStream_t st) {
-    for (size_t p = 0; p < s->planes; p++) if (!s->plane_loaded[p]) return fail(SB200_ERR_STATE, "pack answer: database plane %zu not loaded", p);
-    const size_t ell = s->prm.t_gsw, fd = s->prm.nu2, gsw_polys = 2 * 2 * ell, out_n = s->prm.out_n, rows = out_n + 1;
-    // first dimension for all planes at once, lift, fold (planes batched), keep ct 0 of every plane
-    launch_scan_pack(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->num_per, s->planes, s->plane_words, s->num_per * 2, st);
-    launch_from_ntt(s->cts.p, s->scan_out.p, s->planes * s->num_per * 2, st);
-    size_t np = s->num_per;
-    for (size_t cur = 0; cur < fd; cur++) {
-        np /= 2;
-        const size_t d = fd - 1 - cur;
-        launch_fold_round_generic(s->cts.p, 2, 1, (int)ell, 0, np, s->planes, s->num_per, s->gsw.p + d * gsw_polys * PLW,
-                                  nullptr, s->fold_scratch.p, st);            // CMux form, no negated GSW needed
-    }
-    CU(cudaMemcpy2DAsync(s->result_cts.p, 2 * kN * 8, s->cts.p, s->num_per * 2 * kN * 8, 2 * kN * 8, s->planes, cudaMemcpyDeviceToDevice, st));
-    launch_pack(s->packed.p, s->result_cts.p, s->vW.p, (int)out_n, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
-    launch_from_ntt(s->packed_raw.p, s->packed.p, rows * out_n, st);
-    launch_rescale(s->resp.p, s->packed_raw.p, out_n * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
-    launch_rescale(s->resp.p + out_n * kN, s->packed_raw.p + out_n * kN, (rows - 1) * out_n * (size_t)kN, kQ, 4 * s->prm.p_db, st);
-    CHECK_LAUNCH();
-    if (result_cts_host) CU(cudaMemcpyAsync(result_cts_host, s->result_cts.p, s->planes * 2 * kN * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(resp_host, s->resp.p, rows * out_n * kN * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+// ---- staged query answering (device-resident between stages; bench.py and the multi-GPU path) -------------------
+// packed single-ciphertext query (SpiralPack): H2D of the 2x1 ref-NTT ciphertext
+extern "C" int sb200_pack_server_upload_query(sb200_pack_server *s, const uint64_t *query_cv_host, void *stream) {
+    if (!s || !query_cv_host) return fail(SB200_ERR_ARG, "pack upload_query: null argument");
+    CU(cudaMemcpyAsync(s->stage.p, query_cv_host, 2 * PLW * 8, cudaMemcpyHostToDevice, PS(s, stream)));
     return SB200_OK;
 }
-// packed single-ciphertext query (SpiralPack): expansion + conversion + processing
+// coefficientExpansion + reorientCiphertextsDim1 + regevToSimpleGsw (src/testing.cpp:1015-1024)
+extern "C" int sb200_pack_server_expand_and_convert(sb200_pack_server *s, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (!s->have_params) return fail(SB200_ERR_STATE, "pack expand_and_convert: expansion keys / V not set");
+    return run_stage(s->g_convert, PS(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
+        launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
+        launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
+                      s->offs.data(), s->cnt.data(), st);
+        launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_first.p, s->dim0, st);
+        launch_regev_to_simple_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw, s->V.p,
+                                   (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+    });
+}
+// direct upload (SpiralStreamPack): 2^nu1 first-dimension cts + nu2 GSW cts arrive already expanded (src/testing.cpp:960-1005)
+extern "C" int sb200_pack_server_upload_direct(sb200_pack_server *s, const uint64_t *v_firstdim_host, const uint64_t *v_folding_host, void *stream) {
+    if (!s || !v_firstdim_host) return fail(SB200_ERR_ARG, "pack upload_direct: null argument");
+    cudaStream_t st = PS(s, stream);
+    const size_t ell = s->prm.t_gsw, fd = s->prm.nu2;
+    if (fd && !v_folding_host) return fail(SB200_ERR_ARG, "pack upload_direct: GSW ciphertexts missing");
+    TRY(pack_up(s, s->cv, 0, v_firstdim_host, s->dim0 * 2, st));
+    launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_direct.p, s->dim0, st);
+    if (fd) { CU(cudaStreamSynchronize(st)); TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st)); }
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+// fastMultiplyQueryByDatabaseDim1 for all out_n^2 planes of the shard in one launch (src/testing.cpp:1045-1052)
+extern "C" int sb200_pack_server_scan(sb200_pack_server *s, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    for (size_t p = 0; p < s->planes; p++) if (!s->plane_loaded[p]) return fail(SB200_ERR_STATE, "pack scan: database plane %zu not loaded", p);
+    launch_scan_pack(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, s->planes, s->plane_words, s->local_num_per * 2, PS(s, stream));
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+static void pack_fold_rounds(sb200_pack_server *s, uint64_t *cts, size_t count, size_t plane_stride, size_t first_round, cudaStream_t st) {
+    const size_t ell = s->prm.t_gsw, fd = s->prm.nu2, gsw_polys = 2 * 2 * ell;
+    size_t np = count, cur = first_round;
+    while (np >= 2) {
+        np /= 2;
+        const size_t d = fd - 1 - cur;                        // v_folding[nu2 - 1 - cur] (foldCiphertextsDim1, :607-610)
+        launch_fold_round_generic(cts, 2, 1, (int)ell, 0, np, s->planes, plane_stride, s->gsw.p + d * gsw_polys * PLW,
+                                  nullptr, s->fold_scratch.p, st);            // CMux form, no negated GSW needed
+        cur++;
+    }
+}
+// from_ntt of every scan output + the local fold rounds (src/testing.cpp:1055-1058); leaves `planes` surviving cts
+extern "C" int sb200_pack_server_fold_local(sb200_pack_server *s, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    return run_stage(s->g_fold, PS(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
+        launch_from_ntt(s->cts.p, s->scan_out.p, s->planes * s->local_num_per * 2, st);
+        pack_fold_rounds(s, s->cts.p, s->local_num_per, s->local_num_per, 0, st);
+        cudaMemcpy2DAsync(s->result_cts.p, 2 * kN * 8, s->cts.p, s->local_num_per * 2 * kN * 8, 2 * kN * 8, s->planes, cudaMemcpyDeviceToDevice, st);
+    });
+}
+extern "C" uint64_t *sb200_pack_server_partial_cts(sb200_pack_server *s) { return s ? s->result_cts.p : nullptr; }
+extern "C" size_t sb200_pack_server_partial_words(const sb200_pack_server *s) { return s ? s->planes * 2 * kN : 0; }
+extern "C" int sb200_pack_server_copy_partial(sb200_pack_server *s, uint64_t *dst_dev, void *stream) {
+    if (!s || !dst_dev) return fail(SB200_ERR_ARG, "pack copy_partial: null argument");
+    CU(cudaMemcpyAsync(dst_dev, s->result_cts.p, s->planes * 2 * kN * 8, cudaMemcpyDeviceToDevice, PS(s, stream)));
+    return SB200_OK;
+}
+// rank 0: gathered = [world][planes] surviving cts (device, rank order; world == 1: the server's own partial buffer).
+// Last log2(world) fold rounds, pack (:1066-1072), modulus switch (:1074-1081) -> total_resp_dev ((out_n+1) x out_n raw).
+extern "C" int sb200_pack_server_fold_tail(sb200_pack_server *s, const uint64_t *gathered_dev, uint64_t *total_resp_dev, void *stream) {
+    if (!s || !gathered_dev || !total_resp_dev) return fail(SB200_ERR_ARG, "pack fold_tail: null argument");
+    const size_t out_n = s->prm.out_n, rows = out_n + 1;
+    return run_stage(s->g_tail, PS(s, stream), gathered_dev, total_resp_dev, [&](cudaStream_t st) {
+        const uint64_t *final_cts = gathered_dev;
+        if (s->world > 1) {
+            count_launch(); launch_pdl(k_transpose_cts, dim3((unsigned)(s->world * s->planes)), dim3(256), 0, st, s->tail_cts.p, gathered_dev, s->world, (int)s->planes);
+            pack_fold_rounds(s, s->tail_cts.p, (size_t)s->world, (size_t)s->world, s->prm.nu2 - s->log_world, st);
+            cudaMemcpy2DAsync(s->result_cts.p, 2 * kN * 8, s->tail_cts.p, (size_t)s->world * 2 * kN * 8, 2 * kN * 8, s->planes, cudaMemcpyDeviceToDevice, st);
+            final_cts = s->result_cts.p;
+        }
+        launch_pack(s->packed.p, final_cts, s->vW.p, (int)out_n, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+        launch_from_ntt(s->packed_raw.p, s->packed.p, rows * out_n, st);
+        launch_rescale(total_resp_dev, s->packed_raw.p, out_n * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
+        launch_rescale(total_resp_dev + out_n * kN, s->packed_raw.p + out_n * kN, (rows - 1) * out_n * (size_t)kN, kQ, 4 * s->prm.p_db, st);
+    });
+}
+extern "C" uint64_t *sb200_pack_server_result_cts(sb200_pack_server *s) { return s ? s->result_cts.p : nullptr; }
+extern "C" int sb200_pack_server_download(sb200_pack_server *s, uint64_t *dst_host, const uint64_t *src_dev, size_t words, void *stream) {
+    if (!s || !dst_host || !src_dev) return fail(SB200_ERR_ARG, "pack download: null argument");
+    CU(cudaMemcpyAsync(dst_host, src_dev, words * 8, cudaMemcpyDeviceToHost, PS(s, stream)));
+    CU(cudaStreamSynchronize(PS(s, stream)));
+    return SB200_OK;
+}
+
+static int pack_process(sb200_pack_server *s, uint64_t *resp_host, uint64_t *result_cts_host, void *stream) {
+    if (s->world != 1) return fail(SB200_ERR_STATE, "pack answer: single-shard call on a sharded server (use the staged API)");
+    const size_t out_n = s->prm.out_n, rows = out_n + 1;
+    TRY(sb200_pack_server_scan(s, stream));
+    TRY(sb200_pack_server_fold_local(s, stream));
+    TRY(sb200_pack_server_fold_tail(s, s->result_cts.p, s->resp.p, stream));
+    if (result_cts_host) CU(cudaMemcpyAsync(result_cts_host, s->result_cts.p, s->planes * 2 * kN * 8, cudaMemcpyDeviceToHost, PS(s, stream)));
+    return sb200_pack_server_download(s, resp_host, s->resp.p, rows * out_n * kN, stream);
+}
+// packed single-ciphertext query (SpiralPack): expansion + conversion + processing; 64 KiB in, (out_n+1) x out_n x 16 KiB out
 extern "C" int sb200_pack_server_answer(sb200_pack_server *s, const uint64_t *query_cv_host, uint64_t *total_resp_host,
                                         uint64_t *result_cts_host, void *stream) {
     if (!s || !query_cv_host || !total_resp_host) return fail(SB200_ERR_ARG, "pack answer: null argument");
-    if (!s->have_params) return fail(SB200_ERR_STATE, "pack answer: expansion keys / V not set");
-    cudaStream_t st = S(stream);
-    const size_t ell = s->prm.t_gsw, nbits = ell * s->prm.nu2;
-    std::vector<int> cf(s->dim0), cb(nbits), pb(2 * nbits);
-    for (size_t j = 0; j < s->dim0; j++) cf[j] = (int)(2 * j);                              // reorientCiphertextsDim1(..., 2)
-    for (size_t b = 0; b < nbits; b++) { cb[b] = (int)(2 * b + 1); pb[b] = 2 * cb[b]; pb[nbits + b] = 2 * cb[b] + 1; }   // regevToSimpleGsw(..., 2, 1)
-    CU(cudaMemcpyAsync(s->ct_idx_first.p, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice, st));
-    if (nbits) { CU(cudaMemcpyAsync(s->ct_idx_bits.p, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice, st));
-                 CU(cudaMemcpyAsync(s->poly_idx_bits.p, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, st)); }
-    CU(cudaMemcpyAsync(s->stage.p, query_cv_host, 2 * PLW * 8, cudaMemcpyHostToDevice, st));
-    launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
-    launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p, s->offs.data(), s->cnt.data(), st);
-    launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_first.p, s->dim0, st);
-    launch_regev_to_simple_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)ell, s->V.p,
-                               (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
-    CHECK_LAUNCH();
-    CU(cudaStreamSynchronize(st));          // host index vectors go out of scope
-    return pack_process(s, total_resp_host, result_cts_host, st);
+    TRY(sb200_pack_server_upload_query(s, query_cv_host, stream));
+    TRY(sb200_pack_server_expand_and_convert(s, stream));
+    return pack_process(s, total_resp_host, result_cts_host, stream);
 }
-// direct upload (SpiralStreamPack): 2^nu1 first-dimension cts + nu2 GSW cts arrive already expanded
 extern "C" int sb200_pack_server_answer_direct(sb200_pack_server *s, const uint64_t *v_firstdim_host, const uint64_t *v_folding_host,
                                                uint64_t *total_resp_host, uint64_t *result_cts_host, void *stream) {
     if (!s || !v_firstdim_host || !total_resp_host) return fail(SB200_ERR_ARG, "pack answer_direct: null argument");
-    cudaStream_t st = S(stream);
-    const size_t ell = s->prm.t_gsw, fd = s->prm.nu2;
-    TRY(pack_up(s, s->cv, 0, v_firstdim_host, s->dim0 * 2, st));
-    std::vector<int> cf(s->dim0);
-    for (size_t j = 0; j < s->dim0; j++) cf[j] = (int)j;
-    CU(cudaMemcpyAsync(s->ct_idx_first.p, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice, st));
-    launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_first.p, s->dim0, st);
-    if (fd) {
-        if (!v_folding_host) return fail(SB200_ERR_ARG, "pack answer_direct: GSW ciphertexts missing");
-        TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st));
-    }
-    CHECK_LAUNCH();
-    CU(cudaStreamSynchronize(st));
-    return pack_process(s, total_resp_host, result_cts_host, st);
+    TRY(sb200_pack_server_upload_direct(s, v_firstdim_host, v_folding_host, stream));
+    return pack_process(s, total_resp_host, result_cts_host, stream);
 }
 extern "C" size_t sb200_pack_server_db_bytes(const sb200_pack_server *s) { return s ? s->planes * s->plane_words * 8 : 0; }
 extern "C" size_t sb200_pack_server_response_words(const sb200_pack_server *s) { return s ? (size_t)(s->prm.out_n + 1) * s->prm.out_n * kN : 0; }

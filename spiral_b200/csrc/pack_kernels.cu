@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(kNttThreads) k_db_build_pack(uint64_t *__restr
     const int ih = blockIdx.x, jp = blockIdx.y;                    // i = 2*ih + ipar, j = 2*jp + s
     for (int poly = 0; poly < 4; poly++) {
         const int s = poly >> 1, ipar = poly & 1;
+        if (2 * ih + ipar >= num_per) continue;                    // num_per == 1 (a one-column shard): no odd column
         const size_t item = (size_t)(2 * jp + s) * num_per + (2 * ih + ipar);
         const uint16_t *src = pts + item * kN;
         uint32_t v[16];
@@ -57,14 +58,14 @@ __global__ void __launch_bounds__(kNttThreads) k_db_build_pack(uint64_t *__restr
         b.y = pack_pb3(stash[(3 * 2 + 0) * kN + z], stash[(3 * 2 + 1) * kN + z]);
         ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(db) + ((size_t)z * JP + jp) * num_per + 2 * ih;
         dst[0] = a;
-        dst[1] = b;
+        if (num_per > 1) dst[1] = b;
     }
 }
 void launch_db_build_pack(uint64_t *db_plane, const uint16_t *pts_plane, size_t dim0, size_t num_per, uint32_t p_db, cudaStream_t s) {
     const size_t smem = (2 * kPlaneWords + 4 * 2 * kN) * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_db_build_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    count_launch(); launch_pdl(k_db_build_pack, dim3(dim3((unsigned)(num_per / 2), (unsigned)(dim0 / 2))), dim3(kNttThreads), smem, s, db_plane, pts_plane, (int)dim0, (int)num_per, p_db);
+    count_launch(); launch_pdl(k_db_build_pack, dim3(dim3((unsigned)((num_per + 1) / 2), (unsigned)(dim0 / 2))), dim3(kNttThreads), smem, s, db_plane, pts_plane, (int)dim0, (int)num_per, p_db);
 }
 
 // ============================================================================================

@@ -104,7 +104,19 @@ def load_library():
         "sb200_pack": (C.c_int, [u64p, C.c_uint32, C.c_uint32, u64p, u64p]),
         # tier 3
         "sb200_pack_server_create": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int]),
+        "sb200_pack_server_create_sharded": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int, C.c_int, C.c_int]),
         "sb200_pack_server_destroy": (None, [vp]),
+        "sb200_pack_server_upload_query": (C.c_int, [vp, vp, vp]),
+        "sb200_pack_server_expand_and_convert": (C.c_int, [vp, vp]),
+        "sb200_pack_server_upload_direct": (C.c_int, [vp, vp, vp, vp]),
+        "sb200_pack_server_scan": (C.c_int, [vp, vp]),
+        "sb200_pack_server_fold_local": (C.c_int, [vp, vp]),
+        "sb200_pack_server_partial_cts": (vp, [vp]),
+        "sb200_pack_server_partial_words": (sz, [vp]),
+        "sb200_pack_server_copy_partial": (C.c_int, [vp, vp, vp]),
+        "sb200_pack_server_fold_tail": (C.c_int, [vp, vp, vp, vp]),
+        "sb200_pack_server_result_cts": (vp, [vp]),
+        "sb200_pack_server_download": (C.c_int, [vp, vp, vp, sz, vp]),
         "sb200_pack_server_load_plane_items": (C.c_int, [vp, sz, u16p]),
         "sb200_pack_server_load_plane_reference": (C.c_int, [vp, sz, u64p]),
         "sb200_pack_server_load_random": (C.c_int, [vp, C.c_uint64]),

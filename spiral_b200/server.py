@@ -150,3 +150,111 @@ class SpiralServer:
             self.close()
         except Exception:
             pass
+
+
+class PackServer:
+    """SpiralPack / SpiralStreamPack resident server (testHighRate's server statements, src/testing.cpp:1007-1081):
+    out_n^2 database planes of 1x1 plaintexts, 2x1 Regev ciphertexts, one packed (out_n+1) x out_n response.
+    Sharded like SpiralServer: rank g owns the second-dimension indices ii = g (mod world) of every plane."""
+
+    def __init__(self, params: SpiralParams, device=0, rank=0, world=1):
+        self.lib = load_library()
+        self.params = params
+        self.rank, self.world = rank, world
+        self.dim0, self.num_per = 1 << params.nu1, 1 << params.nu2
+        self.local_num_per = self.num_per // world
+        self.planes = params.out_n * params.out_n
+        h = C.c_void_p()
+        check(self.lib.sb200_pack_server_create_sharded(C.byref(h), C.byref(params), device, rank, world), self.lib)
+        self.h = h
+
+    # ---- database -----------------------------------------------------------------------
+    def shard_items(self, plane_pts):
+        """Select + order this shard's items from one plane's item-major (item = j*num_per + ii) plaintext array."""
+        idx = [j * self.num_per + ii for j in range(self.dim0) for ii in range(self.rank, self.num_per, self.world)]
+        return plane_pts[idx]
+
+    def load_plane_items(self, plane, pts_u16):
+        pts_u16 = np.ascontiguousarray(pts_u16, dtype=np.uint16)
+        assert pts_u16.size == self.dim0 * self.local_num_per * N
+        check(self.lib.sb200_pack_server_load_plane_items(self.h, plane, pts_u16.ctypes.data_as(_P16)), self.lib)
+
+    def load_plane_reference(self, plane, db_buf):
+        """db_buf: the WHOLE plane in the reference's convertDb layout (src/testing.cpp:316-340)."""
+        check(self.lib.sb200_pack_server_load_plane_reference(self.h, plane, _p64(db_buf)), self.lib)
+
+    def load_random(self, seed=1):
+        check(self.lib.sb200_pack_server_load_random(self.h, seed), self.lib)
+
+    def set_public_params(self, W_exp_left, W_exp_right, V, v_W):
+        opt = lambda a: None if a is None else _p64(a)  # noqa: E731
+        check(self.lib.sb200_pack_server_set_public_params(self.h, opt(W_exp_left), opt(W_exp_right), opt(V), _p64(v_W)), self.lib)
+
+    # ---- query answering -----------------------------------------------------------------
+    def answer(self, query_cv, want_cts=False, stream=None):
+        resp = np.empty(self.response_words, dtype=np.uint64)
+        cts = np.empty(self.planes * 2 * N, dtype=np.uint64) if want_cts else None
+        check(self.lib.sb200_pack_server_answer(self.h, query_cv.ctypes.data, resp.ctypes.data, cts.ctypes.data if want_cts else None, stream), self.lib)
+        return (resp, cts) if want_cts else resp
+
+    def answer_direct(self, v_firstdim, v_folding, want_cts=False, stream=None):
+        resp = np.empty(self.response_words, dtype=np.uint64)
+        cts = np.empty(self.planes * 2 * N, dtype=np.uint64) if want_cts else None
+        check(self.lib.sb200_pack_server_answer_direct(self.h, v_firstdim.ctypes.data, None if v_folding is None else v_folding.ctypes.data,
+                                                       resp.ctypes.data, cts.ctypes.data if want_cts else None, stream), self.lib)
+        return (resp, cts) if want_cts else resp
+
+    def upload_query_ptr(self, host_ptr, stream=None):
+        check(self.lib.sb200_pack_server_upload_query(self.h, host_ptr, stream), self.lib)
+
+    def upload_direct_ptr(self, firstdim_ptr, folding_ptr, stream=None):
+        check(self.lib.sb200_pack_server_upload_direct(self.h, firstdim_ptr, folding_ptr, stream), self.lib)
+
+    def expand_and_convert(self, stream=None):
+        check(self.lib.sb200_pack_server_expand_and_convert(self.h, stream), self.lib)
+
+    def scan(self, stream=None):
+        check(self.lib.sb200_pack_server_scan(self.h, stream), self.lib)
+
+    def fold_local(self, stream=None):
+        check(self.lib.sb200_pack_server_fold_local(self.h, stream), self.lib)
+
+    def partial_cts_ptr(self):
+        return self.lib.sb200_pack_server_partial_cts(self.h)
+
+    @property
+    def partial_words(self):
+        return self.lib.sb200_pack_server_partial_words(self.h)
+
+    def copy_partial(self, dst_ptr, stream=None):
+        check(self.lib.sb200_pack_server_copy_partial(self.h, dst_ptr, stream), self.lib)
+
+    def fold_tail(self, gathered_ptr, resp_ptr, stream=None):
+        check(self.lib.sb200_pack_server_fold_tail(self.h, gathered_ptr, resp_ptr, stream), self.lib)
+
+    def result_cts_ptr(self):
+        return self.lib.sb200_pack_server_result_cts(self.h)
+
+    def download(self, dev_ptr, words, stream=None):
+        out = np.empty(words, dtype=np.uint64)
+        check(self.lib.sb200_pack_server_download(self.h, out.ctypes.data, dev_ptr, words, stream), self.lib)
+        return out
+
+    @property
+    def db_bytes(self):
+        return self.lib.sb200_pack_server_db_bytes(self.h)
+
+    @property
+    def response_words(self):
+        return self.lib.sb200_pack_server_response_words(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.sb200_pack_server_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

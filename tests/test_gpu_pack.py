@@ -90,3 +90,84 @@ def test_pack_server_matches_oracle(sb, oracle, cfg, nu1, nu2, mode):
     sb.sb200_pack_server_destroy(h)
     assert np.array_equal(got_cts, want_cts), "folded per-plane ciphertexts differ"
     assert np.array_equal(got, want), "packed + modulus-switched response differs"
+
+
+@pytest.mark.parametrize("cfg,nu1,nu2,mode,world", [("cfg3", 4, 2, "expand", 2), ("cfg3", 3, 2, "expand", 4), ("cfg4", 5, 3, "direct", 2),
+                                                    ("cfg4", 4, 3, "direct", 8), ("cfg1", 4, 1, "expand", 2)])
+def test_sharded_pack_servers_reproduce_oracle(sb, oracle, cfg, nu1, nu2, mode, world):
+    """world shards on ONE device (strided over the second dimension of every plane): staged API, device-side gather of
+    the per-plane surviving ciphertexts, tail folds + pack + modulus switch on shard 0 == the oracle's whole pipeline.
+    Covers one-column shards (num_per / world == 1) and both database ingest paths."""
+    from spiral_b200.server import PackServer
+    prm = ol.make_params(cfg, nu1, nu2)
+    rng = np.random.default_rng(nu1 * 1000 + nu2 * 10 + world)
+    dim0, num_per, n = 1 << nu1, 1 << nu2, prm.out_n
+    planes, ell, fd = n * n, prm.t_gsw, nu2
+    pts, db = build_planes(oracle, prm, rng, dim0, num_per, planes)
+    g, stop = C.c_size_t(), C.c_size_t()
+    oracle.so_pack_expansion_shape(C.byref(prm), C.byref(g), C.byref(stop))
+    g, stop = g.value, stop.value
+    vW = rnd_ntt(rng, n * (n + 1) * prm.t_conv)
+    W_left, W_right, V = rnd_ntt(rng, g * 2 * prm.t_exp), rnd_ntt(rng, (stop + 1) * 2 * prm.t_exp_right), rnd_ntt(rng, 2 * 2 * prm.t_conv)
+    query, v_first, v_fold = rnd_ntt(rng, 2), rnd_ntt(rng, dim0 * 2), rnd_ntt(rng, max(fd, 1) * 2 * 2 * ell)
+    want = np.zeros((n + 1) * n * N, dtype=np.uint64)
+    want_cts = np.zeros(planes * 2 * N, dtype=np.uint64)
+    assert oracle.so_pack_answer(C.byref(prm), int(mode == "expand"), p(query), p(W_left), p(W_right), p(V), p(v_first), p(v_fold),
+                                 p(vW), p(db), p(want), p(want_cts)) == 0
+
+    sp = SpiralParams(nu1, nu2, prm.t_gsw, prm.t_conv, prm.t_exp, prm.t_exp_right, prm.qp_bits, prm.out_n, prm.p_db)
+    shards = [PackServer(sp, rank=r, world=world) for r in range(world)]
+    items = dim0 * num_per
+    for srv in shards:
+        for pl in range(planes):
+            if (pl + srv.rank) % 2 == 0:
+                srv.load_plane_items(pl, srv.shard_items(pts[pl]).astype(np.uint16))
+            else:
+                srv.load_plane_reference(pl, np.ascontiguousarray(db[pl * items * N:(pl + 1) * items * N]))
+        if mode == "expand":
+            srv.set_public_params(W_left, W_right, V, vW)
+        else:
+            srv.set_public_params(None, None, None, vW)
+    import torch
+    words = shards[0].partial_words
+    gathered = torch.zeros(world * words, dtype=torch.int64, device="cuda")
+    resp = torch.zeros(shards[0].response_words, dtype=torch.int64, device="cuda")
+    for rep in range(2):                                        # second pass replays the captured graphs
+        for srv in shards:
+            if mode == "expand":
+                srv.upload_query_ptr(query.ctypes.data)
+                srv.expand_and_convert()
+            else:
+                srv.upload_direct_ptr(v_first.ctypes.data, v_fold.ctypes.data)
+            srv.scan()
+            srv.fold_local()
+            srv.copy_partial(gathered.data_ptr() + srv.rank * words * 8)
+        torch.cuda.synchronize()
+        shards[0].fold_tail(gathered.data_ptr(), resp.data_ptr())
+        torch.cuda.synchronize()
+        got = resp.cpu().numpy().view(np.uint64)
+        got_cts = shards[0].download(shards[0].result_cts_ptr(), planes * 2 * N)
+        assert np.array_equal(got_cts, want_cts), f"folded per-plane ciphertexts differ (pass {rep})"
+        assert np.array_equal(got, want), f"packed + modulus-switched response differs (pass {rep})"
+    with pytest.raises(Exception):
+        shards[0].answer(query)                                 # single-shard call on a sharded server must fail loudly
+    for srv in shards:
+        srv.close()
+
+
+def test_pack_device_random_database_is_deterministic_and_in_range(sb):
+    """sb200_pack_server_load_random (device-side generator): same seed -> same scan output, different seed -> different."""
+    from spiral_b200.server import PackServer
+    sp = SpiralParams(4, 2, 3, 56, 56, 56, 27, 2, 65536)
+    rng = np.random.default_rng(5)
+    vW = rnd_ntt(rng, 2 * 3 * 56)
+    v_first, v_fold = rnd_ntt(rng, 16 * 2), rnd_ntt(rng, 2 * 2 * 2 * 3)
+    outs = []
+    for seed in (7, 7, 8):
+        srv = PackServer(sp)
+        srv.load_random(seed)
+        srv.set_public_params(None, None, None, vW)
+        outs.append(srv.answer_direct(v_first, v_fold))
+        srv.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0], outs[2])
