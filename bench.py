@@ -2,12 +2,16 @@
 """bench.py - Spiral server-side query answering on B200: ms/query and database GB/s scanned.
 
 One "step" = one query answered against the resident database (expansion + conversion +
-first-dimension scan + folding + modulus switch), BASELINE.json's metric.
+first-dimension scan + folding + packing / modulus switch), BASELINE.json's metric.
 
-  python bench.py --gpus 1 --steps K --warmup W            our CUDA path   (config.workload = cfg1)
+  python bench.py --gpus 1 --steps K --warmup W            our CUDA path   (config.workload = cfg1, the headline)
   python bench.py --impl reference ...                      the UNMODIFIED reference (oracle/_ref) on host cores
-  torchrun --nproc-per-node N bench.py --gpus N ...         second dimension sharded over N GPUs (weak scaling:
-                                                            every GPU keeps a 2^20-record shard, nu_2 grows by log2 N)
+  torchrun --nproc-per-node N bench.py --gpus N ...         second dimension sharded over N GPUs
+  python bench.py --workload cfg3|cfg4|cfg5 [--scaling weak|strong]   the other BASELINE.json configurations
+        cfg1  Spiral 2^20 x 256 B (./spiral 8 7)                    weak scaling by default: every GPU keeps a 2 GiB shard
+        cfg5  Spiral 2^22 x 256 B (./spiral 9 8, 8 GiB)             strong scaling: the database is split over the GPUs
+        cfg3  SpiralPack 2^18 x 30 KB (./spiral 10 8 --high-rate, 64 GiB)            strong
+        cfg4  SpiralStreamPack 2^14 x 100 KB (./spiral 11 3 --high-rate --direct-upload, 6.25 GiB)   strong
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -27,15 +31,15 @@ N_POLY = 2048
 # BASELINE.json configs.  cfg1/cfg2 share one shape (the explicit database is the harder, honest one);
 # cfg1 is the default and the headline; the others are selected with --workload.
 WORKLOADS = {
-    "cfg1": dict(kind="spiral", nu1=8, nu2=7, scaling="weak", prm=CFG1, flags="",
+    "cfg1": dict(kind="spiral", nu1=8, nu2=7, scaling="weak", prm=CFG1, flags=[],
                  macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256"),
-    "cfg5": dict(kind="spiral", nu1=9, nu2=8, scaling="strong", flags="",
+    "cfg5": dict(kind="spiral", nu1=9, nu2=8, scaling="strong", flags=[],
                  prm=dict(t_gsw=9, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=21, out_n=2, p_db=256),
                  macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=9 QPBITS=21 PVALUE=256"),
-    "cfg3": dict(kind="pack", nu1=10, nu2=8, scaling="strong", direct=False, flags="--high-rate",
+    "cfg3": dict(kind="pack", nu1=10, nu2=8, scaling="strong", direct=False, flags=["--high-rate"],
                  prm=dict(t_gsw=8, t_conv=4, t_exp=16, t_exp_right=56, qp_bits=20, out_n=4, p_db=256),
                  macros="TEXP=16 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256 OUTN=4", sample=(8, 5)),
-    "cfg4": dict(kind="pack", nu1=11, nu2=3, scaling="strong", direct=True, flags="--high-rate --direct-upload",
+    "cfg4": dict(kind="pack", nu1=11, nu2=3, scaling="strong", direct=True, flags=["--high-rate", "--direct-upload"],
                  prm=dict(t_gsw=3, t_conv=56, t_exp=56, t_exp_right=56, qp_bits=27, out_n=5, p_db=65536),
                  macros="TEXP=56 TEXPRIGHT=56 TCONV=56 TGSW=3 QPBITS=27 PVALUE=65536 OUTN=5", sample=(9, 3)),
 }
@@ -59,6 +63,53 @@ def cpu_model():
     return "unknown"
 
 
+def ceil_log2(x):
+    g = 0
+    while (1 << g) < x:
+        g += 1
+    return g
+
+
+def record_bytes(wl):
+    """Plaintext bytes of one database record (PIR item) of the workload."""
+    p = wl["prm"]
+    bits = (p["p_db"] - 1).bit_length()
+    polys = 4 if wl["kind"] == "spiral" else p["out_n"] ** 2
+    return polys * N_POLY * bits // 8
+
+
+def workload_name(cfg, nu1, nu2):
+    wl = WORKLOADS[cfg]
+    rb = record_bytes(wl)
+    if wl["kind"] == "spiral":
+        # the reference's own accounting (print_summary, src/spiral.cpp:209-216): n = 2^(nu1+nu2) matrix plaintexts of
+        # n0*n2*2048*log2(p) bits; BASELINE.json quotes the same database as 2^(nu1+nu2+5) records x 256 B
+        recs, size = f"2^{nu1 + nu2 + 5}", "256 B"
+        assert rb == 32 * 256
+    else:
+        recs, size = f"2^{nu1 + nu2}", {"cfg3": "30 KB (32 KiB)", "cfg4": "100 KB (100 KiB)"}.get(cfg, f"{rb // 1024} KiB")
+    variant = {"cfg1": "Spiral", "cfg5": "Spiral", "cfg3": "SpiralPack", "cfg4": "SpiralStreamPack"}[cfg]
+    flags = (" a " + " ".join(wl["flags"])) if wl["flags"] else ""
+    return f"{variant} {recs} records x {size} (./spiral {nu1} {nu2}{flags}; {wl['macros']}), explicit DB"
+
+
+def db_bytes_total(wl, nu1, nu2):
+    """Algorithmic database bytes: 8 B per NTT coefficient = the reference's own B / db_buf footprint."""
+    polys = 4 if wl["kind"] == "spiral" else wl["prm"]["out_n"] ** 2
+    return 8 * N_POLY * polys << (nu1 + nu2)
+
+
+def workload_shape(args, world):
+    """(nu1, nu2, scaling) of the whole job at `world` GPUs."""
+    wl = WORKLOADS[args.workload]
+    nu1 = args.nu1 if args.nu1 is not None else wl["nu1"]
+    nu2 = args.nu2 if args.nu2 is not None else wl["nu2"]
+    scaling = args.scaling or wl["scaling"]
+    if scaling == "weak":
+        nu2 += world.bit_length() - 1                        # fixed shard per GPU: the second dimension grows
+    return nu1, nu2, scaling
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the unmodified reference through its own harness (oracle/ref_bench.cpp)
 # ------------------------------------------------------------------------------------------------
@@ -67,46 +118,96 @@ STAGE_RE = {
     "conversion": r"Conversion \(CPU.us\):\s+(\d+)",
     "first_dim": r"First dimension multiply \(CPU.us\):\s+(\d+)",
     "folding": r"Folding \(CPU.us\):\s+(\d+)",
+    "packing": r"Packing \(CPU.us\):\s+(\d+)",
 }
+STAGES = ("expansion", "conversion", "first_dim", "folding", "packing")
 
 
-def run_reference(nu1, nu2, queries, timeout=1500):
-    """Returns per-query stage times (ms) parsed from the reference's own print_summary
-    (src/spiral.cpp:239-263).  `Main expansion` and `Conversion` accumulate across queries in the
-    reference (+=, src/spiral.cpp:2180,2256), so they are differenced; the other two are per query."""
+def run_reference(cfg, nu1, nu2, queries, timeout=3000):
+    """Per-query stage times (ms) parsed from the reference's own summary (src/spiral.cpp:239-263,
+    src/testing.cpp:626-683).  Spiral: `Main expansion` and `Conversion` accumulate across queries
+    (+=, src/spiral.cpp:2180,2256), so they are differenced; the Pack path exits after one query
+    (src/spiral.cpp:1337-1340), so it is one process per query."""
+    wl = WORKLOADS[cfg]
     isa = host_isa()
-    exe = os.path.join(ROOT, "oracle", "_ref", f"ref_bench_cfg1_{isa}")
+    exe = os.path.join(ROOT, "oracle", "_ref", f"ref_bench_{cfg}_{isa}")
     if not os.path.exists(exe):
         return None, f"{exe} not built"
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "oracle", "_ref") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    pack = wl["kind"] == "pack"
+    chunks = []
     try:
-        out = subprocess.run([exe, str(nu1), str(nu2), "1234", str(queries)], capture_output=True, text=True, timeout=timeout, env=env)
+        for _ in range(queries if pack else 1):
+            # ref_bench: <nu1> <nu2> <idx> <queries> [reference flags] (it inserts the dummy file-name argument itself)
+            out = subprocess.run([exe, str(nu1), str(nu2), "1234", "1" if pack else str(queries)] + wl["flags"],
+                                 capture_output=True, text=True, timeout=timeout, env=env)
+            if out.returncode != 0:
+                return None, f"reference exited {out.returncode}: {out.stderr[-200:]}"
+            chunks += out.stdout.split("=== ref_bench query")[1:]
     except Exception as e:  # noqa: BLE001
         return None, f"reference run failed: {e}"
-    if out.returncode != 0:
-        return None, f"reference exited {out.returncode}: {out.stderr[-200:]}"
-    chunks = out.stdout.split("=== ref_bench query")[1:]
     res, prev = [], dict(expansion=0, conversion=0)
     for ch in chunks:
         st = {}
         for k, rx in STAGE_RE.items():
             m = re.search(rx, ch)
-            if not m:
+            if not m and not (k == "packing" and not pack):
                 return None, f"could not parse '{k}' from the reference output"
-            st[k] = int(m.group(1))
-        correct = re.search(r"Is correct\?:\s*(\d)", ch)
-        q = dict(expansion=(st["expansion"] - prev["expansion"]) / 1e3, conversion=(st["conversion"] - prev["conversion"]) / 1e3,
-                 first_dim=st["first_dim"] / 1e3, folding=st["folding"] / 1e3, correct=bool(correct and correct.group(1) == "1"))
-        q["total"] = q["expansion"] + q["conversion"] + q["first_dim"] + q["folding"]
-        prev = dict(expansion=st["expansion"], conversion=st["conversion"])
+            st[k] = int(m.group(1)) if m else 0
+        correct = re.search(r"Is correct\?\s*:\s*(\d)", ch)
+        if pack:
+            q = {k: st[k] / 1e3 for k in STAGES}
+        else:
+            q = dict(expansion=(st["expansion"] - prev["expansion"]) / 1e3, conversion=(st["conversion"] - prev["conversion"]) / 1e3,
+                     first_dim=st["first_dim"] / 1e3, folding=st["folding"] / 1e3, packing=0.0)
+            prev = dict(expansion=st["expansion"], conversion=st["conversion"])
+        q["correct"] = bool(correct and correct.group(1) == "1")
+        q["total"] = sum(q[k] for k in STAGES)
         res.append(q)
     return res, isa
 
 
+def expansion_ntts(prm, nu1, nu2):
+    """Forward-NTT count of coefficientExpansion (src/testing.cpp:40-105) - the scaling proxy for a reduced Pack sample."""
+    nbits = prm["t_gsw"] * nu2
+    g, stop = ceil_log2(nbits + (1 << nu1)), ceil_log2(max(nbits, 1))
+    total = 0
+    for r in range(g):
+        for i in range(2 << r):
+            if stop > 0 and r > stop and i % 2 == 1:
+                continue
+            if stop > 0 and r == stop and i % 2 == 1 and i // 2 > nbits:
+                continue
+            total += prm["t_exp_right"] if i % 2 else prm["t_exp"]
+    return total
+
+
+def pack_sample_scaled(cfg, nu1, nu2):
+    """Pack workloads are too large for the reference on a host (cfg3: 64 GiB packed + 128 GiB of MatPoly copies):
+    one query at the reduced shape WORKLOADS[cfg]['sample'] with the same parameter macros, each stage scaled by its own
+    work ratio (first_dim ~ records, folding ~ 2^nu2 - 1, expansion ~ forward NTTs, conversion ~ nu2, packing ~ 1)."""
+    wl = WORKLOADS[cfg]
+    s1, s2 = wl["sample"]
+    s1, s2 = min(s1, nu1), min(s2, nu2)
+    res, info = run_reference(cfg, s1, s2, 1)
+    if res is None:
+        return None, info, None
+    q = res[0]
+    prm = wl["prm"]
+    scale = dict(first_dim=float(1 << (nu1 + nu2 - s1 - s2)), folding=((1 << nu2) - 1) / max((1 << s2) - 1, 1), packing=1.0,
+                 conversion=nu2 / max(s2, 1),
+                 expansion=(float(1 << (nu1 - s1)) if wl.get("direct") else expansion_ntts(prm, nu1, nu2) / expansion_ntts(prm, s1, s2)))
+    scaled = {k: q[k] * scale[k] for k in STAGES}
+    scaled["total"] = sum(scaled[k] for k in STAGES)
+    scaled["correct"] = q["correct"]
+    text = (f"ONE query of the unmodified reference at the reduced shape ./spiral {s1} {s2} a {' '.join(wl['flags'])} (same macros; measured "
+            f"{q['total']:.0f} ms: " + ", ".join(f"{k} {q[k]:.0f}" for k in STAGES) + "), each stage scaled by its work ratio "
+            + ", ".join(f"{k} x{scale[k]:.3g}" for k in STAGES))
+    return scaled, info, text
+
+
 def oracle_port_baseline(nu1, nu2):
     """Fallback CPU baseline when oracle/_ref is absent: the oracle port (scalar C) on one core."""
-    import ctypes as C
-    import numpy as np
     from tests import oracle_lib as ol
     lib = ol.load()
     s = ol.SpiralSession(lib, "cfg1", nu1, nu2, seed=1)
@@ -119,57 +220,71 @@ def oracle_port_baseline(nu1, nu2):
     return dt
 
 
-def workload_name(nu1, nu2):
-    return f"Spiral 2^{nu1 + nu2 + 5} records x 256 B (./spiral {nu1} {nu2}; TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256), explicit DB"
+def mem_available():
+    try:
+        return int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:  # noqa: BLE001
+        return 1 << 35
 
 
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # the reference is one single-threaded process: it answers the SAME workload our arm runs at this GPU count
-    # (weak scaling: nu_2 grows by log2 N), unless that database would not fit comfortably in host memory
-    nu1, nu2 = args.nu1, args.nu2 + (args.gpus.bit_length() - 1)
-    db_bytes_needed = 8 * N_POLY * 4 << (nu1 + nu2)
-    note = None
-    try:
-        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
-    except Exception:  # noqa: BLE001
-        avail = 1 << 35
-    if db_bytes_needed * 2.5 > avail:
-        note = f"host memory too small for the {db_bytes_needed >> 30} GiB database of the {args.gpus}-GPU workload: reference ran the 1-GPU workload"
-        nu2 = args.nu2
+    cfg, wl = args.workload, WORKLOADS[args.workload]
+    # the reference is one single-threaded process: it answers the SAME workload our arm runs at this GPU count,
+    # unless that database would not fit comfortably in host memory
+    nu1, nu2, scaling = workload_shape(args, args.gpus)
+    base = {"impl": "reference", "metric": "server_ms_per_query", "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": {"workload": workload_name(cfg, nu1, nu2)}}
+    if wl["kind"] == "pack":
+        q, info, text = pack_sample_scaled(cfg, nu1, nu2)
+        if q is None:
+            print(json.dumps(dict(base, unavailable=info)))
+            return 0
+        stages = {k: q[k] for k in STAGES}
+        line = dict(base, steps=1, warmup=0, value=q["total"], ms_per_step=q["total"], stages_ms=stages,
+                    db_gbs_scanned=db_bytes_total(wl, nu1, nu2) / (stages["first_dim"] * 1e-3) / 1e9,
+                    cpu_baseline={"value": q["total"], "unit": "ms", "cores": 1, "kind": "reference",
+                                  "sample": text + f"; single thread on {cpu_model()} ({info}); decoded correctly: {q['correct']}"},
+                    e2e={"value": q["total"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return 0
+    nu2_run = nu2
+    if db_bytes_total(wl, nu1, nu2) * 2.5 > mem_available():
+        nu2_run = wl["nu2"] if args.nu2 is None else args.nu2
+        while db_bytes_total(wl, nu1, nu2_run) * 2.5 > mem_available() and nu2_run > 1:
+            nu2_run -= 1
+        base["config"]["note"] = (f"host memory too small for the {db_bytes_total(wl, nu1, nu2) >> 30} GiB database of the {args.gpus}-GPU workload: "
+                                  f"reference ran ./spiral {nu1} {nu2_run}")
+        base["config"]["workload"] = workload_name(cfg, nu1, nu2_run)
     queries = args.steps + args.warmup
-    if nu2 > args.nu2:                       # ~1.4 s x 2^(nu2 - 7) per CPU query plus ~10 s x 2^(nu2 - 7) of database generation
+    if db_bytes_total(wl, nu1, nu2_run) > (2 << 30):     # ~1.4 s per CPU query and ~10 s of database generation per 2 GiB
         queries = min(queries, 3)
         args.warmup = min(args.warmup, 1)
         args.steps = queries - args.warmup
-    res, info = run_reference(nu1, nu2, queries)
-    base = {"impl": "reference", "metric": "server_ms_per_query", "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": {"workload": workload_name(nu1, nu2)}}
-    if note:
-        base["config"]["note"] = note
+        base["steps"], base["warmup"] = args.steps, args.warmup
+    res, info = run_reference(cfg, nu1, nu2_run, queries)
     if res is None:
-        kind = "port"
         try:
             ms = oracle_port_baseline(6, 4)
             sample = "oracle port (scalar C restatement), ONE query at ./spiral 6 4 (1/32 of the records), 1 core: " + info
         except Exception as e:  # noqa: BLE001
             print(json.dumps(dict(base, unavailable=f"{info}; oracle port failed: {e}")))
             return 0
-        line = dict(base, value=ms, ms_per_step=ms, cpu_baseline={"value": ms, "unit": "ms", "cores": 1, "kind": kind, "sample": sample},
+        line = dict(base, value=ms, ms_per_step=ms, cpu_baseline={"value": ms, "unit": "ms", "cores": 1, "kind": "port", "sample": sample},
                     e2e={"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(line))
         return 0
     timed = res[args.warmup:] if len(res) > args.warmup else res
     ms = sum(q["total"] for q in timed) / len(timed)
     stages = {k: sum(q[k] for q in timed) / len(timed) for k in ("expansion", "conversion", "first_dim", "folding")}
-    db_bytes = 8 * N_POLY * 4 << (nu1 + nu2)
     sample = (f"unmodified reference (oracle/_ref, g++ -O3 -march=x86-64-{'v4' if info == 'avx512' else 'v3'}, {info} scan path), "
               f"{len(timed)} full queries at the same workload after {args.warmup} warm-up, single thread (the reference is single-threaded, "
               f"src/spiral.cpp:1231) on {cpu_model()}; all queries decoded correctly: {all(q['correct'] for q in res)}")
-    line = dict(base, value=ms, ms_per_step=ms, stages_ms=stages, db_gbs_scanned=db_bytes / (stages["first_dim"] * 1e-3) / 1e9,
+    line = dict(base, value=ms, ms_per_step=ms, stages_ms=stages,
+                db_gbs_scanned=db_bytes_total(wl, nu1, nu2_run) / (stages["first_dim"] * 1e-3) / 1e9,
                 cpu_baseline={"value": ms, "unit": "ms", "cores": 1, "kind": "reference", "sample": sample},
                 e2e={"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line))
@@ -219,14 +334,166 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# our arm
+# our arm: one driver per scheme variant, one shared timing harness
 # ------------------------------------------------------------------------------------------------
+def rnd_ntt_factory(np, seed):
+    rng = np.random.default_rng(seed)
+
+    def rnd_ntt(npolys):
+        a = rng.integers(0, 249561089, size=(npolys, 2, N_POLY), dtype=np.uint64)
+        return np.ascontiguousarray(a.reshape(-1))
+    return rnd_ntt
+
+
+class SpiralDriver:
+    """Spiral / SpiralStream (matrix-Regev) path: resident SpiralServer, one 64 KiB query in, one 96 KiB response out."""
+    kernel = "k_scan_spiral"
+
+    def __init__(self, args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np):
+        from spiral_b200 import SpiralParams
+        from spiral_b200.server import SpiralServer
+        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        p = WORKLOADS[cfg]["prm"]
+        prm = SpiralParams(nu1, nu2, p["t_gsw"], p["t_conv"], p["t_exp"], p["t_exp_right"], p["qp_bits"], p["out_n"], p["p_db"])
+        self.srv = srv = SpiralServer(prm, device=local_rank, rank=rank, world=world)
+        srv.load_db_random(seed=1000 + rank)
+        self.use_p2p = world > 1 and args.exchange == "p2p"
+        if self.use_p2p:                                  # cudaIpc handles of every rank's exchange buffer, rank order
+            handles = [None] * world
+            dist.all_gather_object(handles, srv.xchg_export())
+            srv.xchg_connect(handles)
+        # synthetic public parameters and query: uniform ring elements of the right shape (ref-NTT layout)
+        self.rnd_ntt = rnd_ntt = rnd_ntt_factory(np, 7)    # same on every rank (the query is replicated)
+        ell_bits = p["t_gsw"] * nu2
+        self.g = g = ceil_log2(ell_bits + (1 << nu1))
+        stop = ceil_log2(ell_bits) if ell_bits <= (1 << nu1) else 0
+        self.n_right = n_right = stop + 1 if stop else g
+        self.p = p
+        srv.set_public_params(rnd_ntt(g * 2 * p["t_exp"]), rnd_ntt(n_right * 2 * p["t_exp_right"]),
+                              rnd_ntt(3 * 2 * p["t_conv"]), rnd_ntt(3 * 2 * p["t_conv"]))
+        self.q_host = torch.from_numpy(rnd_ntt(2).view(np.int64)).pin_memory()
+        self.resp_host = torch.empty(6 * N_POLY, dtype=torch.int64).pin_memory()
+        self.gathered = torch.empty(world * 6 * N_POLY, dtype=torch.int64, device="cuda")
+        self.part = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
+        self.resp_dev = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
+        self.h2d_bytes, self.d2h_bytes = int(self.q_host.numel() * 8), int(self.resp_host.numel() * 8)
+        self.db_bytes = srv.db_bytes
+        self.exchange = ("none (1 GPU)" if world == 1 else "peer-memory stores + flags over NVLink, fused into the stream (no NCCL call per query)"
+                         if self.use_p2p else "NCCL all_gather of one 96 KiB ciphertext per GPU")
+
+    def upload(self, stream):
+        self.srv.upload_query_ptr(self.q_host.data_ptr(), stream)
+
+    def stage_convert(self, stream):
+        self.srv.expand_and_convert(stream)
+
+    def stage_scan(self, stream):
+        self.srv.scan(stream)
+
+    def stage_rest(self, stream):
+        srv = self.srv
+        srv.lift(stream)
+        srv.fold_local(stream)
+        if self.use_p2p:
+            # exchange step fused into the stream: stores into rank 0's HBM over NVLink + flag, rank 0 waits and folds
+            srv.exchange_and_tail(self.resp_dev.data_ptr(), stream)
+        elif self.world > 1:
+            srv.copy_partial(self.part.data_ptr(), stream)
+            self.dist.all_gather_into_tensor(self.gathered, self.part)    # one 96 KiB ciphertext per GPU over NVLink (NCCL)
+            if self.rank == 0:
+                srv.fold_tail(self.gathered.data_ptr(), self.resp_dev.data_ptr(), stream)
+        else:
+            srv.fold_tail(srv.partial_ct_ptr(), self.resp_dev.data_ptr(), stream)
+
+    def download(self):
+        if self.rank == 0:
+            self.resp_host.copy_(self.resp_dev, non_blocking=True)
+
+    def check(self, stream):
+        if self.use_p2p and self.srv.xchg_error(stream) != 0:
+            raise SystemExit(f"rank {self.rank}: peer exchange timed out (error {self.srv.xchg_error(stream)})")
+
+    def close(self):
+        self.srv.close()
+
+
+class PackDriver:
+    """SpiralPack (packed query + expansion) / SpiralStreamPack (direct upload): resident PackServer, out_n^2 planes."""
+    kernel = "k_scan_pack"
+
+    def __init__(self, args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np):
+        from spiral_b200 import SpiralParams
+        from spiral_b200.server import PackServer
+        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        wl = WORKLOADS[cfg]
+        p = wl["prm"]
+        self.direct = wl["direct"]
+        prm = SpiralParams(nu1, nu2, p["t_gsw"], p["t_conv"], p["t_exp"], p["t_exp_right"], p["qp_bits"], p["out_n"], p["p_db"])
+        self.srv = srv = PackServer(prm, device=local_rank, rank=rank, world=world)
+        srv.load_random(seed=1000 + rank)
+        rnd_ntt = rnd_ntt_factory(np, 7)
+        n, ell, dim0 = p["out_n"], p["t_gsw"], 1 << nu1
+        nbits = ell * nu2
+        g, stop = ceil_log2(nbits + dim0), ceil_log2(max(nbits, 1))
+        vW = rnd_ntt(n * (n + 1) * p["t_conv"])
+        if self.direct:
+            srv.set_public_params(None, None, None, vW)
+            self.vf_host = torch.from_numpy(rnd_ntt(dim0 * 2).view(np.int64)).pin_memory()
+            self.vg_host = torch.from_numpy(rnd_ntt(max(nu2, 1) * 2 * 2 * ell).view(np.int64)).pin_memory()
+            self.h2d_bytes = int((self.vf_host.numel() + self.vg_host.numel()) * 8)
+        else:
+            srv.set_public_params(rnd_ntt(g * 2 * p["t_exp"]), rnd_ntt((stop + 1) * 2 * p["t_exp_right"]), rnd_ntt(2 * 2 * p["t_conv"]), vW)
+            self.q_host = torch.from_numpy(rnd_ntt(2).view(np.int64)).pin_memory()
+            self.h2d_bytes = int(self.q_host.numel() * 8)
+        words = srv.partial_words
+        self.resp_host = torch.empty(srv.response_words, dtype=torch.int64).pin_memory()
+        self.resp_dev = torch.empty(srv.response_words, dtype=torch.int64, device="cuda")
+        self.part = torch.empty(words, dtype=torch.int64, device="cuda")
+        self.gathered = torch.empty(world * words, dtype=torch.int64, device="cuda")
+        self.d2h_bytes = int(self.resp_host.numel() * 8)
+        self.db_bytes = srv.db_bytes
+        self.exchange = "none (1 GPU)" if world == 1 else f"NCCL all_gather of {srv.planes} surviving 32 KiB ciphertexts per GPU"
+
+    def upload(self, stream):
+        if self.direct:   # the already-expanded query: 2^nu1 first-dimension cts + nu2 GSW cts, narrowed + reoriented on arrival
+            self.srv.upload_direct_ptr(self.vf_host.data_ptr(), self.vg_host.data_ptr(), stream)
+        else:
+            self.srv.upload_query_ptr(self.q_host.data_ptr(), stream)
+
+    def stage_convert(self, stream):
+        if not self.direct:
+            self.srv.expand_and_convert(stream)
+
+    def stage_scan(self, stream):
+        self.srv.scan(stream)
+
+    def stage_rest(self, stream):
+        srv = self.srv
+        srv.fold_local(stream)
+        if self.world > 1:
+            srv.copy_partial(self.part.data_ptr(), stream)
+            self.dist.all_gather_into_tensor(self.gathered, self.part)
+            if self.rank == 0:
+                srv.fold_tail(self.gathered.data_ptr(), self.resp_dev.data_ptr(), stream)
+        else:
+            srv.fold_tail(srv.partial_cts_ptr(), self.resp_dev.data_ptr(), stream)
+
+    def download(self):
+        if self.rank == 0:
+            self.resp_host.copy_(self.resp_dev, non_blocking=True)
+
+    def check(self, stream):
+        pass
+
+    def close(self):
+        self.srv.close()
+
+
 def b200_main(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from spiral_b200 import SpiralParams
     from spiral_b200.lib import load_library
     from spiral_b200.server import SpiralServer
 
@@ -247,35 +514,9 @@ def b200_main(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = load_library()
 
-    log_w = world.bit_length() - 1
-    nu1, nu2 = args.nu1, args.nu2 + log_w                    # weak scaling: fixed 2^(nu1+args.nu2) items per GPU
-    prm = SpiralParams(nu1, nu2, CFG1["t_gsw"], CFG1["t_conv"], CFG1["t_exp"], CFG1["t_exp_right"], CFG1["qp_bits"], CFG1["out_n"], CFG1["p_db"])
-    srv = SpiralServer(prm, device=local_rank, rank=rank, world=world)
-    srv.load_db_random(seed=1000 + rank)
-    use_p2p = world > 1 and args.exchange == "p2p"
-    if use_p2p:                                       # cudaIpc handles of every rank's exchange buffer, rank order
-        handles = [None] * world
-        dist.all_gather_object(handles, srv.xchg_export())
-        srv.xchg_connect(handles)
-
-    # synthetic public parameters and query: uniform ring elements of the right shape (ref-NTT layout)
-    rng = np.random.default_rng(7)                           # same on every rank (the query is replicated)
-    PL = 2 * N_POLY
-    ell_bits = CFG1["t_gsw"] * nu2
-    g = int(np.ceil(np.log2(ell_bits + (1 << nu1))))
-    stop = int(np.ceil(np.log2(ell_bits))) if ell_bits <= (1 << nu1) else 0
-    n_right = stop + 1 if stop else g
-
-    def rnd_ntt(npolys):
-        a = rng.integers(0, 249561089, size=(npolys, 2, N_POLY), dtype=np.uint64)
-        return np.ascontiguousarray(a.reshape(-1))
-    srv.set_public_params(rnd_ntt(g * 2 * CFG1["t_exp"]), rnd_ntt(n_right * 2 * CFG1["t_exp_right"]),
-                          rnd_ntt(3 * 2 * CFG1["t_conv"]), rnd_ntt(3 * 2 * CFG1["t_conv"]))
-    q_host = torch.from_numpy(rnd_ntt(2).view(np.int64)).pin_memory()
-    resp_host = torch.empty(6 * N_POLY, dtype=torch.int64).pin_memory()
-    gathered = torch.empty(world * 6 * N_POLY, dtype=torch.int64, device="cuda")
-    part = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
-    resp_dev = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
+    cfg, wl = args.workload, WORKLOADS[args.workload]
+    nu1, nu2, scaling = workload_shape(args, world)
+    drv = (SpiralDriver if wl["kind"] == "spiral" else PackDriver)(args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np)
     # a dedicated (non-legacy) stream: kernels, graph replays, events, NCCL and copies all run on it
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
@@ -286,34 +527,23 @@ def b200_main(args):
 
     def step(timed_events=None, e2e=False):
         """One query.  e2e=True includes the H2D of the query and the D2H of the response."""
-        if e2e or timed_events is None:
-            srv.upload_query_ptr(q_host.data_ptr(), stream)
+        if e2e:
+            drv.upload(stream)
         marks = []
         if timed_events is not None:
             marks.append(ev()); marks[-1].record()
-        srv.expand_and_convert(stream)
+        drv.stage_convert(stream)
         if timed_events is not None:
             marks.append(ev()); marks[-1].record()
-        srv.scan(stream)
+        drv.stage_scan(stream)
         if timed_events is not None:
             marks.append(ev()); marks[-1].record()
-        srv.lift(stream)
-        srv.fold_local(stream)
-        if use_p2p:
-            # exchange step fused into the stream: stores into rank 0's HBM over NVLink + flag, rank 0 waits and folds
-            srv.exchange_and_tail(resp_dev.data_ptr(), stream)
-        elif world > 1:
-            srv.copy_partial(part.data_ptr(), stream)
-            dist.all_gather_into_tensor(gathered, part)       # one 96 KiB ciphertext per GPU over NVLink (NCCL)
-            if rank == 0:
-                srv.fold_tail(gathered.data_ptr(), resp_dev.data_ptr(), stream)
-        else:
-            srv.fold_tail(srv.partial_ct_ptr(), resp_dev.data_ptr(), stream)
+        drv.stage_rest(stream)
         if timed_events is not None:
             marks.append(ev()); marks[-1].record()
             timed_events.append(marks)
-        if e2e and rank == 0:
-            resp_host.copy_(resp_dev, non_blocking=True)
+        if e2e:
+            drv.download()
 
     def barrier():
         if world > 1:
@@ -321,7 +551,7 @@ def b200_main(args):
         torch.cuda.synchronize()
 
     # resident upload once for the device-timed loop
-    srv.upload_query_ptr(q_host.data_ptr(), stream)
+    drv.upload(stream)
     for _ in range(max(args.warmup, 3)):
         step(timed_events=[])
     barrier()
@@ -340,8 +570,7 @@ def b200_main(args):
     barrier()
     launches = lib.sb200_launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
-    if use_p2p and srv.xchg_error(stream) != 0:
-        raise SystemExit(f"rank {rank}: peer exchange timed out (error {srv.xchg_error(stream)})")
+    drv.check(stream)
 
     # end to end through the host-buffer call path (H2D query + D2H response inside the timed region)
     e_begin, e_end = ev(), ev()
@@ -358,16 +587,16 @@ def b200_main(args):
     # serving throughput on ONE GPU: several clients in flight (views over the same resident database, one stream
     # each).  The latency-bound expansion / fold chains of one query overlap the HBM-bound scan of another.
     pipelined = None
-    if world == 1 and args.clients > 1:
+    if world == 1 and args.clients > 1 and wl["kind"] == "spiral":
+        srv, p, rnd_ntt = drv.srv, drv.p, drv.rnd_ntt
+        q_host, resp_host, resp_dev = drv.q_host, drv.resp_host, drv.resp_dev
         clients = [srv] + [srv.view() for _ in range(args.clients - 1)]
         streams = [tstream] + [torch.cuda.Stream() for _ in range(args.clients - 1)]
         resp_hosts = [resp_host] + [torch.empty(6 * N_POLY, dtype=torch.int64).pin_memory() for _ in range(args.clients - 1)]
         resp_devs = [resp_dev] + [torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda") for _ in range(args.clients - 1)]
-        rng2 = np.random.default_rng(7)
         for c in clients[1:]:
-            c.set_public_params(rnd_ntt(g * 2 * CFG1["t_exp"]), rnd_ntt(n_right * 2 * CFG1["t_exp_right"]),
-                                rnd_ntt(3 * 2 * CFG1["t_conv"]), rnd_ntt(3 * 2 * CFG1["t_conv"]))
-        del rng2
+            c.set_public_params(rnd_ntt(drv.g * 2 * p["t_exp"]), rnd_ntt(drv.n_right * 2 * p["t_exp_right"]),
+                                rnd_ntt(3 * 2 * p["t_conv"]), rnd_ntt(3 * 2 * p["t_conv"]))
 
         def one(ci):
             c, st = clients[ci], streams[ci]
@@ -459,50 +688,59 @@ def b200_main(args):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        db_bytes_gpu = srv.db_bytes                            # algorithmic bytes per launch: 8 B x 2048 x 4 x items on this GPU
+        db_bytes_gpu = drv.db_bytes                            # algorithmic bytes per launch: 8 B x NTT coefficients on this GPU
         achieved = db_bytes_gpu / (scan_avg * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch") if cfg == "cfg1" and scaling == "weak" else tj.get(f"dram_bytes_per_launch_{cfg}_{world}gpu")
             except Exception:  # noqa: BLE001
                 traffic = None
         ms_per_query = total_ms / args.steps
+        l2_note = (f"database shard ({db_bytes_gpu / 2**30:.2f} GiB) is {db_bytes_gpu / 126e6:.0f}x the 126 MB L2 and is streamed once per query - no flush needed"
+                   if db_bytes_gpu > 4 * 126e6 else f"database shard is only {db_bytes_gpu / 2**20:.0f} MiB: partly L2-resident between queries")
         line = {
             "metric": "server_ms_per_query", "value": ms_per_query, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_query, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (28-bit CRT residues, 32x32->64 MAC)",
+            "ms_per_step": ms_per_query, "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "u64 (28-bit CRT residues, 32x32->64 MAC)",
             "data": "synthetic",
-            "config": {"workload": workload_name(nu1, nu2), "sharding": f"second dimension strided over {world} GPU(s), {srv.db_bytes / 2**30:.2f} GiB shard per GPU",
-                       "exchange": ("none (1 GPU)" if world == 1 else "peer-memory stores + flags over NVLink, fused into the stream (no NCCL call per query)" if use_p2p
-                                    else "NCCL all_gather of one 96 KiB ciphertext per GPU"),
-                       "l2": "database shard (2 GiB) is 16x the 126 MB L2 and is streamed once per query - no flush needed"},
+            "config": {"workload": workload_name(cfg, nu1, nu2), "sharding": f"second dimension strided over {world} GPU(s), {db_bytes_gpu / 2**30:.2f} GiB shard per GPU",
+                       "exchange": drv.exchange, "l2": l2_note},
             "stages_ms": {"expansion_conversion": exp_ms, "first_dim_scan": scan_avg, "lift_fold_modswitch": rest_ms},
             "db_gbs_scanned": world * db_bytes_gpu / (scan_max * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_scan_spiral", "peak_source": peak_src, "scan_ms_min_med_max": [scan_ms[0], scan_ms[len(scan_ms) // 2], scan_ms[-1]]},
-            "e2e": {"value": e2e_ms / args.steps, "unit": "ms", "h2d_bytes_per_step": int(q_host.numel() * 8), "d2h_bytes_per_step": int(resp_host.numel() * 8)},
+                         "kernel": drv.kernel, "peak_source": peak_src, "scan_ms_min_med_max": [scan_ms[0], scan_ms[len(scan_ms) // 2], scan_ms[-1]]},
+            "e2e": {"value": e2e_ms / args.steps, "unit": "ms", "h2d_bytes_per_step": drv.h2d_bytes, "d2h_bytes_per_step": drv.d2h_bytes},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if pipelined is not None:
             line["pipelined"] = pipelined
         if world == 1 and not args.no_cpu_baseline:
-            res, info = run_reference(args.nu1, args.nu2, 2)
-            if res is not None:
-                qd = res[-1]
-                line["cpu_baseline"] = {"value": qd["total"], "unit": "ms", "cores": 1, "kind": "reference",
-                                        "stages_ms": {k: qd[k] for k in ("expansion", "conversion", "first_dim", "folding")},
-                                        "sample": f"unmodified reference (oracle/_ref, {info}), 2nd of 2 full queries at the same workload, 1 thread on {cpu_model()}, decoded correctly: {qd['correct']}"}
+            if wl["kind"] == "pack":
+                q, info, text = pack_sample_scaled(cfg, nu1, nu2)
+                if q is not None:
+                    line["cpu_baseline"] = {"value": q["total"], "unit": "ms", "cores": 1, "kind": "reference", "stages_ms": {k: q[k] for k in STAGES},
+                                            "sample": text + f"; 1 thread on {cpu_model()} ({info}); decoded correctly: {q['correct']}"}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "reference", "sample": f"unavailable: {info}"}
             else:
-                try:
-                    ms = oracle_port_baseline(6, 4)
-                    line["cpu_baseline"] = {"value": ms, "unit": "ms", "cores": 1, "kind": "port",
-                                            "sample": f"oracle port, one query at ./spiral 6 4 (1/32 of the records), 1 core ({info})"}
-                except Exception as e:  # noqa: BLE001
-                    line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+                res, info = (None, "database too large for the host") if db_bytes_total(wl, nu1, nu2) * 2.5 > mem_available() else run_reference(cfg, nu1, nu2, 2)
+                if res is not None:
+                    qd = res[-1]
+                    line["cpu_baseline"] = {"value": qd["total"], "unit": "ms", "cores": 1, "kind": "reference",
+                                            "stages_ms": {k: qd[k] for k in ("expansion", "conversion", "first_dim", "folding")},
+                                            "sample": f"unmodified reference (oracle/_ref, {info}), 2nd of 2 full queries at the same workload, 1 thread on {cpu_model()}, decoded correctly: {qd['correct']}"}
+                else:
+                    try:
+                        ms = oracle_port_baseline(6, 4)
+                        line["cpu_baseline"] = {"value": ms, "unit": "ms", "cores": 1, "kind": "port",
+                                                "sample": f"oracle port, one query at ./spiral 6 4 (1/32 of the records), 1 core ({info})"}
+                    except Exception as e:  # noqa: BLE001
+                        line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    srv.close()
+    drv.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -514,8 +752,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nu1", type=int, default=8)
-    ap.add_argument("--nu2", type=int, default=7)
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS), help="BASELINE.json configuration (cfg1 = the headline)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: weak for cfg1 (2 GiB shard per GPU), strong for the others")
+    ap.add_argument("--nu1", type=int, default=None)
+    ap.add_argument("--nu2", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clients", type=int, default=4, help="N = 1: concurrent clients for the serving-throughput figure (0/1 = skip)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the surviving ciphertexts reach rank 0")

@@ -69,6 +69,18 @@ int sb200_dev_multiply(uint32_t *out, const uint32_t *a, const uint32_t *b, int 
 int sb200_dev_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t t, void *stream);   /* src/poly.cpp:240-261 */
 int sb200_dev_gadget_ntt(uint32_t *out, const uint64_t *raw, int mx, int rdim, int cols, void *stream); /* src/util.cpp:114-150 + to_ntt */
 int sb200_dev_rescale(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod, void *stream); /* src/poly.cpp:578-601 */
+/* modswitch: round((long double)v * arb_qprime / Q) in the reference's x87 arithmetic, bit-packed at qp_bits (src/spiral.cpp:40-78) */
+int sb200_dev_modswitch(uint64_t *out_words, const uint64_t *cts_raw, size_t ncoeffs, uint32_t qp_bits, void *stream);
+/* write_arbitrary_bits over a buffer: n values of `bits` bits -> sb200_packed_words(n, bits) words (src/core.cpp:32-52) */
+int sb200_dev_bitpack(uint64_t *out_words, const uint64_t *values, size_t n, uint32_t bits, void *stream);
+size_t sb200_packed_words(size_t ncoeffs, uint32_t bits);
+/* response wire format: modulus-switched response, row 0 at qp_bits bits, other rows at log2(4*p_db) bits (sizes: src/spiral.cpp:229-232) */
+size_t sb200_packed_response_words(size_t row0_coeffs, size_t rest_coeffs, uint32_t qp_bits, uint64_t p_db);
+int sb200_dev_pack_response(uint64_t *packed, const uint64_t *total_resp, size_t row0_coeffs, size_t rest_coeffs,
+                            uint32_t qp_bits, uint64_t p_db, void *stream);
+/* client-side inverse (plain host code; read_arbitrary_bits, src/core.cpp:20-30) */
+int sb200_unpack_response(uint64_t *total_resp_host, const uint64_t *packed_host, size_t row0_coeffs, size_t rest_coeffs,
+                          uint32_t qp_bits, uint64_t p_db);
 /* database: plaintext items (u16 coefficients < p_db, [item][m*2+c][2048]) -> scan layout (load_db, src/spiral.cpp:1028-1172) */
 int sb200_dev_db_build(uint64_t *db, const uint16_t *pts, uint32_t nu1, uint32_t nu2, uint32_t p_db,
                        size_t item_begin, size_t item_count, void *stream);
@@ -91,6 +103,8 @@ int sb200_multiply(uint64_t *out, const uint64_t *a, const uint64_t *b, int rs, 
 int sb200_automorph(uint64_t *out_raw, const uint64_t *in_raw, size_t npolys, uint32_t t);
 int sb200_gadget_invert(uint64_t *out_raw, const uint64_t *in_raw, int mx, int rdim, int cols);   /* src/util.cpp:114-150 */
 int sb200_getRescaled(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod);
+/* modswitch(furtherDimsLocals.result, furtherDimsLocals.cts): n1 x n2 x 2048 raw coefficients in, 192 * qp_bits words out (src/spiral.cpp:40) */
+int sb200_modswitch(uint64_t *out_words, const uint64_t *cts_raw, uint32_t qp_bits);
 /* load_db: pts = total_n items of n0*n2 polys, u64 coefficients < p_db (reference generate_random_pt); B in reference layout */
 int sb200_load_db(uint64_t *B_ref_layout, const uint64_t *pts, uint32_t nu1, uint32_t nu2, uint64_t p_db);
 int sb200_reorientCiphertexts(uint64_t *out, const uint64_t *inp_ref_ntt, size_t dim0, size_t n1_padded);
@@ -138,6 +152,9 @@ int sb200_server_set_public_params(sb200_server *srv, const uint64_t *W_exp_left
 /* one query end to end: H2D of the packed query ciphertext (2x1 ref-NTT, 64 KiB), all server stages, D2H of the
  * modulus-switched response (3x2 raw, 96 KiB).  world == 1 only. */
 int sb200_server_answer(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream);
+/* same, response in the wire format (sb200_dev_pack_response): 20 KiB instead of 96 KiB at cfg1 */
+int sb200_server_answer_packed(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *packed_resp_host, void *stream);
+size_t sb200_server_packed_response_bytes(const sb200_server *srv);
 /* staged variants (device-resident between stages; used by bench.py and the multi-GPU path) */
 int sb200_server_upload_query(sb200_server *srv, const uint64_t *query_cv_host, void *stream);
 int sb200_server_expand_and_convert(sb200_server *srv, void *stream);      /* expansion + ScalToMat + RegevToGSW (+negation) */

@@ -40,11 +40,46 @@ static void fill_raw_edgy(uint64_t *out, size_t n, so_rng *r) {
     for (size_t i = 11; i < n; i += 211) out[i] = (so_rng_next(r) & 0xffff);
 }
 
+/* modswitch (src/spiral.cpp:40-78) computes round((long double)v * q' / Q) in x87 arithmetic: the product is rounded to
+ * a 64-bit significand, then the quotient, then roundl.  Uniform inputs never get close enough to k + 1/2 for the
+ * double rounding to show (probability ~2^-45 per coefficient), so the case plants coefficients built to sit just below
+ * a half: P' = M * 2^s (a representable product) with P' mod Q = (Q-1)/2 - t for small t, and val = round(P' / q')
+ * whenever val * q' really rounds to P'.  About 40 % of them round differently from exact integer rounding. */
+typedef unsigned __int128 gc_u128;
+static uint64_t gc_invmod(uint64_t a, uint64_t m) {
+    __int128 t = 0, nt = 1, r = m, nr = a % m;
+    while (nr) { __int128 q = r / nr, tmp = t - q * nt; t = nt; nt = tmp; tmp = r - q * nr; r = nr; nr = tmp; }
+    if (t < 0) t += m;
+    return (uint64_t)t;
+}
+static size_t fill_modswitch_adversarial(uint64_t *out, size_t want, uint64_t qp, so_rng *r) {
+    size_t n = 0;
+    if (qp == 0 || qp % SO_P == 0 || qp % SO_B == 0) return 0;
+    for (unsigned pass = 0; pass < 4096 && n < want; pass++)
+        for (unsigned s = 1; s <= 37 && n < want; s++) {
+            uint64_t inv2s = gc_invmod((uint64_t)(((gc_u128)1 << s) % SO_Q), SO_Q);
+            uint64_t t = so_rng_next(r) % 3000;
+            uint64_t R = (SO_Q - 1) / 2 - t, M0 = (uint64_t)((gc_u128)R * inv2s % SO_Q);
+            for (uint64_t k = 0; k < 300 && n < want; k++) {
+                gc_u128 M = (gc_u128)M0 + (gc_u128)k * SO_Q;
+                if (M < ((gc_u128)1 << 63) || M >= ((gc_u128)1 << 64)) continue;
+                gc_u128 Pp = M << s, val = (Pp + qp / 2) / qp, P = val * qp;
+                if (val > SO_Q) continue;
+                unsigned L = 0; for (gc_u128 v = P; v; v >>= 1) L++;
+                if (L != 64 + s) continue;
+                gc_u128 m = P >> s, rem = P & (((gc_u128)1 << s) - 1), half = (gc_u128)1 << (s - 1);
+                if (rem > half || (rem == half && (m & 1))) m++;
+                if ((m << s) == Pp) out[n++] = (uint64_t)val;
+            }
+        }
+    return n;
+}
+
 static const char *NAMES[SO_CASE_COUNT] = {
     "ntt_forward", "ntt_inverse", "to_ntt", "from_ntt", "multiply", "automorph", "gadget_invert",
     "rescale", "reorient_ciphertexts", "first_dim", "ntt_inv_crt_lift", "split_and_crt", "fold_one",
     "expand_full", "expand_stopround", "scal_to_mat", "regev_to_gsw", "load_db", "convert_db",
-    "reorient_dim1", "first_dim_pack", "fold_dim1", "regev_to_simple_gsw", "pack", "to_ntt_no_reduce",
+    "reorient_dim1", "first_dim_pack", "fold_dim1", "regev_to_simple_gsw", "pack", "to_ntt_no_reduce", "modswitch",
 };
 int so_case_count(void) { return SO_CASE_COUNT; }
 const char *so_case_name(int id) { return (id >= 0 && id < SO_CASE_COUNT) ? NAMES[id] : "?"; }
@@ -77,6 +112,15 @@ void so_case_make_inputs(int id, const so_params *p, uint64_t seed, so_case_io *
         set_in(io, 0, s.npolys * N); fill_raw_edgy(io->in[0], s.npolys * N, &r); break;
     case SO_CASE_TO_NTT_NR:
         set_in(io, 0, s.npolys * N); so_fill_uniform_mod(io->in[0], s.npolys * N, 1ull << 29, &r); break;
+    case SO_CASE_MODSWITCH: {                                   /* furtherDimsLocals.cts: n1 x n2 raw, values in [0, Q] */
+        size_t n = SO_N1 * SO_N2 * N;
+        set_in(io, 0, n); fill_raw_edgy(io->in[0], n, &r);
+        io->in[0][1] = SO_Q; io->in[0][2] = SO_Q / 2; io->in[0][3] = SO_Q / 2 + 1; io->in[0][4] = 1;
+        uint64_t *adv = xalloc(1024);
+        size_t cnt = fill_modswitch_adversarial(adv, 1024, so_arb_qprime(p->qp_bits), &r);
+        for (size_t i = 0; i < cnt; i++) io->in[0][8 + 5 * i] = adv[i];      /* 5 and qp_bits coprime to 64: all word phases */
+        free(adv);
+        break; }
     case SO_CASE_MULTIPLY:
         set_in(io, 0, 2 * 3 * PL); so_fill_uniform_ntt(io->in[0], 6, &r);
         set_in(io, 1, 3 * 2 * PL); so_fill_uniform_ntt(io->in[1], 6, &r); break;
@@ -150,6 +194,9 @@ void so_case_run_oracle(int id, const so_params *p, so_case_io *io) {
         set_out(io, s.npolys * PL, SO_KIND_NTT); so_to_ntt(io->out, io->in[0], s.npolys); break;
     case SO_CASE_TO_NTT_NR:
         set_out(io, s.npolys * PL, SO_KIND_NTT); so_to_ntt_no_reduce(io->out, io->in[0], s.npolys); break;
+    case SO_CASE_MODSWITCH:
+        set_out(io, so_packed_words(io->in_words[0], p->qp_bits), SO_KIND_RAW);
+        so_modswitch(io->out, io->in[0], io->in_words[0], p->qp_bits); break;
     case SO_CASE_FROM_NTT:
         set_out(io, s.npolys * N, SO_KIND_RAW); so_from_ntt(io->out, io->in[0], s.npolys); break;
     case SO_CASE_MULTIPLY:

@@ -11,7 +11,7 @@ enum {
     SO_CASE_NTT_INV_CRT, SO_CASE_SPLIT_AND_CRT, SO_CASE_FOLD_ONE, SO_CASE_EXPAND_FULL,
     SO_CASE_EXPAND_STOP, SO_CASE_SCAL_TO_MAT, SO_CASE_REGEV_TO_GSW, SO_CASE_LOAD_DB,
     SO_CASE_CONVERT_DB, SO_CASE_REORIENT_DIM1, SO_CASE_FIRST_DIM_PACK, SO_CASE_FOLD_DIM1,
-    SO_CASE_REGEV_TO_SGSW, SO_CASE_PACK, SO_CASE_TO_NTT_NR, SO_CASE_COUNT
+    SO_CASE_REGEV_TO_SGSW, SO_CASE_PACK, SO_CASE_TO_NTT_NR, SO_CASE_MODSWITCH, SO_CASE_COUNT
 };
 enum { SO_KIND_RAW = 0, SO_KIND_NTT = 1, SO_KIND_PACKED = 2 };
 #define SO_CASE_MAX_IN 4

@@ -38,6 +38,7 @@ public:
         scratch_cts_double2 = (uint64_t *)calloc(m2 / n1 * num_bytes_C, 1);
     }
 };
+void modswitch(uint64_t *out, const uint64_t *inp);      // src/spiral.cpp:40
 void setup_constants();
 void set_neg1s();
 void load_db();
@@ -90,6 +91,10 @@ static std::vector<uint64_t> run_reference(int id, const so_params *p, so_case_i
         for (size_t i = 0; i < s.npolys; i++) (id == SO_CASE_NTT_FWD ? ntt_forward : ntt_inverse)(&out[i * PLW]);
         break;
     case SO_CASE_TO_NTT: { MatPoly a = mk(1, s.npolys, false, io->in[0]); MatPoly o(1, s.npolys); to_ntt(o, a); out = flat({o}); break; }
+    case SO_CASE_MODSWITCH:
+        out.assign((n1 * n2 * poly_len * bits_to_hold_arb_qprime + 63) / 64 + 1, 0);     // +1: the 128-bit store of write_arbitrary_bits
+        modswitch(out.data(), io->in[0]);
+        out.pop_back(); break;
     case SO_CASE_TO_NTT_NR: { MatPoly a = mk(1, s.npolys, false, io->in[0]); MatPoly o(1, s.npolys); to_ntt_no_reduce(o, a); out = flat({o}); break; }
     case SO_CASE_FROM_NTT: { MatPoly a = mk(1, s.npolys, true, io->in[0]); MatPoly o(1, s.npolys, false); from_ntt(o, a); out = flat({o}); break; }
     case SO_CASE_MULTIPLY: { MatPoly a = mk(2, 3, true, io->in[0]), b = mk(3, 2, true, io->in[1]); MatPoly o(2, 2); multiply(o, a, b); out = flat({o}); break; }

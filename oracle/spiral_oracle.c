@@ -137,6 +137,72 @@ void so_get_rescaled(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t
 }
 
 /* ------------------------------------------------------------------------------------------
+ * bit I/O (src/core.cpp:20-52) and modswitch (src/spiral.cpp:40-78)
+ * ---------------------------------------------------------------------------------------- */
+uint64_t so_read_arbitrary_bits(const uint64_t *p, size_t bit_offs, size_t num_bits) {   /* src/core.cpp:20-30 */
+    size_t word_off = bit_offs / 64, in_word = bit_offs % 64;
+    uint64_t mask = (1ull << num_bits) - 1;
+    if (in_word + num_bits <= 64) return (p[word_off] >> in_word) & mask;
+    u128 v = (u128)p[word_off] | ((u128)p[word_off + 1] << 64);
+    return (uint64_t)(v >> in_word) & mask;
+}
+void so_write_arbitrary_bits(uint64_t *p, uint64_t val, size_t bit_offs, size_t num_bits) {   /* src/core.cpp:32-52 */
+    size_t word_off = bit_offs / 64, in_word = bit_offs % 64;
+    uint64_t mask = (1ull << num_bits) - 1;
+    val &= mask;
+    p[word_off] = (p[word_off] & ~(mask << in_word)) | (val << in_word);
+    if (in_word + num_bits > 64) {
+        size_t spill = in_word + num_bits - 64;                     /* high bits land in the next word */
+        p[word_off + 1] = (p[word_off + 1] & ~((1ull << spill) - 1)) | (val >> (num_bits - spill));
+    }
+}
+size_t so_packed_words(size_t ncoeffs, uint32_t bits) { return (ncoeffs * bits + 63) / 64; }
+
+/* modswitch's arithmetic (src/spiral.cpp:58-64) is x87 extended precision:
+ *     long double d = (long double)val * (long double)arb_qprime / (long double)Q_i;  result = round(d)   [roundl]
+ * i.e. P' = RNE64(val * q')  (the exact product can need 93 bits; round-to-nearest-even to a 64-bit significand),
+ *      D  = RNE64(P' / Q), result = floor(D + 1/2) (half away from zero, D >= 0).
+ * Restated exactly in integers: with I = floor(P'/Q), R = P' mod Q and f = 64 - bitlen(I) fraction bits in D,
+ * D >= I + 1/2  <=>  R/Q >= 1/2 - 2^-(f+1)  (I + 1/2 is representable and its significand is even, so the tie of the
+ * second rounding goes up)  <=>  2R >= Q  or  Q - 2R <= floor(Q / 2^f).  For I = 0 the bound is 2R >= Q. */
+static unsigned bitlen_u128(u128 v) { unsigned n = 0; while (v) { n++; v >>= 1; } return n; }
+uint64_t so_modswitch_coeff(uint64_t val, uint64_t qprime) {
+    u128 P128 = (u128)val * qprime;
+    unsigned L = bitlen_u128(P128);
+    if (L > 64) {                                                   /* first rounding: product to 64 significant bits */
+        unsigned s = L - 64;
+        u128 m = P128 >> s, rem = P128 & (((u128)1 << s) - 1), half = (u128)1 << (s - 1);
+        if (rem > half || (rem == half && (m & 1))) m++;
+        P128 = m << s;
+    }
+    uint64_t I = (uint64_t)(P128 / Q), R = (uint64_t)(P128 % Q);
+    int up;
+    if (2 * R >= Q) up = 1;
+    else if (I == 0) up = 0;
+    else {
+        unsigned f = 64 - bitlen_u128(I);
+        up = (Q - 2 * R) <= (f >= 64 ? 0 : (Q >> f));
+    }
+    return I + (uint64_t)up;
+}
+uint64_t so_modswitch_coeff_x87(uint64_t val, uint64_t qprime) {
+#if defined(__x86_64__) || defined(__i386__)
+    long double d = ((long double)(int64_t)val) * ((long double)qprime) / ((long double)Q);
+    return (uint64_t)(int64_t)roundl(d);
+#else
+    return so_modswitch_coeff(val, qprime);
+#endif
+}
+void so_modswitch(uint64_t *out_words, const uint64_t *in_raw, size_t ncoeffs, uint32_t qp_bits) {   /* src/spiral.cpp:40-78 */
+    uint64_t qprime = so_arb_qprime(qp_bits);
+    size_t bit_offs = 0;
+    for (size_t i = 0; i < ncoeffs; i++) {          /* r, c, m loops of the reference = one linear pass */
+        so_write_arbitrary_bits(out_words, so_modswitch_coeff(in_raw[i], qprime), bit_offs, qp_bits);
+        bit_offs += qp_bits;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * NTT  (src/core.cpp:254-416 forward, :426-514 inverse; scalar statements)
  * ---------------------------------------------------------------------------------------- */
 void so_ntt_forward(uint64_t *op_all) {

@@ -70,6 +70,14 @@ void so_invert(uint64_t *out_raw, const uint64_t *in_raw, size_t npolys);
 void so_build_gadget(uint64_t *G_raw, size_t rows, size_t cols);                 /* src/util.cpp:89-112  */
 void so_gadget_invert(uint64_t *out_raw, const uint64_t *in_raw, size_t mx, size_t rdim, size_t cols); /* src/util.cpp:114-150 */
 void so_get_rescaled(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod); /* src/poly.cpp:593-601 */
+/* bit I/O (src/core.cpp:20-52) and the response bit-packer modswitch (src/spiral.cpp:40-78):
+ * round((long double)v * arb_qprime / Q) packed at qp_bits bits per coefficient, n1*n2*N coefficients. */
+uint64_t so_read_arbitrary_bits(const uint64_t *p, size_t bit_offs, size_t num_bits);
+void so_write_arbitrary_bits(uint64_t *p, uint64_t val, size_t bit_offs, size_t num_bits);
+uint64_t so_modswitch_coeff(uint64_t val, uint64_t qprime);          /* x87 arithmetic restated in integers */
+uint64_t so_modswitch_coeff_x87(uint64_t val, uint64_t qprime);      /* the literal long double statements (x86 only; self-check) */
+void so_modswitch(uint64_t *out_words, const uint64_t *in_raw, size_t ncoeffs, uint32_t qp_bits);
+size_t so_packed_words(size_t ncoeffs, uint32_t bits);               /* u64 words holding ncoeffs values of `bits` bits */
 
 /* ---- Spiral / SpiralStream server path (src/spiral.cpp) --------------------------------- */
 void so_encode_plaintext(uint64_t *out_raw, const uint64_t *pt, size_t ncoeffs, uint64_t p_db);  /* :1116-1127 */

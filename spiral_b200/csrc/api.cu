@@ -93,6 +93,17 @@ extern "C" int sb200_dev_gadget_ntt(uint32_t *out, const uint64_t *raw, int mx, 
 extern "C" int sb200_dev_rescale(uint64_t *out, const uint64_t *in, size_t n, uint64_t inp_mod, uint64_t out_mod, void *stream) {
     NEED_DEVICE(); launch_rescale(out, in, n, inp_mod, out_mod, S(stream)); CHECK_LAUNCH(); return SB200_OK;
 }
+extern "C" size_t sb200_packed_words(size_t ncoeffs, uint32_t bits) { return (ncoeffs * bits + 63) / 64; }
+extern "C" int sb200_dev_modswitch(uint64_t *out_words, const uint64_t *cts_raw, size_t ncoeffs, uint32_t qp_bits, void *stream) {
+    NEED_DEVICE();
+    if (qp_bits == 0 || qp_bits > 36 || !sb200_arb_qprime(qp_bits)) return fail(SB200_ERR_ARG, "modswitch: no arb_qprime for %u bits", qp_bits);
+    launch_modswitch(out_words, cts_raw, ncoeffs, qp_bits, sb200_arb_qprime(qp_bits), S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_bitpack(uint64_t *out_words, const uint64_t *values, size_t n, uint32_t bits, void *stream) {
+    NEED_DEVICE();
+    if (bits == 0 || bits > 63) return fail(SB200_ERR_ARG, "bitpack: bits must be in [1, 63]");
+    launch_bitpack(out_words, values, n, bits, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
 extern "C" size_t sb200_db_words(uint32_t nu1, uint32_t nu2) { return ((size_t)kN << (nu1 + nu2)) * kN0 * kN2; }
 extern "C" int sb200_dev_db_build(uint64_t *db, const uint16_t *pts, uint32_t nu1, uint32_t nu2, uint32_t p_db,
                                   size_t item_begin, size_t item_count, void *stream) {
@@ -233,6 +244,46 @@ extern "C" int sb200_getRescaled(uint64_t *out, const uint64_t *in, size_t n, ui
     CU(di.up(in, n));
     launch_rescale(dout.p, di.p, n, inp_mod, out_mod, 0); CHECK_LAUNCH();
     CU(dout.down(out, n));
+    return SB200_OK;
+}
+// modswitch(furtherDimsLocals.result, furtherDimsLocals.cts) (src/spiral.cpp:40, call :2460): n1 x n2 x 2048 coefficients
+extern "C" int sb200_modswitch(uint64_t *out_words, const uint64_t *cts_raw, uint32_t qp_bits) {
+    NEED_DEVICE();
+    const size_t n = (size_t)kN1 * kN2 * kN, words = sb200_packed_words(n, qp_bits);
+    DBuf<uint64_t> di(n), dout(words);
+    CU(di.up(cts_raw, n));
+    TRY(sb200_dev_modswitch(dout.p, di.p, n, qp_bits, nullptr));
+    CU(dout.down(out_words, words));
+    return SB200_OK;
+}
+// ---- response wire format (sizes as print_summary counts them, src/spiral.cpp:229-232): the modulus-switched
+// response bit-packed, row 0 at qp_bits bits per coefficient, the remaining rows at log2(4 * p_db) bits
+static uint32_t rest_bits_of(uint64_t p_db) { uint32_t b = 0; while ((1ull << b) < 4 * p_db) b++; return b; }
+extern "C" size_t sb200_packed_response_words(size_t row0_coeffs, size_t rest_coeffs, uint32_t qp_bits, uint64_t p_db) {
+    return sb200_packed_words(row0_coeffs, qp_bits) + sb200_packed_words(rest_coeffs, rest_bits_of(p_db));
+}
+extern "C" int sb200_dev_pack_response(uint64_t *packed, const uint64_t *total_resp, size_t row0_coeffs, size_t rest_coeffs,
+                                       uint32_t qp_bits, uint64_t p_db, void *stream) {
+    NEED_DEVICE();
+    if (qp_bits == 0 || qp_bits > 63 || p_db == 0) return fail(SB200_ERR_ARG, "pack_response: bad parameters");
+    launch_bitpack(packed, total_resp, row0_coeffs, qp_bits, S(stream));
+    launch_bitpack(packed + sb200_packed_words(row0_coeffs, qp_bits), total_resp + row0_coeffs, rest_coeffs, rest_bits_of(p_db), S(stream));
+    CHECK_LAUNCH(); return SB200_OK;
+}
+// client-side helper (plain host code, no device): the inverse of sb200_dev_pack_response = read_arbitrary_bits (src/core.cpp:20-30)
+extern "C" int sb200_unpack_response(uint64_t *total_resp, const uint64_t *packed, size_t row0_coeffs, size_t rest_coeffs,
+                                     uint32_t qp_bits, uint64_t p_db) {
+    if (!total_resp || !packed || qp_bits == 0 || qp_bits > 63 || p_db == 0) return fail(SB200_ERR_ARG, "unpack_response: bad argument");
+    auto rd = [](const uint64_t *p, size_t off, uint32_t b) {
+        const size_t w = off / 64, in = off % 64;
+        uint64_t v = p[w] >> in;
+        if (in + b > 64) v |= p[w + 1] << (64 - in);
+        return v & ((1ull << b) - 1);
+    };
+    for (size_t i = 0; i < row0_coeffs; i++) total_resp[i] = rd(packed, i * qp_bits, qp_bits);
+    const uint64_t *seg = packed + sb200_packed_words(row0_coeffs, qp_bits);
+    const uint32_t rb = rest_bits_of(p_db);
+    for (size_t i = 0; i < rest_coeffs; i++) total_resp[row0_coeffs + i] = rd(seg, i * rb, rb);
     return SB200_OK;
 }
 extern "C" int sb200_load_db(uint64_t *B, const uint64_t *pts, uint32_t nu1, uint32_t nu2, uint64_t p_db) {
@@ -793,6 +844,21 @@ extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_hos
     TRY(sb200_server_fold_local(s, stream));
     TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
     return sb200_server_download(s, total_resp_host, s->resp.p, 6 * kN, stream);
+}
+// the same query with the response in its wire format: 20 KiB instead of 96 KiB cross PCIe at cfg1
+extern "C" int sb200_server_answer_packed(sb200_server *s, const uint64_t *query_cv_host, uint64_t *packed_resp_host, void *stream) {
+    if (!s || !packed_resp_host) return fail(SB200_ERR_ARG, "server_answer_packed: null argument");
+    if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer_packed: single-shard call on a sharded server (use the staged API)");
+    TRY(sb200_server_upload_query(s, query_cv_host, stream));
+    TRY(sb200_server_expand_and_convert(s, stream));
+    TRY(sb200_server_first_dim(s, stream));
+    TRY(sb200_server_fold_local(s, stream));
+    TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
+    TRY(sb200_dev_pack_response(s->final_ct.p, s->resp.p, 2 * (size_t)kN, 4 * (size_t)kN, s->prm.qp_bits, s->prm.p_db, ES(s, stream)));
+    return sb200_server_download(s, packed_resp_host, s->final_ct.p, sb200_packed_response_words(2 * (size_t)kN, 4 * (size_t)kN, s->prm.qp_bits, s->prm.p_db), stream);
+}
+extern "C" size_t sb200_server_packed_response_bytes(const sb200_server *s) {
+    return s ? 8 * sb200_packed_response_words(2 * (size_t)kN, 4 * (size_t)kN, s->prm.qp_bits, s->prm.p_db) : 0;
 }
 extern "C" size_t sb200_server_query_bytes(const sb200_server *) { return 2 * PLW * sizeof(uint64_t); }
 extern "C" size_t sb200_server_response_bytes(const sb200_server *) { return 6 * (size_t)kN * sizeof(uint64_t); }

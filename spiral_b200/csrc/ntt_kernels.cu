@@ -292,4 +292,59 @@ void launch_rescale(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t 
     if (ncoeffs) { count_launch(); launch_pdl(k_rescale, dim3((unsigned)((ncoeffs + 255) / 256)), dim3(256), 0, s, out, in, ncoeffs, inp_mod, out_mod); }
 }
 
+// --------------------------------------------------------------------------------------------
+// modswitch (reference src/spiral.cpp:40-78) and bit packing (write_arbitrary_bits, src/core.cpp:32-52).
+// The reference evaluates round((long double)v * q' / Q) in x87 extended precision: the product (up to 93 bits) is
+// rounded to a 64-bit significand, the quotient again, then roundl.  Restated in integers so the GPU agrees bit for
+// bit:  P' = RNE64(v * q'),  I = floor(P'/Q),  R = P' mod Q,  f = 64 - bitlen(I);
+//       result = I + 1  iff  2R >= Q  or  (I > 0 and Q - 2R <= floor(Q / 2^f))      (derivation: oracle/spiral_oracle.c)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t modswitch_one(uint64_t val, uint64_t qp) {
+    uint64_t lo = val * qp, hi = __umul64hi(val, qp);
+    if (hi) {                                               // first rounding: 64 significant bits, ties to even
+        const int s = 64 - __clzll((long long)hi);          // 1 <= s <= 37
+        uint64_t m = (hi << (64 - s)) | (lo >> s);
+        const uint64_t rem = lo & ((1ull << s) - 1), half = 1ull << (s - 1);
+        if (rem > half || (rem == half && (m & 1))) m++;
+        if (m == 0) { hi = 1ull << s; lo = 0; }             // significand overflowed to 2^64
+        else { hi = m >> (64 - s); lo = m << s; }
+    }
+    const uint64_t I = udiv128_64(hi, lo, kQ);              // hi < 2^38 < Q
+    const uint64_t R = lo - I * kQ;
+    bool up;
+    if (2 * R >= kQ) up = true;
+    else if (I == 0) up = false;
+    else up = (kQ - 2 * R) <= (kQ >> __clzll((long long)I));
+    return I + (up ? 1 : 0);
+}
+// One thread per OUTPUT word: gathers the (at most 64/bits + 2) values overlapping it.  MODE 0: plain values,
+// MODE 1: modswitch_one(in[i], qp) computed on the fly.
+template <int MODE>
+__global__ void k_bitpack(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, size_t n, uint32_t bits, uint64_t qp) {
+    pdl_prologue();
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nwords = (n * bits + 63) / 64;
+    if (w >= nwords) return;
+    const uint64_t mask = bits >= 64 ? ~0ull : (1ull << bits) - 1;
+    const size_t lo_bit = w * 64;
+    size_t i = lo_bit / bits;
+    uint64_t word = 0;
+    for (; i < n && i * bits < lo_bit + 64; i++) {
+        uint64_t v = in[i];
+        if (MODE == 1) v = modswitch_one(v, qp);
+        v &= mask;
+        const size_t b = i * bits;
+        word |= b >= lo_bit ? v << (b - lo_bit) : v >> (lo_bit - b);
+    }
+    out[w] = word;
+}
+void launch_bitpack(uint64_t *out, const uint64_t *in, size_t n, uint32_t bits, cudaStream_t s) {
+    const size_t nwords = (n * bits + 63) / 64;
+    if (nwords) { count_launch(); launch_pdl(k_bitpack<0>, dim3((unsigned)((nwords + 127) / 128)), dim3(128), 0, s, out, in, n, bits, (uint64_t)0); }
+}
+void launch_modswitch(uint64_t *out, const uint64_t *in_raw, size_t n, uint32_t bits, uint64_t qprime, cudaStream_t s) {
+    const size_t nwords = (n * bits + 63) / 64;
+    if (nwords) { count_launch(); launch_pdl(k_bitpack<1>, dim3((unsigned)((nwords + 127) / 128)), dim3(128), 0, s, out, in_raw, n, bits, qprime); }
+}
+
 }  // namespace sb200

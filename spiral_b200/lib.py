@@ -73,6 +73,15 @@ def load_library():
         "sb200_dev_automorph": (C.c_int, [vp, vp, sz, C.c_uint32, vp]),
         "sb200_dev_gadget_ntt": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
         "sb200_dev_rescale": (C.c_int, [vp, vp, sz, C.c_uint64, C.c_uint64, vp]),
+        "sb200_dev_modswitch": (C.c_int, [vp, vp, sz, C.c_uint32, vp]),
+        "sb200_dev_bitpack": (C.c_int, [vp, vp, sz, C.c_uint32, vp]),
+        "sb200_packed_words": (sz, [sz, C.c_uint32]),
+        "sb200_packed_response_words": (sz, [sz, sz, C.c_uint32, C.c_uint64]),
+        "sb200_dev_pack_response": (C.c_int, [vp, vp, sz, sz, C.c_uint32, C.c_uint64, vp]),
+        "sb200_unpack_response": (C.c_int, [u64p, u64p, sz, sz, C.c_uint32, C.c_uint64]),
+        "sb200_modswitch": (C.c_int, [u64p, u64p, C.c_uint32]),
+        "sb200_server_answer_packed": (C.c_int, [vp, vp, vp, vp]),
+        "sb200_server_packed_response_bytes": (sz, [vp]),
         "sb200_dev_db_build": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, sz, sz, vp]),
         "sb200_dev_db_from_reference": (C.c_int, [vp, vp, sz, sz, sz, sz, vp]),
         "sb200_dev_reorient_query": (C.c_int, [vp, vp, sz, vp]),

@@ -95,6 +95,15 @@ def load():
     lib.so_pack_expansion_shape.argtypes = [C.POINTER(SoParams), C.POINTER(sz), C.POINTER(sz)]
     lib.so_convert_db.argtypes = [u64p, u64p, sz, sz, sz]
     lib.so_encode_plaintext.argtypes = [u64p, u64p, sz, C.c_uint64]
+    lib.so_modswitch_coeff.restype = C.c_uint64
+    lib.so_modswitch_coeff.argtypes = [C.c_uint64, C.c_uint64]
+    lib.so_modswitch_coeff_x87.restype = C.c_uint64
+    lib.so_modswitch_coeff_x87.argtypes = [C.c_uint64, C.c_uint64]
+    lib.so_modswitch.argtypes = [u64p, u64p, sz, C.c_uint32]
+    lib.so_packed_words.restype = sz
+    lib.so_packed_words.argtypes = [sz, C.c_uint32]
+    lib.so_read_arbitrary_bits.restype = C.c_uint64
+    lib.so_read_arbitrary_bits.argtypes = [u64p, sz, sz]
     lib.so_client_new.restype = C.c_void_p
     lib.so_client_new.argtypes = [C.POINTER(SoParams), C.c_uint64, C.c_int]
     lib.so_client_free.argtypes = [C.c_void_p]

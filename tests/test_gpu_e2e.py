@@ -171,3 +171,29 @@ def test_batched_scan_equals_individual_scans(sb, count):
     assert len({c.tobytes() for c in single}) == count, "the queries must differ for the test to mean anything"
     for s_ in reversed(servers):
         s_.close()
+
+
+def test_packed_response_wire_format(sb, oracle):
+    """sb200_server_answer_packed: the modulus-switched response bit-packed on the device (row 0 at QPBITS bits, rows 1-2
+    at log2(4p) bits - the size print_summary reports, src/spiral.cpp:229-232); unpacking it gives the raw response."""
+    s = ol.SpiralSession(oracle, "cfg1", 4, 2, seed=21)
+    srv = SpiralServer(sb_params(s.prm))
+    srv.load_db_items(s.pts.astype(np.uint16))
+    srv.set_public_params(s.W_left, s.W_right, s.W_conv, s.V_conv)
+    q = s.query(17)
+    raw = srv.answer(q)
+    nbytes = sb.sb200_server_packed_response_bytes(srv.h)
+    N = ol.N
+    assert nbytes == (2 * N * s.prm.qp_bits + 4 * N * 10) // 8 == 20480
+    packed = np.zeros(nbytes // 8, dtype=np.uint64)
+    assert sb.sb200_server_answer_packed(srv.h, q.ctypes.data, packed.ctypes.data, None) == 0, sb.sb200_last_error()
+    back = np.zeros(6 * N, dtype=np.uint64)
+    P64 = C.POINTER(C.c_uint64)
+    assert sb.sb200_unpack_response(back.ctypes.data_as(P64), packed.ctypes.data_as(P64), 2 * N, 4 * N, s.prm.qp_bits, s.prm.p_db) == 0
+    assert np.array_equal(back, raw)
+    assert np.array_equal(s.decode(back), s.pts[17])
+    # the packing agrees with the reference's own bit writer (oracle restatement of write_arbitrary_bits)
+    for k in (0, 1, 63, 64, 2 * N - 1):
+        assert oracle.so_read_arbitrary_bits(ol.ptr(packed), k * s.prm.qp_bits, s.prm.qp_bits) == raw[k]
+    srv.close()
+    s.close()

@@ -1,5 +1,5 @@
 """GPU suite: the CUDA path, called through the C-ABI with the reference's host layouts, against the
-oracle on the same seeded inputs (the 25 parity cases that are pinned to the reference itself).
+oracle on the same seeded inputs (the 26 parity cases that are pinned to the reference itself).
 Bar: bit-exact.  Raw-domain buffers are compared exactly; NTT-domain buffers are compared after
 reducing both sides modulo the prime (the reference's own NTT may emit q for 0)."""
 import ctypes as C
@@ -81,6 +81,8 @@ def run_case(sb, case, prm):
         ok(sb, sb.sb200_regevToSimpleGsw(p(out), p(i[0]), 4 * prm.t_gsw + 2, p(i[1]), prm.t_conv, prm.t_gsw, 2, 2, 1))
     elif name == "pack":
         ok(sb, sb.sb200_pack(p(out), prm.out_n, prm.t_conv, p(i[0]), p(i[1])))
+    elif name == "modswitch":
+        ok(sb, sb.sb200_modswitch(p(out), p(i[0]), prm.qp_bits))
     else:
         return None
     return out
@@ -89,7 +91,7 @@ def run_case(sb, case, prm):
 SPIRAL_CASES = ["ntt_forward", "ntt_inverse", "to_ntt", "to_ntt_no_reduce", "from_ntt", "multiply", "automorph",
                 "gadget_invert", "rescale", "reorient_ciphertexts", "first_dim", "ntt_inv_crt_lift", "split_and_crt",
                 "fold_one", "expand_full", "expand_stopround", "scal_to_mat", "regev_to_gsw", "load_db",
-                "convert_db", "reorient_dim1", "first_dim_pack", "fold_dim1", "regev_to_simple_gsw", "pack"]
+                "convert_db", "reorient_dim1", "first_dim_pack", "fold_dim1", "regev_to_simple_gsw", "pack", "modswitch"]
 
 
 def test_every_golden_case_is_dispatched(oracle):
