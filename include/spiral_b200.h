@@ -213,6 +213,8 @@ int sb200_pack_server_upload_query(sb200_pack_server *srv, const uint64_t *query
 int sb200_pack_server_expand_and_convert(sb200_pack_server *srv, void *stream);   /* coefficientExpansion + reorientCiphertextsDim1 + regevToSimpleGsw */
 int sb200_pack_server_upload_direct(sb200_pack_server *srv, const uint64_t *v_firstdim_host, const uint64_t *v_folding_host, void *stream);
 int sb200_pack_server_scan(sb200_pack_server *srv, void *stream);                 /* fastMultiplyQueryByDatabaseDim1, all planes (src/testing.cpp:364) */
+/* interposed fastMultiplyQueryByDatabaseDim1 against ONE resident plane: host reoriented query in, ref-NTT host cts out */
+int sb200_pack_server_scan_plane_host(sb200_pack_server *srv, size_t plane, const uint64_t *v_firstdim_host, uint64_t *out_ref_ntt_host);
 int sb200_pack_server_fold_local(sb200_pack_server *srv, void *stream);           /* from_ntt + local fold rounds: out_n^2 surviving cts */
 uint64_t *sb200_pack_server_partial_cts(sb200_pack_server *srv);                  /* device ptr: [plane] 2x1 raw cts of this shard */
 size_t sb200_pack_server_partial_words(const sb200_pack_server *srv);

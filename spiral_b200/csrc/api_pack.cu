@@ -324,6 +324,15 @@ extern "C" int sb200_pack_server_scan(sb200_pack_server *s, void *stream) {
     CHECK_LAUNCH();
     return SB200_OK;
 }
+// interposed fastMultiplyQueryByDatabaseDim1 on ONE resident plane: host reoriented query in, ref-NTT host ciphertexts out
+extern "C" int sb200_pack_server_scan_plane_host(sb200_pack_server *s, size_t plane, const uint64_t *v_firstdim_host, uint64_t *out_ref_ntt_host) {
+    if (!s || !v_firstdim_host || !out_ref_ntt_host || plane >= s->planes) return fail(SB200_ERR_ARG, "pack scan_plane_host: bad argument");
+    if (!s->plane_loaded[plane]) return fail(SB200_ERR_STATE, "pack scan_plane_host: database plane %zu not loaded", plane);
+    CU(cudaMemcpy(s->query.p, v_firstdim_host, s->dim0 * 2 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    launch_scan_pack(s->scan_out.p, s->query.p, s->db.p + plane * s->plane_words, s->dim0, s->local_num_per, 1, s->plane_words, s->local_num_per * 2, 0);
+    CHECK_LAUNCH();
+    return down_ntt(out_ref_ntt_host, s->scan_out.p, s->local_num_per * 2);
+}
 static void pack_fold_rounds(sb200_pack_server *s, uint64_t *cts, size_t count, size_t plane_stride, size_t first_round, cudaStream_t st) {
     const size_t ell = s->prm.t_gsw, fd = s->prm.nu2, gsw_polys = 2 * 2 * ell;
     size_t np = count, cur = first_round;

@@ -161,6 +161,200 @@ void regevToGSW(size_t m_conv, size_t t, MatPoly &out, const std::vector<MatPoly
     memcpy(out.data, res.data(), res.size() * 8);
 }
 
+// ---- scalToMat (src/spiral.cpp:1850, the 14-argument form runConversionImproved calls at :2231; the scratch
+// matrices are the reference's own working storage and are left untouched)
+void scalToMat(size_t m_conv, MatPoly &out_reg, const MatPoly &cv, const MatPoly &W, MatPoly &cv_0, MatPoly &cv_1, MatPoly &cv_ntti,
+               MatPoly &square_cv, MatPoly &ginv_c, MatPoly &ginv_c_nttd, MatPoly &prod_W_ginv, MatPoly &padded_cv_1,
+               MatPoly &ginv_c_raw, MatPoly &ginv_c_raw_nttd) {
+    OKAY(sb200_scalToMat(out_reg.data, cv.data, W.data, (uint32_t)m_conv));
+    if (parity_mode()) {
+        static int shown = 0;
+        MatPoly ref(3, 2);
+        next_sym<void (*)(size_t, MatPoly &, const MatPoly &, const MatPoly &, MatPoly &, MatPoly &, MatPoly &, MatPoly &, MatPoly &, MatPoly &,
+                          MatPoly &, MatPoly &, MatPoly &, MatPoly &)>("_Z9scalToMatmR7MatPolyRKS_S2_S0_S0_S0_S0_S0_S0_S0_S0_S0_S0_")(
+            m_conv, ref, cv, W, cv_0, cv_1, cv_ntti, square_cv, ginv_c, ginv_c_nttd, prod_W_ginv, padded_cv_1, ginv_c_raw, ginv_c_raw_nttd);
+        for (size_t i = 0; i < 6 * PL; i++) {
+            const uint64_t q = ((i / N) & 1) ? Bq : P;
+            if (out_reg.data[i] % q != ref.data[i] % q) { fprintf(stderr, "[spiral_b200] PARITY FAIL scalToMat word %zu\n", i); abort(); }
+        }
+        if (!shown++) fprintf(stderr, "[spiral_b200] parity ok: scalToMat (6 polys, mod q; every call is checked)\n");
+        free(ref.data);
+    }
+}
+
+// ---- modswitch (src/spiral.cpp:40): the QPBITS-bit response packer
+void modswitch(uint64_t *out, const uint64_t *inp) {
+    OKAY(sb200_modswitch(out, inp, QPBITS));
+    if (parity_mode()) {
+        const size_t words = sb200_packed_words(3 * 2 * N, QPBITS);
+        std::vector<uint64_t> ref(words + 1, 0);
+        next_sym<void (*)(uint64_t *, const uint64_t *)>("_Z9modswitchPmPKm")(ref.data(), inp);
+        cmp_raw("modswitch", out, ref.data(), words);
+    }
+}
+
+// ---- getRescaled (src/poly.cpp:593): modulus switch of the response
+MatPoly getRescaled(const MatPoly &a, uint64_t inp_mod, uint64_t out_mod) {
+    // the reference's `MatPoly b = a;` is a SHALLOW copy (implicit copy constructor): it rescales a's storage in place and
+    // returns a matrix sharing it - reproduced, since callers may rely on either name
+    const size_t n = a.rows * a.cols * N;
+    std::vector<uint64_t> in(a.data, a.data + n);
+    MatPoly b = a;
+    OKAY(sb200_getRescaled(b.data, in.data(), n, inp_mod, out_mod));
+    if (parity_mode()) {
+        MatPoly a2(a.rows, a.cols, false);
+        memcpy(a2.data, in.data(), n * 8);
+        MatPoly ref = next_sym<MatPoly (*)(const MatPoly &, uint64_t, uint64_t)>("_Z11getRescaledRK7MatPolymm")(a2, inp_mod, out_mod);
+        cmp_raw("getRescaled", b.data, ref.data, n);
+        free(a2.data);
+    }
+    return b;
+}
+
+// =================================================================================================
+// SpiralPack / SpiralStreamPack leaves (src/testing.cpp), driven by testHighRate (`--high-rate`)
+// =================================================================================================
+#ifndef OUTN
+#define OUTN 4
+#endif
+static sb200_pack_server *g_pack = nullptr;                 // resident planes, in convertDb call order
+static std::vector<const uint64_t *> g_plane_bufs;          // the db_buf pointers convertDb returned
+
+// ---- convertDb (src/testing.cpp:316): relayout on the GPU; the plane also becomes resident in HBM
+uint64_t *convertDb(const std::vector<MatPoly> &db, size_t dim0, size_t num_per) {
+    const size_t count = db.size();
+    std::vector<uint64_t> flat = flatten(db, count);
+    uint64_t *buf = (uint64_t *)malloc(count * N * sizeof(uint64_t));
+    OKAY(sb200_convertDb(buf, flat.data(), count, dim0, num_per));
+    if (parity_mode()) {
+        uint64_t *ref = next_sym<uint64_t *(*)(const std::vector<MatPoly> &, size_t, size_t)>("_Z9convertDbRKSt6vectorI7MatPolySaIS0_EEmm")(db, dim0, num_per);
+        cmp_packed("convertDb", buf, ref, count * N);
+        free(ref);
+    }
+    if (!g_pack) {
+        sb200_params prm = {};
+        prm.nu1 = (uint32_t)num_expansions; prm.nu2 = (uint32_t)further_dims;
+        prm.t_gsw = TGSW; prm.t_conv = TCONV; prm.t_exp = TEXP; prm.t_exp_right = TEXPRIGHT;
+        prm.qp_bits = QPBITS; prm.out_n = OUTN; prm.p_db = PVALUE;
+        if (((size_t)1 << prm.nu1) == dim0 && ((size_t)1 << prm.nu2) == num_per) OKAY(sb200_pack_server_create(&g_pack, &prm, 0));
+    }
+    if (g_pack && g_plane_bufs.size() < (size_t)OUTN * OUTN) {
+        OKAY(sb200_pack_server_load_plane_reference(g_pack, g_plane_bufs.size(), buf));
+        g_plane_bufs.push_back(buf);
+        fprintf(stderr, "[spiral_b200] database plane %zu resident on the GPU (%zu MiB)\n", g_plane_bufs.size() - 1, (count * N * 8) >> 20);
+    }
+    return buf;
+}
+
+// ---- coefficientExpansion (src/testing.cpp:40): same body as expandImproved, no return value
+void coefficientExpansion(std::vector<MatPoly> &cv_v, size_t g, size_t m_exp, const std::vector<MatPoly> &W_left_v,
+                          const std::vector<MatPoly> &W_right_v, size_t max_bits_to_gen_right, size_t stopround) {
+    const size_t ncts = (size_t)1 << g;
+    size_t n_right = stopround > 0 ? stopround + 1 : g;
+    if (n_right > W_right_v.size()) n_right = W_right_v.size();
+    std::vector<uint64_t> cv = flatten(cv_v, ncts), Wl = flatten(W_left_v, g), Wr = flatten(W_right_v, n_right);
+    std::vector<MatPoly> ref_cv;
+    if (parity_mode()) for (size_t i = 0; i < ncts; i++) { MatPoly c(2, 1); memcpy(c.data, cv_v[i].data, 2 * PL * 8); ref_cv.push_back(c); }
+    OKAY(sb200_expandImproved(cv.data(), g, (uint32_t)m_exp, Wl.data(), Wr.data(), (uint32_t)W_right_v[0].cols, max_bits_to_gen_right, stopround));
+    for (size_t i = 0; i < ncts; i++) memcpy(cv_v[i].data, &cv[i * 2 * PL], 2 * PL * 8);
+    if (parity_mode()) {
+        next_sym<void (*)(std::vector<MatPoly> &, size_t, size_t, const std::vector<MatPoly> &, const std::vector<MatPoly> &, size_t, size_t)>(
+            "_Z20coefficientExpansionRSt6vectorI7MatPolySaIS0_EEmmRKS2_S5_mm")(ref_cv, g, m_exp, W_left_v, W_right_v, max_bits_to_gen_right, stopround);
+        std::vector<uint64_t> ref = flatten(ref_cv, ncts);
+        cmp_ntt("coefficientExpansion", cv.data(), ref.data(), ncts * 2);
+        for (auto &m : ref_cv) free(m.data);
+    }
+}
+
+// ---- reorientCiphertextsDim1 (src/testing.cpp:342)
+void reorientCiphertextsDim1(uint64_t *out, const std::vector<MatPoly> &v_firstdim, size_t dim0, size_t idx_factor) {
+    const size_t count = v_firstdim.size();
+    std::vector<uint64_t> flat = flatten(v_firstdim, count);
+    OKAY(sb200_reorientCiphertextsDim1(out, flat.data(), count, dim0, idx_factor));
+    if (parity_mode()) {
+        std::vector<uint64_t> ref(dim0 * 2 * N, 0);
+        next_sym<void (*)(uint64_t *, const std::vector<MatPoly> &, size_t, size_t)>("_Z23reorientCiphertextsDim1PmRKSt6vectorI7MatPolySaIS1_EEmm")(ref.data(), v_firstdim, dim0, idx_factor);
+        cmp_packed("reorientCiphertextsDim1", out, ref.data(), ref.size());
+    }
+}
+
+// ---- regevToSimpleGsw (src/testing.cpp:108): appends further_dims GSW ciphertexts (2 x 2*ell) to v_gsw
+void regevToSimpleGsw(std::vector<MatPoly> &v_gsw, const std::vector<MatPoly> &v_inp, const MatPoly &V, size_t m_conv, size_t ell,
+                      size_t fdims, size_t idx_factor, size_t idx_offset) {
+    const size_t count = v_inp.size(), per = 2 * 2 * ell;
+    std::vector<uint64_t> flat = flatten(v_inp, count), res(fdims * per * PL);
+    OKAY(sb200_regevToSimpleGsw(res.data(), flat.data(), count, V.data, (uint32_t)m_conv, (uint32_t)ell, (uint32_t)fdims, idx_factor, idx_offset));
+    if (parity_mode()) {
+        std::vector<MatPoly> ref;
+        next_sym<void (*)(std::vector<MatPoly> &, const std::vector<MatPoly> &, const MatPoly &, size_t, size_t, size_t, size_t, size_t)>(
+            "_Z16regevToSimpleGswRSt6vectorI7MatPolySaIS0_EERKS2_RKS0_mmmmm")(ref, v_inp, V, m_conv, ell, fdims, idx_factor, idx_offset);
+        std::vector<uint64_t> rf = flatten(ref, fdims);
+        cmp_ntt("regevToSimpleGsw", res.data(), rf.data(), fdims * per);
+        for (auto &m : ref) free(m.data);
+    }
+    for (size_t d = 0; d < fdims; d++) {
+        MatPoly ct(2, 2 * ell);
+        memcpy(ct.data, &res[d * per * PL], per * PL * 8);
+        v_gsw.push_back(ct);
+    }
+}
+
+// ---- fastMultiplyQueryByDatabaseDim1 (src/testing.cpp:364): scan of the RESIDENT plane when `db` is a buffer convertDb
+// returned, otherwise the stateless call
+void fastMultiplyQueryByDatabaseDim1(std::vector<MatPoly> &out, const uint64_t *db, const uint64_t *v_firstdim, size_t dim0, size_t num_per) {
+    std::vector<uint64_t> res(num_per * 2 * PL);
+    size_t plane = g_plane_bufs.size();
+    for (size_t k = 0; k < g_plane_bufs.size(); k++) if (g_plane_bufs[k] == db) plane = k;
+    if (g_pack && plane < g_plane_bufs.size()) OKAY(sb200_pack_server_scan_plane_host(g_pack, plane, v_firstdim, res.data()));
+    else OKAY(sb200_fastMultiplyQueryByDatabaseDim1(res.data(), db, v_firstdim, dim0, num_per));
+    if (parity_mode()) {
+        std::vector<MatPoly> ref;
+        for (size_t i = 0; i < num_per; i++) ref.emplace_back(2, 1);
+        next_sym<void (*)(std::vector<MatPoly> &, const uint64_t *, const uint64_t *, size_t, size_t)>(
+            "_Z31fastMultiplyQueryByDatabaseDim1RSt6vectorI7MatPolySaIS0_EEPKmS5_mm")(ref, db, v_firstdim, dim0, num_per);
+        std::vector<uint64_t> rf = flatten(ref, num_per);
+        cmp_ntt("fastMultiplyQueryByDatabaseDim1", res.data(), rf.data(), num_per * 2);
+        for (auto &m : ref) free(m.data);
+    }
+    for (size_t i = 0; i < num_per; i++) memcpy(out[i].data, &res[i * 2 * PL], 2 * PL * 8);
+}
+
+// ---- foldCiphertextsDim1 (src/testing.cpp:596): result left in v_cts[0]
+void foldCiphertextsDim1(std::vector<MatPoly> &v_cts, const std::vector<MatPoly> &v_folding, const std::vector<MatPoly> &v_folding_neg) {
+    const size_t count = v_cts.size(), fd = v_folding.size();
+    if (fd == 0) return;
+    const uint32_t ell = (uint32_t)(v_folding[0].cols / 2);
+    std::vector<uint64_t> cts = flatten(v_cts, count), f = flatten(v_folding, fd), fn = flatten(v_folding_neg, fd);
+    std::vector<MatPoly> ref_cts;
+    if (parity_mode()) for (size_t i = 0; i < count; i++) { MatPoly c(2, 1, false); memcpy(c.data, v_cts[i].data, 2 * N * 8); ref_cts.push_back(c); }
+    OKAY(sb200_foldCiphertextsDim1(cts.data(), count, f.data(), fn.data(), ell));
+    memcpy(v_cts[0].data, cts.data(), 2 * N * 8);
+    if (parity_mode()) {
+        next_sym<void (*)(std::vector<MatPoly> &, const std::vector<MatPoly> &, const std::vector<MatPoly> &)>(
+            "_Z19foldCiphertextsDim1RSt6vectorI7MatPolySaIS0_EERKS2_S5_")(ref_cts, v_folding, v_folding_neg);
+        cmp_raw("foldCiphertextsDim1", v_cts[0].data, ref_cts[0].data, 2 * N);
+        for (auto &m : ref_cts) free(m.data);
+    }
+}
+
+// ---- pack (src/testing.cpp:198)
+void pack(MatPoly &result, size_t out_n, size_t m_conv, const std::vector<MatPoly> &v_ct, const std::vector<MatPoly> &v_W) {
+    std::vector<uint64_t> cts = flatten(v_ct, out_n * out_n), W = flatten(v_W, out_n);
+    OKAY(sb200_pack(result.data, (uint32_t)out_n, (uint32_t)m_conv, cts.data(), W.data()));
+    if (parity_mode()) {
+        MatPoly ref(out_n + 1, out_n);
+        next_sym<void (*)(MatPoly &, size_t, size_t, const std::vector<MatPoly> &, const std::vector<MatPoly> &)>(
+            "_Z4packR7MatPolymmRKSt6vectorIS_SaIS_EES5_")(ref, out_n, m_conv, v_ct, v_W);
+        cmp_ntt("pack", result.data, ref.data, (out_n + 1) * out_n);
+        free(ref.data);
+    }
+}
+
+static void report_at_exit() {          // testHighRate ends in exit(0) (src/spiral.cpp:1337-1340): report from an atexit handler
+    fflush(stdout);
+    fprintf(stderr, "[spiral_b200] %llu CUDA kernel launches\n", (unsigned long long)sb200_launch_count());
+}
+
 // ---- driver entry: run the reference's own main (client + harness) with the definitions above bound
 int main(int argc, char **argv) {
     typedef int (*main_fn)(int, char **);
@@ -168,8 +362,7 @@ int main(int argc, char **argv) {
     if (!ref_main) { fprintf(stderr, "reference main not found: %s\n", dlerror()); return 3; }
     if (sb200_init(0) != 0) { fprintf(stderr, "[spiral_b200] %s\n", sb200_last_error()); return 4; }
     fprintf(stderr, "[spiral_b200] driving the reference harness with the CUDA server path%s\n", parity_mode() ? " (parity mode)" : "");
+    atexit(report_at_exit);
     ref_main(argc, argv);
-    fflush(stdout);
-    fprintf(stderr, "[spiral_b200] %llu CUDA kernel launches\n", (unsigned long long)sb200_launch_count());
     return 0;
 }

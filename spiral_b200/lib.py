@@ -120,6 +120,7 @@ def load_library():
         "sb200_pack_server_upload_direct": (C.c_int, [vp, vp, vp, vp]),
         "sb200_pack_server_scan": (C.c_int, [vp, vp]),
         "sb200_pack_server_fold_local": (C.c_int, [vp, vp]),
+        "sb200_pack_server_scan_plane_host": (C.c_int, [vp, sz, u64p, u64p]),
         "sb200_pack_server_partial_cts": (vp, [vp]),
         "sb200_pack_server_partial_words": (sz, [vp]),
         "sb200_pack_server_copy_partial": (C.c_int, [vp, vp, vp]),

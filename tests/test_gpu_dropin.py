@@ -28,7 +28,33 @@ def test_reference_harness_with_cuda_server(cfg, args):
     assert out.returncode == 0, out.stderr[-2000:]
     assert "Is correct?: 1" in out.stdout, out.stdout[-2000:]
     for leaf in ("reorientCiphertexts", "multiplyQueryByDatabase", "nttInvAndCrtLiftCiphertexts", "foldOneFurtherDimension",
-                 "expandImproved", "regevToGSW"):
+                 "expandImproved", "regevToGSW", "scalToMat", "modswitch", "getRescaled"):
         assert f"parity ok: {leaf}" in out.stderr, f"{leaf} was not exercised:\n{out.stderr[-2000:]}"
     assert "PARITY FAIL" not in out.stderr
     assert "database resident on the GPU" in out.stderr
+
+
+@pytest.mark.parametrize("cfg,args,leaves", [
+    ("cfg3", ["5", "2", "77", "a", "--high-rate"],
+     ("convertDb", "coefficientExpansion", "reorientCiphertextsDim1", "regevToSimpleGsw", "fastMultiplyQueryByDatabaseDim1",
+      "foldCiphertextsDim1", "pack", "getRescaled")),
+    ("cfg4", ["6", "3", "100", "a", "--high-rate", "--direct-upload"],
+     ("convertDb", "fastMultiplyQueryByDatabaseDim1", "foldCiphertextsDim1", "pack", "getRescaled")),
+    ("cfg1", ["6", "2", "9", "a", "--high-rate"],
+     ("convertDb", "coefficientExpansion", "regevToSimpleGsw", "fastMultiplyQueryByDatabaseDim1", "foldCiphertextsDim1", "pack")),
+])
+def test_reference_pack_harness_with_cuda_server(cfg, args, leaves):
+    """SpiralPack / SpiralStreamPack: the reference's testHighRate (src/testing.cpp:777) drives the CUDA path through
+    host_mirror.cpp's definitions of its own leaf functions; the planes convertDb produced stay resident in HBM."""
+    exe = _driver(cfg)
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt reference driver not present (built only where /root/reference exists)")
+    env = dict(os.environ, SB200_PARITY="1")
+    out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Is correct? : 1" in out.stdout, out.stdout[-2000:]
+    for leaf in leaves:
+        assert f"parity ok: {leaf}" in out.stderr, f"{leaf} was not exercised:\n{out.stderr[-2000:]}"
+    assert "PARITY FAIL" not in out.stderr
+    assert "resident on the GPU" in out.stderr
+    assert "CUDA kernel launches" in out.stderr
