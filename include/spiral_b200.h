@@ -90,6 +90,15 @@ int sb200_dev_db_from_reference(uint64_t *db, const uint64_t *B_chunk, size_t di
 size_t sb200_db_words(uint32_t nu1, uint32_t nu2);       /* uint64 words of the scan-layout database */
 int sb200_dev_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, void *stream);   /* src/spiral.cpp:410-433 */
 int sb200_dev_first_dim(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, void *stream); /* src/spiral.cpp:628-999 */
+/* batched first dimension on the tcgen05 tensor cores: multiplyQueryByDatabase (src/spiral.cpp:628-999) for up
+   to 16 queries in ONE database pass.  db_tc: limb-tile copy of the scan-layout database (same byte count); q_tc: the batch's
+   query tiles (sb200_tc_query_bytes, zero-initialised by the caller); out[q]: as sb200_dev_first_dim. */
+int sb200_tc_supported(size_t dim0, size_t num_per);      /* 2*dim0 and 2*num_per must be multiples of 128 */
+size_t sb200_tc_query_bytes(size_t dim0, int capacity);
+int sb200_dev_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, void *stream);
+int sb200_dev_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, void *stream);
+int sb200_dev_first_dim_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc,
+                           size_t dim0, size_t num_per, void *stream);
 size_t sb200_fold_scratch_words(size_t num_per_after, uint32_t t_gsw);   /* uint32 words */
 int sb200_dev_fold_round(uint64_t *cts, size_t num_per_after, const uint32_t *q, const uint32_t *q_neg,
                          uint32_t t_gsw, uint32_t *scratch, void *stream);                      /* src/spiral.cpp:1349-1410 */
@@ -110,6 +119,9 @@ int sb200_load_db(uint64_t *B_ref_layout, const uint64_t *pts, uint32_t nu1, uin
 int sb200_reorientCiphertexts(uint64_t *out, const uint64_t *inp_ref_ntt, size_t dim0, size_t n1_padded);
 int sb200_multiplyQueryByDatabase(uint64_t *out_ref_ntt, const uint64_t *reoriented, const uint64_t *database,
                                   size_t dim0, size_t num_per);
+/* the same for `count` (<= 16) reoriented queries against one database in ONE tensor-core pass (sb200_dev_first_dim_tc) */
+int sb200_multiplyQueryByDatabase_batched(uint64_t *const *out_ref_ntt, const uint64_t *const *reoriented, int count,
+                                          const uint64_t *database, size_t dim0, size_t num_per);
 int sb200_nttInvAndCrtLiftCiphertexts(uint64_t *cts_raw, const uint64_t *scratch_ref_ntt, size_t num_per);
 int sb200_split_and_crt(uint64_t *out_ref_ntt, const uint64_t *in_raw, size_t num_per, uint32_t t_gsw);   /* src/spiral.cpp:270-341 */
 /* q / q_neg: the reference's reoriented GSW buffers (reorient_Q layout, stride n1*m2*2*2048 words per dimension) */
@@ -162,6 +174,10 @@ int sb200_server_first_dim(sb200_server *srv, void *stream);               /* sc
 int sb200_server_scan(sb200_server *srv, void *stream);                    /* multiplyQueryByDatabase only (src/spiral.cpp:628) */
 /* batched first dimension: `count` (2 or 4) servers sharing one database answered in ONE database pass */
 int sb200_server_scan_batched(sb200_server *const *servers, int count, void *stream);
+/* tensor-core variant: build the limb-tile database copy once (database owner; capacity <= 16 queries per pass) ... */
+int sb200_server_enable_tc(sb200_server *srv, int capacity);
+/* ... then answer the first dimension of up to `capacity` servers sharing that database with one tcgen05 pass */
+int sb200_server_scan_batched_tc(sb200_server *const *servers, int count, void *stream);
 int sb200_server_lift(sb200_server *srv, void *stream);                    /* nttInvAndCrtLiftCiphertexts only (src/spiral.cpp:437) */
 /* interposed multiplyQueryByDatabase: host reoriented query in, ref-NTT host ciphertexts out, database stays resident */
 int sb200_server_scan_host(sb200_server *srv, const uint64_t *reoriented_host, uint64_t *out_ref_ntt_host);

@@ -124,6 +124,28 @@ extern "C" int sb200_dev_first_dim(uint32_t *out, const uint64_t *query, const u
     if (!dim0 || !num_per || (dim0 & (dim0 - 1)) || (num_per & (num_per - 1))) return fail(SB200_ERR_ARG, "first_dim: dim0 and num_per must be powers of two");
     launch_scan_spiral(out, query, db, dim0, num_per, S(stream)); CHECK_LAUNCH(); return SB200_OK;
 }
+// ---- batched first dimension on tensor cores (tc_scan.cu)
+extern "C" int sb200_tc_supported(size_t dim0, size_t num_per) { return tc_shape_ok(dim0, num_per); }
+extern "C" size_t sb200_tc_query_bytes(size_t dim0, int capacity) { return tc_query_bytes(dim0, capacity); }
+extern "C" int sb200_dev_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, void *stream) {
+    NEED_DEVICE();
+    if (!db_tc || !db || !tc_shape_ok(dim0, num_per)) return fail(SB200_ERR_ARG, "db_to_tc: needs 2*dim0 and 2*num_per to be multiples of 128");
+    launch_db_to_tc(db_tc, db, dim0, num_per, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, void *stream) {
+    NEED_DEVICE();
+    if (!q_tc || !query || q < 0 || q >= capacity || capacity > 16 || (dim0 * 2) % 128) return fail(SB200_ERR_ARG, "query_to_tc: bad slot, capacity or dim0");
+    launch_query_to_tc(q_tc, query, q, capacity, dim0, S(stream)); CHECK_LAUNCH(); return SB200_OK;
+}
+extern "C" int sb200_dev_first_dim_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc,
+                                      size_t dim0, size_t num_per, void *stream) {
+    NEED_DEVICE();
+    if (!out || !q_tc || !db_tc) return fail(SB200_ERR_ARG, "first_dim_tc: null argument");
+    const int rc = launch_scan_tc(out, count, capacity, q_tc, db_tc, dim0, num_per, S(stream));
+    if (rc == -1) return fail(SB200_ERR_ARG, "first_dim_tc: needs 1 <= count <= capacity <= 16, 2*dim0 and 2*num_per multiples of 128");
+    if (rc) return fail(SB200_ERR_CUDA, "first_dim_tc: cannot reserve %zu bytes of shared memory", (size_t)0);
+    CHECK_LAUNCH(); return SB200_OK;
+}
 extern "C" size_t sb200_fold_scratch_words(size_t num_per_after, uint32_t t_gsw) { return fold_scratch_words(num_per_after, (int)t_gsw); }
 extern "C" int sb200_dev_fold_round(uint64_t *cts, size_t num_per_after, const uint32_t *q, const uint32_t *q_neg,
                                     uint32_t t_gsw, uint32_t *scratch, void *stream) {
@@ -318,6 +340,31 @@ extern "C" int sb200_multiplyQueryByDatabase(uint64_t *out, const uint64_t *reor
     launch_scan_spiral(dout.p, dq.p, ddb.p, dim0, num_per, 0); CHECK_LAUNCH();
     return down_ntt(out, dout.p, opolys);
 }
+// `count` reoriented queries against one database in ONE pass (tensor-core path); outputs as multiplyQueryByDatabase's
+extern "C" int sb200_multiplyQueryByDatabase_batched(uint64_t *const *out, const uint64_t *const *reoriented, int count,
+                                                     const uint64_t *database, size_t dim0, size_t num_per) {
+    NEED_DEVICE();
+    if (!out || !reoriented || count < 1 || count > 16) return fail(SB200_ERR_ARG, "multiplyQueryByDatabase_batched: 1 <= count <= 16");
+    if (!tc_shape_ok(dim0, num_per)) return fail(SB200_ERR_ARG, "multiplyQueryByDatabase_batched: needs 2*dim0 and 2*num_per to be multiples of 128");
+    const size_t qwords = dim0 * 2 * 4 * kN, dbwords = dim0 * num_per * 4 * kN, opolys = num_per * 6;
+    DBuf<uint64_t> dq(qwords), dref(dbwords), ddb(dbwords); DBuf<uint8_t> dtc(dbwords * 8), qtc(tc_query_bytes(dim0, count));
+    DBuf<uint32_t> dout((size_t)count * opolys * PLW);
+    CU(dref.up(database, dbwords));
+    launch_db_from_reference(ddb.p, dref.p, dim0, num_per * kN2, 0, kN, 0); CHECK_LAUNCH();
+    launch_db_to_tc(dtc.p, ddb.p, dim0, num_per, 0); CHECK_LAUNCH();
+    CU(cudaMemset(qtc.p, 0, qtc.n));
+    uint32_t *o[16];
+    for (int b = 0; b < count; b++) {
+        CU(dq.up(reoriented[b], qwords));
+        launch_query_to_tc(qtc.p, dq.p, b, count, dim0, 0); CHECK_LAUNCH();
+        CU(cudaDeviceSynchronize());
+        o[b] = dout.p + (size_t)b * opolys * PLW;
+    }
+    if (launch_scan_tc(o, count, count, qtc.p, dtc.p, dim0, num_per, 0)) return fail(SB200_ERR_CUDA, "multiplyQueryByDatabase_batched: launch failed");
+    CHECK_LAUNCH();
+    for (int b = 0; b < count; b++) TRY(down_ntt(out[b], o[b], opolys));
+    return SB200_OK;
+}
 extern "C" int sb200_nttInvAndCrtLiftCiphertexts(uint64_t *cts_raw, const uint64_t *scratch, size_t num_per) {
     return sb200_from_ntt(cts_raw, scratch, num_per * 6);
 }
@@ -448,6 +495,8 @@ struct sb200_server {
     const sb200_server *db_owner = nullptr;           // views (sb200_server_create_view) scan another server's resident database
     // device memory
     DBuf<uint64_t> db;                                  // scan layout shard
+    DBuf<uint8_t> db_tc, q_tc;                          // tensor-core path (sb200_server_enable_tc): limb-tile database, batched query tiles
+    int tc_capacity = 0;
     DBuf<uint32_t> W_left, W_right, W_conv, V_conv, neg1;
     DBuf<uint64_t> q_stage;                             // uploaded query (ref-NTT)
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch;
@@ -682,6 +731,47 @@ extern "C" int sb200_server_scan_batched(sb200_server *const *servers, int count
     }
     if (launch_scan_spiral_batched(o, q, count, server_db(s0), s0->dim0, s0->local_num_per, ES(s0, stream)) != 0)
         return fail(SB200_ERR_ARG, "scan_batched: needs 2 * num_per to be a multiple of 128");
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+// Tensor-core batched first dimension: build the limb-tile copy of the resident database (owner only) for batches of up
+// to `capacity` (<= 16) queries.  Costs a second database-sized allocation.
+extern "C" int sb200_server_enable_tc(sb200_server *s, int capacity) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "enable_tc: call it on the server that owns the database");
+    if (!s->have_db) return fail(SB200_ERR_STATE, "enable_tc: database not loaded");
+    if (capacity < 1 || capacity > 16) return fail(SB200_ERR_ARG, "enable_tc: capacity must be in [1, 16]");
+    if (!tc_shape_ok(s->dim0, s->local_num_per)) return fail(SB200_ERR_ARG, "enable_tc: needs 2*dim0 and 2*num_per (per shard) to be multiples of 128");
+    CU(cudaSetDevice(s->device));
+    if (!s->db_tc.p) {
+        CU(s->db_tc.alloc(s->db.n * sizeof(uint64_t)));
+        launch_db_to_tc(s->db_tc.p, s->db.p, s->dim0, s->local_num_per, s->own_stream); CHECK_LAUNCH();
+    }
+    if (s->q_tc.p) { cudaFree(s->q_tc.p); s->q_tc.p = nullptr; }
+    CU(s->q_tc.alloc(tc_query_bytes(s->dim0, capacity)));
+    CU(cudaMemsetAsync(s->q_tc.p, 0, s->q_tc.n, s->own_stream));
+    CU(cudaStreamSynchronize(s->own_stream));
+    s->tc_capacity = capacity;
+    return SB200_OK;
+}
+// One tensor-core pass over the database for `count` (<= capacity) servers that share it: converts every server's
+// reoriented query into its rows of the batched tiles, then one k_scan_tc launch fills every server's scan output.
+extern "C" int sb200_server_scan_batched_tc(sb200_server *const *servers, int count, void *stream) {
+    if (!servers || count < 1) return fail(SB200_ERR_ARG, "scan_batched_tc: no servers");
+    sb200_server *s0 = servers[0];
+    if (!s0) return fail(SB200_ERR_ARG, "scan_batched_tc: null server");
+    sb200_server *owner = const_cast<sb200_server *>(s0->db_owner ? s0->db_owner : s0);
+    if (!owner->tc_capacity) return fail(SB200_ERR_STATE, "scan_batched_tc: call sb200_server_enable_tc on the database owner first");
+    if (count > owner->tc_capacity) return fail(SB200_ERR_ARG, "scan_batched_tc: %d queries exceed the enabled capacity %d", count, owner->tc_capacity);
+    uint32_t *o[16];
+    cudaStream_t st = ES(s0, stream);
+    for (int b = 0; b < count; b++) {
+        if (!servers[b] || server_db(servers[b]) != owner->db.p) return fail(SB200_ERR_ARG, "scan_batched_tc: servers must share one database");
+        launch_query_to_tc(owner->q_tc.p, servers[b]->query.p, b, owner->tc_capacity, owner->dim0, st);
+        o[b] = servers[b]->scan_out.p;
+    }
+    if (launch_scan_tc(o, count, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, owner->dim0, owner->local_num_per, st))
+        return fail(SB200_ERR_CUDA, "scan_batched_tc: launch failed");
     CHECK_LAUNCH();
     return SB200_OK;
 }

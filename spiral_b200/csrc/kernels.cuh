@@ -66,6 +66,14 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
 int launch_scan_spiral_batched(uint32_t *const *out, const uint64_t *const *query, int count, const uint64_t *db, size_t dim0,
                                size_t num_per, cudaStream_t s);   // count in {2,4}: queries sharing one database pass
 
+// ---- batched first dimension on tcgen05 tensor cores (tc_scan.cu): up to 16 queries per database pass
+int tc_shape_ok(size_t dim0, size_t num_per);                       // needs 2*dim0 % 128 == 0 and 2*num_per % 128 == 0
+size_t tc_query_bytes(size_t dim0, int capacity);                   // Q_tc bytes for a batch of up to `capacity` queries
+void launch_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s);   // scan layout -> DB_tc (same size)
+void launch_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, cudaStream_t s);
+int launch_scan_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, size_t dim0, size_t num_per,
+                   cudaStream_t s);
+
 // ---- folding (Spiral): cts raw [2*num_per][3][2][2048] -> first num_per folded in place.
 // q_dev / qneg_dev: dev-NTT (3 x 3*t_gsw) GSW ciphertext of THIS round.
 void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,

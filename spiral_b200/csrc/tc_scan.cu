@@ -1,0 +1,360 @@
+// tc_scan.cu - batched first dimension on the 5th-generation tensor cores (north_star "batched-query
+// variant ... dense contraction on int8-limb tcgen05 tiles").
+//
+// Same function as k_scan_spiral (multiplyQueryByDatabase, reference src/spiral.cpp:628-999), for up to 16 queries
+// that share ONE pass over the database:
+//     out_q[i][r][c][n][z] = sum_{k=(j,m)} query_q[z][k][r]_n * DB[z][k][ic]_n   mod prime_n        (ic = 2i + c)
+// For a fixed (z, n) this is a (IC x K) . (K x 3*BQ) integer matrix product with 28-bit operands.  Every residue is
+// split into four unsigned byte limbs (the bytes of the little-endian u32 the database already stores), the 16 limb
+// products run as exact u8 x u8 -> s32 tcgen05.mma (kind::i8) with accumulators in tensor memory, and the epilogue
+// recombines  sum_w 2^(8w) T_w  modulo the prime (T_w = sum of the limb products of weight w = a + b; < 2^28, exact).
+//
+// Layouts (chosen so that the copy engine, not threads, moves every byte):
+//   database  "DB_tc"  : for item it = (z, n, mt):  [kc][a][128 rows (ic)][128 B of k]  - 16 KiB tiles stored in HBM
+//                        EXACTLY as the shared-memory image the MMA wants (K-major, SWIZZLE_128B), in consumption
+//                        order, so one item is one contiguous 32*KC KiB run fetched by cp.async.bulk (UBLKCP).
+//                        Same 8 bytes per NTT coefficient as the scan layout: the four limbs ARE the four bytes.
+//   queries   "Q_tc"   : for (z, n): [kc][4*NB rows][128 B of k], row = b*NB + 3*q + r (b = query limb), same swizzle.
+//   accumulators       : TMEM columns [w*NB, (w+1)*NB), w = 0..6.  The MMA for database limb a writes the window
+//                        [a*NB, a*NB + 4*NB): query limb b lands on weight a + b, so equal weights add up in place.
+// CTA = 6 warps, persistent, one per SM: warp 0 producer (bulk copies into an 8 x 16 KiB A ring and a 3-deep B ring),
+// warp 1 MMA issuer (one thread) + TMEM allocation, warps 2-5 epilogue (TMEM -> registers -> Barrett -> global).
+#include "kernels.cuh"
+#include "common.cuh"
+
+namespace sb200 {
+namespace tc {
+
+constexpr int kM = 128;                    // database columns per tile (UMMA M)
+constexpr int kKB = 128;                   // bytes of k per tile row = one SWIZZLE_128B atom = 4 MMA k-steps
+constexpr int kATile = kM * kKB;           // 16 KiB
+constexpr int kAStages = 8;
+constexpr int kBStages = 3;
+constexpr int kThreads = 192;
+constexpr int kMaxBatch = 16;
+
+struct OutPtrs { uint32_t *out[kMaxBatch]; int count; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (the TMA engine, no tensor map: source tiles are already the shared-memory image)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {     // arrives on `bar` when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor: u8 x u8 -> s32, both operands K-major, M = 128 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t idesc_i8(int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24); }
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int NB> struct Shape {
+    static constexpr int kBRows = 4 * NB;
+    static constexpr int kBTile = kBRows * kKB;
+    static constexpr int kCols = 7 * NB;
+    static constexpr int kAlloc = kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
+    static constexpr size_t kSmem = 1024 + (size_t)kAStages * kATile + (size_t)kBStages * kBTile + 256;
+};
+
+// byte offset of (row, 16-byte chunk) inside a SWIZZLE_128B tile whose base is 1024-byte aligned
+__host__ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) { return row * 128u + ((chunk ^ (row & 7u)) << 4); }
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1) k_scan_tc(const __grid_constant__ OutPtrs outs, const uint8_t *__restrict__ q_tc,
+                                                         const uint8_t *__restrict__ db_tc, int KC, int MT, int n_items) {
+    using S = Shape<NB>;
+    pdl_prologue();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_smem = base, b_smem = base + kAStages * kATile;
+    const uint32_t bars = b_smem + kBStages * S::kBTile;
+    // barrier map (8 bytes each): a_full[8] a_empty[8] b_full[3] b_empty[3] tmem_full tmem_empty ; then the TMEM base address
+    const uint32_t a_full = bars, a_empty = bars + 8 * kAStages, b_full = bars + 16 * kAStages, b_empty = b_full + 8 * kBStages;
+    const uint32_t t_full = b_empty + 8 * kBStages, t_empty = t_full + 8, tmem_slot = t_empty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kAStages; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < kBStages; i++) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+        mbar_init(t_full, 1); mbar_init(t_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(S::kAlloc) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+    if (warp == 0) {                                                // ===== producer (lane 0 issues, the warp stays together) =====
+        const uint64_t pol_db = policy_evict_first(), pol_q = policy_evict_last();
+        uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            if (lane == 0) {
+                const uint8_t *asrc = db_tc + (size_t)it * KC * 4 * kATile;
+                const uint8_t *bsrc = q_tc + (size_t)(it / MT) * KC * S::kBTile;
+                for (int kc = 0; kc < KC; kc++) {
+                    mbar_wait(b_empty + 8 * bs, bph ^ 1);
+                    mbar_expect_tx(b_full + 8 * bs, S::kBTile);
+                    bulk_g2s(b_smem + bs * S::kBTile, bsrc + (size_t)kc * S::kBTile, S::kBTile, b_full + 8 * bs, pol_q);
+                    if (++bs == kBStages) { bs = 0; bph ^= 1; }
+                    for (int a = 0; a < 4; a++) {
+                        mbar_wait(a_empty + 8 * as, aph ^ 1);
+                        mbar_expect_tx(a_full + 8 * as, kATile);
+                        bulk_g2s(a_smem + as * kATile, asrc + (size_t)(kc * 4 + a) * kATile, kATile, a_full + 8 * as, pol_db);
+                        if (++as == kAStages) { as = 0; aph ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {                                         // ===== MMA issuer (one thread) =====
+        uint32_t as = 0, aph = 0, bs = 0, bph = 0, tph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            if (lane == 0) {
+                mbar_wait(t_empty, tph ^ 1);                        // epilogue has drained the previous item's accumulators
+                tc_fence_after();
+                for (int kc = 0; kc < KC; kc++) {
+                    mbar_wait(b_full + 8 * bs, bph);
+                    const uint32_t b_addr = b_smem + bs * S::kBTile;
+                    for (int a = 0; a < 4; a++) {
+                        mbar_wait(a_full + 8 * as, aph);
+                        tc_fence_after();
+                        const uint32_t a_addr = a_smem + as * kATile;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t ad = smem_desc_sw128(a_addr + ks * 32), bd = smem_desc_sw128(b_addr + ks * 32);
+                            const bool first = (kc == 0 && ks == 0);
+                            if (a == 0) {
+                                mma_i8(tmem, ad, bd, idesc_i8(4 * NB), first ? 0u : 1u);
+                            } else if (!first) {
+                                mma_i8(tmem + a * NB, ad, bd, idesc_i8(4 * NB), 1u);
+                            } else {                                // weight block a+3 sees its first product here: overwrite it
+                                mma_i8(tmem + a * NB, ad, bd, idesc_i8(3 * NB), 1u);
+                                mma_i8(tmem + a * NB + 3 * NB, ad, smem_desc_sw128(b_addr + 3 * NB * kKB + ks * 32), idesc_i8(NB), 0u);
+                            }
+                        }
+                        tc_commit(a_empty + 8 * as);
+                        if (++as == kAStages) { as = 0; aph ^= 1; }
+                    }
+                    tc_commit(b_empty + 8 * bs);
+                    if (++bs == kBStages) { bs = 0; bph ^= 1; }
+                }
+                tc_commit(t_full);
+                tph ^= 1;
+            }
+            __syncwarp();
+        }
+    } else {                                                        // ===== epilogue: warps 2..5 =====
+        const int quarter = warp & 3;                               // TMEM lanes this warp may read
+        const int row = quarter * 32 + lane;
+        const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+        uint32_t tph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int mt = it % MT, zn = it / MT, n = zn & 1, z = zn >> 1;
+            const int ic = mt * kM + row, i = ic >> 1, c = ic & 1;
+            const uint32_t c32 = n ? c32b : c32p;
+            mbar_wait(t_full, tph);
+            tc_fence_after();
+            const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int cb = 0; cb < NB / 16; cb++) {
+                uint32_t v[7][16];
+#pragma unroll
+                for (int w = 0; w < 7; w++) tmem_ld16(trow + w * NB + cb * 16, v[w]);
+                tmem_ld_wait();
+                if (cb == NB / 16 - 1) { tc_fence_before(); mbar_arrive(t_empty); }
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int col = cb * 16 + e, q = col / 3, r = col - 3 * q;
+                    if (q < outs.count) {
+                        const uint64_t lo = (uint64_t)v[0][e] + ((uint64_t)v[1][e] << 8) + ((uint64_t)v[2][e] << 16) + ((uint64_t)v[3][e] << 24);
+                        const uint64_t hi = (uint64_t)v[4][e] + ((uint64_t)v[5][e] << 8) + ((uint64_t)v[6][e] << 16);
+                        const uint32_t hr = reduce_u64(hi, n);
+                        const uint32_t res = reduce_u64(lo + (uint64_t)hr * c32, n);
+                        outs.out[q][((((size_t)i * kN1 + r) * kN2 + c) * 2 + n) * kN + z] = res;
+                    }
+                }
+            }
+            tph ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(S::kAlloc) : "memory");
+    }
+}
+
+// ---- database: scan layout DB'[z][j][ic][m] PB64 -> DB_tc.  One thread per (z, kc, ic, 16-byte chunk): 8 j x 2 m.
+__global__ void __launch_bounds__(256) k_db_to_tc(uint8_t *__restrict__ db_tc, const uint4 *__restrict__ db, int dim0, int IC) {
+    const int KC = dim0 * 2 / kKB, MT = IC / kM;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           // ((z*KC + kc)*8 + chunk)*IC + ic
+    if (idx >= (size_t)kN * KC * 8 * IC) return;
+    const int ic = (int)(idx % IC);
+    const int chunk = (int)((idx / IC) & 7);
+    const int kc = (int)((idx / IC / 8) % KC);
+    const int z = (int)(idx / IC / 8 / KC);
+    uint4 d[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) d[jj] = db[((size_t)z * dim0 + kc * 64 + chunk * 8 + jj) * IC + ic];
+    const int mt = ic / kM, row = ic % kM;
+#pragma unroll
+    for (int n = 0; n < 2; n++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {                                        // bytes 4g .. 4g+3 = (j = 2g, m = 0,1), (j = 2g+1, m = 0,1)
+                const uint32_t e0 = n ? d[2 * g].y : d[2 * g].x, e1 = n ? d[2 * g].w : d[2 * g].z;
+                const uint32_t e2 = n ? d[2 * g + 1].y : d[2 * g + 1].x, e3 = n ? d[2 * g + 1].w : d[2 * g + 1].z;
+                w[g] = ((e0 >> (8 * a)) & 0xff) | (((e1 >> (8 * a)) & 0xff) << 8) | (((e2 >> (8 * a)) & 0xff) << 16) | (((e3 >> (8 * a)) & 0xff) << 24);
+            }
+            const size_t item = ((size_t)z * 2 + n) * MT + mt;
+            uint8_t *tile = db_tc + ((item * KC + kc) * 4 + a) * (size_t)kATile;
+            *reinterpret_cast<uint4 *>(tile + sw128(row, chunk)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+}
+
+// ---- queries: reoriented PB64 query[z][j][m][4] (reorientCiphertexts layout) of query q -> its 3 x 4 rows of every Q_tc tile.
+// One thread per (z, kc, 16-byte chunk, r): 8 j x 2 m residues under both primes -> 8 chunks (n, b).
+template <int NB>
+__global__ void __launch_bounds__(256) k_query_to_tc(uint8_t *__restrict__ q_tc, const uint64_t *__restrict__ query, int q, int dim0) {
+    using S = Shape<NB>;
+    pdl_prologue();
+    const int KC = dim0 * 2 / kKB;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           // ((z*KC + kc)*8 + chunk)*3 + r
+    if (idx >= (size_t)kN * KC * 8 * 3) return;
+    const int r = (int)(idx % 3), chunk = (int)((idx / 3) & 7), kc = (int)((idx / 24) % KC), z = (int)(idx / 24 / KC);
+    uint64_t e[16];                                                              // k = kc*128 + chunk*16 + t, t = 2*jj + m
+    const uint64_t *src = query + (((size_t)z * dim0 + kc * 64 + chunk * 8) * 2) * 4 + r;
+#pragma unroll
+    for (int t = 0; t < 16; t++) e[t] = src[(size_t)t * 4];
+#pragma unroll
+    for (int n = 0; n < 2; n++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) acc |= (uint32_t)((e[4 * g + t] >> (32 * n + 8 * b)) & 0xff) << (8 * t);
+                w[g] = acc;
+            }
+            uint8_t *tile = q_tc + (((size_t)z * 2 + n) * KC + kc) * (size_t)S::kBTile;
+            *reinterpret_cast<uint4 *>(tile + sw128(b * NB + 3 * q + r, chunk)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+}
+
+inline int nb_for(int count) { return count <= 5 ? 16 : count <= 10 ? 32 : 48; }
+
+}  // namespace tc
+
+size_t tc_query_bytes(size_t dim0, int capacity) { return (size_t)kN * 2 * (dim0 * 2 / tc::kKB) * 4 * tc::nb_for(capacity) * tc::kKB; }
+
+int tc_shape_ok(size_t dim0, size_t num_per) { return (dim0 * 2) % tc::kKB == 0 && (num_per * 2) % tc::kM == 0; }
+
+void launch_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
+    const size_t IC = num_per * 2, n = (size_t)kN * (dim0 * 2 / tc::kKB) * 8 * IC;
+    count_launch();
+    tc::k_db_to_tc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(db_tc, reinterpret_cast<const uint4 *>(db), (int)dim0, (int)IC);
+}
+
+// capacity fixes the tile shape (NB); q < capacity
+void launch_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, cudaStream_t s) {
+    const size_t n = (size_t)kN * (dim0 * 2 / tc::kKB) * 8 * 3;
+    const dim3 grid((unsigned)((n + 255) / 256));
+    count_launch();
+    switch (tc::nb_for(capacity)) {
+        case 16: launch_pdl(tc::k_query_to_tc<16>, grid, dim3(256), 0, s, q_tc, query, q, (int)dim0); break;
+        case 32: launch_pdl(tc::k_query_to_tc<32>, grid, dim3(256), 0, s, q_tc, query, q, (int)dim0); break;
+        default: launch_pdl(tc::k_query_to_tc<48>, grid, dim3(256), 0, s, q_tc, query, q, (int)dim0); break;
+    }
+}
+
+template <int NB>
+static int launch_scan_tc_nb(const tc::OutPtrs &o, const uint8_t *q_tc, const uint8_t *db_tc, int KC, int MT, cudaStream_t s) {
+    static int sms = 0;
+    static bool attr = false;
+    if (!attr) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(tc::k_scan_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Shape<NB>::kSmem) != cudaSuccess) return -2;
+        attr = true;
+    }
+    const int n_items = kN * 2 * MT;
+    const int grid = n_items < sms ? n_items : sms;
+    count_launch();
+    launch_pdl(tc::k_scan_tc<NB>, dim3(grid), dim3(tc::kThreads), tc::Shape<NB>::kSmem, s, o, q_tc, db_tc, KC, MT, n_items);
+    return 0;
+}
+
+// out[q]: dev-NTT [i][r][c] like launch_scan_spiral; count <= capacity <= 16; q_tc built with the same capacity
+int launch_scan_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, size_t dim0, size_t num_per,
+                   cudaStream_t s) {
+    if (count < 1 || count > capacity || capacity > tc::kMaxBatch || !tc_shape_ok(dim0, num_per)) return -1;
+    tc::OutPtrs o;
+    for (int b = 0; b < tc::kMaxBatch; b++) o.out[b] = b < count ? out[b] : nullptr;
+    o.count = count;
+    const int KC = (int)(dim0 * 2 / tc::kKB), MT = (int)(num_per * 2 / tc::kM);
+    switch (tc::nb_for(capacity)) {
+        case 16: return launch_scan_tc_nb<16>(o, q_tc, db_tc, KC, MT, s);
+        case 32: return launch_scan_tc_nb<32>(o, q_tc, db_tc, KC, MT, s);
+        default: return launch_scan_tc_nb<48>(o, q_tc, db_tc, KC, MT, s);
+    }
+}
+
+}  // namespace sb200

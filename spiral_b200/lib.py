@@ -150,6 +150,14 @@ def load_library():
         "sb200_server_scan": (C.c_int, [vp, vp]),
         "sb200_server_lift": (C.c_int, [vp, vp]),
         "sb200_server_scan_batched": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
+        "sb200_server_enable_tc": (C.c_int, [vp, C.c_int]),
+        "sb200_server_scan_batched_tc": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
+        "sb200_tc_supported": (C.c_int, [sz, sz]),
+        "sb200_tc_query_bytes": (sz, [sz, C.c_int]),
+        "sb200_dev_db_to_tc": (C.c_int, [vp, vp, sz, sz, vp]),
+        "sb200_dev_query_to_tc": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp]),
+        "sb200_dev_first_dim_tc": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, vp, vp, sz, sz, vp]),
+        "sb200_multiplyQueryByDatabase_batched": (C.c_int, [C.POINTER(u64p), C.POINTER(u64p), C.c_int, u64p, sz, sz]),
         "sb200_server_copy_partial": (C.c_int, [vp, vp, vp]),
         "sb200_server_scan_host": (C.c_int, [vp, u64p, u64p]),
         "sb200_server_load_db_random": (C.c_int, [vp, C.c_uint64]),

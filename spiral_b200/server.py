@@ -89,6 +89,16 @@ class SpiralServer:
         arr = (C.c_void_p * len(servers))(*[s.h for s in servers])
         check(servers[0].lib.sb200_server_scan_batched(arr, len(servers), stream), servers[0].lib)
 
+    def enable_tc(self, capacity=16):
+        """Build the tensor-core (limb-tile) copy of the resident database for batches of up to `capacity` queries."""
+        check(self.lib.sb200_server_enable_tc(self.h, capacity), self.lib)
+
+    @staticmethod
+    def scan_batched_tc(servers, stream=None):
+        """One tcgen05 pass over the database for up to 16 servers sharing it (enable_tc on the owner first)."""
+        arr = (C.c_void_p * len(servers))(*[s.h for s in servers])
+        check(servers[0].lib.sb200_server_scan_batched_tc(arr, len(servers), stream), servers[0].lib)
+
     def lift(self, stream=None):
         check(self.lib.sb200_server_lift(self.h, stream), self.lib)
 
