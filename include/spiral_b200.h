@@ -97,8 +97,9 @@ int sb200_tc_supported(size_t dim0, size_t num_per);      /* 2*dim0 and 2*num_pe
 size_t sb200_tc_query_bytes(size_t dim0, int capacity);
 int sb200_dev_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, void *stream);
 int sb200_dev_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, void *stream);
+size_t sb200_tc_scratch_bytes(size_t num_per, int count);   /* tile-order results of one pass (transposed into out[q] by a second kernel) */
 int sb200_dev_first_dim_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc,
-                           size_t dim0, size_t num_per, void *stream);
+                           size_t dim0, size_t num_per, uint32_t *scratch, void *stream);
 size_t sb200_fold_scratch_words(size_t num_per_after, uint32_t t_gsw);   /* uint32 words */
 int sb200_dev_fold_round(uint64_t *cts, size_t num_per_after, const uint32_t *q, const uint32_t *q_neg,
                          uint32_t t_gsw, uint32_t *scratch, void *stream);                      /* src/spiral.cpp:1349-1410 */

@@ -38,7 +38,8 @@ outs = [torch.empty(out_words, dtype=torch.int32, device="cuda") for _ in range(
 ref = torch.empty(out_words, dtype=torch.int32, device="cuda")
 
 
-def timed(fn, iters=10, warm=3):
+def timed(fn, iters=None, warm=3):
+    iters = iters or int(os.environ.get("TC_ITERS", "10"))
     for _ in range(warm):
         fn()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
@@ -50,15 +51,18 @@ def timed(fn, iters=10, warm=3):
     return ts[0], ts[len(ts) // 2]
 
 
-t1 = timed(lambda: sb.sb200_dev_first_dim(ref.data_ptr(), queries[0].data_ptr(), db.data_ptr(), dim0, num_per, None))
-print(json.dumps({"kernel": "k_scan_spiral", "queries": 1, "ms_min": t1[0], "ms_med": t1[1], "db_gbs": db_words * 8 / t1[1] / 1e6}))
-for count in (1, 4, 5, 8, 10, 12, 16):
+ts = timed(lambda: sb.sb200_dev_first_dim(ref.data_ptr(), queries[0].data_ptr(), db.data_ptr(), dim0, num_per, None))
+print(json.dumps({"kernel": "k_scan_spiral", "queries": 1, "ms_min": ts[0], "ms_med": ts[1], "db_gbs": db_words * 8 / ts[1] / 1e6}))
+COUNTS = [int(c) for c in os.environ.get("TC_COUNTS", "1,4,5,8,10,12,16").split(",")]
+ITERS = int(os.environ.get("TC_ITERS", "10"))
+for count in COUNTS:
     q_tc = torch.zeros(sb.sb200_tc_query_bytes(dim0, count), dtype=torch.uint8, device="cuda")
     for b in range(count):
         assert sb.sb200_dev_query_to_tc(q_tc.data_ptr(), queries[b].data_ptr(), b, count, dim0, None) == 0, sb.sb200_last_error()
     arr = (C.c_void_p * count)(*[outs[b].data_ptr() for b in range(count)])
+    t1 = torch.empty(sb.sb200_tc_scratch_bytes(num_per, count), dtype=torch.uint8, device="cuda")
     tq = timed(lambda: sb.sb200_dev_query_to_tc(q_tc.data_ptr(), queries[0].data_ptr(), 0, count, dim0, None))
-    t = timed(lambda: sb.sb200_dev_first_dim_tc(arr, count, count, q_tc.data_ptr(), db_tc.data_ptr(), dim0, num_per, None))
+    t = timed(lambda: sb.sb200_dev_first_dim_tc(arr, count, count, q_tc.data_ptr(), db_tc.data_ptr(), dim0, num_per, t1.data_ptr(), None))
     same = bool(torch.equal(outs[0], ref))
     bytes_moved = db_words * 8 + q_tc.numel() + count * out_words * 4
     print(json.dumps({"kernel": "k_scan_tc", "queries": count, "ms_min": t[0], "ms_med": t[1], "ms_per_query": t[1] / count,

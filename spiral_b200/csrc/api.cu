@@ -137,11 +137,12 @@ extern "C" int sb200_dev_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q
     if (!q_tc || !query || q < 0 || q >= capacity || capacity > 16 || (dim0 * 2) % 128) return fail(SB200_ERR_ARG, "query_to_tc: bad slot, capacity or dim0");
     launch_query_to_tc(q_tc, query, q, capacity, dim0, S(stream)); CHECK_LAUNCH(); return SB200_OK;
 }
+extern "C" size_t sb200_tc_scratch_bytes(size_t num_per, int count) { return tc_scratch_bytes(num_per, count); }
 extern "C" int sb200_dev_first_dim_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc,
-                                      size_t dim0, size_t num_per, void *stream) {
+                                      size_t dim0, size_t num_per, uint32_t *scratch, void *stream) {
     NEED_DEVICE();
-    if (!out || !q_tc || !db_tc) return fail(SB200_ERR_ARG, "first_dim_tc: null argument");
-    const int rc = launch_scan_tc(out, count, capacity, q_tc, db_tc, dim0, num_per, S(stream));
+    if (!out || !q_tc || !db_tc || !scratch) return fail(SB200_ERR_ARG, "first_dim_tc: null argument");
+    const int rc = launch_scan_tc(out, count, capacity, q_tc, db_tc, dim0, num_per, scratch, S(stream));
     if (rc == -1) return fail(SB200_ERR_ARG, "first_dim_tc: needs 1 <= count <= capacity <= 16, 2*dim0 and 2*num_per multiples of 128");
     if (rc) return fail(SB200_ERR_CUDA, "first_dim_tc: cannot reserve %zu bytes of shared memory", (size_t)0);
     CHECK_LAUNCH(); return SB200_OK;
@@ -348,7 +349,7 @@ extern "C" int sb200_multiplyQueryByDatabase_batched(uint64_t *const *out, const
     if (!tc_shape_ok(dim0, num_per)) return fail(SB200_ERR_ARG, "multiplyQueryByDatabase_batched: needs 2*dim0 and 2*num_per to be multiples of 128");
     const size_t qwords = dim0 * 2 * 4 * kN, dbwords = dim0 * num_per * 4 * kN, opolys = num_per * 6;
     DBuf<uint64_t> dq(qwords), dref(dbwords), ddb(dbwords); DBuf<uint8_t> dtc(dbwords * 8), qtc(tc_query_bytes(dim0, count));
-    DBuf<uint32_t> dout((size_t)count * opolys * PLW);
+    DBuf<uint32_t> dout((size_t)count * opolys * PLW), dt1(tc_scratch_bytes(num_per, count) / 4);
     CU(dref.up(database, dbwords));
     launch_db_from_reference(ddb.p, dref.p, dim0, num_per * kN2, 0, kN, 0); CHECK_LAUNCH();
     launch_db_to_tc(dtc.p, ddb.p, dim0, num_per, 0); CHECK_LAUNCH();
@@ -360,7 +361,7 @@ extern "C" int sb200_multiplyQueryByDatabase_batched(uint64_t *const *out, const
         CU(cudaDeviceSynchronize());
         o[b] = dout.p + (size_t)b * opolys * PLW;
     }
-    if (launch_scan_tc(o, count, count, qtc.p, dtc.p, dim0, num_per, 0)) return fail(SB200_ERR_CUDA, "multiplyQueryByDatabase_batched: launch failed");
+    if (launch_scan_tc(o, count, count, qtc.p, dtc.p, dim0, num_per, dt1.p, 0)) return fail(SB200_ERR_CUDA, "multiplyQueryByDatabase_batched: launch failed");
     CHECK_LAUNCH();
     for (int b = 0; b < count; b++) TRY(down_ntt(out[b], o[b], opolys));
     return SB200_OK;
@@ -496,6 +497,7 @@ struct sb200_server {
     // device memory
     DBuf<uint64_t> db;                                  // scan layout shard
     DBuf<uint8_t> db_tc, q_tc;                          // tensor-core path (sb200_server_enable_tc): limb-tile database, batched query tiles
+    DBuf<uint32_t> tc_t1;                               // ... and the tile-order scan results of one pass
     int tc_capacity = 0;
     DBuf<uint32_t> W_left, W_right, W_conv, V_conv, neg1;
     DBuf<uint64_t> q_stage;                             // uploaded query (ref-NTT)
@@ -748,6 +750,8 @@ extern "C" int sb200_server_enable_tc(sb200_server *s, int capacity) {
         launch_db_to_tc(s->db_tc.p, s->db.p, s->dim0, s->local_num_per, s->own_stream); CHECK_LAUNCH();
     }
     if (s->q_tc.p) { cudaFree(s->q_tc.p); s->q_tc.p = nullptr; }
+    if (s->tc_t1.p) { cudaFree(s->tc_t1.p); s->tc_t1.p = nullptr; }
+    CU(s->tc_t1.alloc(tc_scratch_bytes(s->local_num_per, capacity) / 4));
     CU(s->q_tc.alloc(tc_query_bytes(s->dim0, capacity)));
     CU(cudaMemsetAsync(s->q_tc.p, 0, s->q_tc.n, s->own_stream));
     CU(cudaStreamSynchronize(s->own_stream));
@@ -770,7 +774,7 @@ extern "C" int sb200_server_scan_batched_tc(sb200_server *const *servers, int co
         launch_query_to_tc(owner->q_tc.p, servers[b]->query.p, b, owner->tc_capacity, owner->dim0, st);
         o[b] = servers[b]->scan_out.p;
     }
-    if (launch_scan_tc(o, count, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, owner->dim0, owner->local_num_per, st))
+    if (launch_scan_tc(o, count, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, owner->dim0, owner->local_num_per, owner->tc_t1.p, st))
         return fail(SB200_ERR_CUDA, "scan_batched_tc: launch failed");
     CHECK_LAUNCH();
     return SB200_OK;

@@ -71,8 +71,9 @@ int tc_shape_ok(size_t dim0, size_t num_per);                       // needs 2*d
 size_t tc_query_bytes(size_t dim0, int capacity);                   // Q_tc bytes for a batch of up to `capacity` queries
 void launch_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s);   // scan layout -> DB_tc (same size)
 void launch_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, cudaStream_t s);
+size_t tc_scratch_bytes(size_t num_per, int count);                 // tile-order results of one pass, before the transpose
 int launch_scan_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, size_t dim0, size_t num_per,
-                   cudaStream_t s);
+                   uint32_t *scratch, cudaStream_t s);
 
 // ---- folding (Spiral): cts raw [2*num_per][3][2][2048] -> first num_per folded in place.
 // q_dev / qneg_dev: dev-NTT (3 x 3*t_gsw) GSW ciphertext of THIS round.

@@ -17,8 +17,9 @@
 //   queries   "Q_tc"   : for (z, n): [kc][4*NB rows][128 B of k], row = b*NB + 3*q + r (b = query limb), same swizzle.
 //   accumulators       : TMEM columns [w*NB, (w+1)*NB), w = 0..6.  The MMA for database limb a writes the window
 //                        [a*NB, a*NB + 4*NB): query limb b lands on weight a + b, so equal weights add up in place.
-// CTA = 6 warps, persistent, one per SM: warp 0 producer (bulk copies into an 8 x 16 KiB A ring and a 3-deep B ring),
-// warp 1 MMA issuer (one thread) + TMEM allocation, warps 2-5 epilogue (TMEM -> registers -> Barrett -> global).
+// CTA = 2 + NB/4 warps, persistent, one per SM: warp 0 producer (bulk copies into an 8 x 16 KiB A ring and a 3-deep B ring),
+// warp 1 MMA issuer (one thread) + TMEM allocation, then four epilogue warps per 16 accumulator columns
+// (TMEM -> registers, accumulators released at once, -> Barrett -> global).
 #include "kernels.cuh"
 #include "common.cuh"
 
@@ -30,7 +31,6 @@ constexpr int kKB = 128;                   // bytes of k per tile row = one SWIZ
 constexpr int kATile = kM * kKB;           // 16 KiB
 constexpr int kAStages = 8;
 constexpr int kBStages = 3;
-constexpr int kThreads = 192;
 constexpr int kMaxBatch = 16;
 
 struct OutPtrs { uint32_t *out[kMaxBatch]; int count; };
@@ -107,8 +107,53 @@ template <int NB> struct Shape {
 // byte offset of (row, 16-byte chunk) inside a SWIZZLE_128B tile whose base is 1024-byte aligned
 __host__ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) { return row * 128u + ((chunk ^ (row & 7u)) << 4); }
 
+// sum_w 2^(8w) T_w  mod q from the seven weight accumulators of one output (T_w < 2^28): the powers 2^32, 2^40, 2^48 are
+// replaced by their residues so the whole sum stays below 2^59, then one Barrett step with floor(2^59/q) on the top 32 bits.
+// Results go to the tile-order buffer T1[q][n][z][r][ic]: the 32 lanes of a warp own 32 consecutive ic, so every store
+// instruction writes one full 128-byte line (the reference order [i][r][c][n][z] would be 32 separate 4-byte sectors).
+template <int CB>
+__device__ __forceinline__ void epilogue_store(uint32_t *__restrict__ t1, int count, uint32_t IC, const uint32_t (&v)[7][16], uint32_t off, int n) {
+    constexpr uint32_t c4p = (uint32_t)((1ull << 32) % kP), c5p = (uint32_t)((1ull << 40) % kP), c6p = (uint32_t)((1ull << 48) % kP);
+    constexpr uint32_t c4b = (uint32_t)((1ull << 32) % kB), c5b = (uint32_t)((1ull << 40) % kB), c6b = (uint32_t)((1ull << 48) % kB);
+    constexpr uint32_t mup = (uint32_t)((1ull << 59) / kP), mub = (uint32_t)((1ull << 59) / kB);
+    const uint32_t c4 = n ? c4b : c4p, c5 = n ? c5b : c5p, c6 = n ? c6b : c6p, mu = n ? mub : mup, q = n ? kB : kP;
+    const uint32_t sq = 2u * kN * 3u * IC;                              // words per query in T1
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int col = CB * 16 + e, qi = col / 3, r = col - 3 * qi;
+        if (qi < count) {
+            uint64_t x = (uint64_t)v[0][e] + ((uint64_t)v[1][e] << 8) + ((uint64_t)v[2][e] << 16) + ((uint64_t)v[3][e] << 24);
+            x += (uint64_t)v[4][e] * c4 + (uint64_t)v[5][e] * c5 + (uint64_t)v[6][e] * c6;
+            const uint32_t qhat = __umulhi((uint32_t)(x >> 27), mu);
+            uint32_t res = (uint32_t)x - qhat * q;                  // true remainder + at most 3q  (< 2^30)
+            res = min(res, res - 2 * q);
+            res = min(res, res - q);
+            t1[(size_t)(off + (uint32_t)qi * sq + (uint32_t)r * IC)] = res;
+        }
+    }
+}
+
+// T1[q][n][z][r][ic] -> dev-NTT out_q[i][r][c][n][z] (ic = 2i + c): 32 x 32 shared-memory transpose, 128-byte lines both ways
+__global__ void __launch_bounds__(256) k_tc_untile(const __grid_constant__ OutPtrs outs, const uint32_t *__restrict__ t1, int IC) {
+    pdl_prologue();
+    __shared__ uint32_t tile[32][33];
+    const int z0 = blockIdx.x * 32, ic0 = blockIdx.y * 32;
+    const int r = blockIdx.z % 3, n = (blockIdx.z / 3) & 1, q = blockIdx.z / 6;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t *src = t1 + (((size_t)(q * 2 + n) * kN + z0) * 3 + r) * IC + ic0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) tile[ty + 8 * k][tx] = __ldg(src + (size_t)(ty + 8 * k) * 3 * IC + tx);
+    __syncthreads();
+    uint32_t *dst = outs.out[q];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ic = ic0 + ty + 8 * k, i = ic >> 1, c = ic & 1;
+        dst[((((size_t)i * kN1 + r) * kN2 + c) * 2 + n) * kN + z0 + tx] = tile[tx][ty + 8 * k];
+    }
+}
+
 template <int NB>
-__global__ void __launch_bounds__(kThreads, 1) k_scan_tc(const __grid_constant__ OutPtrs outs, const uint8_t *__restrict__ q_tc,
+__global__ void __launch_bounds__(64 + 8 * NB, 1) k_scan_tc(uint32_t *__restrict__ t1, int count, const uint8_t *__restrict__ q_tc,
                                                          const uint8_t *__restrict__ db_tc, int KC, int MT, int n_items) {
     using S = Shape<NB>;
     pdl_prologue();
@@ -124,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_scan_tc(const __grid_constant__
     if (threadIdx.x == 0) {
         for (int i = 0; i < kAStages; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
         for (int i = 0; i < kBStages; i++) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-        mbar_init(t_full, 1); mbar_init(t_empty, 128);
+        mbar_init(t_full, 1); mbar_init(t_empty, 8 * NB);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -196,37 +241,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_scan_tc(const __grid_constant__
             }
             __syncwarp();
         }
-    } else {                                                        // ===== epilogue: warps 2..5 =====
-        const int quarter = warp & 3;                               // TMEM lanes this warp may read
+    } else {                                                        // ===== epilogue: 4 warps per 16-column chunk =====
+        const int e = warp - 2, quarter = warp & 3, cb = e >> 2;   // TMEM lanes are tied to warp % 4; chunk cb of NB/16
         const int row = quarter * 32 + lane;
-        const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
         uint32_t tph = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const int mt = it % MT, zn = it / MT, n = zn & 1, z = zn >> 1;
-            const int ic = mt * kM + row, i = ic >> 1, c = ic & 1;
-            const uint32_t c32 = n ? c32b : c32p;
+            const uint32_t IC = (uint32_t)MT * kM;
+            const uint32_t off = ((uint32_t)(n * kN + z) * 3u) * IC + (uint32_t)(mt * kM + row);   // T1 word index of (q = 0, r = 0)
             mbar_wait(t_full, tph);
             tc_fence_after();
             const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-            for (int cb = 0; cb < NB / 16; cb++) {
-                uint32_t v[7][16];
+            uint32_t v[7][16];
 #pragma unroll
-                for (int w = 0; w < 7; w++) tmem_ld16(trow + w * NB + cb * 16, v[w]);
-                tmem_ld_wait();
-                if (cb == NB / 16 - 1) { tc_fence_before(); mbar_arrive(t_empty); }
-#pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    const int col = cb * 16 + e, q = col / 3, r = col - 3 * q;
-                    if (q < outs.count) {
-                        const uint64_t lo = (uint64_t)v[0][e] + ((uint64_t)v[1][e] << 8) + ((uint64_t)v[2][e] << 16) + ((uint64_t)v[3][e] << 24);
-                        const uint64_t hi = (uint64_t)v[4][e] + ((uint64_t)v[5][e] << 8) + ((uint64_t)v[6][e] << 16);
-                        const uint32_t hr = reduce_u64(hi, n);
-                        const uint32_t res = reduce_u64(lo + (uint64_t)hr * c32, n);
-                        outs.out[q][((((size_t)i * kN1 + r) * kN2 + c) * 2 + n) * kN + z] = res;
-                    }
-                }
-            }
+            for (int w = 0; w < 7; w++) tmem_ld16(trow + w * NB + cb * 16, v[w]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(t_empty);                                   // accumulators are in registers: the next item may start
+            if (cb == 0)      epilogue_store<0>(t1, count, IC, v, off, n);
+            else if (cb == 1) epilogue_store<1>(t1, count, IC, v, off, n);
+            else              epilogue_store<2>(t1, count, IC, v, off, n);
             tph ^= 1;
         }
     }
@@ -325,8 +359,10 @@ void launch_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacit
     }
 }
 
+size_t tc_scratch_bytes(size_t num_per, int count) { return (size_t)count * 2 * kN * 3 * (num_per * 2) * sizeof(uint32_t); }
+
 template <int NB>
-static int launch_scan_tc_nb(const tc::OutPtrs &o, const uint8_t *q_tc, const uint8_t *db_tc, int KC, int MT, cudaStream_t s) {
+static int launch_scan_tc_nb(uint32_t *t1, int count, const uint8_t *q_tc, const uint8_t *db_tc, int KC, int MT, cudaStream_t s) {
     static int sms = 0;
     static bool attr = false;
     if (!attr) {
@@ -338,23 +374,29 @@ static int launch_scan_tc_nb(const tc::OutPtrs &o, const uint8_t *q_tc, const ui
     const int n_items = kN * 2 * MT;
     const int grid = n_items < sms ? n_items : sms;
     count_launch();
-    launch_pdl(tc::k_scan_tc<NB>, dim3(grid), dim3(tc::kThreads), tc::Shape<NB>::kSmem, s, o, q_tc, db_tc, KC, MT, n_items);
+    launch_pdl(tc::k_scan_tc<NB>, dim3(grid), dim3(64 + 8 * NB), tc::Shape<NB>::kSmem, s, t1, count, q_tc, db_tc, KC, MT, n_items);
     return 0;
 }
 
-// out[q]: dev-NTT [i][r][c] like launch_scan_spiral; count <= capacity <= 16; q_tc built with the same capacity
+// out[q]: dev-NTT [i][r][c] like launch_scan_spiral; count <= capacity <= 16; q_tc built with the same capacity;
+// scratch: tc_scratch_bytes(num_per, count) bytes for the tile-order results before the transpose
 int launch_scan_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, size_t dim0, size_t num_per,
-                   cudaStream_t s) {
-    if (count < 1 || count > capacity || capacity > tc::kMaxBatch || !tc_shape_ok(dim0, num_per)) return -1;
+                   uint32_t *scratch, cudaStream_t s) {
+    if (count < 1 || count > capacity || capacity > tc::kMaxBatch || !tc_shape_ok(dim0, num_per) || !scratch) return -1;
     tc::OutPtrs o;
     for (int b = 0; b < tc::kMaxBatch; b++) o.out[b] = b < count ? out[b] : nullptr;
     o.count = count;
     const int KC = (int)(dim0 * 2 / tc::kKB), MT = (int)(num_per * 2 / tc::kM);
+    int rc;
     switch (tc::nb_for(capacity)) {
-        case 16: return launch_scan_tc_nb<16>(o, q_tc, db_tc, KC, MT, s);
-        case 32: return launch_scan_tc_nb<32>(o, q_tc, db_tc, KC, MT, s);
-        default: return launch_scan_tc_nb<48>(o, q_tc, db_tc, KC, MT, s);
+        case 16: rc = launch_scan_tc_nb<16>(scratch, count, q_tc, db_tc, KC, MT, s); break;
+        case 32: rc = launch_scan_tc_nb<32>(scratch, count, q_tc, db_tc, KC, MT, s); break;
+        default: rc = launch_scan_tc_nb<48>(scratch, count, q_tc, db_tc, KC, MT, s); break;
     }
+    if (rc) return rc;
+    count_launch();
+    launch_pdl(tc::k_tc_untile, dim3(kN / 32, (unsigned)(num_per * 2 / 32), (unsigned)(count * 6)), dim3(256), 0, s, o, (const uint32_t *)scratch, (int)(num_per * 2));
+    return 0;
 }
 
 }  // namespace sb200

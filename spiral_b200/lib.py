@@ -156,7 +156,8 @@ def load_library():
         "sb200_tc_query_bytes": (sz, [sz, C.c_int]),
         "sb200_dev_db_to_tc": (C.c_int, [vp, vp, sz, sz, vp]),
         "sb200_dev_query_to_tc": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp]),
-        "sb200_dev_first_dim_tc": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, vp, vp, sz, sz, vp]),
+        "sb200_tc_scratch_bytes": (sz, [sz, C.c_int]),
+        "sb200_dev_first_dim_tc": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, vp, vp, sz, sz, vp, vp]),
         "sb200_multiplyQueryByDatabase_batched": (C.c_int, [C.POINTER(u64p), C.POINTER(u64p), C.c_int, u64p, sz, sz]),
         "sb200_server_copy_partial": (C.c_int, [vp, vp, vp]),
         "sb200_server_scan_host": (C.c_int, [vp, u64p, u64p]),

@@ -64,6 +64,7 @@ def test_tc_scan_equals_single_query_scan_kernel(sb):
     assert sb.sb200_dev_db_to_tc(db_tc.data_ptr(), db.data_ptr(), dim0, num_per, None) == 0, sb.sb200_last_error()
     q_tc = torch.zeros(sb.sb200_tc_query_bytes(dim0, count), dtype=torch.uint8, device="cuda")
     out_words = num_per * 6 * 2 * N
+    t1 = torch.empty(sb.sb200_tc_scratch_bytes(num_per, count), dtype=torch.uint8, device="cuda")
     singles, batched, keep = [], [], []
     for b in range(count):
         q = rnd_pb(rng, (N, dim0, 2, 4)); q[..., 3] = 0
@@ -75,11 +76,11 @@ def test_tc_scan_equals_single_query_scan_kernel(sb):
         assert sb.sb200_dev_query_to_tc(q_tc.data_ptr(), qd.data_ptr(), b, count, dim0, None) == 0, sb.sb200_last_error()
         batched.append(torch.full((out_words,), -1, dtype=torch.int32, device="cuda"))
     arr = (C.c_void_p * count)(*[t.data_ptr() for t in batched])
-    assert sb.sb200_dev_first_dim_tc(arr, count, count, q_tc.data_ptr(), db_tc.data_ptr(), dim0, num_per, None) == 0, sb.sb200_last_error()
+    assert sb.sb200_dev_first_dim_tc(arr, count, count, q_tc.data_ptr(), db_tc.data_ptr(), dim0, num_per, t1.data_ptr(), None) == 0, sb.sb200_last_error()
     torch.cuda.synchronize()
     for b in range(count):
         assert torch.equal(batched[b], singles[b]), f"query {b}"
-    assert sb.sb200_dev_first_dim_tc(arr, count, count, q_tc.data_ptr(), db_tc.data_ptr(), 32, num_per, None) == -3   # 2*dim0 < 128
+    assert sb.sb200_dev_first_dim_tc(arr, count, count, q_tc.data_ptr(), db_tc.data_ptr(), 32, num_per, t1.data_ptr(), None) == -3   # 2*dim0 < 128
 
 
 def test_tc_server_batch_answers_every_client(sb, oracle):
