@@ -443,6 +443,7 @@ class PackDriver:
             self.h2d_bytes = int((self.vf_host.numel() + self.vg_host.numel()) * 8)
         else:
             srv.set_public_params(rnd_ntt(g * 2 * p["t_exp"]), rnd_ntt((stop + 1) * 2 * p["t_exp_right"]), rnd_ntt(2 * 2 * p["t_conv"]), vW)
+            self.view_params = lambda: (rnd_ntt(g * 2 * p["t_exp"]), rnd_ntt((stop + 1) * 2 * p["t_exp_right"]), rnd_ntt(2 * 2 * p["t_conv"]), vW)
             self.q_host = torch.from_numpy(rnd_ntt(2).view(np.int64)).pin_memory()
             self.h2d_bytes = int(self.q_host.numel() * 8)
         words = srv.partial_words
@@ -664,7 +665,127 @@ def b200_main(args):
             pipelined["batched_scan"] = {"queries_per_pass": len(clients), "ms_per_query_amortised": wall_ms / nq, "queries_per_s": nq / (wall_ms * 1e-3),
                                          "scan_pass_ms": sb0.elapsed_time(sb1) / 5,
                                          "effective_db_gbs_per_query_stream": srv.db_bytes * len(clients) / (sb0.elapsed_time(sb1) / 5 * 1e-3) / 1e9}
+        # tensor-core batched first dimension (tc_scan.cu): up to 16 clients' converted queries answered by ONE tcgen05 pass
+        # over the limb-tile copy of the database; expansions and folds of the clients overlap on their own streams
+        if args.tc_batch > 1 and lib.sb200_tc_supported(srv.dim0, srv.num_per):
+            nb = min(args.tc_batch, 16)
+            while len(clients) < nb:
+                c = srv.view()
+                c.set_public_params(rnd_ntt(drv.g * 2 * p["t_exp"]), rnd_ntt(drv.n_right * 2 * p["t_exp_right"]),
+                                    rnd_ntt(3 * 2 * p["t_conv"]), rnd_ntt(3 * 2 * p["t_conv"]))
+                clients.append(c); streams.append(torch.cuda.Stream())
+                resp_hosts.append(torch.empty(6 * N_POLY, dtype=torch.int64).pin_memory())
+                resp_devs.append(torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda"))
+            tcc, tcs = clients[:nb], streams[:nb]
+            srv.enable_tc(nb)
+            evs = [torch.cuda.Event() for _ in tcc]
+            ev_scan = torch.cuda.Event()
+
+            def tc_round():
+                for ci, (c, st) in enumerate(zip(tcc, tcs)):
+                    with torch.cuda.stream(st):
+                        c.upload_query_ptr(q_host.data_ptr(), st.cuda_stream)
+                        c.expand_and_convert(st.cuda_stream)
+                        evs[ci].record(st)
+                with torch.cuda.stream(tcs[0]):
+                    for ci in range(1, nb):
+                        tcs[0].wait_event(evs[ci])
+                    SpiralServer.scan_batched_tc(tcc, tcs[0].cuda_stream)
+                    ev_scan.record(tcs[0])
+                for ci, (c, st) in enumerate(zip(tcc, tcs)):
+                    with torch.cuda.stream(st):
+                        st.wait_event(ev_scan)
+                        c.lift(st.cuda_stream); c.fold_local(st.cuda_stream)
+                        c.fold_tail(c.partial_ct_ptr(), resp_devs[ci].data_ptr(), st.cuda_stream)
+                        resp_hosts[ci].copy_(resp_devs[ci], non_blocking=True)
+            for _ in range(3):
+                tc_round()
+            torch.cuda.synchronize()
+            rounds = max(3, args.steps // 2)
+            t0 = time.perf_counter()
+            for _ in range(rounds):
+                tc_round()
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            sb0, sb1 = ev(), ev()
+            with torch.cuda.stream(tcs[0]):
+                sb0.record(tcs[0])
+                for _ in range(5):
+                    SpiralServer.scan_batched_tc(tcc, tcs[0].cuda_stream)
+                sb1.record(tcs[0])
+            torch.cuda.synchronize()
+            pass_ms = sb0.elapsed_time(sb1) / 5
+            nq = rounds * nb
+            pipelined["tensor_core_batch"] = {
+                "queries_per_pass": nb, "ms_per_query_amortised": wall_ms / nq, "queries_per_s": nq / (wall_ms * 1e-3),
+                "first_dim_pass_ms": pass_ms, "first_dim_ms_per_query": pass_ms / nb,
+                "db_gbs_per_pass": srv.db_bytes / (pass_ms * 1e-3) / 1e9,
+                "effective_db_gbs_x_queries": srv.db_bytes * nb / (pass_ms * 1e-3) / 1e9,
+                "int8_tensor_tops": 2.0 * 16 * 3 * nb * (srv.db_bytes / 8) * 2 / (pass_ms * 1e-3) / 1e12,
+                "note": "pass = query tiles (k_query_to_tc x queries) + k_scan_tc (tcgen05 kind::i8, u8 limbs) + k_tc_untile; bit-exact (tests/test_gpu_tc.py)"}
         for c in clients[1:]:
+            c.close()
+        torch.cuda.set_stream(tstream)
+
+    # SpiralPack: the scan is most of a query (cfg3: 11.5 of 15 ms), so one tensor-core pass over the planes for a batch of
+    # clients multiplies the serving throughput; expansions / folds of the clients overlap on their own streams
+    if world == 1 and args.tc_batch > 1 and wl["kind"] == "pack" and not wl["direct"] and drv.srv.dim0 % 128 == 0 and drv.srv.num_per % 128 == 0:
+        from spiral_b200.server import PackServer
+        srv = drv.srv
+        nb = min(args.tc_batch, 16 if srv.db_bytes <= (32 << 30) else 8)      # cfg3: 64 GiB planes + 64 GiB limb tiles + 8 client contexts
+        srv.enable_tc(nb)
+        tcc = [srv] + [srv.view() for _ in range(nb - 1)]
+        for c in tcc[1:]:
+            c.set_public_params(*drv.view_params())
+        tcs = [tstream] + [torch.cuda.Stream() for _ in range(nb - 1)]
+        resp_devs = [drv.resp_dev] + [torch.empty(srv.response_words, dtype=torch.int64, device="cuda") for _ in range(nb - 1)]
+        resp_hosts = [drv.resp_host] + [torch.empty(srv.response_words, dtype=torch.int64).pin_memory() for _ in range(nb - 1)]
+        evs = [torch.cuda.Event() for _ in tcc]
+        ev_scan = torch.cuda.Event()
+
+        def pack_tc_round():
+            for ci, (c, st) in enumerate(zip(tcc, tcs)):
+                with torch.cuda.stream(st):
+                    c.upload_query_ptr(drv.q_host.data_ptr(), st.cuda_stream)
+                    c.expand_and_convert(st.cuda_stream)
+                    evs[ci].record(st)
+            with torch.cuda.stream(tcs[0]):
+                for ci in range(1, nb):
+                    tcs[0].wait_event(evs[ci])
+                PackServer.scan_batched_tc(tcc, tcs[0].cuda_stream)
+                ev_scan.record(tcs[0])
+            for ci, (c, st) in enumerate(zip(tcc, tcs)):
+                with torch.cuda.stream(st):
+                    st.wait_event(ev_scan)
+                    c.fold_local(st.cuda_stream)
+                    c.fold_tail(c.partial_cts_ptr(), resp_devs[ci].data_ptr(), st.cuda_stream)
+                    resp_hosts[ci].copy_(resp_devs[ci], non_blocking=True)
+        for _ in range(2):
+            pack_tc_round()
+        torch.cuda.synchronize()
+        rounds = max(2, args.steps // 4)
+        t0 = time.perf_counter()
+        for _ in range(rounds):
+            pack_tc_round()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        sb0, sb1 = ev(), ev()
+        with torch.cuda.stream(tcs[0]):
+            sb0.record(tcs[0])
+            for _ in range(3):
+                PackServer.scan_batched_tc(tcc, tcs[0].cuda_stream)
+            sb1.record(tcs[0])
+        torch.cuda.synchronize()
+        pass_ms = sb0.elapsed_time(sb1) / 3
+        nq = rounds * nb
+        pipelined = {"tensor_core_batch": {
+            "queries_per_pass": nb, "ms_per_query_amortised": wall_ms / nq, "queries_per_s": nq / (wall_ms * 1e-3),
+            "first_dim_pass_ms": pass_ms, "first_dim_ms_per_query": pass_ms / nb,
+            "db_gbs_per_pass": srv.db_bytes / (pass_ms * 1e-3) / 1e9,
+            "effective_db_gbs_x_queries": srv.db_bytes * nb / (pass_ms * 1e-3) / 1e9,
+            "int8_tensor_tops": 2.0 * 16 * 2 * nb * (srv.db_bytes / 8) * 2 / (pass_ms * 1e-3) / 1e12,
+            "note": "pass = query tiles + k_scan_tc over all planes (tcgen05 kind::i8, u8 limbs) + k_tc_untile; bit-exact (tests/test_gpu_tc.py); host wall clock, H2D/D2H per query included"}}
+        for c in tcc[1:]:
             c.close()
         torch.cuda.set_stream(tstream)
 
@@ -758,6 +879,7 @@ def main():
     ap.add_argument("--nu2", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clients", type=int, default=4, help="N = 1: concurrent clients for the serving-throughput figure (0/1 = skip)")
+    ap.add_argument("--tc-batch", type=int, default=16, help="N = 1, Spiral: queries per tensor-core database pass in the serving-throughput section (0/1 = skip)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the surviving ciphertexts reach rank 0")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -140,6 +140,9 @@ int sb200_convertDb(uint64_t *db_buf, const uint64_t *db_ref_ntt, size_t count, 
 int sb200_reorientCiphertextsDim1(uint64_t *out, const uint64_t *v_firstdim, size_t count, size_t dim0, size_t idx_factor); /* :342-362 */
 int sb200_fastMultiplyQueryByDatabaseDim1(uint64_t *out_ref_ntt, const uint64_t *db, const uint64_t *v_firstdim,
                                           size_t dim0, size_t num_per);                                                   /* :364-593 */
+/* `count` (<= 16) reoriented queries against one plane in ONE tensor-core pass; outputs as fastMultiplyQueryByDatabaseDim1's */
+int sb200_fastMultiplyQueryByDatabaseDim1_batched(uint64_t *const *out_ref_ntt, const uint64_t *db_buf, const uint64_t *const *v_firstdim_reoriented,
+                                                  int count, size_t dim0, size_t num_per);
 /* v_cts: count cts (2x1 raw), result left in v_cts[0]; v_folding / v_folding_neg: log2(count) x (2 x 2*ell) ref-NTT */
 int sb200_foldCiphertextsDim1(uint64_t *v_cts, size_t count, const uint64_t *v_folding, const uint64_t *v_folding_neg, uint32_t ell); /* :596-624 */
 int sb200_regevToSimpleGsw(uint64_t *v_gsw, const uint64_t *v_inp, size_t count_inp, const uint64_t *V, uint32_t t_conv,
@@ -230,6 +233,10 @@ int sb200_pack_server_upload_query(sb200_pack_server *srv, const uint64_t *query
 int sb200_pack_server_expand_and_convert(sb200_pack_server *srv, void *stream);   /* coefficientExpansion + reorientCiphertextsDim1 + regevToSimpleGsw */
 int sb200_pack_server_upload_direct(sb200_pack_server *srv, const uint64_t *v_firstdim_host, const uint64_t *v_folding_host, void *stream);
 int sb200_pack_server_scan(sb200_pack_server *srv, void *stream);                 /* fastMultiplyQueryByDatabaseDim1, all planes (src/testing.cpp:364) */
+/* several clients over one resident set of planes, and their first dimensions in ONE tensor-core pass (as sb200_server_*_tc) */
+int sb200_pack_server_create_view(sb200_pack_server **out, sb200_pack_server *parent);
+int sb200_pack_server_enable_tc(sb200_pack_server *srv, int capacity);     /* needs dim0 and num_per (per shard) multiples of 128 */
+int sb200_pack_server_scan_batched_tc(sb200_pack_server *const *servers, int count, void *stream);
 /* interposed fastMultiplyQueryByDatabaseDim1 against ONE resident plane: host reoriented query in, ref-NTT host cts out */
 int sb200_pack_server_scan_plane_host(sb200_pack_server *srv, size_t plane, const uint64_t *v_firstdim_host, uint64_t *out_ref_ntt_host);
 int sb200_pack_server_fold_local(sb200_pack_server *srv, void *stream);           /* from_ntt + local fold rounds: out_n^2 surviving cts */

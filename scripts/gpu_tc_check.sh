@@ -1,8 +1,8 @@
 set -x
-( time timeout 600 python -m pytest tests/test_gpu_tc.py -x -q ) > gpurun_out/tc_pytest.log 2>&1; tail -5 gpurun_out/tc_pytest.log
-nvidia-smi --query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap --format=csv -lms 100 > gpurun_out/tc_clocks.csv &
-SMI=$!
-TC_COUNTS=1,4,8,10,12,16 TC_ITERS=20 timeout 300 python scripts/bench_tc.py > gpurun_out/tc_bench_sustained.log 2>&1; tail -7 gpurun_out/tc_bench_sustained.log
-kill $SMI
-sort gpurun_out/tc_clocks.csv | uniq -c | sort -rn | head -8
-TC_COUNTS=16 TC_ITERS=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scan_tc -s 2 -c 1 -o gpurun_out/tc_scan_full python scripts/bench_tc.py > gpurun_out/tc_ncu.log 2>&1; tail -3 gpurun_out/tc_ncu.log
+( time timeout 900 python -m pytest tests/test_gpu_tc.py -x -q ) > gpurun_out/tc_pytest.log 2>&1; tail -12 gpurun_out/tc_pytest.log
+TC_COUNTS=1,8,16 TC_ITERS=10 timeout 300 python scripts/bench_tc.py > gpurun_out/tc_bench.log 2>&1; tail -4 gpurun_out/tc_bench.log | cut -c1-400
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/tc_bench_cfg1.json 2> gpurun_out/tc_bench_cfg1.err; tail -3 gpurun_out/tc_bench_cfg1.err; python -c "
+import json; d=json.load(open('gpurun_out/tc_bench_cfg1.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac']); print(json.dumps(d.get('pipelined',{}).get('tensor_core_batch'), indent=1))"
+timeout 900 python bench.py --workload cfg3 --no-cpu-baseline --steps 8 > gpurun_out/tc_bench_cfg3.json 2> gpurun_out/tc_bench_cfg3.err; tail -3 gpurun_out/tc_bench_cfg3.err; python -c "
+import json; d=json.load(open('gpurun_out/tc_bench_cfg3.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['stages_ms']); print(json.dumps(d.get('pipelined',{}).get('tensor_core_batch'), indent=1))"
+nvidia-smi --query-gpu=memory.used --format=csv

@@ -767,13 +767,13 @@ extern "C" int sb200_server_scan_batched_tc(sb200_server *const *servers, int co
     sb200_server *owner = const_cast<sb200_server *>(s0->db_owner ? s0->db_owner : s0);
     if (!owner->tc_capacity) return fail(SB200_ERR_STATE, "scan_batched_tc: call sb200_server_enable_tc on the database owner first");
     if (count > owner->tc_capacity) return fail(SB200_ERR_ARG, "scan_batched_tc: %d queries exceed the enabled capacity %d", count, owner->tc_capacity);
-    uint32_t *o[16];
+    uint32_t *o[16]; const uint64_t *qs[16];
     cudaStream_t st = ES(s0, stream);
     for (int b = 0; b < count; b++) {
         if (!servers[b] || server_db(servers[b]) != owner->db.p) return fail(SB200_ERR_ARG, "scan_batched_tc: servers must share one database");
-        launch_query_to_tc(owner->q_tc.p, servers[b]->query.p, b, owner->tc_capacity, owner->dim0, st);
-        o[b] = servers[b]->scan_out.p;
+        qs[b] = servers[b]->query.p; o[b] = servers[b]->scan_out.p;
     }
+    launch_queries_to_tc(owner->q_tc.p, qs, count, 0, owner->tc_capacity, owner->dim0, st);
     if (launch_scan_tc(o, count, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, owner->dim0, owner->local_num_per, owner->tc_t1.p, st))
         return fail(SB200_ERR_CUDA, "scan_batched_tc: launch failed");
     CHECK_LAUNCH();

@@ -132,7 +132,11 @@ struct sb200_pack_server {
     int maxcnt = 0, tmax = 0;
     bool have_params = false;
     std::vector<bool> plane_loaded;
+    const sb200_pack_server *db_owner = nullptr;        // views (sb200_pack_server_create_view) scan another server's resident planes
     DBuf<uint64_t> db;
+    DBuf<uint8_t> db_tc, q_tc;                          // tensor-core path (sb200_pack_server_enable_tc)
+    DBuf<uint32_t> tc_t1;
+    int tc_capacity = 0;
     DBuf<uint32_t> W_left, W_right, V, vW, neg1;
     DBuf<uint64_t> stage;
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch, packed;
@@ -144,8 +148,12 @@ struct sb200_pack_server {
     ~sb200_pack_server() { if (own_stream) cudaStreamDestroy(own_stream); }
 };
 static inline cudaStream_t PS(sb200_pack_server *s, void *stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
+static inline const sb200_pack_server *pack_owner(const sb200_pack_server *s) { return s->db_owner ? s->db_owner : s; }
+static inline const uint64_t *pack_db(const sb200_pack_server *s) { return pack_owner(s)->db.p; }
+static inline bool pack_plane_loaded(const sb200_pack_server *s, size_t p) { return pack_owner(s)->plane_loaded[p]; }
+static inline TcGeom pack_geom(const sb200_pack_server *s) { return tc_geom_pack(s->dim0, s->local_num_per, s->planes, s->local_num_per * 2); }
 
-extern "C" int sb200_pack_server_create_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world) {
+static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world, const sb200_pack_server *parent) {
     if (!out || !prm) return fail(SB200_ERR_ARG, "pack_server_create: null argument");
     if (prm->out_n == 0 || prm->nu1 < 1) return fail(SB200_ERR_ARG, "pack_server_create: out_n >= 1 and nu1 >= 1 required");
     if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(SB200_ERR_ARG, "pack_server_create: world must be a power of two and 0 <= rank < world");
@@ -170,7 +178,7 @@ extern "C" int sb200_pack_server_create_sharded(sb200_pack_server **out, const s
     const size_t ncts = std::max((size_t)1 << s->g, s->dim0 + nbits), rows = prm->out_n + 1;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    A(s->db.alloc(s->planes * s->plane_words));
+    if (parent) s->db_owner = parent; else A(s->db.alloc(s->planes * s->plane_words));
     A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc((s->stopround + 1) * 2 * prm->t_exp_right * PLW));
     A(s->V.alloc(2 * 2 * prm->t_conv * PLW)); A(s->vW.alloc(prm->out_n * rows * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
     A(s->stage.alloc((size_t)1024 * PLW));
@@ -205,6 +213,15 @@ extern "C" int sb200_pack_server_create_sharded(sb200_pack_server **out, const s
     *out = s;
     return SB200_OK;
 }
+extern "C" int sb200_pack_server_create_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world) {
+    return pack_server_create_impl(out, prm, device, rank, world, nullptr);
+}
+// A second query context (own keys, scratch, stream) over the parent's resident planes: one per concurrent client.
+extern "C" int sb200_pack_server_create_view(sb200_pack_server **out, sb200_pack_server *parent) {
+    if (!out || !parent) return fail(SB200_ERR_ARG, "pack create_view: null argument");
+    const sb200_pack_server *owner = pack_owner(parent);
+    return pack_server_create_impl(out, &owner->prm, owner->device, owner->rank, owner->world, owner);
+}
 extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device) {
     return sb200_pack_server_create_sharded(out, prm, device, 0, 1);
 }
@@ -213,6 +230,7 @@ extern "C" void sb200_pack_server_destroy(sb200_pack_server *s) { delete s; }
 // pts: this shard's items of the plane, j-major: item = j * local_num_per + ii_local (ii = rank + world * ii_local)
 extern "C" int sb200_pack_server_load_plane_items(sb200_pack_server *s, size_t plane, const uint16_t *pts) {
     if (!s || !pts || plane >= s->planes) return fail(SB200_ERR_ARG, "load_plane_items: bad argument");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
     CU(cudaSetDevice(s->device));
     const size_t items = s->dim0 * s->local_num_per;
     DBuf<uint16_t> d(items * kN);
@@ -225,6 +243,7 @@ extern "C" int sb200_pack_server_load_plane_items(sb200_pack_server *s, size_t p
 // db_buf: the WHOLE plane in the reference's convertDb layout db_buf[z][ii][j]; the shard's rows ii = rank (mod world) are taken
 extern "C" int sb200_pack_server_load_plane_reference(sb200_pack_server *s, size_t plane, const uint64_t *db_buf) {
     if (!s || !db_buf || plane >= s->planes) return fail(SB200_ERR_ARG, "load_plane_reference: bad argument");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
     CU(cudaSetDevice(s->device));
     const size_t zc = 64, row = s->local_num_per * s->dim0;
     DBuf<uint64_t> stage(zc * row);
@@ -246,6 +265,7 @@ extern "C" int sb200_pack_server_load_plane_reference(sb200_pack_server *s, size
 // (centre-lift, CRT, NTT, scan layout) - a 64 GiB cfg3 database is built in well under a second of GPU time
 extern "C" int sb200_pack_server_load_random(sb200_pack_server *s, uint64_t seed) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
     CU(cudaSetDevice(s->device));
     const size_t items = s->dim0 * s->local_num_per, n4 = items * kN / 4;
     DBuf<uint16_t> d;
@@ -319,17 +339,17 @@ extern "C" int sb200_pack_server_upload_direct(sb200_pack_server *s, const uint6
 // fastMultiplyQueryByDatabaseDim1 for all out_n^2 planes of the shard in one launch (src/testing.cpp:1045-1052)
 extern "C" int sb200_pack_server_scan(sb200_pack_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    for (size_t p = 0; p < s->planes; p++) if (!s->plane_loaded[p]) return fail(SB200_ERR_STATE, "pack scan: database plane %zu not loaded", p);
-    launch_scan_pack(s->scan_out.p, s->query.p, s->db.p, s->dim0, s->local_num_per, s->planes, s->plane_words, s->local_num_per * 2, PS(s, stream));
+    for (size_t p = 0; p < s->planes; p++) if (!pack_plane_loaded(s, p)) return fail(SB200_ERR_STATE, "pack scan: database plane %zu not loaded", p);
+    launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s), s->dim0, s->local_num_per, s->planes, s->plane_words, s->local_num_per * 2, PS(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
 }
 // interposed fastMultiplyQueryByDatabaseDim1 on ONE resident plane: host reoriented query in, ref-NTT host ciphertexts out
 extern "C" int sb200_pack_server_scan_plane_host(sb200_pack_server *s, size_t plane, const uint64_t *v_firstdim_host, uint64_t *out_ref_ntt_host) {
     if (!s || !v_firstdim_host || !out_ref_ntt_host || plane >= s->planes) return fail(SB200_ERR_ARG, "pack scan_plane_host: bad argument");
-    if (!s->plane_loaded[plane]) return fail(SB200_ERR_STATE, "pack scan_plane_host: database plane %zu not loaded", plane);
+    if (!pack_plane_loaded(s, plane)) return fail(SB200_ERR_STATE, "pack scan_plane_host: database plane %zu not loaded", plane);
     CU(cudaMemcpy(s->query.p, v_firstdim_host, s->dim0 * 2 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    launch_scan_pack(s->scan_out.p, s->query.p, s->db.p + plane * s->plane_words, s->dim0, s->local_num_per, 1, s->plane_words, s->local_num_per * 2, 0);
+    launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s) + plane * s->plane_words, s->dim0, s->local_num_per, 1, s->plane_words, s->local_num_per * 2, 0);
     CHECK_LAUNCH();
     return down_ntt(out_ref_ntt_host, s->scan_out.p, s->local_num_per * 2);
 }
@@ -343,6 +363,75 @@ static void pack_fold_rounds(sb200_pack_server *s, uint64_t *cts, size_t count, 
                                   nullptr, s->fold_scratch.p, st);            // CMux form, no negated GSW needed
         cur++;
     }
+}
+// ---- tensor-core batched first dimension (tc_scan.cu): fastMultiplyQueryByDatabaseDim1 of every plane for up to 16 clients
+// in ONE pass over the planes.  Needs dim0 and num_per (per shard) to be multiples of 128 (SpiralPack shapes; SpiralStreamPack's
+// 8-column planes cannot fill a 128-row MMA tile and keep the streaming kernel).
+extern "C" int sb200_pack_server_enable_tc(sb200_pack_server *s, int capacity) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "pack enable_tc: call it on the server that owns the database");
+    for (size_t p = 0; p < s->planes; p++) if (!s->plane_loaded[p]) return fail(SB200_ERR_STATE, "pack enable_tc: database plane %zu not loaded", p);
+    if (capacity < 1 || capacity > 16) return fail(SB200_ERR_ARG, "pack enable_tc: capacity must be in [1, 16]");
+    const TcGeom g = pack_geom(s);
+    if (!tc_geom_ok(g)) return fail(SB200_ERR_ARG, "pack enable_tc: needs dim0 and num_per (per shard) to be multiples of 128");
+    if (tc_scratch_bytes_g(g, capacity) / 4 > 0xffffffffull) return fail(SB200_ERR_ARG, "pack enable_tc: capacity too large for this shape");
+    CU(cudaSetDevice(s->device));
+    if (!s->db_tc.p) {
+        CU(s->db_tc.alloc(tc_db_bytes_g(g)));
+        launch_db_to_tc_g(s->db_tc.p, s->db.p, g, s->plane_words, s->own_stream); CHECK_LAUNCH();
+    }
+    if (s->q_tc.p) { cudaFree(s->q_tc.p); s->q_tc.p = nullptr; }
+    if (s->tc_t1.p) { cudaFree(s->tc_t1.p); s->tc_t1.p = nullptr; }
+    CU(s->tc_t1.alloc(tc_scratch_bytes_g(g, capacity) / 4));
+    CU(s->q_tc.alloc(tc_query_bytes_g(g, capacity)));
+    CU(cudaMemsetAsync(s->q_tc.p, 0, s->q_tc.n, s->own_stream));
+    CU(cudaStreamSynchronize(s->own_stream));
+    s->tc_capacity = capacity;
+    return SB200_OK;
+}
+extern "C" int sb200_pack_server_scan_batched_tc(sb200_pack_server *const *servers, int count, void *stream) {
+    if (!servers || count < 1 || !servers[0]) return fail(SB200_ERR_ARG, "pack scan_batched_tc: no servers");
+    sb200_pack_server *s0 = servers[0];
+    sb200_pack_server *owner = const_cast<sb200_pack_server *>(pack_owner(s0));
+    if (!owner->tc_capacity) return fail(SB200_ERR_STATE, "pack scan_batched_tc: call sb200_pack_server_enable_tc on the database owner first");
+    if (count > owner->tc_capacity) return fail(SB200_ERR_ARG, "pack scan_batched_tc: %d queries exceed the enabled capacity %d", count, owner->tc_capacity);
+    uint32_t *o[16]; const uint64_t *qs[16];
+    for (int b = 0; b < count; b++) {
+        if (!servers[b] || pack_owner(servers[b]) != owner) return fail(SB200_ERR_ARG, "pack scan_batched_tc: servers must share one database");
+        qs[b] = servers[b]->query.p; o[b] = servers[b]->scan_out.p;
+    }
+    cudaStream_t st = PS(s0, stream);
+    const TcGeom g = pack_geom(owner);
+    launch_queries_to_tc_g(owner->q_tc.p, qs, count, 0, owner->tc_capacity, g, st);
+    if (launch_scan_tc_g(o, count, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, g, owner->tc_t1.p, st))
+        return fail(SB200_ERR_CUDA, "pack scan_batched_tc: launch failed");
+    CHECK_LAUNCH();
+    return SB200_OK;
+}
+// `count` reoriented queries (reorientCiphertextsDim1 layout) against ONE plane in the reference's convertDb layout, one pass
+extern "C" int sb200_fastMultiplyQueryByDatabaseDim1_batched(uint64_t *const *out, const uint64_t *db, const uint64_t *const *v_firstdim,
+                                                             int count, size_t dim0, size_t num_per) {
+    NEED_DEVICE();
+    if (!out || !db || !v_firstdim || count < 1 || count > 16) return fail(SB200_ERR_ARG, "fastMultiplyQueryByDatabaseDim1_batched: 1 <= count <= 16");
+    const TcGeom g = tc_geom_pack(dim0, num_per, 1, num_per * 2);
+    if (!tc_geom_ok(g)) return fail(SB200_ERR_ARG, "fastMultiplyQueryByDatabaseDim1_batched: needs dim0 and num_per to be multiples of 128");
+    const size_t words = dim0 * num_per * kN, qwords = dim0 * 2 * kN;
+    DBuf<uint64_t> dq((size_t)count * qwords), dref(words), ddb(words); DBuf<uint8_t> dtc(tc_db_bytes_g(g)), qtc(tc_query_bytes_g(g, count));
+    DBuf<uint32_t> dout((size_t)count * num_per * 2 * PLW), dt1(tc_scratch_bytes_g(g, count) / 4);
+    CU(dref.up(db, words));
+    launch_db_from_reference(ddb.p, dref.p, dim0 / 2, num_per, 0, kN, 0); CHECK_LAUNCH();
+    launch_db_to_tc_g(dtc.p, ddb.p, g, words, 0); CHECK_LAUNCH();
+    CU(cudaMemset(qtc.p, 0, qtc.n));
+    uint32_t *o[16]; const uint64_t *qs[16];
+    for (int b = 0; b < count; b++) {
+        CU(cudaMemcpy(dq.p + (size_t)b * qwords, v_firstdim[b], qwords * 8, cudaMemcpyHostToDevice));
+        qs[b] = dq.p + (size_t)b * qwords; o[b] = dout.p + (size_t)b * num_per * 2 * PLW;
+    }
+    launch_queries_to_tc_g(qtc.p, qs, count, 0, count, g, 0); CHECK_LAUNCH();
+    if (launch_scan_tc_g(o, count, count, qtc.p, dtc.p, g, dt1.p, 0)) return fail(SB200_ERR_CUDA, "fastMultiplyQueryByDatabaseDim1_batched: launch failed");
+    CHECK_LAUNCH();
+    for (int b = 0; b < count; b++) TRY(down_ntt(out[b], o[b], num_per * 2));
+    return SB200_OK;
 }
 // from_ntt of every scan output + the local fold rounds (src/testing.cpp:1055-1058); leaves `planes` surviving cts
 extern "C" int sb200_pack_server_fold_local(sb200_pack_server *s, void *stream) {

@@ -67,10 +67,25 @@ int launch_scan_spiral_batched(uint32_t *const *out, const uint64_t *const *quer
                                size_t num_per, cudaStream_t s);   // count in {2,4}: queries sharing one database pass
 
 // ---- batched first dimension on tcgen05 tensor cores (tc_scan.cu): up to 16 queries per database pass
+// generic geometry: K = bytes of k per database row (Spiral 2*dim0, Pack dim0), IC = database columns (Spiral 2*num_per, Pack num_per),
+// RQ = ciphertext rows per query (3 / 2), planes (Pack: out_n^2), kstride = PB64 words between consecutive k in the reoriented query
+struct TcGeom { size_t K, IC; int RQ; size_t planes, out_plane_polys, kstride; };
+TcGeom tc_geom_spiral(size_t dim0, size_t num_per);
+TcGeom tc_geom_pack(size_t dim0, size_t num_per, size_t planes, size_t out_plane_polys);
+int tc_geom_ok(const TcGeom &g);                                      // K and IC multiples of 128
+size_t tc_db_bytes_g(const TcGeom &g);
+size_t tc_query_bytes_g(const TcGeom &g, int capacity);
+size_t tc_scratch_bytes_g(const TcGeom &g, int count);
+void launch_db_to_tc_g(uint8_t *db_tc, const uint64_t *db, const TcGeom &g, size_t src_plane_words, cudaStream_t s);
+void launch_queries_to_tc_g(uint8_t *q_tc, const uint64_t *const *queries, int count, int first_slot, int capacity, const TcGeom &g, cudaStream_t s);
+int launch_scan_tc_g(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, const TcGeom &g,
+                     uint32_t *scratch, cudaStream_t s);
+// Spiral-shaped wrappers
 int tc_shape_ok(size_t dim0, size_t num_per);                       // needs 2*dim0 % 128 == 0 and 2*num_per % 128 == 0
 size_t tc_query_bytes(size_t dim0, int capacity);                   // Q_tc bytes for a batch of up to `capacity` queries
 void launch_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s);   // scan layout -> DB_tc (same size)
 void launch_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, cudaStream_t s);
+void launch_queries_to_tc(uint8_t *q_tc, const uint64_t *const *queries, int count, int first_slot, int capacity, size_t dim0, cudaStream_t s);
 size_t tc_scratch_bytes(size_t num_per, int count);                 // tile-order results of one pass, before the transpose
 int launch_scan_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, size_t dim0, size_t num_per,
                    uint32_t *scratch, cudaStream_t s);

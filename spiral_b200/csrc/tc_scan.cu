@@ -109,18 +109,17 @@ __host__ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk)
 
 // sum_w 2^(8w) T_w  mod q from the seven weight accumulators of one output (T_w < 2^28): the powers 2^32, 2^40, 2^48 are
 // replaced by their residues so the whole sum stays below 2^59, then one Barrett step with floor(2^59/q) on the top 32 bits.
-// Results go to the tile-order buffer T1[q][n][z][r][ic]: the 32 lanes of a warp own 32 consecutive ic, so every store
+// Results go to the tile-order buffer T1[q][g][r][ic], g = (plane*2048 + z)*2 + n: the 32 lanes of a warp own 32 consecutive ic, so every store
 // instruction writes one full 128-byte line (the reference order [i][r][c][n][z] would be 32 separate 4-byte sectors).
-template <int CB>
-__device__ __forceinline__ void epilogue_store(uint32_t *__restrict__ t1, int count, uint32_t IC, const uint32_t (&v)[7][16], uint32_t off, int n) {
+template <int CB, int RQ>
+__device__ __forceinline__ void epilogue_store(uint32_t *__restrict__ t1, int count, uint32_t IC, uint32_t sq, const uint32_t (&v)[7][16], uint32_t off, int n) {
     constexpr uint32_t c4p = (uint32_t)((1ull << 32) % kP), c5p = (uint32_t)((1ull << 40) % kP), c6p = (uint32_t)((1ull << 48) % kP);
     constexpr uint32_t c4b = (uint32_t)((1ull << 32) % kB), c5b = (uint32_t)((1ull << 40) % kB), c6b = (uint32_t)((1ull << 48) % kB);
     constexpr uint32_t mup = (uint32_t)((1ull << 59) / kP), mub = (uint32_t)((1ull << 59) / kB);
     const uint32_t c4 = n ? c4b : c4p, c5 = n ? c5b : c5p, c6 = n ? c6b : c6p, mu = n ? mub : mup, q = n ? kB : kP;
-    const uint32_t sq = 2u * kN * 3u * IC;                              // words per query in T1
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int col = CB * 16 + e, qi = col / 3, r = col - 3 * qi;
+        const int col = CB * 16 + e, qi = col / RQ, r = col - RQ * qi;
         if (qi < count) {
             uint64_t x = (uint64_t)v[0][e] + ((uint64_t)v[1][e] << 8) + ((uint64_t)v[2][e] << 16) + ((uint64_t)v[3][e] << 24);
             x += (uint64_t)v[4][e] * c4 + (uint64_t)v[5][e] * c5 + (uint64_t)v[6][e] * c6;
@@ -128,31 +127,42 @@ __device__ __forceinline__ void epilogue_store(uint32_t *__restrict__ t1, int co
             uint32_t res = (uint32_t)x - qhat * q;                  // true remainder + at most 3q  (< 2^30)
             res = min(res, res - 2 * q);
             res = min(res, res - q);
-            t1[(size_t)(off + (uint32_t)qi * sq + (uint32_t)r * IC)] = res;
+            t1[(size_t)(off + (uint32_t)qi * sq + (uint32_t)r * IC)] = res;     // host checks that T1 has < 2^32 words
         }
     }
 }
 
-// T1[q][n][z][r][ic] -> dev-NTT out_q[i][r][c][n][z] (ic = 2i + c): 32 x 32 shared-memory transpose, 128-byte lines both ways
-__global__ void __launch_bounds__(256) k_tc_untile(const __grid_constant__ OutPtrs outs, const uint32_t *__restrict__ t1, int IC) {
+// T1[q][g][r][ic] -> dev-NTT outputs: 32 x 32 shared-memory transpose, 128-byte lines both ways.
+//   Spiral (RQ = 3): out_q[i][r][c][n][z] with ic = 2i + c           (multiplyQueryByDatabase's output order)
+//   Pack   (RQ = 2): out_q[plane][i = ic][r][n][z]                   (fastMultiplyQueryByDatabaseDim1's 2x1 MatPolys)
+template <int RQ>
+__global__ void __launch_bounds__(256) k_tc_untile(const __grid_constant__ OutPtrs outs, const uint32_t *__restrict__ t1, int IC, int planes,
+                                                   size_t out_plane_polys) {
     pdl_prologue();
     __shared__ uint32_t tile[32][33];
     const int z0 = blockIdx.x * 32, ic0 = blockIdx.y * 32;
-    const int r = blockIdx.z % 3, n = (blockIdx.z / 3) & 1, q = blockIdx.z / 6;
+    int bz = blockIdx.z;
+    const int r = bz % RQ; bz /= RQ;
+    const int n = bz & 1; bz >>= 1;
+    const int plane = bz % planes, q = bz / planes;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const uint32_t *src = t1 + (((size_t)(q * 2 + n) * kN + z0) * 3 + r) * IC + ic0;
+    const size_t sq = (size_t)planes * 2 * kN * RQ * IC;
+    const uint32_t *src = t1 + (size_t)q * sq + ((((size_t)plane * kN + z0) * 2 + n) * RQ + r) * IC + ic0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) tile[ty + 8 * k][tx] = __ldg(src + (size_t)(ty + 8 * k) * 3 * IC + tx);
+    for (int k = 0; k < 4; k++) tile[ty + 8 * k][tx] = __ldg(src + (size_t)(ty + 8 * k) * 2 * RQ * IC + tx);
     __syncthreads();
     uint32_t *dst = outs.out[q];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int ic = ic0 + ty + 8 * k, i = ic >> 1, c = ic & 1;
-        dst[((((size_t)i * kN1 + r) * kN2 + c) * 2 + n) * kN + z0 + tx] = tile[tx][ty + 8 * k];
+        const int ic = ic0 + ty + 8 * k;
+        size_t poly;
+        if (RQ == 3) { const int i = ic >> 1, c = ic & 1; poly = ((size_t)i * kN1 + r) * kN2 + c; }
+        else         poly = (size_t)plane * out_plane_polys + (size_t)ic * 2 + r;
+        dst[(poly * 2 + n) * kN + z0 + tx] = tile[tx][ty + 8 * k];
     }
 }
 
-template <int NB>
+template <int NB, int RQ>
 __global__ void __launch_bounds__(64 + 8 * NB, 1) k_scan_tc(uint32_t *__restrict__ t1, int count, const uint8_t *__restrict__ q_tc,
                                                          const uint8_t *__restrict__ db_tc, int KC, int MT, int n_items) {
     using S = Shape<NB>;
@@ -188,7 +198,7 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) k_scan_tc(uint32_t *__restrict
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             if (lane == 0) {
                 const uint8_t *asrc = db_tc + (size_t)it * KC * 4 * kATile;
-                const uint8_t *bsrc = q_tc + (size_t)(it / MT) * KC * S::kBTile;
+                const uint8_t *bsrc = q_tc + (size_t)((it / MT) % (2 * kN)) * KC * S::kBTile;   // every plane scans the same query tiles
                 for (int kc = 0; kc < KC; kc++) {
                     mbar_wait(b_empty + 8 * bs, bph ^ 1);
                     mbar_expect_tx(b_full + 8 * bs, S::kBTile);
@@ -246,9 +256,10 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) k_scan_tc(uint32_t *__restrict
         const int row = quarter * 32 + lane;
         uint32_t tph = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int mt = it % MT, zn = it / MT, n = zn & 1, z = zn >> 1;
+            const int mt = it % MT, g = it / MT, n = g & 1;          // g = (plane*2048 + z)*2 + n
             const uint32_t IC = (uint32_t)MT * kM;
-            const uint32_t off = ((uint32_t)(n * kN + z) * 3u) * IC + (uint32_t)(mt * kM + row);   // T1 word index of (q = 0, r = 0)
+            const uint32_t sq = (uint32_t)(n_items / MT) * RQ * IC;  // T1 words per query
+            const uint32_t off = ((uint32_t)g * RQ) * IC + (uint32_t)(mt * kM + row);   // T1 word index of (q = 0, r = 0)
             mbar_wait(t_full, tph);
             tc_fence_after();
             const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -258,9 +269,9 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) k_scan_tc(uint32_t *__restrict
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(t_empty);                                   // accumulators are in registers: the next item may start
-            if (cb == 0)      epilogue_store<0>(t1, count, IC, v, off, n);
-            else if (cb == 1) epilogue_store<1>(t1, count, IC, v, off, n);
-            else              epilogue_store<2>(t1, count, IC, v, off, n);
+            if (cb == 0)      epilogue_store<0, RQ>(t1, count, IC, sq, v, off, n);
+            else if (cb == 1) epilogue_store<1, RQ>(t1, count, IC, sq, v, off, n);
+            else              epilogue_store<2, RQ>(t1, count, IC, sq, v, off, n);
             tph ^= 1;
         }
     }
@@ -302,20 +313,24 @@ __global__ void __launch_bounds__(256) k_db_to_tc(uint8_t *__restrict__ db_tc, c
         }
 }
 
-// ---- queries: reoriented PB64 query[z][j][m][4] (reorientCiphertexts layout) of query q -> its 3 x 4 rows of every Q_tc tile.
-// One thread per (z, kc, 16-byte chunk, r): 8 j x 2 m residues under both primes -> 8 chunks (n, b).
+// ---- queries -> their RQ x 4 rows of every Q_tc tile.  Source: PB64 words query[z][k][kstride] with the RQ ciphertext rows
+// first (Spiral: reorientCiphertexts layout [z][j][m][4], k = 2j + m, kstride 4;  Pack: reorientCiphertextsDim1 layout
+// [z][j][2], k = j, kstride 2).  One thread per (z, kc, 16-byte chunk, r): 16 k's under both primes -> 8 chunks (n, b).
+struct QueryPtrs { const uint64_t *query[kMaxBatch]; int first_slot; };
 template <int NB>
-__global__ void __launch_bounds__(256) k_query_to_tc(uint8_t *__restrict__ q_tc, const uint64_t *__restrict__ query, int q, int dim0) {
+__global__ void __launch_bounds__(256) k_query_to_tc(uint8_t *__restrict__ q_tc, const __grid_constant__ QueryPtrs qp, int K, int kstride, int RQ) {
     using S = Shape<NB>;
     pdl_prologue();
-    const int KC = dim0 * 2 / kKB;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           // ((z*KC + kc)*8 + chunk)*3 + r
-    if (idx >= (size_t)kN * KC * 8 * 3) return;
-    const int r = (int)(idx % 3), chunk = (int)((idx / 3) & 7), kc = (int)((idx / 24) % KC), z = (int)(idx / 24 / KC);
-    uint64_t e[16];                                                              // k = kc*128 + chunk*16 + t, t = 2*jj + m
-    const uint64_t *src = query + (((size_t)z * dim0 + kc * 64 + chunk * 8) * 2) * 4 + r;
+    const int KC = K / kKB;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           // ((z*KC + kc)*8 + chunk)*RQ + r
+    if (idx >= (size_t)kN * KC * 8 * RQ) return;
+    const int q = qp.first_slot + blockIdx.y;
+    const uint64_t *__restrict__ query = qp.query[blockIdx.y];
+    const int r = (int)(idx % RQ), chunk = (int)((idx / RQ) & 7), kc = (int)((idx / RQ / 8) % KC), z = (int)(idx / RQ / 8 / KC);
+    uint64_t e[16];
+    const uint64_t *src = query + ((size_t)z * K + kc * kKB + chunk * 16) * kstride + r;
 #pragma unroll
-    for (int t = 0; t < 16; t++) e[t] = src[(size_t)t * 4];
+    for (int t = 0; t < 16; t++) e[t] = __ldg(src + (size_t)t * kstride);
 #pragma unroll
     for (int n = 0; n < 2; n++)
 #pragma unroll
@@ -329,74 +344,110 @@ __global__ void __launch_bounds__(256) k_query_to_tc(uint8_t *__restrict__ q_tc,
                 w[g] = acc;
             }
             uint8_t *tile = q_tc + (((size_t)z * 2 + n) * KC + kc) * (size_t)S::kBTile;
-            *reinterpret_cast<uint4 *>(tile + sw128(b * NB + 3 * q + r, chunk)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(tile + sw128(b * NB + RQ * q + r, chunk)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
 }
 
-inline int nb_for(int count) { return count <= 5 ? 16 : count <= 10 ? 32 : 48; }
+inline int nb_for(int rows) { return rows <= 16 ? 16 : rows <= 32 ? 32 : 48; }      // accumulator block width for `rows` = RQ * capacity
 
 }  // namespace tc
 
-size_t tc_query_bytes(size_t dim0, int capacity) { return (size_t)kN * 2 * (dim0 * 2 / tc::kKB) * 4 * tc::nb_for(capacity) * tc::kKB; }
+// ---- geometry of one tensor-core scan: K bytes of k per row, IC database columns, RQ ciphertext rows per query
+TcGeom tc_geom_spiral(size_t dim0, size_t num_per) { return TcGeom{dim0 * 2, num_per * 2, 3, 1, 0, 4}; }
+TcGeom tc_geom_pack(size_t dim0, size_t num_per, size_t planes, size_t out_plane_polys) { return TcGeom{dim0, num_per, 2, planes, out_plane_polys, 2}; }
+int tc_geom_ok(const TcGeom &g) { return g.K >= (size_t)tc::kKB && g.K % tc::kKB == 0 && g.IC >= (size_t)tc::kM && g.IC % tc::kM == 0 && g.planes >= 1; }
+size_t tc_db_bytes_g(const TcGeom &g) { return g.planes * (size_t)kN * 2 * g.IC * g.K * 4; }
+size_t tc_query_bytes_g(const TcGeom &g, int capacity) { return (size_t)kN * 2 * (g.K / tc::kKB) * 4 * tc::nb_for(g.RQ * capacity) * tc::kKB; }
+size_t tc_scratch_bytes_g(const TcGeom &g, int count) { return (size_t)count * g.planes * 2 * kN * g.RQ * g.IC * sizeof(uint32_t); }
 
-int tc_shape_ok(size_t dim0, size_t num_per) { return (dim0 * 2) % tc::kKB == 0 && (num_per * 2) % tc::kM == 0; }
-
-void launch_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
-    const size_t IC = num_per * 2, n = (size_t)kN * (dim0 * 2 / tc::kKB) * 8 * IC;
-    count_launch();
-    tc::k_db_to_tc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(db_tc, reinterpret_cast<const uint4 *>(db), (int)dim0, (int)IC);
-}
-
-// capacity fixes the tile shape (NB); q < capacity
-void launch_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, cudaStream_t s) {
-    const size_t n = (size_t)kN * (dim0 * 2 / tc::kKB) * 8 * 3;
-    const dim3 grid((unsigned)((n + 255) / 256));
-    count_launch();
-    switch (tc::nb_for(capacity)) {
-        case 16: launch_pdl(tc::k_query_to_tc<16>, grid, dim3(256), 0, s, q_tc, query, q, (int)dim0); break;
-        case 32: launch_pdl(tc::k_query_to_tc<32>, grid, dim3(256), 0, s, q_tc, query, q, (int)dim0); break;
-        default: launch_pdl(tc::k_query_to_tc<48>, grid, dim3(256), 0, s, q_tc, query, q, (int)dim0); break;
+// src_plane_words: u64 words between consecutive planes of the scan-layout source (16-byte pairs of consecutive k per column)
+void launch_db_to_tc_g(uint8_t *db_tc, const uint64_t *db, const TcGeom &g, size_t src_plane_words, cudaStream_t s) {
+    const size_t n = (size_t)kN * (g.K / tc::kKB) * 8 * g.IC, plane_bytes = (size_t)kN * 2 * g.IC * g.K * 4;
+    for (size_t p = 0; p < g.planes; p++) {
+        count_launch();
+        tc::k_db_to_tc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(db_tc + p * plane_bytes, reinterpret_cast<const uint4 *>(db + p * src_plane_words),
+                                                                   (int)(g.K / 2), (int)g.IC);
     }
 }
 
-size_t tc_scratch_bytes(size_t num_per, int count) { return (size_t)count * 2 * kN * 3 * (num_per * 2) * sizeof(uint32_t); }
+// capacity fixes the tile shape (NB); queries[b] goes to batch slot first_slot + b (< capacity); one launch for all of them
+void launch_queries_to_tc_g(uint8_t *q_tc, const uint64_t *const *queries, int count, int first_slot, int capacity, const TcGeom &g, cudaStream_t s) {
+    const size_t n = (size_t)kN * (g.K / tc::kKB) * 8 * g.RQ;
+    const dim3 grid((unsigned)((n + 255) / 256), (unsigned)count);
+    tc::QueryPtrs qp;
+    for (int b = 0; b < tc::kMaxBatch; b++) qp.query[b] = b < count ? queries[b] : nullptr;
+    qp.first_slot = first_slot;
+    count_launch();
+    switch (tc::nb_for(g.RQ * capacity)) {
+        case 16: launch_pdl(tc::k_query_to_tc<16>, grid, dim3(256), 0, s, q_tc, qp, (int)g.K, (int)g.kstride, g.RQ); break;
+        case 32: launch_pdl(tc::k_query_to_tc<32>, grid, dim3(256), 0, s, q_tc, qp, (int)g.K, (int)g.kstride, g.RQ); break;
+        default: launch_pdl(tc::k_query_to_tc<48>, grid, dim3(256), 0, s, q_tc, qp, (int)g.K, (int)g.kstride, g.RQ); break;
+    }
+}
 
-template <int NB>
-static int launch_scan_tc_nb(uint32_t *t1, int count, const uint8_t *q_tc, const uint8_t *db_tc, int KC, int MT, cudaStream_t s) {
+template <int NB, int RQ>
+static int launch_scan_tc_nb(uint32_t *t1, int count, const uint8_t *q_tc, const uint8_t *db_tc, int KC, int MT, size_t groups, cudaStream_t s) {
     static int sms = 0;
     static bool attr = false;
     if (!attr) {
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(tc::k_scan_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Shape<NB>::kSmem) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(tc::k_scan_tc<NB, RQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Shape<NB>::kSmem) != cudaSuccess) return -2;
         attr = true;
     }
-    const int n_items = kN * 2 * MT;
+    const size_t items = groups * MT;
+    if (items > 0x7fffffffull) return -1;
+    const int n_items = (int)items;
     const int grid = n_items < sms ? n_items : sms;
     count_launch();
-    launch_pdl(tc::k_scan_tc<NB>, dim3(grid), dim3(64 + 8 * NB), tc::Shape<NB>::kSmem, s, t1, count, q_tc, db_tc, KC, MT, n_items);
+    launch_pdl(tc::k_scan_tc<NB, RQ>, dim3(grid), dim3(64 + 8 * NB), tc::Shape<NB>::kSmem, s, t1, count, q_tc, db_tc, KC, MT, n_items);
     return 0;
 }
 
-// out[q]: dev-NTT [i][r][c] like launch_scan_spiral; count <= capacity <= 16; q_tc built with the same capacity;
-// scratch: tc_scratch_bytes(num_per, count) bytes for the tile-order results before the transpose
-int launch_scan_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, size_t dim0, size_t num_per,
-                   uint32_t *scratch, cudaStream_t s) {
-    if (count < 1 || count > capacity || capacity > tc::kMaxBatch || !tc_shape_ok(dim0, num_per) || !scratch) return -1;
+// out[q]: device outputs in the order of the single-query scans (launch_scan_spiral / launch_scan_pack); count <= capacity <= 16;
+// q_tc built with the same capacity; scratch: tc_scratch_bytes_g(g, count) bytes for the tile-order results before the transpose
+int launch_scan_tc_g(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, const TcGeom &g,
+                     uint32_t *scratch, cudaStream_t s) {
+    if (count < 1 || count > capacity || capacity > tc::kMaxBatch || !tc_geom_ok(g) || !scratch) return -1;
+    if (tc_scratch_bytes_g(g, count) / 4 > 0xffffffffull) return -1;          // the kernels index T1 with 32-bit words
     tc::OutPtrs o;
     for (int b = 0; b < tc::kMaxBatch; b++) o.out[b] = b < count ? out[b] : nullptr;
     o.count = count;
-    const int KC = (int)(dim0 * 2 / tc::kKB), MT = (int)(num_per * 2 / tc::kM);
+    const int KC = (int)(g.K / tc::kKB), MT = (int)(g.IC / tc::kM);
+    const size_t groups = g.planes * 2 * kN;
     int rc;
-    switch (tc::nb_for(capacity)) {
-        case 16: rc = launch_scan_tc_nb<16>(scratch, count, q_tc, db_tc, KC, MT, s); break;
-        case 32: rc = launch_scan_tc_nb<32>(scratch, count, q_tc, db_tc, KC, MT, s); break;
-        default: rc = launch_scan_tc_nb<48>(scratch, count, q_tc, db_tc, KC, MT, s); break;
+    if (g.RQ == 3) switch (tc::nb_for(3 * capacity)) {
+        case 16: rc = launch_scan_tc_nb<16, 3>(scratch, count, q_tc, db_tc, KC, MT, groups, s); break;
+        case 32: rc = launch_scan_tc_nb<32, 3>(scratch, count, q_tc, db_tc, KC, MT, groups, s); break;
+        default: rc = launch_scan_tc_nb<48, 3>(scratch, count, q_tc, db_tc, KC, MT, groups, s); break;
+    } else switch (tc::nb_for(2 * capacity)) {
+        case 16: rc = launch_scan_tc_nb<16, 2>(scratch, count, q_tc, db_tc, KC, MT, groups, s); break;
+        default: rc = launch_scan_tc_nb<32, 2>(scratch, count, q_tc, db_tc, KC, MT, groups, s); break;
     }
     if (rc) return rc;
     count_launch();
-    launch_pdl(tc::k_tc_untile, dim3(kN / 32, (unsigned)(num_per * 2 / 32), (unsigned)(count * 6)), dim3(256), 0, s, o, (const uint32_t *)scratch, (int)(num_per * 2));
+    const dim3 grid(kN / 32, (unsigned)(g.IC / 32), (unsigned)(count * g.planes * 2 * g.RQ));
+    if (g.RQ == 3) launch_pdl(tc::k_tc_untile<3>, grid, dim3(256), 0, s, o, (const uint32_t *)scratch, (int)g.IC, (int)g.planes, g.out_plane_polys);
+    else           launch_pdl(tc::k_tc_untile<2>, grid, dim3(256), 0, s, o, (const uint32_t *)scratch, (int)g.IC, (int)g.planes, g.out_plane_polys);
     return 0;
+}
+
+// ---- Spiral-shaped wrappers (dim0, num_per)
+int tc_shape_ok(size_t dim0, size_t num_per) { return tc_geom_ok(tc_geom_spiral(dim0, num_per)); }
+size_t tc_query_bytes(size_t dim0, int capacity) { return tc_query_bytes_g(tc_geom_spiral(dim0, 64), capacity); }
+size_t tc_scratch_bytes(size_t num_per, int count) { return tc_scratch_bytes_g(tc_geom_spiral(64, num_per), count); }
+void launch_db_to_tc(uint8_t *db_tc, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
+    launch_db_to_tc_g(db_tc, db, tc_geom_spiral(dim0, num_per), 0, s);
+}
+void launch_queries_to_tc(uint8_t *q_tc, const uint64_t *const *queries, int count, int first_slot, int capacity, size_t dim0, cudaStream_t s) {
+    launch_queries_to_tc_g(q_tc, queries, count, first_slot, capacity, tc_geom_spiral(dim0, 64), s);
+}
+void launch_query_to_tc(uint8_t *q_tc, const uint64_t *query, int q, int capacity, size_t dim0, cudaStream_t s) {
+    launch_queries_to_tc(q_tc, &query, 1, q, capacity, dim0, s);
+}
+int launch_scan_tc(uint32_t *const *out, int count, int capacity, const uint8_t *q_tc, const uint8_t *db_tc, size_t dim0, size_t num_per,
+                   uint32_t *scratch, cudaStream_t s) {
+    return launch_scan_tc_g(out, count, capacity, q_tc, db_tc, tc_geom_spiral(dim0, num_per), scratch, s);
 }
 
 }  // namespace sb200

@@ -167,7 +167,7 @@ class PackServer:
     out_n^2 database planes of 1x1 plaintexts, 2x1 Regev ciphertexts, one packed (out_n+1) x out_n response.
     Sharded like SpiralServer: rank g owns the second-dimension indices ii = g (mod world) of every plane."""
 
-    def __init__(self, params: SpiralParams, device=0, rank=0, world=1):
+    def __init__(self, params: SpiralParams, device=0, rank=0, world=1, _view_of=None):
         self.lib = load_library()
         self.params = params
         self.rank, self.world = rank, world
@@ -175,8 +175,25 @@ class PackServer:
         self.local_num_per = self.num_per // world
         self.planes = params.out_n * params.out_n
         h = C.c_void_p()
-        check(self.lib.sb200_pack_server_create_sharded(C.byref(h), C.byref(params), device, rank, world), self.lib)
+        if _view_of is None:
+            check(self.lib.sb200_pack_server_create_sharded(C.byref(h), C.byref(params), device, rank, world), self.lib)
+        else:
+            check(self.lib.sb200_pack_server_create_view(C.byref(h), _view_of.h), self.lib)
         self.h = h
+        self._parent = _view_of                    # keeps the database owner alive
+
+    def view(self):
+        """A second client context (own keys, scratch) over this server's resident planes."""
+        return PackServer(self.params, rank=self.rank, world=self.world, _view_of=self)
+
+    def enable_tc(self, capacity=16):
+        check(self.lib.sb200_pack_server_enable_tc(self.h, capacity), self.lib)
+
+    @staticmethod
+    def scan_batched_tc(servers, stream=None):
+        """One tcgen05 pass over all planes for up to 16 pack servers sharing them (enable_tc on the owner first)."""
+        arr = (C.c_void_p * len(servers))(*[s.h for s in servers])
+        check(servers[0].lib.sb200_pack_server_scan_batched_tc(arr, len(servers), stream), servers[0].lib)
 
     # ---- database -----------------------------------------------------------------------
     def shard_items(self, plane_pts):

@@ -94,6 +94,7 @@ def load():
     lib.so_pack_answer.argtypes = [C.POINTER(SoParams), C.c_int] + [u64p] * 10
     lib.so_pack_expansion_shape.argtypes = [C.POINTER(SoParams), C.POINTER(sz), C.POINTER(sz)]
     lib.so_convert_db.argtypes = [u64p, u64p, sz, sz, sz]
+    lib.so_fast_multiply_dim1.argtypes = [u64p, u64p, u64p, sz, sz]
     lib.so_encode_plaintext.argtypes = [u64p, u64p, sz, C.c_uint64]
     lib.so_modswitch_coeff.restype = C.c_uint64
     lib.so_modswitch_coeff.argtypes = [C.c_uint64, C.c_uint64]

@@ -123,3 +123,77 @@ def test_tc_server_batch_answers_every_client(sb, oracle):
         s_.close()
     for ses in sessions:
         ses.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SpiralPack shape: 2x1 ciphertexts, 1x1 plaintexts, planes (fastMultiplyQueryByDatabaseDim1, src/testing.cpp:364-593)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("count", [1, 8, 16])           # tile shapes NB = 16, 16, 32 (two rows per query)
+def test_tc_batched_pack_first_dim_matches_oracle(sb, oracle, count):
+    dim0, num_per = 128, 128
+    rng = np.random.default_rng(2000 + count)
+    db = rnd_pb(rng, (N, num_per, dim0))                 # convertDb layout db_buf[z][ii][j]  (src/testing.cpp:316-340)
+    db[:, 0, :] = np.uint64((ol.P - 1) | ((ol.B - 1) << 32))
+    db = np.ascontiguousarray(db.reshape(-1))
+    queries = []
+    for b in range(count):
+        q = rnd_pb(rng, (N, dim0, 2))                    # reorientCiphertextsDim1 layout [z][j][r]
+        if b == count - 1:
+            q[:, :, 1] = np.uint64((ol.P - 1) | ((ol.B - 1) << 32))
+        queries.append(np.ascontiguousarray(q.reshape(-1)))
+    words = num_per * 2 * 2 * N
+    outs = [np.zeros(words, dtype=np.uint64) for _ in range(count)]
+    rc = sb.sb200_fastMultiplyQueryByDatabaseDim1_batched((P64 * count)(*[o.ctypes.data_as(P64) for o in outs]), db.ctypes.data_as(P64),
+                                                          (P64 * count)(*[q.ctypes.data_as(P64) for q in queries]), count, dim0, num_per)
+    assert rc == 0, sb.sb200_last_error().decode()
+    for b in range(count):
+        want = np.zeros(words, dtype=np.uint64)
+        oracle.so_fast_multiply_dim1(ol.ptr(want), ol.ptr(db), ol.ptr(queries[b]), dim0, num_per)
+        bad = np.nonzero(outs[b] != want)[0]
+        assert bad.size == 0, f"query {b} of {count}: {bad.size} of {want.size} words differ, first at {bad[:5]}"
+
+
+def test_tc_pack_server_batch_equals_single_query_path(sb):
+    """Resident SpiralPack server (out_n = 2: four planes): 5 clients with their own keys share the planes; one tensor-core
+    pass over all planes replaces their five scans; every packed response equals the single-query path's bit for bit."""
+    import torch
+    from spiral_b200.server import PackServer
+    nu1, nu2, count = 7, 7, 5
+    prm = SpiralParams(nu1, nu2, 8, 4, 8, 56, 20, 2, 256)
+    rng = np.random.default_rng(99)
+
+    def rnd_ntt(npolys):
+        a = np.empty((npolys, 2, N), dtype=np.uint64)
+        a[:, 0, :] = rng.integers(0, ol.P, size=(npolys, N), dtype=np.uint64)
+        a[:, 1, :] = rng.integers(0, ol.B, size=(npolys, N), dtype=np.uint64)
+        return np.ascontiguousarray(a.reshape(-1))
+    srv = PackServer(prm)
+    srv.load_random(7)
+    with pytest.raises(SB200Error, match="enable_tc"):
+        PackServer.scan_batched_tc([srv])
+    srv.enable_tc(count)
+    servers = [srv] + [srv.view() for _ in range(count - 1)]
+    nbits = 8 * nu2
+    g = int(np.ceil(np.log2(nbits + (1 << nu1))))
+    stop = int(np.ceil(np.log2(nbits)))
+    queries, want = [], []
+    for s_ in servers:
+        s_.set_public_params(rnd_ntt(g * 2 * 8), rnd_ntt((stop + 1) * 2 * 56), rnd_ntt(2 * 2 * 4), rnd_ntt(2 * 3 * 4))
+        queries.append(rnd_ntt(2))
+        want.append(s_.answer(queries[-1]))                        # single-query path (k_scan_pack)
+    assert len({w.tobytes() for w in want}) == count
+    with pytest.raises(SB200Error, match="view"):
+        servers[1].load_random(3)
+    for s_, q in zip(servers, queries):
+        s_.upload_query_ptr(q.ctypes.data); s_.expand_and_convert()
+    torch.cuda.synchronize()
+    PackServer.scan_batched_tc(servers)
+    torch.cuda.synchronize()
+    resp = [torch.empty(srv.response_words, dtype=torch.int64, device="cuda") for _ in range(count)]
+    for k, s_ in enumerate(servers):
+        s_.fold_local(); s_.fold_tail(s_.partial_cts_ptr(), resp[k].data_ptr())
+    torch.cuda.synchronize()
+    for k in range(count):
+        assert np.array_equal(resp[k].cpu().numpy().view(np.uint64), want[k]), f"client {k}"
+    for s_ in reversed(servers):
+        s_.close()
