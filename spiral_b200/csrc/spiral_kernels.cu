@@ -369,6 +369,13 @@ __device__ __forceinline__ uint32_t signed_digit_res(uint64_t val, const SignedD
     if (p.bits_per <= 27) return wrapped ? (uint32_t)piece + q - (1u << p.bits_per) : (uint32_t)piece;
     return raw_to_res(wrapped ? piece + kQ - (1ull << p.bits_per) : piece, n);
 }
+// the same digit as a small signed integer (bits_per <= 27): piece, or piece - 2^bp where the reference adds Q - 2^bp
+__device__ __forceinline__ int32_t signed_digit_small(uint64_t val, const SignedDigitPlan &p) {
+    const uint64_t carry = (((val >> p.off0) & p.lowmask) + p.K) >> p.lowbits;
+    const uint64_t piece = ((val >> p.offk) & p.mask) + (p.lowbits ? carry : 0);
+    const bool wrapped = piece > p.half && p.guard;
+    return wrapped ? (int32_t)piece - (int32_t)(1u << p.bits_per) : (int32_t)piece;
+}
 // Generic over the ciphertext shape so the Pack variant (foldCiphertextsDim1, src/testing.cpp:596-624:
 // 2x1 ciphertexts, UNSIGNED gadget_invert digits, out_n^2 planes batched) shares the kernels:
 //   R x Cc ciphertext, GSW is R x (R*t), digit k of input row r lands in row r + k*R.
@@ -400,8 +407,49 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
             v[e] = fs.is_signed ? signed_digit_res(val, plan, q, n)
                                 : (bits_per <= 29 ? (uint32_t)gadget_digit(val, k, bits_per, mask) : raw_to_res(gadget_digit(val, k, bits_per, mask), n));
         }
+    } else if (bits_per <= 27) {
+        // CMux form: ctl < np is the LOW ciphertext i, its partner is np + i; one NTT of the digit difference.
+        // A digit is a small integer s (|s| <= 2^bp; the reference's "s + Q" for negative digits is s modulo both primes),
+        // so the difference s_hi - s_lo is the same small integer under both primes: each prime plane extracts HALF of the
+        // coefficients and the halves meet in shared memory.  When a digit and the carry chain below it live in one 32-bit
+        // word of the coefficient (t * bp = 64 with word-aligned halves, e.g. t_GSW = 8) the extraction is 32-bit arithmetic.
+        __shared__ int32_t dsm[kN];
+        const uint64_t *hi = src + (size_t)fs.np * RC * kN;
+        const int half_elems = fs.t / 2;
+        const bool word32 = fs.is_signed ? (bits_per * (uint32_t)half_elems == 32u)
+                                         : ((uint32_t)k * bits_per / 32u == ((uint32_t)(k + 1) * bits_per - 1u) / 32u && (uint32_t)(k + 1) * bits_per <= 64u);
+        if (word32) {
+            const int wsel = fs.is_signed ? (k >= half_elems) : (int)((uint32_t)k * bits_per / 32u);
+            const uint32_t sh = fs.is_signed ? plan.lowbits : ((uint32_t)k * bits_per) & 31u;
+            const uint32_t m32 = (uint32_t)mask, K32 = (uint32_t)plan.K, lm32 = (uint32_t)plan.lowmask, half32 = (uint32_t)plan.half;
+            const uint32_t *lo32 = reinterpret_cast<const uint32_t *>(src) + wsel, *hi32 = reinterpret_cast<const uint32_t *>(hi) + wsel;
+#pragma unroll
+            for (int e8 = 0; e8 < 8; e8++) {
+                const int idx = nat_pos(lt, 8 * n + e8);
+                const uint32_t a = __ldg(lo32 + 2 * idx), b = __ldg(hi32 + 2 * idx);
+                int32_t sa, sb;
+                if (fs.is_signed) {
+                    const uint32_t pa = ((a >> sh) & m32) + (((a & lm32) + K32) >> sh), pb = ((b >> sh) & m32) + (((b & lm32) + K32) >> sh);
+                    sa = (pa > half32 && plan.guard) ? (int32_t)pa - (int32_t)(1u << bits_per) : (int32_t)pa;
+                    sb = (pb > half32 && plan.guard) ? (int32_t)pb - (int32_t)(1u << bits_per) : (int32_t)pb;
+                } else { sa = (int32_t)((a >> sh) & m32); sb = (int32_t)((b >> sh) & m32); }
+                dsm[idx] = sb - sa;
+            }
+        } else {
+#pragma unroll
+            for (int e8 = 0; e8 < 8; e8++) {
+                const int idx = nat_pos(lt, 8 * n + e8);
+                const uint64_t a = __ldg(src + idx), b = __ldg(hi + idx);
+                int32_t sa, sb;
+                if (fs.is_signed) { sa = signed_digit_small(a, plan); sb = signed_digit_small(b, plan); }
+                else { sa = (int32_t)gadget_digit(a, k, bits_per, mask); sb = (int32_t)gadget_digit(b, k, bits_per, mask); }
+                dsm[idx] = sb - sa;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 16; e++) v[e] = (uint32_t)(dsm[nat_pos(lt, e)] + (int32_t)(2 * q));   // in (0, 4q): a valid lazy NTT input
     } else {
-        // CMux form: ctl < np is the LOW ciphertext i, its partner is np + i; one NTT of the digit difference
         const uint64_t *hi = src + (size_t)fs.np * RC * kN;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
