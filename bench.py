@@ -769,7 +769,7 @@ def b200_main(args):
     if world == 1 and args.tc_batch > 1 and wl["kind"] == "pack" and not wl["direct"] and drv.srv.dim0 % 128 == 0 and drv.srv.num_per % 128 == 0:
         from spiral_b200.server import PackServer
         srv = drv.srv
-        nb = min(args.tc_batch, 16 if srv.db_bytes <= (32 << 30) else 8)      # cfg3: 64 GiB planes + 64 GiB limb tiles + 8 client contexts
+        nb = min(args.tc_batch, 16)      # cfg3: 64 GiB planes + 64 GiB limb tiles + 16 client contexts of ~1.2 GB fit the 180 GB
         srv.enable_tc(nb)
         tcc = [srv] + [srv.view() for _ in range(nb - 1)]
         for c in tcc[1:]:

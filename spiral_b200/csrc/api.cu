@@ -561,7 +561,7 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc(n_right * 2 * prm->t_exp_right * PLW));
     A(s->W_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->V_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
     A(s->q_stage.alloc(2 * PLW)); A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW));
-    A(s->ginv.alloc((size_t)s->maxcnt * s->tmax * PLW)); A(s->c0.alloc((size_t)s->maxcnt * kN));
+    A(s->ginv.alloc(expand_ginv_polys(s->plan, s->cnt.data()) * PLW)); A(s->c0.alloc((size_t)s->maxcnt * kN));
     A(s->conv_raw.alloc(conv_cols * kN)); A(s->conv_ntt.alloc(conv_cols * prm->t_conv * PLW));
     A(s->gsw.alloc(prm->nu2 * 3 * m2 * PLW));
     A(s->query.alloc(s->dim0 * 2 * 4 * kN)); A(s->scan_out.alloc(s->local_num_per * 6 * PLW));

@@ -105,6 +105,7 @@ void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t coun
 struct ExpandPlan { int g, t_left, t_right, stopround, max_bits_right; };
 size_t expand_active_total(const ExpandPlan &p);
 int expand_build_lists(const ExpandPlan &p, int *list, int *offs, int *cnt);   // host arrays; returns max count
+size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt);                 // polynomials of digit scratch (ginv) launch_expand needs
 // cv: dev-NTT [2^g][2]; W_left: [g][2][t_left]; W_right: [g or stopround+1][2][t_right]; neg1: [g] polys
 // c0_raw: maxcnt*2048 u64; c1_ntt: maxcnt polys; ginv: maxcnt*max(t) polys; list_dev: device copy of list
 void build_automorph_perms(uint16_t *perm_host, int g);      // host: g x 2048 slot permutations (one per round)

@@ -217,6 +217,17 @@ void build_automorph_perms(uint16_t *perm_host, int g) {
     }
 }
 
+// polynomials the digit scratch must hold: max over rounds of (active ciphertexts x digits per slot of that round)
+size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt) {
+    const int tmax = p.t_left > p.t_right ? p.t_left : p.t_right;
+    size_t need = 1;
+    for (int r = 0; r < p.g; r++) {
+        const bool any_odd = !(p.stopround > 0 && r > p.stopround);
+        const size_t polys = (size_t)cnt[r] * (any_odd ? tmax : p.t_left);
+        if (polys > need) need = polys;
+    }
+    return need;
+}
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
                    const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
                    const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end) {
@@ -232,8 +243,9 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         const bool any_odd = !(p.stopround > 0 && r > p.stopround);
         const int ty = any_odd ? tmax : p.t_left;
         count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
-        count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, tmax);
-        count_launch(); launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, tmax);
+        // ginv is indexed [slot][ty]: rounds past stopround only hold t_left digits per slot (see expand_ginv_polys)
+        count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty);
+        count_launch(); launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
     }
 }
 
