@@ -52,10 +52,12 @@ def test_tc_batched_first_dim_matches_oracle(sb, oracle, count):
         assert bad.size == 0, f"query {b} of {count}: {bad.size} of {want.size} words differ, first at {bad[:5]}: got {got[bad[:5]]} want {want[bad[:5]]}"
 
 
-def test_tc_scan_equals_single_query_scan_kernel(sb):
-    """Device-pointer tier: k_scan_tc against k_scan_spiral on the same resident database, two k-chunks, two column tiles."""
+@pytest.mark.parametrize("count", [5, 16])
+def test_tc_scan_equals_single_query_scan_kernel(sb, count):
+    """Device-pointer tier: k_scan_tc against k_scan_spiral on the same resident database, two k-chunks, two column tiles
+    (count 5: 16-column accumulator blocks, count 16: 48-column blocks)."""
     import torch
-    dim0, num_per, count = 128, 128, 5
+    dim0, num_per = 128, 128
     rng = np.random.default_rng(31)
     nu1, nu2 = 7, 7
     db_words = sb.sb200_db_words(nu1, nu2)
