@@ -386,12 +386,14 @@ struct FoldShape {
     int plane_stride;    // ciphertexts between consecutive planes in `cts`
     int cmux;            // 1: resident path, C_lo + Q (x) (G^-1(C_hi) - G^-1(C_lo)); 0: the reference's two-product form
 };
-__global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, FoldShape fs, int cts_per_plane) {
+__global__ void __launch_bounds__(kNttThreads, 5) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, FoldShape fs, int cts_per_plane) {
     pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const int RC = fs.R * fs.Cc;
-    const int ctpoly = blockIdx.x, k = blockIdx.y;          // ctpoly = (plane*cts_per_plane + ct)*RC + r*Cc + c
+    // 1-D grid with the digit index fastest: the t CTAs that decompose the same polynomial run back to back, so all but the
+    // first find it in L2 (with k slowest the re-reads were DRAM traffic: 8x the ciphertext bytes at SpiralPack sizes)
+    const int ctpoly = (int)(blockIdx.x / (unsigned)fs.t), k = (int)(blockIdx.x % (unsigned)fs.t);   // ctpoly = (plane*cts_per_plane + ct)*RC + r*Cc + c
     const int ctd = ctpoly / RC, rc = ctpoly % RC, r = rc / fs.Cc, c = rc % fs.Cc;
     const int plane = ctd / cts_per_plane, ctl = ctd % cts_per_plane;
     const uint32_t bits_per = get_bits_per(fs.t);
@@ -423,10 +425,13 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
             const uint32_t sh = fs.is_signed ? plan.lowbits : ((uint32_t)k * bits_per) & 31u;
             const uint32_t m32 = (uint32_t)mask, K32 = (uint32_t)plan.K, lm32 = (uint32_t)plan.lowmask, half32 = (uint32_t)plan.half;
             const uint32_t *lo32 = reinterpret_cast<const uint32_t *>(src) + wsel, *hi32 = reinterpret_cast<const uint32_t *>(hi) + wsel;
+            uint32_t av[8], bv[8];                       // all 16 loads in flight before the first use
+#pragma unroll
+            for (int e8 = 0; e8 < 8; e8++) { const int idx = nat_pos(lt, 8 * n + e8); av[e8] = __ldg(lo32 + 2 * idx); bv[e8] = __ldg(hi32 + 2 * idx); }
 #pragma unroll
             for (int e8 = 0; e8 < 8; e8++) {
                 const int idx = nat_pos(lt, 8 * n + e8);
-                const uint32_t a = __ldg(lo32 + 2 * idx), b = __ldg(hi32 + 2 * idx);
+                const uint32_t a = av[e8], b = bv[e8];
                 int32_t sa, sb;
                 if (fs.is_signed) {
                     const uint32_t pa = ((a >> sh) & m32) + (((a & lm32) + K32) >> sh), pb = ((b >> sh) & m32) + (((b & lm32) + K32) >> sh);
@@ -436,10 +441,13 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_decomp_ntt(uint32_t *__res
                 dsm[idx] = sb - sa;
             }
         } else {
+            uint64_t av[8], bv[8];
+#pragma unroll
+            for (int e8 = 0; e8 < 8; e8++) { const int idx = nat_pos(lt, 8 * n + e8); av[e8] = __ldg(src + idx); bv[e8] = __ldg(hi + idx); }
 #pragma unroll
             for (int e8 = 0; e8 < 8; e8++) {
                 const int idx = nat_pos(lt, 8 * n + e8);
-                const uint64_t a = __ldg(src + idx), b = __ldg(hi + idx);
+                const uint64_t a = av[e8], b = bv[e8];
                 int32_t sa, sb;
                 if (fs.is_signed) { sa = signed_digit_small(a, plan); sb = signed_digit_small(b, plan); }
                 else { sa = (int32_t)gadget_digit(a, k, bits_per, mask); sb = (int32_t)gadget_digit(b, k, bits_per, mask); }
@@ -530,6 +538,36 @@ __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, co
             make_uint4(reduce_u64(acc[0], n), reduce_u64(acc[1], n), reduce_u64(acc[2], n), reduce_u64(acc[3], n));
     }
 }
+// Throughput variant for rounds with many outputs (CMux form only): CTA = 256 uint4 columns, every thread walks all m2
+// terms of its column, so there is no partial-sum exchange and one Barrett reduction per output word instead of eight.
+__global__ void __launch_bounds__(256) k_fold_mac_wide(uint32_t *__restrict__ out, const uint32_t *__restrict__ scratch,
+                                                       const uint32_t *__restrict__ q_dev, FoldShape fs) {
+    pdl_prologue();
+    const int RC = fs.R * fs.Cc;
+    const int op = blockIdx.x >> 2, seg = blockIdx.x & 3;
+    const int id = op / RC, rc = op % RC, r = rc / fs.Cc, c = rc % fs.Cc;
+    const int m2 = fs.R * fs.t;
+    const int w4 = seg * 256 + threadIdx.x, n = w4 >= 512;
+    const size_t qs = 2 * kN / 4, cs = (size_t)fs.Cc * 2 * kN / 4;
+    const uint4 *Qp = reinterpret_cast<const uint4 *>(q_dev + (size_t)r * m2 * 2 * kN) + w4;
+    const uint4 *Cd = reinterpret_cast<const uint4 *>(scratch + (((size_t)id * m2) * fs.Cc + c) * 2 * kN) + w4;   // id = plane*np + i
+    uint64_t acc[4] = {0, 0, 0, 0};
+    for (int m0 = 0; m0 < m2; m0 += 96) {                    // 96 products of < 2^56 stay below 2^63
+        const int m1 = m0 + 96 < m2 ? m0 + 96 : m2;
+#pragma unroll 8
+        for (int m = m0; m < m1; m++) {
+            const uint4 x = __ldg(Qp + m * qs), y = __ldg(Cd + m * cs);
+            acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
+            acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
+        }
+        if (m1 < m2) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
+        }
+    }
+    reinterpret_cast<uint4 *>(out + (size_t)op * 2 * kN)[w4] =
+        make_uint4(reduce_u64(acc[0], n), reduce_u64(acc[1], n), reduce_u64(acc[2], n), reduce_u64(acc[3], n));
+}
 // inverse NTT + CRT lift of the dense MAC outputs back into the (strided) ciphertext array
 __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict__ cts, const uint32_t *__restrict__ macout, FoldShape fs) {
     pdl_prologue();
@@ -569,9 +607,12 @@ void launch_fold_round_generic(uint64_t *cts, int R, int Cc, int t, int is_signe
     const int cmux = qneg_dev == nullptr;
     FoldShape fs{R, Cc, t, is_signed, (int)np_after, (int)planes, (int)plane_stride, cmux};
     const int RC = R * Cc, cpp = (int)((cmux ? 1 : 2) * np_after);
-    count_launch(); launch_pdl(k_fold_decomp_ntt, dim3(dim3((unsigned)(planes * cpp * RC), t)), dim3(kNttThreads), 0, s, scratch, cts, fs, cpp);
+    count_launch(); launch_pdl(k_fold_decomp_ntt, dim3((unsigned)(planes * cpp * RC * t)), dim3(kNttThreads), 0, s, scratch, cts, fs, cpp);
     uint32_t *macout = scratch + (size_t)planes * cpp * R * t * Cc * 2 * kN;
-    count_launch(); launch_pdl(k_fold_mac, dim3((unsigned)(planes * np_after * RC * 16)), dim3(256), 0, s, macout, scratch, q_dev, qneg_dev, fs);
+    const size_t outputs = planes * np_after * RC;
+    count_launch();
+    if (cmux && outputs >= 384) launch_pdl(k_fold_mac_wide, dim3((unsigned)(outputs * 4)), dim3(256), 0, s, macout, (const uint32_t *)scratch, q_dev, fs);
+    else launch_pdl(k_fold_mac, dim3((unsigned)(outputs * 16)), dim3(256), 0, s, macout, scratch, q_dev, qneg_dev, fs);
     count_launch(); launch_pdl(k_fold_lift, dim3((unsigned)(planes * np_after * RC)), dim3(kNttThreads), 0, s, cts, macout, fs);
 }
 // reference reorient_Q layout (packed [z][r*m2 + m], src/spiral.cpp:388-400) -> dev-NTT [r*m2 + m][n][z]
@@ -595,7 +636,7 @@ size_t fold_scratch_words(size_t num_per_half, int t_gsw) { return fold_scratch_
 // split_and_crt alone (reference src/spiral.cpp:270-341) on `count` ciphertexts: scratch[ct][m][c] dev-NTT
 void launch_fold_decomp_only(uint32_t *scratch, const uint64_t *cts, size_t count, int t_gsw, cudaStream_t s) {
     FoldShape fs{kN1, kN2, t_gsw, 1, (int)count, 1, (int)count, 0};
-    if (count) { count_launch(); launch_pdl(k_fold_decomp_ntt, dim3(dim3((unsigned)(count * 6), t_gsw)), dim3(kNttThreads), 0, s, scratch, cts, fs, (int)count); }
+    if (count) { count_launch(); launch_pdl(k_fold_decomp_ntt, dim3((unsigned)(count * 6 * t_gsw)), dim3(kNttThreads), 0, s, scratch, cts, fs, (int)count); }
 }
 void launch_fold_round(uint64_t *cts, size_t num_per, const uint32_t *q_dev, const uint32_t *qneg_dev,
                        int t_gsw, uint32_t *scratch, cudaStream_t s) {
