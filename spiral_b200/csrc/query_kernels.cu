@@ -138,6 +138,33 @@ __global__ void __launch_bounds__(256) k_expand_accum(uint32_t *__restrict__ cv,
     *dst = o;
 }
 
+// Throughput variant for rounds with many active ciphertexts: CTA = 256 uint4 columns of one slot, every thread walks all
+// digits of its column for BOTH rows, so each digit word is loaded once (not once per row) and there is no partial-sum exchange.
+__global__ void __launch_bounds__(256) k_expand_accum_wide(uint32_t *__restrict__ cv, const int *__restrict__ active, const uint32_t *__restrict__ ginv,
+                                                           const uint32_t *__restrict__ c1_ntt, const uint32_t *__restrict__ W_left,
+                                                           const uint32_t *__restrict__ W_right, int t_left, int t_right, int tmax) {
+    pdl_prologue();
+    const int slot = blockIdx.x, seg = blockIdx.y, i = active[slot];
+    const int w4 = seg * 256 + threadIdx.x, n = w4 >= 512;
+    const int gd = (i & 1) ? t_right : t_left;
+    const size_t ps = 2 * kN / 4;                                     // uint4 per polynomial
+    const uint4 *W0 = reinterpret_cast<const uint4 *>((i & 1) ? W_right : W_left) + w4;
+    const uint4 *W1 = W0 + (size_t)gd * ps;
+    const uint4 *G = reinterpret_cast<const uint4 *>(ginv + (size_t)slot * tmax * 2 * kN) + w4;
+    uint64_t a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int k = 0; k < gd; k++) {                                    // gd <= 56 products of < 2^56: no intermediate reduction
+        const uint4 y = __ldg(G + (size_t)k * ps), x0 = __ldg(W0 + (size_t)k * ps), x1 = __ldg(W1 + (size_t)k * ps);
+        a0[0] += (uint64_t)x0.x * y.x; a0[1] += (uint64_t)x0.y * y.y; a0[2] += (uint64_t)x0.z * y.z; a0[3] += (uint64_t)x0.w * y.w;
+        a1[0] += (uint64_t)x1.x * y.x; a1[1] += (uint64_t)x1.y * y.y; a1[2] += (uint64_t)x1.z * y.z; a1[3] += (uint64_t)x1.w * y.w;
+    }
+    uint4 *d0 = reinterpret_cast<uint4 *>(cv + ((size_t)i * 2 + 0) * 2 * kN) + w4, *d1 = d0 + ps;
+    const uint4 c0 = *d0, c1 = *d1, add = __ldg(reinterpret_cast<const uint4 *>(c1_ntt + (size_t)slot * 2 * kN) + w4);
+    *d0 = make_uint4(reduce_u64(a0[0] + c0.x, n), reduce_u64(a0[1] + c0.y, n), reduce_u64(a0[2] + c0.z, n), reduce_u64(a0[3] + c0.w, n));
+    *d1 = make_uint4(reduce_u64(a1[0] + c1.x + add.x, n), reduce_u64(a1[1] + c1.y + add.y, n), reduce_u64(a1[2] + c1.z + add.z, n),
+                     reduce_u64(a1[3] + c1.w + add.w, n));
+}
+
 // neg1[r] = NTT(invert(x^(N - 2^r))) = NTT(-x^(N-2^r))   (reference src/spiral.cpp:184-192)
 __global__ void __launch_bounds__(kNttThreads) k_build_neg1(uint32_t *__restrict__ neg1) {
     pdl_prologue();
@@ -245,7 +272,9 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
         // ginv is indexed [slot][ty]: rounds past stopround only hold t_left digits per slot (see expand_ginv_polys)
         count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty);
-        count_launch(); launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
+        count_launch();
+        if (cnt[r] >= 64 && tmax <= 128) launch_pdl(k_expand_accum_wide, dim3(dim3(cnt[r], 4)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
+        else launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
     }
 }
 
@@ -322,6 +351,61 @@ __global__ void k_scal_to_mat_accum(uint64_t *__restrict__ query, const uint32_t
         ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(query + (((size_t)z * dim0 + j) * 2 + c) * 4);
         dst[0] = make_ulonglong2(w[0], w[1]);
         dst[1] = make_ulonglong2(w[2], w[3]);
+    }
+}
+// The same, tiled: CTA = 32 z x 8 j.  Operands are read with z across the lanes (coalesced), results go through shared memory
+// and leave with j across the lanes: 512 contiguous bytes per z instead of 64-byte pieces 16 KiB apart (the scattered form spent
+// its time in the store path: 2 M sixteen-byte stores to 2 M different sectors).
+__global__ void __launch_bounds__(256) k_scal_to_mat_accum_tiled(uint64_t *__restrict__ query, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
+                                                                 const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int t_conv, int dim0) {
+    pdl_prologue();
+    constexpr int kRowWords = 8 * 8 + 1;                              // 8 j x 8 words, padded: lanes (z) land on different banks
+    __shared__ __align__(16) uint64_t tile[32 * kRowWords];
+    const int zl = threadIdx.x & 31, jl = threadIdx.x >> 5;
+    const int z = blockIdx.x * 32 + zl, j0 = blockIdx.y * 8, j = j0 + jl;
+    uint64_t acc[3][2][2];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) acc[r][c][0] = acc[r][c][1] = 0;
+    const int wc = 2 * t_conv;
+    for (int k = 0; k < t_conv; k++) {
+        const uint32_t *g = ginv + ((size_t)k * dim0 + j) * 2 * kN;
+        const uint32_t gp = g[z], gb = g[kN + z];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint32_t *w = W + ((size_t)r * wc + 2 * k + c) * 2 * kN;
+                acc[r][c][0] += (uint64_t)__ldg(w + z) * gp;
+                acc[r][c][1] += (uint64_t)__ldg(w + kN + z) * gb;
+            }
+        if ((k & 127) == 127) {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) { acc[r][c][0] = reduce_u64(acc[r][c][0], 0); acc[r][c][1] = reduce_u64(acc[r][c][1], 1); }
+        }
+    }
+    const uint32_t *cv1 = cv + ((size_t)ct_idx[j] * 2 + 1) * 2 * kN;
+    const uint32_t c1p = cv1[z], c1b = cv1[kN + z];
+    acc[1][0][0] += c1p; acc[1][0][1] += c1b;     // place(cv_1, 1, 0)
+    acc[2][1][0] += c1p; acc[2][1][1] += c1b;     // place(cv_1, 2, 1)
+    uint64_t *row = tile + zl * kRowWords + jl * 8;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) row[c * 4 + r] = pack_pb2(reduce_u64(acc[r][c][0], 0), reduce_u64(acc[r][c][1], 1));
+        row[c * 4 + 3] = 0;
+    }
+    __syncthreads();
+    // write-out: warp w takes rows z = w, w + 8, ...; lane l the 16-byte chunk l of the 512-byte run [z][j0 .. j0+8)[m][4]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int zz = wid; zz < 32; zz += 8) {
+        const uint64_t *src = tile + zz * kRowWords + lane * 2;
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(query + (((size_t)(blockIdx.x * 32 + zz) * dim0 + j0) * 2) * 4) + lane;
+        *dst = make_ulonglong2(src[0], src[1]);
     }
 }
 // same product but emitted as dev-NTT MatPoly (3 x 2) per ciphertext - the reference's scalToMat output
@@ -442,7 +526,9 @@ void launch_scal_to_mat_reoriented(uint64_t *query_out, const uint32_t *cv, cons
     launch_from_ntt_indexed(scratch_raw, cv, poly_idx, dim0, s);
     launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, (int)dim0, s);
     const size_t n = dim0 * kN;
-    count_launch(); launch_pdl(k_scal_to_mat_accum, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
+    count_launch();
+    if (dim0 % 8 == 0) launch_pdl(k_scal_to_mat_accum_tiled, dim3(kN / 32, (unsigned)(dim0 / 8)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
+    else launch_pdl(k_scal_to_mat_accum, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
 }
 void launch_scal_to_mat_ntt(uint32_t *out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t count,
                             const uint32_t *W, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
