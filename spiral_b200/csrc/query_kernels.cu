@@ -272,8 +272,8 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
         // ginv is indexed [slot][ty]: rounds past stopround only hold t_left digits per slot (see expand_ginv_polys)
         count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty);
-        count_launch();
-        if (cnt[r] >= 64 && tmax <= 128) launch_pdl(k_expand_accum_wide, dim3(dim3(cnt[r], 4)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
+        count_launch();                                   // rounds with right slots (56-term chains) stay on the split kernel
+        if (((cnt[r] >= 64 && !any_odd) || cnt[r] >= 512) && tmax <= 128) launch_pdl(k_expand_accum_wide, dim3(dim3(cnt[r], 4)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
         else launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
     }
 }
@@ -357,55 +357,52 @@ __global__ void k_scal_to_mat_accum(uint64_t *__restrict__ query, const uint32_t
 // and leave with j across the lanes: 512 contiguous bytes per z instead of 64-byte pieces 16 KiB apart (the scattered form spent
 // its time in the store path: 2 M sixteen-byte stores to 2 M different sectors).
 __global__ void __launch_bounds__(256) k_scal_to_mat_accum_tiled(uint64_t *__restrict__ query, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
-                                                                 const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int t_conv, int dim0) {
+                                                                 const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int dim0, int jtiles) {
     pdl_prologue();
+    constexpr int TC = 4;                                             // t_conv of every Spiral parameter set that reaches this kernel
     constexpr int kRowWords = 8 * 8 + 1;                              // 8 j x 8 words, padded: lanes (z) land on different banks
     __shared__ __align__(16) uint64_t tile[32 * kRowWords];
-    const int zl = threadIdx.x & 31, jl = threadIdx.x >> 5;
-    const int z = blockIdx.x * 32 + zl, j0 = blockIdx.y * 8, j = j0 + jl;
-    uint64_t acc[3][2][2];
+    const int zl = threadIdx.x & 31, jl = threadIdx.x >> 5, lane = zl, wid = jl;
+    const int z = blockIdx.x * 32 + zl;
+    // the conversion key W (3 x 2*t_conv) at this z under both primes stays in registers for all the j of this CTA
+    uint32_t wp[3][2][TC], wb[3][2][TC];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int c = 0; c < 2; c++) acc[r][c][0] = acc[r][c][1] = 0;
-    const int wc = 2 * t_conv;
-    for (int k = 0; k < t_conv; k++) {
-        const uint32_t *g = ginv + ((size_t)k * dim0 + j) * 2 * kN;
-        const uint32_t gp = g[z], gb = g[kN + z];
+        for (int c = 0; c < 2; c++)
 #pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const uint32_t *w = W + ((size_t)r * wc + 2 * k + c) * 2 * kN;
-                acc[r][c][0] += (uint64_t)__ldg(w + z) * gp;
-                acc[r][c][1] += (uint64_t)__ldg(w + kN + z) * gb;
+            for (int k = 0; k < TC; k++) {
+                const uint32_t *w = W + ((size_t)r * (2 * TC) + 2 * k + c) * 2 * kN;
+                wp[r][c][k] = __ldg(w + z); wb[r][c][k] = __ldg(w + kN + z);
             }
-        if ((k & 127) == 127) {
+    for (int jt = 0; jt < jtiles; jt++) {
+        const int j0 = (blockIdx.y * jtiles + jt) * 8, j = j0 + jl;
+        uint32_t gp[TC], gb[TC];
 #pragma unroll
-            for (int r = 0; r < 3; r++)
+        for (int k = 0; k < TC; k++) { const uint32_t *g = ginv + ((size_t)k * dim0 + j) * 2 * kN; gp[k] = __ldg(g + z); gb[k] = __ldg(g + kN + z); }
+        const uint32_t *cv1 = cv + ((size_t)ct_idx[j] * 2 + 1) * 2 * kN;
+        const uint32_t c1p = __ldg(cv1 + z), c1b = __ldg(cv1 + kN + z);
+        uint64_t *row = tile + zl * kRowWords + jl * 8;
 #pragma unroll
-                for (int c = 0; c < 2; c++) { acc[r][c][0] = reduce_u64(acc[r][c][0], 0); acc[r][c][1] = reduce_u64(acc[r][c][1], 1); }
+        for (int c = 0; c < 2; c++) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                uint64_t ap = (r == c + 1) ? c1p : 0, ab = (r == c + 1) ? c1b : 0;      // place(cv_1, 1, 0), place(cv_1, 2, 1)
+#pragma unroll
+                for (int k = 0; k < TC; k++) { ap += (uint64_t)wp[r][c][k] * gp[k]; ab += (uint64_t)wb[r][c][k] * gb[k]; }
+                row[c * 4 + r] = pack_pb2(reduce_u64(ap, 0), reduce_u64(ab, 1));
+            }
+            row[c * 4 + 3] = 0;
         }
-    }
-    const uint32_t *cv1 = cv + ((size_t)ct_idx[j] * 2 + 1) * 2 * kN;
-    const uint32_t c1p = cv1[z], c1b = cv1[kN + z];
-    acc[1][0][0] += c1p; acc[1][0][1] += c1b;     // place(cv_1, 1, 0)
-    acc[2][1][0] += c1p; acc[2][1][1] += c1b;     // place(cv_1, 2, 1)
-    uint64_t *row = tile + zl * kRowWords + jl * 8;
+        __syncthreads();
+        // write-out: warp w takes rows z = w, w + 8, ...; lane l the 16-byte chunk l of the 512-byte run [z][j0 .. j0+8)[m][4]
 #pragma unroll
-    for (int c = 0; c < 2; c++) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) row[c * 4 + r] = pack_pb2(reduce_u64(acc[r][c][0], 0), reduce_u64(acc[r][c][1], 1));
-        row[c * 4 + 3] = 0;
-    }
-    __syncthreads();
-    // write-out: warp w takes rows z = w, w + 8, ...; lane l the 16-byte chunk l of the 512-byte run [z][j0 .. j0+8)[m][4]
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int zz = wid; zz < 32; zz += 8) {
-        const uint64_t *src = tile + zz * kRowWords + lane * 2;
-        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(query + (((size_t)(blockIdx.x * 32 + zz) * dim0 + j0) * 2) * 4) + lane;
-        *dst = make_ulonglong2(src[0], src[1]);
+        for (int zz = wid; zz < 32; zz += 8) {
+            const uint64_t *src = tile + zz * kRowWords + lane * 2;
+            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(query + (((size_t)(blockIdx.x * 32 + zz) * dim0 + j0) * 2) * 4) + lane;
+            *dst = make_ulonglong2(src[0], src[1]);
+        }
+        __syncthreads();
     }
 }
 // same product but emitted as dev-NTT MatPoly (3 x 2) per ciphertext - the reference's scalToMat output
@@ -527,7 +524,10 @@ void launch_scal_to_mat_reoriented(uint64_t *query_out, const uint32_t *cv, cons
     launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, (int)dim0, s);
     const size_t n = dim0 * kN;
     count_launch();
-    if (dim0 % 8 == 0) launch_pdl(k_scal_to_mat_accum_tiled, dim3(kN / 32, (unsigned)(dim0 / 8)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
+    if (dim0 % 8 == 0 && t_conv == 4) {
+        const int jtiles = dim0 % 32 == 0 ? 4 : 1;                    // j-tiles of 8 per CTA: the key registers are amortised over 32 j
+        launch_pdl(k_scal_to_mat_accum_tiled, dim3(kN / 32, (unsigned)(dim0 / 8 / jtiles)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, (int)dim0, jtiles);
+    }
     else launch_pdl(k_scal_to_mat_accum, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
 }
 void launch_scal_to_mat_ntt(uint32_t *out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t count,
