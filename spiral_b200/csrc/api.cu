@@ -504,6 +504,12 @@ struct sb200_server {
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch;
     DBuf<uint64_t> c0, conv_raw, query, cts, resp, final_ct;
     DBuf<int> lists, ct_idx_first, poly_idx_first, ct_idx_bits, poly_idx_bits;
+    // even / odd chains of the expansion tree (stopround > 0): own lists, the odd chain its own scratch (it runs on aux_stream)
+    bool split_chains = false;
+    DBuf<int> lists_e, lists_o;
+    std::vector<int> offs_e, cnt_e, offs_o, cnt_o;
+    DBuf<uint32_t> c1_o, ginv_o;
+    DBuf<uint64_t> c0_o;
     DBuf<uint16_t> perms;
     GraphSlot g_convert, g_lift_fold, g_tail;
     // stream = NULL means "the legacy default stream", which cannot be captured: such calls run on this
@@ -578,6 +584,17 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     for (size_t b = 0; b < nbits; b++) { cb[b] = (int)(s->stopround ? 2 * b + 1 : s->dim0 + b); pb[b] = 2 * cb[b]; pb[nbits + b] = 2 * cb[b] + 1; }
     A(s->lists.up(list.data(), list.size())); A(s->ct_idx_first.up(cf.data(), cf.size())); A(s->poly_idx_first.up(pf.data(), pf.size()));
     if (nbits) { A(s->ct_idx_bits.up(cb.data(), cb.size())); A(s->poly_idx_bits.up(pb.data(), pb.size())); }
+    if (s->stopround > 0 && s->g > 1) {
+        std::vector<int> le(list.size()), lo(list.size());
+        s->offs_e.resize(s->g); s->cnt_e.resize(s->g); s->offs_o.resize(s->g); s->cnt_o.resize(s->g);
+        const int max_odd = expand_split_lists(s->plan, list.data(), s->offs.data(), s->cnt.data(), le.data(), s->offs_e.data(), s->cnt_e.data(),
+                                               lo.data(), s->offs_o.data(), s->cnt_o.data());
+        A(s->lists_e.alloc(le.size())); A(s->lists_o.alloc(lo.size()));
+        A(s->lists_e.up(le.data(), le.size())); A(s->lists_o.up(lo.data(), lo.size()));
+        A(s->c0_o.alloc((size_t)std::max(max_odd, 1) * kN)); A(s->c1_o.alloc((size_t)std::max(max_odd, 1) * PLW));
+        A(s->ginv_o.alloc((size_t)std::max(max_odd, 1) * prm->t_exp_right * PLW));
+        s->split_chains = true;
+    }
     { std::vector<uint16_t> hperm(s->g * kN); build_automorph_perms(hperm.data(), (int)s->g);
       A(s->perms.alloc(hperm.size())); A(s->perms.up(hperm.data(), hperm.size())); }
     build_neg1(s->neg1.p, (int)s->g, 0);
@@ -697,6 +714,26 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
         // The GSW bits live in the odd ciphertexts, which are final after round `stopround`; the remaining rounds
         // only touch even ones.  Fork: RegevToGSW runs on a side stream while the last expansion rounds and
         // ScalToMat continue on the main one (a fork/join pair inside the captured graph).
+        if (s->split_chains) {
+            // After round 0 the tree splits into two independent chains: the even ciphertexts (first dimension: t_left digits,
+            // all g rounds, then ScalToMat) and the odd ones (GSW bits: t_right = 56 digits per key switch, rounds 1..stopround,
+            // then RegevToGSW).  The heavy odd chain runs on the side stream and no longer sits on the path to the scan.
+            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
+                          s->offs.data(), s->cnt.data(), st, 0, 1);
+            cudaEventRecord(s->ev_fork, st);
+            cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0);
+            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_o.p,
+                          s->offs_o.data(), s->cnt_o.data(), s->aux_stream, 1, (int)s->stopround + 1, 1);
+            launch_regev_to_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
+                                s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, s->aux_stream);
+            cudaEventRecord(s->ev_join, s->aux_stream);
+            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists_e.p,
+                          s->offs_e.data(), s->cnt_e.data(), st, 1, (int)s->g, 0);
+            launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
+                                          (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+            cudaStreamWaitEvent(st, s->ev_join, 0);
+            return;
+        }
         const int fork_round = s->stopround > 0 ? (int)s->stopround + 1 : (int)s->g;
         launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
                       s->offs.data(), s->cnt.data(), st, 0, fork_round);

@@ -245,6 +245,20 @@ void build_automorph_perms(uint16_t *perm_host, int g) {
 }
 
 // polynomials the digit scratch must hold: max over rounds of (active ciphertexts x digits per slot of that round)
+// even / odd halves of the per-round lists (rounds >= 1; round 0 stays whole).  Returns the largest odd count.
+int expand_split_lists(const ExpandPlan &p, const int *list, const int *offs, const int *cnt, int *list_e, int *offs_e, int *cnt_e,
+                       int *list_o, int *offs_o, int *cnt_o) {
+    int oe = 0, oo = 0, mx = 0;
+    for (int r = 0; r < p.g; r++) {
+        offs_e[r] = oe; offs_o[r] = oo; cnt_e[r] = cnt_o[r] = 0;
+        for (int k = 0; k < cnt[r]; k++) {
+            const int i = list[offs[r] + k];
+            if (i & 1) { list_o[oo++] = i; cnt_o[r]++; } else { list_e[oe++] = i; cnt_e[r]++; }
+        }
+        if (cnt_o[r] > mx) mx = cnt_o[r];
+    }
+    return mx;
+}
 size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt) {
     const int tmax = p.t_left > p.t_right ? p.t_left : p.t_right;
     size_t need = 1;
@@ -257,7 +271,10 @@ size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt) {
 }
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
                    const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
-                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end) {
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end, int parity) {
+    // parity: -1 = the lists hold every active ciphertext; 0 / 1 = they hold only the even / odd ones (expand_split_lists):
+    // after round 0 the even chain (first-dimension ciphertexts, t_left digits) and the odd chain (GSW bits, t_right digits)
+    // never touch each other's ciphertexts, so the two can run on different streams with their own scratch.
     const int tmax = p.t_left > p.t_right ? p.t_left : p.t_right;
     if (r_end < 0 || r_end > p.g) r_end = p.g;
     for (int r = r_begin; r < r_end; r++) {
@@ -267,8 +284,8 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         const uint32_t *Wl = W_left + (size_t)r * 2 * p.t_left * 2 * kN;
         const uint32_t *Wr = W_right + (size_t)r * 2 * p.t_right * 2 * kN;
         // digits needed this round: t_right only if some odd ciphertext is active
-        const bool any_odd = !(p.stopround > 0 && r > p.stopround);
-        const int ty = any_odd ? tmax : p.t_left;
+        const bool any_odd = parity != 0 && !(p.stopround > 0 && r > p.stopround);
+        const int ty = parity == 1 ? p.t_right : any_odd ? tmax : p.t_left;
         count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
         // ginv is indexed [slot][ty]: rounds past stopround only hold t_left digits per slot (see expand_ginv_polys)
         count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty);
