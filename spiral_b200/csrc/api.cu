@@ -877,8 +877,7 @@ extern "C" int sb200_server_fold_tail(sb200_server *s, uint64_t *gathered, uint6
     return run_stage(s->g_tail, ES(s, stream), gathered, resp_dev, [&](cudaStream_t st) {
         fold_rounds(s, gathered, (size_t)s->world, s->prm.nu2 - s->log_world, st);
         // modulus switch (check_final, reference src/spiral.cpp:1441-1447): row 0 -> arb_qprime, rows 1.. -> 4*p_db
-        launch_rescale(resp_dev, gathered, 2 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
-        launch_rescale(resp_dev + 2 * kN, gathered + 2 * kN, 4 * (size_t)kN, kQ, 4 * s->prm.p_db, st);
+        launch_rescale2(resp_dev, gathered, 2 * (size_t)kN, 4 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), 4 * s->prm.p_db, st);
     });
 }
 // ---- peer-memory exchange: setup -----------------------------------------------------------------
@@ -946,8 +945,7 @@ extern "C" int sb200_server_exchange_and_tail(sb200_server *s, uint64_t *resp_de
         if (s->rank == 0) {
             launch_xchg_wait(s->xchg.p, s->xchg_acks.p, s->gathered.p, s->xchg_state.p, s->world, s->xchg_state.p + 1, st);
             fold_rounds(s, s->gathered.p, (size_t)s->world, s->prm.nu2 - s->log_world, st);
-            launch_rescale(resp_dev, s->gathered.p, 2 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
-            launch_rescale(resp_dev + 2 * kN, s->gathered.p + 2 * kN, 4 * (size_t)kN, kQ, 4 * s->prm.p_db, st);
+            launch_rescale2(resp_dev, s->gathered.p, 2 * (size_t)kN, 4 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), 4 * s->prm.p_db, st);
         }
     });
 }

@@ -464,8 +464,7 @@ extern "C" int sb200_pack_server_fold_tail(sb200_pack_server *s, const uint64_t 
         }
         launch_pack(s->packed.p, final_cts, s->vW.p, (int)out_n, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
         launch_from_ntt(s->packed_raw.p, s->packed.p, rows * out_n, st);
-        launch_rescale(total_resp_dev, s->packed_raw.p, out_n * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), st);
-        launch_rescale(total_resp_dev + out_n * kN, s->packed_raw.p + out_n * kN, (rows - 1) * out_n * (size_t)kN, kQ, 4 * s->prm.p_db, st);
+        launch_rescale2(total_resp_dev, s->packed_raw.p, out_n * (size_t)kN, (rows - 1) * out_n * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), 4 * s->prm.p_db, st);
     });
 }
 extern "C" uint64_t *sb200_pack_server_result_cts(sb200_pack_server *s) { return s ? s->result_cts.p : nullptr; }

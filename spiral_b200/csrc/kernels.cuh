@@ -40,6 +40,7 @@ void launch_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t
 void launch_gadget_ntt(uint32_t *out, const uint64_t *raw, int mx, int rdim, int cols, cudaStream_t s);
 void launch_gadget_raw(uint64_t *out, const uint64_t *raw, int mx, int rdim, int cols, cudaStream_t s);
 void launch_rescale(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod, cudaStream_t s);
+void launch_rescale2(uint64_t *out, const uint64_t *in, size_t n0, size_t n1, uint64_t inp_mod, uint64_t mod0, uint64_t mod1, cudaStream_t s);
 // write_arbitrary_bits over a whole buffer: n values of `bits` bits -> ceil(n*bits/64) words (reference src/core.cpp:32-52)
 void launch_bitpack(uint64_t *out, const uint64_t *in, size_t n, uint32_t bits, cudaStream_t s);
 // modswitch (reference src/spiral.cpp:40-78): round(v * qprime / Q) in the reference's x87 arithmetic, bit-packed

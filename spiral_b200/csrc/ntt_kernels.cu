@@ -288,6 +288,15 @@ __global__ void k_rescale(uint64_t *__restrict__ out, const uint64_t *__restrict
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = rescale_one(in[i] % kQ, inp_mod, out_mod);
 }
+// the response's two modulus switches in one launch: the first n0 coefficients to mod0 (row 0 -> q'), the next n1 to mod1 (-> 4p)
+__global__ void k_rescale2(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, size_t n0, size_t n1, uint64_t inp_mod, uint64_t mod0, uint64_t mod1) {
+    pdl_prologue();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n0 + n1) out[i] = rescale_one(in[i] % kQ, inp_mod, i < n0 ? mod0 : mod1);
+}
+void launch_rescale2(uint64_t *out, const uint64_t *in, size_t n0, size_t n1, uint64_t inp_mod, uint64_t mod0, uint64_t mod1, cudaStream_t s) {
+    if (n0 + n1) { count_launch(); launch_pdl(k_rescale2, dim3((unsigned)((n0 + n1 + 255) / 256)), dim3(256), 0, s, out, in, n0, n1, inp_mod, mod0, mod1); }
+}
 void launch_rescale(uint64_t *out, const uint64_t *in, size_t ncoeffs, uint64_t inp_mod, uint64_t out_mod, cudaStream_t s) {
     if (ncoeffs) { count_launch(); launch_pdl(k_rescale, dim3((unsigned)((ncoeffs + 255) / 256)), dim3(256), 0, s, out, in, ncoeffs, inp_mod, out_mod); }
 }
