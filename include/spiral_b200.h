@@ -250,6 +250,53 @@ int sb200_pack_server_download(sb200_pack_server *srv, uint64_t *dst_host, const
 size_t sb200_pack_server_db_bytes(const sb200_pack_server *srv);                  /* this shard */
 size_t sb200_pack_server_response_words(const sb200_pack_server *srv);
 
+
+/* ---- wire and on-disk formats ------------------------------------------------------------------
+ * The reference keeps client and server in one process: it only ACCOUNTS for the sizes of what would travel
+ * (print_summary, src/spiral.cpp:219-234) and leaves the database file I/O of load_db as `// TODO`
+ * (src/spiral.cpp:1095-1162).  These entries are what a client/server split binds instead; all multi-byte fields are
+ * little endian and bit-packed values follow write_arbitrary_bits (src/core.cpp:32-52): value i occupies bits
+ * [i*bits, (i+1)*bits) of the stream.
+ *
+ * Query (the 2x1 Regev ciphertext of getRegevSample, src/client.cpp:141-157; row 0 = -a is uniformly random):
+ *   bytes 0-3 "SB2Q", bytes 4-5 kind, bytes 6-7 zero, then
+ *   kind 1 SEEDED : 32-byte seed | row 1 raw at 56 bits per coefficient                      (8 + 32 + 14336 bytes)
+ *                   row 0 in NTT form, slot (prime n, z): ChaCha20 block (RFC 8439; key = seed, counter = n*2048 + z,
+ *                   nonce = "SB2Q",0,0), the first of its 16 words whose low 28 bits are below the prime
+ *   kind 2 FULL   : row 0 | row 1, both raw at 56 bits per coefficient                        (8 + 2*14336 bytes)
+ * Response: sb200_dev_pack_response above.
+ * Records: the database as a flat bit stream, log2(p_db) bits per plaintext coefficient, item-major, polynomial-major
+ *   inside an item (Spiral: the 2x2 polynomials (m*2+c) of item j*2^nu2 + ii; Pack: the out_n^2 plane polynomials).
+ * Snapshot: 64-byte header (magic "SB2D", version, kind, nu1, nu2, rank, world, out_n, p_db, words, sum of words) +
+ *   the preprocessed scan-layout shard exactly as it sits in HBM; loading verifies the parameters and the sum. */
+#define SB200_WIRE_QUERY_SEEDED 1u
+#define SB200_WIRE_QUERY_FULL 2u
+size_t sb200_wire_query_bytes(uint32_t kind);                       /* 0 for an unknown kind */
+/* device copy of a wire query (header included) -> cv[0], the 2x1 dev-NTT ciphertext the expansion reads */
+int sb200_dev_query_from_wire(uint32_t *cv_dev, const uint8_t *wire_dev, uint32_t kind, void *stream);
+/* as sb200_server_upload_query, the query in wire form; a malformed buffer is SB200_ERR_ARG and nothing is uploaded */
+int sb200_server_upload_query_wire(sb200_server *srv, const uint8_t *wire_host, size_t bytes, void *stream);
+/* one query entirely in wire form: wire query in, sb200_server_packed_response_bytes() of packed response out */
+int sb200_server_answer_wire(sb200_server *srv, const uint8_t *wire_host, size_t bytes, uint64_t *packed_resp_host, void *stream);
+int sb200_pack_server_upload_query_wire(sb200_pack_server *srv, const uint8_t *wire_host, size_t bytes, void *stream);
+/* as sb200_pack_server_answer, the query in wire form */
+int sb200_pack_server_answer_wire(sb200_pack_server *srv, const uint8_t *wire_host, size_t bytes, uint64_t *total_resp_host,
+                                  uint64_t *result_cts_host, void *stream);
+uint64_t *sb200_pack_server_db_ptr(sb200_pack_server *srv);        /* device pointer of the scan-layout planes of this shard */
+/* load_db's `has_data` branch (src/spiral.cpp:1108-1111): the WHOLE database as records, in memory or in a file; a sharded
+ * server reads only its own items (ii = rank mod world) */
+size_t sb200_server_record_stream_bytes(const sb200_server *srv);
+int sb200_server_load_db_records(sb200_server *srv, const uint8_t *records_host, size_t bytes);
+int sb200_server_load_db_records_file(sb200_server *srv, const char *path);
+/* load_db's `has_file && !load` / `has_file && load` branches (src/spiral.cpp:1095-1097, 1159-1161): the preprocessed shard */
+int sb200_server_save_db(sb200_server *srv, const char *path);
+int sb200_server_load_db_snapshot(sb200_server *srv, const char *path);
+size_t sb200_pack_server_record_stream_bytes(const sb200_pack_server *srv);
+int sb200_pack_server_load_db_records(sb200_pack_server *srv, const uint8_t *records_host, size_t bytes);
+int sb200_pack_server_load_db_records_file(sb200_pack_server *srv, const char *path);
+int sb200_pack_server_save_db(sb200_pack_server *srv, const char *path);
+int sb200_pack_server_load_db_snapshot(sb200_pack_server *srv, const char *path);
+
 #ifdef __cplusplus
 }
 #endif

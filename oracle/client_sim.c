@@ -13,6 +13,7 @@
  * (check_final) :1428-1476, discrete Gaussian src/core.cpp:182-207.
  */
 #include "client_sim.h"
+#include "wire_format.h"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -174,7 +175,7 @@ static int64_t inv_mod(int64_t a, int64_t b) {             /* src/util.cpp:272-2
     return x1;
 }
 
-void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv) {   /* :2098-2157 */
+static uint64_t *query_sigma(so_client *c, size_t idx_target) {   /* :2098-2157 */
     const so_params *p = &c->prm;
     size_t g, stop; so_spiral_expansion_shape(p, &g, &stop);
     size_t fd = p->nu2, ell = p->t_gsw, dim0 = (size_t)1 << p->nu1;
@@ -203,7 +204,41 @@ void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv)
         uint64_t inv = (uint64_t)inv_mod((int64_t)1 << g, (int64_t)SO_Q);
         for (size_t i = 0; i < N; i++) sigma[i] = (uint64_t)((u128)sigma[i] * inv % SO_Q);
     }
+    return sigma;
+}
+void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv) {
+    uint64_t *sigma = query_sigma(c, idx_target);
     encrypt_simple_regev(c, query_cv, sigma);
+    free(sigma);
+}
+/* The same query in its wire form (wire_format.h).  SEEDED: row 0 of the Regev sample (the uniformly random -a,
+ * getRegevSample src/client.cpp:141-157) is drawn from a 32-byte seed directly in NTT form, so only the seed and
+ * row 1 = a*s + e + sigma travel; FULL: an ordinary query with both rows packed at 56 bits per coefficient. */
+void so_client_spiral_query_wire(so_client *c, size_t idx_target, uint32_t kind, uint8_t *wire) {
+    uint64_t *sigma = query_sigma(c, idx_target);
+    if (kind == SO_WIRE_QUERY_FULL) {
+        uint64_t *cv = xalloc(2 * PL);
+        encrypt_simple_regev(c, cv, sigma);
+        so_wire_query_pack_full(cv, wire);
+        free(cv);
+    } else {
+        uint8_t seed[SO_WIRE_SEED_BYTES];
+        for (int i = 0; i < 4; i++) { uint64_t w = so_rng_next(&c->rng); memcpy(seed + 8 * i, &w, 8); }
+        uint64_t *row0 = xalloc(PL), *a_ntt = xalloc(PL), *s_ntt = xalloc(PL), *e = xalloc(N), *e_ntt = xalloc(PL);
+        uint64_t *b = xalloc(PL), *sig_ntt = xalloc(PL);
+        so_wire_seeded_row0(seed, row0);
+        for (size_t z = 0; z < N; z++) {                       /* a = -(row 0) */
+            a_ntt[z] = (SO_P - row0[z]) % SO_P;
+            a_ntt[N + z] = (SO_B - row0[N + z]) % SO_B;
+        }
+        noise(c, e, 1);
+        so_to_ntt(s_ntt, c->sr, 1); so_to_ntt(e_ntt, e, 1); so_to_ntt(sig_ntt, sigma, 1);
+        so_multiply(b, a_ntt, s_ntt, 1, 1, 1);
+        so_add(b, b, e_ntt, 1);
+        so_add(b, b, sig_ntt, 1);
+        so_wire_query_pack_seeded(seed, b, wire);
+        free(row0); free(a_ntt); free(s_ntt); free(e); free(e_ntt); free(b); free(sig_ntt);
+    }
     free(sigma);
 }
 

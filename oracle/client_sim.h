@@ -11,6 +11,8 @@ size_t so_client_w_exp_right_count(const so_params *prm);
 /* W_exp_left: g x (2 x t_exp); W_exp_right: count x (2 x t_exp_right); W_conv, V_conv: 3 x 2*t_conv (all ref-NTT) */
 void so_client_spiral_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *W_conv, uint64_t *V_conv);
 void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv);
+/* kind: SO_WIRE_QUERY_SEEDED / SO_WIRE_QUERY_FULL (wire_format.h); wire: so_wire_query_bytes(kind) bytes */
+void so_client_spiral_query_wire(so_client *c, size_t idx_target, uint32_t kind, uint8_t *wire);
 void so_client_spiral_decode(so_client *c, const uint64_t *total_resp, uint64_t *out_pt);
 #ifdef __cplusplus
 }

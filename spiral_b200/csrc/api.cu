@@ -501,6 +501,8 @@ struct sb200_server {
     int tc_capacity = 0;
     DBuf<uint32_t> W_left, W_right, W_conv, V_conv, neg1;
     DBuf<uint64_t> q_stage;                             // uploaded query (ref-NTT)
+    DBuf<uint8_t> q_wire;                               // uploaded query in its wire form (wire_kernels.cu), header included
+    uint32_t wire_kind = 0;                             // 0: q_stage holds the query; 1 / 2: q_wire does (seeded / full)
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch;
     DBuf<uint64_t> c0, conv_raw, query, cts, resp, final_ct;
     DBuf<int> lists, ct_idx_first, poly_idx_first, ct_idx_bits, poly_idx_bits;
@@ -511,7 +513,7 @@ struct sb200_server {
     DBuf<uint32_t> c1_o, ginv_o;
     DBuf<uint64_t> c0_o;
     DBuf<uint16_t> perms;
-    GraphSlot g_convert, g_lift_fold, g_tail;
+    GraphSlot g_convert, g_convert_wire[2], g_lift_fold, g_tail;
     // stream = NULL means "the legacy default stream", which cannot be captured: such calls run on this
     // BLOCKING stream instead (implicitly ordered with legacy-default-stream work, e.g. torch's default stream)
     cudaStream_t own_stream = nullptr, aux_stream = nullptr;
@@ -566,7 +568,7 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc(n_right * 2 * prm->t_exp_right * PLW));
     A(s->W_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->V_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
-    A(s->q_stage.alloc(2 * PLW)); A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW));
+    A(s->q_stage.alloc(2 * PLW)); A(s->q_wire.alloc(kWireHeaderBytes + 2 * kWireRowBytes + 8)); A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW));
     A(s->ginv.alloc(expand_ginv_polys(s->plan, s->cnt.data()) * PLW)); A(s->c0.alloc((size_t)s->maxcnt * kN));
     A(s->conv_raw.alloc(conv_cols * kN)); A(s->conv_ntt.alloc(conv_cols * prm->t_conv * PLW));
     A(s->gsw.alloc(prm->nu2 * 3 * m2 * PLW));
@@ -704,13 +706,16 @@ extern "C" int sb200_server_set_public_params(sb200_server *s, const uint64_t *W
 extern "C" int sb200_server_upload_query(sb200_server *s, const uint64_t *query_cv_host, void *stream) {
     if (!s || !query_cv_host) return fail(SB200_ERR_ARG, "upload_query: null argument");
     CU(cudaMemcpyAsync(s->q_stage.p, query_cv_host, 2 * PLW * sizeof(uint64_t), cudaMemcpyHostToDevice, ES(s, stream)));
+    s->wire_kind = 0;
     return SB200_OK;      // the narrowing into cv[0] is the first node of the expand_and_convert stage
 }
 extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!s->have_params) return fail(SB200_ERR_STATE, "expand_and_convert: public parameters not set");
-    return run_stage(s->g_convert, ES(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
-        launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, st);       // uploaded query (ref-NTT) -> cv[0]
+    GraphSlot &slot = s->wire_kind ? s->g_convert_wire[s->wire_kind - 1] : s->g_convert;
+    return run_stage(slot, ES(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
+        if (s->wire_kind) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);     // wire query -> cv[0]
+        else launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, st);                             // uploaded query (ref-NTT) -> cv[0]
         // The GSW bits live in the odd ciphertexts, which are final after round `stopround`; the remaining rounds
         // only touch even ones.  Fork: RegevToGSW runs on a side stream while the last expansion rounds and
         // ScalToMat continue on the main one (a fork/join pair inside the captured graph).

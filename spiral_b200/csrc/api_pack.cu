@@ -139,11 +139,13 @@ struct sb200_pack_server {
     int tc_capacity = 0;
     DBuf<uint32_t> W_left, W_right, V, vW, neg1;
     DBuf<uint64_t> stage;
+    DBuf<uint8_t> q_wire;                               // query in its wire form (wire_kernels.cu)
+    uint32_t wire_kind = 0;
     DBuf<uint32_t> cv, c1, ginv, conv_ntt, gsw, scan_out, fold_scratch, packed;
     DBuf<uint64_t> c0, conv_raw, query, cts, result_cts, tail_cts, packed_raw, resp;
     DBuf<int> lists, ct_idx_first, ct_idx_direct, ct_idx_bits, poly_idx_bits;
     DBuf<uint16_t> perms;
-    GraphSlot g_convert, g_fold, g_tail;
+    GraphSlot g_convert, g_convert_wire[2], g_fold, g_tail;
     cudaStream_t own_stream = nullptr;
     ~sb200_pack_server() { if (own_stream) cudaStreamDestroy(own_stream); }
 };
@@ -181,7 +183,7 @@ static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *
     if (parent) s->db_owner = parent; else A(s->db.alloc(s->planes * s->plane_words));
     A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc((s->stopround + 1) * 2 * prm->t_exp_right * PLW));
     A(s->V.alloc(2 * 2 * prm->t_conv * PLW)); A(s->vW.alloc(prm->out_n * rows * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
-    A(s->stage.alloc((size_t)1024 * PLW));
+    A(s->stage.alloc((size_t)1024 * PLW)); A(s->q_wire.alloc(kWireHeaderBytes + 2 * kWireRowBytes + 8));
     A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW)); A(s->ginv.alloc(expand_ginv_polys(s->plan, s->cnt.data()) * PLW));
     A(s->c0.alloc((size_t)s->maxcnt * kN));
     const size_t conv_polys = std::max(2 * nbits, s->planes * 2);
@@ -309,14 +311,17 @@ extern "C" int sb200_pack_server_set_public_params(sb200_pack_server *s, const u
 extern "C" int sb200_pack_server_upload_query(sb200_pack_server *s, const uint64_t *query_cv_host, void *stream) {
     if (!s || !query_cv_host) return fail(SB200_ERR_ARG, "pack upload_query: null argument");
     CU(cudaMemcpyAsync(s->stage.p, query_cv_host, 2 * PLW * 8, cudaMemcpyHostToDevice, PS(s, stream)));
+    s->wire_kind = 0;
     return SB200_OK;
 }
 // coefficientExpansion + reorientCiphertextsDim1 + regevToSimpleGsw (src/testing.cpp:1015-1024)
 extern "C" int sb200_pack_server_expand_and_convert(sb200_pack_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!s->have_params) return fail(SB200_ERR_STATE, "pack expand_and_convert: expansion keys / V not set");
-    return run_stage(s->g_convert, PS(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
-        launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
+    GraphSlot &slot = s->wire_kind ? s->g_convert_wire[s->wire_kind - 1] : s->g_convert;
+    return run_stage(slot, PS(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
+        if (s->wire_kind) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);
+        else launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
         launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
                       s->offs.data(), s->cnt.data(), st);
         launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_first.p, s->dim0, st);

@@ -46,6 +46,14 @@ void launch_bitpack(uint64_t *out, const uint64_t *in, size_t n, uint32_t bits, 
 // modswitch (reference src/spiral.cpp:40-78): round(v * qprime / Q) in the reference's x87 arithmetic, bit-packed
 void launch_modswitch(uint64_t *out, const uint64_t *in_raw, size_t n, uint32_t bits, uint64_t qprime, cudaStream_t s);
 
+// ---- wire / on-disk formats (wire_kernels.cu)
+// wire query (device copy, header included; kind 1 = seeded, 2 = full) -> cv[0] in dev-NTT form
+void launch_query_from_wire(uint32_t *cv, const uint8_t *wire, uint32_t kind, cudaStream_t s);
+// staged records (n_items whole items of `polys` polynomials, `bits` per coefficient, 4 readable padding bytes) -> u16 coefficients
+void launch_records_to_pts(uint16_t *out, const uint8_t *rec, size_t n_items, int polys, uint32_t bits, size_t out_item_stride,
+                           size_t out_poly_stride, cudaStream_t s);
+void launch_sum64(unsigned long long *acc, const uint64_t *words, size_t n, cudaStream_t s);   // *acc += sum of words (mod 2^64)
+
 // ---- database preprocessing
 // plaintext items (values < p_db, one u16 per coefficient, item-major [item][n0*n2][2048]) ->
 // scan layout DB'[z][j][ic][m] PB64 with ic = ii*n2 + c, item = j*num_per + ii.

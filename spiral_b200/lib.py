@@ -178,6 +178,24 @@ def load_library():
         "sb200_server_first_dim_cts": (vp, [vp]),
         "sb200_server_query_bytes": (sz, [vp]),
         "sb200_server_response_bytes": (sz, [vp]),
+        # wire / on-disk formats
+        "sb200_wire_query_bytes": (sz, [C.c_uint32]),
+        "sb200_dev_query_from_wire": (C.c_int, [vp, vp, C.c_uint32, vp]),
+        "sb200_server_upload_query_wire": (C.c_int, [vp, vp, sz, vp]),
+        "sb200_server_answer_wire": (C.c_int, [vp, vp, sz, vp, vp]),
+        "sb200_pack_server_upload_query_wire": (C.c_int, [vp, vp, sz, vp]),
+        "sb200_pack_server_answer_wire": (C.c_int, [vp, vp, sz, vp, vp, vp]),
+        "sb200_pack_server_db_ptr": (vp, [vp]),
+        "sb200_server_record_stream_bytes": (sz, [vp]),
+        "sb200_server_load_db_records": (C.c_int, [vp, vp, sz]),
+        "sb200_server_load_db_records_file": (C.c_int, [vp, C.c_char_p]),
+        "sb200_server_save_db": (C.c_int, [vp, C.c_char_p]),
+        "sb200_server_load_db_snapshot": (C.c_int, [vp, C.c_char_p]),
+        "sb200_pack_server_record_stream_bytes": (sz, [vp]),
+        "sb200_pack_server_load_db_records": (C.c_int, [vp, vp, sz]),
+        "sb200_pack_server_load_db_records_file": (C.c_int, [vp, C.c_char_p]),
+        "sb200_pack_server_save_db": (C.c_int, [vp, C.c_char_p]),
+        "sb200_pack_server_load_db_snapshot": (C.c_int, [vp, C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError here = header/library drift, caught by the CPU tests

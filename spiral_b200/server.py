@@ -51,6 +51,26 @@ class SpiralServer:
         """B: the reference's own database buffer (layout of src/spiral.cpp:1139-1153)."""
         check(self.lib.sb200_server_load_db_reference(self.h, _p64(B)), self.lib)
 
+    def load_db_records(self, records):
+        """records: the WHOLE database as the flat record stream (uint8 array or a file path); load_db's `has_data` branch."""
+        if isinstance(records, (str, bytes)):
+            path = records if isinstance(records, bytes) else records.encode()
+            check(self.lib.sb200_server_load_db_records_file(self.h, path), self.lib)
+        else:
+            records = np.ascontiguousarray(records, dtype=np.uint8)
+            check(self.lib.sb200_server_load_db_records(self.h, records.ctypes.data, records.size), self.lib)
+
+    def save_db(self, path):
+        """Snapshot of the preprocessed shard (load_db's `has_file && !load` branch)."""
+        check(self.lib.sb200_server_save_db(self.h, path.encode()), self.lib)
+
+    def load_db_snapshot(self, path):
+        check(self.lib.sb200_server_load_db_snapshot(self.h, path.encode()), self.lib)
+
+    @property
+    def record_stream_bytes(self):
+        return self.lib.sb200_server_record_stream_bytes(self.h)
+
     def shard_items(self, pts):
         """Select + order this shard's items from the full item-major plaintext array."""
         idx = [j * self.num_per + ii for j in range(self.dim0) for ii in range(self.rank, self.num_per, self.world)]
@@ -66,6 +86,26 @@ class SpiralServer:
         resp = np.empty(6 * N, dtype=np.uint64)
         check(self.lib.sb200_server_answer(self.h, query_cv.ctypes.data, resp.ctypes.data, stream), self.lib)
         return resp
+
+    def answer_wire(self, wire, stream=None):
+        """Wire query (uint8 array, include/spiral_b200.h "wire formats") -> QPBITS-packed response (uint64 words)."""
+        wire = np.ascontiguousarray(wire, dtype=np.uint8)
+        out = np.empty(self.lib.sb200_server_packed_response_bytes(self.h) // 8, dtype=np.uint64)
+        check(self.lib.sb200_server_answer_wire(self.h, wire.ctypes.data, wire.size, out.ctypes.data, stream), self.lib)
+        return out
+
+    def unpack_response(self, packed):
+        """Client-side inverse of the response packing: packed words -> 3x2 raw response."""
+        resp = np.empty(6 * N, dtype=np.uint64)
+        check(self.lib.sb200_unpack_response(_p64(resp), _p64(np.ascontiguousarray(packed)), 2 * N, 4 * N, self.params.qp_bits, self.params.p_db), self.lib)
+        return resp
+
+    def upload_query_wire(self, wire, stream=None):
+        wire = np.ascontiguousarray(wire, dtype=np.uint8)
+        check(self.lib.sb200_server_upload_query_wire(self.h, wire.ctypes.data, wire.size, stream), self.lib)
+
+    def upload_query_wire_ptr(self, host_ptr, nbytes, stream=None):
+        check(self.lib.sb200_server_upload_query_wire(self.h, host_ptr, nbytes, stream), self.lib)
 
     def upload_query(self, query_cv, stream=None):
         check(self.lib.sb200_server_upload_query(self.h, query_cv.ctypes.data, stream), self.lib)
@@ -212,6 +252,35 @@ class PackServer:
 
     def load_random(self, seed=1):
         check(self.lib.sb200_pack_server_load_random(self.h, seed), self.lib)
+
+    def load_db_records(self, records):
+        """records: the WHOLE database (all planes interleaved per item) as a uint8 array or a file path."""
+        if isinstance(records, (str, bytes)):
+            path = records if isinstance(records, bytes) else records.encode()
+            check(self.lib.sb200_pack_server_load_db_records_file(self.h, path), self.lib)
+        else:
+            records = np.ascontiguousarray(records, dtype=np.uint8)
+            check(self.lib.sb200_pack_server_load_db_records(self.h, records.ctypes.data, records.size), self.lib)
+
+    def save_db(self, path):
+        check(self.lib.sb200_pack_server_save_db(self.h, path.encode()), self.lib)
+
+    def load_db_snapshot(self, path):
+        check(self.lib.sb200_pack_server_load_db_snapshot(self.h, path.encode()), self.lib)
+
+    def upload_query_wire(self, wire, stream=None):
+        wire = np.ascontiguousarray(wire, dtype=np.uint8)
+        check(self.lib.sb200_pack_server_upload_query_wire(self.h, wire.ctypes.data, wire.size, stream), self.lib)
+
+    def answer_wire(self, wire, stream=None):
+        wire = np.ascontiguousarray(wire, dtype=np.uint8)
+        resp = np.empty(self.response_words, dtype=np.uint64)
+        check(self.lib.sb200_pack_server_answer_wire(self.h, wire.ctypes.data, wire.size, resp.ctypes.data, None, stream), self.lib)
+        return resp
+
+    def db_words(self):
+        """The scan-layout planes of this shard, read back from HBM (tests)."""
+        return self.download(self.lib.sb200_pack_server_db_ptr(self.h), self.db_bytes // 8)
 
     def set_public_params(self, W_exp_left, W_exp_right, V, v_W):
         opt = lambda a: None if a is None else _p64(a)  # noqa: E731

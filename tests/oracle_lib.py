@@ -113,8 +113,34 @@ def load():
     lib.so_client_spiral_pub_params.argtypes = [C.c_void_p, u64p, u64p, u64p, u64p]
     lib.so_client_spiral_query.argtypes = [C.c_void_p, sz, u64p]
     lib.so_client_spiral_decode.argtypes = [C.c_void_p, u64p, u64p]
+    # wire / on-disk formats (oracle/wire_format.h)
+    u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+    lib.so_chacha20_block.argtypes = [u32p, C.c_uint32, u32p, u32p]
+    lib.so_wire_seeded_row0.argtypes = [u8p, u64p]
+    lib.so_wire_query_bytes.restype = sz
+    lib.so_wire_query_bytes.argtypes = [C.c_uint32]
+    lib.so_wire_query_expand.restype = C.c_int
+    lib.so_wire_query_expand.argtypes = [u8p, sz, u64p]
+    lib.so_wire_query_pack_full.argtypes = [u64p, u8p]
+    lib.so_client_spiral_query_wire.argtypes = [C.c_void_p, sz, C.c_uint32, u8p]
+    lib.so_records_to_plaintexts.argtypes = [u64p, u8p, sz, C.c_uint64]
     _lib = lib
     return lib
+
+
+WIRE_SEEDED, WIRE_FULL = 1, 2
+
+
+def ptr8(a):
+    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def wire_expand(lib, wire):
+    """Wire query (bytes as a uint8 array) -> 2x1 ref-NTT ciphertext, or None when the oracle rejects the buffer."""
+    q = np.zeros(2 * 2 * N, dtype=np.uint64)
+    rc = lib.so_wire_query_expand(ptr8(wire), wire.size, ptr(q))
+    return q if rc == 0 else None
 
 
 def ptr(a):
@@ -192,6 +218,17 @@ class SpiralSession:
         q = np.zeros(2 * 2 * N, dtype=np.uint64)
         self.lib.so_client_spiral_query(self.client, idx, ptr(q))
         return q
+
+    def query_wire(self, idx, kind=WIRE_SEEDED):
+        wire = np.zeros(self.lib.so_wire_query_bytes(kind), dtype=np.uint8)
+        self.lib.so_client_spiral_query_wire(self.client, idx, kind, ptr8(wire))
+        return wire
+
+    def records(self):
+        """The planted plaintexts as the flat record stream of the DB file format (log2(p_db) bits per coefficient)."""
+        bits = int(self.prm.p_db).bit_length() - 1
+        assert bits in (8, 16)
+        return np.ascontiguousarray(self.pts.astype(np.uint8 if bits == 8 else np.uint16).reshape(-1)).view(np.uint8)
 
     def oracle_answer(self, q, Bbuf):
         final_ct = np.zeros(6 * N, dtype=np.uint64)
