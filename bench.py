@@ -622,6 +622,36 @@ def b200_main(args):
     e2e_ms = e_begin.elapsed_time(e_end)
     clocks = sampler.stop() if rank == 0 else None
 
+    # the same exchange in wire form: seed-compressed query in (14 376 B), QPBITS-packed response out;
+    # seed expansion + unpacking are the first node of the expansion graph, the response packer one extra launch
+    e2e_wire = None
+    if world == 1 and wl["kind"] == "spiral":
+        srv = drv.srv
+        wbytes = int(lib.sb200_wire_query_bytes(1))
+        wrng = np.random.default_rng(11)
+        wire = wrng.integers(0, 256, wbytes, dtype=np.uint8)
+        wire[:8] = np.frombuffer(b"SB2Q\x01\x00\x00\x00", dtype=np.uint8)
+        wire_host = torch.from_numpy(wire).pin_memory()
+        pbytes = int(lib.sb200_server_packed_response_bytes(srv.h))
+        packed_host = torch.empty(pbytes // 8, dtype=torch.int64).pin_memory()
+
+        def wire_query():
+            rc = lib.sb200_server_answer_wire(srv.h, wire_host.data_ptr(), wbytes, packed_host.data_ptr(), stream)
+            if rc != 0:
+                raise SystemExit("answer_wire failed: " + lib.sb200_last_error().decode())
+        for _ in range(3):
+            wire_query()
+        w_begin, w_end = ev(), ev()
+        torch.cuda.synchronize()
+        w_begin.record()
+        for _ in range(args.steps):
+            wire_query()                                       # synchronises the stream: the caller holds the packed response
+        w_end.record()
+        torch.cuda.synchronize()
+        e2e_wire = {"value": w_begin.elapsed_time(w_end) / args.steps, "unit": "ms", "h2d_bytes_per_step": wbytes, "d2h_bytes_per_step": pbytes,
+                    "note": "sb200_server_answer_wire: seeded wire query (ChaCha20 row 0) in, packed response out"}
+        drv.upload(stream)                                     # back to the plain query for the sections below
+
     # serving throughput on ONE GPU: several clients in flight (views over the same resident database, one stream
     # each).  The latency-bound expansion / fold chains of one query overlap the HBM-bound scan of another.
     pipelined = None
@@ -872,6 +902,8 @@ def b200_main(args):
             "e2e": {"value": e2e_ms / args.steps, "unit": "ms", "h2d_bytes_per_step": drv.h2d_bytes, "d2h_bytes_per_step": drv.d2h_bytes},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if e2e_wire is not None:
+            line["e2e_wire"] = e2e_wire
         if pipelined is not None:
             line["pipelined"] = pipelined
         if world == 1 and not args.no_cpu_baseline:

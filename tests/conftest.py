@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# Run order: the oracle's own pins first, then the hot path from its leaves outwards (parity cases, whole queries, full
+# sizes, Pack, tensor cores, the reference harness), then the rows of SURVEY 8f that sit either side of the path.
+_ORDER = ["test_abi", "test_oracle_golden", "test_oracle_e2e", "test_oracle_wire", "test_shard_gloo", "test_gpu_parity", "test_gpu_e2e",
+          "test_gpu_fullsize", "test_gpu_pack", "test_gpu_tc", "test_gpu_dropin", "test_gpu_wire", "test_gpu_client"]
+
+
+def pytest_collection_modifyitems(session, config, items):
+    def key(item):
+        name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+        return _ORDER.index(name) if name in _ORDER else len(_ORDER)
+    items.sort(key=key)            # stable: the order inside a file is kept
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from tests import oracle_lib
