@@ -29,7 +29,15 @@ struct so_client {
     uint64_t *Sp;       /* n0 x 1 raw */
     uint64_t *sr;       /* 1 x 1 raw  */
     double cdf[2 * 64 + 1];
+    /* counter-based randomness (so_client_new_chacha): every random polynomial is a ChaCha20 stream named by an object id,
+     * so a parallel implementation (the CUDA client, spiral_b200/csrc/client_kernels.cu) can be compared bit for bit */
+    int chacha;
+    uint32_t key[8];
+    uint64_t thr[128];  /* Gaussian thresholds: floor(cdf[k] * 2^53) + 1 */
 };
+#define CC_MAGIC 0x43324253u            /* "SB2C" */
+#define CC_OBJ(cls, idx) (((uint32_t)(cls) << 24) | (uint32_t)(idx))
+enum { CC_KEYS = 1, CC_W_RIGHT = 2, CC_W_LEFT = 3, CC_W_CONV = 4, CC_V_CONV = 5, CC_QUERY = 6 };
 
 static uint64_t *xalloc(size_t words) {
     uint64_t *p = (uint64_t *)calloc(words ? words : 1, sizeof(uint64_t));
@@ -51,6 +59,32 @@ static uint64_t sample_u64(so_client *c) {                 /* src/client.cpp:7-1
     int64_t v = k - 64;
     return (uint64_t)((v + (int64_t)SO_Q) % (int64_t)SO_Q);
 }
+/* uniform polynomial in NTT form ([2][N]): slot (n, z) from block(counter = n*N + z, nonce = {"SB2C", obj, sub}), the first of
+ * its 16 words whose low 28 bits are below the prime (as so_wire_seeded_row0) */
+static void cc_uniform_ntt(const so_client *c, uint32_t obj, uint32_t sub, uint64_t *out) {
+    uint32_t nonce[3] = {CC_MAGIC, obj, sub}, blk[16];
+    for (uint32_t n = 0; n < 2; n++) {
+        const uint32_t q = (uint32_t)(n == 0 ? SO_P : SO_B);
+        for (uint32_t z = 0; z < N; z++) {
+            so_chacha20_block(c->key, n * N + z, nonce, blk);
+            uint32_t v = (blk[15] & 0x0FFFFFFFu) % q;
+            for (int k = 0; k < 16; k++) { uint32_t w = blk[k] & 0x0FFFFFFFu; if (w < q) { v = w; break; } }
+            out[n * N + z] = v;
+        }
+    }
+}
+/* discrete Gaussian polynomial in raw form: coefficient z from block(counter = z, nonce = {"SB2C", obj, sub}): U = the top 53 bits
+ * of words (1,0); value = -64 + #{k < 128 : U >= thr[k]} - the inverse-CDF walk of sample_u64 on u = U / 2^53, in integers */
+static void cc_gauss_raw(const so_client *c, uint32_t obj, uint32_t sub, uint64_t *out) {
+    uint32_t nonce[3] = {CC_MAGIC, obj, sub}, blk[16];
+    for (uint32_t z = 0; z < N; z++) {
+        so_chacha20_block(c->key, z, nonce, blk);
+        uint64_t U = (((uint64_t)blk[1] << 32) | blk[0]) >> 11;
+        int64_t v = -64;
+        for (int k = 0; k < 128; k++) v += (U >= c->thr[k]);
+        out[z] = v < 0 ? SO_Q - (uint64_t)(-v) : (uint64_t)v;
+    }
+}
 static void noise(so_client *c, uint64_t *E, size_t npolys) { for (size_t i = 0; i < npolys * N; i++) E[i] = sample_u64(c); }
 
 so_client *so_client_new(const so_params *prm, uint64_t seed, int nonoise) {
@@ -65,10 +99,45 @@ so_client *so_client_new(const so_params *prm, uint64_t seed, int nonoise) {
     c->nonoise = saved;
     return c;
 }
+so_client *so_client_new_chacha(const so_params *prm, const uint8_t seed[32]) {
+    so_client *c = (so_client *)calloc(1, sizeof(so_client));
+    c->prm = *prm; c->chacha = 1;
+    for (int i = 0; i < 8; i++) c->key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+    build_cdf(c);
+    for (int k = 0; k < 128; k++) c->thr[k] = (uint64_t)floor(c->cdf[k] * 9007199254740992.0) + 1;
+    c->Sp = xalloc(SO_N0 * N); c->sr = xalloc(N);
+    cc_gauss_raw(c, CC_OBJ(CC_KEYS, 0), 0, c->sr);
+    for (size_t r = 0; r < SO_N0; r++) cc_gauss_raw(c, CC_OBJ(CC_KEYS, 1 + r), 0, &c->Sp[r * N]);
+    return c;
+}
+void so_client_gaussian_thresholds(const so_client *c, uint64_t *out128) { memcpy(out128, c->thr, sizeof(c->thr)); }
+void so_client_secret(const so_client *c, uint64_t *sr, uint64_t *Sp) {
+    memcpy(sr, c->sr, N * sizeof(uint64_t)); memcpy(Sp, c->Sp, SO_N0 * N * sizeof(uint64_t));
+}
 void so_client_free(so_client *c) { if (c) { free(c->Sp); free(c->sr); free(c); } }
 
 /* P (2x1 NTT) = [to_ntt(Q - a) ; a*s + e]   (getRegevSample) */
-static void regev_sample(so_client *c, uint64_t *P_ntt) {
+/* (-row 0) * s + e, row 0 given in NTT form, e in raw form */
+static void regev_row1_from_row0(so_client *c, uint64_t *P_ntt, const uint64_t *e_raw) {
+    uint64_t *a_ntt = xalloc(PL), *s_ntt = xalloc(PL), *e_ntt = xalloc(PL);
+    for (size_t z = 0; z < N; z++) {
+        a_ntt[z] = (SO_P - P_ntt[z]) % SO_P;
+        a_ntt[N + z] = (SO_B - P_ntt[N + z]) % SO_B;
+    }
+    so_to_ntt(s_ntt, c->sr, 1); so_to_ntt(e_ntt, e_raw, 1);
+    so_multiply(P_ntt + PL, a_ntt, s_ntt, 1, 1, 1);
+    so_add(P_ntt + PL, P_ntt + PL, e_ntt, 1);
+    free(a_ntt); free(s_ntt); free(e_ntt);
+}
+static void regev_sample(so_client *c, uint64_t *P_ntt, uint32_t obj) {
+    if (c->chacha) {                                   /* row 0 = -a drawn directly in NTT form */
+        uint64_t *e = xalloc(N);
+        cc_uniform_ntt(c, obj, 0, P_ntt);
+        cc_gauss_raw(c, obj, 1, e);
+        regev_row1_from_row0(c, P_ntt, e);
+        free(e);
+        return;
+    }
     uint64_t *a = xalloc(N), *e = xalloc(N), *a_inv = xalloc(N);
     uint64_t *a_ntt = xalloc(PL), *s_ntt = xalloc(PL), *e_ntt = xalloc(PL), *b = xalloc(PL);
     so_fill_uniform_raw(a, N, &c->rng);
@@ -82,24 +151,41 @@ static void regev_sample(so_client *c, uint64_t *P_ntt) {
     free(a); free(e); free(a_inv); free(a_ntt); free(s_ntt); free(e_ntt); free(b);
 }
 /* encryptSimpleRegev(sigma): 2x1 NTT */
-static void encrypt_simple_regev(so_client *c, uint64_t *out_ntt, const uint64_t *sigma_raw) {
+static void encrypt_simple_regev(so_client *c, uint64_t *out_ntt, const uint64_t *sigma_raw, uint32_t obj) {
     uint64_t *sig_ntt = xalloc(PL);
-    regev_sample(c, out_ntt);
+    regev_sample(c, out_ntt, obj);
     so_to_ntt(sig_ntt, sigma_raw, 1);
     so_add(out_ntt + PL, out_ntt + PL, sig_ntt, 1);
     free(sig_ntt);
 }
 /* encryptSimpleRegevMatrix(s, mat_to_enc (1 x m NTT)) -> 2 x m NTT */
-static void encrypt_simple_regev_matrix(so_client *c, uint64_t *out, const uint64_t *mat_ntt, size_t m) {
+static void encrypt_simple_regev_matrix(so_client *c, uint64_t *out, const uint64_t *mat_ntt, size_t m, uint32_t obj_base) {
     uint64_t P[2 * 2 * SO_N];
     for (size_t i = 0; i < m; i++) {
-        regev_sample(c, P);
+        regev_sample(c, P, obj_base + (uint32_t)i);
         memcpy(&out[(0 * m + i) * PL], P, PL * sizeof(uint64_t));
         so_add(&out[(1 * m + i) * PL], P + PL, &mat_ntt[i * PL], 1);
     }
 }
 /* get_fresh_public_key_raw(Sp, m) -> to_ntt(P), P = [Q - A ; Sp*A + E]  (n1 x m) */
-static void fresh_public_key_ntt(so_client *c, uint64_t *P_ntt, size_t m) {
+static void fresh_public_key_ntt(so_client *c, uint64_t *P_ntt, size_t m, uint32_t cls) {
+    if (c->chacha) {       /* column k: row 0 = -A_k uniform in NTT form (object (cls, k), stream 0), E[r][k] Gaussian (stream 1 + r) */
+        uint64_t *a_ntt = xalloc(PL), *e = xalloc(N), *e_ntt = xalloc(PL), *Sp_ntt = xalloc(SO_N0 * PL), *prod = xalloc(PL);
+        so_to_ntt(Sp_ntt, c->Sp, SO_N0);
+        for (size_t k = 0; k < m; k++) {
+            uint64_t *row0 = &P_ntt[k * PL];
+            cc_uniform_ntt(c, CC_OBJ(cls, k), 0, row0);
+            for (size_t z = 0; z < N; z++) { a_ntt[z] = (SO_P - row0[z]) % SO_P; a_ntt[N + z] = (SO_B - row0[N + z]) % SO_B; }
+            for (size_t r = 0; r < SO_N0; r++) {
+                cc_gauss_raw(c, CC_OBJ(cls, k), 1 + (uint32_t)r, e);
+                so_to_ntt(e_ntt, e, 1);
+                so_multiply(prod, &Sp_ntt[r * PL], a_ntt, 1, 1, 1);
+                so_add(&P_ntt[((1 + r) * m + k) * PL], prod, e_ntt, 1);
+            }
+        }
+        free(a_ntt); free(e); free(e_ntt); free(Sp_ntt); free(prod);
+        return;
+    }
     uint64_t *A = xalloc(m * N), *E = xalloc(SO_N0 * m * N), *A_ntt = xalloc(m * PL), *E_ntt = xalloc(SO_N0 * m * PL);
     uint64_t *Sp_ntt = xalloc(SO_N0 * PL), *Bp = xalloc(SO_N0 * m * PL), *P_raw = xalloc(SO_N1 * m * N);
     so_fill_uniform_raw(A, m * N, &c->rng);
@@ -120,7 +206,7 @@ size_t so_client_w_exp_right_count(const so_params *prm) {
     return stop > 0 ? stop + 1 : g;
 }
 
-static void expansion_keys(so_client *c, uint64_t *W, size_t count, uint32_t t) {   /* getPublicEncryptions */
+static void expansion_keys(so_client *c, uint64_t *W, size_t count, uint32_t t, uint32_t cls) {   /* getPublicEncryptions */
     uint64_t *G = xalloc((size_t)t * N), *G_ntt = xalloc((size_t)t * PL), *tau = xalloc(N), *tau_ntt = xalloc(PL), *prod = xalloc((size_t)t * PL);
     so_build_gadget(G, 1, t);
     so_to_ntt(G_ntt, G, t);
@@ -128,7 +214,7 @@ static void expansion_keys(so_client *c, uint64_t *W, size_t count, uint32_t t) 
         so_automorph(tau, c->sr, 1, (N >> i) + 1);
         so_to_ntt(tau_ntt, tau, 1);
         so_multiply(prod, tau_ntt, G_ntt, 1, 1, t);
-        encrypt_simple_regev_matrix(c, &W[i * 2 * t * PL], prod, t);
+        encrypt_simple_regev_matrix(c, &W[i * 2 * t * PL], prod, t, CC_OBJ(cls, i * t));
     }
     free(G); free(G_ntt); free(tau); free(tau_ntt); free(prod);
 }
@@ -136,8 +222,8 @@ static void expansion_keys(so_client *c, uint64_t *W, size_t count, uint32_t t) 
 void so_client_spiral_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *W_conv, uint64_t *V_conv) {
     const so_params *p = &c->prm;
     size_t g, stop; so_spiral_expansion_shape(p, &g, &stop);
-    expansion_keys(c, W_exp_right, so_client_w_exp_right_count(p), p->t_exp_right);   /* order as :2093-2094 */
-    expansion_keys(c, W_exp_left, g, p->t_exp);
+    expansion_keys(c, W_exp_right, so_client_w_exp_right_count(p), p->t_exp_right, CC_W_RIGHT);   /* order as :2093-2094 */
+    expansion_keys(c, W_exp_left, g, p->t_exp, CC_W_LEFT);
 
     size_t mc = p->t_conv, m = 2 * mc;
     uint64_t *s0_ntt = xalloc(PL), *Sp_ntt = xalloc(SO_N0 * PL);
@@ -147,7 +233,7 @@ void so_client_spiral_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W
         so_build_gadget(G, SO_N0, m);
         so_to_ntt(G_ntt, G, SO_N0 * m);
         so_mul_by_const(s0G, s0_ntt, G_ntt, SO_N0 * m);
-        fresh_public_key_ntt(c, P, m);
+        fresh_public_key_ntt(c, P, m, CC_W_CONV);
         memcpy(W_conv, P, m * PL * sizeof(uint64_t));
         so_add(W_conv + m * PL, P + m * PL, s0G, SO_N0 * m);
         free(G); free(G_ntt); free(s0G); free(P);
@@ -159,7 +245,7 @@ void so_client_spiral_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W
         so_mul_by_const(tog, s0_ntt, gv_ntt, mc);
         memcpy(tog + mc * PL, gv_ntt, mc * PL * sizeof(uint64_t));
         so_multiply(res, Sp_ntt, tog, SO_N0, 1, m);
-        fresh_public_key_ntt(c, P, m);
+        fresh_public_key_ntt(c, P, m, CC_V_CONV);
         memcpy(V_conv, P, m * PL * sizeof(uint64_t));
         so_add(V_conv + m * PL, P + m * PL, res, SO_N0 * m);
         free(gv); free(gv_ntt); free(tog); free(res); free(P);
@@ -208,8 +294,20 @@ static uint64_t *query_sigma(so_client *c, size_t idx_target) {   /* :2098-2157 
 }
 void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv) {
     uint64_t *sigma = query_sigma(c, idx_target);
-    encrypt_simple_regev(c, query_cv, sigma);
+    encrypt_simple_regev(c, query_cv, sigma, CC_OBJ(CC_QUERY, 0));
     free(sigma);
+}
+/* counter-based client: seeded wire query with the wire seed and the query number chosen by the caller
+ * (row 0 from the wire seed as so_wire_seeded_row0, noise = Gaussian object (CC_QUERY, query_id), stream 1) */
+void so_client_chacha_query_wire(so_client *c, size_t idx_target, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire) {
+    uint64_t *sigma = query_sigma(c, idx_target), *P = xalloc(2 * PL), *e = xalloc(N), *sig_ntt = xalloc(PL);
+    so_wire_seeded_row0(wire_seed, P);
+    cc_gauss_raw(c, CC_OBJ(CC_QUERY, query_id), 1, e);
+    regev_row1_from_row0(c, P, e);
+    so_to_ntt(sig_ntt, sigma, 1);
+    so_add(P + PL, P + PL, sig_ntt, 1);
+    so_wire_query_pack_seeded(wire_seed, P + PL, wire);
+    free(sigma); free(P); free(e); free(sig_ntt);
 }
 /* The same query in its wire form (wire_format.h).  SEEDED: row 0 of the Regev sample (the uniformly random -a,
  * getRegevSample src/client.cpp:141-157) is drawn from a 32-byte seed directly in NTT form, so only the seed and
@@ -218,7 +316,7 @@ void so_client_spiral_query_wire(so_client *c, size_t idx_target, uint32_t kind,
     uint64_t *sigma = query_sigma(c, idx_target);
     if (kind == SO_WIRE_QUERY_FULL) {
         uint64_t *cv = xalloc(2 * PL);
-        encrypt_simple_regev(c, cv, sigma);
+        encrypt_simple_regev(c, cv, sigma, CC_OBJ(CC_QUERY, 0));
         so_wire_query_pack_full(cv, wire);
         free(cv);
     } else {

@@ -6,6 +6,12 @@ extern "C" {
 #endif
 typedef struct so_client so_client;
 so_client *so_client_new(const so_params *prm, uint64_t seed, int nonoise);
+/* the same client with counter-based randomness (ChaCha20 streams named by object ids, see client_sim.c): the statement the
+ * CUDA client (include/spiral_b200.h, sb200_client_*) is compared with bit for bit */
+so_client *so_client_new_chacha(const so_params *prm, const uint8_t seed[32]);
+void so_client_gaussian_thresholds(const so_client *c, uint64_t *out128);
+void so_client_secret(const so_client *c, uint64_t *sr_raw, uint64_t *Sp_raw);
+void so_client_chacha_query_wire(so_client *c, size_t idx_target, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire);
 void so_client_free(so_client *c);
 size_t so_client_w_exp_right_count(const so_params *prm);
 /* W_exp_left: g x (2 x t_exp); W_exp_right: count x (2 x t_exp_right); W_conv, V_conv: 3 x 2*t_conv (all ref-NTT) */

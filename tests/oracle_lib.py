@@ -124,6 +124,11 @@ def load():
     lib.so_wire_query_pack_full.argtypes = [u64p, u8p]
     lib.so_client_spiral_query_wire.argtypes = [C.c_void_p, sz, C.c_uint32, u8p]
     lib.so_records_to_plaintexts.argtypes = [u64p, u8p, sz, C.c_uint64]
+    lib.so_client_new_chacha.restype = C.c_void_p
+    lib.so_client_new_chacha.argtypes = [C.POINTER(SoParams), u8p]
+    lib.so_client_gaussian_thresholds.argtypes = [C.c_void_p, u64p]
+    lib.so_client_secret.argtypes = [C.c_void_p, u64p, u64p]
+    lib.so_client_chacha_query_wire.argtypes = [C.c_void_p, sz, C.c_uint32, u8p, u8p]
     _lib = lib
     return lib
 
@@ -190,7 +195,8 @@ def canon(a, kind):
 class SpiralSession:
     """Test-side client + CPU reference pipeline for one parameter set (small sizes only)."""
 
-    def __init__(self, lib, cfg, nu1, nu2, seed=1, nonoise=False):
+    def __init__(self, lib, cfg, nu1, nu2, seed=1, nonoise=False, chacha_seed=None):
+        """chacha_seed (32 bytes): the counter-based client the CUDA client is compared with (so_client_new_chacha)."""
         self.lib, self.prm = lib, make_params(cfg, nu1, nu2)
         p = self.prm
         g, stop = C.c_size_t(), C.c_size_t()
@@ -198,7 +204,10 @@ class SpiralSession:
         self.g, self.stopround = g.value, stop.value
         self.dim0, self.num_per = 1 << nu1, 1 << nu2
         self.total_n = self.dim0 * self.num_per
-        self.client = lib.so_client_new(C.byref(p), seed, int(nonoise))
+        if chacha_seed is None:
+            self.client = lib.so_client_new(C.byref(p), seed, int(nonoise))
+        else:
+            self.client = lib.so_client_new_chacha(C.byref(p), ptr8(np.frombuffer(bytes(chacha_seed), dtype=np.uint8).copy()))
         PL = 2 * N
         n_right = lib.so_client_w_exp_right_count(C.byref(p))
         self.W_left = np.zeros(self.g * 2 * p.t_exp * PL, dtype=np.uint64)
@@ -223,6 +232,16 @@ class SpiralSession:
         wire = np.zeros(self.lib.so_wire_query_bytes(kind), dtype=np.uint8)
         self.lib.so_client_spiral_query_wire(self.client, idx, kind, ptr8(wire))
         return wire
+
+    def chacha_query_wire(self, idx, query_id, wire_seed):
+        wire = np.zeros(self.lib.so_wire_query_bytes(WIRE_SEEDED), dtype=np.uint8)
+        self.lib.so_client_chacha_query_wire(self.client, idx, query_id, ptr8(np.frombuffer(bytes(wire_seed), dtype=np.uint8).copy()), ptr8(wire))
+        return wire
+
+    def secret(self):
+        sr, Sp = np.zeros(N, dtype=np.uint64), np.zeros(2 * N, dtype=np.uint64)
+        self.lib.so_client_secret(self.client, ptr(sr), ptr(Sp))
+        return sr, Sp
 
     def records(self):
         """The planted plaintexts as the flat record stream of the DB file format (log2(p_db) bits per coefficient)."""

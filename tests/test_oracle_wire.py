@@ -102,3 +102,24 @@ def test_records_to_plaintexts(lib):
         out = np.zeros(n, dtype=np.uint64)
         lib.so_records_to_plaintexts(ol.ptr(out), ol.ptr8(np.ascontiguousarray(rec)), n, p_db)
         assert np.array_equal(out, vals)
+
+
+def test_counter_based_client_end_to_end(lib):
+    """The ChaCha-stream client (the statement the CUDA client is compared with): keys, public parameters and a seeded wire
+    query drive the oracle's server to a response that decodes to the planted record; secrets are small and seed-dependent."""
+    seed = bytes(range(32))
+    s = ol.SpiralSession(lib, "cfg1", 3, 2, seed=5, chacha_seed=seed)
+    sr, Sp = s.secret()
+    centred = np.where(sr > ol.Q // 2, sr.astype(np.int64) - ol.Q, sr.astype(np.int64))
+    assert np.abs(centred).max() <= 64 and 1.5 < centred.std() < 3.5          # width 6.4 <-> sigma = 6.4 / sqrt(2 pi) = 2.55
+    Bbuf = s.reference_db()
+    for qid, idx in enumerate((0, 13, s.total_n - 1)):
+        wire = s.chacha_query_wire(idx, qid, bytes([qid + 1] * 32))
+        resp, _, _ = s.oracle_answer(ol.wire_expand(lib, wire), Bbuf)
+        assert np.array_equal(s.decode(resp), s.pts[idx])
+    # the same (wire seed, query id) gives the same bytes; another query id changes only the noise, i.e. row 1
+    a = s.chacha_query_wire(5, 7, bytes([9] * 32)); b = s.chacha_query_wire(5, 7, bytes([9] * 32)); c = s.chacha_query_wire(5, 8, bytes([9] * 32))
+    assert np.array_equal(a, b) and np.array_equal(a[:40], c[:40]) and not np.array_equal(a, c)
+    t = ol.SpiralSession(lib, "cfg1", 3, 2, seed=5, chacha_seed=bytes(range(1, 33)))
+    assert not np.array_equal(t.secret()[0], sr)
+    s.close(); t.close()
