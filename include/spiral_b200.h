@@ -297,6 +297,32 @@ int sb200_pack_server_load_db_records_file(sb200_pack_server *srv, const char *p
 int sb200_pack_server_save_db(sb200_pack_server *srv, const char *path);
 int sb200_pack_server_load_db_snapshot(sb200_pack_server *srv, const char *path);
 
+
+/* ---- the client on the GPU ------------------------------------------------------------------------
+ * Key generation (src/client.cpp:23-47), public parameters (getPublicEncryptions src/client.cpp:271-290; W and V,
+ * src/spiral.cpp:2207-2290), query encoding + encryption (src/spiral.cpp:2098-2157, encryptSimpleRegev src/client.cpp:170-186)
+ * and decoding (check_final, src/spiral.cpp:1428-1476 - the reference's only use of Intel HEXL).  Spiral / SpiralStream
+ * parameter sets (matrix-Regev responses).  The reference draws from an unseeded std::random_device; here all randomness
+ * derives from the 32-byte seed given at creation: every random polynomial is a ChaCha20 (RFC 8439) stream with nonce
+ * {"SB2C", object id, stream}, uniform polynomials drawn directly in NTT form, Gaussian ones (width 6.4, support [-64, 64],
+ * src/core.cpp:182-207) by inverse CDF on 53-bit uniforms.  oracle/client_sim.c (so_client_new_chacha) states the same client
+ * in plain C; the two agree bit for bit. */
+typedef struct sb200_client sb200_client;
+int sb200_client_create(sb200_client **out, const sb200_params *prm, int device, const uint8_t *seed32);
+void sb200_client_destroy(sb200_client *c);
+/* polynomial counts of the four public-parameter matrices (W_exp_left, W_exp_right, W_conv, V_conv), 2*2048 words each */
+int sb200_client_public_param_polys(const sb200_client *c, size_t *out4);
+/* ref-NTT host buffers, exactly what sb200_server_set_public_params takes */
+int sb200_client_public_params(sb200_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *W_conv, uint64_t *V_conv);
+/* SEEDED wire query for record idx_target: row 0 from wire_seed32 (what the server regenerates), noise from the client's own
+ * stream number query_id (< 2^24; never reuse one with the same client seed); wire_out: sb200_wire_query_bytes(1) bytes */
+int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out);
+/* total_resp: 3x2 raw response (sb200_server_answer, or sb200_unpack_response of the packed one) -> 2x2 plaintext polynomials */
+int sb200_client_decode(sb200_client *c, const uint64_t *total_resp_host, uint64_t *pt_out_host);
+/* test taps: the secret key (raw, 1 + 2 polynomials) and the sampler's 128 integer thresholds */
+int sb200_client_secret(sb200_client *c, uint64_t *sr_raw_host, uint64_t *Sp_raw_host);
+int sb200_client_gaussian_thresholds(uint64_t *out128);
+
 #ifdef __cplusplus
 }
 #endif

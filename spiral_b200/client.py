@@ -1,0 +1,65 @@
+"""Host-side face of the GPU client (sb200_client_*): key generation, public parameters, query generation and decoding.
+
+The reference's client lives in src/client.cpp and the client statements of src/spiral.cpp (runConversionImproved :2040-2335,
+check_final :1428-1476); names follow it.  All randomness derives from the 32-byte seed."""
+import ctypes as C
+
+import numpy as np
+
+from .lib import SpiralParams, check, load_library
+
+N = 2048
+_P64 = C.POINTER(C.c_uint64)
+
+
+def _p64(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_P64)
+
+
+class SpiralClient:
+    def __init__(self, params: SpiralParams, seed: bytes, device=0):
+        assert len(seed) == 32
+        self.lib = load_library()
+        self.params = params
+        h = C.c_void_p()
+        self._seed = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+        check(self.lib.sb200_client_create(C.byref(h), C.byref(params), device, self._seed.ctypes.data), self.lib)
+        self.h = h
+
+    def public_params(self):
+        """(W_exp_left, W_exp_right, W_conv, V_conv) as ref-NTT uint64 arrays - the arguments of SpiralServer.set_public_params."""
+        polys = (C.c_size_t * 4)()
+        check(self.lib.sb200_client_public_param_polys(self.h, polys), self.lib)
+        mats = [np.zeros(int(n) * 2 * N, dtype=np.uint64) for n in polys]
+        check(self.lib.sb200_client_public_params(self.h, *[_p64(m) for m in mats]), self.lib)
+        return mats
+
+    def query_wire(self, idx, query_id, wire_seed: bytes):
+        assert len(wire_seed) == 32
+        seed = np.frombuffer(bytes(wire_seed), dtype=np.uint8).copy()
+        wire = np.zeros(self.lib.sb200_wire_query_bytes(1), dtype=np.uint8)
+        check(self.lib.sb200_client_query_wire(self.h, idx, query_id, seed.ctypes.data, wire.ctypes.data), self.lib)
+        return wire
+
+    def decode(self, total_resp):
+        """3x2 raw response -> (4, 2048) plaintext coefficients (the record's 2x2 matrix of polynomials)."""
+        pt = np.zeros(4 * N, dtype=np.uint64)
+        check(self.lib.sb200_client_decode(self.h, _p64(np.ascontiguousarray(total_resp, dtype=np.uint64)), _p64(pt)), self.lib)
+        return pt.reshape(4, N)
+
+    def secret(self):
+        sr, Sp = np.zeros(N, dtype=np.uint64), np.zeros(2 * N, dtype=np.uint64)
+        check(self.lib.sb200_client_secret(self.h, _p64(sr), _p64(Sp)), self.lib)
+        return sr, Sp
+
+    def close(self):
+        if self.h:
+            self.lib.sb200_client_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -31,10 +31,10 @@ __device__ __forceinline__ void chacha_qr(uint32_t &a, uint32_t &b, uint32_t &c,
     a += b; d ^= a; d = __funnelshift_l(d, d, 8);
     c += d; b ^= c; b = __funnelshift_l(b, b, 7);
 }
-// RFC 8439 section 2.3 block function; nonce = {"SB2Q", 0, 0}
-__device__ __forceinline__ void chacha20_block(uint32_t (&x)[16], const uint32_t (&key)[8], uint32_t counter) {
+// RFC 8439 section 2.3 block function
+__device__ __forceinline__ void chacha20_block(uint32_t (&x)[16], const uint32_t (&key)[8], uint32_t counter, uint32_t n0, uint32_t n1, uint32_t n2) {
     uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
-                      key[4], key[5], key[6], key[7], counter, kWireQueryMagic, 0u, 0u};
+                      key[4], key[5], key[6], key[7], counter, n0, n1, n2};
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = s[i];
 #pragma unroll
@@ -44,6 +44,14 @@ __device__ __forceinline__ void chacha20_block(uint32_t (&x)[16], const uint32_t
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] += s[i];
+}
+// uniform residue below q from one block: the FIRST of the 16 words whose low 28 bits are < q (all rejected, probability < 2^-60:
+// the last word reduced)
+__device__ __forceinline__ uint32_t uniform_from_block(const uint32_t (&x)[16], uint32_t q) {
+    uint32_t v = (x[15] & 0x0FFFFFFFu) % q;
+#pragma unroll
+    for (int k = 15; k >= 0; k--) { const uint32_t c = x[k] & 0x0FFFFFFFu; if (c < q) v = c; }
+    return v;
 }
 
 // One launch turns a wire query into cv[0] (dev-NTT, [row][prime][2048]).
@@ -62,11 +70,8 @@ __global__ void __launch_bounds__(kNttThreads) k_query_from_wire(uint32_t *__res
         uint32_t key[8], x[16];
 #pragma unroll
         for (int i = 0; i < 8; i++) key[i] = __ldg(seed + i);
-        chacha20_block(x, key, (uint32_t)slot);
-        uint32_t v = (x[15] & 0x0FFFFFFFu) % q;
-#pragma unroll
-        for (int k = 15; k >= 0; k--) { const uint32_t c = x[k] & 0x0FFFFFFFu; if (c < q) v = c; }   // the FIRST accepted word wins
-        cv[slot] = v;                                                          // row 0 = polynomial 0: [n][z]
+        chacha20_block(x, key, (uint32_t)slot, kWireQueryMagic, 0u, 0u);
+        cv[slot] = uniform_from_block(x, q);                                   // row 0 = polynomial 0: [n][z]
         return;
     }
     const int row = blockIdx.x == 0 ? 1 : 0;
