@@ -446,6 +446,16 @@ class SpiralDriver:
         if self.rank == 0:
             self.resp_host.copy_(self.resp_dev, non_blocking=True)
 
+    # one GPU: the whole resident query / the whole host-buffer query as ONE C-ABI call each (sb200_server_process,
+    # sb200_server_answer) - the call a C++ host makes; the staged calls above remain for the sharded path
+    def process(self, stream, marks):
+        self.srv.process(self.resp_dev.data_ptr(), stream, marks)
+
+    def answer_host(self, stream):
+        rc = self.srv.lib.sb200_server_answer(self.srv.h, self.q_host.data_ptr(), self.resp_host.data_ptr(), stream)
+        if rc != 0:
+            raise SystemExit("sb200_server_answer failed: " + self.srv.lib.sb200_last_error().decode())
+
     def check(self, stream):
         if self.use_p2p and self.srv.xchg_error(stream) != 0:
             raise SystemExit(f"rank {self.rank}: peer exchange timed out (error {self.srv.xchg_error(stream)})")
@@ -563,8 +573,29 @@ def b200_main(args):
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
+    import ctypes
+    fused = world == 1 and hasattr(drv, "process")
+    mark_pool = []
+
+    def new_marks():
+        """Four CUDA events for one query, created up front (torch creates the cudaEvent_t lazily at the first record)."""
+        es = [ev() for _ in range(4)]
+        for e in es:
+            e.record()
+        return es, (ctypes.c_void_p * 4)(*[e.cuda_event for e in es])
+
     def step(timed_events=None, e2e=False):
         """One query.  e2e=True includes the H2D of the query and the D2H of the response."""
+        if fused:
+            if e2e:
+                drv.answer_host(stream)                        # upload, all stages, download, stream synchronised
+            elif timed_events is None or not mark_pool:
+                drv.process(stream, None)
+            else:
+                es, handles = mark_pool.pop()
+                drv.process(stream, handles)
+                timed_events.append(es)
+            return
         if e2e:
             drv.upload(stream)
         marks = []
@@ -594,6 +625,9 @@ def b200_main(args):
         step(timed_events=[])
     barrier()
 
+    if fused:
+        mark_pool.extend(new_marks() for _ in range(args.steps))
+        torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -168,6 +168,10 @@ int sb200_server_set_public_params(sb200_server *srv, const uint64_t *W_exp_left
 /* one query end to end: H2D of the packed query ciphertext (2x1 ref-NTT, 64 KiB), all server stages, D2H of the
  * modulus-switched response (3x2 raw, 96 KiB).  world == 1 only. */
 int sb200_server_answer(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream);
+/* all server stages of the query last uploaded (sb200_server_upload_query[_wire]) in one call, response left in total_resp_dev
+ * (NULL: the server's own buffer); marks: NULL or four cudaEvent_t recorded before the expansion, before and after the
+ * first-dimension scan and at the end.  world == 1 only. */
+int sb200_server_process(sb200_server *srv, uint64_t *total_resp_dev, void *stream, void *const *marks);
 /* same, response in the wire format (sb200_dev_pack_response): 20 KiB instead of 96 KiB at cfg1 */
 int sb200_server_answer_packed(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *packed_resp_host, void *stream);
 size_t sb200_server_packed_response_bytes(const sb200_server *srv);

@@ -979,6 +979,25 @@ extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_hos
     TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
     return sb200_server_download(s, total_resp_host, s->resp.p, 6 * kN, stream);
 }
+// One resident query in ONE call (the query is already in q_stage / q_wire): all server stages into total_resp_dev.  A serving loop
+// written in a scripting language issues one foreign call per query instead of six, so the host stays ahead of the ~1 ms of GPU work.
+// marks (optional): four cudaEvent_t recorded before the expansion, before the scan, after the scan and at the end.
+extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, void *stream, void *const *marks) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->world != 1) return fail(SB200_ERR_STATE, "server_process: single-shard call on a sharded server (use the staged API)");
+    cudaStream_t st = ES(s, stream);
+    uint64_t *resp = total_resp_dev ? total_resp_dev : s->resp.p;
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[0], st));
+    TRY(sb200_server_expand_and_convert(s, stream));
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[1], st));
+    TRY(sb200_server_scan(s, stream));
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[2], st));
+    TRY(sb200_server_lift(s, stream));
+    TRY(sb200_server_fold_local(s, stream));
+    TRY(sb200_server_fold_tail(s, s->cts.p, resp, stream));
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[3], st));
+    return SB200_OK;
+}
 // the same query with the response in its wire format: 20 KiB instead of 96 KiB cross PCIe at cfg1
 extern "C" int sb200_server_answer_packed(sb200_server *s, const uint64_t *query_cv_host, uint64_t *packed_resp_host, void *stream) {
     if (!s || !packed_resp_host) return fail(SB200_ERR_ARG, "server_answer_packed: null argument");

@@ -144,6 +144,7 @@ def load_library():
         "sb200_server_set_public_params": (C.c_int, [vp, u64p, u64p, u64p, u64p]),
         "sb200_server_answer": (C.c_int, [vp, vp, vp, vp]),
         "sb200_server_upload_query": (C.c_int, [vp, vp, vp]),
+        "sb200_server_process": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
         "sb200_server_expand_and_convert": (C.c_int, [vp, vp]),
         "sb200_server_first_dim": (C.c_int, [vp, vp]),
         "sb200_server_fold_local": (C.c_int, [vp, vp]),

@@ -117,6 +117,10 @@ class SpiralServer:
     def expand_and_convert(self, stream=None):
         check(self.lib.sb200_server_expand_and_convert(self.h, stream), self.lib)
 
+    def process(self, resp_ptr=None, stream=None, marks=None):
+        """All server stages of the uploaded query in one call; marks: None or a (c_void_p * 4) of cudaEvent_t handles."""
+        check(self.lib.sb200_server_process(self.h, resp_ptr, stream, marks), self.lib)
+
     def first_dim(self, stream=None):
         check(self.lib.sb200_server_first_dim(self.h, stream), self.lib)
 
