@@ -68,6 +68,8 @@ def cmd_measure(args):
     grid = [("cfg1", a, b) for (a, b) in [(6, 7), (7, 6), (8, 5), (6, 9), (7, 8), (8, 7), (9, 6), (10, 5), (8, 9), (9, 8), (10, 7)]]
     grid += [("cfg5", a, b) for (a, b) in [(6, 9), (7, 8), (8, 7), (9, 6), (9, 8)]]
     grid += [("wiki", a, b) for (a, b) in [(5, 10), (6, 9), (7, 8), (8, 7), (9, 6)]]
+    if args.shapes:
+        grid = [(t.split(":")[0], int(t.split(":")[1].split(",")[0]), int(t.split(":")[1].split(",")[1])) for t in args.shapes.split(";")]
     for name, g in GADGETS.items():
         bench.WORKLOADS.setdefault(name, dict(kind="spiral", prm={k: v for k, v in g.items() if not k.startswith("max_")}))
     torch.cuda.set_device(0)
@@ -172,6 +174,7 @@ def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest="cmd", required=True)
     m = sub.add_parser("measure"); m.add_argument("--out", default="gpurun_out/shape_sweep.json"); m.add_argument("--steps", type=int, default=20)
+    m.add_argument("--shapes", default="", help='subset, e.g. "cfg1:9,6;cfg1:10,5"')
     f = sub.add_parser("fit"); f.add_argument("sweep"); f.add_argument("--out", default="profiles/cost_model_b200.json")
     s = sub.add_parser("select"); s.add_argument("model"); s.add_argument("--log-items", type=int, default=15)
     args = ap.parse_args()

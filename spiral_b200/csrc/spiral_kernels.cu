@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
     pdl_prologue();
     extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4 = 64 bytes per (z, j)
     const int tid = threadIdx.x;
-    const int zl = (U == 1) ? tid / ICT : 0;
-    const int icl = (U == 1) ? tid % ICT : tid;
+    const int TZ = ICT / U;                            // threads per z-slice; thread owns columns icl + u*TZ
+    const int zl = tid / TZ, icl = tid % TZ;
     const int z0 = blockIdx.x * ZT, z = z0 + zl;
     const int ic0 = blockIdx.y * ICT + icl;            // first owned column
-    const bool active = (U == 2) || tid < ZT * ICT;   // tiny IC: surplus threads only help staging
+    const bool active = tid < ZT * TZ;                 // tiny IC: surplus threads only help staging
     const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
 
     uint64_t acc[U][3][2];
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
             const int j = jc0 + jj;
             uint4 d[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) d[u] = ld_stream_u4(dbz + (size_t)j * IC + u * kScanThreads);
+            for (int u = 0; u < U; u++) d[u] = ld_stream_u4(dbz + (size_t)j * IC + u * TZ);
             const uint4 q0 = qz[jj * 4 + 0], q1 = qz[jj * 4 + 1], q2 = qz[jj * 4 + 2], q3 = qz[jj * 4 + 3];
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
     if (active)
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        const int ic = ic0 + u * kScanThreads;
+        const int ic = ic0 + u * TZ;
         const int i = ic >> 1, c = ic & 1;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
@@ -225,14 +225,18 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
     // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
+    // Narrow shards (IC = 64 or 128 columns: a small second dimension, or a database sharded over many GPUs) keep two columns per
+    // thread - one broadcast read of the query slice per two database loads - by giving each z-slice IC/2 threads (a whole number
+    // of warps) and putting 2 or 4 z-slices into the CTA; below 64 columns one column per thread remains.
     const int IC = (int)num_per * 2;
     const int T = 128;
-    const int U = IC >= 256 ? 2 : 1;
+    const int U = IC >= 64 ? 2 : 1;
     const int ICT = IC < T * U ? IC : T * U;
     int ZT = (T * U) / ICT;
     if (ZT > 8) ZT = 8;
+    static const size_t smem_cap = [] { const char *e = getenv("SB200_SCAN_SMEM"); size_t v = e ? (size_t)atol(e) : 0; return v >= 4096 ? v : (size_t)32768; }();
     int JC = (int)dim0;
-    while ((size_t)ZT * JC * 64 > 32768 && JC > kScanFoldEvery) JC >>= 1;
+    while ((size_t)ZT * JC * 64 > smem_cap && JC > kScanFoldEvery) JC >>= 1;
     const size_t smem = (size_t)ZT * JC * 64;
     dim3 grid(kN / ZT, IC / ICT);
     count_launch();

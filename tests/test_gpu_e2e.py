@@ -19,7 +19,9 @@ def sb_params(so):
     return SpiralParams(so.nu1, so.nu2, so.t_gsw, so.t_conv, so.t_exp, so.t_exp_right, so.qp_bits, so.out_n, so.p_db)
 
 
-@pytest.mark.parametrize("cfg,nu1,nu2", [("cfg1", 2, 2), ("cfg1", 4, 1), ("cfg5", 3, 2), ("cfg1", 5, 3), ("cfg1", 6, 2), ("cfg1", 1, 1), ("cfg4", 2, 2), ("cfg3", 4, 2), ("cfg1", 7, 4)])
+# the last two shapes have 64 / 128 database columns per z: the two-columns-per-thread scan with several z-slices per CTA
+@pytest.mark.parametrize("cfg,nu1,nu2", [("cfg1", 2, 2), ("cfg1", 4, 1), ("cfg5", 3, 2), ("cfg1", 5, 3), ("cfg1", 6, 2), ("cfg1", 1, 1), ("cfg4", 2, 2), ("cfg3", 4, 2), ("cfg1", 7, 4),
+                                         ("cfg1", 3, 5), ("cfg1", 2, 6)])
 def test_server_matches_oracle_and_decodes(sb, oracle, cfg, nu1, nu2):
     s = ol.SpiralSession(oracle, cfg, nu1, nu2, seed=11)
     Bbuf = s.reference_db()
