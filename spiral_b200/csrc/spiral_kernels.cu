@@ -147,14 +147,14 @@ __device__ __forceinline__ uint64_t fold_acc(uint64_t a, uint32_t c32) {      //
     return (a & 0xffffffffull) + (uint64_t)(uint32_t)(a >> 32) * c32;
 }
 
-template <int U, int kScanThreads, int UNR>
+template <int U, int kScanThreads, int UNR, bool kFullTile>      // kFullTile: ICT == U * kScanThreads (one z-slice per CTA), strides fold into immediates
 __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
                                                              const uint64_t *__restrict__ db, int dim0, int IC, int ICT,
                                                              int ZT, int JC) {
     pdl_prologue();
     extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4 = 64 bytes per (z, j)
     const int tid = threadIdx.x;
-    const int TZ = ICT / U;                            // threads per z-slice; thread owns columns icl + u*TZ
+    const int TZ = kFullTile ? kScanThreads : ICT / U; // threads per z-slice; thread owns columns icl + u*TZ
     const int zl = tid / TZ, icl = tid % TZ;
     const int z0 = blockIdx.x * ZT, z = z0 + zl;
     const int ic0 = blockIdx.y * ICT + icl;            // first owned column
@@ -240,8 +240,9 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
     const size_t smem = (size_t)ZT * JC * 64;
     dim3 grid(kN / ZT, IC / ICT);
     count_launch();
-    if (U == 2) launch_pdl(k_scan_spiral<2, 128, 4>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else        launch_pdl(k_scan_spiral<1, 128, 4>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    if (U == 2 && ICT == 2 * T) launch_pdl(k_scan_spiral<2, 128, 4, true>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2)            launch_pdl(k_scan_spiral<2, 128, 4, false>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else                        launch_pdl(k_scan_spiral<1, 128, 4, false>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
 }
 
 // ---- batched first dimension: BQ queries answered in ONE pass over the database ------------------------------
