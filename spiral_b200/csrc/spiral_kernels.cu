@@ -225,22 +225,26 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
     // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
+    // The query slice is staged in chunks of at most 16 KiB per CTA: with 32 KiB (first dimensions of 512 and 1024) only 6 CTAs
+    // fit an SM and the scan drops from 6.45 to 5.6-6.0 TB/s (profiles/r01_scan_shapes.md).
     // Narrow shards (IC = 64 or 128 columns: a small second dimension, or a database sharded over many GPUs) keep two columns per
     // thread - one broadcast read of the query slice per two database loads - by giving each z-slice IC/2 threads (a whole number
     // of warps) and putting 2 or 4 z-slices into the CTA; below 64 columns one column per thread remains.
     const int IC = (int)num_per * 2;
-    const int T = 128;
+    static const bool t64 = [] { const char *e = getenv("SB200_SCAN_T64"); return !(e && *e == '0'); }();
+    const int T = (t64 && IC == 64) ? 64 : 128;        // 64-column shards: smaller CTAs spread more evenly over the 148 SMs
     const int U = IC >= 64 ? 2 : 1;
     const int ICT = IC < T * U ? IC : T * U;
     int ZT = (T * U) / ICT;
     if (ZT > 8) ZT = 8;
-    static const size_t smem_cap = [] { const char *e = getenv("SB200_SCAN_SMEM"); size_t v = e ? (size_t)atol(e) : 0; return v >= 4096 ? v : (size_t)32768; }();
+    static const size_t smem_cap = [] { const char *e = getenv("SB200_SCAN_SMEM"); size_t v = e ? (size_t)atol(e) : 0; return v >= 4096 ? v : (size_t)16384; }();
     int JC = (int)dim0;
     while ((size_t)ZT * JC * 64 > smem_cap && JC > kScanFoldEvery) JC >>= 1;
     const size_t smem = (size_t)ZT * JC * 64;
     dim3 grid(kN / ZT, IC / ICT);
     count_launch();
     if (U == 2 && ICT == 2 * T) launch_pdl(k_scan_spiral<2, 128, 4, true>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2 && T == 64) launch_pdl(k_scan_spiral<2, 64, 4, false>, grid, dim3(64), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
     else if (U == 2)            launch_pdl(k_scan_spiral<2, 128, 4, false>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
     else                        launch_pdl(k_scan_spiral<1, 128, 4, false>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
 }
