@@ -45,9 +45,12 @@ def shape_features(nu1, nu2, g):
     """Regressors of one shape: expansion rounds and size, scan bytes, fold rounds and size."""
     ell_bits = g["t_gsw"] * nu2
     rounds = ceil_log2(ell_bits + (1 << nu1))
+    nosplit = float(ell_bits > (1 << nu1))            # stopround == 0: every round carries the 56-digit right-hand key switches
     return {
-        "exp": [1.0, float(rounds), float(1 << nu1), float(ell_bits)],            # launch chain, rounds, first-dim cts, GSW bits
-        "scan": [1.0, float(8 * N * 4 * (1 << (nu1 + nu2)))],                      # fixed + bytes / bandwidth
+        # launch chain, rounds, first-dimension ciphertexts, GSW bits, and the unsplit tree's 2^rounds wide key switches
+        "exp": [1.0, float(rounds), float(1 << nu1), float(ell_bits), nosplit * float(1 << rounds)],
+        # fixed + bytes / bandwidth, one bandwidth per scan tiling (launch_scan_spiral): >= 128, 64, < 64 database columns per z
+        "scan": [1.0] + [float(8 * N * 4 * (1 << (nu1 + nu2))) if cls else 0.0 for cls in (nu2 >= 6, nu2 == 5, nu2 < 5)],
         "fold": [1.0, float(nu2), float(g["t_gsw"] * (1 << nu2))],                 # fixed, rounds, digit NTTs
     }
 
@@ -120,8 +123,8 @@ def cmd_fit(args):
     import numpy as np
     rows = json.load(open(args.sweep))["rows"]
     model = {"source": os.path.basename(args.sweep), "form": {
-        "exp_us": "c0 + c1*rounds + c2*2^nu1 + c3*t_GSW*nu2   (rounds = ceil(log2(2^nu1 + t_GSW*nu2)))",
-        "scan_us": "c0 + c1*db_bytes",
+        "exp_us": "c0 + c1*rounds + c2*2^nu1 + c3*t_GSW*nu2 + c4*[t_GSW*nu2 > 2^nu1]*2^rounds   (rounds = ceil(log2(2^nu1 + t_GSW*nu2)))",
+        "scan_us": "c0 + db_bytes * (c1 if nu2 >= 6 else c2 if nu2 == 5 else c3)   (one bandwidth per scan tiling)",
         "fold_us": "c0 + c1*nu2 + c2*t_GSW*2^nu2"}, "coef": {}, "residual_pct": {}}
     for stage in ("exp", "scan", "fold"):
         X = np.array([shape_features(r["nu1"], r["nu2"], GADGETS[r["cfg"]])[stage] for r in rows])
@@ -130,7 +133,7 @@ def cmd_fit(args):
         pred = X @ coef
         model["coef"][stage] = [float(c) for c in coef]
         model["residual_pct"][stage] = float(np.max(np.abs(pred - y) / y) * 100)
-    model["scan_gbs_asymptotic"] = 1e-3 / model["coef"]["scan"][1]
+    model["scan_gbs_asymptotic"] = [1e-3 / c if c > 0 else None for c in model["coef"]["scan"][1:]]
     with open(args.out, "w") as f:
         json.dump(model, f, indent=1)
     print(json.dumps(model, indent=1))
