@@ -155,11 +155,14 @@ def reference_cost_us(nu1, nu2, g):
 
 def cmd_select(args):
     model = json.load(open(args.model))
-    rows = []
+    rows, skipped = [], []
     for name, g in GADGETS.items():
         for nu1 in range(1, 12):
             nu2 = args.log_items - nu1
             if nu2 < 1 or not feasible(nu1, nu2, g) or nu1 > g["max_nu1"] or nu2 > g["max_nu2"]:
+                continue
+            if nu2 < 5 and model["coef"]["scan"][3] == 0.0:
+                skipped.append((name, nu1, nu2))            # no timing of this scan tiling in the sweep: not ranked
                 continue
             p = predict(model, nu1, nu2, g)
             rows.append((sum(p.values()), name, nu1, nu2, p, reference_cost_us(nu1, nu2, g)))
@@ -168,6 +171,8 @@ def cmd_select(args):
     print("gadgets  nu1 nu2   B200 model us (exp / scan / fold)      reference CPU model us")
     for tot, name, nu1, nu2, p, ref in rows:
         print(f"{name:8s} {nu1:3d} {nu2:3d}   {tot:8.1f} ({p['exp']:6.1f} / {p['scan']:6.1f} / {p['fold']:6.1f})      {ref:12.0f}")
+    if skipped:
+        print("not ranked (fewer than 64 columns per z-slice, no timing in the sweep): " + ", ".join(f"{n} ({a},{b})" for n, a, b in skipped))
     if rows:
         best_ref = min(rows, key=lambda r: r[5])
         print(f"B200 optimum: {rows[0][1]} nu=({rows[0][2]},{rows[0][3]});  CPU-model optimum: {best_ref[1]} nu=({best_ref[2]},{best_ref[3]})")
