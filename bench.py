@@ -574,7 +574,7 @@ def b200_main(args):
         return torch.cuda.Event(enable_timing=True)
 
     import ctypes
-    fused = world == 1 and hasattr(drv, "process")
+    fused = hasattr(drv, "process") and (world == 1 or drv.use_p2p)
     mark_pool = []
 
     def new_marks():
@@ -587,8 +587,10 @@ def b200_main(args):
     def step(timed_events=None, e2e=False):
         """One query.  e2e=True includes the H2D of the query and the D2H of the response."""
         if fused:
-            if e2e:
+            if e2e and world == 1:
                 drv.answer_host(stream)                        # upload, all stages, download, stream synchronised
+            elif e2e:
+                drv.upload(stream); drv.process(stream, None); drv.download()
             elif timed_events is None or not mark_pool:
                 drv.process(stream, None)
             else:

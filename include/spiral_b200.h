@@ -170,7 +170,8 @@ int sb200_server_set_public_params(sb200_server *srv, const uint64_t *W_exp_left
 int sb200_server_answer(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream);
 /* all server stages of the query last uploaded (sb200_server_upload_query[_wire]) in one call, response left in total_resp_dev
  * (NULL: the server's own buffer); marks: NULL or four cudaEvent_t recorded before the expansion, before and after the
- * first-dimension scan and at the end.  world == 1 only. */
+ * first-dimension scan and at the end.  Sharded servers (world > 1, peers connected with sb200_server_xchg_connect): every rank
+ * calls it; the exchange over NVLink peer memory and rank 0's tail folds are part of the call, the response lands on rank 0. */
 int sb200_server_process(sb200_server *srv, uint64_t *total_resp_dev, void *stream, void *const *marks);
 /* same, response in the wire format (sb200_dev_pack_response): 20 KiB instead of 96 KiB at cfg1 */
 int sb200_server_answer_packed(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *packed_resp_host, void *stream);

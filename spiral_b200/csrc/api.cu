@@ -984,7 +984,7 @@ extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_hos
 // marks (optional): four cudaEvent_t recorded before the expansion, before the scan, after the scan and at the end.
 extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, void *stream, void *const *marks) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    if (s->world != 1) return fail(SB200_ERR_STATE, "server_process: single-shard call on a sharded server (use the staged API)");
+    if (s->world > 1 && !s->xchg_connected) return fail(SB200_ERR_STATE, "server_process: sharded server without connected peers (sb200_server_xchg_connect)");
     cudaStream_t st = ES(s, stream);
     uint64_t *resp = total_resp_dev ? total_resp_dev : s->resp.p;
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[0], st));
@@ -994,7 +994,8 @@ extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, v
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[2], st));
     TRY(sb200_server_lift(s, stream));
     TRY(sb200_server_fold_local(s, stream));
-    TRY(sb200_server_fold_tail(s, s->cts.p, resp, stream));
+    // one shard: tail = modulus switch; several: push this shard's ciphertext to rank 0 over NVLink, rank 0 folds the rest
+    TRY(sb200_server_exchange_and_tail(s, resp, stream));
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[3], st));
     return SB200_OK;
 }

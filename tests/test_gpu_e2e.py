@@ -98,8 +98,49 @@ def test_sharded_servers_reproduce_single_gpu_answer(sb, oracle):
             torch.cuda.synchronize()
             got2 = resp.cpu().numpy().view(np.uint64)
             assert np.array_equal(got2, want2), f"world={world} idx={idx} (peer-memory exchange)"
+        # and as ONE call per shard (sb200_server_process: all stages + the exchange), the form bench.py times
+        q3 = s.query(13)
+        want3, _, _ = s.oracle_answer(q3, Bbuf)
+        resp.zero_()
+        torch.cuda.synchronize()
+        for srv in reversed(servers):
+            srv.upload_query(q3)
+            srv.process(resp.data_ptr() if srv.rank == 0 else None)
+        assert all(srv.xchg_error() == 0 for srv in servers)
+        torch.cuda.synchronize()
+        assert np.array_equal(resp.cpu().numpy().view(np.uint64), want3), f"world={world} (one call per shard)"
         for srv in servers:
             srv.close()
+    s.close()
+
+
+def test_process_is_the_staged_calls_in_one(sb, oracle):
+    """sb200_server_process (with and without stage events) leaves the response sb200_server_answer returns."""
+    import ctypes
+    import torch
+    s = ol.SpiralSession(oracle, "cfg1", 4, 2, seed=31)
+    srv = SpiralServer(sb_params(s.prm))
+    srv.load_db_items(s.pts.astype(np.uint16))
+    srv.set_public_params(s.W_left, s.W_right, s.W_conv, s.V_conv)
+    resp = torch.zeros(6 * ol.N, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for e in evs:
+            e.record()
+        marks = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
+        for use_marks in (False, True, True):
+            q = s.query(11 + int(use_marks))
+            want = srv.answer(q)
+            srv.upload_query(q, stream.cuda_stream)
+            srv.process(resp.data_ptr(), stream.cuda_stream, marks if use_marks else None)
+            stream.synchronize()
+            assert np.array_equal(resp.cpu().numpy().view(np.uint64), want)
+        assert 0 < evs[1].elapsed_time(evs[2]) < evs[0].elapsed_time(evs[3])          # scan inside the whole query
+    with pytest.raises(Exception, match="connected"):
+        shard = SpiralServer(sb_params(s.prm), rank=0, world=2)
+        shard.process(resp.data_ptr())
+    srv.close()
     s.close()
 
 
