@@ -222,6 +222,94 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
     }
 }
 
+
+// Narrow shards (16..64 database columns per z-slice: a database sharded over many GPUs, or a small second dimension).  With two
+// columns per thread a z-slice occupies only IC/2 threads, the whole grid a quarter (or less) of the full-tile scan's threads, and
+// the loads in flight no longer cover the HBM latency (4.4-4.6 TB/s).  Here the j axis of a z-slice is split over JS thread groups
+// of the same CTA (interleaved rows, so the groups together still stream consecutive 1 KiB rows), which restores 128 threads per
+// z-slice; the JS partial sums (folded below 2^61 each) meet in shared memory and group 0 reduces and stores.
+//   thread = js * (ZT*TZ) + zl * TZ + icl,  TZ = IC/2 threads per z-slice,  JS * ZT * TZ = 128
+__global__ void __launch_bounds__(128) k_scan_spiral_jsplit(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
+                                                            const uint64_t *__restrict__ db, int dim0, int IC, int ZT, int JS, int JC) {
+    pdl_prologue();
+    extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4, later reused for the reduction
+    const int tid = threadIdx.x;
+    const int TZ = IC >> 1, per = ZT * TZ;
+    const int js = tid / per, loc = tid % per, zl = loc / TZ, icl = loc % TZ;
+    const int z0 = blockIdx.x * ZT, z = z0 + zl;
+    const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+    uint64_t acc[2][3][2];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) acc[u][r][0] = acc[u][r][1] = 0;
+    const uint4 *dbz = reinterpret_cast<const uint4 *>(db) + ((size_t)z * dim0) * IC + icl;
+    const uint4 *qg = reinterpret_cast<const uint4 *>(query);
+    int it = 0;
+    for (int jc0 = 0; jc0 < dim0; jc0 += JC) {
+        __syncthreads();
+        for (int e = tid; e < ZT * JC * 4; e += 128) {
+            const int zz = e / (JC * 4), rem = e % (JC * 4);
+            qs[e] = __ldg(qg + ((size_t)(z0 + zz) * dim0 + jc0) * 4 + rem);
+        }
+        __syncthreads();
+        const uint4 *qz = qs + (size_t)zl * JC * 4;
+#pragma unroll 4
+        for (int jj = js; jj < JC; jj += JS, it++) {
+            const size_t row = (size_t)(jc0 + jj) * IC;
+            const uint4 d0 = ld_stream_u4(dbz + row), d1 = ld_stream_u4(dbz + row + TZ);
+            const uint4 q0 = qz[jj * 4 + 0], q1 = qz[jj * 4 + 1], q2 = qz[jj * 4 + 2], q3 = qz[jj * 4 + 3];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint4 d = u == 0 ? d0 : d1;
+                acc[u][0][0] += (uint64_t)q0.x * d.x;  acc[u][0][1] += (uint64_t)q0.y * d.y;
+                acc[u][1][0] += (uint64_t)q0.z * d.x;  acc[u][1][1] += (uint64_t)q0.w * d.y;
+                acc[u][2][0] += (uint64_t)q1.x * d.x;  acc[u][2][1] += (uint64_t)q1.y * d.y;
+                acc[u][0][0] += (uint64_t)q2.x * d.z;  acc[u][0][1] += (uint64_t)q2.y * d.w;
+                acc[u][1][0] += (uint64_t)q2.z * d.z;  acc[u][1][1] += (uint64_t)q2.w * d.w;
+                acc[u][2][0] += (uint64_t)q3.x * d.z;  acc[u][2][1] += (uint64_t)q3.y * d.w;
+            }
+            if ((it & (kScanFoldEvery - 1)) == kScanFoldEvery - 1) {
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        acc[u][r][0] = fold_acc(acc[u][r][0], c32p);
+                        acc[u][r][1] = fold_acc(acc[u][r][1], c32b);
+                    }
+            }
+        }
+    }
+    // partial sums of the JS groups -> shared memory (each folded below 2^61, so up to 4 of them add without overflow)
+    __syncthreads();
+    uint64_t *red = reinterpret_cast<uint64_t *>(qs);   // [js][12][per]
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            red[((size_t)js * 12 + (u * 3 + r) * 2 + 0) * per + loc] = fold_acc(acc[u][r][0], c32p);
+            red[((size_t)js * 12 + (u * 3 + r) * 2 + 1) * per + loc] = fold_acc(acc[u][r][1], c32b);
+        }
+    __syncthreads();
+    if (js == 0) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int ic = icl + u * TZ;
+            const int i = ic >> 1, c = ic & 1;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                uint64_t a0 = 0, a1 = 0;
+                for (int g = 0; g < JS; g++) {
+                    a0 += red[((size_t)g * 12 + (u * 3 + r) * 2 + 0) * per + loc];
+                    a1 += red[((size_t)g * 12 + (u * 3 + r) * 2 + 1) * per + loc];
+                }
+                uint32_t *o = out + ((((size_t)i * kN1 + r) * kN2 + c) * 2) * kN + z;
+                o[0] = reduce_u64(a0, 0);
+                o[kN] = reduce_u64(a1, 1);
+            }
+        }
+    }
+}
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
     // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
@@ -231,6 +319,19 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
     // thread - one broadcast read of the query slice per two database loads - by giving each z-slice IC/2 threads (a whole number
     // of warps) and putting 2 or 4 z-slices into the CTA; below 64 columns one column per thread remains.
     const int IC = (int)num_per * 2;
+    static const bool jsplit = [] { const char *e = getenv("SB200_SCAN_JSPLIT"); return !(e && *e == '0'); }();
+    if (jsplit && IC >= 16 && IC <= 64 && dim0 >= 4) {
+        const int TZ = IC / 2;
+        int JS = 128 / TZ, ZT = 1;
+        if (JS > 4) { ZT = JS / 4; JS = 4; }              // at most 4 partial sums per output; the rest of the CTA takes more z-slices
+        while (JS > (int)dim0) { JS >>= 1; ZT <<= 1; }
+        int JC = (int)dim0;
+        while ((size_t)ZT * JC * 64 > 16384 && JC > kScanFoldEvery) JC >>= 1;
+        const size_t smem = std::max((size_t)ZT * JC * 64, (size_t)128 * 12 * 8);
+        count_launch();
+        launch_pdl(k_scan_spiral_jsplit, dim3(kN / ZT), dim3(128), smem, s, out, query, db, (int)dim0, IC, ZT, JS, JC);
+        return;
+    }
     static const bool t64 = [] { const char *e = getenv("SB200_SCAN_T64"); return !(e && *e == '0'); }();
     const int T = (t64 && IC == 64) ? 64 : 128;        // 64-column shards: smaller CTAs spread more evenly over the 148 SMs
     const int U = IC >= 64 ? 2 : 1;
