@@ -1,5 +1,6 @@
-# short GPU check: the newest test files, then the default bench (gpurun -- bash scripts/gpu_quick_check.sh [pytest args])
+# final GPU check of a session: the whole GPU suite, smoke(), the default bench (gpurun -- bash scripts/gpu_quick_check.sh)
 set -x
 mkdir -p gpurun_out
-( time timeout 600 python -m pytest ${@:-tests/test_gpu_wire.py tests/test_gpu_client.py} -q -x ) > gpurun_out/pytest_new.log 2>&1; tail -6 gpurun_out/pytest_new.log
-timeout 600 python bench.py > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -3 gpurun_out/bench_1gpu.err; cut -c1-1800 gpurun_out/bench_1gpu.json
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -3 gpurun_out/bench_1gpu.err; cut -c1-1000 gpurun_out/bench_1gpu.json
