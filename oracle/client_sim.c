@@ -377,3 +377,155 @@ void so_client_spiral_decode(so_client *c, const uint64_t *total_resp, uint64_t 
     }
     free(Sp_q); free(s_prod);
 }
+
+/* ===========================================================================================
+ * SpiralPack / SpiralStreamPack client (testHighRate's client statements, src/testing.cpp:777-1155): keys for an
+ * out_n x out_n packed response, packing keys v_W, expansion keys + V, packed or direct-upload query, decoding.
+ * Restates: keygen(S, Sp, sr, out_n) src/client.cpp:23-47; get_fresh_public_key_raw_arb / encryptMatrixArbitrary
+ * src/testing.cpp:141-197; v_W, V and the query :905-1005; decoding :1086-1118.
+ * =========================================================================================== */
+so_client *so_pack_client_new(const so_params *prm, uint64_t seed) {
+    so_client *c = (so_client *)calloc(1, sizeof(so_client));
+    c->prm = *prm; c->rng.s = seed;
+    build_cdf(c);
+    size_t n = prm->out_n;
+    c->Sp = xalloc(n * N); c->sr = xalloc(N);
+    for (size_t m = 0; m < N; m++) c->sr[m] = sample_u64(c) % SO_Q;
+    for (size_t r = 0; r < n; r++) for (size_t m = 0; m < N; m++) c->Sp[r * N + m] = sample_u64(c) % SO_Q;
+    return c;
+}
+/* P = [-A ; Sp*A + E], (out_n+1) x m, NTT form   (get_fresh_public_key_raw_arb + to_ntt) */
+static void fresh_public_key_arb_ntt(so_client *c, uint64_t *P_ntt, size_t m) {
+    size_t n = c->prm.out_n;
+    uint64_t *A = xalloc(m * N), *A_inv = xalloc(m * N), *E = xalloc(n * m * N), *A_ntt = xalloc(m * PL), *E_ntt = xalloc(n * m * PL);
+    uint64_t *Sp_ntt = xalloc(n * PL), *Bp = xalloc(n * m * PL);
+    so_fill_uniform_raw(A, m * N, &c->rng);
+    noise(c, E, n * m);
+    so_to_ntt(A_ntt, A, m); so_to_ntt(E_ntt, E, n * m); so_to_ntt(Sp_ntt, c->Sp, n);
+    so_multiply(Bp, Sp_ntt, A_ntt, n, 1, m);
+    so_add(Bp, E_ntt, Bp, n * m);
+    so_invert(A_inv, A, m);
+    so_to_ntt(P_ntt, A_inv, m);
+    memcpy(P_ntt + m * PL, Bp, n * m * PL * sizeof(uint64_t));
+    free(A); free(A_inv); free(E); free(A_ntt); free(E_ntt); free(Sp_ntt); free(Bp);
+}
+/* W_exp_left: g x (2 x t_exp); W_exp_right: (stopround+1) x (2 x t_exp_right); V: 2 x 2*t_conv; v_W: out_n x ((out_n+1) x t_conv).
+ * The first three may be NULL for a direct-upload client. */
+void so_pack_client_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *V, uint64_t *v_W) {
+    const so_params *p = &c->prm;
+    size_t n = p->out_n, mc = p->t_conv, g, stop;
+    so_pack_expansion_shape(p, &g, &stop);
+    uint64_t *s0_ntt = xalloc(PL), *gv = xalloc(mc * N), *gv_ntt = xalloc(mc * PL), *prod = xalloc(mc * PL);
+    so_to_ntt(s0_ntt, c->sr, 1);
+    so_build_gadget(gv, 1, mc);
+    so_to_ntt(gv_ntt, gv, mc);
+    so_mul_by_const(prod, s0_ntt, gv_ntt, mc);                          /* s0 * g_vec */
+    for (size_t i = 0; i < n; i++) {                                       /* v_W[i] = P + [0 ; AG], AG row i = s0 * g_vec  (:905-912) */
+        uint64_t *W = &v_W[i * (n + 1) * mc * PL];
+        fresh_public_key_arb_ntt(c, W, mc);
+        so_add(&W[(1 + i) * mc * PL], &W[(1 + i) * mc * PL], prod, mc);
+    }
+    if (W_exp_left && W_exp_right && V) {
+        expansion_keys(c, W_exp_left, g, p->t_exp, CC_W_LEFT);
+        expansion_keys(c, W_exp_right, stop + 1, p->t_exp_right, CC_W_RIGHT);
+        /* V (:918-931): column i encrypts s0^2 * G[0][i] (i even) or s0 * G[1][i] (i odd), G = gadget(2, 2*t_conv) */
+        size_t m = 2 * mc;
+        uint64_t *G = xalloc(2 * m * N), *s0sq = xalloc(PL), *cst = xalloc(N), *cst_ntt = xalloc(PL), *sig_ntt = xalloc(PL), *sigma = xalloc(N);
+        uint64_t ct[2 * 2 * SO_N];
+        so_build_gadget(G, 2, m);
+        so_multiply(s0sq, s0_ntt, s0_ntt, 1, 1, 1);
+        for (size_t i = 0; i < m; i++) {
+            memset(cst, 0, N * sizeof(uint64_t));
+            cst[0] = (i % 2 == 0) ? G[i * N] : G[(m + i) * N];
+            so_to_ntt(cst_ntt, cst, 1);
+            so_multiply(sig_ntt, (i % 2 == 0) ? s0sq : s0_ntt, cst_ntt, 1, 1, 1);
+            so_from_ntt(sigma, sig_ntt, 1);
+            encrypt_simple_regev(c, ct, sigma, CC_OBJ(CC_V_CONV, i));
+            memcpy(&V[(0 * m + i) * PL], ct, PL * sizeof(uint64_t));
+            memcpy(&V[(1 * m + i) * PL], ct + PL, PL * sizeof(uint64_t));
+        }
+        free(G); free(s0sq); free(cst); free(cst_ntt); free(sig_ntt); free(sigma);
+    }
+    free(s0_ntt); free(gv); free(gv_ntt); free(prod);
+}
+/* packed single-ciphertext query (:987-1005) */
+void so_pack_client_query(so_client *c, size_t idx_target, uint64_t *query_cv) {
+    const so_params *p = &c->prm;
+    size_t g, stop; so_pack_expansion_shape(p, &g, &stop);
+    size_t fd = p->nu2, ell = p->t_gsw;
+    size_t idx_dim0 = idx_target >> fd, idx_further = idx_target & (((size_t)1 << fd) - 1);
+    uint32_t bits_per = so_get_bits_per((uint32_t)ell);
+    uint64_t *sigma = xalloc(N);
+    sigma[2 * idx_dim0] = (SO_Q / p->p_db) % SO_Q;
+    for (size_t i = 0; i < fd; i++) {
+        uint64_t bit = (idx_further >> i) & 1;
+        for (size_t j = 0; j < ell; j++) sigma[2 * (i * ell + j) + 1] = ((uint64_t)1 << (bits_per * j)) * bit;
+    }
+    uint64_t inv_first = (uint64_t)inv_mod((int64_t)1 << g, (int64_t)SO_Q), inv_rest = (uint64_t)inv_mod((int64_t)1 << (stop + 1), (int64_t)SO_Q);
+    for (size_t i = 0; i < N / 2; i++) {
+        sigma[2 * i] = (uint64_t)((u128)sigma[2 * i] * inv_first % SO_Q);
+        sigma[2 * i + 1] = (uint64_t)((u128)sigma[2 * i + 1] * inv_rest % SO_Q);
+    }
+    encrypt_simple_regev(c, query_cv, sigma, CC_OBJ(CC_QUERY, 0));
+    free(sigma);
+}
+/* direct upload (:962-985): v_firstdim = 2^nu1 cts (2x1 NTT); v_folding = nu2 x (2 x 2*ell) NTT */
+void so_pack_client_query_direct(so_client *c, size_t idx_target, uint64_t *v_firstdim, uint64_t *v_folding) {
+    const so_params *p = &c->prm;
+    size_t fd = p->nu2, ell = p->t_gsw, dim0 = (size_t)1 << p->nu1;
+    size_t idx_dim0 = idx_target >> fd, idx_further = idx_target & (((size_t)1 << fd) - 1);
+    uint32_t bits_per = so_get_bits_per((uint32_t)ell);
+    uint64_t *sigma = xalloc(N), *cst_ntt = xalloc(PL), *s0_ntt = xalloc(PL), *prod = xalloc(PL);
+    uint64_t ct[2 * 2 * SO_N];
+    so_to_ntt(s0_ntt, c->sr, 1);
+    for (size_t i = 0; i < dim0; i++) {
+        memset(sigma, 0, N * sizeof(uint64_t));
+        sigma[0] = i == idx_dim0 ? SO_Q / p->p_db : 0;
+        encrypt_simple_regev(c, &v_firstdim[i * 2 * PL], sigma, CC_OBJ(CC_QUERY, 0));
+    }
+    for (size_t i = 0; i < fd; i++) {
+        uint64_t bit = (idx_further >> i) & 1;
+        uint64_t *gsw = &v_folding[i * 2 * 2 * ell * PL];
+        for (size_t j = 0; j < ell; j++) {
+            uint64_t val = ((uint64_t)1 << (bits_per * j)) * bit;
+            memset(sigma, 0, N * sizeof(uint64_t)); sigma[0] = val;
+            encrypt_simple_regev(c, ct, sigma, CC_OBJ(CC_QUERY, 0));                 /* column 2j+1: val */
+            memcpy(&gsw[(0 * 2 * ell + 2 * j + 1) * PL], ct, PL * sizeof(uint64_t));
+            memcpy(&gsw[(1 * 2 * ell + 2 * j + 1) * PL], ct + PL, PL * sizeof(uint64_t));
+            so_to_ntt(cst_ntt, sigma, 1);
+            so_multiply(prod, s0_ntt, cst_ntt, 1, 1, 1);
+            so_from_ntt(sigma, prod, 1);
+            encrypt_simple_regev(c, ct, sigma, CC_OBJ(CC_QUERY, 0));                 /* column 2j: s0 * val */
+            memcpy(&gsw[(0 * 2 * ell + 2 * j) * PL], ct, PL * sizeof(uint64_t));
+            memcpy(&gsw[(1 * 2 * ell + 2 * j) * PL], ct + PL, PL * sizeof(uint64_t));
+        }
+    }
+    free(sigma); free(cst_ntt); free(s0_ntt); free(prod);
+}
+/* total_resp: (out_n+1) x out_n raw -> out_pt: out_n x out_n polynomials (item (i,j) = plane i*out_n + j)  (:1086-1118) */
+void so_pack_client_decode(so_client *c, const uint64_t *total_resp, uint64_t *out_pt) {
+    const so_params *p = &c->prm;
+    size_t n = p->out_n;
+    uint64_t qp = so_arb_qprime(p->qp_bits), q_1 = 4 * p->p_db;
+    uint64_t *Sp_q = xalloc(n * N), *s_prod = xalloc(n * n * N);
+    for (size_t i = 0; i < n * N; i++) {
+        int64_t a = (int64_t)c->Sp[i];
+        if (a >= (int64_t)(SO_Q / 2)) a -= (int64_t)SO_Q;
+        Sp_q[i] = (uint64_t)((a + (int64_t)((SO_Q / qp) * qp) + 2 * (int64_t)qp) % (int64_t)qp);
+    }
+    for (size_t r = 0; r < n; r++)
+        for (size_t cc = 0; cc < n; cc++)
+            negacyclic_mul_acc(&s_prod[(r * n + cc) * N], &Sp_q[r * N], &total_resp[cc * N], qp);
+    const uint64_t *rest = total_resp + n * N;
+    for (size_t i = 0; i < n * n * N; i++) {
+        int64_t vf = (int64_t)s_prod[i]; if (vf >= (int64_t)(qp / 2)) vf -= (int64_t)qp;
+        int64_t vr = (int64_t)rest[i];   if (vr >= (int64_t)(q_1 / 2)) vr -= (int64_t)q_1;
+        uint64_t denom = qp * (q_1 / p->p_db);
+        int64_t r = vf * (int64_t)q_1 + vr * (int64_t)qp;
+        int64_t sign = r >= 0 ? 1 : -1;
+        __int128 res = ((__int128)r + sign * ((int64_t)denom / 2)) / (__int128)denom;
+        res = (res + (denom / p->p_db) * p->p_db + 2 * p->p_db) % p->p_db;
+        out_pt[i] = (uint64_t)res;
+    }
+    free(Sp_q); free(s_prod);
+}

@@ -20,6 +20,14 @@ void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv)
 /* kind: SO_WIRE_QUERY_SEEDED / SO_WIRE_QUERY_FULL (wire_format.h); wire: so_wire_query_bytes(kind) bytes */
 void so_client_spiral_query_wire(so_client *c, size_t idx_target, uint32_t kind, uint8_t *wire);
 void so_client_spiral_decode(so_client *c, const uint64_t *total_resp, uint64_t *out_pt);
+/* ---- SpiralPack / SpiralStreamPack client (testHighRate's client statements, src/testing.cpp:777-1155) ---- */
+so_client *so_pack_client_new(const so_params *prm, uint64_t seed);
+/* W_exp_left: g x (2 x t_exp), W_exp_right: (stopround+1) x (2 x t_exp_right), V: 2 x 2*t_conv (all three NULL for a direct-upload
+ * client); v_W: out_n x ((out_n+1) x t_conv); all ref-NTT */
+void so_pack_client_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *V, uint64_t *v_W);
+void so_pack_client_query(so_client *c, size_t idx_target, uint64_t *query_cv);
+void so_pack_client_query_direct(so_client *c, size_t idx_target, uint64_t *v_firstdim, uint64_t *v_folding);
+void so_pack_client_decode(so_client *c, const uint64_t *total_resp, uint64_t *out_pt);
 #ifdef __cplusplus
 }
 #endif

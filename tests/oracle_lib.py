@@ -124,6 +124,12 @@ def load():
     lib.so_wire_query_pack_full.argtypes = [u64p, u8p]
     lib.so_client_spiral_query_wire.argtypes = [C.c_void_p, sz, C.c_uint32, u8p]
     lib.so_records_to_plaintexts.argtypes = [u64p, u8p, sz, C.c_uint64]
+    lib.so_pack_client_new.restype = C.c_void_p
+    lib.so_pack_client_new.argtypes = [C.POINTER(SoParams), C.c_uint64]
+    lib.so_pack_client_pub_params.argtypes = [C.c_void_p, u64p, u64p, u64p, u64p]
+    lib.so_pack_client_query.argtypes = [C.c_void_p, sz, u64p]
+    lib.so_pack_client_query_direct.argtypes = [C.c_void_p, sz, u64p, u64p]
+    lib.so_pack_client_decode.argtypes = [C.c_void_p, u64p, u64p]
     lib.so_client_new_chacha.restype = C.c_void_p
     lib.so_client_new_chacha.argtypes = [C.POINTER(SoParams), u8p]
     lib.so_client_gaussian_thresholds.argtypes = [C.c_void_p, u64p]
@@ -262,6 +268,80 @@ class SpiralSession:
         out = np.zeros(4 * N, dtype=np.uint64)
         self.lib.so_client_spiral_decode(self.client, ptr(np.ascontiguousarray(resp)), ptr(out))
         return out.reshape(4, N)
+
+    def close(self):
+        self.lib.so_client_free(self.client)
+
+
+class PackSession:
+    """Test-side SpiralPack / SpiralStreamPack client + CPU reference pipeline (small sizes only): real keys, packing keys,
+    queries and decoding, so the Pack servers are checked on real encryptions and on "decoded == planted"."""
+
+    def __init__(self, lib, cfg, nu1, nu2, direct, seed=1):
+        self.lib, self.prm, self.direct = lib, make_params(cfg, nu1, nu2), direct
+        p = self.prm
+        g, stop = C.c_size_t(), C.c_size_t()
+        lib.so_pack_expansion_shape(C.byref(p), C.byref(g), C.byref(stop))
+        self.g, self.stopround = g.value, stop.value
+        self.dim0, self.num_per, self.n = 1 << nu1, 1 << nu2, p.out_n
+        self.total_n, self.planes = self.dim0 * self.num_per, p.out_n * p.out_n
+        self.client = lib.so_pack_client_new(C.byref(p), seed)
+        PL = 2 * N
+        self.v_W = np.zeros(self.n * (self.n + 1) * p.t_conv * PL, dtype=np.uint64)
+        if direct:
+            self.W_left = self.W_right = self.V = None
+            lib.so_pack_client_pub_params(self.client, None, None, None, ptr(self.v_W))
+        else:
+            self.W_left = np.zeros(self.g * 2 * p.t_exp * PL, dtype=np.uint64)
+            self.W_right = np.zeros((self.stopround + 1) * 2 * p.t_exp_right * PL, dtype=np.uint64)
+            self.V = np.zeros(2 * 2 * p.t_conv * PL, dtype=np.uint64)
+            lib.so_pack_client_pub_params(self.client, ptr(self.W_left), ptr(self.W_right), ptr(self.V), ptr(self.v_W))
+        rng = np.random.default_rng(seed + 2000)
+        self.pts = rng.integers(0, p.p_db, size=(self.planes, self.total_n, N), dtype=np.uint64)      # [plane][item][z]
+
+    def reference_planes(self):
+        """The out_n^2 planes in the reference's convertDb layout, concatenated (what so_pack_answer scans)."""
+        items, PL = self.total_n, 2 * N
+        db = np.zeros(self.planes * items * N, dtype=np.uint64)
+        for pl in range(self.planes):
+            enc = np.zeros(items * N, dtype=np.uint64)
+            self.lib.so_encode_plaintext(ptr(enc), ptr(np.ascontiguousarray(self.pts[pl].reshape(-1))), items * N, self.prm.p_db)
+            ntt = np.zeros(items * PL, dtype=np.uint64)
+            self.lib.so_to_ntt(ptr(ntt), ptr(enc), items)
+            self.lib.so_convert_db(ptr(db[pl * items * N:(pl + 1) * items * N]), ptr(ntt), items, self.dim0, self.num_per)
+        return db
+
+    def query(self, idx):
+        """(query_cv, v_firstdim, v_folding): the packed ciphertext, or the direct-upload ciphertexts."""
+        PL, ell = 2 * N, self.prm.t_gsw
+        if self.direct:
+            v_first = np.zeros(self.dim0 * 2 * PL, dtype=np.uint64)
+            v_fold = np.zeros(max(self.prm.nu2, 1) * 2 * 2 * ell * PL, dtype=np.uint64)
+            self.lib.so_pack_client_query_direct(self.client, idx, ptr(v_first), ptr(v_fold))
+            return None, v_first, v_fold
+        q = np.zeros(2 * PL, dtype=np.uint64)
+        self.lib.so_pack_client_query(self.client, idx, ptr(q))
+        return q, None, None
+
+    def oracle_answer(self, query, db):
+        q, v_first, v_fold = query
+        dummy = np.zeros(2 * 2 * N, dtype=np.uint64)
+        n = self.n
+        resp = np.zeros((n + 1) * n * N, dtype=np.uint64)
+        cts = np.zeros(self.planes * 2 * N, dtype=np.uint64)
+        opt = lambda a: ptr(a if a is not None else dummy)  # noqa: E731
+        rc = self.lib.so_pack_answer(C.byref(self.prm), int(not self.direct), opt(q), opt(self.W_left), opt(self.W_right), opt(self.V),
+                                     opt(v_first), opt(v_fold), ptr(self.v_W), ptr(db), ptr(resp), ptr(cts))
+        assert rc == 0
+        return resp, cts
+
+    def decode(self, resp):
+        out = np.zeros(self.planes * N, dtype=np.uint64)
+        self.lib.so_pack_client_decode(self.client, ptr(np.ascontiguousarray(resp)), ptr(out))
+        return out.reshape(self.planes, N)
+
+    def planted(self, idx):
+        return self.pts[:, idx, :]
 
     def close(self):
         self.lib.so_client_free(self.client)
