@@ -123,3 +123,17 @@ def test_counter_based_client_end_to_end(lib):
     t = ol.SpiralSession(lib, "cfg1", 3, 2, seed=5, chacha_seed=bytes(range(1, 33)))
     assert not np.array_equal(t.secret()[0], sr)
     s.close(); t.close()
+
+
+def test_known_answers_of_the_formats(lib):
+    """tests/golden/wire_kat.json (scripts/make_wire_golden.py): the byte-level behaviour of the wire query, the seed expansion,
+    the counter-based client and the record unpacking is frozen - a format is a contract between machines."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(ol.ROOT, "scripts"))
+    import make_wire_golden
+    with open(os.path.join(ol.GOLDEN_DIR, "wire_kat.json")) as f:
+        want = json.load(f)
+    got = json.loads(json.dumps(make_wire_golden.vectors(lib)))
+    assert got == want
