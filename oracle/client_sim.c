@@ -37,7 +37,7 @@ struct so_client {
 };
 #define CC_MAGIC 0x43324253u            /* "SB2C" */
 #define CC_OBJ(cls, idx) (((uint32_t)(cls) << 24) | (uint32_t)(idx))
-enum { CC_KEYS = 1, CC_W_RIGHT = 2, CC_W_LEFT = 3, CC_W_CONV = 4, CC_V_CONV = 5, CC_QUERY = 6 };
+enum { CC_KEYS = 1, CC_W_RIGHT = 2, CC_W_LEFT = 3, CC_W_CONV = 4, CC_V_CONV = 5, CC_QUERY = 6, CC_PACK_W = 7, CC_QUERY_DIRECT = 8 };
 
 static uint64_t *xalloc(size_t words) {
     uint64_t *p = (uint64_t *)calloc(words ? words : 1, sizeof(uint64_t));
@@ -299,8 +299,12 @@ void so_client_spiral_query(so_client *c, size_t idx_target, uint64_t *query_cv)
 }
 /* counter-based client: seeded wire query with the wire seed and the query number chosen by the caller
  * (row 0 from the wire seed as so_wire_seeded_row0, noise = Gaussian object (CC_QUERY, query_id), stream 1) */
+static void chacha_wire_from_sigma(so_client *c, uint64_t *sigma, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire);
 void so_client_chacha_query_wire(so_client *c, size_t idx_target, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire) {
-    uint64_t *sigma = query_sigma(c, idx_target), *P = xalloc(2 * PL), *e = xalloc(N), *sig_ntt = xalloc(PL);
+    chacha_wire_from_sigma(c, query_sigma(c, idx_target), query_id, wire_seed, wire);
+}
+static void chacha_wire_from_sigma(so_client *c, uint64_t *sigma, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire) {
+    uint64_t *P = xalloc(2 * PL), *e = xalloc(N), *sig_ntt = xalloc(PL);
     so_wire_seeded_row0(wire_seed, P);
     cc_gauss_raw(c, CC_OBJ(CC_QUERY, query_id), 1, e);
     regev_row1_from_row0(c, P, e);
@@ -394,9 +398,41 @@ so_client *so_pack_client_new(const so_params *prm, uint64_t seed) {
     for (size_t r = 0; r < n; r++) for (size_t m = 0; m < N; m++) c->Sp[r * N + m] = sample_u64(c) % SO_Q;
     return c;
 }
-/* P = [-A ; Sp*A + E], (out_n+1) x m, NTT form   (get_fresh_public_key_raw_arb + to_ntt) */
-static void fresh_public_key_arb_ntt(so_client *c, uint64_t *P_ntt, size_t m) {
+/* the Pack client with counter-based randomness (the statement a CUDA Pack client is to be compared with): keys as
+ * so_client_new_chacha (S' has out_n rows), packing keys from objects (CC_PACK_W, i*t_conv + k), direct-upload ciphertexts from
+ * (CC_QUERY_DIRECT, ciphertext number) */
+so_client *so_pack_client_new_chacha(const so_params *prm, const uint8_t seed[32]) {
+    so_client *c = (so_client *)calloc(1, sizeof(so_client));
+    c->prm = *prm; c->chacha = 1;
+    for (int i = 0; i < 8; i++) c->key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+    build_cdf(c);
+    for (int k = 0; k < 128; k++) c->thr[k] = (uint64_t)floor(c->cdf[k] * 9007199254740992.0) + 1;
+    size_t n = prm->out_n;
+    c->Sp = xalloc(n * N); c->sr = xalloc(N);
+    cc_gauss_raw(c, CC_OBJ(CC_KEYS, 0), 0, c->sr);
+    for (size_t r = 0; r < n; r++) cc_gauss_raw(c, CC_OBJ(CC_KEYS, 1 + r), 0, &c->Sp[r * N]);
+    return c;
+}
+/* P = [-A ; Sp*A + E], (out_n+1) x m, NTT form   (get_fresh_public_key_raw_arb + to_ntt); obj_base: object of column 0 */
+static void fresh_public_key_arb_ntt(so_client *c, uint64_t *P_ntt, size_t m, uint32_t obj_base) {
     size_t n = c->prm.out_n;
+    if (c->chacha) {
+        uint64_t *a_ntt = xalloc(PL), *e = xalloc(N), *e_ntt = xalloc(PL), *Sp_ntt = xalloc(n * PL), *prod = xalloc(PL);
+        so_to_ntt(Sp_ntt, c->Sp, n);
+        for (size_t k = 0; k < m; k++) {
+            uint64_t *row0 = &P_ntt[k * PL];
+            cc_uniform_ntt(c, obj_base + (uint32_t)k, 0, row0);
+            for (size_t z = 0; z < N; z++) { a_ntt[z] = (SO_P - row0[z]) % SO_P; a_ntt[N + z] = (SO_B - row0[N + z]) % SO_B; }
+            for (size_t r = 0; r < n; r++) {
+                cc_gauss_raw(c, obj_base + (uint32_t)k, 1 + (uint32_t)r, e);
+                so_to_ntt(e_ntt, e, 1);
+                so_multiply(prod, &Sp_ntt[r * PL], a_ntt, 1, 1, 1);
+                so_add(&P_ntt[((1 + r) * m + k) * PL], prod, e_ntt, 1);
+            }
+        }
+        free(a_ntt); free(e); free(e_ntt); free(Sp_ntt); free(prod);
+        return;
+    }
     uint64_t *A = xalloc(m * N), *A_inv = xalloc(m * N), *E = xalloc(n * m * N), *A_ntt = xalloc(m * PL), *E_ntt = xalloc(n * m * PL);
     uint64_t *Sp_ntt = xalloc(n * PL), *Bp = xalloc(n * m * PL);
     so_fill_uniform_raw(A, m * N, &c->rng);
@@ -422,7 +458,7 @@ void so_pack_client_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_e
     so_mul_by_const(prod, s0_ntt, gv_ntt, mc);                          /* s0 * g_vec */
     for (size_t i = 0; i < n; i++) {                                       /* v_W[i] = P + [0 ; AG], AG row i = s0 * g_vec  (:905-912) */
         uint64_t *W = &v_W[i * (n + 1) * mc * PL];
-        fresh_public_key_arb_ntt(c, W, mc);
+        fresh_public_key_arb_ntt(c, W, mc, CC_OBJ(CC_PACK_W, i * mc));
         so_add(&W[(1 + i) * mc * PL], &W[(1 + i) * mc * PL], prod, mc);
     }
     if (W_exp_left && W_exp_right && V) {
@@ -449,7 +485,7 @@ void so_pack_client_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_e
     free(s0_ntt); free(gv); free(gv_ntt); free(prod);
 }
 /* packed single-ciphertext query (:987-1005) */
-void so_pack_client_query(so_client *c, size_t idx_target, uint64_t *query_cv) {
+static uint64_t *pack_query_sigma(so_client *c, size_t idx_target) {
     const so_params *p = &c->prm;
     size_t g, stop; so_pack_expansion_shape(p, &g, &stop);
     size_t fd = p->nu2, ell = p->t_gsw;
@@ -466,8 +502,16 @@ void so_pack_client_query(so_client *c, size_t idx_target, uint64_t *query_cv) {
         sigma[2 * i] = (uint64_t)((u128)sigma[2 * i] * inv_first % SO_Q);
         sigma[2 * i + 1] = (uint64_t)((u128)sigma[2 * i + 1] * inv_rest % SO_Q);
     }
+    return sigma;
+}
+void so_pack_client_query(so_client *c, size_t idx_target, uint64_t *query_cv) {
+    uint64_t *sigma = pack_query_sigma(c, idx_target);
     encrypt_simple_regev(c, query_cv, sigma, CC_OBJ(CC_QUERY, 0));
     free(sigma);
+}
+/* counter-based client: the packed query in SEEDED wire form (as so_client_chacha_query_wire) */
+void so_pack_client_chacha_query_wire(so_client *c, size_t idx_target, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire) {
+    chacha_wire_from_sigma(c, pack_query_sigma(c, idx_target), query_id, wire_seed, wire);
 }
 /* direct upload (:962-985): v_firstdim = 2^nu1 cts (2x1 NTT); v_folding = nu2 x (2 x 2*ell) NTT */
 void so_pack_client_query_direct(so_client *c, size_t idx_target, uint64_t *v_firstdim, uint64_t *v_folding) {
@@ -481,7 +525,7 @@ void so_pack_client_query_direct(so_client *c, size_t idx_target, uint64_t *v_fi
     for (size_t i = 0; i < dim0; i++) {
         memset(sigma, 0, N * sizeof(uint64_t));
         sigma[0] = i == idx_dim0 ? SO_Q / p->p_db : 0;
-        encrypt_simple_regev(c, &v_firstdim[i * 2 * PL], sigma, CC_OBJ(CC_QUERY, 0));
+        encrypt_simple_regev(c, &v_firstdim[i * 2 * PL], sigma, CC_OBJ(CC_QUERY_DIRECT, i));
     }
     for (size_t i = 0; i < fd; i++) {
         uint64_t bit = (idx_further >> i) & 1;
@@ -489,13 +533,13 @@ void so_pack_client_query_direct(so_client *c, size_t idx_target, uint64_t *v_fi
         for (size_t j = 0; j < ell; j++) {
             uint64_t val = ((uint64_t)1 << (bits_per * j)) * bit;
             memset(sigma, 0, N * sizeof(uint64_t)); sigma[0] = val;
-            encrypt_simple_regev(c, ct, sigma, CC_OBJ(CC_QUERY, 0));                 /* column 2j+1: val */
+            encrypt_simple_regev(c, ct, sigma, CC_OBJ(CC_QUERY_DIRECT, dim0 + (i * ell + j) * 2 + 1));   /* column 2j+1: val */
             memcpy(&gsw[(0 * 2 * ell + 2 * j + 1) * PL], ct, PL * sizeof(uint64_t));
             memcpy(&gsw[(1 * 2 * ell + 2 * j + 1) * PL], ct + PL, PL * sizeof(uint64_t));
             so_to_ntt(cst_ntt, sigma, 1);
             so_multiply(prod, s0_ntt, cst_ntt, 1, 1, 1);
             so_from_ntt(sigma, prod, 1);
-            encrypt_simple_regev(c, ct, sigma, CC_OBJ(CC_QUERY, 0));                 /* column 2j: s0 * val */
+            encrypt_simple_regev(c, ct, sigma, CC_OBJ(CC_QUERY_DIRECT, dim0 + (i * ell + j) * 2));       /* column 2j: s0 * val */
             memcpy(&gsw[(0 * 2 * ell + 2 * j) * PL], ct, PL * sizeof(uint64_t));
             memcpy(&gsw[(1 * 2 * ell + 2 * j) * PL], ct + PL, PL * sizeof(uint64_t));
         }

@@ -22,6 +22,8 @@ void so_client_spiral_query_wire(so_client *c, size_t idx_target, uint32_t kind,
 void so_client_spiral_decode(so_client *c, const uint64_t *total_resp, uint64_t *out_pt);
 /* ---- SpiralPack / SpiralStreamPack client (testHighRate's client statements, src/testing.cpp:777-1155) ---- */
 so_client *so_pack_client_new(const so_params *prm, uint64_t seed);
+so_client *so_pack_client_new_chacha(const so_params *prm, const uint8_t seed[32]);     /* counter-based randomness (see so_client_new_chacha) */
+void so_pack_client_chacha_query_wire(so_client *c, size_t idx_target, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire);
 /* W_exp_left: g x (2 x t_exp), W_exp_right: (stopround+1) x (2 x t_exp_right), V: 2 x 2*t_conv (all three NULL for a direct-upload
  * client); v_W: out_n x ((out_n+1) x t_conv); all ref-NTT */
 void so_pack_client_pub_params(so_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *V, uint64_t *v_W);

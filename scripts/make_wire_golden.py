@@ -51,6 +51,12 @@ def vectors(lib):
     lib.so_records_to_plaintexts(ol.ptr(pts), ol.ptr8(rec), 32, 65536)
     out["records_to_plaintexts(bytes 0..63, p=65536)"] = [int(x) for x in pts[:4]]
     s.close()
+    ps = ol.PackSession(lib, "cfg3", 4, 2, False, seed=1, chacha_seed=seed)
+    out["chacha_pack_client(cfg3,4,2,seed=00..1f)"] = {
+        "v_W": digest(lib, ol.canon(ps.v_W, ol.KIND_NTT)), "V": digest(lib, ol.canon(ps.V, ol.KIND_NTT)),
+        "W_exp_left": digest(lib, ol.canon(ps.W_left, ol.KIND_NTT)), "W_exp_right": digest(lib, ol.canon(ps.W_right, ol.KIND_NTT)),
+        "query_wire(idx=5,query_id=1,wire_seed=07..07)": digest(lib, ps.chacha_query_wire(5, 1, bytes([7] * 32)))}
+    ps.close()
     return out
 
 

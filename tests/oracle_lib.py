@@ -126,6 +126,9 @@ def load():
     lib.so_records_to_plaintexts.argtypes = [u64p, u8p, sz, C.c_uint64]
     lib.so_pack_client_new.restype = C.c_void_p
     lib.so_pack_client_new.argtypes = [C.POINTER(SoParams), C.c_uint64]
+    lib.so_pack_client_new_chacha.restype = C.c_void_p
+    lib.so_pack_client_new_chacha.argtypes = [C.POINTER(SoParams), u8p]
+    lib.so_pack_client_chacha_query_wire.argtypes = [C.c_void_p, sz, C.c_uint32, u8p, u8p]
     lib.so_pack_client_pub_params.argtypes = [C.c_void_p, u64p, u64p, u64p, u64p]
     lib.so_pack_client_query.argtypes = [C.c_void_p, sz, u64p]
     lib.so_pack_client_query_direct.argtypes = [C.c_void_p, sz, u64p, u64p]
@@ -277,7 +280,8 @@ class PackSession:
     """Test-side SpiralPack / SpiralStreamPack client + CPU reference pipeline (small sizes only): real keys, packing keys,
     queries and decoding, so the Pack servers are checked on real encryptions and on "decoded == planted"."""
 
-    def __init__(self, lib, cfg, nu1, nu2, direct, seed=1):
+    def __init__(self, lib, cfg, nu1, nu2, direct, seed=1, chacha_seed=None):
+        """chacha_seed (32 bytes): counter-based randomness (so_pack_client_new_chacha), the statement for a CUDA Pack client."""
         self.lib, self.prm, self.direct = lib, make_params(cfg, nu1, nu2), direct
         p = self.prm
         g, stop = C.c_size_t(), C.c_size_t()
@@ -285,7 +289,10 @@ class PackSession:
         self.g, self.stopround = g.value, stop.value
         self.dim0, self.num_per, self.n = 1 << nu1, 1 << nu2, p.out_n
         self.total_n, self.planes = self.dim0 * self.num_per, p.out_n * p.out_n
-        self.client = lib.so_pack_client_new(C.byref(p), seed)
+        if chacha_seed is None:
+            self.client = lib.so_pack_client_new(C.byref(p), seed)
+        else:
+            self.client = lib.so_pack_client_new_chacha(C.byref(p), ptr8(np.frombuffer(bytes(chacha_seed), dtype=np.uint8).copy()))
         PL = 2 * N
         self.v_W = np.zeros(self.n * (self.n + 1) * p.t_conv * PL, dtype=np.uint64)
         if direct:
@@ -322,6 +329,11 @@ class PackSession:
         q = np.zeros(2 * PL, dtype=np.uint64)
         self.lib.so_pack_client_query(self.client, idx, ptr(q))
         return q, None, None
+
+    def chacha_query_wire(self, idx, query_id, wire_seed):
+        wire = np.zeros(self.lib.so_wire_query_bytes(WIRE_SEEDED), dtype=np.uint8)
+        self.lib.so_pack_client_chacha_query_wire(self.client, idx, query_id, ptr8(np.frombuffer(bytes(wire_seed), dtype=np.uint8).copy()), ptr8(wire))
+        return wire
 
     def oracle_answer(self, query, db):
         q, v_first, v_fold = query

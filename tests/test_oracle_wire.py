@@ -125,6 +125,24 @@ def test_counter_based_client_end_to_end(lib):
     s.close(); t.close()
 
 
+@pytest.mark.parametrize("cfg,nu1,nu2,direct", [("cfg3", 4, 2, False), ("cfg4", 3, 2, True)])
+def test_counter_based_pack_client_end_to_end(lib, cfg, nu1, nu2, direct):
+    """The ChaCha-stream SpiralPack / SpiralStreamPack client: packing keys, expansion keys + V, a seeded wire query (or the
+    direct-upload ciphertexts) drive the oracle's Pack server to a response that decodes to the planted item of every plane."""
+    s = ol.PackSession(lib, cfg, nu1, nu2, direct, seed=8, chacha_seed=bytes(range(32)))
+    db = s.reference_planes()
+    for qid, idx in enumerate((0, s.total_n - 1, 9)):
+        if direct:
+            query = s.query(idx)
+        else:
+            wire = s.chacha_query_wire(idx, qid, bytes([qid + 3] * 32))
+            assert wire.size == 8 + 32 + 14336
+            query = (ol.wire_expand(lib, wire), None, None)
+        resp, _ = s.oracle_answer(query, db)
+        assert np.array_equal(s.decode(resp), s.planted(idx)), f"idx {idx}"
+    s.close()
+
+
 def test_known_answers_of_the_formats(lib):
     """tests/golden/wire_kat.json (scripts/make_wire_golden.py): the byte-level behaviour of the wire query, the seed expansion,
     the counter-based client and the record unpacking is frozen - a format is a contract between machines."""
