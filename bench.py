@@ -35,7 +35,7 @@ WORKLOADS = {
                  macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256"),
     "cfg5": dict(kind="spiral", nu1=9, nu2=8, scaling="strong", flags=[],
                  prm=dict(t_gsw=9, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=21, out_n=2, p_db=256),
-                 macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=9 QPBITS=21 PVALUE=256"),
+                 macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=9 QPBITS=21 PVALUE=256", sample=(9, 5)),
     "cfg3": dict(kind="pack", nu1=10, nu2=8, scaling="strong", direct=False, flags=["--high-rate"],
                  prm=dict(t_gsw=8, t_conv=4, t_exp=16, t_exp_right=56, qp_bits=20, out_n=4, p_db=256),
                  macros="TEXP=16 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256 OUTN=4", sample=(8, 5)),
@@ -206,6 +206,47 @@ def pack_sample_scaled(cfg, nu1, nu2):
     return scaled, info, text
 
 
+def spiral_sample_scaled(cfg, nu1, nu2):
+    """Spiral workloads beyond the headline (cfg5: 8 GiB, ~1 min of host-side database generation alone): the 2nd of 2 queries of
+    the unmodified reference at the reduced second dimension WORKLOADS[cfg]['sample'], each stage scaled by its work ratio
+    (first_dim ~ records, folding ~ 2^nu2 - 1, expansion ~ forward NTTs, conversion ~ the reference's own cost model,
+    select_params.py:185-187: ScalToMat ~ 2^nu1, RegevToGSW ~ nu2 * t_GSW)."""
+    wl = WORKLOADS[cfg]
+    s1, s2 = wl.get("sample", (nu1, nu2))
+    s1, s2 = min(s1, nu1), min(s2, nu2)
+    res, info = run_reference(cfg, s1, s2, 2)
+    if res is None:
+        return None, info, None
+    q = res[-1]
+    prm = wl["prm"]
+    conv = lambda a, b: 185451.0 * (2 ** a / 512) * (prm["t_conv"] / 4) + 93709.0 * (b * prm["t_gsw"] / 40) * (prm["t_conv"] / 4)  # noqa: E731
+    scale = dict(first_dim=float(1 << (nu1 + nu2 - s1 - s2)), folding=((1 << nu2) - 1) / max((1 << s2) - 1, 1), packing=1.0,
+                 conversion=conv(nu1, nu2) / conv(s1, s2), expansion=expansion_ntts_spiral(prm, nu1, nu2) / expansion_ntts_spiral(prm, s1, s2))
+    scaled = {k: q[k] * scale[k] for k in STAGES}
+    scaled["total"] = sum(scaled[k] for k in STAGES)
+    scaled["correct"] = q["correct"]
+    text = (f"2nd of 2 queries of the unmodified reference at the reduced shape ./spiral {s1} {s2} (same macros; measured {q['total']:.0f} ms: "
+            + ", ".join(f"{k} {q[k]:.0f}" for k in STAGES if k != "packing") + "), each stage scaled by its work ratio "
+            + ", ".join(f"{k} x{scale[k]:.3g}" for k in STAGES if k != "packing"))
+    return scaled, info, text
+
+
+def expansion_ntts_spiral(prm, nu1, nu2):
+    """Forward-NTT count of expandImproved (src/spiral.cpp:1664-1743) with runConversionImproved's stopround rule (:2080-2085)."""
+    nbits = prm["t_gsw"] * nu2
+    g = ceil_log2(nbits + (1 << nu1))
+    stop = ceil_log2(max(nbits, 1)) if nbits <= (1 << nu1) else 0
+    total = 0
+    for r in range(g):
+        for i in range(2 << r):
+            if stop > 0 and r > stop and i % 2 == 1:
+                continue
+            if stop > 0 and r == stop and i % 2 == 1 and i // 2 > nbits:
+                continue
+            total += prm["t_exp_right"] if i % 2 else prm["t_exp"]
+    return total
+
+
 def oracle_port_baseline(nu1, nu2):
     """Fallback CPU baseline when oracle/_ref is absent: the oracle port (scalar C) on one core."""
     from tests import oracle_lib as ol
@@ -373,6 +414,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm: one driver per scheme variant, one shared timing harness
 # ------------------------------------------------------------------------------------------------
+CLIENT_SEED = bytes((37 * i + 11) & 0xFF for i in range(32))     # every rank derives the same client, keys and queries
+
+
 def rnd_ntt_factory(np, seed):
     rng = np.random.default_rng(seed)
 
@@ -382,14 +426,37 @@ def rnd_ntt_factory(np, seed):
     return rnd_ntt
 
 
+def planted_targets(nu1, nu2, world, count=None):
+    """Record indices to verify: one owned by EVERY rank (second-dimension index ii = rank mod world), spread over the first
+    dimension too, so each shard's scan, folds and its slot of the peer exchange carry a checked answer."""
+    num_per, dim0 = 1 << nu2, 1 << nu1
+    local = num_per // world
+    n = count or max(world, 2)
+    out = []
+    for k in range(n):
+        g = k % world
+        ii = g + world * ((5 * k + 3) % local)
+        j = (k * 2654435761 + 12345) % dim0
+        out.append(j * num_per + ii)
+    return out
+
+
+def planted_record(np, idx, polys, p_db):
+    return np.random.default_rng(0xB200 + idx).integers(0, p_db, size=(polys, N_POLY), dtype=np.uint64)
+
+
 class SpiralDriver:
-    """Spiral / SpiralStream (matrix-Regev) path: resident SpiralServer, one 64 KiB query in, one 96 KiB response out."""
+    """Spiral / SpiralStream (matrix-Regev) path: resident SpiralServer, one 64 KiB query in, one 96 KiB response out.
+    Keys and queries are REAL: the GPU client (sb200_client_*) generates the public parameters and encrypts the queries, known
+    records are planted in the synthetic database, and verify() decodes the answers of the timed calls."""
     kernel = "k_scan_spiral"
 
     def __init__(self, args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np):
         from spiral_b200 import SpiralParams
+        from spiral_b200.client import SpiralClient
         from spiral_b200.server import SpiralServer
-        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        self.torch, self.dist, self.rank, self.world, self.np = torch, dist, rank, world, np
+        self.nu1, self.nu2 = nu1, nu2
         p = WORKLOADS[cfg]["prm"]
         prm = SpiralParams(nu1, nu2, p["t_gsw"], p["t_conv"], p["t_exp"], p["t_exp_right"], p["qp_bits"], p["out_n"], p["p_db"])
         self.srv = srv = SpiralServer(prm, device=local_rank, rank=rank, world=world)
@@ -399,16 +466,24 @@ class SpiralDriver:
             handles = [None] * world
             dist.all_gather_object(handles, srv.xchg_export())
             srv.xchg_connect(handles)
-        # synthetic public parameters and query: uniform ring elements of the right shape (ref-NTT layout)
-        self.rnd_ntt = rnd_ntt = rnd_ntt_factory(np, 7)    # same on every rank (the query is replicated)
-        ell_bits = p["t_gsw"] * nu2
-        self.g = g = ceil_log2(ell_bits + (1 << nu1))
-        stop = ceil_log2(ell_bits) if ell_bits <= (1 << nu1) else 0
-        self.n_right = n_right = stop + 1 if stop else g
         self.p = p
-        srv.set_public_params(rnd_ntt(g * 2 * p["t_exp"]), rnd_ntt(n_right * 2 * p["t_exp_right"]),
-                              rnd_ntt(3 * 2 * p["t_conv"]), rnd_ntt(3 * 2 * p["t_conv"]))
-        self.q_host = torch.from_numpy(rnd_ntt(2).view(np.int64)).pin_memory()
+        ell_bits = p["t_gsw"] * nu2
+        self.g = ceil_log2(ell_bits + (1 << nu1))
+        stop = ceil_log2(ell_bits) if ell_bits <= (1 << nu1) else 0
+        self.n_right = stop + 1 if stop else self.g
+        self.rnd_ntt = rnd_ntt_factory(np, 7)             # synthetic keys for the extra clients of the serving-throughput section
+        # the client: same seed on every rank -> identical public parameters and queries without any broadcast
+        self.client = SpiralClient(prm, CLIENT_SEED, device=local_rank)
+        srv.set_public_params(*self.client.public_params())
+        # planted records: the owner of ii = idx mod 2^nu2 overwrites its local item
+        self.targets = planted_targets(nu1, nu2, world)
+        num_per, local = 1 << nu2, (1 << nu2) // world
+        for idx in self.targets:
+            j, ii = divmod(idx, num_per)
+            if ii % world == rank:
+                srv.load_db_items(planted_record(np, idx, 4, p["p_db"]).astype(np.uint16)[None], item_begin=j * local + ii // world)
+        self.q_host = torch.empty(2 * 2 * N_POLY, dtype=torch.int64).pin_memory()
+        self.set_query(self.targets[0], 1)
         self.resp_host = torch.empty(6 * N_POLY, dtype=torch.int64).pin_memory()
         self.gathered = torch.empty(world * 6 * N_POLY, dtype=torch.int64, device="cuda")
         self.part = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
@@ -417,6 +492,26 @@ class SpiralDriver:
         self.db_bytes = srv.db_bytes
         self.exchange = ("none (1 GPU)" if world == 1 else "peer-memory stores + flags over NVLink, fused into the stream (no NCCL call per query)"
                          if self.use_p2p else "NCCL all_gather of one 96 KiB ciphertext per GPU")
+
+    def set_query(self, idx, query_id):
+        """Encrypt a query for record idx (GPU client, seeded wire form) and expand it to the 64 KiB in-memory ciphertext that
+        sb200_server_upload_query / sb200_server_answer take (sb200_dev_query_from_wire + sb200_dev_ntt_to_ref)."""
+        torch, lib = self.torch, self.srv.lib
+        wire = self.client.query_wire(idx, query_id)
+        wdev = torch.zeros(wire.size + 64, dtype=torch.uint8, device="cuda")
+        wdev[:wire.size] = torch.from_numpy(wire).cuda()
+        cv = torch.empty(2 * 2 * N_POLY, dtype=torch.int32, device="cuda")
+        out = torch.empty(2 * 2 * N_POLY, dtype=torch.int64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for rc in (lib.sb200_dev_query_from_wire(cv.data_ptr(), wdev.data_ptr(), 1, st), lib.sb200_dev_ntt_to_ref(out.data_ptr(), cv.data_ptr(), 2, st)):
+            if rc != 0:
+                raise SystemExit("query expansion failed: " + lib.sb200_last_error().decode())
+        torch.cuda.current_stream().synchronize()
+        self.q_host.copy_(out.cpu())
+
+    def decode_matches(self, idx):
+        got = self.client.decode(self.resp_host.numpy().view(self.np.uint64))
+        return bool(self.np.array_equal(got, planted_record(self.np, idx, 4, self.p["p_db"])))
 
     def upload(self, stream):
         self.srv.upload_query_ptr(self.q_host.data_ptr(), stream)
@@ -447,7 +542,7 @@ class SpiralDriver:
             self.resp_host.copy_(self.resp_dev, non_blocking=True)
 
     # one GPU: the whole resident query / the whole host-buffer query as ONE C-ABI call each (sb200_server_process,
-    # sb200_server_answer) - the call a C++ host makes; the staged calls above remain for the sharded path
+    # sb200_server_answer) - the call a C++ host makes; the staged calls above remain for the NCCL-exchange path
     def process(self, stream, marks):
         self.srv.process(self.resp_dev.data_ptr(), stream, marks)
 
@@ -461,6 +556,7 @@ class SpiralDriver:
             raise SystemExit(f"rank {self.rank}: peer exchange timed out (error {self.srv.xchg_error(stream)})")
 
     def close(self):
+        self.client.close()
         self.srv.close()
 
 
@@ -471,7 +567,7 @@ class PackDriver:
     def __init__(self, args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np):
         from spiral_b200 import SpiralParams
         from spiral_b200.server import PackServer
-        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        self.torch, self.dist, self.rank, self.world, self.np = torch, dist, rank, world, np
         wl = WORKLOADS[cfg]
         p = wl["prm"]
         self.direct = wl["direct"]
@@ -483,6 +579,7 @@ class PackDriver:
         nbits = ell * nu2
         g, stop = ceil_log2(nbits + dim0), ceil_log2(max(nbits, 1))
         vW = rnd_ntt(n * (n + 1) * p["t_conv"])
+        self.targets = []
         if self.direct:
             srv.set_public_params(None, None, None, vW)
             self.vf_host = torch.from_numpy(rnd_ntt(dim0 * 2).view(np.int64)).pin_memory()
@@ -500,6 +597,7 @@ class PackDriver:
         self.gathered = torch.empty(world * words, dtype=torch.int64, device="cuda")
         self.d2h_bytes = int(self.resp_host.numel() * 8)
         self.db_bytes = srv.db_bytes
+        self.use_p2p = False
         self.exchange = "none (1 GPU)" if world == 1 else f"NCCL all_gather of {srv.planes} surviving 32 KiB ciphertexts per GPU"
 
     def upload(self, stream):
@@ -537,38 +635,19 @@ class PackDriver:
         self.srv.close()
 
 
-def b200_main(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    pass
 
-    from spiral_b200.lib import load_library
-    from spiral_b200.server import SpiralServer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # libraries (NCCL's version banner) write to fd 1: keep the real stdout for the single JSON line
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = load_library()
-
-    cfg, wl = args.workload, WORKLOADS[args.workload]
-    nu1, nu2, scaling = workload_shape(args, world)
+def run_workload(ctx, args, cfg, steps, headline):
+    """Builds the resident server(s) of one BASELINE.json configuration, verifies planted records through the timed calls,
+    times `steps` queries (device-resident and end to end) and returns the result dict on rank 0 (None elsewhere)."""
+    torch, dist, np, lib = ctx.torch, ctx.dist, ctx.np, ctx.lib
+    world, rank, local_rank, tstream, stream = ctx.world, ctx.rank, ctx.local_rank, ctx.tstream, ctx.stream
+    wl = WORKLOADS[cfg]
+    shape_args = args if headline else argparse.Namespace(workload=cfg, nu1=None, nu2=None, scaling=None)
+    nu1, nu2, scaling = workload_shape(shape_args, world)
     drv = (SpiralDriver if wl["kind"] == "spiral" else PackDriver)(args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np)
-    # a dedicated (non-legacy) stream: kernels, graph replays, events, NCCL and copies all run on it
-    tstream = torch.cuda.Stream()
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -621,6 +700,34 @@ def b200_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- correctness of the benchmarked configuration, through the exact calls that are timed below --------------------
+    # every planted record (one owned by each rank) is queried with a real encryption, answered by the (sharded) servers -
+    # at N > 1 through the cudaIpc / NVLink exchange - and decoded by the GPU client on rank 0
+    verified = None
+    if drv.targets:
+        ok, modes = [], []
+        for k, idx in enumerate(drv.targets):
+            drv.set_query(idx, 100 + k)
+            barrier()
+            if k % 2 == 0:                                     # host-buffer call path (e2e)
+                step(e2e=True); modes.append("host-buffer call")
+            else:                                              # device-resident call path (value), response fetched afterwards
+                drv.upload(stream); step(timed_events=[]); drv.download(); modes.append("resident call")
+            torch.cuda.current_stream().synchronize()
+            drv.check(stream)
+            if rank == 0:
+                ok.append(drv.decode_matches(idx))
+        flag = torch.tensor([int(all(ok)) if rank == 0 else 1], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verified = {"queries": len(drv.targets), "decoded_equal_planted": int(sum(ok)) if rank == 0 else None, "record_indices": drv.targets,
+                    "owner_ranks": [int((i % (1 << nu2)) % world) for i in drv.targets], "paths": sorted(set(modes)),
+                    "how": "GPU client (sb200_client_*: keys, public parameters, encrypted queries) -> the timed server calls on every rank "
+                           "(peer exchange included at N > 1) -> GPU decode on rank 0 == the record planted in the synthetic database"}
+        if int(flag[0]) != 1:
+            raise SystemExit(f"bench verification FAILED for {cfg}: decoded records {ok} for targets {drv.targets}")
+        drv.set_query(drv.targets[0], 1)
+
     # resident upload once for the device-timed loop
     drv.upload(stream)
     for _ in range(max(args.warmup, 3)):
@@ -628,7 +735,7 @@ def b200_main(args):
     barrier()
 
     if fused:
-        mark_pool.extend(new_marks() for _ in range(args.steps))
+        mark_pool.extend(new_marks() for _ in range(steps))
         torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -638,7 +745,7 @@ def b200_main(args):
     t_begin, t_end = ev(), ev()
     barrier()
     t_begin.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(timed_events=events)
     t_end.record()
     barrier()
@@ -650,7 +757,7 @@ def b200_main(args):
     e_begin, e_end = ev(), ev()
     barrier()
     e_begin.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(timed_events=None, e2e=True)
         torch.cuda.current_stream().synchronize()             # the caller holds the response before the next query
     e_end.record()
@@ -658,15 +765,148 @@ def b200_main(args):
     e2e_ms = e_begin.elapsed_time(e_end)
     clocks = sampler.stop() if rank == 0 else None
 
+    # sustained: the same device-resident step back to back for >= 2 s, clocks and power sampled over the whole loop
+    sustained = None
+    if headline and args.sustained_s > 0:
+        n_sus = max(steps, int(args.sustained_s * 1e3 / max(total_ms / steps, 1e-3)) + 1)
+        if world > 1:
+            t_n = torch.tensor([n_sus], device="cuda")
+            dist.all_reduce(t_n, op=dist.ReduceOp.MAX)
+            n_sus = int(t_n[0])
+        s_sampler = ClockSampler(local_rank)
+        s0, s1 = ev(), ev()
+        barrier()
+        if rank == 0:
+            s_sampler.start()
+        s0.record()
+        for _ in range(n_sus):
+            step(timed_events=None)
+        s1.record()
+        barrier()
+        sus_ms = s0.elapsed_time(s1)
+        s_clocks = s_sampler.stop() if rank == 0 else None
+        t_s = torch.tensor([sus_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        sustained = {"value": float(t_s[0]) / n_sus, "unit": "ms", "queries": n_sus, "seconds": float(t_s[0]) / 1e3, "clocks": s_clocks}
+        drv.check(stream)
+
+    extras = headline_extras(ctx, args, cfg, drv, steps, ev) if headline else {}
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    scan_ms = sorted(m[1].elapsed_time(m[2]) for m in events)
+    exp_ms = sum(m[0].elapsed_time(m[1]) for m in events) / len(events)
+    rest_ms = sum(m[2].elapsed_time(m[3]) for m in events) / len(events)
+    scan_avg = sum(scan_ms) / len(scan_ms)
+    sc = torch.tensor([scan_avg], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sc, op=dist.ReduceOp.MAX)
+    scan_max = float(sc[0])
+
+    line = None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        db_bytes_gpu = drv.db_bytes                            # algorithmic bytes per launch: 8 B x NTT coefficients on this GPU
+        achieved = db_bytes_gpu / (scan_avg * 1e-3) / 1e9
+        traffic, traffic_note = scan_traffic(cfg, world, scaling)
+        ms_per_query = total_ms / steps
+        l2_note = (f"database shard ({db_bytes_gpu / 2**30:.2f} GiB) is {db_bytes_gpu / 126e6:.0f}x the 126 MB L2 and is streamed once per query - no flush needed"
+                   if db_bytes_gpu > 4 * 126e6 else f"database shard is only {db_bytes_gpu / 2**20:.0f} MiB: partly L2-resident between queries")
+        line = {
+            "metric": "server_ms_per_query", "value": ms_per_query, "unit": "ms", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_query, "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "u64 (28-bit CRT residues, 32x32->64 MAC)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(cfg, nu1, nu2), "sharding": f"second dimension strided over {world} GPU(s), {db_bytes_gpu / 2**30:.2f} GiB shard per GPU",
+                       "exchange": drv.exchange, "l2": l2_note},
+            "stages_ms": {"expansion_conversion": exp_ms, "first_dim_scan": scan_avg, "lift_fold_modswitch": rest_ms},
+            "db_gbs_scanned": world * db_bytes_gpu / (scan_max * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_note, "kernel": drv.kernel, "peak_source": peak_src,
+                         "scan_ms_min_med_max": [scan_ms[0], scan_ms[len(scan_ms) // 2], scan_ms[-1]]},
+            "e2e": {"value": e2e_ms / steps, "unit": "ms", "h2d_bytes_per_step": drv.h2d_bytes, "d2h_bytes_per_step": drv.d2h_bytes},
+            "gpu_launches": int(launches), "clocks": clocks, "verified": verified,
+        }
+        if sustained is not None:
+            line["sustained"] = sustained
+        line.update(extras)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_for(cfg, wl, nu1, nu2, headline)
+    drv.close()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return line
+
+
+def scan_traffic(cfg, world, scaling):
+    """ncu dram__bytes (read + write) per launch of the scan kernel, from profiles/scan_traffic.json - valid only while the kernel
+    sources it was captured with are the ones built now (the file records their SHA-256; scripts/update_scan_traffic.py)."""
+    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if not os.path.exists(tp):
+        return None, "no ncu capture committed"
+    try:
+        import hashlib
+        tj = json.load(open(tp))
+        for rel, want in tj.get("kernel_source_sha256", {}).items():
+            have = hashlib.sha256(open(os.path.join(ROOT, rel), "rb").read()).hexdigest()
+            if have != want:
+                return None, f"stale: {rel} changed since the ncu capture of commit {tj.get('commit', '?')}"
+        key = "dram_bytes_per_launch" if cfg == "cfg1" and scaling == "weak" else f"dram_bytes_per_launch_{cfg}_{world}gpu"
+        if "kernel_source_sha256" not in tj:
+            return None, "capture has no source hashes (made before round 2)"
+        return tj.get(key), f"ncu --set full capture of commit {tj.get('commit', '?')} ({tj.get('captured', '?')})"
+    except Exception as e:  # noqa: BLE001
+        return None, f"unreadable: {e}"
+
+
+def cpu_baseline_for(cfg, wl, nu1, nu2, headline):
+    """The unmodified reference (oracle/_ref) on ONE host core: the same workload when it is small (cfg1), otherwise a bounded
+    sample at a reduced shape with every stage scaled by its own work ratio (stated in `sample`)."""
+    if wl["kind"] == "pack":
+        q, info, text = pack_sample_scaled(cfg, nu1, nu2)
+        if q is not None:
+            return {"value": q["total"], "unit": "ms", "cores": 1, "kind": "reference", "stages_ms": {k: q[k] for k in STAGES},
+                    "sample": text + f"; 1 thread on {cpu_model()} ({info}); decoded correctly: {q['correct']}"}
+        return {"value": None, "unit": "ms", "cores": 0, "kind": "reference", "sample": f"unavailable: {info}"}
+    if not headline:
+        q, info, text = spiral_sample_scaled(cfg, nu1, nu2)
+        if q is not None:
+            return {"value": q["total"], "unit": "ms", "cores": 1, "kind": "reference", "stages_ms": {k: q[k] for k in STAGES if k != "packing"},
+                    "sample": text + f"; 1 thread on {cpu_model()} ({info}); decoded correctly: {q['correct']}"}
+        return {"value": None, "unit": "ms", "cores": 0, "kind": "reference", "sample": f"unavailable: {info}"}
+    res, info = (None, "database too large for the host") if db_bytes_total(wl, nu1, nu2) * 2.5 > mem_available() else run_reference(cfg, nu1, nu2, 2)
+    if res is not None:
+        qd = res[-1]
+        return {"value": qd["total"], "unit": "ms", "cores": 1, "kind": "reference",
+                "stages_ms": {k: qd[k] for k in ("expansion", "conversion", "first_dim", "folding")},
+                "sample": f"unmodified reference (oracle/_ref, {info}), 2nd of 2 full queries at the same workload, 1 thread on {cpu_model()}, decoded correctly: {qd['correct']}"}
+    try:
+        ms = oracle_port_baseline(6, 4)
+        return {"value": ms, "unit": "ms", "cores": 1, "kind": "port", "sample": f"oracle port, one query at ./spiral 6 4 (1/32 of the records), 1 core ({info})"}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+
+
+def headline_extras(ctx, args, cfg, drv, steps, ev):
+    """Sections only the headline workload carries: the wire-format call path and the serving-throughput experiments."""
+    torch, np, lib = ctx.torch, ctx.np, ctx.lib
+    world, tstream, stream = ctx.world, ctx.tstream, ctx.stream
+    wl = WORKLOADS[cfg]
+    from spiral_b200.server import SpiralServer
+    out = {}
     # the same exchange in wire form (SURVEY 8f #2): seed-compressed query in (14 376 B), QPBITS-packed response out;
     # seed expansion + unpacking are the first node of the expansion graph, the response packer one extra launch
-    e2e_wire = None
     if world == 1 and wl["kind"] == "spiral":
         srv = drv.srv
         wbytes = int(lib.sb200_wire_query_bytes(1))
-        wrng = np.random.default_rng(11)
-        wire = wrng.integers(0, 256, wbytes, dtype=np.uint8)
-        wire[:8] = np.frombuffer(b"SB2Q\x01\x00\x00\x00", dtype=np.uint8)
+        wire = drv.client.query_wire(drv.targets[1], 7)
         wire_host = torch.from_numpy(wire).pin_memory()
         pbytes = int(lib.sb200_server_packed_response_bytes(srv.h))
         packed_host = torch.empty(pbytes // 8, dtype=torch.int64).pin_memory()
@@ -680,12 +920,17 @@ def b200_main(args):
         w_begin, w_end = ev(), ev()
         torch.cuda.synchronize()
         w_begin.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             wire_query()                                       # synchronises the stream: the caller holds the packed response
         w_end.record()
         torch.cuda.synchronize()
-        e2e_wire = {"value": w_begin.elapsed_time(w_end) / args.steps, "unit": "ms", "h2d_bytes_per_step": wbytes, "d2h_bytes_per_step": pbytes,
-                    "note": "sb200_server_answer_wire: seeded wire query (ChaCha20 row 0) in, packed response out"}
+        got = drv.client.decode(srv.unpack_response(packed_host.numpy().view(np.uint64)))
+        wire_ok = bool(np.array_equal(got, planted_record(np, drv.targets[1], 4, drv.p["p_db"])))
+        if not wire_ok:
+            raise SystemExit("bench verification FAILED: wire-format answer does not decode to the planted record")
+        out["e2e_wire"] = {"value": w_begin.elapsed_time(w_end) / steps, "unit": "ms", "h2d_bytes_per_step": wbytes, "d2h_bytes_per_step": pbytes,
+                           "decoded_equal_planted": wire_ok,
+                           "note": "sb200_server_answer_wire: seeded wire query (ChaCha20 row 0) in, packed response out"}
         drv.upload(stream)                                     # back to the plain query for the sections below
 
     # serving throughput on ONE GPU: several clients in flight (views over the same resident database, one stream
@@ -715,59 +960,15 @@ def b200_main(args):
                 one(ci)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             for ci in range(len(clients)):
                 one(ci)
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        nq = args.steps * len(clients)
+        nq = steps * len(clients)
         pipelined = {"clients": len(clients), "queries": nq, "ms_per_query_amortised": wall_ms / nq, "queries_per_s": nq / (wall_ms * 1e-3),
                      "db_gbs_scanned": srv.db_bytes * nq / (wall_ms * 1e-3) / 1e9,
                      "note": "host wall clock around all streams; every query includes its H2D query upload and D2H response"}
-        # batched first dimension: the clients' expansions run concurrently, ONE database pass serves all of them
-        # (sb200_server_scan_batched), then their folds run concurrently again
-        if len(clients) in (2, 4):
-            evs = [torch.cuda.Event() for _ in clients]
-            ev_scan = torch.cuda.Event()
-
-            def batch_round():
-                for ci, (c, st) in enumerate(zip(clients, streams)):
-                    with torch.cuda.stream(st):
-                        c.upload_query_ptr(q_host.data_ptr(), st.cuda_stream)
-                        c.expand_and_convert(st.cuda_stream)
-                        evs[ci].record(st)
-                with torch.cuda.stream(streams[0]):
-                    for ci in range(1, len(clients)):
-                        streams[0].wait_event(evs[ci])
-                    SpiralServer.scan_batched(clients, streams[0].cuda_stream)
-                    ev_scan.record(streams[0])
-                for ci, (c, st) in enumerate(zip(clients, streams)):
-                    with torch.cuda.stream(st):
-                        st.wait_event(ev_scan)
-                        c.lift(st.cuda_stream); c.fold_local(st.cuda_stream)
-                        c.fold_tail(c.partial_ct_ptr(), resp_devs[ci].data_ptr(), st.cuda_stream)
-                        resp_hosts[ci].copy_(resp_devs[ci], non_blocking=True)
-            for _ in range(3):
-                batch_round()
-            torch.cuda.synchronize()
-            sb0, sb1 = ev(), ev()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                batch_round()
-            torch.cuda.synchronize()
-            wall_ms = (time.perf_counter() - t0) * 1e3
-            # the batched scan alone, bracketed by events
-            torch.cuda.synchronize()
-            with torch.cuda.stream(streams[0]):
-                sb0.record(streams[0])
-                for _ in range(5):
-                    SpiralServer.scan_batched(clients, streams[0].cuda_stream)
-                sb1.record(streams[0])
-            torch.cuda.synchronize()
-            nq = args.steps * len(clients)
-            pipelined["batched_scan"] = {"queries_per_pass": len(clients), "ms_per_query_amortised": wall_ms / nq, "queries_per_s": nq / (wall_ms * 1e-3),
-                                         "scan_pass_ms": sb0.elapsed_time(sb1) / 5,
-                                         "effective_db_gbs_per_query_stream": srv.db_bytes * len(clients) / (sb0.elapsed_time(sb1) / 5 * 1e-3) / 1e9}
         # tensor-core batched first dimension (tc_scan.cu): up to 16 clients' converted queries answered by ONE tcgen05 pass
         # over the limb-tile copy of the database; expansions and folds of the clients overlap on their own streams
         if args.tc_batch > 1 and lib.sb200_tc_supported(srv.dim0, srv.num_per):
@@ -804,7 +1005,11 @@ def b200_main(args):
             for _ in range(3):
                 tc_round()
             torch.cuda.synchronize()
-            rounds = max(3, args.steps // 2)
+            # client 0 holds the real keys and the real query: its answer out of the shared tensor-core pass must decode
+            tc_ok = bool(np.array_equal(drv.client.decode(resp_hosts[0].numpy().view(np.uint64)), planted_record(np, drv.targets[0], 4, p["p_db"])))
+            if not tc_ok:
+                raise SystemExit("bench verification FAILED: tensor-core batched answer does not decode to the planted record")
+            rounds = max(3, steps // 2)
             t0 = time.perf_counter()
             for _ in range(rounds):
                 tc_round()
@@ -825,6 +1030,7 @@ def b200_main(args):
                 "db_gbs_per_pass": srv.db_bytes / (pass_ms * 1e-3) / 1e9,
                 "effective_db_gbs_x_queries": srv.db_bytes * nb / (pass_ms * 1e-3) / 1e9,
                 "int8_tensor_tops": 2.0 * 16 * 3 * nb * (srv.db_bytes / 8) * 2 / (pass_ms * 1e-3) / 1e12,
+                "decoded_equal_planted": tc_ok,
                 "note": "pass = query tiles (k_query_to_tc x queries) + k_scan_tc (tcgen05 kind::i8, u8 limbs) + k_tc_untile; bit-exact (tests/test_gpu_tc.py)"}
         for c in clients[1:]:
             c.close()
@@ -866,7 +1072,7 @@ def b200_main(args):
         for _ in range(2):
             pack_tc_round()
         torch.cuda.synchronize()
-        rounds = max(2, args.steps // 4)
+        rounds = max(2, steps // 4)
         t0 = time.perf_counter()
         for _ in range(rounds):
             pack_tc_round()
@@ -891,82 +1097,58 @@ def b200_main(args):
         for c in tcc[1:]:
             c.close()
         torch.cuda.set_stream(tstream)
+    if pipelined is not None:
+        out["pipelined"] = pipelined
+    return out
 
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+
+def b200_main(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from spiral_b200.lib import load_library
+
+    ctx = Ctx()
+    ctx.torch, ctx.dist, ctx.np = torch, dist, np
+    ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = rank = int(os.environ.get("RANK", "0"))
+    ctx.local_rank = local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner) write to fd 1: keep the real stdout for the single JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx.lib = load_library()
+    # a dedicated (non-legacy) stream: kernels, graph replays, events, NCCL and copies all run on it
+    ctx.tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(ctx.tstream)
+    ctx.stream = ctx.tstream.cuda_stream
 
-    scan_ms = sorted(m[1].elapsed_time(m[2]) for m in events)
-    exp_ms = sum(m[0].elapsed_time(m[1]) for m in events) / len(events)
-    rest_ms = sum(m[2].elapsed_time(m[3]) for m in events) / len(events)
-    scan_avg = sum(scan_ms) / len(scan_ms)
-    sc = torch.tensor([scan_avg], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(sc, op=dist.ReduceOp.MAX)
-    scan_max = float(sc[0])
-
+    line = run_workload(ctx, args, args.workload, args.steps, headline=True)
+    # the other north-star databases ride on the same line, so the driver's BENCH / SCALE records carry them at every N:
+    # cfg5 (Spiral 2^22 x 256 B, 8 GiB) and cfg3 (SpiralPack 2^18 x 30 KB, 64 GiB), both strong-scaled over the N GPUs
+    extra = [w for w in args.workloads.split(",") if w] if args.workload == "cfg1" and args.nu1 is None and args.nu2 is None else []
+    subs = {}
+    for w in extra:
+        if w not in WORKLOADS or w == args.workload:
+            continue
+        sub = run_workload(ctx, args, w, max(3, min(args.steps, 10 if WORKLOADS[w]["kind"] == "spiral" else 5)), headline=False)
+        if sub is not None:
+            subs[w] = {k: sub[k] for k in ("value", "unit", "steps", "scaling", "config", "stages_ms", "db_gbs_scanned", "roofline", "e2e",
+                                           "gpu_launches", "clocks", "verified", "cpu_baseline") if k in sub}
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-        else:
-            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        db_bytes_gpu = drv.db_bytes                            # algorithmic bytes per launch: 8 B x NTT coefficients on this GPU
-        achieved = db_bytes_gpu / (scan_avg * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get("dram_bytes_per_launch") if cfg == "cfg1" and scaling == "weak" else tj.get(f"dram_bytes_per_launch_{cfg}_{world}gpu")
-            except Exception:  # noqa: BLE001
-                traffic = None
-        ms_per_query = total_ms / args.steps
-        l2_note = (f"database shard ({db_bytes_gpu / 2**30:.2f} GiB) is {db_bytes_gpu / 126e6:.0f}x the 126 MB L2 and is streamed once per query - no flush needed"
-                   if db_bytes_gpu > 4 * 126e6 else f"database shard is only {db_bytes_gpu / 2**20:.0f} MiB: partly L2-resident between queries")
-        line = {
-            "metric": "server_ms_per_query", "value": ms_per_query, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_query, "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "u64 (28-bit CRT residues, 32x32->64 MAC)",
-            "data": "synthetic",
-            "config": {"workload": workload_name(cfg, nu1, nu2), "sharding": f"second dimension strided over {world} GPU(s), {db_bytes_gpu / 2**30:.2f} GiB shard per GPU",
-                       "exchange": drv.exchange, "l2": l2_note},
-            "stages_ms": {"expansion_conversion": exp_ms, "first_dim_scan": scan_avg, "lift_fold_modswitch": rest_ms},
-            "db_gbs_scanned": world * db_bytes_gpu / (scan_max * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": drv.kernel, "peak_source": peak_src, "scan_ms_min_med_max": [scan_ms[0], scan_ms[len(scan_ms) // 2], scan_ms[-1]]},
-            "e2e": {"value": e2e_ms / args.steps, "unit": "ms", "h2d_bytes_per_step": drv.h2d_bytes, "d2h_bytes_per_step": drv.d2h_bytes},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
-        if e2e_wire is not None:
-            line["e2e_wire"] = e2e_wire
-        if pipelined is not None:
-            line["pipelined"] = pipelined
-        if world == 1 and not args.no_cpu_baseline:
-            if wl["kind"] == "pack":
-                q, info, text = pack_sample_scaled(cfg, nu1, nu2)
-                if q is not None:
-                    line["cpu_baseline"] = {"value": q["total"], "unit": "ms", "cores": 1, "kind": "reference", "stages_ms": {k: q[k] for k in STAGES},
-                                            "sample": text + f"; 1 thread on {cpu_model()} ({info}); decoded correctly: {q['correct']}"}
-                else:
-                    line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "reference", "sample": f"unavailable: {info}"}
-            else:
-                res, info = (None, "database too large for the host") if db_bytes_total(wl, nu1, nu2) * 2.5 > mem_available() else run_reference(cfg, nu1, nu2, 2)
-                if res is not None:
-                    qd = res[-1]
-                    line["cpu_baseline"] = {"value": qd["total"], "unit": "ms", "cores": 1, "kind": "reference",
-                                            "stages_ms": {k: qd[k] for k in ("expansion", "conversion", "first_dim", "folding")},
-                                            "sample": f"unmodified reference (oracle/_ref, {info}), 2nd of 2 full queries at the same workload, 1 thread on {cpu_model()}, decoded correctly: {qd['correct']}"}
-                else:
-                    try:
-                        ms = oracle_port_baseline(6, 4)
-                        line["cpu_baseline"] = {"value": ms, "unit": "ms", "cores": 1, "kind": "port",
-                                                "sample": f"oracle port, one query at ./spiral 6 4 (1/32 of the records), 1 core ({info})"}
-                    except Exception as e:  # noqa: BLE001
-                        line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+        if subs:
+            line["workloads"] = subs
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    drv.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -986,6 +1168,9 @@ def main():
     ap.add_argument("--clients", type=int, default=4, help="N = 1: concurrent clients for the serving-throughput figure (0/1 = skip)")
     ap.add_argument("--tc-batch", type=int, default=16, help="N = 1, Spiral: queries per tensor-core database pass in the serving-throughput section (0/1 = skip)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the surviving ciphertexts reach rank 0")
+    ap.add_argument("--workloads", default="cfg5,cfg3", help="with the default headline (cfg1): further BASELINE.json configurations measured into "
+                    "the line's `workloads` section ('' = none)")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="seconds of back-to-back queries for the `sustained` figure (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 8:

@@ -59,6 +59,15 @@ int sb200_abi_version(void);
 uint64_t sb200_arb_qprime(uint32_t qp_bits);           /* include/values.h:74-76 */
 /* kernels launched by this process since load (our own launches only) */
 uint64_t sb200_launch_count(void);
+/* names of the distinct kernels launched since the last reset, comma-separated and sorted; returns the bytes needed
+   (tests print the kernel set a shape dispatched to) */
+size_t sb200_kernel_log(char *buf, size_t cap);
+void sb200_kernel_log_reset(void);
+/* timeline trace (profiling): with capacity > 0 the first CTA of every kernel records {ns it was scheduled, ns its
+   dependencies were resolved, gridDim.x | gridDim.y << 24 | blockDim.x << 48}; read copies up to max_records x 3 words.
+   Works inside replayed CUDA graphs, where ncu's serialised timings say nothing about a dependent chain.  0 = off. */
+int sb200_trace_enable(uint32_t capacity);
+size_t sb200_trace_read(uint64_t *out, size_t max_records, int reset);
 
 /* ---- tier 1: device pointers ---------------------------------------------------------- */
 int sb200_dev_ntt_from_ref(uint32_t *out, const uint64_t *in_ref_ntt, size_t npolys, void *stream);
@@ -165,6 +174,9 @@ uint64_t *sb200_server_db_ptr(sb200_server *srv);          /* device pointer of 
  * W_conv 3 x 2*t_conv, V_conv 3 x 2*t_conv  (runConversionImproved, src/spiral.cpp:2093-2300) */
 int sb200_server_set_public_params(sb200_server *srv, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
                                    const uint64_t *W_conv, const uint64_t *V_conv);
+/* polynomial counts (2*2048 words each) of those four matrices, in that order: what the server will READ.  Public parameters
+ * arrive from an untrusted client - compare the sizes received with these before calling sb200_server_set_public_params. */
+int sb200_server_public_param_polys(const sb200_server *srv, size_t *out4);
 /* one query end to end: H2D of the packed query ciphertext (2x1 ref-NTT, 64 KiB), all server stages, D2H of the
  * modulus-switched response (3x2 raw, 96 KiB).  world == 1 only. */
 int sb200_server_answer(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream);
@@ -205,6 +217,10 @@ int sb200_server_xchg_connect(sb200_server *srv, const void *all_handles);      
 int sb200_server_xchg_connect_local(sb200_server *srv, sb200_server *const *all_servers);  /* shards inside one process */
 int sb200_server_exchange_and_tail(sb200_server *srv, uint64_t *total_resp_dev, void *stream);
 int sb200_server_xchg_error(sb200_server *srv, void *stream);      /* 0 ok; 1/2 = a bounded spin timed out (4 s) */
+/* after a time-out the shards are out of step and every later exchange would time out too: with no query in flight EVERY rank
+ * calls this (epochs, flags, acks, error word start over).  sb200_server_download on a sharded server returns SB200_ERR_STATE
+ * instead of a garbage response while the error word is set. */
+int sb200_server_xchg_reset(sb200_server *srv);
 int sb200_server_download(sb200_server *srv, uint64_t *dst_host, const uint64_t *src_dev, size_t words, void *stream);
 /* debug taps (device pointers): raw cts after the first dimension; final ct before modulus switch */
 uint64_t *sb200_server_first_dim_cts(sb200_server *srv);
@@ -319,9 +335,16 @@ void sb200_client_destroy(sb200_client *c);
 int sb200_client_public_param_polys(const sb200_client *c, size_t *out4);
 /* ref-NTT host buffers, exactly what sb200_server_set_public_params takes */
 int sb200_client_public_params(sb200_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *W_conv, uint64_t *V_conv);
-/* SEEDED wire query for record idx_target: row 0 from wire_seed32 (what the server regenerates), noise from the client's own
- * stream number query_id (< 2^24; never reuse one with the same client seed); wire_out: sb200_wire_query_bytes(1) bytes */
+/* SEEDED wire query for record idx_target; wire_out: sb200_wire_query_bytes(1) bytes.
+ * FRESHNESS (privacy-critical): query_id (< 2^24) names the noise stream AND, with wire_seed32 == NULL (the recommended call),
+ * the seed of row 0 = -a, which is then derived from the client key and query_id (sb200_client_wire_seed) - so ONE monotonic
+ * counter per client key is all a caller keeps, and it must never repeat.  An explicit wire_seed32 is for tests / callers with
+ * their own randomness; it too must never repeat under one client key: two queries sharing `a` reveal sigma - sigma' (the
+ * difference of the queried indices) to the server. */
 int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out);
+/* the row-0 seed sb200_client_query_wire derives for query_id: ChaCha20 block (key = client seed, counter 0, nonce {"SB2C",
+ * 6 << 24 | query_id, "wsee"}), first 32 bytes */
+int sb200_client_wire_seed(const sb200_client *c, uint32_t query_id, uint8_t *seed32_out);
 /* total_resp: 3x2 raw response (sb200_server_answer, or sb200_unpack_response of the packed one) -> 2x2 plaintext polynomials */
 int sb200_client_decode(sb200_client *c, const uint64_t *total_resp_host, uint64_t *pt_out_host);
 /* test taps: the secret key (raw, 1 + 2 polynomials) and the sampler's 128 integer thresholds */

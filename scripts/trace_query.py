@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Timeline of ONE query inside the replayed CUDA graphs (sb200_trace_enable / sb200_trace_read): for every kernel the time its
+first CTA was scheduled and the time its dependencies were resolved (griddepcontrol.wait returned).  The difference between
+consecutive dependency-resolved times is what each link of the launch chain really costs - ncu's serialised, cold-cache
+durations cannot show that.  usage: python scripts/trace_query.py [cfg1|cfg5] [--nu1 N --nu2 N] > profiles/rNN_trace.md"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from spiral_b200 import SpiralParams  # noqa: E402
+from spiral_b200.lib import load_library  # noqa: E402
+from spiral_b200.server import SpiralServer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workload", nargs="?", default="cfg1")
+    ap.add_argument("--nu1", type=int)
+    ap.add_argument("--nu2", type=int)
+    ap.add_argument("--queries", type=int, default=3)
+    a = ap.parse_args()
+    wl = bench.WORKLOADS[a.workload]
+    p = wl["prm"]
+    nu1, nu2 = a.nu1 or wl["nu1"], a.nu2 or wl["nu2"]
+    lib = load_library()
+    prm = SpiralParams(nu1, nu2, p["t_gsw"], p["t_conv"], p["t_exp"], p["t_exp_right"], p["qp_bits"], p["out_n"], p["p_db"])
+    srv = SpiralServer(prm)
+    srv.load_db_random(1)
+    rnd = bench.rnd_ntt_factory(np, 7)
+    nbits = p["t_gsw"] * nu2
+    g = bench.ceil_log2(nbits + (1 << nu1))
+    stop = bench.ceil_log2(nbits) if nbits <= (1 << nu1) else 0
+    srv.set_public_params(rnd(g * 2 * p["t_exp"]), rnd((stop + 1 if stop else g) * 2 * p["t_exp_right"]), rnd(6 * p["t_conv"]), rnd(6 * p["t_conv"]))
+    st = torch.cuda.Stream()
+    torch.cuda.set_stream(st)
+    q = torch.from_numpy(rnd(2).view(np.int64)).pin_memory()
+    srv.upload_query_ptr(q.data_ptr(), st.cuda_stream)
+    for _ in range(5):
+        srv.process(None, st.cuda_stream, None)
+    torch.cuda.synchronize()
+    assert lib.sb200_trace_enable(4096) == 0
+    for _ in range(a.queries):
+        srv.process(None, st.cuda_stream, None)
+    torch.cuda.synchronize()
+    buf = np.zeros(4096 * 3, dtype=np.uint64)
+    n = lib.sb200_trace_read(buf.ctypes.data, 4096, 1)
+    lib.sb200_trace_enable(0)
+    rec = buf[:3 * n].reshape(n, 3)
+    per = n // a.queries
+    rec = rec[(a.queries - 1) * per:]                       # the last query
+    rec = rec[np.argsort(rec[:, 1], kind="stable")]
+    t0 = int(rec[0, 1])
+    print(f"# {bench.workload_name(a.workload, nu1, nu2)}: one query, {per} kernels, {(int(rec[-1, 1]) - t0) / 1e3:.1f} us from the first to the last dependency-resolved time")
+    print("| # | grid | block | scheduled us | ready us | to next ready us | waited us |")
+    print("|---:|---|---:|---:|---:|---:|---:|")
+    for i, (ts, tr, shape) in enumerate(rec):
+        gx, gy, bx = int(shape) & 0xFFFFFF, (int(shape) >> 24) & 0xFFFFFF, int(shape) >> 48
+        nxt = (int(rec[i + 1, 1]) - int(tr)) / 1e3 if i + 1 < len(rec) else 0.0
+        print(f"| {i} | ({gx},{gy}) | {bx} | {(int(ts) - t0) / 1e3:.1f} | {(int(tr) - t0) / 1e3:.1f} | {nxt:.1f} | {(int(tr) - int(ts)) / 1e3:.1f} |")
+    srv.close()
+
+
+if __name__ == "__main__":
+    main()

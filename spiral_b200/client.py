@@ -35,12 +35,22 @@ class SpiralClient:
         check(self.lib.sb200_client_public_params(self.h, *[_p64(m) for m in mats]), self.lib)
         return mats
 
-    def query_wire(self, idx, query_id, wire_seed: bytes):
+    def query_wire(self, idx, query_id, wire_seed: bytes = None):
+        """SEEDED wire query.  query_id must never repeat under one client seed; wire_seed=None (recommended) derives the
+        row-0 seed from the client key and query_id, an explicit one must be fresh per query as well."""
+        wire = np.zeros(self.lib.sb200_wire_query_bytes(1), dtype=np.uint8)
+        if wire_seed is None:
+            check(self.lib.sb200_client_query_wire(self.h, idx, query_id, None, wire.ctypes.data), self.lib)
+            return wire
         assert len(wire_seed) == 32
         seed = np.frombuffer(bytes(wire_seed), dtype=np.uint8).copy()
-        wire = np.zeros(self.lib.sb200_wire_query_bytes(1), dtype=np.uint8)
         check(self.lib.sb200_client_query_wire(self.h, idx, query_id, seed.ctypes.data, wire.ctypes.data), self.lib)
         return wire
+
+    def wire_seed(self, query_id):
+        out = np.zeros(32, dtype=np.uint8)
+        check(self.lib.sb200_client_wire_seed(self.h, query_id, out.ctypes.data), self.lib)
+        return out.tobytes()
 
     def decode(self, total_resp):
         """3x2 raw response -> (4, 2048) plaintext coefficients (the record's 2x2 matrix of polynomials)."""

@@ -46,6 +46,10 @@ static int ensure_device() {
 extern "C" const char *sb200_last_error(void) { return g_err.c_str(); }
 extern "C" int sb200_abi_version(void) { return 1; }
 extern "C" uint64_t sb200_launch_count(void) { return launch_count(); }
+extern "C" size_t sb200_kernel_log(char *buf, size_t cap) { return kernel_log(buf, cap); }
+extern "C" void sb200_kernel_log_reset(void) { kernel_log_reset(); }
+extern "C" int sb200_trace_enable(uint32_t capacity) { int rc_ = ensure_device(); if (rc_) return rc_; return trace_enable(capacity) ? fail(SB200_ERR_CUDA, "trace_enable failed") : SB200_OK; }
+extern "C" size_t sb200_trace_read(uint64_t *out, size_t max_records, int reset) { return trace_read(reinterpret_cast<unsigned long long *>(out), max_records, reset); }
 extern "C" uint64_t sb200_arb_qprime(uint32_t qp_bits) {     // reference include/values.h:74-76
     static const uint64_t qprime_mods[37] = {
         0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 12289, 12289, 61441, 65537, 65537, 520193, 786433,
@@ -546,6 +550,10 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(SB200_ERR_ARG, "server_create: world must be a power of two and 0 <= rank < world");
     if (((size_t)1 << prm->nu2) < (size_t)world) return fail(SB200_ERR_ARG, "server_create: 2^nu2 < world");
     if (prm->t_gsw == 0 || prm->t_conv == 0 || prm->t_exp == 0 || prm->t_exp_right == 0) return fail(SB200_ERR_ARG, "server_create: zero gadget length");
+    if (sb200_arb_qprime(prm->qp_bits) == 0) return fail(SB200_ERR_ARG, "server_create: no response modulus for qp_bits = %u (14..36)", prm->qp_bits);
+    if (prm->p_db == 0 || prm->p_db > 65536) return fail(SB200_ERR_ARG, "server_create: p_db must be in [1, 65536]");
+    if (prm->nu1 > 11 || ((size_t)1 << prm->nu1) + (size_t)prm->t_gsw * prm->nu2 > (size_t)kN)
+        return fail(SB200_ERR_ARG, "server_create: 2^nu1 + t_GSW*nu2 exceeds the 2048 slots of a packed query");
     int rc = sb200_init(device);
     if (rc) return rc;
     sb200_server *s = new sb200_server();
@@ -688,6 +696,15 @@ static int server_up_ntt(sb200_server *s, DBuf<uint32_t> &dst, const uint64_t *h
         launch_ntt_u64_to_dev(dst.p + o * PLW, tmp.p, n, 0); CHECK_LAUNCH();
         CU(cudaDeviceSynchronize());
     }
+    return SB200_OK;
+}
+// polynomial counts (2*2048 words each) of the four matrices sb200_server_set_public_params reads: a host that receives them
+// from an untrusted client checks the sizes against these before handing the pointers over
+extern "C" int sb200_server_public_param_polys(const sb200_server *s, size_t *out4) {
+    if (!s || !out4) return fail(SB200_ERR_ARG, "server_public_param_polys: null argument");
+    const size_t n_right = s->stopround > 0 ? s->stopround + 1 : s->g;
+    out4[0] = s->g * 2 * s->prm.t_exp; out4[1] = n_right * 2 * s->prm.t_exp_right;
+    out4[2] = out4[3] = 3 * 2 * (size_t)s->prm.t_conv;
     return SB200_OK;
 }
 extern "C" int sb200_server_set_public_params(sb200_server *s, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
@@ -844,22 +861,37 @@ extern "C" int sb200_server_copy_partial(sb200_server *s, uint64_t *dst_dev, voi
     CU(cudaMemcpyAsync(dst_dev, s->cts.p, 6 * (size_t)kN * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ES(s, stream)));
     return SB200_OK;
 }
+// synthetic plaintext coefficients, uniform in [0, p_db): counter-based (splitmix64), 4 values per thread
+__global__ void k_fill_random_u16(uint16_t *__restrict__ dst, size_t n4, uint32_t p_db, uint64_t seed) {
+    pdl_prologue();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    uint64_t x = seed + (i + 1) * 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull; x ^= x >> 31;
+    ushort4 o;
+    o.x = (uint16_t)((x & 0xffff) % p_db); o.y = (uint16_t)(((x >> 16) & 0xffff) % p_db);
+    o.z = (uint16_t)(((x >> 32) & 0xffff) % p_db); o.w = (uint16_t)((x >> 48) % p_db);
+    reinterpret_cast<ushort4 *>(dst)[i] = o;
+}
 extern "C" int sb200_server_load_db_random(sb200_server *s, uint64_t seed) {
-    // synthetic database for benchmarks: uniform plaintext coefficients generated on the host in chunks
+    // synthetic database for benchmarks: uniform plaintext coefficients generated ON THE DEVICE chunk by chunk, then the normal
+    // preprocessing (centre-lift, CRT, NTT, scan layout)
     if (!s) return fail(SB200_ERR_ARG, "null server");
-    const size_t total_local = s->dim0 * s->local_num_per, chunk = 2048;
-    std::vector<uint16_t> h(chunk * 4 * kN);
-    uint64_t x = seed * 0x9e3779b97f4a7c15ull + 0x1234567ull;
-    const uint32_t p_db = (uint32_t)s->prm.p_db;
+    CU(cudaSetDevice(s->device));
+    TRY(server_alloc_db(s));
+    const size_t total_local = s->dim0 * s->local_num_per, chunk = 8192;
+    DBuf<uint16_t> d;
+    CU(d.alloc(std::min(chunk, total_local) * 4 * kN));
+    const uint32_t nu2_local = (uint32_t)ceil_log2(s->local_num_per);
     for (size_t o = 0; o < total_local; o += chunk) {
-        const size_t n = std::min(chunk, total_local - o);
-        for (size_t i = 0; i < n * 4 * kN; i += 4) {
-            x ^= x << 13; x ^= x >> 7; x ^= x << 17;                    // xorshift64
-            h[i] = (uint16_t)((x & 0xffff) % p_db); h[i + 1] = (uint16_t)(((x >> 16) & 0xffff) % p_db);
-            h[i + 2] = (uint16_t)(((x >> 32) & 0xffff) % p_db); h[i + 3] = (uint16_t)((x >> 48) % p_db);
-        }
-        TRY(sb200_server_load_db_items(s, h.data(), o, n));
+        const size_t n = std::min(chunk, total_local - o), n4 = n * 4 * kN / 4;
+        count_launch(); launch_pdl(k_fill_random_u16, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 0, d.p, n4, (uint32_t)s->prm.p_db,
+                                   seed * 0x100000001b3ull + o * 0x632be59bd9b4e019ull + 0x1234567ull);
+        launch_db_build_spiral(s->db.p, d.p, (int)s->prm.nu1, (int)nu2_local, (uint32_t)s->prm.p_db, o, n, 0);
+        CHECK_LAUNCH();
+        CU(cudaDeviceSynchronize());
     }
+    s->have_db = true;
     return SB200_OK;
 }
 static void fold_rounds(sb200_server *s, uint64_t *cts, size_t count, size_t first_dim, cudaStream_t st) {
@@ -967,6 +999,23 @@ extern "C" int sb200_server_download(sb200_server *s, uint64_t *dst, const uint6
     if (!s) return fail(SB200_ERR_ARG, "null server");
     CU(cudaMemcpyAsync(dst, src, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ES(s, stream)));
     CU(cudaStreamSynchronize(ES(s, stream)));
+    if (s->world > 1 && s->xchg_connected) {       // a response produced after a timed-out exchange is garbage: never hand it out as SB200_OK
+        unsigned int st[2] = {0, 0};
+        CU(cudaMemcpy(st, s->xchg_state.p, sizeof st, cudaMemcpyDeviceToHost));
+        if (st[1]) return fail(SB200_ERR_STATE, "peer exchange timed out (error %u: %s); the shards are out of step - call sb200_server_xchg_reset on every rank",
+                               st[1], st[1] == 1 ? "no free slot on rank 0" : "a shard's ciphertext never arrived");
+    }
+    return SB200_OK;
+}
+// after a timed-out exchange: EVERY rank calls this with no query in flight; epochs, flags, acks and the error word start over
+extern "C" int sb200_server_xchg_reset(sb200_server *s) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->world < 2) return SB200_OK;
+    CU(cudaSetDevice(s->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(s->xchg.p, 0, xchg_ack_offset() + 128));
+    CU(cudaMemset(s->xchg_state.p, 0, 2 * sizeof(unsigned int)));
+    CU(cudaDeviceSynchronize());
     return SB200_OK;
 }
 extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream) {

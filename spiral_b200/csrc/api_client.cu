@@ -80,6 +80,8 @@ extern "C" int sb200_client_create(sb200_client **out, const sb200_params *prm, 
     if (!out || !prm || !seed32) return fail(SB200_ERR_ARG, "client_create: null argument");
     if (prm->t_gsw == 0 || prm->t_conv == 0 || prm->t_exp == 0 || prm->t_exp_right == 0) return fail(SB200_ERR_ARG, "client_create: zero gadget length");
     if (((size_t)1 << prm->nu1) + (size_t)prm->t_gsw * prm->nu2 > (size_t)kN) return fail(SB200_ERR_ARG, "client_create: 2^nu1 + t_GSW*nu2 exceeds the 2048 query slots");
+    if (sb200_arb_qprime(prm->qp_bits) == 0) return fail(SB200_ERR_ARG, "client_create: no response modulus for qp_bits = %u (14..36)", prm->qp_bits);
+    if (prm->p_db == 0 || prm->p_db > 65536) return fail(SB200_ERR_ARG, "client_create: p_db must be in [1, 65536]");
     int rc = sb200_init(device);
     if (rc) return rc;
     sb200_client *c = new sb200_client();
@@ -162,9 +164,27 @@ extern "C" int sb200_client_public_params(sb200_client *c, uint64_t *W_exp_left,
     }
     return SB200_OK;
 }
+// The wire seed fixes row 0 = -a of the query ciphertext.  Two queries of one client with the same `a` leak the difference of
+// their messages (row1 - row1' = e - e' + sigma - sigma'), so the seed must be fresh per query: it is derived from the client key
+// and the query counter - one ChaCha20 block, nonce {"SB2C", CC_QUERY | query_id, "wsee"} - and a monotonic query_id is the only
+// thing a caller has to keep.
+static const uint32_t kWireSeedStream = 0x65657377u;
+extern "C" int sb200_client_wire_seed(const sb200_client *c, uint32_t query_id, uint8_t *seed32_out) {
+    if (!c || !seed32_out) return fail(SB200_ERR_ARG, "client_wire_seed: null argument");
+    if (query_id >= (1u << 24)) return fail(SB200_ERR_ARG, "client_wire_seed: query_id must be below 2^24");
+    uint32_t x[16];
+    chacha20_block(x, c->key.w, 0u, kClientMagic, cc_obj(CC_QUERY, query_id), kWireSeedStream);
+    memcpy(seed32_out, x, 32);
+    return SB200_OK;
+}
 // query encoding (src/spiral.cpp:2098-2157) + encryptSimpleRegev, straight into the SEEDED wire form
 extern "C" int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out) {
-    if (!c || !wire_seed32 || !wire_out) return fail(SB200_ERR_ARG, "client_query_wire: null argument");
+    if (!c || !wire_out) return fail(SB200_ERR_ARG, "client_query_wire: null argument");
+    uint8_t derived[32];
+    if (!wire_seed32) {                      // the safe default: row-0 seed from (client key, query_id)
+        TRY(sb200_client_wire_seed(c, query_id, derived));
+        wire_seed32 = derived;
+    }
     const sb200_params &p = c->prm;
     const size_t fd = p.nu2, ell = p.t_gsw, dim0 = (size_t)1 << p.nu1;
     if (idx_target >= (dim0 << fd)) return fail(SB200_ERR_ARG, "client_query_wire: index %zu outside the 2^%zu records", idx_target, (size_t)(p.nu1 + fd));

@@ -101,18 +101,6 @@ extern "C" int sb200_pack(uint64_t *result, uint32_t out_n, uint32_t t_conv, con
 // fold rounds for bits >= log2(world) pair ciphertexts on the same GPU; one exchange of `planes` surviving 2x1
 // ciphertexts per GPU (32 KiB each) precedes the last log2(world) rounds, the packing and the modulus switch on rank 0.
 // ---------------------------------------------------------------------------------------------
-// synthetic plaintext coefficients, uniform in [0, p_db): counter-based (splitmix64), 4 values per thread
-__global__ void k_fill_random_u16(uint16_t *__restrict__ dst, size_t n4, uint32_t p_db, uint64_t seed) {
-    pdl_prologue();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    uint64_t x = seed + (i + 1) * 0x9e3779b97f4a7c15ull;
-    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull; x ^= x >> 31;
-    ushort4 o;
-    o.x = (uint16_t)((x & 0xffff) % p_db); o.y = (uint16_t)(((x >> 16) & 0xffff) % p_db);
-    o.z = (uint16_t)(((x >> 32) & 0xffff) % p_db); o.w = (uint16_t)((x >> 48) % p_db);
-    reinterpret_cast<ushort4 *>(dst)[i] = o;
-}
 // gathered [world][planes] ciphertexts (2 x 2048 u64 each) -> [planes][world]: the fold kernels want a plane's ciphertexts contiguous
 __global__ void k_transpose_cts(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, int world, int planes) {
     pdl_prologue();
@@ -160,6 +148,10 @@ static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *
     if (prm->out_n == 0 || prm->nu1 < 1) return fail(SB200_ERR_ARG, "pack_server_create: out_n >= 1 and nu1 >= 1 required");
     if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(SB200_ERR_ARG, "pack_server_create: world must be a power of two and 0 <= rank < world");
     if (((size_t)1 << prm->nu2) < (size_t)world) return fail(SB200_ERR_ARG, "pack_server_create: 2^nu2 < world");
+    if (prm->t_gsw == 0 || prm->t_conv == 0 || prm->t_exp == 0 || prm->t_exp_right == 0) return fail(SB200_ERR_ARG, "pack_server_create: zero gadget length");
+    if (sb200_arb_qprime(prm->qp_bits) == 0) return fail(SB200_ERR_ARG, "pack_server_create: no response modulus for qp_bits = %u (14..36)", prm->qp_bits);
+    if (prm->p_db == 0 || prm->p_db > 65536) return fail(SB200_ERR_ARG, "pack_server_create: p_db must be in [1, 65536]");
+    if (prm->nu1 > 11) return fail(SB200_ERR_ARG, "pack_server_create: nu1 > 11");
     int rc = sb200_init(device);
     if (rc) return rc;
     sb200_pack_server *s = new sb200_pack_server();
@@ -296,6 +288,8 @@ static int pack_up(sb200_pack_server *s, DBuf<uint32_t> &dst, size_t dst_off_pol
 extern "C" int sb200_pack_server_set_public_params(sb200_pack_server *s, const uint64_t *W_exp_left, const uint64_t *W_exp_right,
                                                    const uint64_t *V, const uint64_t *v_W) {
     if (!s || !v_W) return fail(SB200_ERR_ARG, "pack set_public_params: null argument");
+    if ((W_exp_left || W_exp_right || V) && s->dim0 + (size_t)s->prm.t_gsw * s->prm.nu2 > (size_t)kN)
+        return fail(SB200_ERR_ARG, "pack set_public_params: 2^nu1 + t_GSW*nu2 exceeds the 2048 slots of a packed query (direct upload only)");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = s->own_stream;
     if (W_exp_left) { TRY(pack_up(s, s->W_left, 0, W_exp_left, s->g * 2 * s->prm.t_exp, st)); CU(cudaStreamSynchronize(st)); }

@@ -105,27 +105,27 @@ __global__ void __launch_bounds__(kNttThreads) k_client_regev_cols(uint32_t *__r
 // grid (8, 4): blockIdx.y = r*2 + c, 256 output coefficients per CTA; the two 2048-term operands sit in shared memory.
 __global__ void __launch_bounds__(256) k_client_decode(uint64_t *__restrict__ pt, const uint64_t *__restrict__ resp, const uint64_t *__restrict__ Sp_raw,
                                                        uint64_t qp, uint64_t p_db) {
-    __shared__ uint32_t sa[kN], sb[kN];
+    // operands stay 64-bit and the 2048 products (each < qp^2 <= 2^74 for the 37-bit moduli of qprime_mods) are summed in
+    // 128 bits: exact for every q' the reference's table holds (oracle/client_sim.c does the same with __int128)
+    __shared__ uint64_t sa[kN], sb[kN];
     const int r = blockIdx.y >> 1, c = blockIdx.y & 1;
     for (int i = threadIdx.x; i < kN; i += 256) {
         const uint64_t raw = Sp_raw[(size_t)r * kN + i];                   // recentring of to_ntt_qprime (src/util.cpp:224-229)
         const int64_t a = raw >= kQ / 2 ? (int64_t)raw - (int64_t)kQ : (int64_t)raw;
         int64_t m = a % (int64_t)qp;
-        sa[i] = (uint32_t)(m < 0 ? m + (int64_t)qp : m);
-        sb[i] = (uint32_t)(resp[(size_t)c * kN + i] % qp);
+        sa[i] = (uint64_t)(m < 0 ? m + (int64_t)qp : m);
+        sb[i] = resp[(size_t)c * kN + i] % qp;
     }
     __syncthreads();
     const int k = blockIdx.x * 256 + threadIdx.x;
-    uint64_t pos = 0, neg = 0;
-    for (int i0 = 0; i0 < kN; i0 += 64) {
+    unsigned __int128 pos128 = 0, neg128 = 0;
 #pragma unroll 8
-        for (int i = i0; i < i0 + 64; i++) {
-            const int j = k - i;
-            const uint64_t prod = (uint64_t)sa[i] * sb[j & (kN - 1)];
-            if (j >= 0) pos += prod; else neg += prod;                      // x^N = -1
-        }
-        pos %= qp; neg %= qp;
+    for (int i = 0; i < kN; i++) {
+        const int j = k - i;
+        const unsigned __int128 prod = (unsigned __int128)sa[i] * sb[j & (kN - 1)];
+        if (j >= 0) pos128 += prod; else neg128 += prod;                    // x^N = -1
     }
+    const uint64_t pos = (uint64_t)(pos128 % qp), neg = (uint64_t)(neg128 % qp);
     const uint64_t sp = (pos + qp - neg) % qp;
     const uint64_t q1 = 4 * p_db, denom = qp * (q1 / p_db);
     const uint64_t rest = resp[(size_t)(kN2 + r * kN2 + c) * kN + k];
@@ -140,16 +140,16 @@ __global__ void __launch_bounds__(256) k_client_decode(uint64_t *__restrict__ pt
 
 void launch_client_gauss_raw(uint64_t *out, const ClientKey &key, uint32_t obj_base, uint32_t sub, int npolys, cudaStream_t s) {
     count_launch();
-    k_client_gauss_raw<<<dim3(kN / 256, npolys), 256, 0, s>>>(out, key, obj_base, sub);
+    note_kernel("k_client_gauss_raw"); k_client_gauss_raw<<<dim3(kN / 256, npolys), 256, 0, s>>>(out, key, obj_base, sub);
 }
 void launch_client_regev_cols(uint32_t *out, const RegevArgs &a, cudaStream_t s) {
     if (a.ncols <= 0) return;
     count_launch();
-    k_client_regev_cols<<<a.ncols, kNttThreads, 0, s>>>(out, a);
+    note_kernel("k_client_regev_cols"); k_client_regev_cols<<<a.ncols, kNttThreads, 0, s>>>(out, a);
 }
 void launch_client_decode(uint64_t *pt, const uint64_t *resp, const uint64_t *Sp_raw, uint64_t qp, uint64_t p_db, cudaStream_t s) {
     count_launch();
-    k_client_decode<<<dim3(kN / 256, kN0 * kN2), 256, 0, s>>>(pt, resp, Sp_raw, qp, p_db);
+    note_kernel("k_client_decode"); k_client_decode<<<dim3(kN / 256, kN0 * kN2), 256, 0, s>>>(pt, resp, Sp_raw, qp, p_db);
 }
 
 }  // namespace sb200

@@ -77,9 +77,22 @@ __device__ __forceinline__ uint64_t gadget_digit(uint64_t val, int k, uint32_t b
 // launch_dependents lets the NEXT kernel of the stream / graph be scheduled while this one is still running;
 // wait blocks until the PREVIOUS kernel has completed and its writes are visible, so nothing is consumed early.
 // The dozens of short dependent kernels of one query thereby overlap their launch + ramp-up latencies.
+struct TraceCtl { unsigned long long *buf; unsigned int *counter; unsigned int cap; };   // timeline trace (ntt_kernels.cu); buf == nullptr: off
+__constant__ TraceCtl c_trace;
+__device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void pdl_prologue() {
+    const bool tr = c_trace.buf != nullptr && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+    unsigned long long t0 = 0;
+    if (tr) t0 = global_timer_ns();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tr) {
+        const unsigned int i = atomicAdd(c_trace.counter, 1u);
+        if (i < c_trace.cap) {
+            c_trace.buf[3 * i] = t0; c_trace.buf[3 * i + 1] = global_timer_ns();
+            c_trace.buf[3 * i + 2] = (unsigned long long)gridDim.x | ((unsigned long long)gridDim.y << 24) | ((unsigned long long)blockDim.x << 48);
+        }
+    }
 }
 
 }  // namespace sb200

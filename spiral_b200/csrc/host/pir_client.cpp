@@ -1,6 +1,6 @@
 // pir_client.cpp - the client half of a client/server split, on the GPU through sb200_client_* (C-ABI only).
 //   pir_client keygen --params P --seed seed.bin --out pp.bin
-//   pir_client query  --params P --seed seed.bin --idx N --query-id K --wire-seed ws.bin --out query.bin
+//   pir_client query  --params P --seed seed.bin --idx N --query-id K [--wire-seed ws.bin] --out query.bin   (K: never reuse)
 //   pir_client decode --params P --seed seed.bin --in resp.bin --out item.bin
 // The 32-byte seed IS the client's state: keys are re-derived from it (the reference's keygen draws from an unseeded
 // std::random_device and keeps the key in globals, src/client.cpp:3-5,23-47).  item.bin holds the decoded plaintext matrix in the
@@ -29,10 +29,13 @@ int main(int argc, char **argv) {
         OK(sb200_client_public_params(c, m[0], m[1], m[2], m[3]));
         write_file(arg(argc, argv, "--out"), buf.data(), buf.size() * 8);
     } else if (cmd == "query") {
-        const std::vector<uint8_t> ws = read_file(arg(argc, argv, "--wire-seed"));
-        if (ws.size() != 32) die("--wire-seed wants a 32-byte file");
+        // --query-id is mandatory: it names the noise stream and (without --wire-seed) the row-0 seed; reusing one under the
+        // same client seed breaks the privacy of both queries.  --wire-seed (a 32-byte file) overrides the derived row-0 seed.
+        const uint32_t qid = (uint32_t)strtoul(arg(argc, argv, "--query-id"), nullptr, 10);
+        std::vector<uint8_t> ws;
+        if (*arg(argc, argv, "--wire-seed", "")) { ws = read_file(arg(argc, argv, "--wire-seed")); if (ws.size() != 32) die("--wire-seed wants a 32-byte file"); }
         std::vector<uint8_t> wire(sb200_wire_query_bytes(SB200_WIRE_QUERY_SEEDED));
-        OK(sb200_client_query_wire(c, strtoull(arg(argc, argv, "--idx"), nullptr, 10), (uint32_t)atoi(arg(argc, argv, "--query-id", "0")), ws.data(), wire.data()));
+        OK(sb200_client_query_wire(c, strtoull(arg(argc, argv, "--idx"), nullptr, 10), qid, ws.empty() ? nullptr : ws.data(), wire.data()));
         write_file(arg(argc, argv, "--out"), wire.data(), wire.size());
     } else if (cmd == "decode") {
         const std::vector<uint8_t> packed = read_file(arg(argc, argv, "--in"));

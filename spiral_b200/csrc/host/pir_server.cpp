@@ -32,9 +32,15 @@ int main(int argc, char **argv) {
     PubHeader h;
     if (pp.size() < sizeof(h)) die("--pp: not a public-parameter file");
     memcpy(&h, pp.data(), sizeof(h));
-    size_t total = 0;
-    for (int i = 0; i < 4; i++) total += h.polys[i];
-    if (h.magic != kPubMagic || pp.size() != sizeof(h) + total * 2 * SB200_POLY_LEN * 8) die("--pp: not a public-parameter file");
+    // the file comes from the client: its four counts must be exactly what THIS server (shapes derived from --params) will read
+    size_t expect[4], total = 0;
+    OK(sb200_server_public_param_polys(srv, expect));
+    if (h.magic != kPubMagic) die("--pp: not a public-parameter file");
+    for (int i = 0; i < 4; i++) {
+        if (h.polys[i] != expect[i]) die("--pp: public parameters were generated for other scheme parameters (matrix " + std::to_string(i) + ")");
+        total += expect[i];
+    }
+    if (pp.size() != sizeof(h) + total * 2 * SB200_POLY_LEN * 8) die("--pp: truncated or padded public-parameter file");
     const uint64_t *m[4], *p = reinterpret_cast<const uint64_t *>(pp.data() + sizeof(h));
     for (int i = 0; i < 4; i++) { m[i] = p; p += h.polys[i] * 2 * SB200_POLY_LEN; }
     OK(sb200_server_set_public_params(srv, m[0], m[1], m[2], m[3]));

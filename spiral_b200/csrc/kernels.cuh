@@ -14,8 +14,9 @@ namespace sb200 {
 void count_launch(int n = 1);        // our own kernel launches since load (sb200_launch_count)
 uint64_t launch_count();
 bool pdl_enabled();                    // SB200_NO_PDL=1 disables programmatic dependent launch
+void note_kernel(const char *name);    // distinct kernel names launched since the last reset (sb200_kernel_log)
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+inline void launch_pdl_impl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -24,6 +25,13 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+// every launch of the library goes through this macro: it records the kernel's name (a template instance is written in
+// parentheses at the call site so its commas survive the preprocessor)
+#define launch_pdl(kernel, ...) (::sb200::note_kernel(#kernel), ::sb200::launch_pdl_impl(kernel, __VA_ARGS__))
+size_t kernel_log(char *buf, size_t cap);
+void kernel_log_reset();
+int trace_enable(unsigned int capacity);                 // timeline trace of dependency-resolved times (profiling; 0 = off)
+size_t trace_read(unsigned long long *out, size_t max_records, int reset);
 int init_tables();   // builds twiddle tables on the current device (idempotent, per device)
 
 // ---- format conversion at the boundary (reference u64-per-residue NTT layout <-> dev-NTT)

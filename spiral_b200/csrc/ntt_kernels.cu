@@ -1,7 +1,10 @@
 // ntt_kernels.cu - twiddle tables + the batched MatPoly primitives built on the CTA-level NTT.
 #include "kernels.cuh"
 #include "ntt.cuh"
+#include <algorithm>
 #include <atomic>
+#include <cstring>
+#include <string>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -30,6 +33,58 @@ static uint2 h_shoup(uint64_t w, uint64_t q) {
 static std::atomic<uint64_t> g_launch_count{0};
 void count_launch(int n) { g_launch_count.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launch_count.load(); }
+
+// distinct kernel names launched since the last reset: call sites pass string literals, so a pointer table is enough
+static std::mutex g_names_mutex;
+static std::vector<const char *> g_names;
+void note_kernel(const char *name) {
+    static thread_local const char *last = nullptr;
+    if (name == last) return;
+    last = name;
+    std::lock_guard<std::mutex> lock(g_names_mutex);
+    for (const char *n : g_names) if (n == name) return;
+    g_names.push_back(name);
+}
+size_t kernel_log(char *buf, size_t cap) {       // comma-separated, sorted; returns the length needed
+    std::vector<std::string> v;
+    { std::lock_guard<std::mutex> lock(g_names_mutex); for (const char *n : g_names) v.emplace_back(n); }
+    for (auto &n : v) { while (!n.empty() && (n.front() == '(' || n.front() == ' ')) n.erase(n.begin()); while (!n.empty() && (n.back() == ')' || n.back() == ' ')) n.pop_back(); }
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    std::string out;
+    for (size_t i = 0; i < v.size(); i++) { if (i) out += ","; out += v[i]; }
+    if (buf && cap) { size_t n = std::min(cap - 1, out.size()); memcpy(buf, out.data(), n); buf[n] = 0; }
+    return out.size() + 1;
+}
+void kernel_log_reset() { std::lock_guard<std::mutex> lock(g_names_mutex); g_names.clear(); }
+
+// timeline trace (profiling): when enabled, CTA 0 of every kernel appends {time it was scheduled, time its dependencies were
+// resolved (griddepcontrol.wait returned), grid/block shape} - the dependency-resolved times of consecutive kernels give
+// the cost of each link of a launch chain INSIDE a replayed graph, which ncu (serialised, cold) cannot show
+static unsigned long long *g_trace_dev = nullptr;
+static unsigned int g_trace_cap = 0;
+int trace_enable(unsigned int capacity) {
+    TraceCtl ctl{};
+    if (g_trace_dev) { cudaFree(g_trace_dev); g_trace_dev = nullptr; g_trace_cap = 0; }
+    if (capacity) {
+        if (cudaMalloc(&g_trace_dev, (size_t)capacity * 3 * 8 + 8) != cudaSuccess) return -1;
+        cudaMemset(g_trace_dev, 0, (size_t)capacity * 3 * 8 + 8);
+        g_trace_cap = capacity;
+        ctl.buf = g_trace_dev + 1; ctl.counter = reinterpret_cast<unsigned int *>(g_trace_dev); ctl.cap = capacity;
+    }
+    cudaDeviceSynchronize();
+    return cudaMemcpyToSymbol(c_trace, &ctl, sizeof ctl) == cudaSuccess ? 0 : -1;
+}
+size_t trace_read(unsigned long long *out, size_t max_records, int reset) {
+    if (!g_trace_dev) return 0;
+    cudaDeviceSynchronize();
+    unsigned int n = 0;
+    cudaMemcpy(&n, g_trace_dev, 4, cudaMemcpyDeviceToHost);
+    size_t m = std::min<size_t>(std::min<size_t>(n, g_trace_cap), max_records);
+    if (out && m) cudaMemcpy(out, g_trace_dev + 1, m * 3 * 8, cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(g_trace_dev, 0, 8);
+    return m;
+}
 
 bool pdl_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("SB200_NO_PDL"); v = (e && *e == '1') ? 0 : 1; } return v == 1; }
 
@@ -349,11 +404,11 @@ __global__ void k_bitpack(uint64_t *__restrict__ out, const uint64_t *__restrict
 }
 void launch_bitpack(uint64_t *out, const uint64_t *in, size_t n, uint32_t bits, cudaStream_t s) {
     const size_t nwords = (n * bits + 63) / 64;
-    if (nwords) { count_launch(); launch_pdl(k_bitpack<0>, dim3((unsigned)((nwords + 127) / 128)), dim3(128), 0, s, out, in, n, bits, (uint64_t)0); }
+    if (nwords) { count_launch(); launch_pdl((k_bitpack<0>), dim3((unsigned)((nwords + 127) / 128)), dim3(128), 0, s, out, in, n, bits, (uint64_t)0); }
 }
 void launch_modswitch(uint64_t *out, const uint64_t *in_raw, size_t n, uint32_t bits, uint64_t qprime, cudaStream_t s) {
     const size_t nwords = (n * bits + 63) / 64;
-    if (nwords) { count_launch(); launch_pdl(k_bitpack<1>, dim3((unsigned)((nwords + 127) / 128)), dim3(128), 0, s, out, in_raw, n, bits, qprime); }
+    if (nwords) { count_launch(); launch_pdl((k_bitpack<1>), dim3((unsigned)((nwords + 127) / 128)), dim3(128), 0, s, out, in_raw, n, bits, qprime); }
 }
 
 }  // namespace sb200

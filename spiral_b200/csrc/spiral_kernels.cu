@@ -343,11 +343,12 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
     while ((size_t)ZT * JC * 64 > smem_cap && JC > kScanFoldEvery) JC >>= 1;
     const size_t smem = (size_t)ZT * JC * 64;
     dim3 grid(kN / ZT, IC / ICT);
+    if (JC < (int)dim0) note_kernel("k_scan_spiral[query slice staged in chunks]");     // visible in sb200_kernel_log
     count_launch();
-    if (U == 2 && ICT == 2 * T) launch_pdl(k_scan_spiral<2, 128, 4, true>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2 && T == 64) launch_pdl(k_scan_spiral<2, 64, 4, false>, grid, dim3(64), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2)            launch_pdl(k_scan_spiral<2, 128, 4, false>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else                        launch_pdl(k_scan_spiral<1, 128, 4, false>, grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    if (U == 2 && ICT == 2 * T) launch_pdl((k_scan_spiral<2, 128, 4, true>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2 && T == 64) launch_pdl((k_scan_spiral<2, 64, 4, false>), grid, dim3(64), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else if (U == 2)            launch_pdl((k_scan_spiral<2, 128, 4, false>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    else                        launch_pdl((k_scan_spiral<1, 128, 4, false>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
 }
 
 // ---- batched first dimension: BQ queries answered in ONE pass over the database ------------------------------
@@ -432,8 +433,8 @@ int launch_scan_spiral_batched(uint32_t *const *out, const uint64_t *const *quer
     }
     dim3 grid(kN, IC / 128);
     count_launch();
-    if (count == 2) launch_pdl(k_scan_spiral_batched<2>, grid, dim3(128), smem, s, a, db, (int)dim0, IC, JC);
-    else            launch_pdl(k_scan_spiral_batched<4>, grid, dim3(128), smem, s, a, db, (int)dim0, IC, JC);
+    if (count == 2) launch_pdl((k_scan_spiral_batched<2>), grid, dim3(128), smem, s, a, db, (int)dim0, IC, JC);
+    else            launch_pdl((k_scan_spiral_batched<4>), grid, dim3(128), smem, s, a, db, (int)dim0, IC, JC);
     return 0;
 }
 

@@ -365,7 +365,7 @@ void launch_db_to_tc_g(uint8_t *db_tc, const uint64_t *db, const TcGeom &g, size
     const size_t n = (size_t)kN * (g.K / tc::kKB) * 8 * g.IC, plane_bytes = (size_t)kN * 2 * g.IC * g.K * 4;
     for (size_t p = 0; p < g.planes; p++) {
         count_launch();
-        tc::k_db_to_tc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(db_tc + p * plane_bytes, reinterpret_cast<const uint4 *>(db + p * src_plane_words),
+        note_kernel("k_db_to_tc"); tc::k_db_to_tc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(db_tc + p * plane_bytes, reinterpret_cast<const uint4 *>(db + p * src_plane_words),
                                                                    (int)(g.K / 2), (int)g.IC);
     }
 }
@@ -400,7 +400,7 @@ static int launch_scan_tc_nb(uint32_t *t1, int count, const uint8_t *q_tc, const
     const int n_items = (int)items;
     const int grid = n_items < sms ? n_items : sms;
     count_launch();
-    launch_pdl(tc::k_scan_tc<NB, RQ>, dim3(grid), dim3(64 + 8 * NB), tc::Shape<NB>::kSmem, s, t1, count, q_tc, db_tc, KC, MT, n_items);
+    launch_pdl((tc::k_scan_tc<NB, RQ>), dim3(grid), dim3(64 + 8 * NB), tc::Shape<NB>::kSmem, s, t1, count, q_tc, db_tc, KC, MT, n_items);
     return 0;
 }
 

@@ -25,14 +25,15 @@ constexpr uint32_t kWireQueryMagic = 0x51324253u;      // "SB2Q"
 constexpr uint32_t kWireSeeded = 1, kWireFull = 2;
 constexpr size_t kWireHeaderBytes = 8, kWireSeedBytes = 32, kWireRowBytes = (size_t)kN * 56 / 8;
 
-__device__ __forceinline__ void chacha_qr(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
-    a += b; d ^= a; d = __funnelshift_l(d, d, 16);
-    c += d; b ^= c; b = __funnelshift_l(b, b, 12);
-    a += b; d ^= a; d = __funnelshift_l(d, d, 8);
-    c += d; b ^= c; b = __funnelshift_l(b, b, 7);
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }   // one SHF on the device
+__host__ __device__ __forceinline__ void chacha_qr(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+    a += b; d ^= a; d = rotl32(d, 16);
+    c += d; b ^= c; b = rotl32(b, 12);
+    a += b; d ^= a; d = rotl32(d, 8);
+    c += d; b ^= c; b = rotl32(b, 7);
 }
-// RFC 8439 section 2.3 block function
-__device__ __forceinline__ void chacha20_block(uint32_t (&x)[16], const uint32_t (&key)[8], uint32_t counter, uint32_t n0, uint32_t n1, uint32_t n2) {
+// RFC 8439 section 2.3 block function (also used on the host: the client derives per-query wire seeds with it)
+__host__ __device__ __forceinline__ void chacha20_block(uint32_t (&x)[16], const uint32_t (&key)[8], uint32_t counter, uint32_t n0, uint32_t n1, uint32_t n2) {
     uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
                       key[4], key[5], key[6], key[7], counter, n0, n1, n2};
 #pragma unroll
@@ -113,7 +114,7 @@ void launch_records_to_pts(uint16_t *out, const uint8_t *rec, size_t n_items, in
     const size_t n = n_items * polys * kN;
     if (!n) return;
     count_launch();
-    k_records_to_pts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, rec, n_items, polys, bits, out_item_stride, out_poly_stride);
+    note_kernel("k_records_to_pts"); k_records_to_pts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, rec, n_items, polys, bits, out_item_stride, out_poly_stride);
 }
 
 // integrity word of a database snapshot: sum of all 64-bit words modulo 2^64
@@ -126,7 +127,7 @@ __global__ void k_sum64(unsigned long long *__restrict__ acc, const uint64_t *__
 }
 void launch_sum64(unsigned long long *acc, const uint64_t *words, size_t n, cudaStream_t s) {
     count_launch();
-    k_sum64<<<148 * 8, 256, 0, s>>>(acc, words, n);
+    note_kernel("k_sum64"); k_sum64<<<148 * 8, 256, 0, s>>>(acc, words, n);
 }
 
 }  // namespace sb200

@@ -62,6 +62,10 @@ def load_library():
         "sb200_abi_version": (C.c_int, []),
         "sb200_arb_qprime": (C.c_uint64, [C.c_uint32]),
         "sb200_launch_count": (C.c_uint64, []),
+        "sb200_kernel_log": (sz, [C.c_char_p, sz]),
+        "sb200_kernel_log_reset": (None, []),
+        "sb200_trace_enable": (C.c_int, [C.c_uint32]),
+        "sb200_trace_read": (sz, [vp, sz, C.c_int]),
         "sb200_db_words": (sz, [C.c_uint32, C.c_uint32]),
         "sb200_fold_scratch_words": (sz, [sz, C.c_uint32]),
         # tier 1 (device pointers as integers)
@@ -176,6 +180,9 @@ def load_library():
         "sb200_server_xchg_connect_local": (C.c_int, [vp, C.POINTER(vp)]),
         "sb200_server_exchange_and_tail": (C.c_int, [vp, vp, vp]),
         "sb200_server_xchg_error": (C.c_int, [vp, vp]),
+        "sb200_server_xchg_reset": (C.c_int, [vp]),
+        "sb200_server_public_param_polys": (C.c_int, [vp, C.POINTER(sz)]),
+        "sb200_client_wire_seed": (C.c_int, [vp, C.c_uint32, vp]),
         "sb200_server_first_dim_cts": (vp, [vp]),
         "sb200_server_query_bytes": (sz, [vp]),
         "sb200_server_response_bytes": (sz, [vp]),
@@ -213,6 +220,15 @@ def load_library():
     lib._sb200_signatures = sig
     _lib = lib
     return lib
+
+
+def kernel_log(lib=None):
+    """Sorted list of the distinct kernel names launched since the last sb200_kernel_log_reset()."""
+    lib = lib or load_library()
+    n = lib.sb200_kernel_log(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.sb200_kernel_log(buf, n + 1)
+    return [k for k in buf.value.decode().split(",") if k]
 
 
 def check(rc, lib=None):

@@ -84,3 +84,61 @@ def test_client_rejects_impossible_shapes(sb):
     with pytest.raises(SB200Error, match="query slots"):
         SpiralClient(SpiralParams(11, 4, 8, 4, 8, 56, 20, 2, 256), SEED)      # 2048 + 32 slots do not fit one polynomial
     assert load_library() is sb
+
+
+def test_wire_seed_is_derived_per_query(sb, oracle):
+    """row 0 = -a must be fresh per query.  With no explicit seed the client derives it from (client key, query_id):
+    one ChaCha20 block, nonce {"SB2C", CC_QUERY | query_id, "wsee"} - checked against the oracle's RFC 8439 block function."""
+    import ctypes as C
+    prm = ol.make_params("cfg1", 4, 2)
+    c = SpiralClient(sb_params(prm), SEED)
+    seeds = [c.wire_seed(q) for q in (0, 1, 2, (1 << 24) - 1)]
+    assert len(set(seeds)) == 4 and c.wire_seed(1) == seeds[1]
+    for q, got in zip((0, 1, 2, (1 << 24) - 1), seeds):
+        out = (C.c_uint32 * 16)()
+        oracle.so_chacha20_block((C.c_uint32 * 8)(*np.frombuffer(SEED, dtype="<u4")), 0,
+                                 (C.c_uint32 * 3)(0x43324253, (6 << 24) | q, 0x65657377), out)
+        assert bytes(np.array(out[:8], dtype="<u4").tobytes()) == got
+    a, b = c.query_wire(5, 1), c.query_wire(5, 2)
+    assert np.array_equal(a, c.query_wire(5, 1, seeds[1])) and np.array_equal(a, c.query_wire(5, 1))
+    assert not np.array_equal(a[8:40], b[8:40]), "two queries share row 0"
+    other = SpiralClient(sb_params(prm), bytes([9] * 32))
+    assert other.wire_seed(1) != seeds[1]
+    with pytest.raises(SB200Error, match="query_id"):
+        c.wire_seed(1 << 24)
+    other.close()
+    c.close()
+
+
+# ADVICE r1: response moduli of 30+ bits (q_prime_bits 31 / 32 occur in the reference's parameter files; the table goes to 36):
+# 64 products of ~qp^2 no longer fit 64 bits, the decode sums in 128 bits like the oracle
+@pytest.mark.parametrize("qp_bits", [29, 31, 32, 36])
+def test_decode_with_wide_response_moduli(sb, oracle, qp_bits):
+    cfg = dict(ol.CONFIGS["cfg1"], qp_bits=qp_bits)
+    s = ol.SpiralSession(oracle, cfg, 3, 2, seed=4, chacha_seed=SEED)
+    c = SpiralClient(sb_params(s.prm), SEED)
+    Bbuf = s.reference_db()
+    for idx in (0, 9, s.total_n - 1):
+        resp, _, _ = s.oracle_answer(ol.wire_expand(oracle, s.chacha_query_wire(idx, idx, bytes([idx + 1] * 32))), Bbuf)
+        got = c.decode(resp)
+        assert np.array_equal(got, s.decode(resp)), f"qp_bits {qp_bits}: GPU decode differs from the oracle"
+        assert np.array_equal(got, s.pts[idx]), f"qp_bits {qp_bits}: record {idx} not recovered"
+    rng = np.random.default_rng(qp_bits)
+    qp = oracle.so_arb_qprime(qp_bits)
+    rnd = np.concatenate([rng.integers(0, qp, 2 * ol.N, dtype=np.uint64), rng.integers(0, 4 * s.prm.p_db, 4 * ol.N, dtype=np.uint64)])
+    assert np.array_equal(c.decode(rnd), s.decode(rnd))
+    c.close()
+    s.close()
+
+
+def test_servers_reject_parameters_they_cannot_serve(sb):
+    import ctypes as C
+    for bad in (SpiralParams(4, 2, 8, 4, 8, 56, 13, 2, 256), SpiralParams(4, 2, 8, 4, 8, 56, 40, 2, 256),
+                SpiralParams(4, 2, 8, 4, 8, 56, 20, 2, 0), SpiralParams(4, 2, 8, 4, 8, 56, 20, 2, 1 << 17), SpiralParams(11, 4, 8, 4, 8, 56, 20, 2, 256)):
+        h = C.c_void_p()
+        assert sb.sb200_server_create(C.byref(h), C.byref(bad), 0, 0, 1) == -3, "bad parameters accepted"
+    for bad in (SpiralParams(4, 2, 8, 4, 8, 56, 13, 2, 256), SpiralParams(4, 2, 8, 4, 8, 56, 20, 2, 0)):
+        h = C.c_void_p()
+        assert sb.sb200_pack_server_create(C.byref(h), C.byref(bad), 0) == -3
+    with pytest.raises(SB200Error, match="response modulus"):
+        SpiralClient(SpiralParams(4, 2, 8, 4, 8, 56, 13, 2, 256), SEED)

@@ -58,3 +58,78 @@ def test_reference_pack_harness_with_cuda_server(cfg, args, leaves):
     assert "PARITY FAIL" not in out.stderr
     assert "resident on the GPU" in out.stderr
     assert "CUDA kernel launches" in out.stderr
+
+
+def _mem_available():
+    try:
+        return int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+def _kernels(stderr):
+    line = [l for l in stderr.splitlines() if l.startswith("[spiral_b200] kernels:")]
+    assert line, "the driver did not report its kernel set"
+    return set(line[-1].split(":", 1)[1].strip().split(","))
+
+
+# The BASELINE.json sizes themselves (cfg1 = ./spiral 8 7, 2 GiB; cfg5 = ./spiral 9 8, 8 GiB): every mirrored leaf is compared with
+# the reference's own function on the harness's real encryptions, AND the resident server (sb200_server_answer - the call bench.py
+# times, with the kernels that are only dispatched at these shapes) answers the same query and must return the harness's total_resp.
+@pytest.mark.parametrize("cfg,args,need_gib,kernels", [
+    ("cfg1", ["8", "7", "1234"], 12,
+     ("k_scan_spiral<2, 128, 4, true>", "k_fold_mac_wide", "k_expand_accum_wide", "k_scal_to_mat_accum_tiled", "k_fold_mac", "k_fold_lift")),
+    ("cfg5", ["9", "8", "77777"], 40,
+     ("k_scan_spiral<2, 128, 4, true>", "k_scan_spiral[query slice staged in chunks]", "k_fold_mac_wide", "k_expand_accum_wide",
+      "k_scal_to_mat_accum_tiled")),
+])
+def test_full_size_reference_harness_and_resident_server(cfg, args, need_gib, kernels):
+    exe = _driver(cfg)
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt reference driver not present (built only where /root/reference exists)")
+    if _mem_available() < need_gib << 30:
+        pytest.skip(f"host has less than {need_gib} GiB available for the reference's own database copies")
+    env = dict(os.environ, SB200_PARITY="1")
+    out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=1500, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "Is correct?: 1" in out.stdout, out.stdout[-2000:]
+    assert "(parity mode)" in out.stderr
+    for leaf in ("reorientCiphertexts", "multiplyQueryByDatabase", "nttInvAndCrtLiftCiphertexts", "foldOneFurtherDimension",
+                 "expandImproved", "regevToGSW", "scalToMat", "modswitch", "getRescaled",
+                 "tier-3 resident server response row 0", "tier-3 resident server response rows 1-2"):
+        assert f"parity ok: {leaf}" in out.stderr, f"{leaf} was not exercised:\n{out.stderr[-3000:]}"
+    assert out.stderr.count("parity ok: foldOneFurtherDimension") == int(args[1])
+    assert "PARITY FAIL" not in out.stderr
+    got = _kernels(out.stderr)
+    print("kernel set:", sorted(got))
+    for k in kernels:
+        assert k in got, f"{k} was not dispatched at this shape; kernels: {sorted(got)}"
+
+
+# The largest host-feasible Pack shapes with the BASELINE.json parameter sets: cfg3's SpiralPack at 2^15 records of 32 KiB
+# (16 planes, 256-column scans, wide fold rounds) and cfg4's SpiralStreamPack at its full 2^14 x 100 KB size (25 planes, 8 columns).
+@pytest.mark.parametrize("cfg,args,need_gib,leaves,kernels", [
+    ("cfg3", ["10", "5", "31000", "a", "--high-rate"], 48,
+     ("convertDb", "coefficientExpansion", "reorientCiphertextsDim1", "regevToSimpleGsw", "fastMultiplyQueryByDatabaseDim1",
+      "foldCiphertextsDim1", "pack", "getRescaled"), ("k_scan_pack", "k_expand_accum_wide", "k_fold_mac_wide", "k_pack_accum")),
+    ("cfg4", ["11", "3", "9999", "a", "--high-rate", "--direct-upload"], 40,
+     ("convertDb", "fastMultiplyQueryByDatabaseDim1", "foldCiphertextsDim1", "pack", "getRescaled"), ("k_scan_pack", "k_pack_accum")),
+])
+def test_full_size_pack_harness_and_resident_server(cfg, args, need_gib, leaves, kernels):
+    exe = _driver(cfg)
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt reference driver not present (built only where /root/reference exists)")
+    if _mem_available() < need_gib << 30:
+        pytest.skip(f"host has less than {need_gib} GiB available for the reference's own database copies")
+    env = dict(os.environ, SB200_PARITY="1")
+    out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=2400, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "Is correct? : 1" in out.stdout, out.stdout[-2000:]
+    for leaf in leaves + ("tier-3 resident pack server, folded per-plane ciphertexts", "tier-3 resident server response row 0",
+                          "tier-3 resident server response rows 1.."):
+        assert f"parity ok: {leaf}" in out.stderr, f"{leaf} was not exercised:\n{out.stderr[-3000:]}"
+    assert "PARITY FAIL" not in out.stderr
+    got = _kernels(out.stderr)
+    print("kernel set:", sorted(got))
+    for k in kernels:
+        assert k in got, f"{k} was not dispatched at this shape; kernels: {sorted(got)}"
