@@ -59,7 +59,7 @@ int sb200_abi_version(void);
 uint64_t sb200_arb_qprime(uint32_t qp_bits);           /* include/values.h:74-76 */
 /* kernels launched by this process since load (our own launches only) */
 uint64_t sb200_launch_count(void);
-/* names of the distinct kernels launched since the last reset, comma-separated and sorted; returns the bytes needed
+/* names of the distinct kernels launched since the last reset, ';'-separated and sorted; returns the bytes needed
    (tests print the kernel set a shape dispatched to) */
 size_t sb200_kernel_log(char *buf, size_t cap);
 void sb200_kernel_log_reset(void);
@@ -233,6 +233,12 @@ typedef struct sb200_pack_server sb200_pack_server;
 int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device);
 /* shard `rank` of `world`: second-dimension indices ii = rank (mod world) of every plane */
 int sb200_pack_server_create_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world);
+/* plane sharding ("Pack alternative"; src/testing.cpp:1045-1061 runs the planes as independent trials): rank r holds
+ * the WHOLE planes p = r (mod world), scans and folds them alone; the one exchange is a folded 32 KiB ciphertext per plane to
+ * rank 0, which packs.  Plane arguments of the load entries stay GLOBAL indices; a plane of another rank is SB200_ERR_ARG. */
+int sb200_pack_server_create_plane_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world);
+int sb200_pack_server_owns_plane(const sb200_pack_server *srv, size_t plane);
+size_t sb200_pack_server_local_planes(const sb200_pack_server *srv);
 void sb200_pack_server_destroy(sb200_pack_server *srv);
 /* one of the out_n^2 database planes: this shard's 2^nu1 * (2^nu2 / world) items of one polynomial each (u16 coefficients
  * < p_db), j-major: item = j * local_num_per + ii_local */
@@ -267,7 +273,23 @@ int sb200_pack_server_copy_partial(sb200_pack_server *srv, uint64_t *dst_dev, vo
 /* rank 0: gathered = [world][plane] cts (device, rank order); last log2(world) folds + pack + modulus switch */
 int sb200_pack_server_fold_tail(sb200_pack_server *srv, const uint64_t *gathered_dev, uint64_t *total_resp_dev, void *stream);
 uint64_t *sb200_pack_server_result_cts(sb200_pack_server *srv);                   /* device ptr: folded per-plane cts after fold_tail */
+uint64_t *sb200_pack_server_response_ptr(sb200_pack_server *srv);                 /* device ptr: the server's own response buffer */
 int sb200_pack_server_download(sb200_pack_server *srv, uint64_t *dst_host, const uint64_t *src_dev, size_t words, void *stream);
+/* the exchange step over NVLink peer memory, as sb200_server_xchg_*: every rank stores its surviving ciphertexts into rank 0's
+ * HBM and raises a flag; rank 0 waits, runs the tail (last log2(world) folds under second-dimension sharding; nothing under
+ * plane sharding), packs and switches the modulus.  Handles carry the exchange buffer and the query buffer of a rank. */
+size_t sb200_pack_server_xchg_handle_bytes(void);
+int sb200_pack_server_xchg_export(sb200_pack_server *srv, void *handle_out);
+int sb200_pack_server_xchg_connect(sb200_pack_server *srv, const void *all_handles);                     /* one process per GPU (cudaIpc) */
+int sb200_pack_server_xchg_connect_local(sb200_pack_server *srv, sb200_pack_server *const *all_servers);  /* shards inside one process */
+int sb200_pack_server_exchange_and_tail(sb200_pack_server *srv, uint64_t *total_resp_dev, void *stream);
+int sb200_pack_server_xchg_error(sb200_pack_server *srv, void *stream);    /* 0 ok; 1/2/3 = a bounded spin timed out (4 s) */
+/* sharded direct upload: this rank's 1/world of the first-dimension ciphertexts (j in [rank, rank + 1) * 2^nu1 / world) + all GSW
+ * ciphertexts; the reorientation kernel stores the slice into EVERY rank's query buffer over peer memory (fused all-gather) */
+int sb200_pack_server_upload_direct_split(sb200_pack_server *srv, const uint64_t *v_firstdim_slice_host, const uint64_t *v_folding_host, void *stream);
+/* all server stages of the query last uploaded in ONE call (every rank of a sharded server calls it; response on rank 0, in
+ * total_resp_dev or the server's own buffer when NULL); marks as sb200_server_process */
+int sb200_pack_server_process(sb200_pack_server *srv, uint64_t *total_resp_dev, void *stream, void *const *marks);
 size_t sb200_pack_server_db_bytes(const sb200_pack_server *srv);                  /* this shard */
 size_t sb200_pack_server_response_words(const sb200_pack_server *srv);
 

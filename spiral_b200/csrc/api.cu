@@ -1013,7 +1013,7 @@ extern "C" int sb200_server_xchg_reset(sb200_server *s) {
     if (s->world < 2) return SB200_OK;
     CU(cudaSetDevice(s->device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemset(s->xchg.p, 0, xchg_ack_offset() + 128));
+    CU(cudaMemset(s->xchg.p, 0, xchg_header_bytes()));
     CU(cudaMemset(s->xchg_state.p, 0, 2 * sizeof(unsigned int)));
     CU(cudaDeviceSynchronize());
     return SB200_OK;

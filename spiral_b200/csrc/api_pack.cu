@@ -110,6 +110,15 @@ __global__ void k_transpose_cts(uint64_t *__restrict__ out, const uint64_t *__re
     for (int i = threadIdx.x; i < sb200::kN; i += blockDim.x) dst[i] = src[i];
 }
 
+// plane sharding: gathered [world][slot_words] holds rank r's planes (p = r, r + world, ...) in local order -> plane order
+__global__ void k_gather_planes(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, int world, size_t slot_words) {
+    pdl_prologue();
+    const int p = blockIdx.x, r = p % world, l = p / world;
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(in + (size_t)r * slot_words) + (size_t)l * sb200::kN;
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out) + (size_t)p * sb200::kN;
+    for (int i = threadIdx.x; i < sb200::kN; i += blockDim.x) dst[i] = src[i];
+}
+
 struct sb200_pack_server {
     sb200_params prm;
     int device = 0, rank = 0, world = 1, log_world = 0;
@@ -133,9 +142,33 @@ struct sb200_pack_server {
     DBuf<uint64_t> c0, conv_raw, query, cts, result_cts, tail_cts, packed_raw, resp;
     DBuf<int> lists, ct_idx_first, ct_idx_direct, ct_idx_bits, poly_idx_bits;
     DBuf<uint16_t> perms;
-    GraphSlot g_convert, g_convert_wire[2], g_fold, g_tail;
+    GraphSlot g_convert, g_convert_wire[2], g_fold, g_tail, g_xchg;
     cudaStream_t own_stream = nullptr;
-    ~sb200_pack_server() { if (own_stream) cudaStreamDestroy(own_stream); }
+    // sharding: 0 = second dimension strided (ii = rank mod world of EVERY plane; one exchange, then log2(world) tail folds);
+    // 1 = whole planes (plane p lives on rank p mod world: no exchange before the packing; src/testing.cpp:1045-1061 runs
+    // the out_n^2 planes as independent trials).  `planes` counts the LOCAL planes, `planes_total` = out_n^2.
+    int shard_planes = 0;
+    size_t planes_total = 0;
+    std::vector<int> plane_ids;                          // global plane index of each local plane
+    int query_mode = 0;                                  // 1 packed query, 2 direct upload, 3 direct upload split over the ranks
+    // peer-memory exchange (xchg_kernels.cu), as sb200_server's
+    DBuf<uint8_t> xchg;
+    DBuf<unsigned int> xchg_state;                       // [0] epoch, [1] error
+    DBuf<unsigned int *> xchg_acks;
+    DBuf<uint64_t> gathered;                             // rank 0: [world][slot_words]
+    size_t slot_words = 0;
+    void *xchg_target = nullptr;
+    std::vector<void *> ipc_opened;
+    bool xchg_connected = false;
+    QueryPeers qpeers{};                                 // every rank's query buffer + exchange header (split direct upload)
+    ~sb200_pack_server() {
+        if (own_stream) cudaStreamDestroy(own_stream);
+        for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
+    }
+    int local_plane(size_t global_plane) const {
+        for (size_t k = 0; k < plane_ids.size(); k++) if ((size_t)plane_ids[k] == global_plane) return (int)k;
+        return -1;
+    }
 };
 static inline cudaStream_t PS(sb200_pack_server *s, void *stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
 static inline const sb200_pack_server *pack_owner(const sb200_pack_server *s) { return s->db_owner ? s->db_owner : s; }
@@ -143,11 +176,14 @@ static inline const uint64_t *pack_db(const sb200_pack_server *s) { return pack_
 static inline bool pack_plane_loaded(const sb200_pack_server *s, size_t p) { return pack_owner(s)->plane_loaded[p]; }
 static inline TcGeom pack_geom(const sb200_pack_server *s) { return tc_geom_pack(s->dim0, s->local_num_per, s->planes, s->local_num_per * 2); }
 
-static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world, const sb200_pack_server *parent) {
+static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world, const sb200_pack_server *parent,
+                                   int shard_planes = 0) {
     if (!out || !prm) return fail(SB200_ERR_ARG, "pack_server_create: null argument");
     if (prm->out_n == 0 || prm->nu1 < 1) return fail(SB200_ERR_ARG, "pack_server_create: out_n >= 1 and nu1 >= 1 required");
     if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail(SB200_ERR_ARG, "pack_server_create: world must be a power of two and 0 <= rank < world");
-    if (((size_t)1 << prm->nu2) < (size_t)world) return fail(SB200_ERR_ARG, "pack_server_create: 2^nu2 < world");
+    if (!shard_planes && ((size_t)1 << prm->nu2) < (size_t)world) return fail(SB200_ERR_ARG, "pack_server_create: 2^nu2 < world");
+    if (shard_planes && (size_t)prm->out_n * prm->out_n < (size_t)world) return fail(SB200_ERR_ARG, "pack_server_create: fewer planes than ranks");
+    if (world > 16) return fail(SB200_ERR_ARG, "pack_server_create: world > 16 not supported by the peer exchange");
     if (prm->t_gsw == 0 || prm->t_conv == 0 || prm->t_exp == 0 || prm->t_exp_right == 0) return fail(SB200_ERR_ARG, "pack_server_create: zero gadget length");
     if (sb200_arb_qprime(prm->qp_bits) == 0) return fail(SB200_ERR_ARG, "pack_server_create: no response modulus for qp_bits = %u (14..36)", prm->qp_bits);
     if (prm->p_db == 0 || prm->p_db > 65536) return fail(SB200_ERR_ARG, "pack_server_create: p_db must be in [1, 65536]");
@@ -156,8 +192,18 @@ static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *
     if (rc) return rc;
     sb200_pack_server *s = new sb200_pack_server();
     s->prm = *prm; s->device = device; s->rank = rank; s->world = world; s->log_world = (int)ceil_log2((size_t)world);
-    s->dim0 = (size_t)1 << prm->nu1; s->num_per = (size_t)1 << prm->nu2; s->local_num_per = s->num_per / world;
-    s->planes = (size_t)prm->out_n * prm->out_n;
+    s->dim0 = (size_t)1 << prm->nu1; s->num_per = (size_t)1 << prm->nu2;
+    s->shard_planes = shard_planes && world > 1;
+    s->planes_total = (size_t)prm->out_n * prm->out_n;
+    if (s->shard_planes) {
+        s->local_num_per = s->num_per; s->log_world = 0;
+        for (size_t pl = (size_t)rank; pl < s->planes_total; pl += (size_t)world) s->plane_ids.push_back((int)pl);
+    } else {
+        s->local_num_per = s->num_per / world;
+        for (size_t pl = 0; pl < s->planes_total; pl++) s->plane_ids.push_back((int)pl);
+    }
+    s->planes = s->plane_ids.size();
+    s->slot_words = (s->shard_planes ? (s->planes_total + world - 1) / world : s->planes_total) * 2 * (size_t)kN;
     s->plane_words = s->dim0 * s->local_num_per * kN;
     s->plane_loaded.assign(s->planes, false);
     const size_t ell = prm->t_gsw, nbits = ell * prm->nu2;
@@ -178,13 +224,18 @@ static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *
     A(s->stage.alloc((size_t)1024 * PLW)); A(s->q_wire.alloc(kWireHeaderBytes + 2 * kWireRowBytes + 8));
     A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW)); A(s->ginv.alloc(expand_ginv_polys(s->plan, s->cnt.data()) * PLW));
     A(s->c0.alloc((size_t)s->maxcnt * kN));
-    const size_t conv_polys = std::max(2 * nbits, s->planes * 2);
+    const size_t conv_polys = std::max(2 * nbits, s->planes_total * 2);
     A(s->conv_raw.alloc(std::max(conv_polys, (size_t)1) * kN));
-    A(s->conv_ntt.alloc(std::max((size_t)2 * prm->t_conv * nbits, (prm->t_conv + 1) * s->planes) * PLW));
+    A(s->conv_ntt.alloc(std::max((size_t)2 * prm->t_conv * nbits, (prm->t_conv + 1) * s->planes_total) * PLW));
     A(s->gsw.alloc(std::max(prm->nu2, 1u) * 2 * 2 * ell * PLW));
     A(s->query.alloc(s->dim0 * 2 * kN)); A(s->scan_out.alloc(s->planes * s->local_num_per * 2 * PLW));
-    A(s->cts.alloc(s->planes * s->local_num_per * 2 * kN)); A(s->result_cts.alloc(s->planes * 2 * kN));
-    A(s->tail_cts.alloc(s->planes * (size_t)world * 2 * kN));
+    A(s->cts.alloc(s->planes * s->local_num_per * 2 * kN)); A(s->result_cts.alloc(s->planes_total * 2 * kN));
+    A(s->tail_cts.alloc(std::max(s->planes * (size_t)world, s->planes_total) * 2 * kN));
+    if (world > 1) {
+        A(s->xchg.alloc(xchg_buffer_bytes_w(world, s->slot_words))); A(s->xchg_state.alloc(2)); A(s->xchg_acks.alloc(world));
+        A(s->gathered.alloc((size_t)world * s->slot_words));
+        if (e == cudaSuccess) { A(cudaMemset(s->xchg.p, 0, xchg_buffer_bytes_w(world, s->slot_words))); A(cudaMemset(s->xchg_state.p, 0, 2 * sizeof(unsigned int))); }
+    }
     A(s->fold_scratch.alloc(fold_scratch_words_generic(std::max(s->planes * std::max(s->local_num_per, (size_t)world), (size_t)2), 2, 1, (int)ell)));
     A(s->packed.alloc(rows * prm->out_n * PLW)); A(s->packed_raw.alloc(rows * prm->out_n * kN)); A(s->resp.alloc(rows * prm->out_n * kN));
     A(s->lists.alloc(list.size())); A(s->ct_idx_first.alloc(s->dim0)); A(s->ct_idx_direct.alloc(s->dim0));
@@ -210,11 +261,19 @@ static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *
 extern "C" int sb200_pack_server_create_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world) {
     return pack_server_create_impl(out, prm, device, rank, world, nullptr);
 }
+// plane sharding ("Pack alternative"): rank r holds the WHOLE planes p = r (mod world) and runs their scans and all
+// nu2 fold rounds alone; the only exchange is one folded 32 KiB ciphertext per plane to rank 0, which packs.  The shape for
+// SpiralStreamPack (cfg4: 25 planes of 8 columns - splitting 8 columns over 8 GPUs starves the scan).
+extern "C" int sb200_pack_server_create_plane_sharded(sb200_pack_server **out, const sb200_params *prm, int device, int rank, int world) {
+    return pack_server_create_impl(out, prm, device, rank, world, nullptr, 1);
+}
+extern "C" int sb200_pack_server_owns_plane(const sb200_pack_server *s, size_t plane) { return s && s->local_plane(plane) >= 0; }
+extern "C" size_t sb200_pack_server_local_planes(const sb200_pack_server *s) { return s ? s->planes : 0; }
 // A second query context (own keys, scratch, stream) over the parent's resident planes: one per concurrent client.
 extern "C" int sb200_pack_server_create_view(sb200_pack_server **out, sb200_pack_server *parent) {
     if (!out || !parent) return fail(SB200_ERR_ARG, "pack create_view: null argument");
     const sb200_pack_server *owner = pack_owner(parent);
-    return pack_server_create_impl(out, &owner->prm, owner->device, owner->rank, owner->world, owner);
+    return pack_server_create_impl(out, &owner->prm, owner->device, owner->rank, owner->world, owner, owner->shard_planes);
 }
 extern "C" int sb200_pack_server_create(sb200_pack_server **out, const sb200_params *prm, int device) {
     return sb200_pack_server_create_sharded(out, prm, device, 0, 1);
@@ -223,8 +282,10 @@ extern "C" void sb200_pack_server_destroy(sb200_pack_server *s) { delete s; }
 
 // pts: this shard's items of the plane, j-major: item = j * local_num_per + ii_local (ii = rank + world * ii_local)
 extern "C" int sb200_pack_server_load_plane_items(sb200_pack_server *s, size_t plane, const uint16_t *pts) {
-    if (!s || !pts || plane >= s->planes) return fail(SB200_ERR_ARG, "load_plane_items: bad argument");
+    if (!s || !pts || plane >= s->planes_total) return fail(SB200_ERR_ARG, "load_plane_items: bad argument");
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
+    if (s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "load_plane_items: plane %zu lives on rank %zu (plane sharding)", plane, plane % s->world);
+    plane = (size_t)s->local_plane(plane);
     CU(cudaSetDevice(s->device));
     const size_t items = s->dim0 * s->local_num_per;
     DBuf<uint16_t> d(items * kN);
@@ -236,13 +297,15 @@ extern "C" int sb200_pack_server_load_plane_items(sb200_pack_server *s, size_t p
 }
 // db_buf: the WHOLE plane in the reference's convertDb layout db_buf[z][ii][j]; the shard's rows ii = rank (mod world) are taken
 extern "C" int sb200_pack_server_load_plane_reference(sb200_pack_server *s, size_t plane, const uint64_t *db_buf) {
-    if (!s || !db_buf || plane >= s->planes) return fail(SB200_ERR_ARG, "load_plane_reference: bad argument");
+    if (!s || !db_buf || plane >= s->planes_total) return fail(SB200_ERR_ARG, "load_plane_reference: bad argument");
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
+    if (s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "load_plane_reference: plane %zu lives on rank %zu (plane sharding)", plane, plane % s->world);
+    plane = (size_t)s->local_plane(plane);
     CU(cudaSetDevice(s->device));
     const size_t zc = 64, row = s->local_num_per * s->dim0;
     DBuf<uint64_t> stage(zc * row);
     for (size_t z0 = 0; z0 < (size_t)kN; z0 += zc) {
-        if (s->world == 1) {
+        if (s->world == 1 || s->shard_planes) {
             CU(stage.up(db_buf + z0 * row, zc * row));
         } else {
             for (size_t z = 0; z < zc; z++)
@@ -266,7 +329,7 @@ extern "C" int sb200_pack_server_load_random(sb200_pack_server *s, uint64_t seed
     CU(d.alloc(items * kN));
     for (size_t p = 0; p < s->planes; p++) {
         count_launch(); launch_pdl(k_fill_random_u16, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 0, d.p, n4, (uint32_t)s->prm.p_db,
-                                   seed * 0x100000001b3ull + p * 0x632be59bd9b4e019ull);
+                                   seed * 0x100000001b3ull + (uint64_t)s->plane_ids[p] * 0x632be59bd9b4e019ull);
         launch_db_build_pack(s->db.p + p * s->plane_words, d.p, s->dim0, s->local_num_per, (uint32_t)s->prm.p_db, 0); CHECK_LAUNCH();
         CU(cudaDeviceSynchronize());
         s->plane_loaded[p] = true;
@@ -305,7 +368,7 @@ extern "C" int sb200_pack_server_set_public_params(sb200_pack_server *s, const u
 extern "C" int sb200_pack_server_upload_query(sb200_pack_server *s, const uint64_t *query_cv_host, void *stream) {
     if (!s || !query_cv_host) return fail(SB200_ERR_ARG, "pack upload_query: null argument");
     CU(cudaMemcpyAsync(s->stage.p, query_cv_host, 2 * PLW * 8, cudaMemcpyHostToDevice, PS(s, stream)));
-    s->wire_kind = 0;
+    s->wire_kind = 0; s->query_mode = 1;
     return SB200_OK;
 }
 // coefficientExpansion + reorientCiphertextsDim1 + regevToSimpleGsw (src/testing.cpp:1015-1024)
@@ -333,19 +396,42 @@ extern "C" int sb200_pack_server_upload_direct(sb200_pack_server *s, const uint6
     launch_reorient_dim1(s->query.p, s->cv.p, s->ct_idx_direct.p, s->dim0, st);
     if (fd) { CU(cudaStreamSynchronize(st)); TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st)); }
     CHECK_LAUNCH();
+    s->query_mode = 2;
+    return SB200_OK;
+}
+// Sharded direct upload: every rank scans with the WHOLE first-dimension query, but uploads only ITS 1/world of it - the
+// ciphertexts j in [rank * 2^nu1 / world, (rank + 1) * 2^nu1 / world) - and the reorientation kernel stores that slice straight
+// into every rank's query buffer over NVLink peer memory (an all-gather fused into the kernel that produces the data; each
+// PCIe link carries 1/world of the 2^nu1 x 64 KiB).  v_firstdim_slice_host: this rank's ciphertexts only; v_folding_host: all
+// nu2 GSW ciphertexts (small).  Needs connected peers; the scan waits for all slices (k_query_wait).
+extern "C" int sb200_pack_server_upload_direct_split(sb200_pack_server *s, const uint64_t *v_firstdim_slice_host, const uint64_t *v_folding_host, void *stream) {
+    if (!s || !v_firstdim_slice_host) return fail(SB200_ERR_ARG, "pack upload_direct_split: null argument");
+    if (s->world < 2) return sb200_pack_server_upload_direct(s, v_firstdim_slice_host, v_folding_host, stream);
+    if (!s->xchg_connected) return fail(SB200_ERR_STATE, "pack upload_direct_split: peers not connected (sb200_pack_server_xchg_connect)");
+    if (s->dim0 % (2 * (size_t)s->world)) return fail(SB200_ERR_ARG, "pack upload_direct_split: 2^nu1 must be a multiple of 2 * world");
+    cudaStream_t st = PS(s, stream);
+    const size_t ell = s->prm.t_gsw, fd = s->prm.nu2, jc = s->dim0 / s->world;
+    if (fd && !v_folding_host) return fail(SB200_ERR_ARG, "pack upload_direct_split: GSW ciphertexts missing");
+    TRY(pack_up(s, s->cv, 0, v_firstdim_slice_host, jc * 2, st));
+    launch_reorient_dim1_allgather(s->qpeers, s->cv.p, s->dim0, (size_t)s->rank * jc, jc, s->rank, s->world, s->xchg_state.p, s->xchg.p, st);
+    if (fd) { CU(cudaStreamSynchronize(st)); TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st)); }
+    CHECK_LAUNCH();
+    s->query_mode = 3;
     return SB200_OK;
 }
 // fastMultiplyQueryByDatabaseDim1 for all out_n^2 planes of the shard in one launch (src/testing.cpp:1045-1052)
 extern "C" int sb200_pack_server_scan(sb200_pack_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     for (size_t p = 0; p < s->planes; p++) if (!pack_plane_loaded(s, p)) return fail(SB200_ERR_STATE, "pack scan: database plane %zu not loaded", p);
+    if (s->query_mode == 3) launch_query_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, PS(s, stream));
     launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s), s->dim0, s->local_num_per, s->planes, s->plane_words, s->local_num_per * 2, PS(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
 }
 // interposed fastMultiplyQueryByDatabaseDim1 on ONE resident plane: host reoriented query in, ref-NTT host ciphertexts out
 extern "C" int sb200_pack_server_scan_plane_host(sb200_pack_server *s, size_t plane, const uint64_t *v_firstdim_host, uint64_t *out_ref_ntt_host) {
-    if (!s || !v_firstdim_host || !out_ref_ntt_host || plane >= s->planes) return fail(SB200_ERR_ARG, "pack scan_plane_host: bad argument");
+    if (!s || !v_firstdim_host || !out_ref_ntt_host || s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "pack scan_plane_host: bad argument");
+    plane = (size_t)s->local_plane(plane);
     if (!pack_plane_loaded(s, plane)) return fail(SB200_ERR_STATE, "pack scan_plane_host: database plane %zu not loaded", plane);
     CU(cudaMemcpy(s->query.p, v_firstdim_host, s->dim0 * 2 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
     launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s) + plane * s->plane_words, s->dim0, s->local_num_per, 1, s->plane_words, s->local_num_per * 2, 0);
@@ -450,23 +536,125 @@ extern "C" int sb200_pack_server_copy_partial(sb200_pack_server *s, uint64_t *ds
 }
 // rank 0: gathered = [world][planes] surviving cts (device, rank order; world == 1: the server's own partial buffer).
 // Last log2(world) fold rounds, pack (:1066-1072), modulus switch (:1074-1081) -> total_resp_dev ((out_n+1) x out_n raw).
+// gathered: [world][slot_words] (rank order).  Second-dimension sharding: slot = planes_total ciphertexts, the last log2(world)
+// fold rounds run here; plane sharding: slot r = rank r's planes in local order, they are only put back into plane order.
+static void pack_tail_body(sb200_pack_server *s, const uint64_t *gathered_dev, uint64_t *total_resp_dev, cudaStream_t st) {
+    const size_t out_n = s->prm.out_n, rows = out_n + 1;
+    const uint64_t *final_cts = gathered_dev;
+    if (s->world > 1 && s->shard_planes) {
+        count_launch(); launch_pdl(k_gather_planes, dim3((unsigned)s->planes_total), dim3(256), 0, st, s->tail_cts.p, gathered_dev, s->world, s->slot_words);
+        cudaMemcpyAsync(s->result_cts.p, s->tail_cts.p, s->planes_total * 2 * kN * 8, cudaMemcpyDeviceToDevice, st);
+        final_cts = s->result_cts.p;
+    } else if (s->world > 1) {
+        count_launch(); launch_pdl(k_transpose_cts, dim3((unsigned)(s->world * s->planes)), dim3(256), 0, st, s->tail_cts.p, gathered_dev, s->world, (int)s->planes);
+        pack_fold_rounds(s, s->tail_cts.p, (size_t)s->world, (size_t)s->world, s->prm.nu2 - s->log_world, st);
+        cudaMemcpy2DAsync(s->result_cts.p, 2 * kN * 8, s->tail_cts.p, (size_t)s->world * 2 * kN * 8, 2 * kN * 8, s->planes, cudaMemcpyDeviceToDevice, st);
+        final_cts = s->result_cts.p;
+    }
+    launch_pack(s->packed.p, final_cts, s->vW.p, (int)out_n, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+    launch_from_ntt(s->packed_raw.p, s->packed.p, rows * out_n, st);
+    launch_rescale2(total_resp_dev, s->packed_raw.p, out_n * (size_t)kN, (rows - 1) * out_n * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), 4 * s->prm.p_db, st);
+}
 extern "C" int sb200_pack_server_fold_tail(sb200_pack_server *s, const uint64_t *gathered_dev, uint64_t *total_resp_dev, void *stream) {
     if (!s || !gathered_dev || !total_resp_dev) return fail(SB200_ERR_ARG, "pack fold_tail: null argument");
-    const size_t out_n = s->prm.out_n, rows = out_n + 1;
-    return run_stage(s->g_tail, PS(s, stream), gathered_dev, total_resp_dev, [&](cudaStream_t st) {
-        const uint64_t *final_cts = gathered_dev;
-        if (s->world > 1) {
-            count_launch(); launch_pdl(k_transpose_cts, dim3((unsigned)(s->world * s->planes)), dim3(256), 0, st, s->tail_cts.p, gathered_dev, s->world, (int)s->planes);
-            pack_fold_rounds(s, s->tail_cts.p, (size_t)s->world, (size_t)s->world, s->prm.nu2 - s->log_world, st);
-            cudaMemcpy2DAsync(s->result_cts.p, 2 * kN * 8, s->tail_cts.p, (size_t)s->world * 2 * kN * 8, 2 * kN * 8, s->planes, cudaMemcpyDeviceToDevice, st);
-            final_cts = s->result_cts.p;
+    return run_stage(s->g_tail, PS(s, stream), gathered_dev, total_resp_dev, [&](cudaStream_t st) { pack_tail_body(s, gathered_dev, total_resp_dev, st); });
+}
+// ---- peer-memory exchange for the Pack servers (same protocol and kernels as sb200_server_xchg_*, payload = this rank's surviving
+// ciphertexts: planes_total x 32 KiB under second-dimension sharding, its own planes under plane sharding)
+extern "C" size_t sb200_pack_server_xchg_handle_bytes(void) { return 2 * sizeof(cudaIpcMemHandle_t); }
+extern "C" int sb200_pack_server_xchg_export(sb200_pack_server *s, void *handle_out) {
+    if (!s || !handle_out || s->world < 2) return fail(SB200_ERR_ARG, "pack xchg_export: needs a sharded server");
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], s->xchg.p));
+    CU(cudaIpcGetMemHandle(&h[1], s->query.p));
+    memcpy(handle_out, h, sizeof h);
+    return SB200_OK;
+}
+static int pack_xchg_finish(sb200_pack_server *s, const std::vector<void *> &bufs, const std::vector<void *> &queries) {
+    s->xchg_target = bufs[0];
+    for (int r = 0; r < s->world; r++) { s->qpeers.query[r] = (uint64_t *)queries[r]; s->qpeers.xb[r] = (XchgBuf *)bufs[r]; }
+    if (s->rank == 0) {
+        std::vector<unsigned int *> acks(s->world);
+        for (int r = 0; r < s->world; r++) acks[r] = reinterpret_cast<unsigned int *>(reinterpret_cast<uint8_t *>(bufs[r]) + xchg_ack_offset());
+        CU(s->xchg_acks.up(acks.data(), s->world));
+    }
+    s->xchg_connected = true;
+    return SB200_OK;
+}
+extern "C" int sb200_pack_server_xchg_connect(sb200_pack_server *s, const void *all_handles) {
+    if (!s || !all_handles || s->world < 2) return fail(SB200_ERR_ARG, "pack xchg_connect: needs a sharded server");
+    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr);
+    for (int r = 0; r < s->world; r++) {
+        if (r == s->rank) { bufs[r] = s->xchg.p; queries[r] = s->query.p; continue; }
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, reinterpret_cast<const uint8_t *>(all_handles) + (size_t)r * sizeof h, sizeof h);
+        void *pb = nullptr, *pq = nullptr;
+        CU(cudaIpcOpenMemHandle(&pb, h[0], cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pb);
+        CU(cudaIpcOpenMemHandle(&pq, h[1], cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pq);
+        bufs[r] = pb; queries[r] = pq;
+    }
+    return pack_xchg_finish(s, bufs, queries);
+}
+extern "C" int sb200_pack_server_xchg_connect_local(sb200_pack_server *s, sb200_pack_server *const *all) {
+    if (!s || !all || s->world < 2) return fail(SB200_ERR_ARG, "pack xchg_connect_local: needs a sharded server");
+    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr);
+    for (int r = 0; r < s->world; r++) {
+        if (!all[r] || all[r]->world != s->world || all[r]->rank != r || all[r]->shard_planes != s->shard_planes) return fail(SB200_ERR_ARG, "pack xchg_connect_local: server %d mismatched", r);
+        bufs[r] = all[r]->xchg.p; queries[r] = all[r]->query.p;
+        if (all[r]->device != s->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, s->device, all[r]->device));
+            if (!can) return fail(SB200_ERR_CUDA, "pack xchg_connect_local: no peer access %d -> %d", s->device, all[r]->device);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(all[r]->device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CU(pe);
+            cudaGetLastError();
         }
-        launch_pack(s->packed.p, final_cts, s->vW.p, (int)out_n, (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
-        launch_from_ntt(s->packed_raw.p, s->packed.p, rows * out_n, st);
-        launch_rescale2(total_resp_dev, s->packed_raw.p, out_n * (size_t)kN, (rows - 1) * out_n * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), 4 * s->prm.p_db, st);
+    }
+    return pack_xchg_finish(s, bufs, queries);
+}
+// every rank: push the surviving ciphertexts into rank 0's HBM; rank 0 also waits for all ranks and runs the tail (the last fold
+// rounds under second-dimension sharding, then pack + modulus switch) into resp_dev (ignored on the other ranks)
+extern "C" int sb200_pack_server_exchange_and_tail(sb200_pack_server *s, uint64_t *resp_dev, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->world < 2) return sb200_pack_server_fold_tail(s, s->result_cts.p, resp_dev ? resp_dev : s->resp.p, stream);
+    if (!s->xchg_connected) return fail(SB200_ERR_STATE, "pack exchange_and_tail: peers not connected (sb200_pack_server_xchg_connect)");
+    if (s->rank == 0 && !resp_dev) resp_dev = s->resp.p;
+    return run_stage(s->g_xchg, PS(s, stream), resp_dev, nullptr, [&](cudaStream_t st) {
+        launch_xchg_push_w(s->xchg_target, s->xchg.p, s->result_cts.p, s->xchg_state.p, s->rank, s->world, s->xchg_state.p + 1,
+                           s->planes * 2 * (size_t)kN, s->slot_words, st);
+        if (s->rank == 0) {
+            launch_xchg_wait_w(s->xchg.p, s->xchg_acks.p, s->gathered.p, s->xchg_state.p, s->world, s->xchg_state.p + 1, s->slot_words, st);
+            pack_tail_body(s, s->gathered.p, resp_dev, st);
+        }
     });
 }
+extern "C" int sb200_pack_server_xchg_error(sb200_pack_server *s, void *stream) {
+    if (!s || s->world < 2) return 0;
+    unsigned int st[2] = {0, 0};
+    if (cudaStreamSynchronize(PS(s, stream)) != cudaSuccess) return -1;
+    if (cudaMemcpy(st, s->xchg_state.p, sizeof st, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)st[1];
+}
+// all server stages of the query last uploaded (sb200_pack_server_upload_query / _upload_direct / _upload_direct_split) in ONE
+// call, sharded servers included (every rank calls it; the response lands on rank 0).  marks: NULL or four cudaEvent_t recorded
+// before the expansion, before and after the first-dimension scan and at the end.
+extern "C" int sb200_pack_server_process(sb200_pack_server *s, uint64_t *total_resp_dev, void *stream, void *const *marks) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (!s->query_mode) return fail(SB200_ERR_STATE, "pack process: no query uploaded");
+    if (s->world > 1 && !s->xchg_connected) return fail(SB200_ERR_STATE, "pack process: sharded server without connected peers (sb200_pack_server_xchg_connect)");
+    cudaStream_t st = PS(s, stream);
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[0], st));
+    if (s->query_mode == 1) TRY(sb200_pack_server_expand_and_convert(s, stream));
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[1], st));
+    TRY(sb200_pack_server_scan(s, stream));
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[2], st));
+    TRY(sb200_pack_server_fold_local(s, stream));
+    TRY(sb200_pack_server_exchange_and_tail(s, total_resp_dev, stream));
+    if (marks) CU(cudaEventRecord((cudaEvent_t)marks[3], st));
+    return SB200_OK;
+}
 extern "C" uint64_t *sb200_pack_server_result_cts(sb200_pack_server *s) { return s ? s->result_cts.p : nullptr; }
+extern "C" uint64_t *sb200_pack_server_response_ptr(sb200_pack_server *s) { return s ? s->resp.p : nullptr; }
 extern "C" int sb200_pack_server_download(sb200_pack_server *s, uint64_t *dst_host, const uint64_t *src_dev, size_t words, void *stream) {
     if (!s || !dst_host || !src_dev) return fail(SB200_ERR_ARG, "pack download: null argument");
     CU(cudaMemcpyAsync(dst_host, src_dev, words * 8, cudaMemcpyDeviceToHost, PS(s, stream)));
@@ -480,7 +668,7 @@ static int pack_process(sb200_pack_server *s, uint64_t *resp_host, uint64_t *res
     TRY(sb200_pack_server_scan(s, stream));
     TRY(sb200_pack_server_fold_local(s, stream));
     TRY(sb200_pack_server_fold_tail(s, s->result_cts.p, s->resp.p, stream));
-    if (result_cts_host) CU(cudaMemcpyAsync(result_cts_host, s->result_cts.p, s->planes * 2 * kN * 8, cudaMemcpyDeviceToHost, PS(s, stream)));
+    if (result_cts_host) CU(cudaMemcpyAsync(result_cts_host, s->result_cts.p, s->planes_total * 2 * kN * 8, cudaMemcpyDeviceToHost, PS(s, stream)));
     return sb200_pack_server_download(s, resp_host, s->resp.p, rows * out_n * kN, stream);
 }
 // packed single-ciphertext query (SpiralPack): expansion + conversion + processing; 64 KiB in, (out_n+1) x out_n x 16 KiB out

@@ -175,6 +175,7 @@ int server_load_records(sb200_server *s, const ByteSource &src) {
 int pack_server_load_records(sb200_pack_server *s, const ByteSource &src) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
+    if (s->shard_planes) return fail(SB200_ERR_STATE, "plane-sharded pack servers load their planes with sb200_pack_server_load_plane_*");
     const uint32_t bits = coeff_bits(s->prm.p_db);
     if (!bits) return fail(SB200_ERR_ARG, "load_db_records: p_db must be a power of two <= 65536");
     CU(cudaSetDevice(s->device));
@@ -319,6 +320,7 @@ extern "C" size_t sb200_pack_server_record_stream_bytes(const sb200_pack_server 
     return s && coeff_bits(s->prm.p_db) ? s->dim0 * s->num_per * s->planes * (size_t)kN * coeff_bits(s->prm.p_db) / 8 : 0;
 }
 extern "C" int sb200_pack_server_load_db_records(sb200_pack_server *s, const uint8_t *records_host, size_t bytes) {
+    if (s && s->shard_planes) return fail(SB200_ERR_STATE, "plane-sharded pack servers load their planes with sb200_pack_server_load_plane_*");
     if (!records_host) return fail(SB200_ERR_ARG, "load_db_records: null argument");
     ByteSource src; src.mem = records_host; src.size = bytes;
     return pack_server_load_records(s, src);
@@ -329,6 +331,7 @@ extern "C" int sb200_pack_server_load_db_records_file(sb200_pack_server *s, cons
     return pack_server_load_records(s, src);
 }
 extern "C" int sb200_pack_server_save_db(sb200_pack_server *s, const char *path) {
+    if (s && s->shard_planes) return fail(SB200_ERR_STATE, "plane-sharded pack servers load their planes with sb200_pack_server_load_plane_*");
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner) return fail(SB200_ERR_STATE, "save_db: this pack server is a view");
     for (size_t p = 0; p < s->planes; p++) if (!s->plane_loaded[p]) return fail(SB200_ERR_STATE, "save_db: plane %zu not loaded", p);
@@ -336,6 +339,7 @@ extern "C" int sb200_pack_server_save_db(sb200_pack_server *s, const char *path)
     return snapshot_save(path, pack_snap_header(s), s->db.p, s->planes * s->plane_words);
 }
 extern "C" int sb200_pack_server_load_db_snapshot(sb200_pack_server *s, const char *path) {
+    if (s && s->shard_planes) return fail(SB200_ERR_STATE, "plane-sharded pack servers load their planes with sb200_pack_server_load_plane_*");
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
     CU(cudaSetDevice(s->device));

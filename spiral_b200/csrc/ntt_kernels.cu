@@ -45,14 +45,14 @@ void note_kernel(const char *name) {
     for (const char *n : g_names) if (n == name) return;
     g_names.push_back(name);
 }
-size_t kernel_log(char *buf, size_t cap) {       // comma-separated, sorted; returns the length needed
+size_t kernel_log(char *buf, size_t cap) {       // ';'-separated (template instances contain commas), sorted; returns the length needed
     std::vector<std::string> v;
     { std::lock_guard<std::mutex> lock(g_names_mutex); for (const char *n : g_names) v.emplace_back(n); }
     for (auto &n : v) { while (!n.empty() && (n.front() == '(' || n.front() == ' ')) n.erase(n.begin()); while (!n.empty() && (n.back() == ')' || n.back() == ' ')) n.pop_back(); }
     std::sort(v.begin(), v.end());
     v.erase(std::unique(v.begin(), v.end()), v.end());
     std::string out;
-    for (size_t i = 0; i < v.size(); i++) { if (i) out += ","; out += v[i]; }
+    for (size_t i = 0; i < v.size(); i++) { if (i) out += ";"; out += v[i]; }
     if (buf && cap) { size_t n = std::min(cap - 1, out.size()); memcpy(buf, out.data(), n); buf[n] = 0; }
     return out.size() + 1;
 }

@@ -95,58 +95,66 @@ void launch_reorient_dim1(uint64_t *out, const uint32_t *cv, const int *ct_idx, 
 // sums are combined through shared memory, so every lane still streams 16-byte pairs.
 // ============================================================================================
 constexpr int kPackScanThreads = 256;
+// PG planes per CTA: the staged query slice of one z serves PG planes (SpiralStreamPack: the 32 KiB slice is a quarter of the
+// 128 KiB of database one (plane, z) streams - re-staging it per plane cost 15 % of the scan)
 __global__ void __launch_bounds__(kPackScanThreads) k_scan_pack(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
                                                                 const uint64_t *__restrict__ db, int dim0, int IC, int ICT, int JC,
-                                                                size_t plane_words, size_t out_plane_polys) {
+                                                                size_t plane_words, size_t out_plane_polys, int planes, int PG) {
     pdl_prologue();
-    extern __shared__ __align__(16) uint4 qs[];        // [JC pairs][2] uint4, later reused for the reduction
+    extern __shared__ __align__(16) uint4 qs[];        // [JC pairs][2] uint4 (+ the reduction area behind it when the j axis is split)
     const int tid = threadIdx.x, JS = kPackScanThreads / ICT;
     const int i = tid % ICT, js = tid / ICT;
-    const int z = blockIdx.x, i0 = blockIdx.y * ICT, plane = blockIdx.z;
+    const int z = blockIdx.x, i0 = blockIdx.y * ICT, plane0 = blockIdx.z * PG;
     const int JP = dim0 / 2;
     const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
-    uint64_t acc[2][2] = {{0, 0}, {0, 0}};
-    const uint4 *dbz = reinterpret_cast<const uint4 *>(db + plane * plane_words) + ((size_t)z * JP) * IC + i0 + i;
     const uint4 *qg = reinterpret_cast<const uint4 *>(query) + (size_t)z * JP * 2;
-    int since_fold = 0;
-    for (int jc0 = 0; jc0 < JP; jc0 += JC) {
-        __syncthreads();
-        for (int e = tid; e < JC * 2; e += kPackScanThreads) qs[e] = __ldg(qg + (size_t)jc0 * 2 + e);
-        __syncthreads();
+    const bool whole = JC == JP;                       // the slice fits: staged once for all PG planes
+    uint4 *rs = qs + (size_t)JC * 2;                   // [js][i]
+    for (int pg = 0; pg < PG && plane0 + pg < planes; pg++) {
+        const int plane = plane0 + pg;
+        uint64_t acc[2][2] = {{0, 0}, {0, 0}};
+        const uint4 *dbz = reinterpret_cast<const uint4 *>(db + plane * plane_words) + ((size_t)z * JP) * IC + i0 + i;
+        int since_fold = 0;
+        for (int jc0 = 0; jc0 < JP; jc0 += JC) {
+            if (!whole || pg == 0) {
+                __syncthreads();
+                for (int e = tid; e < JC * 2; e += kPackScanThreads) qs[e] = __ldg(qg + (size_t)jc0 * 2 + e);
+                __syncthreads();
+            }
 #pragma unroll 8
-        for (int jj = js; jj < JC; jj += JS) {
-            const uint4 d = ld_stream_u4p(dbz + (size_t)(jc0 + jj) * IC);      // (j0.p, j0.b, j1.p, j1.b)
-            const uint4 q0 = qs[jj * 2], q1 = qs[jj * 2 + 1];                  // j0:(r0.p r0.b r1.p r1.b), j1
-            acc[0][0] += (uint64_t)q0.x * d.x;  acc[0][1] += (uint64_t)q0.y * d.y;
-            acc[1][0] += (uint64_t)q0.z * d.x;  acc[1][1] += (uint64_t)q0.w * d.y;
-            acc[0][0] += (uint64_t)q1.x * d.z;  acc[0][1] += (uint64_t)q1.y * d.w;
-            acc[1][0] += (uint64_t)q1.z * d.z;  acc[1][1] += (uint64_t)q1.w * d.w;
-            if (++since_fold == 60) {
-                since_fold = 0;
+            for (int jj = js; jj < JC; jj += JS) {
+                const uint4 d = ld_stream_u4p(dbz + (size_t)(jc0 + jj) * IC);      // (j0.p, j0.b, j1.p, j1.b)
+                const uint4 q0 = qs[jj * 2], q1 = qs[jj * 2 + 1];                  // j0:(r0.p r0.b r1.p r1.b), j1
+                acc[0][0] += (uint64_t)q0.x * d.x;  acc[0][1] += (uint64_t)q0.y * d.y;
+                acc[1][0] += (uint64_t)q0.z * d.x;  acc[1][1] += (uint64_t)q0.w * d.y;
+                acc[0][0] += (uint64_t)q1.x * d.z;  acc[0][1] += (uint64_t)q1.y * d.w;
+                acc[1][0] += (uint64_t)q1.z * d.z;  acc[1][1] += (uint64_t)q1.w * d.w;
+                if (++since_fold == 60) {
+                    since_fold = 0;
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    acc[r][0] = (acc[r][0] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[r][0] >> 32) * c32p;
-                    acc[r][1] = (acc[r][1] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[r][1] >> 32) * c32b;
+                    for (int r = 0; r < 2; r++) {
+                        acc[r][0] = (acc[r][0] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[r][0] >> 32) * c32p;
+                        acc[r][1] = (acc[r][1] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[r][1] >> 32) * c32b;
+                    }
                 }
             }
         }
-    }
-    uint32_t red[4] = {reduce_u64(acc[0][0], 0), reduce_u64(acc[0][1], 1), reduce_u64(acc[1][0], 0), reduce_u64(acc[1][1], 1)};
-    if (JS > 1) {
-        __syncthreads();
-        uint4 *rs = qs;                               // [js][i]
-        rs[js * ICT + i] = make_uint4(red[0], red[1], red[2], red[3]);
-        __syncthreads();
-        if (js == 0) {
-            uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int k = 0; k < JS; k++) { const uint4 v = rs[k * ICT + i]; s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w; }
-            red[0] = reduce_u64(s0, 0); red[1] = reduce_u64(s1, 1); red[2] = reduce_u64(s2, 0); red[3] = reduce_u64(s3, 1);
+        uint32_t red[4] = {reduce_u64(acc[0][0], 0), reduce_u64(acc[0][1], 1), reduce_u64(acc[1][0], 0), reduce_u64(acc[1][1], 1)};
+        if (JS > 1) {
+            rs[js * ICT + i] = make_uint4(red[0], red[1], red[2], red[3]);
+            __syncthreads();
+            if (js == 0) {
+                uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                for (int k = 0; k < JS; k++) { const uint4 v = rs[k * ICT + i]; s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w; }
+                red[0] = reduce_u64(s0, 0); red[1] = reduce_u64(s1, 1); red[2] = reduce_u64(s2, 0); red[3] = reduce_u64(s3, 1);
+            }
+            __syncthreads();                               // rs is rewritten by the next plane
         }
-    }
-    if (js == 0) {
-        uint32_t *o = out + ((size_t)plane * out_plane_polys + (size_t)(i0 + i) * 2) * 2 * kN + z;
-        o[0] = red[0]; o[kN] = red[1];                // row 0: planes p, b
-        o[2 * kN] = red[2]; o[3 * kN] = red[3];       // row 1
+        if (js == 0) {
+            uint32_t *o = out + ((size_t)plane * out_plane_polys + (size_t)(i0 + i) * 2) * 2 * kN + z;
+            o[0] = red[0]; o[kN] = red[1];                // row 0: planes p, b
+            o[2 * kN] = red[2]; o[3 * kN] = red[3];       // row 1
+        }
     }
 }
 void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, size_t planes,
@@ -156,11 +164,17 @@ void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, 
     const int JP = (int)dim0 / 2, JS = kPackScanThreads / ICT;
     int JC = JP;
     while ((size_t)JC * 32 > 32768) JC >>= 1;
-    size_t smem = (size_t)JC * 32;
-    const size_t red = (size_t)JS * ICT * 16;
-    if (red > smem) smem = red;
-    dim3 grid(kN, IC / ICT, (unsigned)planes);
-    count_launch(); launch_pdl(k_scan_pack, dim3(grid), dim3(kPackScanThreads), smem, s, out, query, db, (int)dim0, IC, ICT, JC, db_plane_words, out_plane_polys);
+    const size_t smem = (size_t)JC * 32 + (JS > 1 ? (size_t)JS * ICT * 16 : 0);
+    // planes per CTA: amortise the query staging where it is a visible share of the CTA's traffic (narrow planes), but keep
+    // at least ~4 waves of CTAs on the 148 SMs
+    int PG = 1;
+    if (JC == JP && IC <= 64) { PG = 5; while (PG > 1 && (size_t)kN * (IC / ICT) * ((planes + PG - 1) / PG) < 148 * 7 * 2) PG--; }
+    static const int pg_env = [] { const char *e = getenv("SB200_PACK_SCAN_PG"); return e ? atoi(e) : 0; }();
+    if (pg_env > 0 && JC == JP) PG = pg_env;
+    dim3 grid(kN, IC / ICT, (unsigned)((planes + PG - 1) / PG));
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_scan_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr_set = true; }
+    count_launch(); launch_pdl(k_scan_pack, dim3(grid), dim3(kPackScanThreads), smem, s, out, query, db, (int)dim0, IC, ICT, JC, db_plane_words, out_plane_polys, (int)planes, PG);
 }
 
 // ============================================================================================

@@ -23,12 +23,16 @@ constexpr size_t kCtWords = 6 * (size_t)kN;
 struct XchgBuf {                 // lives in ONE cudaMalloc allocation per rank (exported through cudaIpc)
     unsigned int flags[kXchgSlots][kXchgMaxWorld];
     unsigned int ack;            // last epoch rank 0 has consumed (written remotely by rank 0)
-    unsigned int pad[31];
-    // followed by slots[kXchgSlots][world][kCtWords] u64 (only rank 0's copy is used as the target)
+    unsigned int arrive[2];      // CTA arrival counters of this rank's multi-CTA push / wait kernels
+    unsigned int qflags[kXchgMaxWorld];   // query all-gather (Pack direct upload): epoch of the slice rank r has stored here
+    unsigned int pad[13];
+    // followed by slots[kXchgSlots][world][slot_words] u64 (only rank 0's copy is used as the target)
 };
-__host__ __device__ inline size_t xchg_bytes(int world) { return sizeof(XchgBuf) + (size_t)kXchgSlots * world * kCtWords * 8; }
-__device__ __forceinline__ uint64_t *xchg_slot(XchgBuf *b, int slot, int world, int r) {
-    return reinterpret_cast<uint64_t *>(b + 1) + ((size_t)slot * world + r) * kCtWords;
+static_assert(sizeof(XchgBuf) % 16 == 0, "slots must stay 16-byte aligned");
+__host__ __device__ inline size_t xchg_bytes_w(int world, size_t slot_words) { return sizeof(XchgBuf) + (size_t)kXchgSlots * world * slot_words * 8; }
+__host__ __device__ inline size_t xchg_bytes(int world) { return xchg_bytes_w(world, kCtWords); }
+__device__ __forceinline__ uint64_t *xchg_slot(XchgBuf *b, int slot, int world, int r, size_t slot_words) {
+    return reinterpret_cast<uint64_t *>(b + 1) + ((size_t)slot * world + r) * slot_words;
 }
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
     unsigned int v;
@@ -53,27 +57,39 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned int *p, unsigned in
     return true;
 }
 
-// one CTA of 1024 threads; `target` = rank 0's XchgBuf (peer mapping, or local on rank 0), `mine` = this rank's own XchgBuf
+// gridDim.x CTAs of 1024 threads; `target` = rank 0's XchgBuf (peer mapping, or local on rank 0), `mine` = this rank's own XchgBuf.
+// Every CTA stores its share of the `words`-word payload into slot [epoch % 2][rank]; the last CTA to finish publishes the flag.
 __global__ void __launch_bounds__(1024) k_xchg_push(XchgBuf *target, XchgBuf *mine, const uint64_t *ct, unsigned int *epoch,
-                                                    int rank, int world, unsigned int *error) {
+                                                    int rank, int world, unsigned int *error, size_t words, size_t slot_words) {
     pdl_prologue();
     __shared__ int ok;
     const unsigned int e = *epoch + 1;
     const int slot = e % kXchgSlots;
     if (threadIdx.x == 0) ok = (e <= (unsigned)kXchgSlots) ? 1 : spin_until_ge(&mine->ack, e - kXchgSlots);
     __syncthreads();
-    if (!ok) { if (threadIdx.x == 0) { *error = 1; *epoch = e; } return; }
-    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(ct);
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(xchg_slot(target, slot, world, rank));
-    for (int i = threadIdx.x; i < (int)(kCtWords / 2); i += blockDim.x) dst[i] = src[i];
-    __threadfence_system();
+    if (ok) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(ct);
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(xchg_slot(target, slot, world, rank, slot_words));
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words / 2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+        __threadfence_system();
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { st_release_sys(&target->flags[slot][rank], e); *epoch = e; }
+    if (threadIdx.x == 0) {
+        if (!ok) *error = 1;
+        __threadfence();
+        if (atomicAdd(&mine->arrive[0], 1u) == gridDim.x - 1) {          // every CTA's stores are fenced before its arrival
+            mine->arrive[0] = 0;
+            __threadfence_system();
+            if (ld_acquire_sys(error) == 0) st_release_sys(&target->flags[slot][rank], e);
+            *epoch = e;
+        }
+    }
 }
 
-// rank 0 only: `mine` = rank 0's XchgBuf, `acks[r]` = pointer to rank r's XchgBuf::ack (peer mappings), out = world x ct
+// rank 0 only: `mine` = rank 0's XchgBuf, `acks[r]` = pointer to rank r's XchgBuf::ack (peer mappings), out = world x slot_words.
+// gridDim.x CTAs: each waits for all flags, copies its share of the slots into the private buffer; the last one acknowledges.
 __global__ void __launch_bounds__(1024) k_xchg_wait(XchgBuf *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch,
-                                                    int world, unsigned int *error) {
+                                                    int world, unsigned int *error, size_t slot_words) {
     pdl_prologue();
     __shared__ int ok;
     const unsigned int e = *epoch;                 // already advanced by this rank's own push (same stream)
@@ -82,24 +98,103 @@ __global__ void __launch_bounds__(1024) k_xchg_wait(XchgBuf *mine, unsigned int 
     __syncthreads();
     if (threadIdx.x < world) { if (!spin_until_ge(&mine->flags[slot][threadIdx.x], e)) ok = 0; }
     __syncthreads();
-    if (!ok) { if (threadIdx.x == 0) *error = 2; return; }
-    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(xchg_slot(mine, slot, world, 0));
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out);
-    for (size_t i = threadIdx.x; i < (size_t)world * kCtWords / 2; i += blockDim.x) dst[i] = __ldcg(src + i);
-    __threadfence_system();
+    if (ok) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(xchg_slot(mine, slot, world, 0, slot_words));
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)world * slot_words / 2; i += (size_t)gridDim.x * blockDim.x) dst[i] = __ldcg(src + i);
+        __threadfence_system();
+    }
     __syncthreads();
-    if (threadIdx.x < world) st_release_sys(acks[threadIdx.x], e);
+    if (threadIdx.x == 0) {
+        if (!ok) *error = 2;
+        __threadfence();
+        if (atomicAdd(&mine->arrive[1], 1u) == gridDim.x - 1) {
+            mine->arrive[1] = 0;
+            __threadfence_system();
+            if (ld_acquire_sys(error) == 0) for (int r = 0; r < world; r++) st_release_sys(acks[r], e);
+        }
+    }
 }
 
-void launch_xchg_push(void *target, void *mine, const uint64_t *ct, unsigned int *epoch, int rank, int world, unsigned int *error, cudaStream_t s) {
+static inline unsigned xchg_grid(size_t words) { size_t g = (words * 8 + 131071) / 131072; return (unsigned)(g < 1 ? 1 : g > 32 ? 32 : g); }   // ~128 KiB per CTA
+void launch_xchg_push_w(void *target, void *mine, const uint64_t *ct, unsigned int *epoch, int rank, int world, unsigned int *error,
+                        size_t words, size_t slot_words, cudaStream_t s) {
     count_launch();
-    launch_pdl(k_xchg_push, dim3(1), dim3(1024), 0, s, (XchgBuf *)target, (XchgBuf *)mine, ct, epoch, rank, world, error);
+    launch_pdl(k_xchg_push, dim3(xchg_grid(words)), dim3(1024), 0, s, (XchgBuf *)target, (XchgBuf *)mine, ct, epoch, rank, world, error, words, slot_words);
+}
+void launch_xchg_wait_w(void *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch, int world, unsigned int *error,
+                        size_t slot_words, cudaStream_t s) {
+    count_launch();
+    launch_pdl(k_xchg_wait, dim3(xchg_grid((size_t)world * slot_words)), dim3(1024), 0, s, (XchgBuf *)mine, acks, out, epoch, world, error, slot_words);
+}
+void launch_xchg_push(void *target, void *mine, const uint64_t *ct, unsigned int *epoch, int rank, int world, unsigned int *error, cudaStream_t s) {
+    launch_xchg_push_w(target, mine, ct, epoch, rank, world, error, kCtWords, kCtWords, s);
 }
 void launch_xchg_wait(void *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch, int world, unsigned int *error, cudaStream_t s) {
-    count_launch();
-    launch_pdl(k_xchg_wait, dim3(1), dim3(1024), 0, s, (XchgBuf *)mine, acks, out, epoch, world, error);
+    launch_xchg_wait_w(mine, acks, out, epoch, world, error, kCtWords, s);
 }
 size_t xchg_buffer_bytes(int world) { return xchg_bytes(world); }
+size_t xchg_buffer_bytes_w(int world, size_t slot_words) { return xchg_bytes_w(world, slot_words); }
 size_t xchg_ack_offset() { return offsetof(XchgBuf, ack); }
+size_t xchg_header_bytes() { return sizeof(XchgBuf); }
+
+// ---- query all-gather over peer memory (Pack direct upload, sharded): every rank uploads and reorients only its 1/world
+// slice of the first-dimension ciphertexts and stores it into EVERY rank's query buffer, then raises qflags[rank] there;
+// k_query_wait (first kernel of the scan's stream order) waits until all world slices of this epoch have landed.
+struct QueryPeers { uint64_t *query[kXchgMaxWorld]; XchgBuf *xb[kXchgMaxWorld]; };
+__global__ void __launch_bounds__(256) k_reorient_dim1_allgather(const __grid_constant__ QueryPeers peers, const uint32_t *__restrict__ cv,
+                                                                 int dim0, int j_begin, int j_count, int rank, int world,
+                                                                 const unsigned int *epoch, XchgBuf *mine) {
+    pdl_prologue();
+    // this query is number e of the exchange sequence; its slices may only overwrite the peers' query buffers once rank 0 has
+    // gathered query e - 1 from EVERY rank (ack >= e - 1: all scans of the previous query are over)
+    __shared__ int ok;
+    const unsigned int qepoch = *epoch + 1;
+    if (threadIdx.x == 0) ok = qepoch <= 1 ? 1 : spin_until_ge(&mine->ack, qepoch - 1);
+    __syncthreads();
+    if (!ok) return;                                   // the missing flag makes every rank's k_query_wait report the time-out
+    // thread = (z, j-pair): 32 bytes of two consecutive j per store, to every peer
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (z, jl/2), j fastest: contiguous runs per z
+    const int half = j_count / 2;
+    if (idx < (size_t)kN * half) {
+        const int z = (int)(idx / half), jl = (int)(idx % half) * 2;
+        ulonglong2 w[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const uint32_t *ct = cv + (size_t)(jl + t) * 2 * 2 * kN;
+            w[t].x = (uint64_t)ct[z] | ((uint64_t)ct[kN + z] << 32);
+            w[t].y = (uint64_t)ct[2 * kN + z] | ((uint64_t)ct[3 * kN + z] << 32);
+        }
+        const size_t o = (size_t)z * dim0 + j_begin + jl;
+        for (int r = 0; r < world; r++) {
+            ulonglong2 *q = reinterpret_cast<ulonglong2 *>(peers.query[(rank + r) % world]);      // start with the own copy, spread the peers
+            q[o] = w[0]; q[o + 1] = w[1];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&mine->arrive[0], 1u) == gridDim.x - 1) {
+            mine->arrive[0] = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; r++) st_release_sys(&peers.xb[r]->qflags[rank], qepoch);
+        }
+    }
+}
+__global__ void k_query_wait(XchgBuf *mine, int world, const unsigned int *epoch, unsigned int *error) {
+    pdl_prologue();
+    if ((int)threadIdx.x < world && !spin_until_ge(&mine->qflags[threadIdx.x], *epoch + 1)) *error = 3;
+}
+void launch_reorient_dim1_allgather(const QueryPeers &peers, const uint32_t *cv, size_t dim0, size_t j_begin, size_t j_count, int rank, int world,
+                                    const unsigned int *qepoch, void *mine, cudaStream_t s) {
+    const size_t n = (size_t)kN * (j_count / 2);
+    count_launch();
+    launch_pdl(k_reorient_dim1_allgather, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, peers, cv, (int)dim0, (int)j_begin, (int)j_count, rank, world, qepoch, (XchgBuf *)mine);
+}
+void launch_query_wait(void *mine, int world, const unsigned int *qepoch, unsigned int *error, cudaStream_t s) {
+    count_launch();
+    launch_pdl(k_query_wait, dim3(1), dim3(32), 0, s, (XchgBuf *)mine, world, qepoch, error);
+}
 
 }  // namespace sb200

@@ -119,6 +119,17 @@ def load_library():
         "sb200_pack_server_create": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int]),
         "sb200_pack_server_create_sharded": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int, C.c_int, C.c_int]),
         "sb200_pack_server_destroy": (None, [vp]),
+        "sb200_pack_server_create_plane_sharded": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int, C.c_int, C.c_int]),
+        "sb200_pack_server_owns_plane": (C.c_int, [vp, sz]),
+        "sb200_pack_server_local_planes": (sz, [vp]),
+        "sb200_pack_server_xchg_handle_bytes": (sz, []),
+        "sb200_pack_server_xchg_export": (C.c_int, [vp, vp]),
+        "sb200_pack_server_xchg_connect": (C.c_int, [vp, vp]),
+        "sb200_pack_server_xchg_connect_local": (C.c_int, [vp, C.POINTER(vp)]),
+        "sb200_pack_server_exchange_and_tail": (C.c_int, [vp, vp, vp]),
+        "sb200_pack_server_xchg_error": (C.c_int, [vp, vp]),
+        "sb200_pack_server_upload_direct_split": (C.c_int, [vp, vp, vp, vp]),
+        "sb200_pack_server_process": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
         "sb200_pack_server_upload_query": (C.c_int, [vp, vp, vp]),
         "sb200_pack_server_expand_and_convert": (C.c_int, [vp, vp]),
         "sb200_pack_server_upload_direct": (C.c_int, [vp, vp, vp, vp]),
@@ -130,6 +141,7 @@ def load_library():
         "sb200_pack_server_copy_partial": (C.c_int, [vp, vp, vp]),
         "sb200_pack_server_fold_tail": (C.c_int, [vp, vp, vp, vp]),
         "sb200_pack_server_result_cts": (vp, [vp]),
+        "sb200_pack_server_response_ptr": (vp, [vp]),
         "sb200_pack_server_download": (C.c_int, [vp, vp, vp, sz, vp]),
         "sb200_pack_server_load_plane_items": (C.c_int, [vp, sz, u16p]),
         "sb200_pack_server_load_plane_reference": (C.c_int, [vp, sz, u64p]),
@@ -228,7 +240,7 @@ def kernel_log(lib=None):
     n = lib.sb200_kernel_log(None, 0)
     buf = C.create_string_buffer(n + 1)
     lib.sb200_kernel_log(buf, n + 1)
-    return [k for k in buf.value.decode().split(",") if k]
+    return [k for k in buf.value.decode().split(";") if k]
 
 
 def check(rc, lib=None):

@@ -211,15 +211,20 @@ class PackServer:
     out_n^2 database planes of 1x1 plaintexts, 2x1 Regev ciphertexts, one packed (out_n+1) x out_n response.
     Sharded like SpiralServer: rank g owns the second-dimension indices ii = g (mod world) of every plane."""
 
-    def __init__(self, params: SpiralParams, device=0, rank=0, world=1, _view_of=None):
+    def __init__(self, params: SpiralParams, device=0, rank=0, world=1, _view_of=None, shard="nu2"):
+        """shard: "nu2" = second dimension strided over the ranks (every plane on every rank); "planes" = whole planes
+        p = rank (mod world) per rank (no exchange before the packing)."""
         self.lib = load_library()
         self.params = params
         self.rank, self.world = rank, world
+        self.shard = shard if world > 1 else "nu2"
         self.dim0, self.num_per = 1 << params.nu1, 1 << params.nu2
-        self.local_num_per = self.num_per // world
+        self.local_num_per = self.num_per if self.shard == "planes" else self.num_per // world
         self.planes = params.out_n * params.out_n
         h = C.c_void_p()
-        if _view_of is None:
+        if _view_of is None and self.shard == "planes":
+            check(self.lib.sb200_pack_server_create_plane_sharded(C.byref(h), C.byref(params), device, rank, world), self.lib)
+        elif _view_of is None:
             check(self.lib.sb200_pack_server_create_sharded(C.byref(h), C.byref(params), device, rank, world), self.lib)
         else:
             check(self.lib.sb200_pack_server_create_view(C.byref(h), _view_of.h), self.lib)
@@ -228,7 +233,36 @@ class PackServer:
 
     def view(self):
         """A second client context (own keys, scratch) over this server's resident planes."""
-        return PackServer(self.params, rank=self.rank, world=self.world, _view_of=self)
+        return PackServer(self.params, rank=self.rank, world=self.world, _view_of=self, shard=self.shard)
+
+    def owns_plane(self, plane):
+        return bool(self.lib.sb200_pack_server_owns_plane(self.h, plane))
+
+    # ---- exchange over NVLink peer memory (sharded servers) ----------------------------------
+    def xchg_export(self):
+        buf = C.create_string_buffer(self.lib.sb200_pack_server_xchg_handle_bytes())
+        check(self.lib.sb200_pack_server_xchg_export(self.h, buf), self.lib)
+        return buf.raw
+
+    def xchg_connect(self, handles):
+        check(self.lib.sb200_pack_server_xchg_connect(self.h, b"".join(handles)), self.lib)
+
+    def xchg_connect_local(self, servers):
+        arr = (C.c_void_p * len(servers))(*[s.h for s in servers])
+        check(self.lib.sb200_pack_server_xchg_connect_local(self.h, arr), self.lib)
+
+    def exchange_and_tail(self, resp_ptr=None, stream=None):
+        check(self.lib.sb200_pack_server_exchange_and_tail(self.h, resp_ptr, stream), self.lib)
+
+    def xchg_error(self, stream=None):
+        return self.lib.sb200_pack_server_xchg_error(self.h, stream)
+
+    def upload_direct_split_ptr(self, firstdim_slice_ptr, folding_ptr, stream=None):
+        check(self.lib.sb200_pack_server_upload_direct_split(self.h, firstdim_slice_ptr, folding_ptr, stream), self.lib)
+
+    def process(self, resp_ptr=None, stream=None, marks=None):
+        """All server stages of the uploaded query in one call (sharded servers: every rank calls it)."""
+        check(self.lib.sb200_pack_server_process(self.h, resp_ptr, stream, marks), self.lib)
 
     def enable_tc(self, capacity=16):
         check(self.lib.sb200_pack_server_enable_tc(self.h, capacity), self.lib)

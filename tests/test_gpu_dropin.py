@@ -70,7 +70,7 @@ def _mem_available():
 def _kernels(stderr):
     line = [l for l in stderr.splitlines() if l.startswith("[spiral_b200] kernels:")]
     assert line, "the driver did not report its kernel set"
-    return set(line[-1].split(":", 1)[1].strip().split(","))
+    return set(line[-1].split(":", 1)[1].strip().split(";"))
 
 
 # The BASELINE.json sizes themselves (cfg1 = ./spiral 8 7, 2 GiB; cfg5 = ./spiral 9 8, 8 GiB): every mirrored leaf is compared with

@@ -171,3 +171,71 @@ def test_pack_device_random_database_is_deterministic_and_in_range(sb):
         srv.close()
     assert np.array_equal(outs[0], outs[1])
     assert not np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("cfg,nu1,nu2,mode,world,shard", [
+    ("cfg3", 4, 2, "expand", 2, "nu2"), ("cfg3", 3, 2, "expand", 4, "planes"), ("cfg4", 5, 3, "direct", 8, "planes"),
+    ("cfg4", 5, 3, "split", 4, "planes"), ("cfg4", 4, 3, "split", 2, "nu2"), ("cfg1", 4, 1, "expand", 2, "planes"), ("cfg4", 5, 2, "direct", 4, "nu2")])
+def test_pack_peer_exchange_and_one_call_process(sb, oracle, cfg, nu1, nu2, mode, world, shard):
+    """The exchange step inside the product (sb200_pack_server_exchange_and_tail, same peer-memory protocol as the Spiral server),
+    both shardings - second dimension (tail folds on rank 0) and whole planes (no fold after the exchange) -, the split direct
+    upload (each shard uploads 1/world of the first-dimension ciphertexts, the reorientation kernel all-gathers them through
+    peer stores) and the one-call form sb200_pack_server_process: world shards on ONE device == the oracle's whole pipeline."""
+    from spiral_b200.server import PackServer
+    prm = ol.make_params(cfg, nu1, nu2)
+    rng = np.random.default_rng(nu1 * 1000 + nu2 * 10 + world)
+    dim0, num_per, n = 1 << nu1, 1 << nu2, prm.out_n
+    planes, ell, fd = n * n, prm.t_gsw, nu2
+    pts, db = build_planes(oracle, prm, rng, dim0, num_per, planes)
+    g, stop = C.c_size_t(), C.c_size_t()
+    oracle.so_pack_expansion_shape(C.byref(prm), C.byref(g), C.byref(stop))
+    g, stop = g.value, stop.value
+    vW = rnd_ntt(rng, n * (n + 1) * prm.t_conv)
+    W_left, W_right, V = rnd_ntt(rng, g * 2 * prm.t_exp), rnd_ntt(rng, (stop + 1) * 2 * prm.t_exp_right), rnd_ntt(rng, 2 * 2 * prm.t_conv)
+    sp = SpiralParams(nu1, nu2, prm.t_gsw, prm.t_conv, prm.t_exp, prm.t_exp_right, prm.qp_bits, prm.out_n, prm.p_db)
+    shards = [PackServer(sp, rank=r, world=world, shard=shard) for r in range(world)]
+    items = dim0 * num_per
+    for srv in shards:
+        for pl in range(planes):
+            if not srv.owns_plane(pl):
+                with pytest.raises(Exception):
+                    srv.load_plane_reference(pl, np.ascontiguousarray(db[pl * items * N:(pl + 1) * items * N]))
+                continue
+            if (pl + srv.rank) % 2 == 0:
+                srv.load_plane_items(pl, (pts[pl] if shard == "planes" else srv.shard_items(pts[pl])).astype(np.uint16))
+            else:
+                srv.load_plane_reference(pl, np.ascontiguousarray(db[pl * items * N:(pl + 1) * items * N]))
+        srv.set_public_params(*((W_left, W_right, V, vW) if mode == "expand" else (None, None, None, vW)))
+    assert sum(int(sb.sb200_pack_server_local_planes(s.h)) for s in shards) == (planes if shard == "planes" else planes * world)
+    for srv in shards:
+        srv.xchg_connect_local(shards)
+    import torch
+    streams = [torch.cuda.Stream() for _ in shards]
+    jc = dim0 // world
+    for rep in range(3):                                        # later passes replay the captured graphs and reuse the exchange slots
+        query, v_first, v_fold = rnd_ntt(rng, 2), rnd_ntt(rng, dim0 * 2), rnd_ntt(rng, max(fd, 1) * 2 * 2 * ell)
+        want = np.zeros((n + 1) * n * N, dtype=np.uint64)
+        want_cts = np.zeros(planes * 2 * N, dtype=np.uint64)
+        assert oracle.so_pack_answer(C.byref(prm), int(mode == "expand"), p(query), p(W_left), p(W_right), p(V), p(v_first), p(v_fold),
+                                     p(vW), p(db), p(want), p(want_cts)) == 0
+        # all uploads first (the split upload stores into EVERY shard's query buffer), then the one-call form, rank 0 last:
+        # its wait kernel needs the other shards' pushes, and everything shares one device here
+        for srv, st in zip(shards, streams):
+            if mode == "expand":
+                srv.upload_query_ptr(query.ctypes.data, st.cuda_stream)
+            elif mode == "direct":
+                srv.upload_direct_ptr(v_first.ctypes.data, v_fold.ctypes.data, st.cuda_stream)
+            else:
+                sl = np.ascontiguousarray(v_first.reshape(dim0, -1)[srv.rank * jc:(srv.rank + 1) * jc].reshape(-1))
+                srv.upload_direct_split_ptr(sl.ctypes.data, v_fold.ctypes.data, st.cuda_stream)
+                st.synchronize()
+        for srv, st in list(zip(shards, streams))[::-1]:
+            srv.process(None, st.cuda_stream)
+        torch.cuda.synchronize()
+        assert all(s.xchg_error() == 0 for s in shards)
+        got = shards[0].download(sb.sb200_pack_server_response_ptr(shards[0].h), shards[0].response_words)
+        got_cts = shards[0].download(shards[0].result_cts_ptr(), planes * 2 * N)
+        assert np.array_equal(got_cts, want_cts), f"folded per-plane ciphertexts differ (pass {rep})"
+        assert np.array_equal(got, want), f"packed + modulus-switched response differs (pass {rep})"
+    for srv in shards:
+        srv.close()
