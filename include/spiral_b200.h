@@ -64,7 +64,8 @@ uint64_t sb200_launch_count(void);
 size_t sb200_kernel_log(char *buf, size_t cap);
 void sb200_kernel_log_reset(void);
 /* timeline trace (profiling): with capacity > 0 the first CTA of every kernel records {ns it was scheduled, ns its
-   dependencies were resolved, gridDim.x | gridDim.y << 24 | blockDim.x << 48}; read copies up to max_records x 3 words.
+   dependencies were resolved, gridDim.x | gridDim.y << 20 | blockDim.x << 36 | source line of the kernel's prologue << 48}; read
+   copies up to max_records x 3 words.
    Works inside replayed CUDA graphs, where ncu's serialised timings say nothing about a dependent chain.  0 = off. */
 int sb200_trace_enable(uint32_t capacity);
 size_t sb200_trace_read(uint64_t *out, size_t max_records, int reset);
@@ -216,7 +217,10 @@ int sb200_server_xchg_export(sb200_server *srv, void *handle_out);
 int sb200_server_xchg_connect(sb200_server *srv, const void *all_handles);                 /* one process per GPU (cudaIpc) */
 int sb200_server_xchg_connect_local(sb200_server *srv, sb200_server *const *all_servers);  /* shards inside one process */
 int sb200_server_exchange_and_tail(sb200_server *srv, uint64_t *total_resp_dev, void *stream);
-int sb200_server_xchg_error(sb200_server *srv, void *stream);      /* 0 ok; 1/2 = a bounded spin timed out (4 s) */
+int sb200_server_xchg_error(sb200_server *srv, void *stream);      /* 0 ok; 1/2/3 = a bounded spin timed out (4 s) */
+/* 1 when the last expansion was sharded: connected peers and 2^nu1 / world a multiple of 8 - each rank then expands and converts
+ * only the first-dimension ciphertexts j = rank (mod world) and stores them into every rank's query buffer over peer memory */
+int sb200_server_expansion_sharded(const sb200_server *srv);
 /* after a time-out the shards are out of step and every later exchange would time out too: with no query in flight EVERY rank
  * calls this (epochs, flags, acks, error word start over).  sb200_server_download on a sharded server returns SB200_ERR_STATE
  * instead of a garbage response while the error word is set. */

@@ -17,6 +17,28 @@ from spiral_b200.lib import load_library  # noqa: E402
 from spiral_b200.server import SpiralServer  # noqa: E402
 
 
+def kernel_lines():
+    """source line of every pdl_prologue() call -> the kernel(s) it sits in (lines can collide across the unity build's files)."""
+    import re
+    out = {}
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spiral_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cu", ".cuh")):
+            continue
+        cur = None
+        for n, text in enumerate(open(os.path.join(csrc, f)), 1):
+            m = re.search(r"\b(k_[a-z0-9_]+)\s*\(", text)
+            if m and "__global__" in text or (m and cur is None and "launch_pdl" not in text and "void" in text):
+                cur = m.group(1)
+            elif "__global__" in text:
+                cur = None                                  # name on the next line
+            elif cur is None and m and "launch" not in text:
+                cur = m.group(1)
+            if "pdl_prologue()" in text and "#define" not in text and cur:
+                out.setdefault(n, []).append(cur)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("workload", nargs="?", default="cfg1")
@@ -56,12 +78,14 @@ def main():
     rec = rec[np.argsort(rec[:, 1], kind="stable")]
     t0 = int(rec[0, 1])
     print(f"# {bench.workload_name(a.workload, nu1, nu2)}: one query, {per} kernels, {(int(rec[-1, 1]) - t0) / 1e3:.1f} us from the first to the last dependency-resolved time")
-    print("| # | grid | block | scheduled us | ready us | to next ready us | waited us |")
-    print("|---:|---|---:|---:|---:|---:|---:|")
+    names = kernel_lines()
+    print("| # | kernel | grid | block | scheduled us | ready us | to next ready us | waited us |")
+    print("|---:|---|---|---:|---:|---:|---:|---:|")
     for i, (ts, tr, shape) in enumerate(rec):
-        gx, gy, bx = int(shape) & 0xFFFFFF, (int(shape) >> 24) & 0xFFFFFF, int(shape) >> 48
+        shape = int(shape)
+        gx, gy, bx, line = shape & 0xFFFFF, (shape >> 20) & 0xFFFF, (shape >> 36) & 0xFFF, shape >> 48
         nxt = (int(rec[i + 1, 1]) - int(tr)) / 1e3 if i + 1 < len(rec) else 0.0
-        print(f"| {i} | ({gx},{gy}) | {bx} | {(int(ts) - t0) / 1e3:.1f} | {(int(tr) - t0) / 1e3:.1f} | {nxt:.1f} | {(int(tr) - int(ts)) / 1e3:.1f} |")
+        print(f"| {i} | {'/'.join(names.get(line, ['?']))} | ({gx},{gy}) | {bx} | {(int(ts) - t0) / 1e3:.1f} | {(int(tr) - t0) / 1e3:.1f} | {nxt:.1f} | {(int(tr) - int(ts)) / 1e3:.1f} |")
     srv.close()
 
 

@@ -405,7 +405,7 @@ extern "C" int sb200_expandImproved(uint64_t *cv, size_t g, uint32_t t_exp, cons
     std::vector<int> list(expand_active_total(plan)), offs(g), cnt(g);
     const int maxcnt = expand_build_lists(plan, list.data(), offs.data(), cnt.data());
     const int tmax = plan.t_left > plan.t_right ? plan.t_left : plan.t_right;
-    DBuf<uint32_t> dcv, dWl, dWr, neg1(g * PLW), c1((size_t)maxcnt * PLW), ginv((size_t)maxcnt * tmax * PLW);
+    DBuf<uint32_t> dcv, dWl, dWr, neg1(2 * g * PLW), c1((size_t)maxcnt * PLW), ginv((size_t)maxcnt * tmax * PLW);
     DBuf<uint64_t> c0((size_t)maxcnt * kN); DBuf<int> dlist(list.size());
     TRY(up_ntt(dcv, cv, ncts * 2)); TRY(up_ntt(dWl, W_left, g * 2 * t_exp)); TRY(up_ntt(dWr, W_right, n_right * 2 * t_exp_right));
     CU(dlist.up(list.data(), list.size()));
@@ -518,6 +518,17 @@ struct sb200_server {
     DBuf<uint64_t> c0_o;
     DBuf<uint16_t> perms;
     GraphSlot g_convert, g_convert_wire[2], g_lift_fold, g_tail;
+    // split chains as two independent graphs (even chain on the caller's stream, odd chain + RegevToGSW on aux_stream, joined
+    // only before the folds); [0] in-memory query, [1] / [2] wire kinds
+    GraphSlot g_even[3], g_odd[3];
+    DBuf<uint32_t> cv_o;                                // the odd chain's own ciphertext array
+    bool join_pending = false;                          // ev_join not yet waited for on the main stream
+    // sharded expansion (world > 1, peers connected): this rank expands and converts only the first-dimension ciphertexts
+    // j = rank (mod world) and stores them into every rank's query buffer (fused all-gather)
+    DBuf<int> lists_es, ct_idx_first_s, poly_idx_first_s;
+    std::vector<int> offs_es, cnt_es;
+    std::vector<void *> peer_query, peer_xb;            // every rank's query buffer / exchange header as seen from here
+    bool shard_eligible = false, query_sharded = false;
     // stream = NULL means "the legacy default stream", which cannot be captured: such calls run on this
     // BLOCKING stream instead (implicitly ordered with legacy-default-stream work, e.g. torch's default stream)
     cudaStream_t own_stream = nullptr, aux_stream = nullptr;
@@ -575,7 +586,7 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc(n_right * 2 * prm->t_exp_right * PLW));
-    A(s->W_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->V_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
+    A(s->W_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->V_conv.alloc(3 * 2 * prm->t_conv * PLW)); A(s->neg1.alloc(2 * s->g * PLW));
     A(s->q_stage.alloc(2 * PLW)); A(s->q_wire.alloc(kWireHeaderBytes + 2 * kWireRowBytes + 8)); A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW));
     A(s->ginv.alloc(expand_ginv_polys(s->plan, s->cnt.data()) * PLW)); A(s->c0.alloc((size_t)s->maxcnt * kN));
     A(s->conv_raw.alloc(conv_cols * kN)); A(s->conv_ntt.alloc(conv_cols * prm->t_conv * PLW));
@@ -603,7 +614,30 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
         A(s->lists_e.up(le.data(), le.size())); A(s->lists_o.up(lo.data(), lo.size()));
         A(s->c0_o.alloc((size_t)std::max(max_odd, 1) * kN)); A(s->c1_o.alloc((size_t)std::max(max_odd, 1) * PLW));
         A(s->ginv_o.alloc((size_t)std::max(max_odd, 1) * prm->t_exp_right * PLW));
+        A(s->cv_o.alloc(((size_t)2 << s->stopround) * 2 * PLW));
         s->split_chains = true;
+        // this rank's share of the even chain: output i = 2 j'' of round r is kept when j'' = rank modulo min(world, 2^r) - the
+        // ancestors of the first-dimension ciphertexts j = rank (mod world) and nothing else
+        if (world > 1 && (s->dim0 / world) % 8 == 0 && s->dim0 / world >= 8 && prm->t_conv == 4) {
+            std::vector<int> ls;
+            s->offs_es.resize(s->g); s->cnt_es.resize(s->g);
+            for (size_t r = 0; r < s->g; r++) {
+                s->offs_es[r] = (int)ls.size();
+                const size_t m = std::min((size_t)world, (size_t)1 << r);
+                for (int k = 0; k < s->cnt_e[r]; k++) {
+                    const int i = le[s->offs_e[r] + k];
+                    if (((size_t)(i / 2)) % m == (size_t)rank % m) ls.push_back(i);
+                }
+                s->cnt_es[r] = (int)ls.size() - s->offs_es[r];
+            }
+            const size_t cl = s->dim0 / world;
+            std::vector<int> cfs(cl), pfs(cl);
+            for (size_t jl = 0; jl < cl; jl++) { cfs[jl] = (int)(2 * ((size_t)rank + (size_t)world * jl)); pfs[jl] = 2 * cfs[jl]; }
+            A(s->lists_es.alloc(ls.size())); A(s->lists_es.up(ls.data(), ls.size()));
+            A(s->ct_idx_first_s.alloc(cl)); A(s->ct_idx_first_s.up(cfs.data(), cl));
+            A(s->poly_idx_first_s.alloc(cl)); A(s->poly_idx_first_s.up(pfs.data(), cl));
+            s->shard_eligible = true;
+        }
     }
     { std::vector<uint16_t> hperm(s->g * kN); build_automorph_perms(hperm.data(), (int)s->g);
       A(s->perms.alloc(hperm.size())); A(s->perms.up(hperm.data(), hperm.size())); }
@@ -726,36 +760,71 @@ extern "C" int sb200_server_upload_query(sb200_server *s, const uint64_t *query_
     s->wire_kind = 0;
     return SB200_OK;      // the narrowing into cv[0] is the first node of the expand_and_convert stage
 }
-extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
+// expansion + conversion.  defer_join: the odd chain (GSW bits -> RegevToGSW) is only needed by the folds, so the one-call paths
+// leave it running on the side stream across the scan and join in sb200_server_fold_local.
+static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_join) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!s->have_params) return fail(SB200_ERR_STATE, "expand_and_convert: public parameters not set");
+    cudaStream_t main_st = ES(s, stream);
+    if (s->split_chains) {
+        // The expansion tree splits at its root into two independent chains: the even ciphertexts (first dimension: t_left digits,
+        // all g rounds, then ScalToMat) and the odd ones (GSW bits: t_right = 56 digits per key switch, rounds 0..stopround, then
+        // RegevToGSW).  Each is its own graph on its own stream, each starts from the uploaded query (the odd chain works on a
+        // private ciphertext array); the scan waits for the even chain only.  The even chain's kernels carry the greatest launch
+        // priority, the odd chain's the least: where both have CTAs pending the critical chain is dispatched first.
+        const int wk = (int)s->wire_kind;
+        const bool shard = s->world > 1 && s->xchg_connected && s->shard_eligible;
+        static const bool skip_odd = [] { const char *e = getenv("SB200_PROFILE_SKIP_ODD_CHAIN"); return e && *e == '1'; }();   // timing experiments only: answers are wrong
+        CU(cudaEventRecord(s->ev_fork, main_st));
+        CU(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+        if (!skip_odd) TRY(run_stage(s->g_odd[wk], s->aux_stream, nullptr, nullptr, [&](cudaStream_t st) {
+            LaunchPriority low(false);
+            if (wk) launch_query_from_wire(s->cv_o.p, s->q_wire.p, s->wire_kind, st);
+            else launch_ntt_u64_to_dev(s->cv_o.p, s->q_stage.p, 2, st);
+            launch_expand(s->cv_o.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_o.p,
+                          s->offs_o.data(), s->cnt_o.data(), st, 0, (int)s->stopround + 1, 1, 1);
+            // no GSW negation on the resident path: the fold uses the CMux form (launch_fold_round_generic)
+            launch_regev_to_gsw(s->gsw.p, nullptr, s->cv_o.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
+                                s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, st);
+        }));
+        CU(cudaEventRecord(s->ev_join, s->aux_stream));
+        TRY(run_stage(s->g_even[wk], main_st, shard ? (const void *)s->xchg.p : nullptr, nullptr, [&](cudaStream_t st) {
+            LaunchPriority high(true);
+            if (wk) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);     // wire query -> cv[0]
+            else launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, st);                   // uploaded query (ref-NTT) -> cv[0]
+            if (!shard) {
+                launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists_e.p,
+                              s->offs_e.data(), s->cnt_e.data(), st, 0, (int)s->g, 0, 1);
+                launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
+                                              (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+                return;
+            }
+            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists_es.p,
+                          s->offs_es.data(), s->cnt_es.data(), st, 0, (int)s->g, 0, 1);
+            ScalTargets tg{};
+            tg.ntargets = s->world;
+            for (int t = 0; t < s->world; t++) {                       // own buffer first, then the peers in ring order
+                const int r = (s->rank + t) % s->world;
+                tg.query[t] = (uint64_t *)s->peer_query[r];
+                tg.flag[t] = xchg_qflag_ptr(s->peer_xb[r], s->rank);
+            }
+            tg.arrive = xchg_arrive_ptr(s->xchg.p, 0); tg.ack = xchg_ack_ptr(s->xchg.p);
+            tg.epoch = s->xchg_state.p; tg.error = s->xchg_state.p + 1;
+            launch_scal_to_mat_sharded(tg, s->cv.p, s->ct_idx_first_s.p, s->poly_idx_first_s.p, s->dim0, s->dim0 / s->world, s->rank, s->world,
+                                       s->W_conv.p, s->conv_raw.p, s->conv_ntt.p, st);
+        }));
+        s->query_sharded = shard;
+        if (defer_join) s->join_pending = true;
+        else CU(cudaStreamWaitEvent(main_st, s->ev_join, 0));
+        return SB200_OK;
+    }
+    s->query_sharded = false;
     GraphSlot &slot = s->wire_kind ? s->g_convert_wire[s->wire_kind - 1] : s->g_convert;
-    return run_stage(slot, ES(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
+    return run_stage(slot, main_st, nullptr, nullptr, [&](cudaStream_t st) {
         if (s->wire_kind) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);     // wire query -> cv[0]
         else launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, st);                             // uploaded query (ref-NTT) -> cv[0]
-        // The GSW bits live in the odd ciphertexts, which are final after round `stopround`; the remaining rounds
-        // only touch even ones.  Fork: RegevToGSW runs on a side stream while the last expansion rounds and
-        // ScalToMat continue on the main one (a fork/join pair inside the captured graph).
-        if (s->split_chains) {
-            // After round 0 the tree splits into two independent chains: the even ciphertexts (first dimension: t_left digits,
-            // all g rounds, then ScalToMat) and the odd ones (GSW bits: t_right = 56 digits per key switch, rounds 1..stopround,
-            // then RegevToGSW).  The heavy odd chain runs on the side stream and no longer sits on the path to the scan.
-            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
-                          s->offs.data(), s->cnt.data(), st, 0, 1);
-            cudaEventRecord(s->ev_fork, st);
-            cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0);
-            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_o.p,
-                          s->offs_o.data(), s->cnt_o.data(), s->aux_stream, 1, (int)s->stopround + 1, 1);
-            launch_regev_to_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
-                                s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, s->aux_stream);
-            cudaEventRecord(s->ev_join, s->aux_stream);
-            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists_e.p,
-                          s->offs_e.data(), s->cnt_e.data(), st, 1, (int)s->g, 0);
-            launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
-                                          (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
-            cudaStreamWaitEvent(st, s->ev_join, 0);
-            return;
-        }
+        // stopround == 0 (more GSW bits than first-dimension slots): one tree; RegevToGSW forks to the side stream after the last
+        // round that touches its ciphertexts (a fork/join pair inside the captured graph)
         const int fork_round = s->stopround > 0 ? (int)s->stopround + 1 : (int)s->g;
         launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists.p,
                       s->offs.data(), s->cnt.data(), st, 0, fork_round);
@@ -772,9 +841,17 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) {
         cudaStreamWaitEvent(st, s->ev_join, 0);
     });
 }
+extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) { return expand_and_convert_impl(s, stream, false); }
+extern "C" int sb200_server_expansion_sharded(const sb200_server *s) { return s && s->query_sharded; }
+static int join_odd_chain(sb200_server *s, cudaStream_t st) {
+    if (s->join_pending) { CU(cudaStreamWaitEvent(st, s->ev_join, 0)); s->join_pending = false; }
+    return SB200_OK;
+}
 extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan: database not loaded");
+    // sharded expansion: every rank's slice of the query must have landed in this rank's buffer
+    if (s->query_sharded) launch_query_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, ES(s, stream));
     launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, ES(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
@@ -905,12 +982,14 @@ static void fold_rounds(sb200_server *s, uint64_t *cts, size_t count, size_t fir
 }
 extern "C" int sb200_server_fold_local(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
+    TRY(join_odd_chain(s, ES(s, stream)));                      // the GSW ciphertexts come from the side stream
     return run_stage(s->g_lift_fold, ES(s, stream), nullptr, nullptr, [&](cudaStream_t st) { fold_rounds(s, s->cts.p, s->local_num_per, 0, st); });
 }
 extern "C" uint64_t *sb200_server_partial_ct(sb200_server *s) { return s ? s->cts.p : nullptr; }
 extern "C" uint64_t *sb200_server_first_dim_cts(sb200_server *s) { return s ? s->cts.p : nullptr; }
 extern "C" int sb200_server_fold_tail(sb200_server *s, uint64_t *gathered, uint64_t *resp_dev, void *stream) {
     if (!s || !gathered || !resp_dev) return fail(SB200_ERR_ARG, "fold_tail: null argument");
+    TRY(join_odd_chain(s, ES(s, stream)));
     return run_stage(s->g_tail, ES(s, stream), gathered, resp_dev, [&](cudaStream_t st) {
         fold_rounds(s, gathered, (size_t)s->world, s->prm.nu2 - s->log_world, st);
         // modulus switch (check_final, reference src/spiral.cpp:1441-1447): row 0 -> arb_qprime, rows 1.. -> 4*p_db
@@ -918,15 +997,18 @@ extern "C" int sb200_server_fold_tail(sb200_server *s, uint64_t *gathered, uint6
     });
 }
 // ---- peer-memory exchange: setup -----------------------------------------------------------------
-extern "C" size_t sb200_server_xchg_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+extern "C" size_t sb200_server_xchg_handle_bytes(void) { return 2 * sizeof(cudaIpcMemHandle_t); }
+// a rank's handle = its exchange buffer + its query buffer (the sharded expansion stores converted query slices into the peers')
 extern "C" int sb200_server_xchg_export(sb200_server *s, void *handle_out) {
     if (!s || !handle_out || s->world < 2) return fail(SB200_ERR_ARG, "xchg_export: needs a sharded server");
-    cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, s->xchg.p));
-    memcpy(handle_out, &h, sizeof h);
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], s->xchg.p));
+    CU(cudaIpcGetMemHandle(&h[1], s->query.p));
+    memcpy(handle_out, h, sizeof h);
     return SB200_OK;
 }
-static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs) {
+static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs, const std::vector<void *> &queries) {
+    s->peer_xb = bufs; s->peer_query = queries;
     s->xchg_target = bufs[0];
     if (s->rank == 0) {
         std::vector<unsigned int *> acks(s->world);
@@ -939,26 +1021,25 @@ static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs)
 // all_handles: world handles in rank order (each rank's sb200_server_xchg_export), one process per GPU
 extern "C" int sb200_server_xchg_connect(sb200_server *s, const void *all_handles) {
     if (!s || !all_handles || s->world < 2) return fail(SB200_ERR_ARG, "xchg_connect: needs a sharded server");
-    std::vector<void *> bufs(s->world, nullptr);
+    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr);
     for (int r = 0; r < s->world; r++) {
-        if (r == s->rank) { bufs[r] = s->xchg.p; continue; }
-        if (s->rank != 0 && r != 0) continue;                     // non-root ranks only need rank 0's buffer
-        cudaIpcMemHandle_t h;
-        memcpy(&h, reinterpret_cast<const uint8_t *>(all_handles) + (size_t)r * sizeof h, sizeof h);
-        void *p = nullptr;
-        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        s->ipc_opened.push_back(p);
-        bufs[r] = p;
+        if (r == s->rank) { bufs[r] = s->xchg.p; queries[r] = s->query.p; continue; }
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, reinterpret_cast<const uint8_t *>(all_handles) + (size_t)r * sizeof h, sizeof h);
+        void *pb = nullptr, *pq = nullptr;
+        CU(cudaIpcOpenMemHandle(&pb, h[0], cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pb);
+        CU(cudaIpcOpenMemHandle(&pq, h[1], cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pq);
+        bufs[r] = pb; queries[r] = pq;
     }
-    return xchg_finish_connect(s, bufs);
+    return xchg_finish_connect(s, bufs, queries);
 }
 // same-process variant (several shards driven from one process, e.g. tests on one device): direct pointers
 extern "C" int sb200_server_xchg_connect_local(sb200_server *s, sb200_server *const *all_servers) {
     if (!s || !all_servers || s->world < 2) return fail(SB200_ERR_ARG, "xchg_connect_local: needs a sharded server");
-    std::vector<void *> bufs(s->world, nullptr);
+    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr);
     for (int r = 0; r < s->world; r++) {
         if (!all_servers[r] || all_servers[r]->world != s->world || all_servers[r]->rank != r) return fail(SB200_ERR_ARG, "xchg_connect_local: server %d mismatched", r);
-        bufs[r] = all_servers[r]->xchg.p;
+        bufs[r] = all_servers[r]->xchg.p; queries[r] = all_servers[r]->query.p;
         if (all_servers[r]->device != s->device) {
             int can = 0;
             CU(cudaDeviceCanAccessPeer(&can, s->device, all_servers[r]->device));
@@ -968,7 +1049,7 @@ extern "C" int sb200_server_xchg_connect_local(sb200_server *s, sb200_server *co
             cudaGetLastError();
         }
     }
-    return xchg_finish_connect(s, bufs);
+    return xchg_finish_connect(s, bufs, queries);
 }
 // every rank: push the surviving ciphertext into rank 0's HBM; rank 0 additionally waits for all shards, runs the
 // tail folds and the modulus switch into resp_dev (ignored on other ranks)
@@ -977,6 +1058,7 @@ extern "C" int sb200_server_exchange_and_tail(sb200_server *s, uint64_t *resp_de
     if (s->world < 2) return sb200_server_fold_tail(s, s->cts.p, resp_dev, stream);
     if (!s->xchg_connected) return fail(SB200_ERR_STATE, "exchange_and_tail: peers not connected (sb200_server_xchg_connect)");
     if (s->rank == 0 && !resp_dev) return fail(SB200_ERR_ARG, "exchange_and_tail: rank 0 needs a response buffer");
+    TRY(join_odd_chain(s, ES(s, stream)));
     return run_stage(s->g_xchg, ES(s, stream), resp_dev, nullptr, [&](cudaStream_t st) {
         launch_xchg_push(s->xchg_target, s->xchg.p, s->cts.p, s->xchg_state.p, s->rank, s->world, s->xchg_state.p + 1, st);
         if (s->rank == 0) {
@@ -1022,7 +1104,7 @@ extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_hos
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer: single-shard call on a sharded server (use the staged API)");
     TRY(sb200_server_upload_query(s, query_cv_host, stream));
-    TRY(sb200_server_expand_and_convert(s, stream));
+    TRY(expand_and_convert_impl(s, stream, true));
     TRY(sb200_server_first_dim(s, stream));
     TRY(sb200_server_fold_local(s, stream));
     TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
@@ -1037,7 +1119,7 @@ extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, v
     cudaStream_t st = ES(s, stream);
     uint64_t *resp = total_resp_dev ? total_resp_dev : s->resp.p;
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[0], st));
-    TRY(sb200_server_expand_and_convert(s, stream));
+    TRY(expand_and_convert_impl(s, stream, true));
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[1], st));
     TRY(sb200_server_scan(s, stream));
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[2], st));
@@ -1053,7 +1135,7 @@ extern "C" int sb200_server_answer_packed(sb200_server *s, const uint64_t *query
     if (!s || !packed_resp_host) return fail(SB200_ERR_ARG, "server_answer_packed: null argument");
     if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer_packed: single-shard call on a sharded server (use the staged API)");
     TRY(sb200_server_upload_query(s, query_cv_host, stream));
-    TRY(sb200_server_expand_and_convert(s, stream));
+    TRY(expand_and_convert_impl(s, stream, true));
     TRY(sb200_server_first_dim(s, stream));
     TRY(sb200_server_fold_local(s, stream));
     TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));

@@ -235,7 +235,7 @@ extern "C" int sb200_client_decode(sb200_client *c, const uint64_t *total_resp_h
     DBuf<uint64_t> resp, pt;
     CU(resp.alloc(6 * (size_t)kN)); CU(pt.alloc(4 * (size_t)kN));
     CU(cudaMemcpyAsync(resp.p, total_resp_host, 6 * (size_t)kN * 8, cudaMemcpyHostToDevice, c->st));
-    launch_client_decode(pt.p, resp.p, c->Sp_raw.p, sb200_arb_qprime(c->prm.qp_bits), c->prm.p_db, c->st); CHECK_LAUNCH();
+    launch_client_decode(pt.p, resp.p, c->Sp_raw.p, sb200_arb_qprime(c->prm.qp_bits), c->prm.p_db, kN2, c->st); CHECK_LAUNCH();
     CU(cudaMemcpyAsync(pt_out_host, pt.p, 4 * (size_t)kN * 8, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     return SB200_OK;

@@ -220,7 +220,7 @@ static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     if (parent) s->db_owner = parent; else A(s->db.alloc(s->planes * s->plane_words));
     A(s->W_left.alloc(s->g * 2 * prm->t_exp * PLW)); A(s->W_right.alloc((s->stopround + 1) * 2 * prm->t_exp_right * PLW));
-    A(s->V.alloc(2 * 2 * prm->t_conv * PLW)); A(s->vW.alloc(prm->out_n * rows * prm->t_conv * PLW)); A(s->neg1.alloc(s->g * PLW));
+    A(s->V.alloc(2 * 2 * prm->t_conv * PLW)); A(s->vW.alloc(prm->out_n * rows * prm->t_conv * PLW)); A(s->neg1.alloc(2 * s->g * PLW));
     A(s->stage.alloc((size_t)1024 * PLW)); A(s->q_wire.alloc(kWireHeaderBytes + 2 * kWireRowBytes + 8));
     A(s->cv.alloc(ncts * 2 * PLW)); A(s->c1.alloc((size_t)s->maxcnt * PLW)); A(s->ginv.alloc(expand_ginv_polys(s->plan, s->cnt.data()) * PLW));
     A(s->c0.alloc((size_t)s->maxcnt * kN));

@@ -58,13 +58,16 @@ struct RegevArgs {
     const uint32_t *msg;            // [R] dev-NTT message bases (nullptr: no message)
     const uint32_t *scal;           // [R][ncols][2] residues of the per-column scalar (nullptr: 1)
     int ncols;
+    int col_stride;                 // 0 / 1: consecutive columns; s: launch column c is matrix column col_begin + c*s, object obj_base + c*s
+    int ct_major;                   // 0: polynomial (row, col) at row*out_cols + col (a matrix); 1: at col*(1+R) + row (a vector of ciphertexts)
 };
 __global__ void __launch_bounds__(kNttThreads) k_client_regev_cols(uint32_t *__restrict__ out, RegevArgs a) {
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     const uint32_t q = modulus(n);
-    const int c = blockIdx.x, col = a.col_begin + c;
-    const uint32_t obj = a.obj_base + (uint32_t)c;
+    const int c = blockIdx.x, cs = a.col_stride > 1 ? a.col_stride : 1, col = a.col_begin + c * cs;
+    const uint32_t obj = a.obj_base + (uint32_t)(c * cs);
+    const size_t rows = 1 + (size_t)a.R;
     uint32_t row0[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(kNttThreads) k_client_regev_cols(uint32_t *__r
         else chacha20_block(x, a.key.w, slot, kClientMagic, obj, 0u);
         row0[k] = uniform_from_block(x, q);
     }
-    store_ntt_regs(row0, out + ((size_t)col * 2 + n) * kN, lt);
+    store_ntt_regs(row0, out + ((a.ct_major ? (size_t)col * rows : (size_t)col) * 2 + n) * kN, lt);
     for (int r = 0; r < a.R; r++) {
         uint32_t e[16];
 #pragma unroll
@@ -97,18 +100,18 @@ __global__ void __launch_bounds__(kNttThreads) k_client_regev_cols(uint32_t *__r
             if (a.msg) acc += (uint64_t)m[k] * sc;
             e[k] = reduce_u64(acc, n);
         }
-        store_ntt_regs(e, out + (((size_t)(1 + r) * a.out_cols + col) * 2 + n) * kN, lt);
+        store_ntt_regs(e, out + ((a.ct_major ? (size_t)col * rows + 1 + r : (size_t)(1 + r) * a.out_cols + col) * 2 + n) * kN, lt);
     }
 }
 
 // Decoding (check_final): pt[r][c] = round-and-reduce of  Sp_r * resp_row0[c] (negacyclic, mod q')  combined with rows 1..2.
 // grid (8, 4): blockIdx.y = r*2 + c, 256 output coefficients per CTA; the two 2048-term operands sit in shared memory.
 __global__ void __launch_bounds__(256) k_client_decode(uint64_t *__restrict__ pt, const uint64_t *__restrict__ resp, const uint64_t *__restrict__ Sp_raw,
-                                                       uint64_t qp, uint64_t p_db) {
+                                                       uint64_t qp, uint64_t p_db, int nn) {      // nn = n2 (Spiral: 2) or out_n (Pack variants)
     // operands stay 64-bit and the 2048 products (each < qp^2 <= 2^74 for the 37-bit moduli of qprime_mods) are summed in
     // 128 bits: exact for every q' the reference's table holds (oracle/client_sim.c does the same with __int128)
     __shared__ uint64_t sa[kN], sb[kN];
-    const int r = blockIdx.y >> 1, c = blockIdx.y & 1;
+    const int r = blockIdx.y / nn, c = blockIdx.y % nn;
     for (int i = threadIdx.x; i < kN; i += 256) {
         const uint64_t raw = Sp_raw[(size_t)r * kN + i];                   // recentring of to_ntt_qprime (src/util.cpp:224-229)
         const int64_t a = raw >= kQ / 2 ? (int64_t)raw - (int64_t)kQ : (int64_t)raw;
@@ -128,14 +131,14 @@ __global__ void __launch_bounds__(256) k_client_decode(uint64_t *__restrict__ pt
     const uint64_t pos = (uint64_t)(pos128 % qp), neg = (uint64_t)(neg128 % qp);
     const uint64_t sp = (pos + qp - neg) % qp;
     const uint64_t q1 = 4 * p_db, denom = qp * (q1 / p_db);
-    const uint64_t rest = resp[(size_t)(kN2 + r * kN2 + c) * kN + k];
+    const uint64_t rest = resp[(size_t)(nn + r * nn + c) * kN + k];
     const int64_t vf = sp >= qp / 2 ? (int64_t)sp - (int64_t)qp : (int64_t)sp;
     const int64_t vr = rest >= q1 / 2 ? (int64_t)rest - (int64_t)q1 : (int64_t)rest;
     const int64_t rr = vf * (int64_t)q1 + vr * (int64_t)qp;
     const int64_t half = (int64_t)(denom / 2);
     int64_t res = (rr + (rr >= 0 ? half : -half)) / (int64_t)denom;       // C truncating division, as the reference
     res = (res + (int64_t)((denom / p_db) * p_db) + 2 * (int64_t)p_db) % (int64_t)p_db;
-    pt[(size_t)(r * kN2 + c) * kN + k] = (uint64_t)res;
+    pt[(size_t)(r * nn + c) * kN + k] = (uint64_t)res;
 }
 
 void launch_client_gauss_raw(uint64_t *out, const ClientKey &key, uint32_t obj_base, uint32_t sub, int npolys, cudaStream_t s) {
@@ -147,9 +150,9 @@ void launch_client_regev_cols(uint32_t *out, const RegevArgs &a, cudaStream_t s)
     count_launch();
     note_kernel("k_client_regev_cols"); k_client_regev_cols<<<a.ncols, kNttThreads, 0, s>>>(out, a);
 }
-void launch_client_decode(uint64_t *pt, const uint64_t *resp, const uint64_t *Sp_raw, uint64_t qp, uint64_t p_db, cudaStream_t s) {
+void launch_client_decode(uint64_t *pt, const uint64_t *resp, const uint64_t *Sp_raw, uint64_t qp, uint64_t p_db, int nn, cudaStream_t s) {
     count_launch();
-    note_kernel("k_client_decode"); k_client_decode<<<dim3(kN / 256, kN0 * kN2), 256, 0, s>>>(pt, resp, Sp_raw, qp, p_db);
+    note_kernel("k_client_decode"); k_client_decode<<<dim3(kN / 256, nn * nn), 256, 0, s>>>(pt, resp, Sp_raw, qp, p_db, nn);
 }
 
 }  // namespace sb200

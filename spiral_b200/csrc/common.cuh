@@ -19,6 +19,7 @@ constexpr uint64_t kPsiB = 158221ull;                  // regenerate src/constan
 constexpr uint64_t kCr1P = 68736257792ull;             // floor(2^64/p)       values.h:59
 constexpr uint64_t kCr1B = 73916747789ull;             // floor(2^64/b)       values.h:61
 constexpr uint32_t kBInvModP = 163640210u;             // b^-1 mod p          values.h:25
+constexpr uint32_t kBInvModPShoup = 2618882725u;       // floor(b^-1 * 2^32 / p)
 constexpr uint32_t kPInvModB = 97389680u;              // p^-1 mod b          values.h:24
 constexpr int kN0 = 2, kN1 = 3, kN2 = 2;               // values.h:67-69
 
@@ -54,7 +55,7 @@ __device__ __forceinline__ uint32_t csub(uint32_t x, uint32_t q) {   // x in [0,
 __device__ __forceinline__ uint64_t crt_compose(uint32_t x, uint32_t y) {
     uint32_t ymp = y >= kP ? y - kP : y;                 // y < b < p, kept for safety with y == b
     uint32_t d = x >= ymp ? x - ymp : x + kP - ymp;      // (x - y) mod p
-    uint32_t t = mulmod(d, kBInvModP, 0);
+    uint32_t t = csub(mul_shoup_lazy(d, kBInvModP, kBInvModPShoup, kP), kP);   // d * b^-1 mod p with the constant's Shoup companion
     return (uint64_t)y + (uint64_t)kB * t;
 }
 
@@ -80,7 +81,9 @@ __device__ __forceinline__ uint64_t gadget_digit(uint64_t val, int k, uint32_t b
 struct TraceCtl { unsigned long long *buf; unsigned int *counter; unsigned int cap; };   // timeline trace (ntt_kernels.cu); buf == nullptr: off
 __constant__ TraceCtl c_trace;
 __device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ void pdl_prologue() {
+// every kernel starts with pdl_prologue(); the macro passes the call site's line, which names the kernel in the trace
+#define pdl_prologue() pdl_prologue_at(__LINE__)
+__device__ __forceinline__ void pdl_prologue_at(int line) {
     const bool tr = c_trace.buf != nullptr && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
     unsigned long long t0 = 0;
     if (tr) t0 = global_timer_ns();
@@ -90,7 +93,8 @@ __device__ __forceinline__ void pdl_prologue() {
         const unsigned int i = atomicAdd(c_trace.counter, 1u);
         if (i < c_trace.cap) {
             c_trace.buf[3 * i] = t0; c_trace.buf[3 * i + 1] = global_timer_ns();
-            c_trace.buf[3 * i + 2] = (unsigned long long)gridDim.x | ((unsigned long long)gridDim.y << 24) | ((unsigned long long)blockDim.x << 48);
+            c_trace.buf[3 * i + 2] = (unsigned long long)(gridDim.x & 0xFFFFFu) | ((unsigned long long)(gridDim.y & 0xFFFFu) << 20) |
+                                     ((unsigned long long)(blockDim.x & 0xFFFu) << 36) | ((unsigned long long)(line & 0xFFFF) << 48);
         }
     }
 }

@@ -14,15 +14,30 @@ namespace sb200 {
 void count_launch(int n = 1);        // our own kernel launches since load (sb200_launch_count)
 uint64_t launch_count();
 bool pdl_enabled();                    // SB200_NO_PDL=1 disables programmatic dependent launch
+// Launch priority of the calling thread's next launches (captured into graph kernel nodes as well): the expansion runs two
+// independent chains on two streams - the one the scan waits for is launched at the device's greatest priority, so that when
+// both have CTAs pending the critical chain's are dispatched first.
+constexpr int kNoPriority = 1 << 30;
+int &launch_priority();
+struct LaunchPriority {
+    int saved;
+    explicit LaunchPriority(bool high);
+    ~LaunchPriority() { launch_priority() = saved; }
+};
 void note_kernel(const char *name);    // distinct kernel names launched since the last reset (sb200_kernel_log)
 template <typename... KArgs, typename... Args>
 inline void launch_pdl_impl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (launch_priority() != kNoPriority) {            // LaunchPriority scope: kernels of a latency-critical chain go first
+        attr[1].id = cudaLaunchAttributePriority;
+        attr[1].val.priority = launch_priority();
+        cfg.numAttrs = 2;
+    }
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 // every launch of the library goes through this macro: it records the kernel's name (a template instance is written in
@@ -128,10 +143,11 @@ size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt);                 /
 void build_automorph_perms(uint16_t *perm_host, int g);      // host: g x 2048 slot permutations (one per round)
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
                    const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
-                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin = 0, int r_end = -1, int parity = -1);
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin = 0, int r_end = -1, int parity = -1,
+                   int store_self = 0);
 int expand_split_lists(const ExpandPlan &p, const int *list, const int *offs, const int *cnt, int *list_e, int *offs_e, int *cnt_e,
                        int *list_o, int *offs_o, int *cnt_o);                    // even / odd chains of the expansion tree
-void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s);   // neg1[r] = NTT(-x^(N-2^r)), r < count
+void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s);   // neg1[r] = NTT(-x^(N-2^r)), r < count, then their Shoup companions (2 * count polys)
 
 // ---- conversion
 void launch_from_ntt_indexed(uint64_t *raw, const uint32_t *in, const int *poly_idx, size_t count, cudaStream_t s);

@@ -86,6 +86,14 @@ size_t trace_read(unsigned long long *out, size_t max_records, int reset) {
     return m;
 }
 
+int &launch_priority() { static thread_local int p = kNoPriority; return p; }
+LaunchPriority::LaunchPriority(bool high) : saved(launch_priority()) {
+    static const bool off = [] { const char *e = getenv("SB200_NO_PRIO"); return e && *e == '1'; }();
+    if (off) return;
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return; }
+    launch_priority() = high ? greatest : least;
+}
 bool pdl_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("SB200_NO_PDL"); v = (e && *e == '1') ? 0 : 1; } return v == 1; }
 
 static std::mutex g_tab_mutex;

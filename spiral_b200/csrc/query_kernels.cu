@@ -25,8 +25,9 @@ __device__ __forceinline__ uint64_t pack_pb2(uint32_t p, uint32_t b) { return (u
 //   k_expand_accum  : cv[i][row] += sum_k W[row][k] * ginv[slot][k] + row * c1_ntt[slot]
 // ============================================================================================
 __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restrict__ cv, const int *__restrict__ active, int num_in,
-                                                             const uint32_t *__restrict__ neg1, uint32_t tpow, const uint16_t *__restrict__ perm,
-                                                             uint64_t *__restrict__ c0_raw, uint32_t *__restrict__ c1_ntt) {
+                                                             const uint32_t *__restrict__ neg1, const uint32_t *__restrict__ neg1_shoup, uint32_t tpow,
+                                                             const uint16_t *__restrict__ perm, uint64_t *__restrict__ c0_raw, uint32_t *__restrict__ c1_ntt,
+                                                             int store_self) {
     pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
@@ -35,19 +36,27 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
     if (i < num_in) {
         // the reference writes cv[2^r + i] = x^(-2^r) * cv[i] whenever i is processed, even if 2^r + i
         // itself is skipped later in the round (src/spiral.cpp:1709) - so the producer stores it
-        uint32_t w[16], nb[16];
+        // neg1 is a constant of the round: the product is a Shoup multiplication (3 multiplies) instead of a 64-bit Barrett
+        uint32_t w[16], ws[16], nb[16];
+        const uint32_t q = modulus(n);
         load_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
         load_ntt_regs(w, neg1 + n * kN, lt);
+        load_ntt_regs(ws, neg1_shoup + n * kN, lt);
 #pragma unroll
-        for (int e = 0; e < 16; e++) nb[e] = mulmod(v[e], w[e], n);
+        for (int e = 0; e < 16; e++) nb[e] = csub(mul_shoup_lazy(v[e], w[e], ws[e], q), q);
         store_ntt_regs(nb, cv + (((size_t)(i + num_in) * 2 + row) * 2 + n) * kN, lt);
     } else {
         // same product recomputed locally: no dependence on the producer CTA of this launch
-        uint32_t a[16], w[16];
+        uint32_t a[16], w[16], ws[16];
+        const uint32_t q = modulus(n);
         load_ntt_regs(a, cv + (((size_t)(i - num_in) * 2 + row) * 2 + n) * kN, lt);
         load_ntt_regs(w, neg1 + n * kN, lt);
+        load_ntt_regs(ws, neg1_shoup + n * kN, lt);
 #pragma unroll
-        for (int e = 0; e < 16; e++) v[e] = mulmod(a[e], w[e], n);
+        for (int e = 0; e < 16; e++) v[e] = csub(mul_shoup_lazy(a[e], w[e], ws[e], q), q);
+        // a chain that follows only its own subtree (odd / even graphs, a rank's share of a sharded expansion) may process
+        // output i without its sibling i - num_in: then nobody else stores the base value the accumulation adds to
+        if (store_self) store_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
     }
     if (row == 1) {
         // NTT(automorph(c_1)) is a permutation of the NTT slots of c_1 (x -> x^t maps evaluation point
@@ -165,7 +174,8 @@ __global__ void __launch_bounds__(256) k_expand_accum_wide(uint32_t *__restrict_
                      reduce_u64(a1[3] + c1.w + add.w, n));
 }
 
-// neg1[r] = NTT(invert(x^(N - 2^r))) = NTT(-x^(N-2^r))   (reference src/spiral.cpp:184-192)
+// neg1[r] = NTT(invert(x^(N - 2^r))) = NTT(-x^(N-2^r))   (reference src/spiral.cpp:184-192), followed at + count polynomials by
+// the Shoup companions floor(neg1 * 2^32 / q)
 __global__ void __launch_bounds__(kNttThreads) k_build_neg1(uint32_t *__restrict__ neg1) {
     pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
@@ -177,8 +187,12 @@ __global__ void __launch_bounds__(kNttThreads) k_build_neg1(uint32_t *__restrict
     for (int k = 0; k < 16; k++) v[k] = (nat_pos(lt, k) == idx) ? q - 1 : 0;
     ntt_forward_plane(v, sm[n], lt, n);
     store_ntt_regs(v, neg1 + ((size_t)r * 2 + n) * kN, lt);
+    uint32_t ws[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) ws[k] = (uint32_t)(((uint64_t)v[k] << 32) / q);
+    store_ntt_regs(ws, neg1 + ((size_t)(gridDim.x + r) * 2 + n) * kN, lt);
 }
-void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s) {
+void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s) {   // neg1_dev: 2 * count polynomials
     if (count) { count_launch(); launch_pdl(k_build_neg1, dim3(count), dim3(kNttThreads), 0, s, neg1_dev); }
 }
 
@@ -271,7 +285,7 @@ size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt) {
 }
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
                    const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
-                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end, int parity) {
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end, int parity, int store_self) {
     // parity: -1 = the lists hold every active ciphertext; 0 / 1 = they hold only the even / odd ones (expand_split_lists):
     // after round 0 the even chain (first-dimension ciphertexts, t_left digits) and the odd chain (GSW bits, t_right digits)
     // never touch each other's ciphertexts, so the two can run on different streams with their own scratch.
@@ -286,7 +300,7 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         // digits needed this round: t_right only if some odd ciphertext is active
         const bool any_odd = parity != 0 && !(p.stopround > 0 && r > p.stopround);
         const int ty = parity == 1 ? p.t_right : any_odd ? tmax : p.t_left;
-        count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt);
+        count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, neg1 + (size_t)(p.g + r) * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt, store_self);
         // ginv is indexed [slot][ty]: rounds past stopround only hold t_left digits per slot (see expand_ginv_polys)
         count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty);
         count_launch();                                   // rounds with right slots (56-term chains) stay on the split kernel
@@ -373,14 +387,51 @@ __global__ void k_scal_to_mat_accum(uint64_t *__restrict__ query, const uint32_t
 // The same, tiled: CTA = 32 z x 8 j.  Operands are read with z across the lanes (coalesced), results go through shared memory
 // and leave with j across the lanes: 512 contiguous bytes per z instead of 64-byte pieces 16 KiB apart (the scattered form spent
 // its time in the store path: 2 M sixteen-byte stores to 2 M different sectors).
-__global__ void __launch_bounds__(256) k_scal_to_mat_accum_tiled(uint64_t *__restrict__ query, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
-                                                                 const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int dim0, int jtiles) {
+// Sharded expansion: this rank converts only the `count` ciphertexts jl whose first-dimension index is j = j_off + j_stride * jl and
+// stores them into the query buffer of EVERY rank (peer pointers: the all-gather is fused into the kernel that produces the
+// data); the last CTA to finish raises this rank's flag on every peer (k_query_wait is the consumer side).
+struct ScalTargets {
+    uint64_t *query[16];                // [0] = this rank's own buffer; ntargets == 1: unsharded
+    unsigned int *flag[16];             // flag[t]: this rank's arrival flag inside target t's exchange header
+    int ntargets;
+    unsigned int *arrive;               // this rank's CTA arrival counter
+    const unsigned int *ack;            // rank 0's acknowledgement of the previous query, as seen by this rank
+    const unsigned int *epoch;          // exchange epoch of the last completed query
+    unsigned int *error;
+};
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) k_scal_to_mat_accum_tiled(const __grid_constant__ ScalTargets tg, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
+                                                                 const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int dim0, int count,
+                                                                 int j_off, int j_stride, int jtiles) {
     pdl_prologue();
     constexpr int TC = 4;                                             // t_conv of every Spiral parameter set that reaches this kernel
     constexpr int kRowWords = 8 * 8 + 1;                              // 8 j x 8 words, padded: lanes (z) land on different banks
     __shared__ __align__(16) uint64_t tile[32 * kRowWords];
+    __shared__ int ok;
     const int zl = threadIdx.x & 31, jl = threadIdx.x >> 5, lane = zl, wid = jl;
     const int z = blockIdx.x * 32 + zl;
+    unsigned int e = 0;
+    if (tg.ntargets > 1) {
+        // the peers' query buffers may be overwritten only after every rank has finished scanning the previous query: rank 0's
+        // acknowledgement of that query's exchange (bounded spin, as in xchg_kernels.cu)
+        if (threadIdx.x == 0) {
+            e = *tg.epoch + 1;
+            ok = 1;
+            if (e > 1) {
+                unsigned long long t0 = global_timer_ns();
+                while ((int)(ld_acquire_sys_u32(tg.ack) - (e - 1)) < 0) {
+                    __nanosleep(200);
+                    if (global_timer_ns() - t0 > 4000000000ull) { ok = 0; break; }
+                }
+            }
+        }
+        __syncthreads();
+        if (!ok) { if (threadIdx.x == 0) *tg.error = 3; return; }
+    }
     // the conversion key W (3 x 2*t_conv) at this z under both primes stays in registers for all the j of this CTA
     uint32_t wp[3][2][TC], wb[3][2][TC];
 #pragma unroll
@@ -393,10 +444,10 @@ __global__ void __launch_bounds__(256) k_scal_to_mat_accum_tiled(uint64_t *__res
                 wp[r][c][k] = __ldg(w + z); wb[r][c][k] = __ldg(w + kN + z);
             }
     for (int jt = 0; jt < jtiles; jt++) {
-        const int j0 = (blockIdx.y * jtiles + jt) * 8, j = j0 + jl;
+        const int j0 = (blockIdx.y * jtiles + jt) * 8, j = j0 + jl;           // local ciphertext numbers
         uint32_t gp[TC], gb[TC];
 #pragma unroll
-        for (int k = 0; k < TC; k++) { const uint32_t *g = ginv + ((size_t)k * dim0 + j) * 2 * kN; gp[k] = __ldg(g + z); gb[k] = __ldg(g + kN + z); }
+        for (int k = 0; k < TC; k++) { const uint32_t *g = ginv + ((size_t)k * count + j) * 2 * kN; gp[k] = __ldg(g + z); gb[k] = __ldg(g + kN + z); }
         const uint32_t *cv1 = cv + ((size_t)ct_idx[j] * 2 + 1) * 2 * kN;
         const uint32_t c1p = __ldg(cv1 + z), c1b = __ldg(cv1 + kN + z);
         uint64_t *row = tile + zl * kRowWords + jl * 8;
@@ -412,14 +463,29 @@ __global__ void __launch_bounds__(256) k_scal_to_mat_accum_tiled(uint64_t *__res
             row[c * 4 + 3] = 0;
         }
         __syncthreads();
-        // write-out: warp w takes rows z = w, w + 8, ...; lane l the 16-byte chunk l of the 512-byte run [z][j0 .. j0+8)[m][4]
+        // write-out: warp w takes rows z = w, w + 8, ...; lane l the 16-byte chunk l of the 8 x 64 bytes [z][j(j0 .. j0+8)][m][4]
+        // (one 512-byte run when j_stride == 1)
+        const size_t jg = (size_t)j_off + (size_t)j_stride * (j0 + (lane >> 2));
 #pragma unroll
         for (int zz = wid; zz < 32; zz += 8) {
             const uint64_t *src = tile + zz * kRowWords + lane * 2;
-            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(query + (((size_t)(blockIdx.x * 32 + zz) * dim0 + j0) * 2) * 4) + lane;
-            *dst = make_ulonglong2(src[0], src[1]);
+            const ulonglong2 val = make_ulonglong2(src[0], src[1]);
+            const size_t o = (((size_t)(blockIdx.x * 32 + zz) * dim0 + jg) * 2) * 4 / 2 + (lane & 3);     // in 16-byte units
+            for (int t = 0; t < tg.ntargets; t++) reinterpret_cast<ulonglong2 *>(tg.query[t])[o] = val;
         }
         __syncthreads();
+    }
+    if (tg.ntargets > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(tg.arrive, 1u) == gridDim.x * gridDim.y - 1) {
+                *tg.arrive = 0;
+                __threadfence_system();
+                for (int t = 0; t < tg.ntargets; t++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tg.flag[t]), "r"(e) : "memory");
+            }
+        }
     }
 }
 // same product but emitted as dev-NTT MatPoly (3 x 2) per ciphertext - the reference's scalToMat output
@@ -543,9 +609,21 @@ void launch_scal_to_mat_reoriented(uint64_t *query_out, const uint32_t *cv, cons
     count_launch();
     if (dim0 % 8 == 0 && t_conv == 4) {
         const int jtiles = dim0 % 32 == 0 ? 4 : 1;                    // j-tiles of 8 per CTA: the key registers are amortised over 32 j
-        launch_pdl(k_scal_to_mat_accum_tiled, dim3(kN / 32, (unsigned)(dim0 / 8 / jtiles)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, (int)dim0, jtiles);
+        ScalTargets tg{};
+        tg.query[0] = query_out; tg.ntargets = 1;
+        launch_pdl(k_scal_to_mat_accum_tiled, dim3(kN / 32, (unsigned)(dim0 / 8 / jtiles)), dim3(256), 0, s, tg, cv, ct_idx, scratch_ntt, W, (int)dim0, (int)dim0, 0, 1, jtiles);
     }
     else launch_pdl(k_scal_to_mat_accum, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, query_out, cv, ct_idx, scratch_ntt, W, t_conv, (int)dim0);
+}
+// a rank's share of a sharded conversion: `count` (multiple of 8) ciphertexts, first-dimension index j = j_off + j_stride * jl,
+// t_conv == 4; results are stored into every target of `tg` and this rank's flag is raised on each (see the kernel)
+void launch_scal_to_mat_sharded(const ScalTargets &tg, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t dim0, size_t count,
+                                int j_off, int j_stride, const uint32_t *W, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
+    launch_from_ntt_indexed(scratch_raw, cv, poly_idx, count, s);
+    launch_gadget_ntt(scratch_ntt, scratch_raw, 4, 1, (int)count, s);
+    const int jtiles = count % 32 == 0 ? 4 : 1;
+    count_launch();
+    launch_pdl(k_scal_to_mat_accum_tiled, dim3(kN / 32, (unsigned)(count / 8 / jtiles)), dim3(256), 0, s, tg, cv, ct_idx, scratch_ntt, W, (int)dim0, (int)count, j_off, j_stride, jtiles);
 }
 void launch_scal_to_mat_ntt(uint32_t *out, const uint32_t *cv, const int *ct_idx, const int *poly_idx, size_t count,
                             const uint32_t *W, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {

@@ -137,6 +137,9 @@ size_t xchg_buffer_bytes(int world) { return xchg_bytes(world); }
 size_t xchg_buffer_bytes_w(int world, size_t slot_words) { return xchg_bytes_w(world, slot_words); }
 size_t xchg_ack_offset() { return offsetof(XchgBuf, ack); }
 size_t xchg_header_bytes() { return sizeof(XchgBuf); }
+unsigned int *xchg_qflag_ptr(void *buf, int rank) { return &reinterpret_cast<XchgBuf *>(buf)->qflags[rank]; }   // address arithmetic only
+unsigned int *xchg_arrive_ptr(void *buf, int k) { return &reinterpret_cast<XchgBuf *>(buf)->arrive[k]; }
+unsigned int *xchg_ack_ptr(void *buf) { return &reinterpret_cast<XchgBuf *>(buf)->ack; }
 
 // ---- query all-gather over peer memory (Pack direct upload, sharded): every rank uploads and reorients only its 1/world
 // slice of the first-dimension ciphertexts and stores it into EVERY rank's query buffer, then raises qflags[rank] there;

@@ -193,6 +193,7 @@ def load_library():
         "sb200_server_exchange_and_tail": (C.c_int, [vp, vp, vp]),
         "sb200_server_xchg_error": (C.c_int, [vp, vp]),
         "sb200_server_xchg_reset": (C.c_int, [vp]),
+        "sb200_server_expansion_sharded": (C.c_int, [vp]),
         "sb200_server_public_param_polys": (C.c_int, [vp, C.POINTER(sz)]),
         "sb200_client_wire_seed": (C.c_int, [vp, C.c_uint32, vp]),
         "sb200_server_first_dim_cts": (vp, [vp]),

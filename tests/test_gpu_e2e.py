@@ -240,3 +240,48 @@ def test_packed_response_wire_format(sb, oracle):
         assert oracle.so_read_arbitrary_bits(ol.ptr(packed), k * s.prm.qp_bits, s.prm.qp_bits) == raw[k]
     srv.close()
     s.close()
+
+
+@pytest.mark.parametrize("cfg,nu1,nu2,world", [("cfg1", 6, 3, 2), ("cfg1", 5, 3, 4), ("cfg5", 6, 2, 4), ("cfg1", 7, 3, 8)])
+def test_sharded_expansion_with_fused_all_gather(sb, oracle, cfg, nu1, nu2, world):
+    """Connected shards with 2^nu1 / world a multiple of 8 no longer replicate the query-side work: each rank expands only the
+    ancestors of the first-dimension ciphertexts j = rank (mod world), converts those, and its ScalToMat kernel stores them into
+    EVERY rank's query buffer (peer stores + flags); the scan waits for all slices.  world shards on one device, several queries
+    in a row (the slices of query k+1 may only land after every rank has scanned query k), == the oracle's unsharded answer."""
+    import torch
+    s = ol.SpiralSession(oracle, cfg, nu1, nu2, seed=21)
+    Bbuf = s.reference_db()
+    servers = [SpiralServer(sb_params(s.prm), rank=r, world=world) for r in range(world)]
+    streams = [torch.cuda.Stream() for _ in servers]
+    for srv in servers:
+        srv.load_db_items(srv.shard_items(s.pts).astype(np.uint16))
+        srv.set_public_params(s.W_left, s.W_right, s.W_conv, s.V_conv)
+    for srv in servers:
+        srv.xchg_connect_local(servers)
+    resp = torch.zeros(6 * ol.N, dtype=torch.int64, device="cuda")
+    for k, idx in enumerate((5, s.total_n - 1, 77 % s.total_n, 5)):
+        q = s.query(idx)
+        want, _, _ = s.oracle_answer(q, Bbuf)
+        resp.zero_()
+        torch.cuda.synchronize()
+        for srv, st in list(zip(servers, streams))[::-1]:        # rank 0 last: its wait kernel needs the others' pushes
+            srv.upload_query(q, st.cuda_stream)
+            srv.process(resp.data_ptr() if srv.rank == 0 else None, st.cuda_stream)
+        torch.cuda.synchronize()
+        assert all(srv.xchg_error() == 0 for srv in servers)
+        assert all(sb.sb200_server_expansion_sharded(srv.h) == 1 for srv in servers), "the expansion was replicated, not sharded"
+        got = resp.cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, want), f"query {k} (idx {idx}): sharded expansion changed the response"
+        assert np.array_equal(s.decode(got), s.pts[idx])
+    # the staged calls take the same path (join before returning from expand_and_convert)
+    q = s.query(9)
+    want, _, _ = s.oracle_answer(q, Bbuf)
+    for srv, st in list(zip(servers, streams))[::-1]:
+        srv.upload_query(q, st.cuda_stream); srv.expand_and_convert(st.cuda_stream); srv.first_dim(st.cuda_stream); srv.fold_local(st.cuda_stream)
+        srv.exchange_and_tail(resp.data_ptr() if srv.rank == 0 else None, st.cuda_stream)
+    torch.cuda.synchronize()
+    assert all(srv.xchg_error() == 0 for srv in servers)
+    assert np.array_equal(resp.cpu().numpy().view(np.uint64), want)
+    for srv in servers:
+        srv.close()
+    s.close()
