@@ -373,7 +373,23 @@ int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint32_t query_i
 int sb200_client_wire_seed(const sb200_client *c, uint32_t query_id, uint8_t *seed32_out);
 /* total_resp: 3x2 raw response (sb200_server_answer, or sb200_unpack_response of the packed one) -> 2x2 plaintext polynomials */
 int sb200_client_decode(sb200_client *c, const uint64_t *total_resp_host, uint64_t *pt_out_host);
-/* test taps: the secret key (raw, 1 + 2 polynomials) and the sampler's 128 integer thresholds */
+/* ---- the SpiralPack / SpiralStreamPack client (testHighRate's client statements, src/testing.cpp:904-1005, 1086-1122): keys with
+ * out_n rows of S', packing keys v_W (:905-912), expansion keys + V (:913-931), the packed query (:987-1005) or the direct upload
+ * (:962-985), out_n x out_n decoding (:1086-1118).  Same counter-based randomness; oracle/client_sim.c (so_pack_client_new_chacha)
+ * states it in plain C.  Destroy / wire seed / secret tap: the sb200_client_* entries. */
+int sb200_pack_client_create(sb200_client **out, const sb200_params *prm, int device, const uint8_t *seed32);
+/* polynomial counts of W_exp_left, W_exp_right, V, v_W - the arguments of sb200_pack_server_set_public_params */
+int sb200_pack_client_public_param_polys(const sb200_client *c, size_t *out4);
+/* W_exp_left, W_exp_right and V may all be NULL (direct-upload client) */
+int sb200_pack_client_public_params(sb200_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *V, uint64_t *v_W);
+/* SEEDED wire query (as sb200_client_query_wire; needs 2^nu1 + t_GSW*nu2 <= 2048) */
+int sb200_pack_client_query_wire(sb200_client *c, size_t idx_target, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out);
+/* direct upload: v_firstdim = 2^nu1 ciphertexts (2x1 ref-NTT), v_folding = nu2 x (2 x 2*t_GSW) ref-NTT; query_id < 2^8 selects a
+ * fresh block of 2^16 randomness objects (never reuse one under the same client seed) */
+int sb200_pack_client_query_direct(sb200_client *c, size_t idx_target, uint32_t query_id, uint64_t *v_firstdim, uint64_t *v_folding);
+/* total_resp (out_n+1) x out_n raw -> out_n x out_n plaintext polynomials (entry i*out_n + j = the record's polynomial of that plane) */
+int sb200_pack_client_decode(sb200_client *c, const uint64_t *total_resp_host, uint64_t *pt_out_host);
+/* test taps: the secret key (raw, 1 + 2 polynomials; 1 + out_n for a Pack client) and the sampler's 128 integer thresholds */
 int sb200_client_secret(sb200_client *c, uint64_t *sr_raw_host, uint64_t *Sp_raw_host);
 int sb200_client_gaussian_thresholds(uint64_t *out128);
 

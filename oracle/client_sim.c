@@ -114,6 +114,10 @@ void so_client_gaussian_thresholds(const so_client *c, uint64_t *out128) { memcp
 void so_client_secret(const so_client *c, uint64_t *sr, uint64_t *Sp) {
     memcpy(sr, c->sr, N * sizeof(uint64_t)); memcpy(Sp, c->Sp, SO_N0 * N * sizeof(uint64_t));
 }
+/* the same for a Pack client: S' has sp_rows = out_n rows */
+void so_client_secret_n(const so_client *c, uint64_t *sr, uint64_t *Sp, size_t sp_rows) {
+    memcpy(sr, c->sr, N * sizeof(uint64_t)); memcpy(Sp, c->Sp, sp_rows * N * sizeof(uint64_t));
+}
 void so_client_free(so_client *c) { if (c) { free(c->Sp); free(c->sr); free(c); } }
 
 /* P (2x1 NTT) = [to_ntt(Q - a) ; a*s + e]   (getRegevSample) */

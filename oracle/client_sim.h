@@ -11,6 +11,7 @@ so_client *so_client_new(const so_params *prm, uint64_t seed, int nonoise);
 so_client *so_client_new_chacha(const so_params *prm, const uint8_t seed[32]);
 void so_client_gaussian_thresholds(const so_client *c, uint64_t *out128);
 void so_client_secret(const so_client *c, uint64_t *sr_raw, uint64_t *Sp_raw);
+void so_client_secret_n(const so_client *c, uint64_t *sr_raw, uint64_t *Sp_raw, size_t sp_rows);
 void so_client_chacha_query_wire(so_client *c, size_t idx_target, uint32_t query_id, const uint8_t wire_seed[32], uint8_t *wire);
 void so_client_free(so_client *c);
 size_t so_client_w_exp_right_count(const so_params *prm);

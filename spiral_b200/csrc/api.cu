@@ -477,7 +477,9 @@ int run_stage(GraphSlot &slot, cudaStream_t st, const void *k0, const void *k1, 
         if (e != cudaSuccess || !graph) { cudaGetLastError(); return fail(SB200_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e)); }
         slot.launches = (int)(launch_count() - before);
         count_launch(-slot.launches);                       // capture enqueues nothing; replays are counted below
-        e = cudaGraphInstantiate(&slot.exec, graph, 0);
+        // node priorities (LaunchPriority scopes during capture) only count when the graph is instantiated with this flag; without
+        // it every node runs at the priority of the stream the graph is launched into
+        e = cudaGraphInstantiateWithFlags(&slot.exec, graph, cudaGraphInstantiateFlagUseNodePriority);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { slot.exec = nullptr; return fail(SB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
         slot.key0 = k0; slot.key1 = k1;

@@ -7,6 +7,8 @@ struct sb200_client {
     sb200_params prm;
     int device = 0;
     size_t g = 0, stopround = 0, n_right = 0;
+    size_t sp_rows = kN0;                       // rows of S': n0 = 2 (Spiral), out_n (Pack variants)
+    bool pack = false;
     ClientKey key{};
     DBuf<uint64_t> sr_raw, Sp_raw;              // 1 and 2 polynomials, raw (small signed values mod Q)
     DBuf<uint32_t> sr_ntt, Sp_ntt;              // the same in dev-NTT form
@@ -15,7 +17,7 @@ struct sb200_client {
 };
 
 namespace {
-enum { CC_KEYS = 1, CC_W_RIGHT = 2, CC_W_LEFT = 3, CC_W_CONV = 4, CC_V_CONV = 5, CC_QUERY = 6 };
+enum { CC_KEYS = 1, CC_W_RIGHT = 2, CC_W_LEFT = 3, CC_W_CONV = 4, CC_V_CONV = 5, CC_QUERY = 6, CC_PACK_W = 7, CC_QUERY_DIRECT = 8 };
 inline uint32_t cc_obj(uint32_t cls, size_t idx) { return (cls << 24) | (uint32_t)idx; }
 
 // discrete Gaussian of width 6.4 on [-64, 64] (src/core.cpp:182-207) as integer thresholds on a 53-bit uniform
@@ -76,46 +78,59 @@ extern "C" int sb200_client_gaussian_thresholds(uint64_t *out128) {
     gaussian_thresholds(out128);
     return SB200_OK;
 }
-extern "C" int sb200_client_create(sb200_client **out, const sb200_params *prm, int device, const uint8_t *seed32) {
+static int client_create_impl(sb200_client **out, const sb200_params *prm, int device, const uint8_t *seed32, bool pack) {
     if (!out || !prm || !seed32) return fail(SB200_ERR_ARG, "client_create: null argument");
     if (prm->t_gsw == 0 || prm->t_conv == 0 || prm->t_exp == 0 || prm->t_exp_right == 0) return fail(SB200_ERR_ARG, "client_create: zero gadget length");
-    if (((size_t)1 << prm->nu1) + (size_t)prm->t_gsw * prm->nu2 > (size_t)kN) return fail(SB200_ERR_ARG, "client_create: 2^nu1 + t_GSW*nu2 exceeds the 2048 query slots");
+    if (pack && (prm->out_n == 0 || prm->out_n > 16 || prm->nu1 < 1 || prm->nu1 > 11)) return fail(SB200_ERR_ARG, "pack_client_create: 1 <= out_n <= 16 and 1 <= nu1 <= 11 required");
+    if (!pack && ((size_t)1 << prm->nu1) + (size_t)prm->t_gsw * prm->nu2 > (size_t)kN) return fail(SB200_ERR_ARG, "client_create: 2^nu1 + t_GSW*nu2 exceeds the 2048 query slots");
     if (sb200_arb_qprime(prm->qp_bits) == 0) return fail(SB200_ERR_ARG, "client_create: no response modulus for qp_bits = %u (14..36)", prm->qp_bits);
     if (prm->p_db == 0 || prm->p_db > 65536) return fail(SB200_ERR_ARG, "client_create: p_db must be in [1, 65536]");
     int rc = sb200_init(device);
     if (rc) return rc;
     sb200_client *c = new sb200_client();
-    c->prm = *prm; c->device = device;
+    c->prm = *prm; c->device = device; c->pack = pack;
     const size_t nbits = (size_t)prm->t_gsw * prm->nu2, dim0 = (size_t)1 << prm->nu1;       // src/spiral.cpp:2076-2085
     c->g = ceil_log2(nbits + dim0);
-    c->stopround = nbits > dim0 ? 0 : ceil_log2(nbits);
-    c->n_right = c->stopround > 0 ? c->stopround + 1 : c->g;
+    if (pack) {                                 // testHighRate, src/testing.cpp:795-798: always the stopround form
+        c->sp_rows = prm->out_n;
+        c->stopround = ceil_log2(nbits ? nbits : 1);
+        c->n_right = c->stopround + 1;
+    } else {
+        c->stopround = nbits > dim0 ? 0 : ceil_log2(nbits);
+        c->n_right = c->stopround > 0 ? c->stopround + 1 : c->g;
+    }
     for (int i = 0; i < 8; i++) memcpy(&c->key.w[i], seed32 + 4 * i, 4);
     uint64_t thr[128];
     gaussian_thresholds(thr);
     cudaError_t e = cudaMemcpyToSymbol(c_gauss_thr, thr, sizeof(thr));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = c->sr_raw.alloc(kN);
-    if (e == cudaSuccess) e = c->Sp_raw.alloc(kN0 * (size_t)kN);
+    if (e == cudaSuccess) e = c->Sp_raw.alloc(c->sp_rows * (size_t)kN);
     if (e == cudaSuccess) e = c->sr_ntt.alloc(PLW);
-    if (e == cudaSuccess) e = c->Sp_ntt.alloc(kN0 * PLW);
+    if (e == cudaSuccess) e = c->Sp_ntt.alloc(c->sp_rows * PLW);
     if (e != cudaSuccess) { delete c; return fail(SB200_ERR_CUDA, "client_create: %s", cudaGetErrorString(e)); }
     // keygen (src/client.cpp:23-47): s and S' from the error distribution
     launch_client_gauss_raw(c->sr_raw.p, c->key, cc_obj(CC_KEYS, 0), 0, 1, c->st);
-    launch_client_gauss_raw(c->Sp_raw.p, c->key, cc_obj(CC_KEYS, 1), 0, kN0, c->st);
+    launch_client_gauss_raw(c->Sp_raw.p, c->key, cc_obj(CC_KEYS, 1), 0, (int)c->sp_rows, c->st);
     launch_to_ntt(c->sr_ntt.p, c->sr_raw.p, 1, c->st);
-    launch_to_ntt(c->Sp_ntt.p, c->Sp_raw.p, kN0, c->st);
+    launch_to_ntt(c->Sp_ntt.p, c->Sp_raw.p, c->sp_rows, c->st);
     e = cudaStreamSynchronize(c->st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { delete c; return fail(SB200_ERR_CUDA, "client_create: %s", cudaGetErrorString(e)); }
     *out = c;
     return SB200_OK;
 }
+extern "C" int sb200_client_create(sb200_client **out, const sb200_params *prm, int device, const uint8_t *seed32) {
+    return client_create_impl(out, prm, device, seed32, false);
+}
+extern "C" int sb200_pack_client_create(sb200_client **out, const sb200_params *prm, int device, const uint8_t *seed32) {
+    return client_create_impl(out, prm, device, seed32, true);
+}
 extern "C" void sb200_client_destroy(sb200_client *c) { delete c; }
 extern "C" int sb200_client_secret(sb200_client *c, uint64_t *sr_raw_host, uint64_t *Sp_raw_host) {
     if (!c || !sr_raw_host || !Sp_raw_host) return fail(SB200_ERR_ARG, "client_secret: null argument");
     CU(c->sr_raw.down(sr_raw_host, kN));
-    CU(c->Sp_raw.down(Sp_raw_host, kN0 * (size_t)kN));
+    CU(c->Sp_raw.down(Sp_raw_host, c->sp_rows * (size_t)kN));
     return SB200_OK;
 }
 extern "C" int sb200_client_public_param_polys(const sb200_client *c, size_t *out4) {
@@ -126,6 +141,7 @@ extern "C" int sb200_client_public_param_polys(const sb200_client *c, size_t *ou
 }
 extern "C" int sb200_client_public_params(sb200_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *W_conv, uint64_t *V_conv) {
     if (!c || !W_exp_left || !W_exp_right || !W_conv || !V_conv) return fail(SB200_ERR_ARG, "client_public_params: null argument");
+    if (c->pack) return fail(SB200_ERR_STATE, "client_public_params: this is a Pack client (sb200_pack_client_public_params)");
     CU(cudaSetDevice(c->device));
     TRY(client_expansion_keys(c, W_exp_right, c->n_right, c->prm.t_exp_right, CC_W_RIGHT));
     TRY(client_expansion_keys(c, W_exp_left, c->g, c->prm.t_exp, CC_W_LEFT));
@@ -177,6 +193,7 @@ extern "C" int sb200_client_wire_seed(const sb200_client *c, uint32_t query_id, 
     memcpy(seed32_out, x, 32);
     return SB200_OK;
 }
+static int client_wire_from_sigma(sb200_client *c, const std::vector<uint64_t> &sigma, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out);
 // query encoding (src/spiral.cpp:2098-2157) + encryptSimpleRegev, straight into the SEEDED wire form
 extern "C" int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out) {
     if (!c || !wire_out) return fail(SB200_ERR_ARG, "client_query_wire: null argument");
@@ -187,6 +204,7 @@ extern "C" int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint3
     }
     const sb200_params &p = c->prm;
     const size_t fd = p.nu2, ell = p.t_gsw, dim0 = (size_t)1 << p.nu1;
+    if (c->pack && dim0 + ell * fd > (size_t)kN) return fail(SB200_ERR_ARG, "pack_client_query_wire: 2^nu1 + t_GSW*nu2 exceeds the 2048 query slots (direct upload only)");
     if (idx_target >= (dim0 << fd)) return fail(SB200_ERR_ARG, "client_query_wire: index %zu outside the 2^%zu records", idx_target, (size_t)(p.nu1 + fd));
     if (query_id >= (1u << 24)) return fail(SB200_ERR_ARG, "client_query_wire: query_id must be below 2^24");
     CU(cudaSetDevice(c->device));
@@ -194,7 +212,7 @@ extern "C" int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint3
     const uint32_t bits_per = get_bits_per((uint32_t)ell);
     std::vector<uint64_t> sigma(kN, 0);
     const uint64_t scale_k = kQ / p.p_db;
-    if (c->stopround != 0) {
+    if (c->pack || c->stopround != 0) {       // Pack variants always use the two-scale encoding (src/testing.cpp:987-1004)
         const uint64_t inv_first = inv_pow2_mod_Q(c->g), inv_rest = inv_pow2_mod_Q(c->stopround + 1);
         sigma[2 * idx_dim0] = mulmod_u64(scale_k % kQ, inv_first, kQ);
         for (size_t i = 0; i < fd; i++)
@@ -208,6 +226,9 @@ extern "C" int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint3
             for (size_t j = 0; j < ell; j++, ctr++)
                 if ((idx_further >> i) & 1) sigma[dim0 + ctr] = mulmod_u64((1ull << (bits_per * j)) % kQ, inv, kQ);
     }
+    return client_wire_from_sigma(c, sigma, query_id, wire_seed32, wire_out);
+}
+static int client_wire_from_sigma(sb200_client *c, const std::vector<uint64_t> &sigma, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out) {
     DBuf<uint64_t> sig_raw, row1_raw, packed;
     DBuf<uint32_t> sig_ntt, ct;
     CU(sig_raw.alloc(kN)); CU(row1_raw.alloc(kN)); CU(packed.alloc(kWireRowBytes / 8)); CU(sig_ntt.alloc(PLW)); CU(ct.alloc(2 * PLW));
@@ -232,11 +253,125 @@ extern "C" int sb200_client_query_wire(sb200_client *c, size_t idx_target, uint3
 extern "C" int sb200_client_decode(sb200_client *c, const uint64_t *total_resp_host, uint64_t *pt_out_host) {
     if (!c || !total_resp_host || !pt_out_host) return fail(SB200_ERR_ARG, "client_decode: null argument");
     CU(cudaSetDevice(c->device));
+    // Spiral: 3x2 response -> 2x2 plaintext polynomials; Pack variants: (out_n+1) x out_n -> out_n x out_n (item of plane i*out_n + j)
+    const size_t nn = c->pack ? c->prm.out_n : (size_t)kN2, rw = (nn + 1) * nn * (size_t)kN, pw = nn * nn * (size_t)kN;
     DBuf<uint64_t> resp, pt;
-    CU(resp.alloc(6 * (size_t)kN)); CU(pt.alloc(4 * (size_t)kN));
-    CU(cudaMemcpyAsync(resp.p, total_resp_host, 6 * (size_t)kN * 8, cudaMemcpyHostToDevice, c->st));
-    launch_client_decode(pt.p, resp.p, c->Sp_raw.p, sb200_arb_qprime(c->prm.qp_bits), c->prm.p_db, kN2, c->st); CHECK_LAUNCH();
-    CU(cudaMemcpyAsync(pt_out_host, pt.p, 4 * (size_t)kN * 8, cudaMemcpyDeviceToHost, c->st));
+    CU(resp.alloc(rw)); CU(pt.alloc(pw));
+    CU(cudaMemcpyAsync(resp.p, total_resp_host, rw * 8, cudaMemcpyHostToDevice, c->st));
+    launch_client_decode(pt.p, resp.p, c->Sp_raw.p, sb200_arb_qprime(c->prm.qp_bits), c->prm.p_db, (int)nn, c->st); CHECK_LAUNCH();
+    CU(cudaMemcpyAsync(pt_out_host, pt.p, pw * 8, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     return SB200_OK;
+}
+
+
+// ---- SpiralPack / SpiralStreamPack client (testHighRate's client statements, src/testing.cpp:904-1005, 1086-1122) ---------------
+// Same counter-based randomness as the Spiral client; oracle/client_sim.c (so_pack_client_new_chacha) states it in plain C.
+//   keys        S' has out_n rows (keygen(S, Sp, sr, out_n), src/client.cpp:23-47)
+//   v_W[i]      (out_n+1) x t_conv: fresh public key under S' + [0 ; s0 * g_vec in row 1+i]   (:905-912), objects (7, i*t_conv + k)
+//   V           2 x 2*t_conv: column i encrypts s0^2 * G[0][i] (i even) or s0 * G[1][i] (i odd) under s0   (:918-931), objects (5, i)
+//   queries     the packed single ciphertext (:987-1005, wire form as the Spiral client's) or the direct upload (:962-985):
+//               2^nu1 Regev ciphertexts + nu2 GSW ciphertexts (2 x 2*ell), objects (8, ciphertext number)
+//   decode      out_n x out_n products S'_r * resp_row0[c] over q' and the reference's rounding (:1086-1118)
+extern "C" int sb200_pack_client_public_param_polys(const sb200_client *c, size_t *out4) {
+    if (!c || !out4 || !c->pack) return fail(SB200_ERR_ARG, "pack_client_public_param_polys: needs a Pack client");
+    const size_t n = c->prm.out_n;
+    out4[0] = c->g * 2 * c->prm.t_exp; out4[1] = c->n_right * 2 * c->prm.t_exp_right;
+    out4[2] = 2 * 2 * (size_t)c->prm.t_conv; out4[3] = n * (n + 1) * c->prm.t_conv;
+    return SB200_OK;
+}
+extern "C" int sb200_pack_client_public_params(sb200_client *c, uint64_t *W_exp_left, uint64_t *W_exp_right, uint64_t *V, uint64_t *v_W) {
+    if (!c || !v_W || !c->pack) return fail(SB200_ERR_ARG, "pack_client_public_params: needs a Pack client and v_W");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->prm.out_n, mc = c->prm.t_conv;
+    const uint32_t bp = get_bits_per((uint32_t)mc);
+    {   // packing keys
+        DBuf<uint32_t> M, msg, scal;
+        CU(M.alloc((n + 1) * mc * PLW)); CU(msg.alloc(n * PLW)); CU(scal.alloc(n * mc * 2));
+        for (size_t r = 0; r < n; r++) CU(cudaMemcpyAsync(msg.p + r * PLW, c->sr_ntt.p, PLW * 4, cudaMemcpyDeviceToDevice, c->st));
+        for (size_t i = 0; i < n; i++) {
+            std::vector<uint32_t> hs(n * mc * 2, 0);
+            for (size_t k = 0; k < mc; k++) gadget_scalar(bp, k, &hs[(i * mc + k) * 2]);             // the message sits in row 1 + i only
+            CU(cudaMemcpyAsync(scal.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->st));
+            RegevArgs a{};
+            a.key = c->key; a.obj_base = cc_obj(CC_PACK_W, i * mc); a.sub_e = 1; a.R = (int)n; a.out_cols = (int)mc; a.col_begin = 0;
+            a.S = c->Sp_ntt.p; a.msg = msg.p; a.scal = scal.p; a.ncols = (int)mc;
+            launch_client_regev_cols(M.p, a, c->st); CHECK_LAUNCH();
+            TRY(client_matrix_down(c, v_W + i * (n + 1) * mc * PLW, M.p, (n + 1) * mc));           // synchronises: hs may go out of scope
+        }
+    }
+    if (!W_exp_left && !W_exp_right && !V) return SB200_OK;                                        // direct-upload client
+    if (!W_exp_left || !W_exp_right || !V) return fail(SB200_ERR_ARG, "pack_client_public_params: expansion keys and V come together");
+    TRY(client_expansion_keys(c, W_exp_left, c->g, c->prm.t_exp, CC_W_LEFT));
+    TRY(client_expansion_keys(c, W_exp_right, c->n_right, c->prm.t_exp_right, CC_W_RIGHT));
+    {   // V: even columns carry s0^2 * 2^(bp * i/2), odd columns s0 * 2^(bp * i/2)  (G = gadget(2, 2*t_conv))
+        const size_t m = 2 * mc;
+        DBuf<uint32_t> M, s0sq, scal;
+        CU(M.alloc(2 * m * PLW)); CU(s0sq.alloc(PLW)); CU(scal.alloc(mc * 2));
+        std::vector<uint32_t> hs(mc * 2);
+        for (size_t k = 0; k < mc; k++) gadget_scalar(bp, k, &hs[k * 2]);
+        CU(cudaMemcpyAsync(scal.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->st));
+        launch_matmul(s0sq.p, c->sr_ntt.p, c->sr_ntt.p, 1, 1, 1, c->st);
+        RegevArgs a{};
+        a.key = c->key; a.sub_e = 1; a.R = 1; a.out_cols = (int)m; a.S = c->sr_ntt.p; a.scal = scal.p; a.ncols = (int)mc; a.col_stride = 2;
+        a.obj_base = cc_obj(CC_V_CONV, 0); a.col_begin = 0; a.msg = s0sq.p;
+        launch_client_regev_cols(M.p, a, c->st);
+        a.obj_base = cc_obj(CC_V_CONV, 1); a.col_begin = 1; a.msg = c->sr_ntt.p;
+        launch_client_regev_cols(M.p, a, c->st); CHECK_LAUNCH();
+        TRY(client_matrix_down(c, V, M.p, 2 * m));
+    }
+    return SB200_OK;
+}
+extern "C" int sb200_pack_client_query_wire(sb200_client *c, size_t idx_target, uint32_t query_id, const uint8_t *wire_seed32, uint8_t *wire_out) {
+    if (!c || !c->pack) return fail(SB200_ERR_ARG, "pack_client_query_wire: needs a Pack client");
+    return sb200_client_query_wire(c, idx_target, query_id, wire_seed32, wire_out);
+}
+// direct upload: v_firstdim = 2^nu1 ciphertexts (2x1 ref-NTT each), v_folding = nu2 x (2 x 2*ell) ref-NTT - the arguments of
+// sb200_pack_server_answer_direct / _upload_direct.  query_id (< 2^8) selects a fresh block of 2^16 objects per query.
+extern "C" int sb200_pack_client_query_direct(sb200_client *c, size_t idx_target, uint32_t query_id, uint64_t *v_firstdim, uint64_t *v_folding) {
+    if (!c || !c->pack || !v_firstdim) return fail(SB200_ERR_ARG, "pack_client_query_direct: needs a Pack client and output buffers");
+    const sb200_params &p = c->prm;
+    const size_t fd = p.nu2, ell = p.t_gsw, dim0 = (size_t)1 << p.nu1;
+    if (fd && !v_folding) return fail(SB200_ERR_ARG, "pack_client_query_direct: v_folding missing");
+    if (idx_target >= (dim0 << fd)) return fail(SB200_ERR_ARG, "pack_client_query_direct: index %zu outside the 2^%zu records", idx_target, (size_t)(p.nu1 + fd));
+    if (query_id >= 256 || dim0 + 2 * ell * fd > 65536) return fail(SB200_ERR_ARG, "pack_client_query_direct: query_id must be below 2^8");
+    CU(cudaSetDevice(c->device));
+    const size_t idx_dim0 = idx_target >> fd, idx_further = idx_target & (((size_t)1 << fd) - 1);
+    const uint32_t bits_per = get_bits_per((uint32_t)ell), qbase = query_id << 16;
+    const uint64_t scale_k = kQ / p.p_db;
+    DBuf<uint32_t> ones, cts, scal;
+    DBuf<uint64_t> one_raw;
+    CU(ones.alloc(PLW)); CU(one_raw.alloc(kN)); CU(cts.alloc(std::max(dim0 * 2, 2 * 2 * ell) * PLW)); CU(scal.alloc(std::max(dim0, ell) * 2));
+    CU(cudaMemsetAsync(one_raw.p, 0, kN * 8, c->st));
+    const uint64_t one = 1;
+    CU(cudaMemcpyAsync(one_raw.p, &one, 8, cudaMemcpyHostToDevice, c->st));
+    launch_to_ntt(ones.p, one_raw.p, 1, c->st);                                  // NTT of the constant 1
+    {   // first dimension: Regev encryptions of scale_k * [i == idx_dim0]
+        std::vector<uint32_t> hs(dim0 * 2, 0);
+        hs[idx_dim0 * 2] = (uint32_t)(scale_k % kP); hs[idx_dim0 * 2 + 1] = (uint32_t)(scale_k % kB);
+        CU(cudaMemcpyAsync(scal.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->st));
+        RegevArgs a{};
+        a.key = c->key; a.obj_base = cc_obj(CC_QUERY_DIRECT, qbase); a.sub_e = 1; a.R = 1; a.out_cols = (int)dim0; a.col_begin = 0; a.ct_major = 1;
+        a.S = c->sr_ntt.p; a.msg = ones.p; a.scal = scal.p; a.ncols = (int)dim0;
+        launch_client_regev_cols(cts.p, a, c->st); CHECK_LAUNCH();
+        TRY(client_matrix_down(c, v_firstdim, cts.p, dim0 * 2));
+    }
+    for (size_t i = 0; i < fd; i++) {   // GSW ciphertext of bit i: column 2j+1 encrypts val_j = bit * 2^(bits_per j), column 2j encrypts s0 * val_j
+        const uint64_t bit = (idx_further >> i) & 1;
+        std::vector<uint32_t> hs(ell * 2, 0);
+        for (size_t j = 0; j < ell; j++) { const uint64_t val = ((uint64_t)1 << (bits_per * j)) * bit; hs[2 * j] = (uint32_t)(val % kP); hs[2 * j + 1] = (uint32_t)(val % kB); }
+        CU(cudaMemcpyAsync(scal.p, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, c->st));
+        RegevArgs a{};
+        a.key = c->key; a.sub_e = 1; a.R = 1; a.out_cols = (int)(2 * ell); a.S = c->sr_ntt.p; a.scal = scal.p; a.ncols = (int)ell; a.col_stride = 2;
+        a.obj_base = cc_obj(CC_QUERY_DIRECT, qbase + dim0 + i * ell * 2); a.col_begin = 0; a.msg = c->sr_ntt.p;
+        launch_client_regev_cols(cts.p, a, c->st);
+        a.obj_base = cc_obj(CC_QUERY_DIRECT, qbase + dim0 + i * ell * 2 + 1); a.col_begin = 1; a.msg = ones.p;
+        launch_client_regev_cols(cts.p, a, c->st); CHECK_LAUNCH();
+        TRY(client_matrix_down(c, v_folding + i * 2 * 2 * ell * PLW, cts.p, 2 * 2 * ell));
+    }
+    return SB200_OK;
+}
+extern "C" int sb200_pack_client_decode(sb200_client *c, const uint64_t *total_resp_host, uint64_t *pt_out_host) {
+    if (!c || !c->pack) return fail(SB200_ERR_ARG, "pack_client_decode: needs a Pack client");
+    return sb200_client_decode(c, total_resp_host, pt_out_host);
 }

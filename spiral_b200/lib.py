@@ -208,6 +208,12 @@ def load_library():
         "sb200_client_decode": (C.c_int, [vp, u64p, u64p]),
         "sb200_client_secret": (C.c_int, [vp, u64p, u64p]),
         "sb200_client_gaussian_thresholds": (C.c_int, [u64p]),
+        "sb200_pack_client_create": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int, vp]),
+        "sb200_pack_client_public_param_polys": (C.c_int, [vp, C.POINTER(sz)]),
+        "sb200_pack_client_public_params": (C.c_int, [vp, u64p, u64p, u64p, u64p]),
+        "sb200_pack_client_query_wire": (C.c_int, [vp, sz, C.c_uint32, vp, vp]),
+        "sb200_pack_client_query_direct": (C.c_int, [vp, sz, C.c_uint32, u64p, u64p]),
+        "sb200_pack_client_decode": (C.c_int, [vp, u64p, u64p]),
         # wire / on-disk formats
         "sb200_wire_query_bytes": (sz, [C.c_uint32]),
         "sb200_dev_query_from_wire": (C.c_int, [vp, vp, C.c_uint32, vp]),

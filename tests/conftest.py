@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# Several tests run up to 8 shards of a sharded server on ONE device, each on its own streams, with kernels that wait for each
+# other's flags.  With the default 8 hardware queues distinct streams can share a queue, and a waiting kernel then blocks the very
+# kernel it waits for.  Must be set before the CUDA context exists; one process per GPU (the deployed form) never needs it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -137,6 +137,7 @@ def load():
     lib.so_client_new_chacha.argtypes = [C.POINTER(SoParams), u8p]
     lib.so_client_gaussian_thresholds.argtypes = [C.c_void_p, u64p]
     lib.so_client_secret.argtypes = [C.c_void_p, u64p, u64p]
+    lib.so_client_secret_n.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
     lib.so_client_chacha_query_wire.argtypes = [C.c_void_p, sz, C.c_uint32, u8p, u8p]
     _lib = lib
     return lib
