@@ -561,77 +561,121 @@ class SpiralDriver:
 
 
 class PackDriver:
-    """SpiralPack (packed query + expansion) / SpiralStreamPack (direct upload): resident PackServer, out_n^2 planes."""
+    """SpiralPack (packed query + expansion) / SpiralStreamPack (direct upload): resident PackServer, out_n^2 planes.
+    Real keys and queries from the GPU Pack client, planted records, the exchange inside the C-ABI (sb200_pack_server_process).
+    N > 1: SpiralPack shards the second dimension of every plane (tail folds on rank 0); SpiralStreamPack shards whole planes
+    (its 8-column planes cannot be split 8 ways) and every rank uploads only 1/N of the direct-upload query."""
     kernel = "k_scan_pack"
 
     def __init__(self, args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np):
         from spiral_b200 import SpiralParams
+        from spiral_b200.client import PackClient
         from spiral_b200.server import PackServer
         self.torch, self.dist, self.rank, self.world, self.np = torch, dist, rank, world, np
+        self.nu1, self.nu2 = nu1, nu2
         wl = WORKLOADS[cfg]
-        p = wl["prm"]
+        self.p = p = wl["prm"]
         self.direct = wl["direct"]
+        self.shard = "planes" if (self.direct and world > 1) else "nu2"
         prm = SpiralParams(nu1, nu2, p["t_gsw"], p["t_conv"], p["t_exp"], p["t_exp_right"], p["qp_bits"], p["out_n"], p["p_db"])
-        self.srv = srv = PackServer(prm, device=local_rank, rank=rank, world=world)
-        srv.load_random(seed=1000 + rank)
-        rnd_ntt = rnd_ntt_factory(np, 7)
-        n, ell, dim0 = p["out_n"], p["t_gsw"], 1 << nu1
-        nbits = ell * nu2
-        g, stop = ceil_log2(nbits + dim0), ceil_log2(max(nbits, 1))
-        vW = rnd_ntt(n * (n + 1) * p["t_conv"])
-        self.targets = []
+        self.srv = srv = PackServer(prm, device=local_rank, rank=rank, world=world, shard=self.shard)
+        srv.load_random(seed=1000 + (rank if self.shard == "nu2" else 0))
+        self.use_p2p = world > 1
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, srv.xchg_export())
+            srv.xchg_connect(handles)
+        self.client = PackClient(prm, CLIENT_SEED, device=local_rank)
+        self.pub = self.client.public_params(direct=self.direct)
+        srv.set_public_params(*self.pub)
+        self.view_params = lambda: self.pub
+        # planted records: one polynomial per plane at each target index
+        self.planes, self.dim0 = p["out_n"] ** 2, 1 << nu1
+        self.targets = planted_targets(nu1, nu2, world if self.shard == "nu2" else 1)
+        num_per = 1 << nu2
+        for idx in self.targets:
+            j, ii = divmod(idx, num_per)
+            for pl in range(self.planes):
+                if not srv.owns_plane(pl):
+                    continue
+                if self.shard == "nu2":
+                    if ii % world == rank:
+                        srv.set_plane_item(pl, j, ii // world, self.planted(idx)[pl].astype(np.uint16))
+                else:
+                    srv.set_plane_item(pl, j, ii, self.planted(idx)[pl].astype(np.uint16))
+        PL = 2 * N_POLY
         if self.direct:
-            srv.set_public_params(None, None, None, vW)
-            self.vf_host = torch.from_numpy(rnd_ntt(dim0 * 2).view(np.int64)).pin_memory()
-            self.vg_host = torch.from_numpy(rnd_ntt(max(nu2, 1) * 2 * 2 * ell).view(np.int64)).pin_memory()
-            self.h2d_bytes = int((self.vf_host.numel() + self.vg_host.numel()) * 8)
+            self.vf_host = torch.empty(self.dim0 * 2 * PL, dtype=torch.int64).pin_memory()
+            self.vg_host = torch.empty(max(nu2, 1) * 2 * 2 * p["t_gsw"] * PL, dtype=torch.int64).pin_memory()
+            jc = self.dim0 // world
+            self.slice_words = jc * 2 * PL
+            self.h2d_bytes = int((self.slice_words if world > 1 else self.vf_host.numel()) + self.vg_host.numel()) * 8
         else:
-            srv.set_public_params(rnd_ntt(g * 2 * p["t_exp"]), rnd_ntt((stop + 1) * 2 * p["t_exp_right"]), rnd_ntt(2 * 2 * p["t_conv"]), vW)
-            self.view_params = lambda: (rnd_ntt(g * 2 * p["t_exp"]), rnd_ntt((stop + 1) * 2 * p["t_exp_right"]), rnd_ntt(2 * 2 * p["t_conv"]), vW)
-            self.q_host = torch.from_numpy(rnd_ntt(2).view(np.int64)).pin_memory()
+            self.q_host = torch.empty(2 * PL, dtype=torch.int64).pin_memory()
             self.h2d_bytes = int(self.q_host.numel() * 8)
-        words = srv.partial_words
+        self.set_query(self.targets[0], 1)
         self.resp_host = torch.empty(srv.response_words, dtype=torch.int64).pin_memory()
         self.resp_dev = torch.empty(srv.response_words, dtype=torch.int64, device="cuda")
-        self.part = torch.empty(words, dtype=torch.int64, device="cuda")
-        self.gathered = torch.empty(world * words, dtype=torch.int64, device="cuda")
         self.d2h_bytes = int(self.resp_host.numel() * 8)
         self.db_bytes = srv.db_bytes
-        self.use_p2p = False
-        self.exchange = "none (1 GPU)" if world == 1 else f"NCCL all_gather of {srv.planes} surviving 32 KiB ciphertexts per GPU"
+        self.exchange = ("none (1 GPU)" if world == 1 else
+                         (f"plane sharding: peer-memory stores of one folded 32 KiB ciphertext per plane to rank 0 (no fold after the exchange); "
+                          f"the direct-upload query is uploaded 1/{world} per rank and all-gathered by the reorientation kernel over NVLink") if self.shard == "planes"
+                         else f"peer-memory stores of {self.planes} surviving 32 KiB ciphertexts per GPU + flags over NVLink, fused into the stream")
+
+    def planted(self, idx):
+        return self.np.stack([planted_record(self.np, idx * 64 + pl, 1, self.p["p_db"])[0] for pl in range(self.planes)])
+
+    def set_query(self, idx, query_id):
+        torch, np, lib = self.torch, self.np, self.srv.lib
+        if self.direct:
+            vf, vg = self.client.query_direct(idx, query_id % 256)
+            self.vf_host.copy_(torch.from_numpy(vf.view(np.int64)))
+            self.vg_host[:vg.size].copy_(torch.from_numpy(vg.view(np.int64)))
+            return
+        wire = self.client.query_wire(idx, query_id)
+        wdev = torch.zeros(wire.size + 64, dtype=torch.uint8, device="cuda")
+        wdev[:wire.size] = torch.from_numpy(wire).cuda()
+        cv = torch.empty(2 * 2 * N_POLY, dtype=torch.int32, device="cuda")
+        out = torch.empty(2 * 2 * N_POLY, dtype=torch.int64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for rc in (lib.sb200_dev_query_from_wire(cv.data_ptr(), wdev.data_ptr(), 1, st), lib.sb200_dev_ntt_to_ref(out.data_ptr(), cv.data_ptr(), 2, st)):
+            if rc != 0:
+                raise SystemExit("query expansion failed: " + lib.sb200_last_error().decode())
+        torch.cuda.current_stream().synchronize()
+        self.q_host.copy_(out.cpu())
+
+    def decode_matches(self, idx):
+        got = self.client.decode(self.resp_host.numpy().view(self.np.uint64))
+        return bool(self.np.array_equal(got, self.planted(idx)))
 
     def upload(self, stream):
-        if self.direct:   # the already-expanded query: 2^nu1 first-dimension cts + nu2 GSW cts, narrowed + reoriented on arrival
-            self.srv.upload_direct_ptr(self.vf_host.data_ptr(), self.vg_host.data_ptr(), stream)
-        else:
-            self.srv.upload_query_ptr(self.q_host.data_ptr(), stream)
-
-    def stage_convert(self, stream):
         if not self.direct:
-            self.srv.expand_and_convert(stream)
-
-    def stage_scan(self, stream):
-        self.srv.scan(stream)
-
-    def stage_rest(self, stream):
-        srv = self.srv
-        srv.fold_local(stream)
-        if self.world > 1:
-            srv.copy_partial(self.part.data_ptr(), stream)
-            self.dist.all_gather_into_tensor(self.gathered, self.part)
-            if self.rank == 0:
-                srv.fold_tail(self.gathered.data_ptr(), self.resp_dev.data_ptr(), stream)
+            self.srv.upload_query_ptr(self.q_host.data_ptr(), stream)
+        elif self.world > 1:   # this rank's 1/N of the first-dimension ciphertexts; the reorientation kernel all-gathers over NVLink
+            self.srv.upload_direct_split_ptr(self.vf_host.data_ptr() + self.rank * self.slice_words * 8, self.vg_host.data_ptr(), stream)
         else:
-            srv.fold_tail(srv.partial_cts_ptr(), self.resp_dev.data_ptr(), stream)
+            self.srv.upload_direct_ptr(self.vf_host.data_ptr(), self.vg_host.data_ptr(), stream)
+
+    def process(self, stream, marks):
+        self.srv.process(self.resp_dev.data_ptr(), stream, marks)
+
+    def answer_host(self, stream):
+        self.upload(stream)
+        self.srv.process(self.resp_dev.data_ptr(), stream, None)
+        self.resp_host.copy_(self.resp_dev, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
 
     def download(self):
         if self.rank == 0:
             self.resp_host.copy_(self.resp_dev, non_blocking=True)
 
     def check(self, stream):
-        pass
+        if self.world > 1 and self.srv.xchg_error(stream) != 0:
+            raise SystemExit(f"rank {self.rank}: peer exchange timed out (error {self.srv.xchg_error(stream)})")
 
     def close(self):
+        self.client.close()
         self.srv.close()
 
 

@@ -247,6 +247,8 @@ void sb200_pack_server_destroy(sb200_pack_server *srv);
 /* one of the out_n^2 database planes: this shard's 2^nu1 * (2^nu2 / world) items of one polynomial each (u16 coefficients
  * < p_db), j-major: item = j * local_num_per + ii_local */
 int sb200_pack_server_load_plane_items(sb200_pack_server *srv, size_t plane, const uint16_t *pts_host);
+/* one item of a loaded plane replaced in place: first-dimension index j, second-dimension index ii_local inside this shard */
+int sb200_pack_server_set_plane_item(sb200_pack_server *srv, size_t plane, size_t j, size_t ii_local, const uint16_t *poly_host);
 /* the WHOLE plane in the reference's convertDb layout (src/testing.cpp:316-340); the shard's rows are extracted */
 int sb200_pack_server_load_plane_reference(sb200_pack_server *srv, size_t plane, const uint64_t *db_buf_host);
 int sb200_pack_server_load_random(sb200_pack_server *srv, uint64_t seed);     /* synthetic plaintexts generated on the device */

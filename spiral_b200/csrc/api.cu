@@ -437,12 +437,6 @@ extern "C" int sb200_regevToGSW(uint64_t *out, const uint64_t *cv_v, uint32_t t_
     return down_ntt(out, dout.p, (size_t)3 * 3 * t);
 }
 
-namespace sb200 {
-void launch_xchg_push(void *target, void *mine, const uint64_t *ct, unsigned int *epoch, int rank, int world, unsigned int *error, cudaStream_t s);
-void launch_xchg_wait(void *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch, int world, unsigned int *error, cudaStream_t s);
-size_t xchg_buffer_bytes(int world);
-size_t xchg_ack_offset();
-}
 // ---------------------------------------------------------------------------------------------
 // tier 3: resident server
 // ---------------------------------------------------------------------------------------------
@@ -529,8 +523,12 @@ struct sb200_server {
     // j = rank (mod world) and stores them into every rank's query buffer (fused all-gather)
     DBuf<int> lists_es, ct_idx_first_s, poly_idx_first_s;
     std::vector<int> offs_es, cnt_es;
-    std::vector<void *> peer_query, peer_xb;            // every rank's query buffer / exchange header as seen from here
-    bool shard_eligible = false, query_sharded = false;
+    // ... and of the odd chain only the ancestors of the GSW bits b = rank (mod world); its RegevToGSW columns go to every rank
+    DBuf<int> lists_os, ct_idx_bits_s, poly_idx_bits_s, bit_ids_s;
+    std::vector<int> offs_os, cnt_os;
+    int nbits_local = 0;
+    std::vector<void *> peer_query, peer_xb, peer_gsw;  // every rank's query buffer / exchange header / GSW buffer as seen from here
+    bool shard_eligible = false, query_sharded = false, gsw_wait_pending = false;
     // stream = NULL means "the legacy default stream", which cannot be captured: such calls run on this
     // BLOCKING stream instead (implicitly ordered with legacy-default-stream work, e.g. torch's default stream)
     cudaStream_t own_stream = nullptr, aux_stream = nullptr;
@@ -638,7 +636,27 @@ extern "C" int sb200_server_create(sb200_server **out, const sb200_params *prm, 
             A(s->lists_es.alloc(ls.size())); A(s->lists_es.up(ls.data(), ls.size()));
             A(s->ct_idx_first_s.alloc(cl)); A(s->ct_idx_first_s.up(cfs.data(), cl));
             A(s->poly_idx_first_s.alloc(cl)); A(s->poly_idx_first_s.up(pfs.data(), cl));
-            s->shard_eligible = true;
+            std::vector<int> lo_s;
+            s->offs_os.resize(s->g); s->cnt_os.resize(s->g);
+            for (size_t r = 0; r < s->g; r++) {
+                s->offs_os[r] = (int)lo_s.size();
+                const size_t m = std::min((size_t)world, (size_t)1 << r);
+                for (int k = 0; k < s->cnt_o[r]; k++) {
+                    const int i = lo[s->offs_o[r] + k];
+                    if (((size_t)(i / 2)) % m == (size_t)rank % m) lo_s.push_back(i);
+                }
+                s->cnt_os[r] = (int)lo_s.size() - s->offs_os[r];
+            }
+            std::vector<int> cbs, bids;
+            for (size_t b = (size_t)rank; b < nbits; b += (size_t)world) { bids.push_back((int)b); cbs.push_back((int)(2 * b + 1)); }
+            s->nbits_local = (int)bids.size();
+            std::vector<int> pbs(2 * bids.size());
+            for (size_t l = 0; l < bids.size(); l++) { pbs[l] = 2 * cbs[l]; pbs[bids.size() + l] = 2 * cbs[l] + 1; }
+            A(s->lists_os.alloc(std::max(lo_s.size(), (size_t)1))); A(s->lists_os.up(lo_s.data(), lo_s.size()));
+            A(s->ct_idx_bits_s.alloc(std::max(cbs.size(), (size_t)1))); A(s->ct_idx_bits_s.up(cbs.data(), cbs.size()));
+            A(s->poly_idx_bits_s.alloc(std::max(pbs.size(), (size_t)1))); A(s->poly_idx_bits_s.up(pbs.data(), pbs.size()));
+            A(s->bit_ids_s.alloc(std::max(bids.size(), (size_t)1))); A(s->bit_ids_s.up(bids.data(), bids.size()));
+            s->shard_eligible = nbits >= (size_t)world;
         }
     }
     { std::vector<uint16_t> hperm(s->g * kN); build_automorph_perms(hperm.data(), (int)s->g);
@@ -762,6 +780,7 @@ extern "C" int sb200_server_upload_query(sb200_server *s, const uint64_t *query_
     s->wire_kind = 0;
     return SB200_OK;      // the narrowing into cv[0] is the first node of the expand_and_convert stage
 }
+static int join_odd_chain(sb200_server *s, cudaStream_t st);
 // expansion + conversion.  defer_join: the odd chain (GSW bits -> RegevToGSW) is only needed by the folds, so the one-call paths
 // leave it running on the side stream across the scan and join in sb200_server_fold_local.
 static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_join) {
@@ -779,19 +798,39 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
         static const bool skip_odd = [] { const char *e = getenv("SB200_PROFILE_SKIP_ODD_CHAIN"); return e && *e == '1'; }();   // timing experiments only: answers are wrong
         CU(cudaEventRecord(s->ev_fork, main_st));
         CU(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
-        if (!skip_odd) TRY(run_stage(s->g_odd[wk], s->aux_stream, nullptr, nullptr, [&](cudaStream_t st) {
-            LaunchPriority low(false);
+        if (!skip_odd) TRY(run_stage(s->g_odd[wk], s->aux_stream, shard ? (const void *)s->xchg.p : nullptr, nullptr, [&](cudaStream_t st) {
+            // The odd chain's 56-digit rounds are thousands of NTT CTAs; queued in one go they sit AHEAD of the even chain's next
+            // kernels in the block scheduler's FIFO (strict launch priorities starve the odd chain instead, which then spills into
+            // the scan).  Its digit kernels therefore hold a fixed two CTA slots per SM and walk their work list.
+            static const int odd_slots = [] { const char *e = getenv("SB200_ODD_SLOTS"); return e ? atoi(e) : 2; }();
+            LaunchPriority low(false);                  // no-op unless SB200_PRIO=1 (experiments)
             if (wk) launch_query_from_wire(s->cv_o.p, s->q_wire.p, s->wire_kind, st);
             else launch_ntt_u64_to_dev(s->cv_o.p, s->q_stage.p, 2, st);
+            if (shard) {
+                launch_expand(s->cv_o.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_os.p,
+                              s->offs_os.data(), s->cnt_os.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148);
+                GswTargets tg{};
+                tg.ntargets = s->world;
+                for (int t = 0; t < s->world; t++) {
+                    const int r = (s->rank + t) % s->world;
+                    tg.gsw[t] = (uint32_t *)s->peer_gsw[r];
+                    tg.flag[t] = xchg_gflag_ptr(s->peer_xb[r], s->rank);
+                }
+                tg.arrive = xchg_arrive_aux_ptr(s->xchg.p); tg.ack = xchg_ack_ptr(s->xchg.p);
+                tg.epoch = s->xchg_state.p; tg.error = s->xchg_state.p + 1;
+                launch_regev_to_gsw_sharded(tg, s->cv_o.p, s->ct_idx_bits_s.p, s->poly_idx_bits_s.p, s->bit_ids_s.p, s->nbits_local, (int)s->prm.nu2,
+                                            (int)s->prm.t_gsw, s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, st);
+                return;
+            }
             launch_expand(s->cv_o.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_o.p,
-                          s->offs_o.data(), s->cnt_o.data(), st, 0, (int)s->stopround + 1, 1, 1);
+                          s->offs_o.data(), s->cnt_o.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148);
             // no GSW negation on the resident path: the fold uses the CMux form (launch_fold_round_generic)
             launch_regev_to_gsw(s->gsw.p, nullptr, s->cv_o.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
                                 s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, st);
         }));
         CU(cudaEventRecord(s->ev_join, s->aux_stream));
         TRY(run_stage(s->g_even[wk], main_st, shard ? (const void *)s->xchg.p : nullptr, nullptr, [&](cudaStream_t st) {
-            LaunchPriority high(true);
+            LaunchPriority high(true);                  // no-op unless SB200_PRIO=1 (experiments)
             if (wk) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);     // wire query -> cv[0]
             else launch_ntt_u64_to_dev(s->cv.p, s->q_stage.p, 2, st);                   // uploaded query (ref-NTT) -> cv[0]
             if (!shard) {
@@ -816,8 +855,9 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
                                        s->W_conv.p, s->conv_raw.p, s->conv_ntt.p, st);
         }));
         s->query_sharded = shard;
+        s->gsw_wait_pending = shard;
         if (defer_join) s->join_pending = true;
-        else CU(cudaStreamWaitEvent(main_st, s->ev_join, 0));
+        else { s->join_pending = true; TRY(join_odd_chain(s, main_st)); }
         return SB200_OK;
     }
     s->query_sharded = false;
@@ -847,13 +887,17 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) { 
 extern "C" int sb200_server_expansion_sharded(const sb200_server *s) { return s && s->query_sharded; }
 static int join_odd_chain(sb200_server *s, cudaStream_t st) {
     if (s->join_pending) { CU(cudaStreamWaitEvent(st, s->ev_join, 0)); s->join_pending = false; }
+    if (s->gsw_wait_pending) {                               // sharded conversion: every rank's GSW columns must have landed here
+        launch_flag_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, 1, 0, st);
+        s->gsw_wait_pending = false;
+    }
     return SB200_OK;
 }
 extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan: database not loaded");
     // sharded expansion: every rank's slice of the query must have landed in this rank's buffer
-    if (s->query_sharded) launch_query_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, ES(s, stream));
+    if (s->query_sharded) launch_flag_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, 0, 0, ES(s, stream));
     launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, ES(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
@@ -999,18 +1043,20 @@ extern "C" int sb200_server_fold_tail(sb200_server *s, uint64_t *gathered, uint6
     });
 }
 // ---- peer-memory exchange: setup -----------------------------------------------------------------
-extern "C" size_t sb200_server_xchg_handle_bytes(void) { return 2 * sizeof(cudaIpcMemHandle_t); }
-// a rank's handle = its exchange buffer + its query buffer (the sharded expansion stores converted query slices into the peers')
+extern "C" size_t sb200_server_xchg_handle_bytes(void) { return 3 * sizeof(cudaIpcMemHandle_t); }
+// a rank's handle = its exchange buffer + its query buffer + its GSW buffer (the sharded expansion stores converted query slices
+// and GSW columns into the peers')
 extern "C" int sb200_server_xchg_export(sb200_server *s, void *handle_out) {
     if (!s || !handle_out || s->world < 2) return fail(SB200_ERR_ARG, "xchg_export: needs a sharded server");
-    cudaIpcMemHandle_t h[2];
+    cudaIpcMemHandle_t h[3];
     CU(cudaIpcGetMemHandle(&h[0], s->xchg.p));
     CU(cudaIpcGetMemHandle(&h[1], s->query.p));
+    CU(cudaIpcGetMemHandle(&h[2], s->gsw.p));
     memcpy(handle_out, h, sizeof h);
     return SB200_OK;
 }
-static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs, const std::vector<void *> &queries) {
-    s->peer_xb = bufs; s->peer_query = queries;
+static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs, const std::vector<void *> &queries, const std::vector<void *> &gsws) {
+    s->peer_xb = bufs; s->peer_query = queries; s->peer_gsw = gsws;
     s->xchg_target = bufs[0];
     if (s->rank == 0) {
         std::vector<unsigned int *> acks(s->world);
@@ -1023,25 +1069,26 @@ static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs,
 // all_handles: world handles in rank order (each rank's sb200_server_xchg_export), one process per GPU
 extern "C" int sb200_server_xchg_connect(sb200_server *s, const void *all_handles) {
     if (!s || !all_handles || s->world < 2) return fail(SB200_ERR_ARG, "xchg_connect: needs a sharded server");
-    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr);
+    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr), gsws(s->world, nullptr);
     for (int r = 0; r < s->world; r++) {
-        if (r == s->rank) { bufs[r] = s->xchg.p; queries[r] = s->query.p; continue; }
-        cudaIpcMemHandle_t h[2];
+        if (r == s->rank) { bufs[r] = s->xchg.p; queries[r] = s->query.p; gsws[r] = s->gsw.p; continue; }
+        cudaIpcMemHandle_t h[3];
         memcpy(h, reinterpret_cast<const uint8_t *>(all_handles) + (size_t)r * sizeof h, sizeof h);
-        void *pb = nullptr, *pq = nullptr;
+        void *pb = nullptr, *pq = nullptr, *pg = nullptr;
         CU(cudaIpcOpenMemHandle(&pb, h[0], cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pb);
         CU(cudaIpcOpenMemHandle(&pq, h[1], cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pq);
-        bufs[r] = pb; queries[r] = pq;
+        CU(cudaIpcOpenMemHandle(&pg, h[2], cudaIpcMemLazyEnablePeerAccess)); s->ipc_opened.push_back(pg);
+        bufs[r] = pb; queries[r] = pq; gsws[r] = pg;
     }
-    return xchg_finish_connect(s, bufs, queries);
+    return xchg_finish_connect(s, bufs, queries, gsws);
 }
 // same-process variant (several shards driven from one process, e.g. tests on one device): direct pointers
 extern "C" int sb200_server_xchg_connect_local(sb200_server *s, sb200_server *const *all_servers) {
     if (!s || !all_servers || s->world < 2) return fail(SB200_ERR_ARG, "xchg_connect_local: needs a sharded server");
-    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr);
+    std::vector<void *> bufs(s->world, nullptr), queries(s->world, nullptr), gsws(s->world, nullptr);
     for (int r = 0; r < s->world; r++) {
         if (!all_servers[r] || all_servers[r]->world != s->world || all_servers[r]->rank != r) return fail(SB200_ERR_ARG, "xchg_connect_local: server %d mismatched", r);
-        bufs[r] = all_servers[r]->xchg.p; queries[r] = all_servers[r]->query.p;
+        bufs[r] = all_servers[r]->xchg.p; queries[r] = all_servers[r]->query.p; gsws[r] = all_servers[r]->gsw.p;
         if (all_servers[r]->device != s->device) {
             int can = 0;
             CU(cudaDeviceCanAccessPeer(&can, s->device, all_servers[r]->device));
@@ -1051,7 +1098,7 @@ extern "C" int sb200_server_xchg_connect_local(sb200_server *s, sb200_server *co
             cudaGetLastError();
         }
     }
-    return xchg_finish_connect(s, bufs, queries);
+    return xchg_finish_connect(s, bufs, queries, gsws);
 }
 // every rank: push the surviving ciphertext into rank 0's HBM; rank 0 additionally waits for all shards, runs the
 // tail folds and the modulus switch into resp_dev (ignored on other ranks)
@@ -1061,12 +1108,15 @@ extern "C" int sb200_server_exchange_and_tail(sb200_server *s, uint64_t *resp_de
     if (!s->xchg_connected) return fail(SB200_ERR_STATE, "exchange_and_tail: peers not connected (sb200_server_xchg_connect)");
     if (s->rank == 0 && !resp_dev) return fail(SB200_ERR_ARG, "exchange_and_tail: rank 0 needs a response buffer");
     TRY(join_odd_chain(s, ES(s, stream)));
-    return run_stage(s->g_xchg, ES(s, stream), resp_dev, nullptr, [&](cudaStream_t st) {
+    const bool late_ack = s->query_sharded;       // sharded expansion: peers write into this rank's query / GSW buffers, so rank 0
+                                                  // acknowledges only once its tail folds no longer read them
+    return run_stage(s->g_xchg, ES(s, stream), resp_dev, late_ack ? (const void *)s->xchg.p : nullptr, [&](cudaStream_t st) {
         launch_xchg_push(s->xchg_target, s->xchg.p, s->cts.p, s->xchg_state.p, s->rank, s->world, s->xchg_state.p + 1, st);
         if (s->rank == 0) {
-            launch_xchg_wait(s->xchg.p, s->xchg_acks.p, s->gathered.p, s->xchg_state.p, s->world, s->xchg_state.p + 1, st);
+            launch_xchg_wait(s->xchg.p, s->xchg_acks.p, s->gathered.p, s->xchg_state.p, s->world, s->xchg_state.p + 1, st, late_ack ? 0 : 1);
             fold_rounds(s, s->gathered.p, (size_t)s->world, s->prm.nu2 - s->log_world, st);
             launch_rescale2(resp_dev, s->gathered.p, 2 * (size_t)kN, 4 * (size_t)kN, kQ, sb200_arb_qprime(s->prm.qp_bits), 4 * s->prm.p_db, st);
+            if (late_ack) launch_xchg_ack(s->xchg_acks.p, s->xchg_state.p, s->world, s->xchg_state.p + 1, st);
         }
     });
 }

@@ -4,6 +4,7 @@
 namespace sb200 {
 void launch_db_build_pack(uint64_t *db_plane, const uint16_t *pts_plane, size_t dim0, size_t num_per, uint32_t p_db, cudaStream_t s);
 void launch_reorient_dim1(uint64_t *out, const uint32_t *cv, const int *ct_idx, size_t dim0, cudaStream_t s);
+void launch_db_set_item_pack(uint64_t *db_plane, const uint16_t *poly, size_t dim0, size_t num_per, uint32_t p_db, size_t i, size_t j, cudaStream_t s);
 void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, size_t planes,
                       size_t db_plane_words, size_t out_plane_polys, cudaStream_t s);
 void launch_regev_to_simple_gsw(uint32_t *gsw_out, uint32_t *gsw_neg_out, const uint32_t *cv, const int *ct_idx, const int *poly_idx,
@@ -293,6 +294,21 @@ extern "C" int sb200_pack_server_load_plane_items(sb200_pack_server *s, size_t p
     launch_db_build_pack(s->db.p + plane * s->plane_words, d.p, s->dim0, s->local_num_per, (uint32_t)s->prm.p_db, 0); CHECK_LAUNCH();
     CU(cudaDeviceSynchronize());
     s->plane_loaded[plane] = true;
+    return SB200_OK;
+}
+// one item of a loaded plane replaced: first-dimension index j, second-dimension index ii_local inside this shard (global
+// ii = rank + world * ii_local under second-dimension sharding), its polynomial as 2048 u16 coefficients < p_db
+extern "C" int sb200_pack_server_set_plane_item(sb200_pack_server *s, size_t plane, size_t j, size_t ii_local, const uint16_t *poly_host) {
+    if (!s || !poly_host || plane >= s->planes_total || j >= s->dim0 || ii_local >= s->local_num_per) return fail(SB200_ERR_ARG, "set_plane_item: bad argument");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
+    if (s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "set_plane_item: plane %zu lives on rank %zu (plane sharding)", plane, plane % s->world);
+    const size_t lp = (size_t)s->local_plane(plane);
+    if (!s->plane_loaded[lp]) return fail(SB200_ERR_STATE, "set_plane_item: plane %zu not loaded", plane);
+    CU(cudaSetDevice(s->device));
+    DBuf<uint16_t> d(kN);
+    CU(d.up(poly_host, kN));
+    launch_db_set_item_pack(s->db.p + lp * s->plane_words, d.p, s->dim0, s->local_num_per, (uint32_t)s->prm.p_db, ii_local, j, 0); CHECK_LAUNCH();
+    CU(cudaDeviceSynchronize());
     return SB200_OK;
 }
 // db_buf: the WHOLE plane in the reference's convertDb layout db_buf[z][ii][j]; the shard's rows ii = rank (mod world) are taken

@@ -68,6 +68,32 @@ void launch_db_build_pack(uint64_t *db_plane, const uint16_t *pts_plane, size_t 
     count_launch(); launch_pdl(k_db_build_pack, dim3(dim3((unsigned)((num_per + 1) / 2), (unsigned)(dim0 / 2))), dim3(kNttThreads), smem, s, db_plane, pts_plane, (int)dim0, (int)num_per, p_db);
 }
 
+// one item of a plane replaced in place (planting known records in a synthetic database): centre-lift + NTT of its polynomial,
+// then its 2048 words go to DBP[z][j/2][i][j&1]
+__global__ void __launch_bounds__(kNttThreads) k_db_set_item_pack(uint64_t *__restrict__ db, const uint16_t *__restrict__ poly,
+                                                                  int dim0, int num_per, uint32_t p_db, int i, int j) {
+    pdl_prologue();
+    __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
+    __shared__ __align__(16) uint32_t stash[2][kN];
+    const int n = plane_of_thread(), lt = lane_in_plane();
+    const uint32_t q = modulus(n);
+    uint32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t c = poly[nat_pos(lt, k)];
+        v[k] = (c >= p_db / 2) ? (q - ((p_db - c) % q)) % q : c % q;
+    }
+    ntt_forward_plane(v, sm[n], lt, n);
+    store_ntt_regs(v, stash[n], lt);
+    __syncthreads();
+    const size_t JP = dim0 / 2;
+    for (int z = threadIdx.x; z < kN; z += kNttThreads)
+        db[(((size_t)z * JP + j / 2) * num_per + i) * 2 + (j & 1)] = pack_pb3(stash[0][z], stash[1][z]);
+}
+void launch_db_set_item_pack(uint64_t *db_plane, const uint16_t *poly, size_t dim0, size_t num_per, uint32_t p_db, size_t i, size_t j, cudaStream_t s) {
+    count_launch(); launch_pdl(k_db_set_item_pack, dim3(1), dim3(kNttThreads), 0, s, db_plane, poly, (int)dim0, (int)num_per, p_db, (int)i, (int)j);
+}
+
 // ============================================================================================
 // reorientCiphertextsDim1: selected 2x1 dev-NTT cts -> query[z][j][r] PB64
 // ============================================================================================

@@ -86,24 +86,30 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
 }
 
 __global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restrict__ ginv, const uint64_t *__restrict__ c0_raw,
-                                                               const int *__restrict__ active, int t_left, int t_right, int tmax) {
+                                                               const int *__restrict__ active, int t_left, int t_right, int tmax, int cnt) {
     pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
-    const int slot = blockIdx.x, k = blockIdx.y, i = active[slot];
-    const int gd = (i & 1) ? t_right : t_left;
-    if (k >= gd) return;
-    const uint32_t bits_per = get_bits_per(gd);
-    const uint64_t mask = (1ull << bits_per) - 1;
-    const uint64_t *src = c0_raw + (size_t)slot * kN;
-    uint32_t v[16];
+    // grid (cnt, tmax), or - for a chain that must not crowd out a concurrent, more urgent one - a smaller 1-D grid whose CTAs
+    // walk the cnt x tmax items: the kernel then holds a fixed number of CTA slots instead of queueing thousands of CTAs ahead
+    // of the other chain's
+    const int total = cnt * tmax;
+    for (int item = gridDim.y > 1 ? (int)(blockIdx.x * gridDim.y + blockIdx.y) : (int)blockIdx.x; item < total; item += gridDim.y > 1 ? total : (int)gridDim.x) {
+        const int slot = item / tmax, k = item % tmax, i = active[slot];
+        const int gd = (i & 1) ? t_right : t_left;
+        if (k >= gd) continue;
+        const uint32_t bits_per = get_bits_per(gd);
+        const uint64_t mask = (1ull << bits_per) - 1;
+        const uint64_t *src = c0_raw + (size_t)slot * kN;
+        uint32_t v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const uint64_t d = gadget_digit(__ldg(src + nat_pos(lt, e)), k, bits_per, mask);
-        v[e] = bits_per >= 28 ? raw_to_res(d, n) : (uint32_t)d;
+        for (int e = 0; e < 16; e++) {
+            const uint64_t d = gadget_digit(__ldg(src + nat_pos(lt, e)), k, bits_per, mask);
+            v[e] = bits_per >= 28 ? raw_to_res(d, n) : (uint32_t)d;
+        }
+        ntt_forward_plane(v, sm[n], lt, n);
+        store_ntt_regs(v, ginv + (((size_t)slot * tmax + k) * 2 + n) * kN, lt);
     }
-    ntt_forward_plane(v, sm[n], lt, n);
-    store_ntt_regs(v, ginv + (((size_t)slot * tmax + k) * 2 + n) * kN, lt);
 }
 
 __global__ void __launch_bounds__(256) k_expand_accum(uint32_t *__restrict__ cv, const int *__restrict__ active, const uint32_t *__restrict__ ginv,
@@ -285,7 +291,7 @@ size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt) {
 }
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
                    const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
-                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end, int parity, int store_self) {
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end, int parity, int store_self, int slot_limit) {
     // parity: -1 = the lists hold every active ciphertext; 0 / 1 = they hold only the even / odd ones (expand_split_lists):
     // after round 0 the even chain (first-dimension ciphertexts, t_left digits) and the odd chain (GSW bits, t_right digits)
     // never touch each other's ciphertexts, so the two can run on different streams with their own scratch.
@@ -302,7 +308,9 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         const int ty = parity == 1 ? p.t_right : any_odd ? tmax : p.t_left;
         count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, neg1 + (size_t)(p.g + r) * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt, store_self);
         // ginv is indexed [slot][ty]: rounds past stopround only hold t_left digits per slot (see expand_ginv_polys)
-        count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty);
+        count_launch();
+        if (slot_limit > 0 && cnt[r] * ty > slot_limit) launch_pdl(k_expand_digits, dim3(slot_limit), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty, cnt[r]);
+        else launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty, cnt[r]);
         count_launch();                                   // rounds with right slots (56-term chains) stay on the split kernel
         if (((cnt[r] >= 64 && !any_odd) || cnt[r] >= 512) && tmax <= 128) launch_pdl(k_expand_accum_wide, dim3(dim3(cnt[r], 4)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
         else launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
@@ -561,6 +569,84 @@ __global__ void k_regev_to_gsw_accum(uint32_t *__restrict__ gsw, const uint32_t 
     }
 }
 
+// The same for a rank's share of a sharded conversion: `count` bits, local bit l is the global bit bit_ids[l] (the ciphertexts of
+// the odd chain this rank expanded); the 9 words of every (bit, slot) go into the GSW buffer of EVERY rank (peer pointers), and
+// the last CTA raises this rank's flag on each (gflags; k_flag_wait before the folds is the consumer side).
+struct GswTargets {
+    uint32_t *gsw[16];
+    unsigned int *flag[16];
+    int ntargets;
+    unsigned int *arrive;
+    const unsigned int *ack, *epoch;
+    unsigned int *error;
+};
+__global__ void __launch_bounds__(256) k_regev_to_gsw_accum_sharded(const __grid_constant__ GswTargets tg, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
+                                                                    const int *__restrict__ bit_ids, const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W,
+                                                                    const uint32_t *__restrict__ V, int t_conv, int ell, int nu2, int count) {
+    pdl_prologue();
+    __shared__ int ok;
+    unsigned int e = 0;
+    if (threadIdx.x == 0) {        // the peers' GSW buffers are free once rank 0 has finished the previous query (its acknowledgement)
+        e = *tg.epoch + 1;
+        ok = 1;
+        if (e > 1) {
+            unsigned long long t0 = global_timer_ns();
+            while ((int)(ld_acquire_sys_u32(tg.ack) - (e - 1)) < 0) {
+                __nanosleep(200);
+                if (global_timer_ns() - t0 > 4000000000ull) { ok = 0; break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (!ok) { if (threadIdx.x == 0) *tg.error = 4; return; }
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (l, n, z)
+    if (idx < (size_t)count * 2 * kN) {
+        const int nz = (int)(idx % (2 * kN)), l = (int)(idx / (2 * kN)), n = nz >= kN;
+        const int b = bit_ids[l], d = b / ell, jj = b % ell, wc = 2 * t_conv, m2 = 3 * ell;
+        uint64_t s2m[3][2] = {{0, 0}, {0, 0}, {0, 0}}, pr[3] = {0, 0, 0};
+        for (int k = 0; k < t_conv; k++) {
+            const uint32_t g0 = ginv[(((size_t)0 * t_conv + k) * count + l) * 2 * kN + nz];
+            const uint32_t g1 = ginv[(((size_t)1 * t_conv + k) * count + l) * 2 * kN + nz];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                pr[r] += (uint64_t)V[((size_t)r * wc + k) * 2 * kN + nz] * g0 + (uint64_t)V[((size_t)r * wc + t_conv + k) * 2 * kN + nz] * g1;
+#pragma unroll
+                for (int c = 0; c < 2; c++) s2m[r][c] += (uint64_t)W[((size_t)r * wc + 2 * k + c) * 2 * kN + nz] * g0;
+            }
+            if ((k & 63) == 63) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    pr[r] = reduce_u64(pr[r], n);
+#pragma unroll
+                    for (int c = 0; c < 2; c++) s2m[r][c] = reduce_u64(s2m[r][c], n);
+                }
+            }
+        }
+        const uint32_t c1 = cv[((size_t)ct_idx[l] * 2 + 1) * 2 * kN + nz];
+        s2m[1][0] += c1; s2m[2][1] += c1;
+        const size_t base = (size_t)(nu2 - 1 - d) * 3 * m2 * 2 * kN;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const uint32_t v0 = reduce_u64(pr[r], n), v1 = reduce_u64(s2m[r][0], n), v2 = reduce_u64(s2m[r][1], n);
+            const size_t o = base + ((size_t)r * m2 + 3 * jj) * 2 * kN + nz;
+            for (int t = 0; t < tg.ntargets; t++) {
+                uint32_t *g = tg.gsw[t];
+                g[o] = v0; g[o + 2 * kN] = v1; g[o + 4 * kN] = v2;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(tg.arrive, 1u) == gridDim.x - 1) {
+            *tg.arrive = 0;
+            __threadfence_system();
+            for (int t = 0; t < tg.ntargets; t++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tg.flag[t]), "r"(e) : "memory");
+        }
+    }
+}
+
 // GSW negation: Qneg = NTT(G2 - from_ntt(Q))  per polynomial (d, r, m); G2 = buildGadget(n1, m2)
 // (reference src/spiral.cpp:2361-2378; `long` subtraction, +Q when negative)
 __global__ void __launch_bounds__(kNttThreads) k_gsw_negate(uint32_t *__restrict__ neg, const uint32_t *__restrict__ gsw, int ell, int rows) {
@@ -595,6 +681,16 @@ __global__ void __launch_bounds__(kNttThreads) k_gsw_negate(uint32_t *__restrict
     for (int k = 0; k < 16; k++) v[k] = au[n][nat_pos(lt, k)];
     ntt_forward_plane(v, sm[n], lt, n);
     store_ntt_regs(v, neg + ((size_t)poly * 2 + n) * kN, lt);
+}
+// poly_idx: 2*count entries (row-0 polynomials of this rank's bit ciphertexts, then their row-1 polynomials)
+void launch_regev_to_gsw_sharded(const GswTargets &tg, const uint32_t *cv, const int *ct_idx, const int *poly_idx, const int *bit_ids, int count,
+                                 int nu2, int t_gsw, const uint32_t *W, const uint32_t *V, int t_conv, uint64_t *scratch_raw, uint32_t *scratch_ntt, cudaStream_t s) {
+    if (!count) return;
+    launch_from_ntt_indexed(scratch_raw, cv, poly_idx, 2 * (size_t)count, s);
+    launch_gadget_ntt(scratch_ntt, scratch_raw, t_conv, 1, count, s);
+    launch_gadget_ntt(scratch_ntt + (size_t)t_conv * count * 2 * kN, scratch_raw + (size_t)count * kN, t_conv, 1, count, s);
+    const size_t n = (size_t)count * 2 * kN;
+    count_launch(); launch_pdl(k_regev_to_gsw_accum_sharded, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, tg, cv, ct_idx, bit_ids, scratch_ntt, W, V, t_conv, t_gsw, nu2, count);
 }
 void launch_gsw_negate(uint32_t *neg, const uint32_t *gsw, int count, int ell, int rows, cudaStream_t s) {
     const int polys = count * rows * rows * ell;

@@ -24,8 +24,10 @@ struct XchgBuf {                 // lives in ONE cudaMalloc allocation per rank 
     unsigned int flags[kXchgSlots][kXchgMaxWorld];
     unsigned int ack;            // last epoch rank 0 has consumed (written remotely by rank 0)
     unsigned int arrive[2];      // CTA arrival counters of this rank's multi-CTA push / wait kernels
-    unsigned int qflags[kXchgMaxWorld];   // query all-gather (Pack direct upload): epoch of the slice rank r has stored here
-    unsigned int pad[13];
+    unsigned int qflags[kXchgMaxWorld];   // query all-gather (sharded expansion / Pack direct upload): epoch of the slice rank r has stored here
+    unsigned int gflags[kXchgMaxWorld];   // GSW all-gather (sharded RegevToGSW): epoch of the columns rank r has stored here
+    unsigned int arrive_aux;              // CTA arrival counter of kernels on the side stream
+    unsigned int pad[12];
     // followed by slots[kXchgSlots][world][slot_words] u64 (only rank 0's copy is used as the target)
 };
 static_assert(sizeof(XchgBuf) % 16 == 0, "slots must stay 16-byte aligned");
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(1024) k_xchg_push(XchgBuf *target, XchgBuf *mi
 // rank 0 only: `mine` = rank 0's XchgBuf, `acks[r]` = pointer to rank r's XchgBuf::ack (peer mappings), out = world x slot_words.
 // gridDim.x CTAs: each waits for all flags, copies its share of the slots into the private buffer; the last one acknowledges.
 __global__ void __launch_bounds__(1024) k_xchg_wait(XchgBuf *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch,
-                                                    int world, unsigned int *error, size_t slot_words) {
+                                                    int world, unsigned int *error, size_t slot_words, int ack_now) {
     pdl_prologue();
     __shared__ int ok;
     const unsigned int e = *epoch;                 // already advanced by this rank's own push (same stream)
@@ -111,9 +113,22 @@ __global__ void __launch_bounds__(1024) k_xchg_wait(XchgBuf *mine, unsigned int 
         if (atomicAdd(&mine->arrive[1], 1u) == gridDim.x - 1) {
             mine->arrive[1] = 0;
             __threadfence_system();
-            if (ld_acquire_sys(error) == 0) for (int r = 0; r < world; r++) st_release_sys(acks[r], e);
+            if (ack_now && ld_acquire_sys(error) == 0) for (int r = 0; r < world; r++) st_release_sys(acks[r], e);
         }
     }
+}
+// rank 0, at the very END of a query whose expansion was sharded: the acknowledgement that lets the other ranks overwrite this
+// rank's query and GSW buffers (with it sent right after the gather, rank 0's tail folds could still be reading the GSW ciphertexts)
+__global__ void k_xchg_ack(unsigned int *const *acks, const unsigned int *epoch, int world, const unsigned int *error) {
+    pdl_prologue();
+    if ((int)threadIdx.x < world && ld_acquire_sys(error) == 0) { __threadfence_system(); st_release_sys(acks[threadIdx.x], *epoch); }
+}
+// waits until all `world` flags of this rank's header (qflags: which = 0, gflags: which = 1) have reached the current query
+__global__ void k_flag_wait(XchgBuf *mine, int world, const unsigned int *epoch, unsigned int *error, int which, int advanced) {
+    pdl_prologue();
+    const unsigned int e = *epoch + (advanced ? 0u : 1u);          // advanced: this rank's push of the query has already run
+    const unsigned int *f = which ? mine->gflags : mine->qflags;
+    if ((int)threadIdx.x < world && !spin_until_ge(&f[threadIdx.x], e)) *error = 3 + which;
 }
 
 static inline unsigned xchg_grid(size_t words) { size_t g = (words * 8 + 131071) / 131072; return (unsigned)(g < 1 ? 1 : g > 32 ? 32 : g); }   // ~128 KiB per CTA
@@ -123,15 +138,21 @@ void launch_xchg_push_w(void *target, void *mine, const uint64_t *ct, unsigned i
     launch_pdl(k_xchg_push, dim3(xchg_grid(words)), dim3(1024), 0, s, (XchgBuf *)target, (XchgBuf *)mine, ct, epoch, rank, world, error, words, slot_words);
 }
 void launch_xchg_wait_w(void *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch, int world, unsigned int *error,
-                        size_t slot_words, cudaStream_t s) {
+                        size_t slot_words, cudaStream_t s, int ack_now = 1) {
     count_launch();
-    launch_pdl(k_xchg_wait, dim3(xchg_grid((size_t)world * slot_words)), dim3(1024), 0, s, (XchgBuf *)mine, acks, out, epoch, world, error, slot_words);
+    launch_pdl(k_xchg_wait, dim3(xchg_grid((size_t)world * slot_words)), dim3(1024), 0, s, (XchgBuf *)mine, acks, out, epoch, world, error, slot_words, ack_now);
+}
+void launch_xchg_ack(unsigned int *const *acks, const unsigned int *epoch, int world, const unsigned int *error, cudaStream_t s) {
+    count_launch(); launch_pdl(k_xchg_ack, dim3(1), dim3(32), 0, s, acks, epoch, world, error);
+}
+void launch_flag_wait(void *mine, int world, const unsigned int *epoch, unsigned int *error, int which, int advanced, cudaStream_t s) {
+    count_launch(); launch_pdl(k_flag_wait, dim3(1), dim3(32), 0, s, (XchgBuf *)mine, world, epoch, error, which, advanced);
 }
 void launch_xchg_push(void *target, void *mine, const uint64_t *ct, unsigned int *epoch, int rank, int world, unsigned int *error, cudaStream_t s) {
     launch_xchg_push_w(target, mine, ct, epoch, rank, world, error, kCtWords, kCtWords, s);
 }
-void launch_xchg_wait(void *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch, int world, unsigned int *error, cudaStream_t s) {
-    launch_xchg_wait_w(mine, acks, out, epoch, world, error, kCtWords, s);
+void launch_xchg_wait(void *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch, int world, unsigned int *error, cudaStream_t s, int ack_now = 1) {
+    launch_xchg_wait_w(mine, acks, out, epoch, world, error, kCtWords, s, ack_now);
 }
 size_t xchg_buffer_bytes(int world) { return xchg_bytes(world); }
 size_t xchg_buffer_bytes_w(int world, size_t slot_words) { return xchg_bytes_w(world, slot_words); }
@@ -140,6 +161,8 @@ size_t xchg_header_bytes() { return sizeof(XchgBuf); }
 unsigned int *xchg_qflag_ptr(void *buf, int rank) { return &reinterpret_cast<XchgBuf *>(buf)->qflags[rank]; }   // address arithmetic only
 unsigned int *xchg_arrive_ptr(void *buf, int k) { return &reinterpret_cast<XchgBuf *>(buf)->arrive[k]; }
 unsigned int *xchg_ack_ptr(void *buf) { return &reinterpret_cast<XchgBuf *>(buf)->ack; }
+unsigned int *xchg_gflag_ptr(void *buf, int rank) { return &reinterpret_cast<XchgBuf *>(buf)->gflags[rank]; }
+unsigned int *xchg_arrive_aux_ptr(void *buf) { return &reinterpret_cast<XchgBuf *>(buf)->arrive_aux; }
 
 // ---- query all-gather over peer memory (Pack direct upload, sharded): every rank uploads and reorients only its 1/world
 // slice of the first-dimension ciphertexts and stores it into EVERY rank's query buffer, then raises qflags[rank] there;

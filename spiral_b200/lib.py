@@ -145,6 +145,7 @@ def load_library():
         "sb200_pack_server_download": (C.c_int, [vp, vp, vp, sz, vp]),
         "sb200_pack_server_load_plane_items": (C.c_int, [vp, sz, u16p]),
         "sb200_pack_server_load_plane_reference": (C.c_int, [vp, sz, u64p]),
+        "sb200_pack_server_set_plane_item": (C.c_int, [vp, sz, sz, sz, u16p]),
         "sb200_pack_server_load_random": (C.c_int, [vp, C.c_uint64]),
         "sb200_pack_server_set_public_params": (C.c_int, [vp, u64p, u64p, u64p, u64p]),
         "sb200_pack_server_answer": (C.c_int, [vp, vp, vp, vp, vp]),

@@ -284,6 +284,12 @@ class PackServer:
         assert pts_u16.size == self.dim0 * self.local_num_per * N
         check(self.lib.sb200_pack_server_load_plane_items(self.h, plane, pts_u16.ctypes.data_as(_P16)), self.lib)
 
+    def set_plane_item(self, plane, j, ii_local, poly_u16):
+        """Replace one item of a loaded plane (first-dimension index j, shard-local second-dimension index ii_local)."""
+        poly_u16 = np.ascontiguousarray(poly_u16, dtype=np.uint16)
+        assert poly_u16.size == N
+        check(self.lib.sb200_pack_server_set_plane_item(self.h, plane, j, ii_local, poly_u16.ctypes.data_as(_P16)), self.lib)
+
     def load_plane_reference(self, plane, db_buf):
         """db_buf: the WHOLE plane in the reference's convertDb layout (src/testing.cpp:316-340)."""
         check(self.lib.sb200_pack_server_load_plane_reference(self.h, plane, _p64(db_buf)), self.lib)
