@@ -33,6 +33,10 @@ N_POLY = 2048
 WORKLOADS = {
     "cfg1": dict(kind="spiral", nu1=8, nu2=7, scaling="weak", prm=CFG1, flags=[],
                  macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256"),
+    # cfg2 = cfg1's shape with the reference's --random-data ("implicit") database: one constant record, dummyWorkingSet =
+    # min(2^25 / total_n, 2048) z-slices held in memory, slice z mod dummyWorkingSet scanned (src/spiral.cpp:647,1032-1081,1274-1282)
+    "cfg2": dict(kind="spiral", nu1=8, nu2=7, scaling="weak", prm=CFG1, flags=["--random-data"], implicit=True,
+                 macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=8 QPBITS=20 PVALUE=256"),
     "cfg5": dict(kind="spiral", nu1=9, nu2=8, scaling="strong", flags=[],
                  prm=dict(t_gsw=9, t_conv=4, t_exp=8, t_exp_right=56, qp_bits=21, out_n=2, p_db=256),
                  macros="TEXP=8 TEXPRIGHT=56 TCONV=4 TGSW=9 QPBITS=21 PVALUE=256", sample=(9, 5)),
@@ -88,9 +92,15 @@ def workload_name(cfg, nu1, nu2):
         assert rb == 32 * 256
     else:
         recs, size = f"2^{nu1 + nu2}", {"cfg3": "30 KB (32 KiB)", "cfg4": "100 KB (100 KiB)"}.get(cfg, f"{rb // 1024} KiB")
-    variant = {"cfg1": "Spiral", "cfg5": "Spiral", "cfg3": "SpiralPack", "cfg4": "SpiralStreamPack"}[cfg]
+    variant = {"cfg1": "Spiral", "cfg2": "Spiral", "cfg5": "Spiral", "cfg3": "SpiralPack", "cfg4": "SpiralStreamPack"}[cfg]
     flags = (" a " + " ".join(wl["flags"])) if wl["flags"] else ""
-    return f"{variant} {recs} records x {size} (./spiral {nu1} {nu2}{flags}; {wl['macros']}), explicit DB"
+    kind = "implicit DB (one constant record, %d of 2048 slices resident)" % implicit_slices(nu1, nu2) if wl.get("implicit") else "explicit DB"
+    return f"{variant} {recs} records x {size} (./spiral {nu1} {nu2}{flags}; {wl['macros']}), {kind}"
+
+
+def implicit_slices(nu1, nu2):
+    """dummyWorkingSet of the reference's --random-data mode (src/spiral.cpp:1277)."""
+    return min((1 << 25) >> (nu1 + nu2), N_POLY) or 1
 
 
 def db_bytes_total(wl, nu1, nu2):
@@ -460,7 +470,12 @@ class SpiralDriver:
         p = WORKLOADS[cfg]["prm"]
         prm = SpiralParams(nu1, nu2, p["t_gsw"], p["t_conv"], p["t_exp"], p["t_exp_right"], p["qp_bits"], p["out_n"], p["p_db"])
         self.srv = srv = SpiralServer(prm, device=local_rank, rank=rank, world=world)
-        srv.load_db_random(seed=1000 + rank)
+        self.implicit = bool(WORKLOADS[cfg].get("implicit"))
+        self.const_value = 41                             # the one record of an implicit database (the reference draws rand % (p_db / 4))
+        if self.implicit:
+            srv.load_db_implicit_constant(self.const_value, implicit_slices(nu1, nu2))
+        else:
+            srv.load_db_random(seed=1000 + rank)
         self.use_p2p = world > 1 and args.exchange == "p2p"
         if self.use_p2p:                                  # cudaIpc handles of every rank's exchange buffer, rank order
             handles = [None] * world
@@ -480,7 +495,7 @@ class SpiralDriver:
         num_per, local = 1 << nu2, (1 << nu2) // world
         for idx in self.targets:
             j, ii = divmod(idx, num_per)
-            if ii % world == rank:
+            if ii % world == rank and not self.implicit:
                 srv.load_db_items(planted_record(np, idx, 4, p["p_db"]).astype(np.uint16)[None], item_begin=j * local + ii // world)
         self.q_host = torch.empty(2 * 2 * N_POLY, dtype=torch.int64).pin_memory()
         self.set_query(self.targets[0], 1)
@@ -509,9 +524,16 @@ class SpiralDriver:
         torch.cuda.current_stream().synchronize()
         self.q_host.copy_(out.cpu())
 
+    def expected(self, idx):
+        if self.implicit:                                 # every record: the constant in coefficient 0 of its four polynomials
+            rec = self.np.zeros((4, N_POLY), dtype=self.np.uint64)
+            rec[:, 0] = self.const_value
+            return rec
+        return planted_record(self.np, idx, 4, self.p["p_db"])
+
     def decode_matches(self, idx):
         got = self.client.decode(self.resp_host.numpy().view(self.np.uint64))
-        return bool(self.np.array_equal(got, planted_record(self.np, idx, 4, self.p["p_db"])))
+        return bool(self.np.array_equal(got, self.expected(idx)))
 
     def upload(self, stream):
         self.srv.upload_query_ptr(self.q_host.data_ptr(), stream)
@@ -969,7 +991,7 @@ def headline_extras(ctx, args, cfg, drv, steps, ev):
         w_end.record()
         torch.cuda.synchronize()
         got = drv.client.decode(srv.unpack_response(packed_host.numpy().view(np.uint64)))
-        wire_ok = bool(np.array_equal(got, planted_record(np, drv.targets[1], 4, drv.p["p_db"])))
+        wire_ok = bool(np.array_equal(got, drv.expected(drv.targets[1])))
         if not wire_ok:
             raise SystemExit("bench verification FAILED: wire-format answer does not decode to the planted record")
         out["e2e_wire"] = {"value": w_begin.elapsed_time(w_end) / steps, "unit": "ms", "h2d_bytes_per_step": wbytes, "d2h_bytes_per_step": pbytes,
@@ -1015,7 +1037,7 @@ def headline_extras(ctx, args, cfg, drv, steps, ev):
                      "note": "host wall clock around all streams; every query includes its H2D query upload and D2H response"}
         # tensor-core batched first dimension (tc_scan.cu): up to 16 clients' converted queries answered by ONE tcgen05 pass
         # over the limb-tile copy of the database; expansions and folds of the clients overlap on their own streams
-        if args.tc_batch > 1 and lib.sb200_tc_supported(srv.dim0, srv.num_per):
+        if args.tc_batch > 1 and lib.sb200_tc_supported(srv.dim0, srv.num_per) and not drv.implicit:
             nb = min(args.tc_batch, 16)
             while len(clients) < nb:
                 c = srv.view()
@@ -1050,7 +1072,7 @@ def headline_extras(ctx, args, cfg, drv, steps, ev):
                 tc_round()
             torch.cuda.synchronize()
             # client 0 holds the real keys and the real query: its answer out of the shared tensor-core pass must decode
-            tc_ok = bool(np.array_equal(drv.client.decode(resp_hosts[0].numpy().view(np.uint64)), planted_record(np, drv.targets[0], 4, p["p_db"])))
+            tc_ok = bool(np.array_equal(drv.client.decode(resp_hosts[0].numpy().view(np.uint64)), drv.expected(drv.targets[0])))
             if not tc_ok:
                 raise SystemExit("bench verification FAILED: tensor-core batched answer does not decode to the planted record")
             rounds = max(3, steps // 2)

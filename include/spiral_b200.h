@@ -170,6 +170,13 @@ int sb200_server_create_view(sb200_server **out, sb200_server *parent);
 int sb200_server_load_db_items(sb200_server *srv, const uint16_t *pts_host, size_t item_begin, size_t item_count);
 /* database handed over in the reference's layout (the WHOLE B of load_db); the shard's rows are extracted */
 int sb200_server_load_db_reference(sb200_server *srv, const uint64_t *B_host);
+/* the reference's --random-data ("implicit database") mode, src/spiral.cpp:1032-1081, 1274-1282: B_slices holds `working_set`
+ * z-slices in load_db's layout (dummyWorkingSet = min(2^25 / total_n, 2048), a power of two) and the scan reads slice
+ * z mod working_set (:647, the AVX-512 statement) - half the memory, the same 8 B x 2048 x 4 x 2^(nu1+nu2) algorithmic bytes */
+int sb200_server_load_db_implicit(sb200_server *srv, const uint64_t *B_slices_host, size_t working_set);
+/* the same database generated on the device: every record the constant `value` (< p_db / 2) in coefficient 0 of its four polynomials */
+int sb200_server_load_db_implicit_constant(sb200_server *srv, uint64_t value, size_t working_set);
+size_t sb200_server_db_slices(const sb200_server *srv);     /* 2048 for an explicit database */
 uint64_t *sb200_server_db_ptr(sb200_server *srv);          /* device pointer of the scan-layout shard */
 /* public parameters, ref-NTT host buffers: W_exp_left g x (2 x t_exp), W_exp_right (stopround+1 or g) x (2 x t_exp_right),
  * W_conv 3 x 2*t_conv, V_conv 3 x 2*t_conv  (runConversionImproved, src/spiral.cpp:2093-2300) */

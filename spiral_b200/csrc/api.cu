@@ -493,6 +493,7 @@ struct sb200_server {
     std::vector<int> offs, cnt;
     int maxcnt = 0, tmax = 0;
     bool have_db = false, have_params = false;
+    size_t z_slices = 0;                                // 0 / 2048: explicit database; an implicit (--random-data) one holds fewer slices
     const sb200_server *db_owner = nullptr;           // views (sb200_server_create_view) scan another server's resident database
     // device memory
     DBuf<uint64_t> db;                                  // scan layout shard
@@ -690,10 +691,14 @@ extern "C" int sb200_server_create_view(sb200_server **out, sb200_server *parent
 
 static inline const uint64_t *server_db(const sb200_server *s) { return s->db_owner ? s->db_owner->db.p : s->db.p; }
 static inline bool server_has_db(const sb200_server *s) { return s->db_owner ? s->db_owner->have_db : s->have_db; }
-static int server_alloc_db(sb200_server *s) {
+static inline size_t server_z_slices(const sb200_server *s) { const sb200_server *o = s->db_owner ? s->db_owner : s; return o->z_slices ? o->z_slices : (size_t)kN; }
+static int server_alloc_db(sb200_server *s, size_t z_slices = 0) {
     if (s->db_owner) return fail(SB200_ERR_STATE, "this server is a view: load the database through its parent");
+    const size_t want = z_slices ? z_slices : (size_t)kN;
+    if (s->db.p && server_z_slices(s) != want) { cudaFree(s->db.p); s->db.p = nullptr; s->have_db = false; }
+    s->z_slices = z_slices;
     if (s->db.p) return SB200_OK;
-    CU(s->db.alloc(s->dim0 * s->local_num_per * 4 * kN));
+    CU(s->db.alloc(s->dim0 * s->local_num_per * 4 * want));
     return SB200_OK;
 }
 extern "C" int sb200_server_load_db_items(sb200_server *s, const uint16_t *pts, size_t item_begin, size_t item_count) {
@@ -715,14 +720,14 @@ extern "C" int sb200_server_load_db_items(sb200_server *s, const uint16_t *pts, 
     s->have_db = true;
     return SB200_OK;
 }
-extern "C" int sb200_server_load_db_reference(sb200_server *s, const uint64_t *B) {
-    if (!s) return fail(SB200_ERR_ARG, "null server");
+static int server_load_db_reference_slices(sb200_server *s, const uint64_t *B, size_t slices) {
+    if (!s || !B) return fail(SB200_ERR_ARG, "null argument");
     CU(cudaSetDevice(s->device));
-    TRY(server_alloc_db(s));
+    TRY(server_alloc_db(s, slices == (size_t)kN ? 0 : slices));
     // per z-slice the reference holds num_per rows (ii) of n2*dim0*n0 words; the shard takes rows ii = rank (mod world)
-    const size_t row_words = kN2 * s->dim0 * kN0, zc = 16;
+    const size_t row_words = kN2 * s->dim0 * kN0, zc = std::min((size_t)16, slices);
     DBuf<uint64_t> stage(zc * s->local_num_per * row_words);
-    for (size_t z0 = 0; z0 < (size_t)kN; z0 += zc) {
+    for (size_t z0 = 0; z0 < slices; z0 += zc) {
         if (s->world == 1) {
             CU(stage.up(B + z0 * s->num_per * row_words, zc * s->num_per * row_words));
         } else {
@@ -738,6 +743,33 @@ extern "C" int sb200_server_load_db_reference(sb200_server *s, const uint64_t *B
     s->have_db = true;
     return SB200_OK;
 }
+extern "C" int sb200_server_load_db_reference(sb200_server *s, const uint64_t *B) { return server_load_db_reference_slices(s, B, kN); }
+// The implicit database of the reference's --random-data mode (src/spiral.cpp:1032-1081, 1274-1282): B holds only `working_set`
+// z-slices (a power of two <= 2048; dummyWorkingSet = min(2^25 / total_n, 2048)) and the scan reads slice z mod working_set
+// (:647, the AVX-512 statement).  The algorithmic size of a scan stays the full 2^(nu1+nu2) x 4 x 2048 words.
+extern "C" int sb200_server_load_db_implicit(sb200_server *s, const uint64_t *B_slices_host, size_t working_set) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (!working_set || working_set > (size_t)kN || (working_set & (working_set - 1))) return fail(SB200_ERR_ARG, "load_db_implicit: working_set must be a power of two <= 2048");
+    if (s->db_tc.p) return fail(SB200_ERR_STATE, "load_db_implicit: the tensor-core copy was built for an explicit database");
+    return server_load_db_reference_slices(s, B_slices_host, working_set);
+}
+// every record the same constant polynomial `value` (< p_db / 4) in coefficient 0 of its four polynomials, as load_db generates
+// it (:1034-1072): every word of every slice is the same residue pair, written on the device
+extern "C" int sb200_server_load_db_implicit_constant(sb200_server *s, uint64_t value, size_t working_set) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (!working_set || working_set > (size_t)kN || (working_set & (working_set - 1))) return fail(SB200_ERR_ARG, "load_db_implicit: working_set must be a power of two <= 2048");
+    if (value >= s->prm.p_db / 2) return fail(SB200_ERR_ARG, "load_db_implicit_constant: value must be below p_db / 2");
+    if (s->db_tc.p) return fail(SB200_ERR_STATE, "load_db_implicit: the tensor-core copy was built for an explicit database");
+    CU(cudaSetDevice(s->device));
+    TRY(server_alloc_db(s, working_set == (size_t)kN ? 0 : working_set));
+    const uint64_t word = (value % kP) | ((value % kB) << 32);
+    const size_t words = s->dim0 * s->local_num_per * 4 * working_set;
+    std::vector<uint64_t> h(1 << 16, word);
+    for (size_t o = 0; o < words; o += h.size()) CU(cudaMemcpy(s->db.p + o, h.data(), std::min(h.size(), words - o) * 8, cudaMemcpyHostToDevice));
+    s->have_db = true;
+    return SB200_OK;
+}
+extern "C" size_t sb200_server_db_slices(const sb200_server *s) { return s ? server_z_slices(s) : 0; }
 extern "C" uint64_t *sb200_server_db_ptr(sb200_server *s) { return s ? const_cast<uint64_t *>(server_db(s)) : nullptr; }
 
 static int server_up_ntt(sb200_server *s, DBuf<uint32_t> &dst, const uint64_t *host, size_t npolys) {
@@ -898,7 +930,7 @@ extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan: database not loaded");
     // sharded expansion: every rank's slice of the query must have landed in this rank's buffer
     if (s->query_sharded) launch_flag_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, 0, 0, ES(s, stream));
-    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, ES(s, stream));
+    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, ES(s, stream), server_z_slices(s));
     CHECK_LAUNCH();
     return SB200_OK;
 }
@@ -908,6 +940,7 @@ extern "C" int sb200_server_scan_batched(sb200_server *const *servers, int count
     if (!servers || (count != 2 && count != 4)) return fail(SB200_ERR_ARG, "scan_batched: count must be 2 or 4");
     sb200_server *s0 = servers[0];
     if (!s0 || !server_has_db(s0)) return fail(SB200_ERR_STATE, "scan_batched: database not loaded");
+    if (server_z_slices(s0) != (size_t)kN) return fail(SB200_ERR_STATE, "scan_batched: needs an explicit database");
     const uint64_t *q[4]; uint32_t *o[4];
     for (int b = 0; b < count; b++) {
         if (!servers[b] || server_db(servers[b]) != server_db(s0)) return fail(SB200_ERR_ARG, "scan_batched: servers must share one database");
@@ -924,6 +957,7 @@ extern "C" int sb200_server_enable_tc(sb200_server *s, int capacity) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner) return fail(SB200_ERR_STATE, "enable_tc: call it on the server that owns the database");
     if (!s->have_db) return fail(SB200_ERR_STATE, "enable_tc: database not loaded");
+    if (server_z_slices(s) != (size_t)kN) return fail(SB200_ERR_STATE, "enable_tc: needs an explicit database");
     if (capacity < 1 || capacity > 16) return fail(SB200_ERR_ARG, "enable_tc: capacity must be in [1, 16]");
     if (!tc_shape_ok(s->dim0, s->local_num_per)) return fail(SB200_ERR_ARG, "enable_tc: needs 2*dim0 and 2*num_per (per shard) to be multiples of 128");
     CU(cudaSetDevice(s->device));
@@ -976,7 +1010,7 @@ extern "C" int sb200_server_scan_host(sb200_server *s, const uint64_t *reoriente
     if (!s || !reoriented_host || !out_ref_ntt_host) return fail(SB200_ERR_ARG, "scan_host: null argument");
     if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan_host: database not loaded");
     CU(cudaMemcpy(s->query.p, reoriented_host, s->dim0 * 2 * 4 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, 0); CHECK_LAUNCH();
+    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, 0, server_z_slices(s)); CHECK_LAUNCH();
     return down_ntt(out_ref_ntt_host, s->scan_out.p, s->local_num_per * 6);
 }
 extern "C" int sb200_server_copy_partial(sb200_server *s, uint64_t *dst_dev, void *stream) {

@@ -304,6 +304,7 @@ extern "C" int sb200_server_load_db_records_file(sb200_server *s, const char *pa
 extern "C" int sb200_server_save_db(sb200_server *s, const char *path) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner || !s->have_db) return fail(SB200_ERR_STATE, "save_db: this server owns no loaded database");
+    if (server_z_slices(s) != (size_t)kN) return fail(SB200_ERR_STATE, "save_db: an implicit database has no snapshot form");
     CU(cudaSetDevice(s->device));
     return snapshot_save(path, server_snap_header(s), s->db.p, s->dim0 * s->local_num_per * 4 * kN);
 }

@@ -53,6 +53,8 @@ static void cmp_raw(const char *what, const uint64_t *a, const uint64_t *b, size
 // ---- reference globals the mirror reads (defined by the reference library) ---------------------
 extern uint64_t *B;                       // src/spiral.cpp:1017
 extern size_t num_expansions, further_dims;
+extern bool random_data;                  // src/spiral.cpp:18   (--random-data: the implicit database)
+extern size_t dummyWorkingSet;            // src/util.cpp:3      (z-slices B holds in that mode)
 
 static sb200_server *g_srv = nullptr;     // resident database shard (whole database, world = 1)
 
@@ -98,6 +100,12 @@ void load_db() {
     prm.t_gsw = TGSW; prm.t_conv = TCONV; prm.t_exp = TEXP; prm.t_exp_right = TEXPRIGHT;
     prm.qp_bits = QPBITS; prm.out_n = 2; prm.p_db = PVALUE;
     OKAY(sb200_server_create(&g_srv, &prm, 0, 0, 1));
+    if (random_data) {        // implicit database: B holds dummyWorkingSet slices, the scan reads slice z mod dummyWorkingSet (:647)
+        OKAY(sb200_server_load_db_implicit(g_srv, B, dummyWorkingSet));
+        fprintf(stderr, "[spiral_b200] implicit database resident on the GPU (%zu of 2048 slices, %zu MiB)\n", dummyWorkingSet,
+                (sb200_db_words(prm.nu1, prm.nu2) / 2048 * dummyWorkingSet * 8) >> 20);
+        return;
+    }
     OKAY(sb200_server_load_db_reference(g_srv, B));
     fprintf(stderr, "[spiral_b200] database resident on the GPU (%zu MiB)\n", (sb200_db_words(prm.nu1, prm.nu2) * 8) >> 20);
 }

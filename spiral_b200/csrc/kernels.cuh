@@ -93,7 +93,8 @@ void launch_unreorient_q(uint32_t *out, const uint64_t *q_reor, int rm_count, cu
 // query: [z][j][m][4] PB64 (reference reorientCiphertexts layout);  db: scan layout;
 // out: dev-NTT [i][r][c] (num_per x 3 x 2 polys)
 void launch_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, cudaStream_t s);
-void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s);
+// z_slices: slices the database buffer holds (2048; an implicit database holds a power of two fewer and slice z mod z_slices is read)
+void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s, size_t z_slices = 0);
 
 int launch_scan_spiral_batched(uint32_t *const *out, const uint64_t *const *query, int count, const uint64_t *db, size_t dim0,
                                size_t num_per, cudaStream_t s);   // count in {2,4}: queries sharing one database pass

@@ -150,7 +150,7 @@ __device__ __forceinline__ uint64_t fold_acc(uint64_t a, uint32_t c32) {      //
 template <int U, int kScanThreads, int UNR, bool kFullTile>      // kFullTile: ICT == U * kScanThreads (one z-slice per CTA), strides fold into immediates
 __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
                                                              const uint64_t *__restrict__ db, int dim0, int IC, int ICT,
-                                                             int ZT, int JC) {
+                                                             int ZT, int JC, int zmask) {
     pdl_prologue();
     extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4 = 64 bytes per (z, j)
     const int tid = threadIdx.x;
@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
 #pragma unroll
         for (int r = 0; r < 3; r++) acc[u][r][0] = acc[u][r][1] = 0;
 
-    const uint4 *dbz = reinterpret_cast<const uint4 *>(db) + ((size_t)z * dim0) * IC + ic0;
+    // zmask = 2047 for an explicit database; an implicit (--random-data) one holds only zmask + 1 slices and NTT coefficient z
+    // reads slice z mod (zmask + 1)  (reference src/spiral.cpp:647)
+    const uint4 *dbz = reinterpret_cast<const uint4 *>(db) + ((size_t)(z & zmask) * dim0) * IC + ic0;
     const uint4 *qg = reinterpret_cast<const uint4 *>(query);
 
     for (int jc0 = 0; jc0 < dim0; jc0 += JC) {
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spiral(uint32_t *__restri
 // z-slice; the JS partial sums (folded below 2^61 each) meet in shared memory and group 0 reduces and stores.
 //   thread = js * (ZT*TZ) + zl * TZ + icl,  TZ = IC/2 threads per z-slice,  JS * ZT * TZ = 128
 __global__ void __launch_bounds__(128) k_scan_spiral_jsplit(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
-                                                            const uint64_t *__restrict__ db, int dim0, int IC, int ZT, int JS, int JC) {
+                                                            const uint64_t *__restrict__ db, int dim0, int IC, int ZT, int JS, int JC, int zmask) {
     pdl_prologue();
     extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4, later reused for the reduction
     const int tid = threadIdx.x;
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(128) k_scan_spiral_jsplit(uint32_t *__restrict
     for (int u = 0; u < 2; u++)
 #pragma unroll
         for (int r = 0; r < 3; r++) acc[u][r][0] = acc[u][r][1] = 0;
-    const uint4 *dbz = reinterpret_cast<const uint4 *>(db) + ((size_t)z * dim0) * IC + icl;
+    const uint4 *dbz = reinterpret_cast<const uint4 *>(db) + ((size_t)(z & zmask) * dim0) * IC + icl;
     const uint4 *qg = reinterpret_cast<const uint4 *>(query);
     int it = 0;
     for (int jc0 = 0; jc0 < dim0; jc0 += JC) {
@@ -310,7 +312,8 @@ __global__ void __launch_bounds__(128) k_scan_spiral_jsplit(uint32_t *__restrict
         }
     }
 }
-void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s) {
+void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s, size_t z_slices) {
+    const int zmask = (int)(z_slices ? z_slices : (size_t)kN) - 1;
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
     // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
     // The query slice is staged in chunks of at most 16 KiB per CTA: with 32 KiB (first dimensions of 512 and 1024) only 6 CTAs
@@ -329,7 +332,7 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
         while ((size_t)ZT * JC * 64 > 16384 && JC > kScanFoldEvery) JC >>= 1;
         const size_t smem = std::max((size_t)ZT * JC * 64, (size_t)128 * 12 * 8);
         count_launch();
-        launch_pdl(k_scan_spiral_jsplit, dim3(kN / ZT), dim3(128), smem, s, out, query, db, (int)dim0, IC, ZT, JS, JC);
+        launch_pdl(k_scan_spiral_jsplit, dim3(kN / ZT), dim3(128), smem, s, out, query, db, (int)dim0, IC, ZT, JS, JC, zmask);
         return;
     }
     static const bool t64 = [] { const char *e = getenv("SB200_SCAN_T64"); return !(e && *e == '0'); }();
@@ -345,10 +348,10 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
     dim3 grid(kN / ZT, IC / ICT);
     if (JC < (int)dim0) note_kernel("k_scan_spiral[query slice staged in chunks]");     // visible in sb200_kernel_log
     count_launch();
-    if (U == 2 && ICT == 2 * T) launch_pdl((k_scan_spiral<2, 128, 4, true>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2 && T == 64) launch_pdl((k_scan_spiral<2, 64, 4, false>), grid, dim3(64), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else if (U == 2)            launch_pdl((k_scan_spiral<2, 128, 4, false>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
-    else                        launch_pdl((k_scan_spiral<1, 128, 4, false>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC);
+    if (U == 2 && ICT == 2 * T) launch_pdl((k_scan_spiral<2, 128, 4, true>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC, zmask);
+    else if (U == 2 && T == 64) launch_pdl((k_scan_spiral<2, 64, 4, false>), grid, dim3(64), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC, zmask);
+    else if (U == 2)            launch_pdl((k_scan_spiral<2, 128, 4, false>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC, zmask);
+    else                        launch_pdl((k_scan_spiral<1, 128, 4, false>), grid, dim3(128), smem, s, out, query, db, (int)dim0, IC, ICT, ZT, JC, zmask);
 }
 
 // ---- batched first dimension: BQ queries answered in ONE pass over the database ------------------------------

@@ -158,6 +158,9 @@ def load_library():
         "sb200_server_load_db_items": (C.c_int, [vp, u16p, sz, sz]),
         "sb200_server_load_db_reference": (C.c_int, [vp, u64p]),
         "sb200_server_db_ptr": (vp, [vp]),
+        "sb200_server_load_db_implicit": (C.c_int, [vp, u64p, sz]),
+        "sb200_server_load_db_implicit_constant": (C.c_int, [vp, C.c_uint64, sz]),
+        "sb200_server_db_slices": (sz, [vp]),
         "sb200_server_set_public_params": (C.c_int, [vp, u64p, u64p, u64p, u64p]),
         "sb200_server_answer": (C.c_int, [vp, vp, vp, vp]),
         "sb200_server_upload_query": (C.c_int, [vp, vp, vp]),

@@ -51,6 +51,13 @@ class SpiralServer:
         """B: the reference's own database buffer (layout of src/spiral.cpp:1139-1153)."""
         check(self.lib.sb200_server_load_db_reference(self.h, _p64(B)), self.lib)
 
+    def load_db_implicit(self, B_slices, working_set):
+        """The reference's --random-data database: `working_set` z-slices in load_db's layout; the scan reads slice z mod working_set."""
+        check(self.lib.sb200_server_load_db_implicit(self.h, _p64(B_slices), working_set), self.lib)
+
+    def load_db_implicit_constant(self, value, working_set):
+        check(self.lib.sb200_server_load_db_implicit_constant(self.h, value, working_set), self.lib)
+
     def load_db_records(self, records):
         """records: the WHOLE database as the flat record stream (uint8 array or a file path); load_db's `has_data` branch."""
         if isinstance(records, (str, bytes)):
@@ -192,6 +199,7 @@ class SpiralServer:
 
     @property
     def db_bytes(self):
+        """ALGORITHMIC bytes of one scan of this shard (an implicit database holds fewer slices but every scan covers all 2048)."""
         return self.dim0 * self.local_num_per * 4 * N * 8
 
     def close(self):

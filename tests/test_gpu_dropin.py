@@ -133,3 +133,22 @@ def test_full_size_pack_harness_and_resident_server(cfg, args, need_gib, leaves,
     print("kernel set:", sorted(got))
     for k in kernels:
         assert k in got, f"{k} was not dispatched at this shape; kernels: {sorted(got)}"
+
+
+def test_reference_harness_random_data_mode_with_implicit_resident_database():
+    """BASELINE.json configs[1]: `./spiral 8 7 <idx> a --random-data`.  The reference's load_db builds 1024 of the 2048 z-slices
+    (1 GiB), the mirror makes exactly those resident and the scan reads slice z mod 1024; every leaf and the resident server are
+    compared with the reference.  Needs the AVX-512 build: only that branch of the reference's scan implements z mod dummyWorkingSet
+    (its AVX2 branch pins the QUERY slice to z = 0, src/spiral.cpp:754-755, and is a timing-only path)."""
+    exe = _driver("cfg1")
+    if not exe.endswith("avx512") or not os.path.exists(exe):
+        pytest.skip("needs the prebuilt AVX-512 reference driver")
+    env = dict(os.environ, SB200_PARITY="1")
+    out = subprocess.run([exe, "8", "7", "31415", "a", "--random-data"], capture_output=True, text=True, timeout=1500, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "Is correct?: 1" in out.stdout, out.stdout[-2000:]
+    assert "implicit database resident on the GPU (1024 of 2048 slices" in out.stderr
+    for leaf in ("multiplyQueryByDatabase", "nttInvAndCrtLiftCiphertexts", "foldOneFurtherDimension", "expandImproved", "regevToGSW",
+                 "tier-3 resident server response row 0", "tier-3 resident server response rows 1-2"):
+        assert f"parity ok: {leaf}" in out.stderr, f"{leaf} was not exercised:\n{out.stderr[-3000:]}"
+    assert "PARITY FAIL" not in out.stderr

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from spiral_b200 import SpiralParams
+from spiral_b200.lib import check
 from spiral_b200.server import SpiralServer
 from tests import oracle_lib as ol
 
@@ -284,4 +285,51 @@ def test_sharded_expansion_with_fused_all_gather(sb, oracle, cfg, nu1, nu2, worl
     assert np.array_equal(resp.cpu().numpy().view(np.uint64), want)
     for srv in servers:
         srv.close()
+    s.close()
+
+
+@pytest.mark.parametrize("nu1,nu2,dws", [(4, 2, 256), (6, 2, 64), (3, 3, 2048), (5, 1, 1)])
+def test_implicit_database_scan_reads_slice_z_mod_working_set(sb, oracle, nu1, nu2, dws):
+    """cfg2, the reference's --random-data mode (src/spiral.cpp:647,1032-1081): the resident buffer holds `dws` z-slices and NTT
+    coefficient z is multiplied with slice z mod dws.  Checked against the oracle's scan of the database written out in full."""
+    rng = np.random.default_rng(nu1 * 10 + nu2)
+    dim0, num_per, N = 1 << nu1, 1 << nu2, ol.N
+    row = num_per * 2 * dim0 * 2                                   # words of one z-slice in load_db's layout
+
+    def rnd_pb(n):
+        return rng.integers(0, ol.P, size=n, dtype=np.uint64) | (rng.integers(0, ol.B, size=n, dtype=np.uint64) << np.uint64(32))
+    slices = np.ascontiguousarray(rnd_pb(dws * row))
+    full = np.ascontiguousarray(np.tile(slices.reshape(dws, row), (N // dws, 1)).reshape(-1))
+    q = rnd_pb(N * dim0 * 2 * 4).reshape(N, dim0, 2, 4)
+    q[..., 3] = 0
+    q = np.ascontiguousarray(q.reshape(-1))
+    want = np.zeros(num_per * 6 * 2 * N, dtype=np.uint64)
+    oracle.so_multiply_query_by_database(ol.ptr(want), ol.ptr(q), ol.ptr(full), dim0, num_per)
+    prm = ol.make_params("cfg1", nu1, nu2)
+    srv = SpiralServer(sb_params(prm))
+    srv.load_db_implicit(slices, dws)
+    assert sb.sb200_server_db_slices(srv.h) == dws
+    got = np.zeros_like(want)
+    check(sb.sb200_server_scan_host(srv.h, ol.ptr(q), ol.ptr(got)), sb)
+    assert np.array_equal(ol.canon(got, ol.KIND_NTT), ol.canon(want, ol.KIND_NTT))
+    with pytest.raises(Exception):
+        srv.enable_tc(4)                                           # the tensor-core copy needs an explicit database
+    srv.load_db_reference(full)                                    # back to an explicit database on the same server
+    assert sb.sb200_server_db_slices(srv.h) == N
+    check(sb.sb200_server_scan_host(srv.h, ol.ptr(q), ol.ptr(got)), sb)
+    assert np.array_equal(ol.canon(got, ol.KIND_NTT), ol.canon(want, ol.KIND_NTT))
+    srv.close()
+
+
+def test_implicit_constant_database_answers_every_index_with_the_constant(sb, oracle):
+    """The whole cfg2 pipeline at a small shape: device-generated constant database, real query, decoded record == the constant."""
+    s = ol.SpiralSession(oracle, "cfg1", 5, 3, seed=3)
+    srv = SpiralServer(sb_params(s.prm))
+    srv.load_db_implicit_constant(29, 128)
+    srv.set_public_params(s.W_left, s.W_right, s.W_conv, s.V_conv)
+    want = np.zeros((4, ol.N), dtype=np.uint64)
+    want[:, 0] = 29
+    for idx in (0, 100, s.total_n - 1):
+        assert np.array_equal(s.decode(srv.answer(s.query(idx))), want)
+    srv.close()
     s.close()
