@@ -505,8 +505,11 @@ class SpiralDriver:
         self.resp_dev = torch.empty(6 * N_POLY, dtype=torch.int64, device="cuda")
         self.h2d_bytes, self.d2h_bytes = int(self.q_host.numel() * 8), int(self.resp_host.numel() * 8)
         self.db_bytes = srv.db_bytes
-        self.exchange = ("none (1 GPU)" if world == 1 else "peer-memory stores + flags over NVLink, fused into the stream (no NCCL call per query)"
-                         if self.use_p2p else "NCCL all_gather of one 96 KiB ciphertext per GPU")
+        self.exchange = ("none (1 GPU)" if world == 1 else "peer-memory stores + flags over NVLink, fused into the stream (no NCCL call per query); the "
+                         "expansion is sharded too: every rank expands / converts 1/N of the first-dimension and GSW ciphertexts and its "
+                         "ScalToMat / RegevToGSW kernels store them into all ranks' buffers" if self.use_p2p else "NCCL all_gather of one 96 KiB ciphertext per GPU")
+        if world == 1 or self.use_p2p:
+            srv.prepare(self.resp_dev.data_ptr(), torch.cuda.current_stream().cuda_stream)
 
     def set_query(self, idx, query_id):
         """Encrypt a query for record idx (GPU client, seeded wire form) and expand it to the 64 KiB in-memory ciphertext that

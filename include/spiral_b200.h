@@ -193,6 +193,9 @@ int sb200_server_answer(sb200_server *srv, const uint64_t *query_cv_host, uint64
  * first-dimension scan and at the end.  Sharded servers (world > 1, peers connected with sb200_server_xchg_connect): every rank
  * calls it; the exchange over NVLink peer memory and rank 0's tail folds are part of the call, the response lands on rank 0. */
 int sb200_server_process(sb200_server *srv, uint64_t *total_resp_dev, void *stream, void *const *marks);
+/* captures and instantiates every CUDA graph sb200_server_process will replay, without running anything (the first query then
+ * costs what the others do; needs the public parameters and, on a sharded server, connected peers) */
+int sb200_server_prepare(sb200_server *srv, uint64_t *total_resp_dev, void *stream);
 /* same, response in the wire format (sb200_dev_pack_response): 20 KiB instead of 96 KiB at cfg1 */
 int sb200_server_answer_packed(sb200_server *srv, const uint64_t *query_cv_host, uint64_t *packed_resp_host, void *stream);
 size_t sb200_server_packed_response_bytes(const sb200_server *srv);

@@ -10,11 +10,8 @@ try:
     d = json.load(open("gpurun_out/q_bench.json"))
     print("ms/query", d["value"], d["stages_ms"], "e2e", d["e2e"]["value"], "sustained", (d.get("sustained") or {}).get("value"), "verified", d["verified"]["decoded_equal_planted"])
     for w, v in d.get("workloads", {}).items():
-        print(w, v["value"], v["stages_ms"], v["roofline"]["frac"], v["e2e"]["value"])
+        print(w, v["value"], v["stages_ms"], v["roofline"]["frac"], v["e2e"]["value"], v["verified"] and v["verified"]["decoded_equal_planted"])
 except Exception as e:
     print("bench failed:", e)
 P
 python scripts/trace_query.py cfg1 > gpurun_out/q_trace_cfg1.md 2> gpurun_out/q_trace.err
-SB200_PROFILE_SKIP_ODD_CHAIN=1 python scripts/trace_query.py cfg1 > gpurun_out/q_trace_cfg1_noodd.md 2> gpurun_out/q_trace_noodd.err
-SB200_NO_PRIO=1 python scripts/trace_query.py cfg1 > gpurun_out/q_trace_cfg1_noprio.md 2>> gpurun_out/q_trace_noodd.err
-head -2 gpurun_out/q_trace_cfg1.md gpurun_out/q_trace_cfg1_noodd.md gpurun_out/q_trace_cfg1_noprio.md | cut -c1-250

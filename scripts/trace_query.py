@@ -34,7 +34,7 @@ def kernel_lines():
                 cur = None                                  # name on the next line
             elif cur is None and m and "launch" not in text:
                 cur = m.group(1)
-            if "pdl_prologue()" in text and "#define" not in text and cur:
+            if ("pdl_prologue()" in text or "pdl_prologue_no_early_dependents()" in text) and "#define" not in text and cur:
                 out.setdefault(n, []).append(cur)
     return out
 

@@ -455,9 +455,11 @@ bool graphs_enabled() {
     if (v < 0) { const char *e = getenv("SB200_NO_GRAPH"); v = (e && *e == '1') ? 0 : 1; }
     return v == 1;
 }
+// sb200_server_prepare: build (capture + instantiate) the graphs of a query without running anything
+static thread_local bool tl_prepare_only = false;
 template <typename F>
 int run_stage(GraphSlot &slot, cudaStream_t st, const void *k0, const void *k1, F &&body) {
-    if (!graphs_enabled()) { body(st); CHECK_LAUNCH(); return SB200_OK; }
+    if (!graphs_enabled()) { if (!tl_prepare_only) { body(st); CHECK_LAUNCH(); } return SB200_OK; }
     if (slot.exec && (slot.key0 != k0 || slot.key1 != k1)) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
     if (!slot.exec) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -478,6 +480,7 @@ int run_stage(GraphSlot &slot, cudaStream_t st, const void *k0, const void *k1, 
         if (e != cudaSuccess) { slot.exec = nullptr; return fail(SB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
         slot.key0 = k0; slot.key1 = k1;
     }
+    if (tl_prepare_only) return SB200_OK;
     CU(cudaGraphLaunch(slot.exec, st));
     count_launch(slot.launches);
     return SB200_OK;
@@ -823,18 +826,18 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
         // The expansion tree splits at its root into two independent chains: the even ciphertexts (first dimension: t_left digits,
         // all g rounds, then ScalToMat) and the odd ones (GSW bits: t_right = 56 digits per key switch, rounds 0..stopround, then
         // RegevToGSW).  Each is its own graph on its own stream, each starts from the uploaded query (the odd chain works on a
-        // private ciphertext array); the scan waits for the even chain only.  The even chain's kernels carry the greatest launch
-        // priority, the odd chain's the least: where both have CTAs pending the critical chain is dispatched first.
+        // private ciphertext array); the scan waits for the even chain only, the folds join the odd chain.
         const int wk = (int)s->wire_kind;
         const bool shard = s->world > 1 && s->xchg_connected && s->shard_eligible;
         static const bool skip_odd = [] { const char *e = getenv("SB200_PROFILE_SKIP_ODD_CHAIN"); return e && *e == '1'; }();   // timing experiments only: answers are wrong
         CU(cudaEventRecord(s->ev_fork, main_st));
         CU(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
         if (!skip_odd) TRY(run_stage(s->g_odd[wk], s->aux_stream, shard ? (const void *)s->xchg.p : nullptr, nullptr, [&](cudaStream_t st) {
-            // The odd chain's 56-digit rounds are thousands of NTT CTAs; queued in one go they sit AHEAD of the even chain's next
-            // kernels in the block scheduler's FIFO (strict launch priorities starve the odd chain instead, which then spills into
-            // the scan).  Its digit kernels therefore hold a fixed two CTA slots per SM and walk their work list.
-            static const int odd_slots = [] { const char *e = getenv("SB200_ODD_SLOTS"); return e ? atoi(e) : 2; }();
+            // The odd chain's 56-digit rounds are thousands of NTT CTAs that sit ahead of the even chain's next kernels in the block
+            // scheduler's queue and cost the even chain ~90 us.  Measured alternatives (profiles/r02_expansion_chains.md): strict launch
+            // priorities starve the odd chain, which then spills into the scan; digit kernels confined to SB200_ODD_SLOTS CTA slots
+            // per SM make the contention last longer (1.01 ms/query at 2 slots against 0.94 unlimited).  Default: unlimited.
+            static const int odd_slots = [] { const char *e = getenv("SB200_ODD_SLOTS"); return e ? atoi(e) : 0; }();
             LaunchPriority low(false);                  // no-op unless SB200_PRIO=1 (experiments)
             if (wk) launch_query_from_wire(s->cv_o.p, s->q_wire.p, s->wire_kind, st);
             else launch_ntt_u64_to_dev(s->cv_o.p, s->q_stage.p, 2, st);
@@ -919,10 +922,10 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) { 
 extern "C" int sb200_server_expansion_sharded(const sb200_server *s) { return s && s->query_sharded; }
 static int join_odd_chain(sb200_server *s, cudaStream_t st) {
     if (s->join_pending) { CU(cudaStreamWaitEvent(st, s->ev_join, 0)); s->join_pending = false; }
-    if (s->gsw_wait_pending) {                               // sharded conversion: every rank's GSW columns must have landed here
+    if (s->gsw_wait_pending && !tl_prepare_only) {           // sharded conversion: every rank's GSW columns must have landed here
         launch_flag_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, 1, 0, st);
-        s->gsw_wait_pending = false;
     }
+    s->gsw_wait_pending = false;
     return SB200_OK;
 }
 extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
@@ -1199,6 +1202,25 @@ extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_hos
 // One resident query in ONE call (the query is already in q_stage / q_wire): all server stages into total_resp_dev.  A serving loop
 // written in a scripting language issues one foreign call per query instead of six, so the host stays ahead of the ~1 ms of GPU work.
 // marks (optional): four cudaEvent_t recorded before the expansion, before the scan, after the scan and at the end.
+// Capture and instantiate every CUDA graph sb200_server_process will replay (expansion chains, folds, exchange + tail) without
+// running anything: the first query then costs what the others do.  Needs the public parameters (and connected peers on a sharded
+// server, since the sharded expansion is a different graph); total_resp_dev as it will be passed to sb200_server_process.
+extern "C" int sb200_server_prepare(sb200_server *s, uint64_t *total_resp_dev, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (!s->have_params) return fail(SB200_ERR_STATE, "server_prepare: public parameters not set");
+    if (s->world > 1 && !s->xchg_connected) return fail(SB200_ERR_STATE, "server_prepare: sharded server without connected peers");
+    CU(cudaSetDevice(s->device));
+    uint64_t *resp = total_resp_dev ? total_resp_dev : s->resp.p;
+    tl_prepare_only = true;
+    int rc = expand_and_convert_impl(s, stream, true);
+    if (!rc) rc = sb200_server_fold_local(s, stream);
+    if (!rc) rc = sb200_server_exchange_and_tail(s, resp, stream);
+    tl_prepare_only = false;
+    s->join_pending = s->gsw_wait_pending = s->query_sharded = false;
+    CU(cudaStreamSynchronize(s->aux_stream));
+    CU(cudaStreamSynchronize(ES(s, stream)));
+    return rc;
+}
 extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, void *stream, void *const *marks) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->world > 1 && !s->xchg_connected) return fail(SB200_ERR_STATE, "server_process: sharded server without connected peers (sb200_server_xchg_connect)");

@@ -82,12 +82,15 @@ struct TraceCtl { unsigned long long *buf; unsigned int *counter; unsigned int c
 __constant__ TraceCtl c_trace;
 __device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // every kernel starts with pdl_prologue(); the macro passes the call site's line, which names the kernel in the trace
-#define pdl_prologue() pdl_prologue_at(__LINE__)
-__device__ __forceinline__ void pdl_prologue_at(int line) {
+#define pdl_prologue() pdl_prologue_at(__LINE__, true)
+// for kernels that may SPIN on a flag written by another GPU (or, in single-device tests, by another stream): their dependents must
+// not be launched early - a pre-launched grid would sit in griddepcontrol.wait holding SM slots the flag's producer may need
+#define pdl_prologue_no_early_dependents() pdl_prologue_at(__LINE__, false)
+__device__ __forceinline__ void pdl_prologue_at(int line, bool early_dependents) {
     const bool tr = c_trace.buf != nullptr && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
     unsigned long long t0 = 0;
     if (tr) t0 = global_timer_ns();
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (early_dependents) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tr) {
         const unsigned int i = atomicAdd(c_trace.counter, 1u);

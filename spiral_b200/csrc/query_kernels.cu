@@ -415,7 +415,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p
 __global__ void __launch_bounds__(256) k_scal_to_mat_accum_tiled(const __grid_constant__ ScalTargets tg, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
                                                                  const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W, int dim0, int count,
                                                                  int j_off, int j_stride, int jtiles) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     constexpr int TC = 4;                                             // t_conv of every Spiral parameter set that reaches this kernel
     constexpr int kRowWords = 8 * 8 + 1;                              // 8 j x 8 words, padded: lanes (z) land on different banks
     __shared__ __align__(16) uint64_t tile[32 * kRowWords];
@@ -583,7 +583,7 @@ struct GswTargets {
 __global__ void __launch_bounds__(256) k_regev_to_gsw_accum_sharded(const __grid_constant__ GswTargets tg, const uint32_t *__restrict__ cv, const int *__restrict__ ct_idx,
                                                                     const int *__restrict__ bit_ids, const uint32_t *__restrict__ ginv, const uint32_t *__restrict__ W,
                                                                     const uint32_t *__restrict__ V, int t_conv, int ell, int nu2, int count) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     __shared__ int ok;
     unsigned int e = 0;
     if (threadIdx.x == 0) {        // the peers' GSW buffers are free once rank 0 has finished the previous query (its acknowledgement)

@@ -63,7 +63,7 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned int *p, unsigned in
 // Every CTA stores its share of the `words`-word payload into slot [epoch % 2][rank]; the last CTA to finish publishes the flag.
 __global__ void __launch_bounds__(1024) k_xchg_push(XchgBuf *target, XchgBuf *mine, const uint64_t *ct, unsigned int *epoch,
                                                     int rank, int world, unsigned int *error, size_t words, size_t slot_words) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     __shared__ int ok;
     const unsigned int e = *epoch + 1;
     const int slot = e % kXchgSlots;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(1024) k_xchg_push(XchgBuf *target, XchgBuf *mi
 // gridDim.x CTAs: each waits for all flags, copies its share of the slots into the private buffer; the last one acknowledges.
 __global__ void __launch_bounds__(1024) k_xchg_wait(XchgBuf *mine, unsigned int *const *acks, uint64_t *out, const unsigned int *epoch,
                                                     int world, unsigned int *error, size_t slot_words, int ack_now) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     __shared__ int ok;
     const unsigned int e = *epoch;                 // already advanced by this rank's own push (same stream)
     const int slot = e % kXchgSlots;
@@ -120,12 +120,12 @@ __global__ void __launch_bounds__(1024) k_xchg_wait(XchgBuf *mine, unsigned int 
 // rank 0, at the very END of a query whose expansion was sharded: the acknowledgement that lets the other ranks overwrite this
 // rank's query and GSW buffers (with it sent right after the gather, rank 0's tail folds could still be reading the GSW ciphertexts)
 __global__ void k_xchg_ack(unsigned int *const *acks, const unsigned int *epoch, int world, const unsigned int *error) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     if ((int)threadIdx.x < world && ld_acquire_sys(error) == 0) { __threadfence_system(); st_release_sys(acks[threadIdx.x], *epoch); }
 }
 // waits until all `world` flags of this rank's header (qflags: which = 0, gflags: which = 1) have reached the current query
 __global__ void k_flag_wait(XchgBuf *mine, int world, const unsigned int *epoch, unsigned int *error, int which, int advanced) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     const unsigned int e = *epoch + (advanced ? 0u : 1u);          // advanced: this rank's push of the query has already run
     const unsigned int *f = which ? mine->gflags : mine->qflags;
     if ((int)threadIdx.x < world && !spin_until_ge(&f[threadIdx.x], e)) *error = 3 + which;
@@ -171,7 +171,7 @@ struct QueryPeers { uint64_t *query[kXchgMaxWorld]; XchgBuf *xb[kXchgMaxWorld]; 
 __global__ void __launch_bounds__(256) k_reorient_dim1_allgather(const __grid_constant__ QueryPeers peers, const uint32_t *__restrict__ cv,
                                                                  int dim0, int j_begin, int j_count, int rank, int world,
                                                                  const unsigned int *epoch, XchgBuf *mine) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     // this query is number e of the exchange sequence; its slices may only overwrite the peers' query buffers once rank 0 has
     // gathered query e - 1 from EVERY rank (ack >= e - 1: all scans of the previous query are over)
     __shared__ int ok;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) k_reorient_dim1_allgather(const __grid_co
     }
 }
 __global__ void k_query_wait(XchgBuf *mine, int world, const unsigned int *epoch, unsigned int *error) {
-    pdl_prologue();
+    pdl_prologue_no_early_dependents();
     if ((int)threadIdx.x < world && !spin_until_ge(&mine->qflags[threadIdx.x], *epoch + 1)) *error = 3;
 }
 void launch_reorient_dim1_allgather(const QueryPeers &peers, const uint32_t *cv, size_t dim0, size_t j_begin, size_t j_count, int rank, int world,

@@ -165,6 +165,7 @@ def load_library():
         "sb200_server_answer": (C.c_int, [vp, vp, vp, vp]),
         "sb200_server_upload_query": (C.c_int, [vp, vp, vp]),
         "sb200_server_process": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
+        "sb200_server_prepare": (C.c_int, [vp, vp, vp]),
         "sb200_server_expand_and_convert": (C.c_int, [vp, vp]),
         "sb200_server_first_dim": (C.c_int, [vp, vp]),
         "sb200_server_fold_local": (C.c_int, [vp, vp]),

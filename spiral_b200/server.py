@@ -128,6 +128,10 @@ class SpiralServer:
         """All server stages of the uploaded query in one call; marks: None or a (c_void_p * 4) of cudaEvent_t handles."""
         check(self.lib.sb200_server_process(self.h, resp_ptr, stream, marks), self.lib)
 
+    def prepare(self, resp_ptr=None, stream=None):
+        """Build the CUDA graphs process() replays, without running anything."""
+        check(self.lib.sb200_server_prepare(self.h, resp_ptr, stream), self.lib)
+
     def first_dim(self, stream=None):
         check(self.lib.sb200_server_first_dim(self.h, stream), self.lib)
 
