@@ -480,7 +480,7 @@ int run_stage(GraphSlot &slot, cudaStream_t st, const void *k0, const void *k1, 
         if (e != cudaSuccess) { slot.exec = nullptr; return fail(SB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
         slot.key0 = k0; slot.key1 = k1;
     }
-    if (tl_prepare_only) return SB200_OK;
+    if (tl_prepare_only) { CU(cudaGraphUpload(slot.exec, st)); return SB200_OK; }       // the first launch then has nothing left to set up
     CU(cudaGraphLaunch(slot.exec, st));
     count_launch(slot.launches);
     return SB200_OK;
@@ -838,12 +838,13 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
             // priorities starve the odd chain, which then spills into the scan; digit kernels confined to SB200_ODD_SLOTS CTA slots
             // per SM make the contention last longer (1.01 ms/query at 2 slots against 0.94 unlimited).  Default: unlimited.
             static const int odd_slots = [] { const char *e = getenv("SB200_ODD_SLOTS"); return e ? atoi(e) : 0; }();
+            static const int odd_chunk = [] { const char *e = getenv("SB200_ODD_CHUNK"); return e ? atoi(e) : 740; }();   // ~one wave of NTT CTAs
             LaunchPriority low(false);                  // no-op unless SB200_PRIO=1 (experiments)
             if (wk) launch_query_from_wire(s->cv_o.p, s->q_wire.p, s->wire_kind, st);
             else launch_ntt_u64_to_dev(s->cv_o.p, s->q_stage.p, 2, st);
             if (shard) {
                 launch_expand(s->cv_o.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_os.p,
-                              s->offs_os.data(), s->cnt_os.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148);
+                              s->offs_os.data(), s->cnt_os.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148, odd_chunk);
                 GswTargets tg{};
                 tg.ntargets = s->world;
                 for (int t = 0; t < s->world; t++) {
@@ -858,7 +859,7 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
                 return;
             }
             launch_expand(s->cv_o.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_o.p,
-                          s->offs_o.data(), s->cnt_o.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148);
+                          s->offs_o.data(), s->cnt_o.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148, odd_chunk);
             // no GSW negation on the resident path: the fold uses the CMux form (launch_fold_round_generic)
             launch_regev_to_gsw(s->gsw.p, nullptr, s->cv_o.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
                                 s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, st);
@@ -1092,7 +1093,23 @@ extern "C" int sb200_server_xchg_export(sb200_server *s, void *handle_out) {
     memcpy(handle_out, h, sizeof h);
     return SB200_OK;
 }
+// CUDA loads kernels lazily, at their first launch, and loading may need a context-wide synchronisation - which never comes while
+// a kernel of this context is spinning on a flag that the not-yet-loaded kernel (or anything queued behind the load) would set.
+// Everything a sharded query launches is therefore loaded when the peers are connected, before any flag is waited for.
+template <typename K> static void preload_kernel(K *k) { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError(); }
+static void preload_exchange_kernels() {
+    preload_kernel(k_xchg_push); preload_kernel(k_xchg_wait); preload_kernel(k_xchg_ack); preload_kernel(k_flag_wait); preload_kernel(k_query_wait);
+    preload_kernel(k_reorient_dim1_allgather); preload_kernel(k_scal_to_mat_accum_tiled); preload_kernel(k_regev_to_gsw_accum_sharded);
+    preload_kernel(k_rescale2); preload_kernel(k_fold_decomp_ntt); preload_kernel(k_fold_mac); preload_kernel(k_fold_mac_wide); preload_kernel(k_fold_lift);
+    preload_kernel(k_from_ntt); preload_kernel(k_from_ntt_indexed); preload_kernel(k_gadget_ntt); preload_kernel(k_expand_prep); preload_kernel(k_expand_digits);
+    preload_kernel(k_expand_accum); preload_kernel(k_expand_accum_wide); preload_kernel(k_ntt_u64_to_dev); preload_kernel(k_query_from_wire);
+    preload_kernel(k_scan_spiral_jsplit); preload_kernel(k_scan_spiral<2, 128, 4, true>); preload_kernel(k_scan_spiral<2, 128, 4, false>);
+    preload_kernel(k_scan_spiral<2, 64, 4, false>); preload_kernel(k_scan_spiral<1, 128, 4, false>);
+    preload_kernel(k_scan_pack); preload_kernel(k_pack_accum); preload_kernel(k_split_rows); preload_kernel(k_simple_gsw_accum); preload_kernel(k_reorient_dim1);
+    cudaGetLastError();
+}
 static int xchg_finish_connect(sb200_server *s, const std::vector<void *> &bufs, const std::vector<void *> &queries, const std::vector<void *> &gsws) {
+    preload_exchange_kernels();
     s->peer_xb = bufs; s->peer_query = queries; s->peer_gsw = gsws;
     s->xchg_target = bufs[0];
     if (s->rank == 0) {

@@ -152,6 +152,7 @@ struct sb200_pack_server {
     size_t planes_total = 0;
     std::vector<int> plane_ids;                          // global plane index of each local plane
     int query_mode = 0;                                  // 1 packed query, 2 direct upload, 3 direct upload split over the ranks
+    bool query_wait_pending = false;
     // peer-memory exchange (xchg_kernels.cu), as sb200_server's
     DBuf<uint8_t> xchg;
     DBuf<unsigned int> xchg_state;                       // [0] epoch, [1] error
@@ -428,18 +429,23 @@ extern "C" int sb200_pack_server_upload_direct_split(sb200_pack_server *s, const
     cudaStream_t st = PS(s, stream);
     const size_t ell = s->prm.t_gsw, fd = s->prm.nu2, jc = s->dim0 / s->world;
     if (fd && !v_folding_host) return fail(SB200_ERR_ARG, "pack upload_direct_split: GSW ciphertexts missing");
+    // GSW ciphertexts first: the all-gather kernel may wait for rank 0's acknowledgement of the previous query, nothing should queue behind it
+    if (fd) { TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st)); CU(cudaStreamSynchronize(st)); }
     TRY(pack_up(s, s->cv, 0, v_firstdim_slice_host, jc * 2, st));
     launch_reorient_dim1_allgather(s->qpeers, s->cv.p, s->dim0, (size_t)s->rank * jc, jc, s->rank, s->world, s->xchg_state.p, s->xchg.p, st);
-    if (fd) { CU(cudaStreamSynchronize(st)); TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st)); }
     CHECK_LAUNCH();
     s->query_mode = 3;
+    s->query_wait_pending = true;        // the next scan waits for every rank's slice of THIS upload (later scans reuse the query)
     return SB200_OK;
 }
 // fastMultiplyQueryByDatabaseDim1 for all out_n^2 planes of the shard in one launch (src/testing.cpp:1045-1052)
 extern "C" int sb200_pack_server_scan(sb200_pack_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     for (size_t p = 0; p < s->planes; p++) if (!pack_plane_loaded(s, p)) return fail(SB200_ERR_STATE, "pack scan: database plane %zu not loaded", p);
-    if (s->query_mode == 3) launch_query_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, PS(s, stream));
+    if (s->query_mode == 3 && s->query_wait_pending) {
+        launch_query_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, PS(s, stream));
+        s->query_wait_pending = false;
+    }
     launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s), s->dim0, s->local_num_per, s->planes, s->plane_words, s->local_num_per * 2, PS(s, stream));
     CHECK_LAUNCH();
     return SB200_OK;
@@ -587,6 +593,7 @@ extern "C" int sb200_pack_server_xchg_export(sb200_pack_server *s, void *handle_
     return SB200_OK;
 }
 static int pack_xchg_finish(sb200_pack_server *s, const std::vector<void *> &bufs, const std::vector<void *> &queries) {
+    preload_exchange_kernels(); preload_kernel(k_gather_planes); preload_kernel(k_transpose_cts);
     s->xchg_target = bufs[0];
     for (int r = 0; r < s->world; r++) { s->qpeers.query[r] = (uint64_t *)queries[r]; s->qpeers.xb[r] = (XchgBuf *)bufs[r]; }
     if (s->rank == 0) {

@@ -145,7 +145,8 @@ void build_automorph_perms(uint16_t *perm_host, int g);      // host: g x 2048 s
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
                    const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
                    const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin = 0, int r_end = -1, int parity = -1,
-                   int store_self = 0, int slot_limit = 0);   // slot_limit > 0: the digit kernels never hold more than that many CTAs
+                   int store_self = 0, int slot_limit = 0, int digit_chunk = 0);   // slot_limit > 0: the digit kernels never hold more than that
+                                                                                   // many CTAs; digit_chunk > 0: big digit rounds in launches of ~that many
 int expand_split_lists(const ExpandPlan &p, const int *list, const int *offs, const int *cnt, int *list_e, int *offs_e, int *cnt_e,
                        int *list_o, int *offs_o, int *cnt_o);                    // even / odd chains of the expansion tree
 void build_neg1(uint32_t *neg1_dev, int count, cudaStream_t s);   // neg1[r] = NTT(-x^(N-2^r)), r < count, then their Shoup companions (2 * count polys)

@@ -86,15 +86,16 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
 }
 
 __global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restrict__ ginv, const uint64_t *__restrict__ c0_raw,
-                                                               const int *__restrict__ active, int t_left, int t_right, int tmax, int cnt) {
+                                                               const int *__restrict__ active, int t_left, int t_right, int tmax, int cnt, int k_begin) {
     pdl_prologue();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     // grid (cnt, tmax), or - for a chain that must not crowd out a concurrent, more urgent one - a smaller 1-D grid whose CTAs
     // walk the cnt x tmax items: the kernel then holds a fixed number of CTA slots instead of queueing thousands of CTAs ahead
     // of the other chain's
+    // k_begin >= 0: 2-D grid (cnt, digits of this launch), digit k = k_begin + blockIdx.y
     const int total = cnt * tmax;
-    for (int item = gridDim.y > 1 ? (int)(blockIdx.x * gridDim.y + blockIdx.y) : (int)blockIdx.x; item < total; item += gridDim.y > 1 ? total : (int)gridDim.x) {
+    for (int item = k_begin >= 0 ? (int)(blockIdx.x * tmax + k_begin + blockIdx.y) : (int)blockIdx.x; item < total; item += k_begin >= 0 ? total : (int)gridDim.x) {
         const int slot = item / tmax, k = item % tmax, i = active[slot];
         const int gd = (i & 1) ? t_right : t_left;
         if (k >= gd) continue;
@@ -291,7 +292,7 @@ size_t expand_ginv_polys(const ExpandPlan &p, const int *cnt) {
 }
 void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, const uint32_t *W_right,
                    const uint32_t *neg1, const uint16_t *perms, uint64_t *c0_raw, uint32_t *c1_ntt, uint32_t *ginv,
-                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end, int parity, int store_self, int slot_limit) {
+                   const int *list_dev, const int *offs, const int *cnt, cudaStream_t s, int r_begin, int r_end, int parity, int store_self, int slot_limit, int digit_chunk) {
     // parity: -1 = the lists hold every active ciphertext; 0 / 1 = they hold only the even / odd ones (expand_split_lists):
     // after round 0 the even chain (first-dimension ciphertexts, t_left digits) and the odd chain (GSW bits, t_right digits)
     // never touch each other's ciphertexts, so the two can run on different streams with their own scratch.
@@ -308,9 +309,18 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
         const int ty = parity == 1 ? p.t_right : any_odd ? tmax : p.t_left;
         count_launch(); launch_pdl(k_expand_prep, dim3(dim3(cnt[r], 2)), dim3(kNttThreads), 0, s, cv, act, 1 << r, neg1 + (size_t)r * 2 * kN, neg1 + (size_t)(p.g + r) * 2 * kN, tpow, perms + (size_t)r * kN, c0_raw, c1_ntt, store_self);
         // ginv is indexed [slot][ty]: rounds past stopround only hold t_left digits per slot (see expand_ginv_polys)
-        count_launch();
-        if (slot_limit > 0 && cnt[r] * ty > slot_limit) launch_pdl(k_expand_digits, dim3(slot_limit), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty, cnt[r]);
-        else launch_pdl(k_expand_digits, dim3(dim3(cnt[r], ty)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty, cnt[r]);
+        if (slot_limit > 0 && cnt[r] * ty > slot_limit) {
+            count_launch(); launch_pdl(k_expand_digits, dim3(slot_limit), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty, cnt[r], -1);
+        } else {
+            // digit_chunk > 0: a round with thousands of digit NTTs goes out as several launches of about digit_chunk CTAs, so that
+            // a concurrent chain's kernels wait behind one wave of this chain's CTAs, not behind all of them
+            int per = ty;
+            if (digit_chunk > 0 && cnt[r] * ty > 2 * digit_chunk) { per = digit_chunk / cnt[r]; if (per < 1) per = 1; }
+            for (int k0 = 0; k0 < ty; k0 += per) {
+                const int kn = k0 + per < ty ? per : ty - k0;
+                count_launch(); launch_pdl(k_expand_digits, dim3(dim3(cnt[r], kn)), dim3(kNttThreads), 0, s, ginv, c0_raw, act, p.t_left, p.t_right, ty, cnt[r], k0);
+            }
+        }
         count_launch();                                   // rounds with right slots (56-term chains) stay on the split kernel
         if (((cnt[r] >= 64 && !any_odd) || cnt[r] >= 512) && tmax <= 128) launch_pdl(k_expand_accum_wide, dim3(dim3(cnt[r], 4)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);
         else launch_pdl(k_expand_accum, dim3(dim3(cnt[r], 32)), dim3(256), 0, s, cv, act, ginv, c1_ntt, Wl, Wr, p.t_left, p.t_right, ty);

@@ -7,6 +7,8 @@ import pytest
 # other's flags.  With the default 8 hardware queues distinct streams can share a queue, and a waiting kernel then blocks the very
 # kernel it waits for.  Must be set before the CUDA context exists; one process per GPU (the deployed form) never needs it.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and lazy kernel loading may need a context-wide synchronisation that a spinning kernel of the same context never allows
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

@@ -269,8 +269,12 @@ def test_sharded_expansion_with_fused_all_gather(sb, oracle, cfg, nu1, nu2, worl
         want, _, _ = s.oracle_answer(q, Bbuf)
         resp.zero_()
         torch.cuda.synchronize()
-        for srv, st in list(zip(servers, streams))[::-1]:        # rank 0 last: its wait kernel needs the others' pushes
+        # all uploads first: a host-to-device copy from pageable memory can block the host behind ANOTHER shard's kernel that is
+        # spinning on a flag on this same device (one process per GPU with pinned buffers - the deployed form - never meets this)
+        for srv, st in zip(servers, streams):
             srv.upload_query(q, st.cuda_stream)
+        torch.cuda.synchronize()
+        for srv, st in list(zip(servers, streams))[::-1]:        # rank 0 last: its wait kernel needs the others' pushes
             srv.process(resp.data_ptr() if srv.rank == 0 else None, st.cuda_stream)
         torch.cuda.synchronize()
         errs = [srv.xchg_error() for srv in servers]
@@ -282,8 +286,11 @@ def test_sharded_expansion_with_fused_all_gather(sb, oracle, cfg, nu1, nu2, worl
     # the staged calls take the same path (join before returning from expand_and_convert)
     q = s.query(9)
     want, _, _ = s.oracle_answer(q, Bbuf)
-    for srv, st in list(zip(servers, streams))[::-1]:
-        srv.upload_query(q, st.cuda_stream); srv.expand_and_convert(st.cuda_stream); srv.first_dim(st.cuda_stream); srv.fold_local(st.cuda_stream)
+    for srv, st in zip(servers, streams):
+        srv.upload_query(q, st.cuda_stream)
+    torch.cuda.synchronize()
+    for srv, st in list(zip(servers, streams))[::-1]:            # first call of the staged form: its graphs exist already (same slots)
+        srv.expand_and_convert(st.cuda_stream); srv.first_dim(st.cuda_stream); srv.fold_local(st.cuda_stream)
         srv.exchange_and_tail(resp.data_ptr() if srv.rank == 0 else None, st.cuda_stream)
     torch.cuda.synchronize()
     assert all(srv.xchg_error() == 0 for srv in servers)
