@@ -1,9 +1,5 @@
-N=2
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N "$@"; }
-run --workload cfg4 --steps 20 --warmup 3 --sustained-s 0 > gpurun_out/m_bench_cfg4_${N}gpu.json 2> gpurun_out/m_bench_cfg4_${N}gpu.err
-grep -v "^\*\|W1017\|OMP" gpurun_out/m_bench_cfg4_${N}gpu.err | tail -5
-python - <<P
-import json
-d = json.load(open("gpurun_out/m_bench_cfg4_2gpu.json"))
-print("cfg4 N=2 ms/query", round(d["value"], 4), d["stages_ms"], "frac", round(d["roofline"]["frac"], 3), "e2e", round(d["e2e"]["value"], 4), d["e2e"], "verified", d["verified"]["decoded_equal_planted"], d["config"]["exchange"][:80])
-P
+python -m pytest tests -m gpu -q -x -k "not full_size and not dropin and not cli and not wire and not tc and not client" 2>&1 | tail -3
+python bench.py --steps 30 --warmup 3 --workloads "" --no-cpu-baseline --clients 0 --sustained-s 0 2>/dev/null | python -c "import json,sys; d=json.load(sys.stdin); print('ms/query', round(d['value'],4), {k: round(v,4) for k,v in d['stages_ms'].items()}, 'e2e', round(d['e2e']['value'],4), 'verified', d['verified']['decoded_equal_planted'])"
+SB200_PROFILE_SKIP_ODD_CHAIN=1 python scripts/trace_query.py cfg1 > gpurun_out/q_trace_marks.md 2>/dev/null
+head -24 gpurun_out/q_trace_marks.md | cut -c1-110
+python scripts/trace_query.py cfg1 > gpurun_out/q_trace_cfg1.md 2>/dev/null

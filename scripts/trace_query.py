@@ -34,7 +34,7 @@ def kernel_lines():
                 cur = None                                  # name on the next line
             elif cur is None and m and "launch" not in text:
                 cur = m.group(1)
-            if ("pdl_prologue()" in text or "pdl_prologue_no_early_dependents()" in text) and "#define" not in text and cur:
+            if ("pdl_prologue()" in text or "pdl_prologue_no_early_dependents()" in text or "pdl_wait()" in text) and "#define" not in text and cur:
                 out.setdefault(n, []).append(cur)
     return out
 
@@ -84,6 +84,9 @@ def main():
     for i, (ts, tr, shape) in enumerate(rec):
         shape = int(shape)
         gx, gy, bx, line = shape & 0xFFFFF, (shape >> 20) & 0xFFFF, (shape >> 36) & 0xFFF, shape >> 48
+        if line >= 0xF000:
+            print(f"| {i} | mark {line & 0xFFF} | | | | {(int(tr) - t0) / 1e3:.1f} | | |")
+            continue
         nxt = (int(rec[i + 1, 1]) - int(tr)) / 1e3 if i + 1 < len(rec) else 0.0
         print(f"| {i} | {'/'.join(names.get(line, ['?']))} | ({gx},{gy}) | {bx} | {(int(ts) - t0) / 1e3:.1f} | {(int(tr) - t0) / 1e3:.1f} | {nxt:.1f} | {(int(tr) - int(ts)) / 1e3:.1f} |")
     srv.close()

@@ -83,9 +83,22 @@ __constant__ TraceCtl c_trace;
 __device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // every kernel starts with pdl_prologue(); the macro passes the call site's line, which names the kernel in the trace
 #define pdl_prologue() pdl_prologue_at(__LINE__, true)
+// Split form for the kernels of the latency chains: pdl_begin() lets the dependents launch, then the kernel issues every load that
+// does NOT depend on its predecessor (index lists, keys, twiddles - constant during a query) and only then pdl_wait()s; that part
+// runs while the predecessor is still computing.
+#define pdl_begin() unsigned long long pdl_t0_ = pdl_begin_at()
+#define pdl_wait() pdl_wait_at(__LINE__, pdl_t0_)
 // for kernels that may SPIN on a flag written by another GPU (or, in single-device tests, by another stream): their dependents must
 // not be launched early - a pre-launched grid would sit in griddepcontrol.wait holding SM slots the flag's producer may need
 #define pdl_prologue_no_early_dependents() pdl_prologue_at(__LINE__, false)
+__device__ __forceinline__ unsigned long long pdl_begin_at() {
+    const bool tr = c_trace.buf != nullptr && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+    unsigned long long t0 = 0;
+    if (tr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    return t0;
+}
+__device__ __forceinline__ void pdl_wait_at(int line, unsigned long long t0);
 __device__ __forceinline__ void pdl_prologue_at(int line, bool early_dependents) {
     const bool tr = c_trace.buf != nullptr && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
     unsigned long long t0 = 0;
@@ -93,6 +106,25 @@ __device__ __forceinline__ void pdl_prologue_at(int line, bool early_dependents)
     if (early_dependents) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tr) {
+        const unsigned int i = atomicAdd(c_trace.counter, 1u);
+        if (i < c_trace.cap) {
+            c_trace.buf[3 * i] = t0; c_trace.buf[3 * i + 1] = global_timer_ns();
+            c_trace.buf[3 * i + 2] = (unsigned long long)(gridDim.x & 0xFFFFFu) | ((unsigned long long)(gridDim.y & 0xFFFFu) << 20) |
+                                     ((unsigned long long)(blockDim.x & 0xFFFu) << 36) | ((unsigned long long)(line & 0xFFFF) << 48);
+        }
+    }
+}
+
+// phase marks inside a kernel (timeline trace only): CTA (0,0,0), thread 0 appends {0, now, 0xF000 | id in the line field}
+__device__ __forceinline__ void trace_mark(int id) {
+    if (c_trace.buf != nullptr && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+        const unsigned int i = atomicAdd(c_trace.counter, 1u);
+        if (i < c_trace.cap) { c_trace.buf[3 * i] = 0; c_trace.buf[3 * i + 1] = global_timer_ns(); c_trace.buf[3 * i + 2] = (unsigned long long)(0xF000 | (id & 0xFFF)) << 48; }
+    }
+}
+__device__ __forceinline__ void pdl_wait_at(int line, unsigned long long t0) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (c_trace.buf != nullptr && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
         const unsigned int i = atomicAdd(c_trace.counter, 1u);
         if (i < c_trace.cap) {
             c_trace.buf[3 * i] = t0; c_trace.buf[3 * i + 1] = global_timer_ns();

@@ -201,9 +201,11 @@ __device__ __forceinline__ void intt_crt_store(uint32_t (&v)[16], uint32_t (*sm)
     }
 }
 __global__ void __launch_bounds__(kNttThreads) k_from_ntt(uint64_t *__restrict__ raw, const uint32_t *__restrict__ in) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
+    prefetch_twiddles(c_ntt.inv[n], lt);
+    pdl_wait();
     uint32_t v[16];
     load_ntt_regs(v, in + ((size_t)blockIdx.x * 2 + n) * kN, lt);
     intt_crt_store(v, sm, raw + (size_t)blockIdx.x * kN);
@@ -284,9 +286,11 @@ void launch_automorph(uint64_t *out, const uint64_t *in, size_t npolys, uint32_t
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNttThreads) k_gadget_ntt(uint32_t *__restrict__ out, const uint64_t *__restrict__ raw,
                                                             int mx, int rdim, int cols) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
+    prefetch_twiddles(c_ntt.fwd[n], lt);
+    pdl_wait();
     const int col = blockIdx.x, row = blockIdx.y;
     const int j = row % rdim, k = row / rdim;
     const uint32_t bits_per = get_bits_per(mx / rdim);

@@ -28,32 +28,41 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
                                                              const uint32_t *__restrict__ neg1, const uint32_t *__restrict__ neg1_shoup, uint32_t tpow,
                                                              const uint16_t *__restrict__ perm, uint64_t *__restrict__ c0_raw, uint32_t *__restrict__ c1_ntt,
                                                              int store_self) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
+    // constant during a query, loaded while the previous kernel is still running: the active list, the round's neg1 (+ Shoup
+    // companion), the inverse twiddles
     const int slot = blockIdx.x, row = blockIdx.y, i = active[slot];
-    uint32_t v[16];
+    const uint32_t q = modulus(n);
+    uint32_t v[16], w[16], ws[16];
+    load_ntt_regs(w, neg1 + n * kN, lt);
+    load_ntt_regs(ws, neg1_shoup + n * kN, lt);
+    // row 1: the slot permutation of this thread's 16 output positions (the loop below used to fetch them one by one, a chain of 16
+    // dependent L2 round trips - 5 us, the critical path of the whole kernel)
+    uint16_t pm[16];
+    if (row == 0) prefetch_twiddles(c_ntt.inv[n], lt);
+    else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) pm[k] = __ldg(perm + lt + kPlaneThreads * k);
+    }
+    pdl_wait();
     if (i < num_in) {
         // the reference writes cv[2^r + i] = x^(-2^r) * cv[i] whenever i is processed, even if 2^r + i
         // itself is skipped later in the round (src/spiral.cpp:1709) - so the producer stores it
         // neg1 is a constant of the round: the product is a Shoup multiplication (3 multiplies) instead of a 64-bit Barrett
-        uint32_t w[16], ws[16], nb[16];
-        const uint32_t q = modulus(n);
+        uint32_t nb[16];
         load_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
-        load_ntt_regs(w, neg1 + n * kN, lt);
-        load_ntt_regs(ws, neg1_shoup + n * kN, lt);
 #pragma unroll
         for (int e = 0; e < 16; e++) nb[e] = csub(mul_shoup_lazy(v[e], w[e], ws[e], q), q);
         store_ntt_regs(nb, cv + (((size_t)(i + num_in) * 2 + row) * 2 + n) * kN, lt);
     } else {
         // same product recomputed locally: no dependence on the producer CTA of this launch
-        uint32_t a[16], w[16], ws[16];
-        const uint32_t q = modulus(n);
+        uint32_t a[16];
         load_ntt_regs(a, cv + (((size_t)(i - num_in) * 2 + row) * 2 + n) * kN, lt);
-        load_ntt_regs(w, neg1 + n * kN, lt);
-        load_ntt_regs(ws, neg1_shoup + n * kN, lt);
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = csub(mul_shoup_lazy(a[e], w[e], ws[e], q), q);
+        trace_mark(1);
         // a chain that follows only its own subtree (odd / even graphs, a rank's share of a sharded expansion) may process
         // output i without its sibling i - num_in: then nobody else stores the base value the accumulation adds to
         if (store_self) store_ntt_regs(v, cv + (((size_t)i * 2 + row) * 2 + n) * kN, lt);
@@ -66,10 +75,13 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
         for (int k = 0; k < 16; k++) sm[n][ntt_pos(lt, k)] = v[k];
         plane_sync(n);
         uint32_t *dst = c1_ntt + ((size_t)slot * 2 + n) * kN;
-        for (int pos = lt; pos < kN; pos += kPlaneThreads) dst[pos] = sm[n][perm[pos]];
+#pragma unroll
+        for (int k = 0; k < 16; k++) dst[lt + kPlaneThreads * k] = sm[n][pm[k]];
         return;
     }
+    trace_mark(2);
     ntt_inverse_plane(v, sm[n], lt, n);
+    trace_mark(3);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
@@ -83,13 +95,16 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restric
         if ((it >> kLogN) & 1) val = kQ - val;                 // 0 -> Q on purpose (reference src/poly.cpp:256)
         c0_raw[(size_t)slot * kN + rem] = val;
     }
+    trace_mark(4);
 }
 
 __global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restrict__ ginv, const uint64_t *__restrict__ c0_raw,
                                                                const int *__restrict__ active, int t_left, int t_right, int tmax, int cnt, int k_begin) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
+    prefetch_twiddles(c_ntt.fwd[n], lt);                   // constant: fetched while the previous kernel is still running
+    pdl_wait();
     // grid (cnt, tmax), or - for a chain that must not crowd out a concurrent, more urgent one - a smaller 1-D grid whose CTAs
     // walk the cnt x tmax items: the kernel then holds a fixed number of CTA slots instead of queueing thousands of CTAs ahead
     // of the other chain's
@@ -108,15 +123,18 @@ __global__ void __launch_bounds__(kNttThreads) k_expand_digits(uint32_t *__restr
             const uint64_t d = gadget_digit(__ldg(src + nat_pos(lt, e)), k, bits_per, mask);
             v[e] = bits_per >= 28 ? raw_to_res(d, n) : (uint32_t)d;
         }
+        trace_mark(5);
         ntt_forward_plane(v, sm[n], lt, n);
+        trace_mark(6);
         store_ntt_regs(v, ginv + (((size_t)slot * tmax + k) * 2 + n) * kN, lt);
+        trace_mark(7);
     }
 }
 
 __global__ void __launch_bounds__(256) k_expand_accum(uint32_t *__restrict__ cv, const int *__restrict__ active, const uint32_t *__restrict__ ginv,
                                const uint32_t *__restrict__ c1_ntt, const uint32_t *__restrict__ W_left,
                                const uint32_t *__restrict__ W_right, int t_left, int t_right, int tmax) {
-    pdl_prologue();
+    pdl_begin();
     // grid (slot, row*16 + segment); CTA = 64 uint4 columns x 4 digit groups (same split as k_fold_mac: every
     // thread's loads are independent, partial sums meet in shared memory)
     __shared__ ulonglong2 part[3][64][2];
@@ -127,11 +145,28 @@ __global__ void __launch_bounds__(256) k_expand_accum(uint32_t *__restrict__ cv,
     const uint4 *W = reinterpret_cast<const uint4 *>(((i & 1) ? W_right : W_left) + (size_t)row * gd * 2 * kN) + w4;
     const uint4 *G = reinterpret_cast<const uint4 *>(ginv + (size_t)slot * tmax * 2 * kN) + w4;
     uint64_t acc[4] = {0, 0, 0, 0};
+    if (gd <= 8) {
+        // short chains (t_left = 8): this thread's key words (constant during a query) are in registers before the digits exist
+        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+        if (grp < gd) x0 = __ldg(W + (size_t)grp * (2 * kN / 4));
+        if (grp + 4 < gd) x1 = __ldg(W + (size_t)(grp + 4) * (2 * kN / 4));
+        pdl_wait();
+        if (grp < gd) {
+            const uint4 y = __ldg(G + (size_t)grp * (2 * kN / 4));
+            acc[0] += (uint64_t)x0.x * y.x; acc[1] += (uint64_t)x0.y * y.y; acc[2] += (uint64_t)x0.z * y.z; acc[3] += (uint64_t)x0.w * y.w;
+        }
+        if (grp + 4 < gd) {
+            const uint4 y = __ldg(G + (size_t)(grp + 4) * (2 * kN / 4));
+            acc[0] += (uint64_t)x1.x * y.x; acc[1] += (uint64_t)x1.y * y.y; acc[2] += (uint64_t)x1.z * y.z; acc[3] += (uint64_t)x1.w * y.w;
+        }
+    } else {
+        pdl_wait();
 #pragma unroll 4
-    for (int k = grp; k < gd; k += 4) {
-        const uint4 x = __ldg(W + (size_t)k * (2 * kN / 4)), y = __ldg(G + (size_t)k * (2 * kN / 4));
-        acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
-        acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
+        for (int k = grp; k < gd; k += 4) {
+            const uint4 x = __ldg(W + (size_t)k * (2 * kN / 4)), y = __ldg(G + (size_t)k * (2 * kN / 4));
+            acc[0] += (uint64_t)x.x * y.x; acc[1] += (uint64_t)x.y * y.y;
+            acc[2] += (uint64_t)x.z * y.z; acc[3] += (uint64_t)x.w * y.w;
+        }
     }
     if (grp > 0) {
         part[grp - 1][col][0] = make_ulonglong2(acc[0], acc[1]);
@@ -333,11 +368,14 @@ void launch_expand(uint32_t *cv, const ExpandPlan &p, const uint32_t *W_left, co
 // raw[slot] = from_ntt(poly src[poly_idx[slot]])
 __global__ void __launch_bounds__(kNttThreads) k_from_ntt_indexed(uint64_t *__restrict__ raw, const uint32_t *__restrict__ in,
                                                                   const int *__restrict__ poly_idx) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
+    const int poly = poly_idx[blockIdx.x];                 // constant index list: read before the previous kernel is done
+    prefetch_twiddles(c_ntt.inv[n], lt);
+    pdl_wait();
     uint32_t v[16];
-    load_ntt_regs(v, in + ((size_t)poly_idx[blockIdx.x] * 2 + n) * kN, lt);
+    load_ntt_regs(v, in + ((size_t)poly * 2 + n) * kN, lt);
     ntt_inverse_plane(v, sm[n], lt, n);
     __syncthreads();
 #pragma unroll

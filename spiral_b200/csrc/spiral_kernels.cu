@@ -501,9 +501,11 @@ struct FoldShape {
     int cmux;            // 1: resident path, C_lo + Q (x) (G^-1(C_hi) - G^-1(C_lo)); 0: the reference's two-product form
 };
 __global__ void __launch_bounds__(kNttThreads, 5) k_fold_decomp_ntt(uint32_t *__restrict__ scratch, const uint64_t *__restrict__ cts, FoldShape fs, int cts_per_plane) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
+    prefetch_twiddles(c_ntt.fwd[n], lt);                   // constant: fetched while the previous kernel is still running
+    pdl_wait();
     const int RC = fs.R * fs.Cc;
     // 1-D grid with the digit index fastest: the t CTAs that decompose the same polynomial run back to back, so all but the
     // first find it in L2 (with k slowest the re-reads were DRAM traffic: 8x the ciphertext bytes at SpiralPack sizes)
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(kNttThreads, 5) k_fold_decomp_ntt(uint32_t *__
 constexpr int kMacCols = 64, kMacGroups = 4;
 __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, const uint32_t *__restrict__ scratch,
                                                   const uint32_t *__restrict__ q_dev, const uint32_t *__restrict__ qneg_dev, FoldShape fs) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ ulonglong2 part[kMacGroups - 1][kMacCols][2];
     const int RC = fs.R * fs.Cc;
     const int op = blockIdx.x >> 4, seg = blockIdx.x & 15;
@@ -609,7 +611,25 @@ __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, co
     const uint4 *C1 = reinterpret_cast<const uint4 *>(scratch + (((size_t)(plane * 2 * fs.np + fs.np + i) * m2) * fs.Cc + c) * 2 * kN) + w4;
     uint64_t acc[4] = {0, 0, 0, 0};
     int cnt = 0;
-    if (fs.cmux) {        // scratch holds one difference-digit set per OUTPUT ciphertext (dense index plane*np + i)
+    if (fs.cmux && m2 <= 6 * kMacGroups) {
+        // short chains (t_GSW <= 8: at most six terms per thread): the GSW words - complete before this graph starts - are in
+        // registers before the digits of the previous kernel exist
+        const uint4 *Cd = reinterpret_cast<const uint4 *>(scratch + (((size_t)(plane * fs.np + i) * m2) * fs.Cc + c) * 2 * kN) + w4;
+        uint4 x[6];
+#pragma unroll
+        for (int t = 0; t < 6; t++) { const int m = grp + t * kMacGroups; x[t] = m < m2 ? __ldg(Qp + m * qs) : make_uint4(0, 0, 0, 0); }
+        pdl_wait();
+#pragma unroll
+        for (int t = 0; t < 6; t++) {
+            const int m = grp + t * kMacGroups;
+            if (m < m2) {
+                const uint4 y = __ldg(Cd + m * cs);
+                acc[0] += (uint64_t)x[t].x * y.x; acc[1] += (uint64_t)x[t].y * y.y;
+                acc[2] += (uint64_t)x[t].z * y.z; acc[3] += (uint64_t)x[t].w * y.w;
+            }
+        }
+    } else if (fs.cmux) {        // scratch holds one difference-digit set per OUTPUT ciphertext (dense index plane*np + i)
+        pdl_wait();
         const uint4 *Cd = reinterpret_cast<const uint4 *>(scratch + (((size_t)(plane * fs.np + i) * m2) * fs.Cc + c) * 2 * kN) + w4;
 #pragma unroll 4
         for (int m = grp; m < m2; m += kMacGroups) {
@@ -622,7 +642,8 @@ __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, co
                 for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
             }
         }
-    } else
+    } else {
+    pdl_wait();
 #pragma unroll 4
     for (int tm = grp; tm < 2 * m2; tm += kMacGroups) {
         const int h = tm >= m2, m = h ? tm - m2 : tm;
@@ -634,6 +655,7 @@ __global__ void __launch_bounds__(256) k_fold_mac(uint32_t *__restrict__ out, co
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
         }
+    }
     }
 #pragma unroll
     for (int e = 0; e < 4; e++) acc[e] = reduce_u64(acc[e], n);
@@ -684,9 +706,11 @@ __global__ void __launch_bounds__(256) k_fold_mac_wide(uint32_t *__restrict__ ou
 }
 // inverse NTT + CRT lift of the dense MAC outputs back into the (strided) ciphertext array
 __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict__ cts, const uint32_t *__restrict__ macout, FoldShape fs) {
-    pdl_prologue();
+    pdl_begin();
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
+    prefetch_twiddles(c_ntt.inv[n], lt);
+    pdl_wait();
     const int RC = fs.R * fs.Cc;
     const int id = blockIdx.x / RC, rc = blockIdx.x % RC;
     const int plane = id / fs.np, i = id % fs.np;
