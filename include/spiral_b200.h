@@ -145,6 +145,22 @@ int sb200_scalToMat(uint64_t *out_reg, const uint64_t *cv, const uint64_t *W, ui
 int sb200_regevToGSW(uint64_t *out, const uint64_t *cv_v, uint32_t t_conv, uint32_t t, const uint64_t *W,
                      const uint64_t *V);                                                            /* src/spiral.cpp:1985-2025 */
 
+typedef struct sb200_server sb200_server;      /* the resident server, tier 3 below */
+/* resident forms of the leaves of process_query_fast (src/spiral.cpp:1584-1629) for a drop-in host that must keep the reference's
+ * call sequence: the intermediates stay in HBM between the leaves and the harness's own host pointers are only
+ * KEYS naming what is resident.  A leaf whose input key does not match returns SB200_ERR_STATE - call the stateless form then.
+ *   reorientCiphertexts      uploads the 2^nu1 converted ciphertexts, leaves the reoriented query resident under out_key
+ *   multiplyQueryByDatabase  scans the resident database with the resident query; result resident under out_key
+ *   nttInvAndCrtLift...      lifts the resident scan output; ciphertexts resident under cts_key (= furtherDimsLocals.cts)
+ *   reorient_Q               one GSW ciphertext (n1 x m2 ref-NTT, the INPUT of the reference's reorient_Q) resident under out_key
+ *   foldOneFurtherDimension  one fold round (the reference's two-product form, arbitrary q_neg); the last round (num_per == 1)
+ *                            downloads the surviving ciphertext into cts_host, which check_final / modswitch read */
+int sb200_resident_reorientCiphertexts(sb200_server *srv, const void *out_key, const uint64_t *inp_ref_ntt_host, size_t dim0);
+int sb200_resident_multiplyQueryByDatabase(sb200_server *srv, const void *out_key, const void *reoriented_key);
+int sb200_resident_nttInvAndCrtLiftCiphertexts(sb200_server *srv, const void *cts_key, const void *scratch_key);
+int sb200_resident_reorient_Q(sb200_server *srv, const void *out_key, const uint64_t *inp_ref_ntt_host);
+int sb200_resident_foldOneFurtherDimension(sb200_server *srv, size_t num_per, const void *q_key, const void *q_neg_key, uint64_t *cts_host);
+
 /* SpiralPack / SpiralStreamPack leaves (src/testing.cpp) */
 int sb200_convertDb(uint64_t *db_buf, const uint64_t *db_ref_ntt, size_t count, size_t dim0, size_t num_per);          /* :316-340 */
 int sb200_reorientCiphertextsDim1(uint64_t *out, const uint64_t *v_firstdim, size_t count, size_t dim0, size_t idx_factor); /* :342-362 */

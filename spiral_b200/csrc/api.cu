@@ -533,6 +533,11 @@ struct sb200_server {
     int nbits_local = 0;
     std::vector<void *> peer_query, peer_xb, peer_gsw;  // every rank's query buffer / exchange header / GSW buffer as seen from here
     bool shard_eligible = false, query_sharded = false, gsw_wait_pending = false;
+    // resident drop-in (sb200_resident_*): which HOST buffers of the reference harness currently live in this server's device
+    // buffers instead (keys are the harness's own pointers; the host copies are stale until a leaf downloads them)
+    const void *res_query_key = nullptr, *res_scan_key = nullptr, *res_cts_key = nullptr;
+    std::vector<std::pair<const void *, DBuf<uint32_t> *>> res_gsw;     // reorient_Q outputs -> dev-NTT GSW ciphertexts
+    DBuf<uint32_t> res_cts_in;                                          // staging of the 2^nu1 ScalToMat outputs (dev-NTT)
     // stream = NULL means "the legacy default stream", which cannot be captured: such calls run on this
     // BLOCKING stream instead (implicitly ordered with legacy-default-stream work, e.g. torch's default stream)
     cudaStream_t own_stream = nullptr, aux_stream = nullptr;
@@ -549,6 +554,7 @@ struct sb200_server {
     bool xchg_connected = false;
     GraphSlot g_xchg;
     ~sb200_server() {
+        for (auto &e : res_gsw) delete e.second;
         if (own_stream) cudaStreamDestroy(own_stream);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -1206,6 +1212,75 @@ extern "C" int sb200_server_xchg_reset(sb200_server *s) {
     CU(cudaDeviceSynchronize());
     return SB200_OK;
 }
+// ---------------------------------------------------------------------------------------------
+// resident drop-in: the leaf functions of process_query_fast (src/spiral.cpp:1584-1629) driven by the
+// UNMODIFIED harness, with every intermediate staying in HBM between the leaves.  The harness's host buffers are only KEYS here:
+// a leaf whose input key matches what the previous leaf left on the device skips the upload, and nothing is downloaded until
+// un-interposed host code needs it (the final ciphertext, 96 KiB).  A mismatch returns SB200_ERR_STATE and the caller falls back
+// to the stateless sb200_<refname> call, so correctness never depends on the harness's call order.
+// ---------------------------------------------------------------------------------------------
+extern "C" int sb200_resident_reorientCiphertexts(sb200_server *s, const void *out_key, const uint64_t *inp_ref_ntt_host, size_t dim0) {
+    if (!s || !out_key || !inp_ref_ntt_host) return fail(SB200_ERR_ARG, "resident reorientCiphertexts: null argument");
+    if (dim0 != s->dim0 || s->world != 1) return fail(SB200_ERR_STATE, "resident reorientCiphertexts: shape differs from the resident server");
+    CU(cudaSetDevice(s->device));
+    if (!s->res_cts_in.p) CU(s->res_cts_in.alloc(s->dim0 * kN1 * 2 * PLW));
+    TRY(server_up_ntt(s, s->res_cts_in, inp_ref_ntt_host, s->dim0 * kN1 * 2));
+    launch_reorient_query(s->query.p, s->res_cts_in.p, s->dim0, 0); CHECK_LAUNCH();
+    CU(cudaDeviceSynchronize());
+    s->res_query_key = out_key; s->res_scan_key = s->res_cts_key = nullptr;
+    return SB200_OK;
+}
+extern "C" int sb200_resident_multiplyQueryByDatabase(sb200_server *s, const void *out_key, const void *reoriented_key) {
+    if (!s || !out_key) return fail(SB200_ERR_ARG, "resident multiplyQueryByDatabase: null argument");
+    if (!s->res_query_key || reoriented_key != s->res_query_key) return fail(SB200_ERR_STATE, "resident multiplyQueryByDatabase: the query is not resident");
+    if (!server_has_db(s)) return fail(SB200_ERR_STATE, "resident multiplyQueryByDatabase: database not loaded");
+    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, 0, server_z_slices(s)); CHECK_LAUNCH();
+    CU(cudaDeviceSynchronize());                       // the harness's timer brackets the call
+    s->res_scan_key = out_key; s->res_cts_key = nullptr;
+    return SB200_OK;
+}
+extern "C" int sb200_resident_nttInvAndCrtLiftCiphertexts(sb200_server *s, const void *cts_key, const void *scratch_key) {
+    if (!s || !cts_key) return fail(SB200_ERR_ARG, "resident nttInvAndCrtLiftCiphertexts: null argument");
+    if (!s->res_scan_key || scratch_key != s->res_scan_key) return fail(SB200_ERR_STATE, "resident nttInvAndCrtLiftCiphertexts: the scan output is not resident");
+    launch_from_ntt(s->cts.p, s->scan_out.p, s->local_num_per * 6, 0); CHECK_LAUNCH();
+    CU(cudaDeviceSynchronize());
+    s->res_cts_key = cts_key;
+    return SB200_OK;
+}
+// reorient_Q(out, inp) (src/spiral.cpp:388-400): inp = one GSW ciphertext (n1 x m2, ref-NTT); its dev-NTT copy is registered under `out`
+extern "C" int sb200_resident_reorient_Q(sb200_server *s, const void *out_key, const uint64_t *inp_ref_ntt_host) {
+    if (!s || !out_key || !inp_ref_ntt_host) return fail(SB200_ERR_ARG, "resident reorient_Q: null argument");
+    CU(cudaSetDevice(s->device));
+    const size_t polys = (size_t)kN1 * kN1 * s->prm.t_gsw;
+    DBuf<uint32_t> *buf = nullptr;
+    for (auto &e : s->res_gsw) if (e.first == out_key) buf = e.second;
+    if (!buf) {
+        if (s->res_gsw.size() >= 4 * (size_t)s->prm.nu2 + 8) {        // keys of earlier queries (the harness mallocs fresh buffers per query)
+            for (auto &e : s->res_gsw) delete e.second;
+            s->res_gsw.clear();
+        }
+        buf = new DBuf<uint32_t>();
+        cudaError_t e = buf->alloc(polys * PLW);
+        if (e != cudaSuccess) { delete buf; return fail(SB200_ERR_CUDA, "resident reorient_Q: %s", cudaGetErrorString(e)); }
+        s->res_gsw.emplace_back(out_key, buf);
+    }
+    return server_up_ntt(s, *buf, inp_ref_ntt_host, polys);
+}
+// foldOneFurtherDimension on the resident ciphertexts; q_key / q_neg_key: the reorient_Q outputs of THIS dimension.  When one
+// ciphertext is left (num_per == 1) it is downloaded into cts_host (the harness's check_final / modswitch read it there).
+extern "C" int sb200_resident_foldOneFurtherDimension(sb200_server *s, size_t num_per, const void *q_key, const void *q_neg_key, uint64_t *cts_host) {
+    if (!s || !cts_host) return fail(SB200_ERR_ARG, "resident foldOneFurtherDimension: null argument");
+    if (!s->res_cts_key || (const void *)cts_host != s->res_cts_key) return fail(SB200_ERR_STATE, "resident foldOneFurtherDimension: the ciphertexts are not resident");
+    const uint32_t *q = nullptr, *qn = nullptr;
+    for (auto &e : s->res_gsw) { if (e.first == q_key) q = e.second->p; if (e.first == q_neg_key) qn = e.second->p; }
+    if (!q || !qn) return fail(SB200_ERR_STATE, "resident foldOneFurtherDimension: the GSW ciphertexts are not resident");
+    if (2 * num_per > s->local_num_per) return fail(SB200_ERR_ARG, "resident foldOneFurtherDimension: num_per too large");
+    launch_fold_round(s->cts.p, num_per, q, qn, (int)s->prm.t_gsw, s->fold_scratch.p, 0); CHECK_LAUNCH();   // the reference's two-product form
+    if (num_per == 1) CU(cudaMemcpy(cts_host, s->cts.p, 6 * (size_t)kN * 8, cudaMemcpyDeviceToHost));
+    else CU(cudaDeviceSynchronize());
+    return SB200_OK;
+}
+
 extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_host, uint64_t *total_resp_host, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer: single-shard call on a sharded server (use the staged API)");

@@ -24,6 +24,9 @@
 static const size_t N = 2048, PL = 4096;
 static const uint64_t P = 268369921ull, Bq = 249561089ull;
 
+// resident mode (default when not checking parity): the leaves of process_query_fast keep their intermediates in HBM between
+// calls (sb200_resident_*); SB200_RESIDENT=0 restores one H2D + D2H per leaf
+static bool resident_mode() { static int v = -1; if (v < 0) { const char *e = getenv("SB200_RESIDENT"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
 static bool parity_mode() { static int v = -1; if (v < 0) { const char *e = getenv("SB200_PARITY"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
 static void die(const char *what) { fprintf(stderr, "[spiral_b200] %s: %s\n", what, sb200_last_error()); abort(); }
 #define OKAY(call) do { if ((call) != 0) die(#call); } while (0)
@@ -112,6 +115,7 @@ void load_db() {
 
 // ---- reorientCiphertexts (src/spiral.cpp:410)
 void reorientCiphertexts(uint64_t *out, const uint64_t *inp, size_t dim0, size_t n1_padded) {
+    if (g_srv && resident_mode() && !parity_mode() && n1_padded == 4 && sb200_resident_reorientCiphertexts(g_srv, out, inp, dim0) == 0) return;
     OKAY(sb200_reorientCiphertexts(out, inp, dim0, n1_padded));
     if (parity_mode()) {
         std::vector<uint64_t> ref(dim0 * 2 * n1_padded * N, 0);
@@ -123,6 +127,8 @@ void reorientCiphertexts(uint64_t *out, const uint64_t *inp, size_t dim0, size_t
 // ---- multiplyQueryByDatabase (src/spiral.cpp:628): scan of the RESIDENT database when `database`
 // is the buffer registered by load_db, otherwise the stateless call
 void multiplyQueryByDatabase(uint64_t *output, const uint64_t *reorientedCiphertexts, const uint64_t *database, size_t dim0, size_t num_per) {
+    // resident: the reoriented query is already in HBM (left there by reorientCiphertexts), the result stays there for the lift
+    if (g_srv && database == B && resident_mode() && !parity_mode() && sb200_resident_multiplyQueryByDatabase(g_srv, output, reorientedCiphertexts) == 0) return;
     if (g_srv && database == B) OKAY(sb200_server_scan_host(g_srv, reorientedCiphertexts, output));
     else OKAY(sb200_multiplyQueryByDatabase(output, reorientedCiphertexts, database, dim0, num_per));
     if (parity_mode()) {
@@ -134,6 +140,7 @@ void multiplyQueryByDatabase(uint64_t *output, const uint64_t *reorientedCiphert
 
 // ---- nttInvAndCrtLiftCiphertexts (src/spiral.cpp:437): locals passed by value
 void nttInvAndCrtLiftCiphertexts(size_t num_per, FurtherDimsLocals locals) {
+    if (g_srv && resident_mode() && !parity_mode() && sb200_resident_nttInvAndCrtLiftCiphertexts(g_srv, locals.cts, locals.scratch_cts1) == 0) return;
     std::vector<uint64_t> ref_in;
     if (parity_mode()) ref_in.assign(locals.scratch_cts1, locals.scratch_cts1 + num_per * 6 * PL);
     OKAY(sb200_nttInvAndCrtLiftCiphertexts(locals.cts, locals.scratch_cts1, num_per));
@@ -147,6 +154,9 @@ void nttInvAndCrtLiftCiphertexts(size_t num_per, FurtherDimsLocals locals) {
 
 // ---- foldOneFurtherDimension (src/spiral.cpp:1349)
 void foldOneFurtherDimension(size_t cur_dim, size_t num_per, const uint64_t *query_ct, const uint64_t *query_ct_neg, FurtherDimsLocals locals) {
+    const size_t q_stride = (size_t)3 * 3 * TGSW * 2 * N;       // words between the dimensions' reoriented GSW ciphertexts (:2385-2386)
+    if (g_srv && resident_mode() && !parity_mode() &&
+        sb200_resident_foldOneFurtherDimension(g_srv, num_per, query_ct + cur_dim * q_stride, query_ct_neg + cur_dim * q_stride, locals.cts) == 0) return;
     std::vector<uint64_t> before;
     if (parity_mode()) before.assign(locals.cts, locals.cts + 2 * num_per * 6 * N);
     OKAY(sb200_foldOneFurtherDimension(cur_dim, num_per, query_ct, query_ct_neg, locals.cts, TGSW));
@@ -156,6 +166,13 @@ void foldOneFurtherDimension(size_t cur_dim, size_t num_per, const uint64_t *que
         next_sym<void (*)(size_t, size_t, const uint64_t *, const uint64_t *, FurtherDimsLocals)>("_Z23foldOneFurtherDimensionmmPKmS0_17FurtherDimsLocals")(cur_dim, num_per, query_ct, query_ct_neg, locals);
         cmp_raw("foldOneFurtherDimension", got.data(), locals.cts, got.size());
     }
+}
+
+// ---- reorient_Q (src/spiral.cpp:388): the host relayout stays the reference's; in resident mode the GSW ciphertext it was handed
+// (n1 x m2, NTT form) also goes to HBM, registered under the output pointer foldOneFurtherDimension will pass back
+void reorient_Q(uint64_t *out, const uint64_t *inp) {
+    next_sym<void (*)(uint64_t *, const uint64_t *)>("_Z10reorient_QPmPKm")(out, inp);
+    if (g_srv && resident_mode() && !parity_mode()) OKAY(sb200_resident_reorient_Q(g_srv, out, inp));
 }
 
 // ---- expandImproved (src/spiral.cpp:1664): returns its own elapsed microseconds (appendix C.1)

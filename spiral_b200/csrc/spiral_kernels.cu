@@ -710,10 +710,18 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict_
     __shared__ __align__(16) uint32_t sm[2][kPlaneWords];
     const int n = plane_of_thread(), lt = lane_in_plane();
     prefetch_twiddles(c_ntt.inv[n], lt);
-    pdl_wait();
     const int RC = fs.R * fs.Cc;
     const int id = blockIdx.x / RC, rc = blockIdx.x % RC;
     const int plane = id / fs.np, i = id % fs.np;
+    uint64_t *dst = cts + ((size_t)(plane * fs.plane_stride + i) * RC + rc) * kN;
+    // C_lo was written two kernels ago (the previous round's lift, or the first lift) and nothing in between touches it: it is
+    // fetched before the MAC kernel this one depends on has finished
+    uint64_t clo[8];
+    if (fs.cmux) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) clo[k] = dst[threadIdx.x + 256 * k];
+    }
+    pdl_wait();
     uint32_t v[16];
     load_ntt_regs(v, macout + ((size_t)blockIdx.x * 2 + n) * kN, lt);
     ntt_inverse_plane(v, sm[n], lt, n);
@@ -721,13 +729,12 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict_
 #pragma unroll
     for (int k = 0; k < 16; k++) sm[n][nat_pos(lt, k)] = v[k];
     __syncthreads();
-    uint64_t *dst = cts + ((size_t)(plane * fs.plane_stride + i) * RC + rc) * kN;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int z = threadIdx.x + 256 * k;
         uint64_t val = crt_compose(sm[0][z], sm[1][z]);
         if (fs.cmux) {                      // + C_lo (G * G^-1(C_lo) = C_lo mod Q), canonical result
-            uint64_t lo = dst[z];
+            uint64_t lo = clo[k];
             lo = lo >= kQ ? lo - kQ : lo;
             val += lo;
             val = val >= kQ ? val - kQ : val;

@@ -115,6 +115,11 @@ def load_library():
         "sb200_foldCiphertextsDim1": (C.c_int, [u64p, sz, u64p, u64p, C.c_uint32]),
         "sb200_regevToSimpleGsw": (C.c_int, [u64p, u64p, sz, u64p, C.c_uint32, C.c_uint32, C.c_uint32, sz, sz]),
         "sb200_pack": (C.c_int, [u64p, C.c_uint32, C.c_uint32, u64p, u64p]),
+        "sb200_resident_reorientCiphertexts": (C.c_int, [vp, vp, u64p, sz]),
+        "sb200_resident_multiplyQueryByDatabase": (C.c_int, [vp, vp, vp]),
+        "sb200_resident_nttInvAndCrtLiftCiphertexts": (C.c_int, [vp, vp, vp]),
+        "sb200_resident_reorient_Q": (C.c_int, [vp, vp, u64p]),
+        "sb200_resident_foldOneFurtherDimension": (C.c_int, [vp, sz, vp, vp, u64p]),
         # tier 3
         "sb200_pack_server_create": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int]),
         "sb200_pack_server_create_sharded": (C.c_int, [C.POINTER(vp), C.POINTER(SpiralParams), C.c_int, C.c_int, C.c_int]),
