@@ -83,9 +83,10 @@ __constant__ TraceCtl c_trace;
 __device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // every kernel starts with pdl_prologue(); the macro passes the call site's line, which names the kernel in the trace
 #define pdl_prologue() pdl_prologue_at(__LINE__, true)
-// Split form for the kernels of the latency chains: pdl_begin() lets the dependents launch, then the kernel issues every load that
-// does NOT depend on its predecessor (index lists, keys, twiddles - constant during a query) and only then pdl_wait()s; that part
-// runs while the predecessor is still computing.
+// Split form for the kernels of the latency chains: pdl_begin() lets the dependents launch, then the kernel issues loads of data
+// that is CONSTANT FOR THE WHOLE QUERY (index lists, keys, twiddles, permutations) and only then pdl_wait()s; that part runs while
+// the predecessor is still computing.  Nothing written during the query may be touched before the wait, however many kernels ago:
+// early launches cascade, so a kernel can be resident while a kernel several links back in the chain is still running.
 #define pdl_begin() unsigned long long pdl_t0_ = pdl_begin_at()
 #define pdl_wait() pdl_wait_at(__LINE__, pdl_t0_)
 // for kernels that may SPIN on a flag written by another GPU (or, in single-device tests, by another stream): their dependents must

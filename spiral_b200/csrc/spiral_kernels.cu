@@ -714,14 +714,14 @@ __global__ void __launch_bounds__(kNttThreads) k_fold_lift(uint64_t *__restrict_
     const int id = blockIdx.x / RC, rc = blockIdx.x % RC;
     const int plane = id / fs.np, i = id % fs.np;
     uint64_t *dst = cts + ((size_t)(plane * fs.plane_stride + i) * RC + rc) * kN;
-    // C_lo was written two kernels ago (the previous round's lift, or the first lift) and nothing in between touches it: it is
-    // fetched before the MAC kernel this one depends on has finished
+    // NOTE: only data that is constant for the whole query may be read before pdl_wait(): early launches cascade (this kernel can be
+    // resident while the lift TWO rounds back is still writing), so C_lo - written "two kernels ago" - is read after the wait
+    pdl_wait();
     uint64_t clo[8];
     if (fs.cmux) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) clo[k] = dst[threadIdx.x + 256 * k];
+        for (int k = 0; k < 8; k++) clo[k] = dst[threadIdx.x + 256 * k];      // in flight during the inverse transform
     }
-    pdl_wait();
     uint32_t v[16];
     load_ntt_regs(v, macout + ((size_t)blockIdx.x * 2 + n) * kN, lt);
     ntt_inverse_plane(v, sm[n], lt, n);
