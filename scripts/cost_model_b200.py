@@ -16,6 +16,7 @@ dimension, a (nu_1, nu_2) the reference itself certified for the same gadget par
     python scripts/cost_model_b200.py measure --out gpurun_out/shape_sweep.json
     python scripts/cost_model_b200.py fit profiles/r01_shape_sweep.json --out profiles/r01_cost_model_b200.json
     python scripts/cost_model_b200.py select profiles/r01_cost_model_b200.json --log-items 15
+    python scripts/cost_model_b200.py emit profiles/r01_cost_model_b200.json /path/to/all_parameter_choices.txt --out profiles/b200_parameter_choices.txt
 """
 import argparse
 import json
@@ -178,6 +179,75 @@ def cmd_select(args):
         print(f"B200 optimum: {rows[0][1]} nu=({rows[0][2]},{rows[0][3]});  CPU-model optimum: {best_ref[1]} nu=({best_ref[2]},{best_ref[3]})")
 
 
+# ---- emit: the B200 choice in the form select_params.py's consumers read ------------------------------------------------------
+# all_parameter_choices.txt is a "/* Table */" line followed by a JSON object: "(log2 records, record bytes)" -> scheme -> {"params":
+# {nu_1, nu_2, p, q_prime_bits, query_size, s_e, t_GSW, t_conv, t_exp, t_exp_right}} (all_parameter_choices.txt:1-80; run_all.py
+# and select_params.py:300-340 look entries up by that key).  For every "spiral" entry whose gadget lengths are a set this model
+# was fitted on, the record count is kept (nu_1 + nu_2 unchanged) and the split is re-chosen by the B200 model among the shapes the
+# reference certified for those gadgets; everything else in the entry is copied.
+def best_split(model, total_nu, g):
+    cands = []
+    for nu1 in range(1, 12):
+        nu2 = total_nu - nu1
+        if nu2 < 1 or not feasible(nu1, nu2, g) or nu1 > g["max_nu1"] or nu2 > g["max_nu2"]:
+            continue
+        if nu2 < 5 and model["coef"]["scan"][3] == 0.0:
+            continue                                         # scan tiling not covered by the sweep
+        cands.append((sum(predict(model, nu1, nu2, g).values()), nu1, nu2))
+    return min(cands) if cands else None
+
+
+def emit_choices(model, table):
+    """table: the reference's dict; returns a dict of the same shape with the entries this model can re-choose."""
+    out = {}
+    for key, schemes in table.items():
+        ent = schemes.get("spiral", {}).get("params")
+        if not ent:
+            continue
+        match = [g for g in GADGETS.values() if (g["t_gsw"], g["t_conv"], g["t_exp"], g["t_exp_right"], g["qp_bits"], g["p_db"]) ==
+                 (ent["t_GSW"], ent["t_conv"], ent["t_exp"], ent["t_exp_right"], ent["q_prime_bits"], ent["p"])]
+        if not match:
+            continue
+        best = best_split(model, ent["nu_1"] + ent["nu_2"], match[0])
+        if best is None:
+            continue
+        new = dict(ent, nu_1=best[1], nu_2=best[2])
+        ref_us = sum(predict(model, ent["nu_1"], ent["nu_2"], match[0]).values())
+        out[key] = {"spiral": {"params": new, "b200_model_us": round(best[0], 1), "reference_choice": {"nu_1": ent["nu_1"], "nu_2": ent["nu_2"],
+                                                                                                      "b200_model_us": round(ref_us, 1)}}}
+    return out
+
+
+def parse_choices(text):
+    """all_parameter_choices.txt -> [(section name, dict), ...]: sections are a C comment line followed by one or more JSON objects."""
+    out, pos, name, dec = [], 0, "", json.JSONDecoder()
+    while True:
+        while pos < len(text) and text[pos] in " \t\r\n":
+            pos += 1
+        if pos >= len(text):
+            return out
+        if text.startswith("/*", pos):
+            end = text.index("*/", pos)
+            name, pos = text[pos + 2:end].strip(), end + 2
+            continue
+        obj, pos = dec.raw_decode(text, pos)
+        out.append((name, obj))
+
+
+def cmd_emit(args):
+    model = json.load(open(args.model))
+    with open(args.out, "w") as f:
+        for name, table in parse_choices(open(args.table).read()):
+            out = emit_choices(model, table)
+            if not out:
+                continue
+            f.write(f"/* {name} */\n" + json.dumps(out, indent=4, sort_keys=True) + "\n")
+            for k, v in sorted(out.items()):
+                p, r = v["spiral"]["params"], v["spiral"]["reference_choice"]
+                print(f"[{name}] {k}: B200 ({p['nu_1']},{p['nu_2']}) {v['spiral']['b200_model_us']} us;  reference ({r['nu_1']},{r['nu_2']}) "
+                      f"{r['b200_model_us']} us on the B200 model")
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -185,8 +255,10 @@ def main():
     m.add_argument("--shapes", default="", help='subset, e.g. "cfg1:9,6;cfg1:10,5"')
     f = sub.add_parser("fit"); f.add_argument("sweep"); f.add_argument("--out", default="profiles/cost_model_b200.json")
     s = sub.add_parser("select"); s.add_argument("model"); s.add_argument("--log-items", type=int, default=15)
+    e = sub.add_parser("emit"); e.add_argument("model"); e.add_argument("table", help="the reference's all_parameter_choices.txt")
+    e.add_argument("--out", default="profiles/b200_parameter_choices.txt")
     args = ap.parse_args()
-    {"measure": cmd_measure, "fit": cmd_fit, "select": cmd_select}[args.cmd](args)
+    {"measure": cmd_measure, "fit": cmd_fit, "select": cmd_select, "emit": cmd_emit}[args.cmd](args)
 
 
 if __name__ == "__main__":

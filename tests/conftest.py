@@ -21,7 +21,7 @@ def pytest_configure(config):
 
 # Run order: the oracle's own pins first, then the hot path from its leaves outwards (parity cases, whole queries, full
 # sizes, Pack, tensor cores, the reference harness), then the rows of SURVEY 8f that sit either side of the path.
-_ORDER = ["test_abi", "test_oracle_golden", "test_oracle_e2e", "test_oracle_wire", "test_wire_host", "test_shard_gloo", "test_gpu_parity", "test_gpu_e2e",
+_ORDER = ["test_abi", "test_cost_model", "test_oracle_golden", "test_oracle_e2e", "test_oracle_wire", "test_wire_host", "test_shard_gloo", "test_gpu_parity", "test_gpu_e2e",
           "test_gpu_fullsize", "test_gpu_pack", "test_gpu_tc", "test_gpu_dropin", "test_gpu_wire", "test_gpu_client", "test_gpu_cli", "test_gpu_pack_client"]
 
 
