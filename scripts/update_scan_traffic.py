@@ -20,12 +20,15 @@ CAPS = {  # capture -> (json key, description, algorithmic bytes)
     "scan_pack_cfg4": ("dram_bytes_per_launch_cfg4_1gpu", "k_scan_pack, cfg4 ./spiral 11 3 (25 planes x 8 columns, 6.25 GiB)", 25 * 8 * 2048 * (1 << 14)),
     "scan_pack_cfg3": ("dram_bytes_per_launch_cfg3_1gpu", "k_scan_pack, cfg3 ./spiral 10 8 (16 planes x 256 columns, 64 GiB)", 64 << 30),
 }
-METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-           "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-           "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct",
-           "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
-           "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
-           "sm__maximum_warps_per_active_cycle_pct", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+           "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+           "lts__t_sector_hit_rate.pct",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 
 
 def to_bytes(val, unit):
@@ -62,7 +65,7 @@ def main():
         rd, wr = to_bytes(*d["dram__bytes_read.sum"]), to_bytes(*d["dram__bytes_write.sum"])
         tj[key] = rd + wr
         dur_v, dur_u = d["gpu__time_duration.sum"]
-        dur_us = float(dur_v.replace(",", "")) * {"nsecond": 1e-3, "usecond": 1, "msecond": 1e3, "second": 1e6}.get(dur_u, 1)
+        dur_us = float(dur_v.replace(",", "")) * {"ns": 1e-3, "nsecond": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(dur_u, 1)
         md += [f"## {desc}", "", f"kernel `{d.get('Kernel Name', ('?', ''))[0]}`", "", "| metric | value |", "|---|---:|",
                f"| duration | {dur_us:.1f} us |", f"| algorithmic bytes | {algo / 1e9:.3f} GB |", f"| DRAM traffic (read + write) | {(rd + wr) / 1e9:.3f} GB ({(rd + wr) / algo:.3f} x algorithmic) |",
                f"| GB/s under the profiler (algorithmic / duration) | {algo / dur_us / 1e3:.0f} |"]

@@ -312,6 +312,82 @@ __global__ void __launch_bounds__(128) k_scan_spiral_jsplit(uint32_t *__restrict
         }
     }
 }
+// The same with the shard's shape as compile-time constants (IC = 16 / 32 / 64 columns, JS j-groups, ZT z-slices per CTA) and eight
+// resident CTAs per SM.  ncu of the run-time-shaped kernel at 64 columns (profiles/r02_scan_ncu.md): 72 registers -> 7 CTAs per SM,
+// 103 warp instructions per 32 bytes of database against 49 in the full-tile scan (64-bit row-address multiplies, run-time strides),
+// issue slots 44 % busy at 4.9 TB/s - an integer-overhead problem on top of the HBM stream, not a memory one.
+template <int IC, int JS, int ZT>
+__global__ void __launch_bounds__(128, 8) k_scan_spiral_jsplit_t(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
+                                                                 const uint64_t *__restrict__ db, int dim0, int JC, int zmask) {
+    pdl_prologue();
+    extern __shared__ __align__(16) uint4 qs[];        // [ZT][JC][4] uint4, later reused for the reduction
+    constexpr int TZ = IC / 2, per = ZT * TZ;
+    static_assert(JS * per == 128, "one CTA = 128 threads");
+    const int tid = threadIdx.x;
+    const int js = tid / per, loc = tid % per, zl = loc / TZ, icl = loc % TZ;
+    const int z0 = blockIdx.x * ZT, z = z0 + zl;
+    const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+    uint64_t acc[2][3][2];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) acc[u][r][0] = acc[u][r][1] = 0;
+    const uint4 *dbp = reinterpret_cast<const uint4 *>(db) + ((size_t)(z & zmask) * dim0 + js) * IC + icl;   // row js of this z-slice
+    const uint4 *qg = reinterpret_cast<const uint4 *>(query);
+    int it = 0;
+    for (int jc0 = 0; jc0 < dim0; jc0 += JC) {
+        __syncthreads();
+        for (int e = tid; e < ZT * JC * 4; e += 128) {
+            const int zz = e / (JC * 4), rem = e % (JC * 4);
+            qs[e] = __ldg(qg + ((size_t)(z0 + zz) * dim0 + jc0) * 4 + rem);
+        }
+        __syncthreads();
+        const uint4 *qz = qs + (size_t)zl * JC * 4 + js * 4;
+#pragma unroll 4
+        for (int jj = js; jj < JC; jj += JS, it++, dbp += JS * IC, qz += JS * 4) {
+            const uint4 d0 = ld_stream_u4(dbp), d1 = ld_stream_u4(dbp + TZ);
+            const uint4 q0 = qz[0], q1 = qz[1], q2 = qz[2], q3 = qz[3];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint4 d = u == 0 ? d0 : d1;
+                acc[u][0][0] += (uint64_t)q0.x * d.x;  acc[u][0][1] += (uint64_t)q0.y * d.y;
+                acc[u][1][0] += (uint64_t)q0.z * d.x;  acc[u][1][1] += (uint64_t)q0.w * d.y;
+                acc[u][2][0] += (uint64_t)q1.x * d.x;  acc[u][2][1] += (uint64_t)q1.y * d.y;
+                acc[u][0][0] += (uint64_t)q2.x * d.z;  acc[u][0][1] += (uint64_t)q2.y * d.w;
+                acc[u][1][0] += (uint64_t)q2.z * d.z;  acc[u][1][1] += (uint64_t)q2.w * d.w;
+                acc[u][2][0] += (uint64_t)q3.x * d.z;  acc[u][2][1] += (uint64_t)q3.y * d.w;
+            }
+            if ((it & (kScanFoldEvery - 1)) == kScanFoldEvery - 1) {
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        acc[u][r][0] = fold_acc(acc[u][r][0], c32p);
+                        acc[u][r][1] = fold_acc(acc[u][r][1], c32b);
+                    }
+            }
+        }
+    }
+    __syncthreads();
+    uint64_t *red = reinterpret_cast<uint64_t *>(qs);   // [js][12][per]
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            red[((size_t)js * 12 + (u * 3 + r) * 2 + 0) * per + loc] = fold_acc(acc[u][r][0], c32p);
+            red[((size_t)js * 12 + (u * 3 + r) * 2 + 1) * per + loc] = fold_acc(acc[u][r][1], c32b);
+        }
+    __syncthreads();
+    // every thread finishes 12 / JS of its column pair's 12 sums (the run-time kernel left the whole epilogue to group 0)
+    for (int o = js; o < 12; o += JS) {
+        uint64_t a = 0;
+#pragma unroll
+        for (int g = 0; g < JS; g++) a += red[((size_t)g * 12 + o) * per + loc];
+        const int u = o / 6, r = (o % 6) / 2, n = o & 1;
+        const int ic = icl + u * TZ, i = ic >> 1, c = ic & 1;
+        out[((((size_t)i * kN1 + r) * kN2 + c) * 2 + n) * kN + z] = reduce_u64(a, n);
+    }
+}
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s, size_t z_slices) {
     const int zmask = (int)(z_slices ? z_slices : (size_t)kN) - 1;
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
@@ -332,6 +408,12 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
         while ((size_t)ZT * JC * 64 > 16384 && JC > kScanFoldEvery) JC >>= 1;
         const size_t smem = std::max((size_t)ZT * JC * 64, (size_t)128 * 12 * 8);
         count_launch();
+        static const bool fixed = [] { const char *e = getenv("SB200_SCAN_JSPLIT_FIXED"); return !(e && *e == '0'); }();
+        if (fixed && JS == 4 && JC % 4 == 0) {             // the common shapes (first dimension >= 4) with compile-time strides
+            if (IC == 64 && ZT == 1) { launch_pdl((k_scan_spiral_jsplit_t<64, 4, 1>), dim3(kN), dim3(128), smem, s, out, query, db, (int)dim0, JC, zmask); return; }
+            if (IC == 32 && ZT == 2) { launch_pdl((k_scan_spiral_jsplit_t<32, 4, 2>), dim3(kN / 2), dim3(128), smem, s, out, query, db, (int)dim0, JC, zmask); return; }
+            if (IC == 16 && ZT == 4) { launch_pdl((k_scan_spiral_jsplit_t<16, 4, 4>), dim3(kN / 4), dim3(128), smem, s, out, query, db, (int)dim0, JC, zmask); return; }
+        }
         launch_pdl(k_scan_spiral_jsplit, dim3(kN / ZT), dim3(128), smem, s, out, query, db, (int)dim0, IC, ZT, JS, JC, zmask);
         return;
     }
