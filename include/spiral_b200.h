@@ -224,6 +224,10 @@ int sb200_server_scan(sb200_server *srv, void *stream);                    /* mu
 int sb200_server_scan_batched(sb200_server *const *servers, int count, void *stream);
 /* tensor-core variant: build the limb-tile database copy once (database owner; capacity <= 16 queries per pass) ... */
 int sb200_server_enable_tc(sb200_server *srv, int capacity);
+/* ... optionally keep ONLY that copy: the scan-layout copy is freed (one database's worth of HBM instead of two) and a single query's
+   first dimension - sb200_server_scan / _process / _answer* - becomes a one-query pass of the tensor-core kernel.  Servers sharing
+   the database must then scan on one stream; loading the database again drops the tensor-core state; snapshots need the scan layout */
+int sb200_server_tc_only(sb200_server *srv);
 /* ... then answer the first dimension of up to `capacity` servers sharing that database with one tcgen05 pass */
 int sb200_server_scan_batched_tc(sb200_server *const *servers, int count, void *stream);
 int sb200_server_lift(sb200_server *srv, void *stream);                    /* nttInvAndCrtLiftCiphertexts only (src/spiral.cpp:437) */
@@ -295,6 +299,7 @@ int sb200_pack_server_scan(sb200_pack_server *srv, void *stream);               
 /* several clients over one resident set of planes, and their first dimensions in ONE tensor-core pass (as sb200_server_*_tc) */
 int sb200_pack_server_create_view(sb200_pack_server **out, sb200_pack_server *parent);
 int sb200_pack_server_enable_tc(sb200_pack_server *srv, int capacity);     /* needs dim0 and num_per (per shard) multiples of 128 */
+int sb200_pack_server_tc_only(sb200_pack_server *srv);                       /* as sb200_server_tc_only: SpiralPack cfg3 = 64 GiB resident, not 128 */
 int sb200_pack_server_scan_batched_tc(sb200_pack_server *const *servers, int count, void *stream);
 /* interposed fastMultiplyQueryByDatabaseDim1 against ONE resident plane: host reoriented query in, ref-NTT host cts out */
 int sb200_pack_server_scan_plane_host(sb200_pack_server *srv, size_t plane, const uint64_t *v_firstdim_host, uint64_t *out_ref_ntt_host);

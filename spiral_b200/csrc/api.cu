@@ -460,11 +460,14 @@ static thread_local bool tl_prepare_only = false;
 template <typename F>
 int run_stage(GraphSlot &slot, cudaStream_t st, const void *k0, const void *k1, F &&body) {
     if (!graphs_enabled()) { if (!tl_prepare_only) { body(st); CHECK_LAUNCH(); } return SB200_OK; }
-    if (slot.exec && (slot.key0 != k0 || slot.key1 != k1)) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
-    if (!slot.exec) {
+    {   // the caller is capturing (a whole-query graph around this stage, or a user's own capture): enqueue the stage's kernels
+        // into that capture - never this stage's own executable graph, which would become a child-graph node
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
-        if (cs != cudaStreamCaptureStatusNone) { body(st); CHECK_LAUNCH(); return SB200_OK; }   // caller is capturing: just enqueue
+        if (cs != cudaStreamCaptureStatusNone) { body(st); CHECK_LAUNCH(); return SB200_OK; }
+    }
+    if (slot.exec && (slot.key0 != k0 || slot.key1 != k1)) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+    if (!slot.exec) {
         const uint64_t before = launch_count();
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -503,6 +506,7 @@ struct sb200_server {
     DBuf<uint8_t> db_tc, q_tc;                          // tensor-core path (sb200_server_enable_tc): limb-tile database, batched query tiles
     DBuf<uint32_t> tc_t1;                               // ... and the tile-order scan results of one pass
     int tc_capacity = 0;
+    bool tc_only = false;                               // sb200_server_tc_only: the limb-tile copy is the only one, every scan runs on k_scan_tc
     DBuf<uint32_t> W_left, W_right, W_conv, V_conv, neg1;
     DBuf<uint64_t> q_stage;                             // uploaded query (ref-NTT)
     DBuf<uint8_t> q_wire;                               // uploaded query in its wire form (wire_kernels.cu), header included
@@ -704,6 +708,11 @@ static inline size_t server_z_slices(const sb200_server *s) { const sb200_server
 static int server_alloc_db(sb200_server *s, size_t z_slices = 0) {
     if (s->db_owner) return fail(SB200_ERR_STATE, "this server is a view: load the database through its parent");
     const size_t want = z_slices ? z_slices : (size_t)kN;
+    if (s->db_tc.p) {                                   // a (re)load makes the limb-tile copy stale: drop it (enable again afterwards)
+        cudaFree(s->db_tc.p); s->db_tc.p = nullptr;
+        s->tc_capacity = 0;
+        if (s->tc_only) { s->tc_only = false; s->have_db = false; }     // ... and it was the only copy
+    }
     if (s->db.p && server_z_slices(s) != want) { cudaFree(s->db.p); s->db.p = nullptr; s->have_db = false; }
     s->z_slices = z_slices;
     if (s->db.p) return SB200_OK;
@@ -838,19 +847,20 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
         static const bool skip_odd = [] { const char *e = getenv("SB200_PROFILE_SKIP_ODD_CHAIN"); return e && *e == '1'; }();   // timing experiments only: answers are wrong
         CU(cudaEventRecord(s->ev_fork, main_st));
         CU(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
-        if (!skip_odd) TRY(run_stage(s->g_odd[wk], s->aux_stream, shard ? (const void *)s->xchg.p : nullptr, nullptr, [&](cudaStream_t st) {
-            // The odd chain's 56-digit rounds are thousands of NTT CTAs that sit ahead of the even chain's next kernels in the block
-            // scheduler's queue and cost the even chain ~90 us.  Measured alternatives (profiles/r02_expansion_chains.md): strict launch
-            // priorities starve the odd chain, which then spills into the scan; digit kernels confined to SB200_ODD_SLOTS CTA slots
-            // per SM make the contention last longer (1.01 ms/query at 2 slots against 0.94 unlimited).  Default: unlimited.
-            static const int odd_slots = [] { const char *e = getenv("SB200_ODD_SLOTS"); return e ? atoi(e) : 0; }();
-            static const int odd_chunk = [] { const char *e = getenv("SB200_ODD_CHUNK"); return e ? atoi(e) : 740; }();   // ~one wave of NTT CTAs
+        const int odd_end = (int)s->stopround + 1;
+        // The odd chain's 56-digit rounds are thousands of NTT CTAs that sit ahead of the even chain's next kernels in the block
+        // scheduler's queue and cost the even chain ~90 us.  Measured alternatives (profiles/r02_expansion_chains.md): strict launch
+        // priorities starve the odd chain, which then spills into the scan; digit kernels confined to SB200_ODD_SLOTS CTA slots
+        // per SM make the contention last longer (1.01 ms/query at 2 slots against 0.94 unlimited).  Default: unlimited.
+        static const int odd_slots = [] { const char *e = getenv("SB200_ODD_SLOTS"); return e ? atoi(e) : 0; }();
+        static const int odd_chunk = [] { const char *e = getenv("SB200_ODD_CHUNK"); return e ? atoi(e) : 740; }();   // ~one wave of NTT CTAs
+        auto odd_chain = [&](cudaStream_t st) {
             LaunchPriority low(false);                  // no-op unless SB200_PRIO=1 (experiments)
             if (wk) launch_query_from_wire(s->cv_o.p, s->q_wire.p, s->wire_kind, st);
             else launch_ntt_u64_to_dev(s->cv_o.p, s->q_stage.p, 2, st);
             if (shard) {
                 launch_expand(s->cv_o.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_os.p,
-                              s->offs_os.data(), s->cnt_os.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148, odd_chunk);
+                              s->offs_os.data(), s->cnt_os.data(), st, 0, odd_end, 1, 1, odd_slots * 148, odd_chunk);
                 GswTargets tg{};
                 tg.ntargets = s->world;
                 for (int t = 0; t < s->world; t++) {
@@ -865,12 +875,15 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
                 return;
             }
             launch_expand(s->cv_o.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0_o.p, s->c1_o.p, s->ginv_o.p, s->lists_o.p,
-                          s->offs_o.data(), s->cnt_o.data(), st, 0, (int)s->stopround + 1, 1, 1, odd_slots * 148, odd_chunk);
+                          s->offs_o.data(), s->cnt_o.data(), st, 0, odd_end, 1, 1, odd_slots * 148, odd_chunk);
             // no GSW negation on the resident path: the fold uses the CMux form (launch_fold_round_generic)
             launch_regev_to_gsw(s->gsw.p, nullptr, s->cv_o.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw,
                                 s->W_conv.p, s->V_conv.p, (int)s->prm.t_conv, s->conv_raw2.p, s->conv_ntt2.p, st);
-        }));
-        CU(cudaEventRecord(s->ev_join, s->aux_stream));
+        };
+        // Also measured and not adopted: the chain's last rounds (or RegevToGSW alone) as a second graph that starts with the scan.
+        // The scan keeps every register file full (8 CTAs x 8 K registers per SM; at 7 / 6 CTAs it takes 0.390 / 0.414 ms instead
+        // of 0.360) and the lift's CTAs, launched early, take the slots that free up - the deferred work runs after the scan.
+        if (!skip_odd) TRY(run_stage(s->g_odd[wk], s->aux_stream, shard ? (const void *)s->xchg.p : nullptr, nullptr, odd_chain));
         TRY(run_stage(s->g_even[wk], main_st, shard ? (const void *)s->xchg.p : nullptr, nullptr, [&](cudaStream_t st) {
             LaunchPriority high(true);                  // no-op unless SB200_PRIO=1 (experiments)
             if (wk) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);     // wire query -> cv[0]
@@ -878,6 +891,7 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
             if (!shard) {
                 launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists_e.p,
                               s->offs_e.data(), s->cnt_e.data(), st, 0, (int)s->g, 0, 1);
+                LaunchPriority tail(true, 2);
                 launch_scal_to_mat_reoriented(s->query.p, s->cv.p, s->ct_idx_first.p, s->poly_idx_first.p, s->dim0, s->W_conv.p,
                                               (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
                 return;
@@ -896,6 +910,7 @@ static int expand_and_convert_impl(sb200_server *s, void *stream, bool defer_joi
             launch_scal_to_mat_sharded(tg, s->cv.p, s->ct_idx_first_s.p, s->poly_idx_first_s.p, s->dim0, s->dim0 / s->world, s->rank, s->world,
                                        s->W_conv.p, s->conv_raw.p, s->conv_ntt.p, st);
         }));
+        CU(cudaEventRecord(s->ev_join, s->aux_stream));
         s->query_sharded = shard;
         s->gsw_wait_pending = shard;
         if (defer_join) s->join_pending = true;
@@ -929,10 +944,29 @@ extern "C" int sb200_server_expand_and_convert(sb200_server *s, void *stream) { 
 extern "C" int sb200_server_expansion_sharded(const sb200_server *s) { return s && s->query_sharded; }
 static int join_odd_chain(sb200_server *s, cudaStream_t st) {
     if (s->join_pending) { CU(cudaStreamWaitEvent(st, s->ev_join, 0)); s->join_pending = false; }
-    if (s->gsw_wait_pending && !tl_prepare_only) {           // sharded conversion: every rank's GSW columns must have landed here
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (s->gsw_wait_pending && (!tl_prepare_only || cs != cudaStreamCaptureStatusNone)) {   // sharded conversion: every rank's GSW columns must have landed here
         launch_flag_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, 1, 0, st);
     }
     s->gsw_wait_pending = false;
+    return SB200_OK;
+}
+static inline sb200_server *server_owner(sb200_server *s) { return s->db_owner ? const_cast<sb200_server *>(s->db_owner) : s; }
+// first dimension of ONE server's converted query: the streaming kernel on the scan-layout database, or - when only the limb-tile
+// copy is resident (sb200_server_tc_only) - a one-query pass of the tensor-core kernel
+static int scan_one(sb200_server *s, cudaStream_t st) {
+    sb200_server *owner = server_owner(s);
+    if (owner->tc_only) {
+        uint32_t *o[1] = {s->scan_out.p}; const uint64_t *q[1] = {s->query.p};
+        launch_queries_to_tc(owner->q_tc.p, q, 1, 0, owner->tc_capacity, owner->dim0, st);
+        if (launch_scan_tc(o, 1, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, owner->dim0, owner->local_num_per, owner->tc_t1.p, st))
+            return fail(SB200_ERR_CUDA, "scan (tensor-core copy only): launch failed");
+    } else {
+        LaunchPriority first(true, 3);
+        launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, st, server_z_slices(s));
+    }
+    CHECK_LAUNCH();
     return SB200_OK;
 }
 extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
@@ -940,9 +974,7 @@ extern "C" int sb200_server_scan(sb200_server *s, void *stream) {
     if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan: database not loaded");
     // sharded expansion: every rank's slice of the query must have landed in this rank's buffer
     if (s->query_sharded) launch_flag_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, 0, 0, ES(s, stream));
-    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, ES(s, stream), server_z_slices(s));
-    CHECK_LAUNCH();
-    return SB200_OK;
+    return scan_one(s, ES(s, stream));
 }
 // One pass over the database for `count` (2 or 4) servers that share it (a parent and its views): every server's own
 // converted query is scanned, every server's own ciphertext buffer is filled.  Launched on `stream`.
@@ -951,9 +983,10 @@ extern "C" int sb200_server_scan_batched(sb200_server *const *servers, int count
     sb200_server *s0 = servers[0];
     if (!s0 || !server_has_db(s0)) return fail(SB200_ERR_STATE, "scan_batched: database not loaded");
     if (server_z_slices(s0) != (size_t)kN) return fail(SB200_ERR_STATE, "scan_batched: needs an explicit database");
+    if (server_owner(s0)->tc_only) return fail(SB200_ERR_STATE, "scan_batched: the scan-layout copy was released (sb200_server_tc_only): use sb200_server_scan_batched_tc");
     const uint64_t *q[4]; uint32_t *o[4];
     for (int b = 0; b < count; b++) {
-        if (!servers[b] || server_db(servers[b]) != server_db(s0)) return fail(SB200_ERR_ARG, "scan_batched: servers must share one database");
+        if (!servers[b] || server_owner(servers[b]) != server_owner(s0)) return fail(SB200_ERR_ARG, "scan_batched: servers must share one database");
         q[b] = servers[b]->query.p; o[b] = servers[b]->scan_out.p;
     }
     if (launch_scan_spiral_batched(o, q, count, server_db(s0), s0->dim0, s0->local_num_per, ES(s0, stream)) != 0)
@@ -971,7 +1004,7 @@ extern "C" int sb200_server_enable_tc(sb200_server *s, int capacity) {
     if (capacity < 1 || capacity > 16) return fail(SB200_ERR_ARG, "enable_tc: capacity must be in [1, 16]");
     if (!tc_shape_ok(s->dim0, s->local_num_per)) return fail(SB200_ERR_ARG, "enable_tc: needs 2*dim0 and 2*num_per (per shard) to be multiples of 128");
     CU(cudaSetDevice(s->device));
-    if (!s->db_tc.p) {
+    if (!s->db_tc.p) {                                  // (after sb200_server_tc_only the copy exists and only the staging is resized)
         CU(s->db_tc.alloc(s->db.n * sizeof(uint64_t)));
         launch_db_to_tc(s->db_tc.p, s->db.p, s->dim0, s->local_num_per, s->own_stream); CHECK_LAUNCH();
     }
@@ -996,13 +1029,29 @@ extern "C" int sb200_server_scan_batched_tc(sb200_server *const *servers, int co
     uint32_t *o[16]; const uint64_t *qs[16];
     cudaStream_t st = ES(s0, stream);
     for (int b = 0; b < count; b++) {
-        if (!servers[b] || server_db(servers[b]) != owner->db.p) return fail(SB200_ERR_ARG, "scan_batched_tc: servers must share one database");
+        if (!servers[b] || server_owner(servers[b]) != owner) return fail(SB200_ERR_ARG, "scan_batched_tc: servers must share one database");
         qs[b] = servers[b]->query.p; o[b] = servers[b]->scan_out.p;
     }
     launch_queries_to_tc(owner->q_tc.p, qs, count, 0, owner->tc_capacity, owner->dim0, st);
     if (launch_scan_tc(o, count, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, owner->dim0, owner->local_num_per, owner->tc_t1.p, st))
         return fail(SB200_ERR_CUDA, "scan_batched_tc: launch failed");
     CHECK_LAUNCH();
+    return SB200_OK;
+}
+// Keep ONLY the limb-tile copy of the database (it holds the same residues, as u8 limbs in MMA tile order): the scan-layout
+// copy is freed, so a server that batches on the tensor cores occupies one database's worth of HBM, not two, and a single query's
+// first dimension (sb200_server_scan / _process / _answer*) becomes a one-query pass of k_scan_tc (0.41 ms instead of 0.36 ms
+// at 2 GiB).  Servers sharing this database must issue their scans on one stream: they share the query-tile and result staging.
+// Peak footprint is still two copies while sb200_server_enable_tc converts; loading the database again drops the tensor-core state.
+extern "C" int sb200_server_tc_only(sb200_server *s) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "tc_only: call it on the server that owns the database");
+    if (!s->tc_capacity || !s->db_tc.p) return fail(SB200_ERR_STATE, "tc_only: call sb200_server_enable_tc first");
+    if (s->tc_only) return SB200_OK;
+    CU(cudaSetDevice(s->device));
+    CU(cudaDeviceSynchronize());                        // no scan of the copy being freed may be in flight
+    cudaFree(s->db.p); s->db.p = nullptr;
+    s->tc_only = true;
     return SB200_OK;
 }
 extern "C" int sb200_server_lift(sb200_server *s, void *stream) {
@@ -1020,7 +1069,7 @@ extern "C" int sb200_server_scan_host(sb200_server *s, const uint64_t *reoriente
     if (!s || !reoriented_host || !out_ref_ntt_host) return fail(SB200_ERR_ARG, "scan_host: null argument");
     if (!server_has_db(s)) return fail(SB200_ERR_STATE, "scan_host: database not loaded");
     CU(cudaMemcpy(s->query.p, reoriented_host, s->dim0 * 2 * 4 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, 0, server_z_slices(s)); CHECK_LAUNCH();
+    TRY(scan_one(s, 0));
     return down_ntt(out_ref_ntt_host, s->scan_out.p, s->local_num_per * 6);
 }
 extern "C" int sb200_server_copy_partial(sb200_server *s, uint64_t *dst_dev, void *stream) {
@@ -1234,7 +1283,7 @@ extern "C" int sb200_resident_multiplyQueryByDatabase(sb200_server *s, const voi
     if (!s || !out_key) return fail(SB200_ERR_ARG, "resident multiplyQueryByDatabase: null argument");
     if (!s->res_query_key || reoriented_key != s->res_query_key) return fail(SB200_ERR_STATE, "resident multiplyQueryByDatabase: the query is not resident");
     if (!server_has_db(s)) return fail(SB200_ERR_STATE, "resident multiplyQueryByDatabase: database not loaded");
-    launch_scan_spiral(s->scan_out.p, s->query.p, server_db(s), s->dim0, s->local_num_per, 0, server_z_slices(s)); CHECK_LAUNCH();
+    TRY(scan_one(s, 0));
     CU(cudaDeviceSynchronize());                       // the harness's timer brackets the call
     s->res_scan_key = out_key; s->res_cts_key = nullptr;
     return SB200_OK;
@@ -1285,10 +1334,7 @@ extern "C" int sb200_server_answer(sb200_server *s, const uint64_t *query_cv_hos
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer: single-shard call on a sharded server (use the staged API)");
     TRY(sb200_server_upload_query(s, query_cv_host, stream));
-    TRY(expand_and_convert_impl(s, stream, true));
-    TRY(sb200_server_first_dim(s, stream));
-    TRY(sb200_server_fold_local(s, stream));
-    TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
+    TRY(sb200_server_process(s, s->resp.p, stream, nullptr));
     return sb200_server_download(s, total_resp_host, s->resp.p, 6 * kN, stream);
 }
 // One resident query in ONE call (the query is already in q_stage / q_wire): all server stages into total_resp_dev.  A serving loop
@@ -1313,11 +1359,8 @@ extern "C" int sb200_server_prepare(sb200_server *s, uint64_t *total_resp_dev, v
     CU(cudaStreamSynchronize(ES(s, stream)));
     return rc;
 }
-extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, void *stream, void *const *marks) {
-    if (!s) return fail(SB200_ERR_ARG, "null server");
-    if (s->world > 1 && !s->xchg_connected) return fail(SB200_ERR_STATE, "server_process: sharded server without connected peers (sb200_server_xchg_connect)");
+static int process_stages(sb200_server *s, uint64_t *resp, void *stream, void *const *marks) {
     cudaStream_t st = ES(s, stream);
-    uint64_t *resp = total_resp_dev ? total_resp_dev : s->resp.p;
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[0], st));
     TRY(expand_and_convert_impl(s, stream, true));
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[1], st));
@@ -1330,15 +1373,21 @@ extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, v
     if (marks) CU(cudaEventRecord((cudaEvent_t)marks[3], st));
     return SB200_OK;
 }
+// Measured and not adopted (profiles/r02_expansion_chains.md): the whole query captured as ONE graph (both chains, scan, folds).
+// Device-resident it runs as fast as the per-stage graphs (0.933 vs 0.935 ms - a graph-to-graph boundary costs nothing that the
+// programmatic launches do not already hide), and with host buffers it is slower (1.00 vs 0.96 ms): the first kernel cannot start
+// before all ~200 nodes are submitted, while the first small stage graph starts at once and the rest is submitted under it.
+extern "C" int sb200_server_process(sb200_server *s, uint64_t *total_resp_dev, void *stream, void *const *marks) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->world > 1 && !s->xchg_connected) return fail(SB200_ERR_STATE, "server_process: sharded server without connected peers (sb200_server_xchg_connect)");
+    return process_stages(s, total_resp_dev ? total_resp_dev : s->resp.p, stream, marks);
+}
 // the same query with the response in its wire format: 20 KiB instead of 96 KiB cross PCIe at cfg1
 extern "C" int sb200_server_answer_packed(sb200_server *s, const uint64_t *query_cv_host, uint64_t *packed_resp_host, void *stream) {
     if (!s || !packed_resp_host) return fail(SB200_ERR_ARG, "server_answer_packed: null argument");
     if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer_packed: single-shard call on a sharded server (use the staged API)");
     TRY(sb200_server_upload_query(s, query_cv_host, stream));
-    TRY(expand_and_convert_impl(s, stream, true));
-    TRY(sb200_server_first_dim(s, stream));
-    TRY(sb200_server_fold_local(s, stream));
-    TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
+    TRY(sb200_server_process(s, s->resp.p, stream, nullptr));
     TRY(sb200_dev_pack_response(s->final_ct.p, s->resp.p, 2 * (size_t)kN, 4 * (size_t)kN, s->prm.qp_bits, s->prm.p_db, ES(s, stream)));
     return sb200_server_download(s, packed_resp_host, s->final_ct.p, sb200_packed_response_words(2 * (size_t)kN, 4 * (size_t)kN, s->prm.qp_bits, s->prm.p_db), stream);
 }

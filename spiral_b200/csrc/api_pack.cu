@@ -135,6 +135,7 @@ struct sb200_pack_server {
     DBuf<uint8_t> db_tc, q_tc;                          // tensor-core path (sb200_pack_server_enable_tc)
     DBuf<uint32_t> tc_t1;
     int tc_capacity = 0;
+    bool tc_only = false;                               // sb200_pack_server_tc_only: only the limb-tile planes are resident
     DBuf<uint32_t> W_left, W_right, V, vW, neg1;
     DBuf<uint64_t> stage;
     DBuf<uint8_t> q_wire;                               // query in its wire form (wire_kernels.cu)
@@ -175,6 +176,8 @@ struct sb200_pack_server {
 static inline cudaStream_t PS(sb200_pack_server *s, void *stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
 static inline const sb200_pack_server *pack_owner(const sb200_pack_server *s) { return s->db_owner ? s->db_owner : s; }
 static inline const uint64_t *pack_db(const sb200_pack_server *s) { return pack_owner(s)->db.p; }
+// loaders and the plane-at-a-time host path work on the scan-layout planes
+#define NEED_SCAN_PLANES(s, what) do { if (!(s)->db.p) return fail(SB200_ERR_STATE, what ": the scan-layout planes were released (sb200_pack_server_tc_only); create a new server to load another database"); } while (0)
 static inline bool pack_plane_loaded(const sb200_pack_server *s, size_t p) { return pack_owner(s)->plane_loaded[p]; }
 static inline TcGeom pack_geom(const sb200_pack_server *s) { return tc_geom_pack(s->dim0, s->local_num_per, s->planes, s->local_num_per * 2); }
 
@@ -288,6 +291,7 @@ extern "C" int sb200_pack_server_load_plane_items(sb200_pack_server *s, size_t p
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
     if (s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "load_plane_items: plane %zu lives on rank %zu (plane sharding)", plane, plane % s->world);
     plane = (size_t)s->local_plane(plane);
+    NEED_SCAN_PLANES(s, "pack load_plane_items");
     CU(cudaSetDevice(s->device));
     const size_t items = s->dim0 * s->local_num_per;
     DBuf<uint16_t> d(items * kN);
@@ -305,6 +309,7 @@ extern "C" int sb200_pack_server_set_plane_item(sb200_pack_server *s, size_t pla
     if (s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "set_plane_item: plane %zu lives on rank %zu (plane sharding)", plane, plane % s->world);
     const size_t lp = (size_t)s->local_plane(plane);
     if (!s->plane_loaded[lp]) return fail(SB200_ERR_STATE, "set_plane_item: plane %zu not loaded", plane);
+    NEED_SCAN_PLANES(s, "pack set_plane_item");
     CU(cudaSetDevice(s->device));
     DBuf<uint16_t> d(kN);
     CU(d.up(poly_host, kN));
@@ -318,6 +323,7 @@ extern "C" int sb200_pack_server_load_plane_reference(sb200_pack_server *s, size
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
     if (s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "load_plane_reference: plane %zu lives on rank %zu (plane sharding)", plane, plane % s->world);
     plane = (size_t)s->local_plane(plane);
+    NEED_SCAN_PLANES(s, "pack load_plane_reference");
     CU(cudaSetDevice(s->device));
     const size_t zc = 64, row = s->local_num_per * s->dim0;
     DBuf<uint64_t> stage(zc * row);
@@ -340,6 +346,7 @@ extern "C" int sb200_pack_server_load_plane_reference(sb200_pack_server *s, size
 extern "C" int sb200_pack_server_load_random(sb200_pack_server *s, uint64_t seed) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
+    NEED_SCAN_PLANES(s, "pack load_random");
     CU(cudaSetDevice(s->device));
     const size_t items = s->dim0 * s->local_num_per, n4 = items * kN / 4;
     DBuf<uint16_t> d;
@@ -446,7 +453,16 @@ extern "C" int sb200_pack_server_scan(sb200_pack_server *s, void *stream) {
         launch_query_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, PS(s, stream));
         s->query_wait_pending = false;
     }
-    launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s), s->dim0, s->local_num_per, s->planes, s->plane_words, s->local_num_per * 2, PS(s, stream));
+    sb200_pack_server *owner = const_cast<sb200_pack_server *>(pack_owner(s));
+    if (owner->tc_only) {                               // only the limb-tile planes are resident: a one-query pass of k_scan_tc
+        uint32_t *o[1] = {s->scan_out.p}; const uint64_t *q[1] = {s->query.p};
+        const TcGeom g = pack_geom(owner);
+        launch_queries_to_tc_g(owner->q_tc.p, q, 1, 0, owner->tc_capacity, g, PS(s, stream));
+        if (launch_scan_tc_g(o, 1, owner->tc_capacity, owner->q_tc.p, owner->db_tc.p, g, owner->tc_t1.p, PS(s, stream)))
+            return fail(SB200_ERR_CUDA, "pack scan (tensor-core copy only): launch failed");
+    } else {
+        launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s), s->dim0, s->local_num_per, s->planes, s->plane_words, s->local_num_per * 2, PS(s, stream));
+    }
     CHECK_LAUNCH();
     return SB200_OK;
 }
@@ -455,6 +471,7 @@ extern "C" int sb200_pack_server_scan_plane_host(sb200_pack_server *s, size_t pl
     if (!s || !v_firstdim_host || !out_ref_ntt_host || s->local_plane(plane) < 0) return fail(SB200_ERR_ARG, "pack scan_plane_host: bad argument");
     plane = (size_t)s->local_plane(plane);
     if (!pack_plane_loaded(s, plane)) return fail(SB200_ERR_STATE, "pack scan_plane_host: database plane %zu not loaded", plane);
+    if (!pack_db(s)) return fail(SB200_ERR_STATE, "pack scan_plane_host: the scan-layout planes were released (sb200_pack_server_tc_only)");
     CU(cudaMemcpy(s->query.p, v_firstdim_host, s->dim0 * 2 * kN * sizeof(uint64_t), cudaMemcpyHostToDevice));
     launch_scan_pack(s->scan_out.p, s->query.p, pack_db(s) + plane * s->plane_words, s->dim0, s->local_num_per, 1, s->plane_words, s->local_num_per * 2, 0);
     CHECK_LAUNCH();
@@ -494,6 +511,18 @@ extern "C" int sb200_pack_server_enable_tc(sb200_pack_server *s, int capacity) {
     CU(cudaMemsetAsync(s->q_tc.p, 0, s->q_tc.n, s->own_stream));
     CU(cudaStreamSynchronize(s->own_stream));
     s->tc_capacity = capacity;
+    return SB200_OK;
+}
+// Keep ONLY the limb-tile planes (as sb200_server_tc_only): SpiralPack's 64 GiB of planes then occupy 64 GiB, not 128, of the 180.
+extern "C" int sb200_pack_server_tc_only(sb200_pack_server *s) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->db_owner) return fail(SB200_ERR_STATE, "pack tc_only: call it on the server that owns the database");
+    if (!s->tc_capacity || !s->db_tc.p) return fail(SB200_ERR_STATE, "pack tc_only: call sb200_pack_server_enable_tc first");
+    if (s->tc_only) return SB200_OK;
+    CU(cudaSetDevice(s->device));
+    CU(cudaDeviceSynchronize());
+    cudaFree(s->db.p); s->db.p = nullptr;
+    s->tc_only = true;
     return SB200_OK;
 }
 extern "C" int sb200_pack_server_scan_batched_tc(sb200_pack_server *const *servers, int count, void *stream) {

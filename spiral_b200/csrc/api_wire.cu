@@ -48,10 +48,7 @@ extern "C" int sb200_server_answer_wire(sb200_server *s, const uint8_t *wire_hos
     if (!s || !packed_resp_host) return fail(SB200_ERR_ARG, "server_answer_wire: null argument");
     if (s->world != 1) return fail(SB200_ERR_STATE, "server_answer_wire: single-shard call on a sharded server (use the staged API)");
     TRY(sb200_server_upload_query_wire(s, wire_host, bytes, stream));
-    TRY(sb200_server_expand_and_convert(s, stream));
-    TRY(sb200_server_first_dim(s, stream));
-    TRY(sb200_server_fold_local(s, stream));
-    TRY(sb200_server_fold_tail(s, s->cts.p, s->resp.p, stream));
+    TRY(sb200_server_process(s, s->resp.p, stream, nullptr));
     TRY(sb200_dev_pack_response(s->final_ct.p, s->resp.p, 2 * (size_t)kN, 4 * (size_t)kN, s->prm.qp_bits, s->prm.p_db, ES(s, stream)));
     return sb200_server_download(s, packed_resp_host, s->final_ct.p, sb200_packed_response_words(2 * (size_t)kN, 4 * (size_t)kN, s->prm.qp_bits, s->prm.p_db), stream);
 }
@@ -178,6 +175,7 @@ int pack_server_load_records(sb200_pack_server *s, const ByteSource &src) {
     if (s->shard_planes) return fail(SB200_ERR_STATE, "plane-sharded pack servers load their planes with sb200_pack_server_load_plane_*");
     const uint32_t bits = coeff_bits(s->prm.p_db);
     if (!bits) return fail(SB200_ERR_ARG, "load_db_records: p_db must be a power of two <= 65536");
+    NEED_SCAN_PLANES(s, "pack load_db_records");
     CU(cudaSetDevice(s->device));
     const size_t items = s->dim0 * s->local_num_per, item_bytes = s->planes * (size_t)kN * bits / 8;
     DBuf<uint16_t> pts;                                        // [plane][local item][2048]
@@ -305,6 +303,7 @@ extern "C" int sb200_server_save_db(sb200_server *s, const char *path) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner || !s->have_db) return fail(SB200_ERR_STATE, "save_db: this server owns no loaded database");
     if (server_z_slices(s) != (size_t)kN) return fail(SB200_ERR_STATE, "save_db: an implicit database has no snapshot form");
+    if (!s->db.p) return fail(SB200_ERR_STATE, "save_db: the scan-layout copy was released (sb200_server_tc_only); snapshots hold that layout");
     CU(cudaSetDevice(s->device));
     return snapshot_save(path, server_snap_header(s), s->db.p, s->dim0 * s->local_num_per * 4 * kN);
 }
@@ -336,6 +335,7 @@ extern "C" int sb200_pack_server_save_db(sb200_pack_server *s, const char *path)
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner) return fail(SB200_ERR_STATE, "save_db: this pack server is a view");
     for (size_t p = 0; p < s->planes; p++) if (!s->plane_loaded[p]) return fail(SB200_ERR_STATE, "save_db: plane %zu not loaded", p);
+    NEED_SCAN_PLANES(s, "pack save_db");
     CU(cudaSetDevice(s->device));
     return snapshot_save(path, pack_snap_header(s), s->db.p, s->planes * s->plane_words);
 }
@@ -343,6 +343,7 @@ extern "C" int sb200_pack_server_load_db_snapshot(sb200_pack_server *s, const ch
     if (s && s->shard_planes) return fail(SB200_ERR_STATE, "plane-sharded pack servers load their planes with sb200_pack_server_load_plane_*");
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (s->db_owner) return fail(SB200_ERR_STATE, "this pack server is a view: load the database through its parent");
+    NEED_SCAN_PLANES(s, "pack load_db_snapshot");
     CU(cudaSetDevice(s->device));
     for (size_t p = 0; p < s->planes; p++) s->plane_loaded[p] = false;
     TRY(snapshot_load(path, pack_snap_header(s), s->db.p, s->planes * s->plane_words));

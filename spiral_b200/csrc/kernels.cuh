@@ -21,7 +21,7 @@ constexpr int kNoPriority = 1 << 30;
 int &launch_priority();
 struct LaunchPriority {
     int saved;
-    explicit LaunchPriority(bool high);
+    explicit LaunchPriority(bool high, int level = 1);   // active when SB200_PRIO == level
     ~LaunchPriority() { launch_priority() = saved; }
 };
 void note_kernel(const char *name);    // distinct kernel names launched since the last reset (sb200_kernel_log)

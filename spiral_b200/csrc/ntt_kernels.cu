@@ -87,11 +87,11 @@ size_t trace_read(unsigned long long *out, size_t max_records, int reset) {
 }
 
 int &launch_priority() { static thread_local int p = kNoPriority; return p; }
-LaunchPriority::LaunchPriority(bool high) : saved(launch_priority()) {
+LaunchPriority::LaunchPriority(bool high, int level) : saved(launch_priority()) {
     // measured (profiles/r02_expansion_chains.md): strict priorities starve the low-priority chain whenever the other graph has
     // nodes pending, even dependency-blocked ones - the odd chain then spills into the scan.  Off unless SB200_PRIO=1.
-    static const bool on = [] { const char *e = getenv("SB200_PRIO"); return e && *e == '1'; }();
-    if (!on) return;
+    static const int mode = [] { const char *e = getenv("SB200_PRIO"); return e ? atoi(e) : 0; }();
+    if (mode != level && !(level == 3 && mode == 2)) return;
     int least = 0, greatest = 0;
     if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return; }
     launch_priority() = high ? greatest : least;

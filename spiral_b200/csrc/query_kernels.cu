@@ -24,7 +24,7 @@ __device__ __forceinline__ uint64_t pack_pb2(uint32_t p, uint32_t b) { return (u
 //   k_expand_digits : (slot,k)   digit k of c0_raw[slot] -> NTT -> ginv[slot][k]
 //   k_expand_accum  : cv[i][row] += sum_k W[row][k] * ginv[slot][k] + row * c1_ntt[slot]
 // ============================================================================================
-__global__ void __launch_bounds__(kNttThreads) k_expand_prep(uint32_t *__restrict__ cv, const int *__restrict__ active, int num_in,
+__global__ void __launch_bounds__(kNttThreads, 4) k_expand_prep(uint32_t *__restrict__ cv, const int *__restrict__ active, int num_in,
                                                              const uint32_t *__restrict__ neg1, const uint32_t *__restrict__ neg1_shoup, uint32_t tpow,
                                                              const uint16_t *__restrict__ perm, uint64_t *__restrict__ c0_raw, uint32_t *__restrict__ c1_ntt,
                                                              int store_self) {

@@ -391,7 +391,8 @@ __global__ void __launch_bounds__(128, 8) k_scan_spiral_jsplit_t(uint32_t *__res
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s, size_t z_slices) {
     const int zmask = (int)(z_slices ? z_slices : (size_t)kN) - 1;
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
-    // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower.
+    // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower
+    // (8 CTAs per SM: 0.360 ms, 7: 0.390, 6: 0.414 - round 2, profiles/r02_expansion_chains.md).
     // The query slice is staged in chunks of at most 16 KiB per CTA: with 32 KiB (first dimensions of 512 and 1024) only 6 CTAs
     // fit an SM and the scan drops from 6.45 to 5.6-6.0 TB/s (profiles/r01_scan_shapes.md).
     // Narrow shards (IC = 64 or 128 columns: a small second dimension, or a database sharded over many GPUs) keep two columns per

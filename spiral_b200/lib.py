@@ -179,9 +179,11 @@ def load_library():
         "sb200_server_scan_batched": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
         "sb200_pack_server_create_view": (C.c_int, [C.POINTER(vp), vp]),
         "sb200_pack_server_enable_tc": (C.c_int, [vp, C.c_int]),
+        "sb200_pack_server_tc_only": (C.c_int, [vp]),
         "sb200_pack_server_scan_batched_tc": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
         "sb200_fastMultiplyQueryByDatabaseDim1_batched": (C.c_int, [C.POINTER(u64p), u64p, C.POINTER(u64p), C.c_int, sz, sz]),
         "sb200_server_enable_tc": (C.c_int, [vp, C.c_int]),
+        "sb200_server_tc_only": (C.c_int, [vp]),
         "sb200_server_scan_batched_tc": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
         "sb200_tc_supported": (C.c_int, [sz, sz]),
         "sb200_tc_query_bytes": (sz, [sz, C.c_int]),

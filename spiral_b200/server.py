@@ -148,6 +148,10 @@ class SpiralServer:
         """Build the tensor-core (limb-tile) copy of the resident database for batches of up to `capacity` queries."""
         check(self.lib.sb200_server_enable_tc(self.h, capacity), self.lib)
 
+    def tc_only(self):
+        """Free the scan-layout copy: the limb-tile copy is then the only one and single queries scan on the tensor-core kernel."""
+        check(self.lib.sb200_server_tc_only(self.h), self.lib)
+
     @staticmethod
     def scan_batched_tc(servers, stream=None):
         """One tcgen05 pass over the database for up to 16 servers sharing it (enable_tc on the owner first)."""
@@ -278,6 +282,10 @@ class PackServer:
 
     def enable_tc(self, capacity=16):
         check(self.lib.sb200_pack_server_enable_tc(self.h, capacity), self.lib)
+
+    def tc_only(self):
+        """Free the scan-layout planes (see SpiralServer.tc_only)."""
+        check(self.lib.sb200_pack_server_tc_only(self.h), self.lib)
 
     @staticmethod
     def scan_batched_tc(servers, stream=None):

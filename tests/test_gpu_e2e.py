@@ -130,13 +130,23 @@ def test_process_is_the_staged_calls_in_one(sb, oracle):
         for e in evs:
             e.record()
         marks = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
-        for use_marks in (False, True, True):
-            q = s.query(11 + int(use_marks))
-            want = srv.answer(q)
+        # without marks the whole query is ONE graph (captured at the first call, replayed afterwards); with marks the stages are
+        # separate graphs; the staged calls are the third form - all three against the oracle, on different queries
+        for k, use_marks in enumerate((False, True, False, True, False)):
+            q = s.query(11 + 3 * k)
+            want, _, _ = s.oracle_answer(q, s.reference_db())
+            assert np.array_equal(srv.answer(q), want)
+            resp.zero_()
             srv.upload_query(q, stream.cuda_stream)
             srv.process(resp.data_ptr(), stream.cuda_stream, marks if use_marks else None)
             stream.synchronize()
-            assert np.array_equal(resp.cpu().numpy().view(np.uint64), want)
+            assert np.array_equal(resp.cpu().numpy().view(np.uint64), want), f"process, marks={use_marks}"
+            resp.zero_()
+            srv.upload_query(q, stream.cuda_stream)
+            srv.expand_and_convert(stream.cuda_stream); srv.first_dim(stream.cuda_stream); srv.fold_local(stream.cuda_stream)
+            srv.fold_tail(srv.partial_ct_ptr(), resp.data_ptr(), stream.cuda_stream)
+            stream.synchronize()
+            assert np.array_equal(resp.cpu().numpy().view(np.uint64), want), "staged calls"
         assert 0 < evs[1].elapsed_time(evs[2]) < evs[0].elapsed_time(evs[3])          # scan inside the whole query
     with pytest.raises(Exception, match="connected"):
         shard = SpiralServer(sb_params(s.prm), rank=0, world=2)

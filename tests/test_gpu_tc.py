@@ -121,6 +121,27 @@ def test_tc_server_batch_answers_every_client(sb, oracle):
         assert np.array_equal(ses.decode(got), a.pts[idx]), f"client {k} decodes record {idx}"
     with pytest.raises(SB200Error, match="capacity"):
         SpiralServer.scan_batched_tc(servers + [servers[0]] * 3)
+    # keep ONLY the limb-tile copy: the scan-layout database is freed (one copy in HBM, not two) and the single-query calls of
+    # the owner and of its views go through a one-query pass of the tensor-core kernel - same responses, bit for bit
+    free0 = torch.cuda.mem_get_info()[0]
+    srv.tc_only()
+    assert torch.cuda.mem_get_info()[0] - free0 >= srv.db_bytes * 9 // 10, "the scan-layout copy was not released"
+    assert not sb.sb200_server_db_ptr(srv.h)
+    for k in (0, 3, 5):
+        assert np.array_equal(servers[k].answer(queries[k]), want[k]), f"tc_only, client {k}"
+    SpiralServer.scan_batched_tc(servers)                             # the batched pass is unchanged
+    torch.cuda.synchronize()
+    servers[1].lift(); servers[1].fold_local(); servers[1].fold_tail(servers[1].partial_ct_ptr(), resp[1].data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(resp[1].cpu().numpy().view(np.uint64), want[1])
+    with pytest.raises(SB200Error, match="released"):
+        SpiralServer.scan_batched(servers[:2])
+    with pytest.raises(SB200Error, match="released"):
+        srv.save_db("/tmp/sb200_tc_only_should_not_exist.snap")
+    srv.load_db_items(a.pts.astype(np.uint16))                        # a reload starts over: scan layout back, tensor-core state dropped
+    assert np.array_equal(srv.answer(queries[0]), want[0])
+    with pytest.raises(SB200Error, match="enable_tc"):
+        SpiralServer.scan_batched_tc([srv])
     for s_ in reversed(servers):
         s_.close()
     for ses in sessions:
@@ -197,5 +218,12 @@ def test_tc_pack_server_batch_equals_single_query_path(sb):
     torch.cuda.synchronize()
     for k in range(count):
         assert np.array_equal(resp[k].cpu().numpy().view(np.uint64), want[k]), f"client {k}"
+    free0 = torch.cuda.mem_get_info()[0]
+    srv.tc_only()                                                     # the limb-tile planes are the only copy from here on
+    assert torch.cuda.mem_get_info()[0] - free0 >= srv.db_bytes * 9 // 10
+    for k in (0, count - 1):
+        assert np.array_equal(servers[k].answer(queries[k]), want[k]), f"tc_only, client {k}"
+    with pytest.raises(SB200Error, match="released"):
+        srv.load_random(8)
     for s_ in reversed(servers):
         s_.close()
