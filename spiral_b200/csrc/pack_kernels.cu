@@ -183,9 +183,158 @@ __global__ void __launch_bounds__(kPackScanThreads) k_scan_pack(uint32_t *__rest
         }
     }
 }
+// Wide planes (SpiralPack: 256 or more columns per z-slice, the whole query slice of a z in <= 32 KiB): the shape is known at
+// compile time, so the loop carries no stride multiplies, no fold counter and no j-split bookkeeping - one 128-bit database
+// load per column, two shared-memory query reads per pair of columns, 8 MACs per load.  CTA = T threads x U columns on one
+// (plane, z), 8 CTAs per SM.  The generic kernel issued 56 % of the scheduler's slots for 45 % FMA-pipe work and ran into the
+// power cap on 10 ms scans (profiles/r02_scan_ncu.md); accumulators fold after every 32 pairs (64 products < 2^62 on top of < 2^60).
+template <int U, int T, int UNR>
+__global__ void __launch_bounds__(T, 1024 / T) k_scan_pack_wide(uint32_t *__restrict__ out, const uint64_t *__restrict__ query,
+                                                              const uint64_t *__restrict__ db, int JP, int IC, size_t plane_words, size_t out_plane_polys) {
+    pdl_prologue();
+    extern __shared__ __align__(16) uint4 qs[];        // [JP][2]
+    const int tid = threadIdx.x, z = blockIdx.x, i0 = blockIdx.y * (T * U) + tid, plane = blockIdx.z;
+    const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+    const uint4 *qg = reinterpret_cast<const uint4 *>(query) + (size_t)z * JP * 2;
+    for (int e = tid; e < JP * 2; e += T) qs[e] = __ldg(qg + e);
+    __syncthreads();
+    const uint4 *dbz = reinterpret_cast<const uint4 *>(db + plane * plane_words) + ((size_t)z * JP) * IC + i0;
+    uint64_t acc[U][2][2];
+#pragma unroll
+    for (int u = 0; u < U; u++) acc[u][0][0] = acc[u][0][1] = acc[u][1][0] = acc[u][1][1] = 0;
+    for (int jb = 0; jb < JP; jb += 32) {
+        const uint4 *row = dbz + (size_t)jb * IC;
+        const uint4 *qb = qs + jb * 2;
+#pragma unroll UNR
+        for (int jj = 0; jj < 32; jj++) {
+            uint4 d[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) d[u] = ld_stream_u4p(row + (size_t)jj * IC + u * T);      // (j0.p, j0.b, j1.p, j1.b)
+            const uint4 q0 = qb[jj * 2], q1 = qb[jj * 2 + 1];                                     // j0:(r0.p r0.b r1.p r1.b), j1
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                acc[u][0][0] += (uint64_t)q0.x * d[u].x;  acc[u][0][1] += (uint64_t)q0.y * d[u].y;
+                acc[u][1][0] += (uint64_t)q0.z * d[u].x;  acc[u][1][1] += (uint64_t)q0.w * d[u].y;
+                acc[u][0][0] += (uint64_t)q1.x * d[u].z;  acc[u][0][1] += (uint64_t)q1.y * d[u].w;
+                acc[u][1][0] += (uint64_t)q1.z * d[u].z;  acc[u][1][1] += (uint64_t)q1.w * d[u].w;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                acc[u][r][0] = (acc[u][r][0] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[u][r][0] >> 32) * c32p;
+                acc[u][r][1] = (acc[u][r][1] & 0xffffffffull) + (uint64_t)(uint32_t)(acc[u][r][1] >> 32) * c32b;
+            }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        uint32_t *o = out + ((size_t)plane * out_plane_polys + (size_t)(i0 + u * T) * 2) * 2 * kN + z;
+        o[0] = reduce_u64(acc[u][0][0], 0); o[kN] = reduce_u64(acc[u][0][1], 1);                  // row 0: planes p, b
+        o[2 * kN] = reduce_u64(acc[u][1][0], 0); o[3 * kN] = reduce_u64(acc[u][1][1], 1);         // row 1
+    }
+}
+// Narrow planes (SpiralStreamPack: 8 columns per z-slice, 25 planes): one WARP owns a whole (plane, z) - its 32 lanes cover
+// 32 / IC consecutive 16-byte rows of IC columns, i.e. 512 contiguous bytes per load step - and the CTA's warps take different
+// planes of the same z, sharing the staged query slice.  No j-split across warps: the partial sums of the 32 / IC row groups
+// meet in two shuffles at the very end, so nothing synchronises after the staging and every warp streams its 128 KiB without
+// a bubble (the generic kernel reduces 32 partial sums through shared memory and two barriers per plane).
+template <int IC, int UNR, int S>                      // S warps share one (plane, z): each takes a contiguous 1/S of its rows
+__global__ void __launch_bounds__(512) k_scan_pack_narrow(uint32_t *__restrict__ out, const uint64_t *__restrict__ query, const uint64_t *__restrict__ db,
+                                                          int JP, size_t plane_words, size_t out_plane_polys, int planes) {
+    pdl_prologue();
+    extern __shared__ __align__(16) uint4 qs[];        // [JP][2], then (S > 1) the partial sums [warp][IC]
+    constexpr int G = 32 / IC;                         // row groups per warp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.x;
+    const int W = (int)(blockDim.x >> 5) / S;          // planes per CTA
+    const int plane = blockIdx.y * W + warp / S, split = warp % S;
+    const uint4 *qg = reinterpret_cast<const uint4 *>(query) + (size_t)z * JP * 2;
+    for (int e = tid; e < JP * 2; e += blockDim.x) qs[e] = __ldg(qg + e);
+    __syncthreads();
+    const bool live = plane < planes;
+    const int g = lane / IC, i = lane % IC;
+    const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
+    uint64_t a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+    if (live) {
+        const uint4 *dbz = reinterpret_cast<const uint4 *>(db + plane * plane_words) + ((size_t)z * JP) * IC + lane;     // row jj0 + g, column i
+        const int j_begin = split * (JP / S), j_end = j_begin + JP / S;
+        for (int jb = j_begin; jb < j_end; jb += G * 32) {
+            const uint4 *row = dbz + (size_t)jb * IC;
+            const uint4 *qb = qs + (jb + g) * 2;
+#pragma unroll 1
+            for (int k0 = 0; k0 < 32; k0 += UNR) {
+                uint4 d[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; u++) d[u] = ld_stream_u4p(row + (k0 + u) * 32);     // (j0.p, j0.b, j1.p, j1.b) of row jb + k*G + g
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const uint4 q0 = qb[(k0 + u) * G * 2], q1 = qb[(k0 + u) * G * 2 + 1];
+                    a00 += (uint64_t)q0.x * d[u].x;  a01 += (uint64_t)q0.y * d[u].y;
+                    a10 += (uint64_t)q0.z * d[u].x;  a11 += (uint64_t)q0.w * d[u].y;
+                    a00 += (uint64_t)q1.x * d[u].z;  a01 += (uint64_t)q1.y * d[u].w;
+                    a10 += (uint64_t)q1.z * d[u].z;  a11 += (uint64_t)q1.w * d[u].w;
+                }
+            }
+            a00 = (a00 & 0xffffffffull) + (uint64_t)(uint32_t)(a00 >> 32) * c32p;  a01 = (a01 & 0xffffffffull) + (uint64_t)(uint32_t)(a01 >> 32) * c32b;
+            a10 = (a10 & 0xffffffffull) + (uint64_t)(uint32_t)(a10 >> 32) * c32p;  a11 = (a11 & 0xffffffffull) + (uint64_t)(uint32_t)(a11 >> 32) * c32b;
+        }
+    }
+    uint32_t r0 = reduce_u64(a00, 0), r1 = reduce_u64(a01, 1), r2 = reduce_u64(a10, 0), r3 = reduce_u64(a11, 1);
+#pragma unroll
+    for (int off = IC; off < 32; off <<= 1) {          // sums of at most 4 residues < 2^30
+        r0 += __shfl_xor_sync(0xffffffffu, r0, off); r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, off); r3 += __shfl_xor_sync(0xffffffffu, r3, off);
+    }
+    if (S > 1) {                                       // the other warps of this plane hand their sums over (< 2^30 each, S <= 4)
+        uint4 *ps = qs + (size_t)JP * 2;
+        if (split != 0 && g == 0) ps[warp * IC + i] = make_uint4(r0, r1, r2, r3);
+        __syncthreads();
+        if (split == 0 && g == 0) {
+#pragma unroll
+            for (int k = 1; k < S; k++) { const uint4 v = ps[(warp + k) * IC + i]; r0 += v.x; r1 += v.y; r2 += v.z; r3 += v.w; }
+        }
+    }
+    if (live && split == 0 && g == 0) {
+        uint32_t *o = out + ((size_t)plane * out_plane_polys + (size_t)i * 2) * 2 * kN + z;
+        o[0] = reduce_u64(r0, 0); o[kN] = reduce_u64(r1, 1);                      // row 0: planes p, b
+        o[2 * kN] = reduce_u64(r2, 0); o[3 * kN] = reduce_u64(r3, 1);             // row 1
+    }
+}
 void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, size_t planes,
                       size_t db_plane_words, size_t out_plane_polys, cudaStream_t s) {
     const int IC = (int)num_per;
+    // SB200_PACK_SCAN_SHAPED=0: the generic kernel everywhere (experiments)
+    static const bool shaped = [] { const char *e = getenv("SB200_PACK_SCAN_SHAPED"); return !(e && *e == '0'); }();
+    const int JPs = (int)dim0 / 2;
+    if (shaped && IC % 256 == 0 && JPs % 32 == 0 && (size_t)JPs * 32 <= 32768) {
+        // measured at SpiralPack cfg3 (64 GiB): 9.63 ms with 256 threads x 1 column, 9.71 ms with 128 x 2, 11.1 ms generic
+        count_launch();
+        launch_pdl((k_scan_pack_wide<1, 256, 8>), dim3(kN, IC / 256, (unsigned)planes), dim3(256), (size_t)JPs * 32, s, out, query, db, JPs, IC, db_plane_words, out_plane_polys);
+        return;
+    }
+    if (shaped && (IC == 8 || IC == 16 || IC == 32) && JPs % ((32 / IC) * 32) == 0 && (size_t)JPs * 32 <= 32768) {
+        int W = planes <= 8 ? (int)planes : 8;
+        if (planes > 8) { int best = 1 << 30; for (int w = 8; w >= 4; w--) { const int waste = (int)(((planes + w - 1) / w) * w - planes); if (waste < best) { best = waste; W = w; } } }
+        // S warps per (plane, z): twice the loads in flight where the rows allow it (the 32 KiB query slice caps an SM at 6 CTAs)
+        static const int s_env = [] { const char *e = getenv("SB200_PACK_SCAN_SPLIT"); return e ? atoi(e) : 2; }();
+        const int S = (s_env == 2 && JPs % (2 * (32 / IC) * 32) == 0) ? 2 : 1;
+        const dim3 grid(kN, (unsigned)((planes + W - 1) / W));
+        const size_t smem_n = (size_t)JPs * 32 + (S > 1 ? (size_t)W * S * IC * 16 : 0);
+        static bool attr_n = false;
+        if (!attr_n) {
+            cudaFuncSetAttribute(k_scan_pack_narrow<8, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+            cudaFuncSetAttribute(k_scan_pack_narrow<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+            cudaFuncSetAttribute(k_scan_pack_narrow<32, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+            attr_n = true;
+        }
+        count_launch();
+#define SB200_NARROW(ICv, Sv) launch_pdl((k_scan_pack_narrow<ICv, 8, Sv>), grid, dim3(32 * W * Sv), smem_n, s, out, query, db, JPs, db_plane_words, out_plane_polys, (int)planes)
+        if (IC == 8)       { if (S == 2) SB200_NARROW(8, 2); else SB200_NARROW(8, 1); }
+        else if (IC == 16) { if (S == 2) SB200_NARROW(16, 2); else SB200_NARROW(16, 1); }
+        else               { if (S == 2) SB200_NARROW(32, 2); else SB200_NARROW(32, 1); }
+#undef SB200_NARROW
+        return;
+    }
     const int ICT = IC < kPackScanThreads ? IC : kPackScanThreads;
     const int JP = (int)dim0 / 2, JS = kPackScanThreads / ICT;
     int JC = JP;

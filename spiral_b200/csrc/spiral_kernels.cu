@@ -392,7 +392,9 @@ void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db
     const int zmask = (int)(z_slices ? z_slices : (size_t)kN) - 1;
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
     // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower
-    // (8 CTAs per SM: 0.360 ms, 7: 0.390, 6: 0.414 - round 2, profiles/r02_expansion_chains.md).
+    // (8 CTAs per SM: 0.360 ms, 7: 0.390, 6: 0.414 - round 2, profiles/r02_expansion_chains.md).  One column per thread at 44
+    // registers (11 CTAs per SM, more loads in flight) is within 1 % of this shape at 2 GiB and 8 GiB: at 6.5 TB/s the scan's
+    // 0.75 IMAD.WIDE per byte keep the multiplier pipe 56 % busy (30 IMAD.WIDE per SM per clock measured, scripts/micro/pipes.cu).
     // The query slice is staged in chunks of at most 16 KiB per CTA: with 32 KiB (first dimensions of 512 and 1024) only 6 CTAs
     // fit an SM and the scan drops from 6.45 to 5.6-6.0 TB/s (profiles/r01_scan_shapes.md).
     // Narrow shards (IC = 64 or 128 columns: a small second dimension, or a database sharded over many GPUs) keep two columns per

@@ -43,8 +43,48 @@ def build_planes(oracle, prm, rng, dim0, num_per, planes):
     return pts, db
 
 
+@pytest.mark.parametrize("dim0,num_per", [(64, 256), (128, 512), (512, 256), (32, 256), (256, 8), (2048, 8), (512, 16), (64, 32), (128, 8)])
+def test_shaped_plane_scans_match_oracle(sb, oracle, dim0, num_per):
+    """fastMultiplyQueryByDatabaseDim1 through the compile-time-shaped kernels - k_scan_pack_wide at SpiralPack widths (>= 256
+    columns per z-slice), k_scan_pack_narrow (one warp per plane and z) at SpiralStreamPack widths (8 / 16 / 32 columns) - and,
+    for the shapes outside their domains, the generic one, against the oracle; all-maximal residues in two columns and one query
+    row, so the accumulators see their largest sums."""
+    rng = np.random.default_rng(dim0 * 7 + num_per)
+    words = dim0 * num_per * N
+
+    def rnd_pb(shape):
+        return rng.integers(0, ol.P, size=shape, dtype=np.uint64) | (rng.integers(0, ol.B, size=shape, dtype=np.uint64) << np.uint64(32))
+    big = np.uint64((ol.P - 1) | ((ol.B - 1) << 32))
+    db = rnd_pb((N, num_per, dim0))                      # convertDb layout db_buf[z][ii][j]  (src/testing.cpp:316-340)
+    db[:, 3 % num_per, :] = big
+    db[:, num_per - 1, :] = big
+    q = rnd_pb((N, dim0, 2))                             # reorientCiphertextsDim1 layout [z][j][r]
+    q[:, :, 1] = big
+    db = np.ascontiguousarray(db.reshape(-1)); q = np.ascontiguousarray(q.reshape(-1))
+    assert db.size == words
+    got = np.zeros(num_per * 2 * 2 * N, dtype=np.uint64)
+    want = np.zeros_like(got)
+    sb.sb200_kernel_log_reset()
+    check(sb.sb200_fastMultiplyQueryByDatabaseDim1(p(got), p(db), p(q), dim0, num_per), sb)
+    from spiral_b200.lib import kernel_log
+    kernels = kernel_log(sb)
+    jp = dim0 // 2
+    if num_per % 256 == 0:
+        shaped = "k_scan_pack_wide" if jp % 32 == 0 and jp * 32 <= 32768 else None
+    else:
+        shaped = "k_scan_pack_narrow" if jp % ((32 // num_per) * 32) == 0 and jp * 32 <= 32768 else None
+    if shaped:
+        assert any(shaped in k for k in kernels) and "k_scan_pack" not in kernels, (shaped, kernels)
+    else:
+        assert "k_scan_pack" in kernels, kernels
+    oracle.so_fast_multiply_dim1(p(want), p(db), p(q), dim0, num_per)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, f"{bad.size} of {want.size} words differ, first at {bad[:5]}"
+
+
 @pytest.mark.parametrize("cfg,nu1,nu2,mode", [("cfg1", 5, 2, "expand"), ("cfg3", 4, 1, "expand"), ("cfg4", 5, 2, "direct"),
-                                              ("cfg4", 6, 3, "direct"), ("cfg1", 5, 3, "direct"), ("cfg5", 5, 1, "expand")])
+                                              ("cfg4", 6, 3, "direct"), ("cfg1", 5, 3, "direct"), ("cfg5", 5, 1, "expand"),
+                                              ("cfg4", 8, 3, "direct")])     # 25 planes x 8 columns, 128 pairs: k_scan_pack_narrow, 5 warps per CTA
 def test_pack_server_matches_oracle(sb, oracle, cfg, nu1, nu2, mode):
     prm = ol.make_params(cfg, nu1, nu2)
     rng = np.random.default_rng(nu1 * 100 + nu2)
