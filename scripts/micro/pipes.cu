@@ -34,6 +34,21 @@ template <int CH> __global__ void __launch_bounds__(128) k_lo(uint32_t *out, uin
     for (int i = 0; i < CH; i++) s ^= acc[i];
     if (s == 0x1234567) out[0] = s;
 }
+template <int CH> __global__ void __launch_bounds__(128) k_dfma(double *out, double a0, double b0, int iters) {
+    double acc[CH], a[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) { acc[i] = i; a[i] = a0 + i * 7 + threadIdx.x; }
+    double b = b0 + blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) acc[i] = fma(a[i], b, acc[i]);
+        b += 3.0;
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; i++) s += acc[i];
+    if (s == 0.1234567) out[0] = s;
+}
 __device__ __forceinline__ uint4 ld_na(const uint4 *p) {
     uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r;
 }
@@ -65,6 +80,8 @@ int main() {
         float ms = timed([&] { k_wide<16><<<sms * ctas, 128>>>(o64, 3, 5, iters); }, 5);
         double ops = (double)sms * ctas * 128 * 16.0 * iters;
         printf("IMAD.WIDE.U32 (+64-bit add), 16 chains, %d CTAs x 128 thr / SM: %.1f per SM per clk (at %.3f GHz nominal)\n", ctas, ops / (ms * 1e-3) / sms / (ghz * 1e9), ghz);
+        ms = timed([&] { k_dfma<16><<<sms * ctas, 128>>>((double *)o64, 3.0, 5.0, iters); }, 5);
+        printf("DFMA (fp64), 16 chains, %d CTAs x 128 thr / SM: %.1f per SM per clk\n", ctas, ops / (ms * 1e-3) / sms / (ghz * 1e9));
         ms = timed([&] { k_lo<16><<<sms * ctas, 128>>>(o32, 3, 5, iters); }, 5);
         printf("IMAD (32-bit), 16 chains, %d CTAs x 128 thr / SM: %.1f per SM per clk\n", ctas, ops / (ms * 1e-3) / sms / (ghz * 1e9));
     }

@@ -1160,6 +1160,7 @@ static void preload_exchange_kernels() {
     preload_kernel(k_expand_accum); preload_kernel(k_expand_accum_wide); preload_kernel(k_ntt_u64_to_dev); preload_kernel(k_query_from_wire);
     preload_kernel(k_scan_spiral_jsplit); preload_kernel(k_scan_spiral<2, 128, 4, true>); preload_kernel(k_scan_spiral<2, 128, 4, false>);
     preload_kernel(k_scan_spiral<2, 64, 4, false>); preload_kernel(k_scan_spiral<1, 128, 4, false>);
+    scan_tma_prepare(); preload_kernel(k_scan_pack_wide<1, 256, 8>); preload_kernel(k_scan_pack_narrow<8, 8, 2>); preload_kernel(k_scan_pack_narrow<8, 8, 1>);
     preload_kernel(k_scan_pack); preload_kernel(k_pack_accum); preload_kernel(k_split_rows); preload_kernel(k_simple_gsw_accum); preload_kernel(k_reorient_dim1);
     cudaGetLastError();
 }

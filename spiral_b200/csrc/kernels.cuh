@@ -95,6 +95,9 @@ void launch_unreorient_q(uint32_t *out, const uint64_t *q_reor, int rm_count, cu
 void launch_reorient_query(uint64_t *out, const uint32_t *cts, size_t dim0, cudaStream_t s);
 // z_slices: slices the database buffer holds (2048; an implicit database holds a power of two fewer and slice z mod z_slices is read)
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s, size_t z_slices = 0);
+// the same scan with the database streamed through shared memory by the TMA engine (scan_tma.cu); false: shape outside its domain
+bool launch_scan_spiral_tma(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s, size_t z_slices);
+void scan_tma_prepare();
 
 int launch_scan_spiral_batched(uint32_t *const *out, const uint64_t *const *query, int count, const uint64_t *db, size_t dim0,
                                size_t num_per, cudaStream_t s);   // count in {2,4}: queries sharing one database pass

@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(128, 8) k_scan_spiral_jsplit_t(uint32_t *__res
     }
 }
 void launch_scan_spiral(uint32_t *out, const uint64_t *query, const uint64_t *db, size_t dim0, size_t num_per, cudaStream_t s, size_t z_slices) {
+    if (launch_scan_spiral_tma(out, query, db, dim0, num_per, s, z_slices)) return;     // wide shards: database tiles through the TMA ring
     const int zmask = (int)(z_slices ? z_slices : (size_t)kN) - 1;
     // Tiling measured on B200 at cfg1 (profiles/r01_kernel_times_warm.md): 128 threads x 2 columns, unroll 4 is the
     // best of {64x4, 128x2, 256x1} x {unroll 2, 4, 8}; capping residency to make the 2048 CTAs an exact two waves is slower

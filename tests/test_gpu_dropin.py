@@ -78,10 +78,9 @@ def _kernels(stderr):
 # times, with the kernels that are only dispatched at these shapes) answers the same query and must return the harness's total_resp.
 @pytest.mark.parametrize("cfg,args,need_gib,kernels", [
     ("cfg1", ["8", "7", "1234"], 12,
-     ("k_scan_spiral<2, 128, 4, true>", "k_fold_mac_wide", "k_expand_accum_wide", "k_scal_to_mat_accum_tiled", "k_fold_mac", "k_fold_lift")),
+     ("k_scan_spiral_tma", "k_fold_mac_wide", "k_expand_accum_wide", "k_scal_to_mat_accum_tiled", "k_fold_mac", "k_fold_lift")),
     ("cfg5", ["9", "8", "77777"], 40,
-     ("k_scan_spiral<2, 128, 4, true>", "k_scan_spiral[query slice staged in chunks]", "k_fold_mac_wide", "k_expand_accum_wide",
-      "k_scal_to_mat_accum_tiled")),
+     ("k_scan_spiral_tma", "k_fold_mac_wide", "k_expand_accum_wide", "k_scal_to_mat_accum_tiled")),
 ])
 def test_full_size_reference_harness_and_resident_server(cfg, args, need_gib, kernels):
     exe = _driver(cfg)
@@ -103,7 +102,7 @@ def test_full_size_reference_harness_and_resident_server(cfg, args, need_gib, ke
     got = _kernels(out.stderr)
     print("kernel set:", sorted(got))
     for k in kernels:
-        assert k in got, f"{k} was not dispatched at this shape; kernels: {sorted(got)}"
+        assert any(k in g for g in got), f"{k} was not dispatched at this shape; kernels: {sorted(got)}"
 
 
 # The largest host-feasible Pack shapes with the BASELINE.json parameter sets: cfg3's SpiralPack at 2^15 records of 32 KiB
@@ -111,9 +110,9 @@ def test_full_size_reference_harness_and_resident_server(cfg, args, need_gib, ke
 @pytest.mark.parametrize("cfg,args,need_gib,leaves,kernels", [
     ("cfg3", ["10", "5", "31000", "a", "--high-rate"], 48,
      ("convertDb", "coefficientExpansion", "reorientCiphertextsDim1", "regevToSimpleGsw", "fastMultiplyQueryByDatabaseDim1",
-      "foldCiphertextsDim1", "pack", "getRescaled"), ("k_scan_pack", "k_expand_accum_wide", "k_fold_mac_wide", "k_pack_accum")),
+      "foldCiphertextsDim1", "pack", "getRescaled"), ("k_scan_pack_narrow<32, 8, 2>", "k_expand_accum_wide", "k_fold_mac_wide", "k_pack_accum")),
     ("cfg4", ["11", "3", "9999", "a", "--high-rate", "--direct-upload"], 40,
-     ("convertDb", "fastMultiplyQueryByDatabaseDim1", "foldCiphertextsDim1", "pack", "getRescaled"), ("k_scan_pack", "k_pack_accum")),
+     ("convertDb", "fastMultiplyQueryByDatabaseDim1", "foldCiphertextsDim1", "pack", "getRescaled"), ("k_scan_pack_narrow<8, 8, 2>", "k_pack_accum")),
 ])
 def test_full_size_pack_harness_and_resident_server(cfg, args, need_gib, leaves, kernels):
     exe = _driver(cfg)
@@ -132,7 +131,7 @@ def test_full_size_pack_harness_and_resident_server(cfg, args, need_gib, leaves,
     got = _kernels(out.stderr)
     print("kernel set:", sorted(got))
     for k in kernels:
-        assert k in got, f"{k} was not dispatched at this shape; kernels: {sorted(got)}"
+        assert any(k in g for g in got), f"{k} was not dispatched at this shape; kernels: {sorted(got)}"
 
 
 def test_reference_harness_random_data_mode_with_implicit_resident_database():
@@ -173,6 +172,6 @@ def test_resident_dropin_keeps_intermediates_in_hbm():
     print(f"harness timers with the resident drop-in: first dimension {fdim} us, folding {fold} us")
     assert fdim <= 1000 and fold <= 1000, f"first dimension {fdim} us, folding {fold} us (host clock of the unmodified harness)"
     kernels = _kernels(out.stderr)
-    assert "k_scan_spiral<2, 128, 4, true>" in kernels and "k_fold_decomp_ntt" in kernels
+    assert "k_scan_spiral_tma" in kernels and "k_fold_decomp_ntt" in kernels
     slow = subprocess.run([exe, "6", "3", "77"], capture_output=True, text=True, timeout=600, env=dict(os.environ, SB200_PARITY="0", SB200_RESIDENT="0"))
     assert slow.returncode == 0 and "Is correct?: 1" in slow.stdout

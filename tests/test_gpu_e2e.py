@@ -355,3 +355,38 @@ def test_implicit_constant_database_answers_every_index_with_the_constant(sb, or
         assert np.array_equal(s.decode(srv.answer(s.query(idx))), want)
     srv.close()
     s.close()
+
+
+@pytest.mark.parametrize("dim0,num_per", [(64, 128), (128, 256), (512, 128), (32, 128), (64, 64), (512, 64)])
+def test_wide_shard_scan_matches_oracle(sb, oracle, dim0, num_per):
+    """multiplyQueryByDatabase (src/spiral.cpp:628-999) at shard widths of 256 database columns and more - cfg1 / cfg5's shapes
+    scaled down in the first dimension: the TMA-ring kernel (k_scan_spiral_tma) where the shape is in its domain (64..512 first-
+    dimension ciphertexts), k_scan_spiral otherwise, both against the oracle on random residues with all-maximal columns and an
+    all-maximal query row (largest accumulator sums, every fold step)."""
+    import ctypes as C
+    from spiral_b200.lib import check, kernel_log
+    P64 = C.POINTER(C.c_uint64)
+    rng = np.random.default_rng(dim0 * 31 + num_per)
+    N = ol.N
+
+    def rnd_pb(shape):
+        return rng.integers(0, ol.P, size=shape, dtype=np.uint64) | (rng.integers(0, ol.B, size=shape, dtype=np.uint64) << np.uint64(32))
+    big = np.uint64((ol.P - 1) | ((ol.B - 1) << 32))
+    db = rnd_pb((N, num_per, 2, dim0, 2))               # reference layout B[z][ii][c][j][m]  (src/spiral.cpp:1139-1153)
+    db[:, 0, 0] = big
+    db[:, num_per - 1, 1] = big
+    q = rnd_pb((N, dim0, 2, 4))                         # reorientCiphertexts layout [z][j][m][4], lane r = 3 is zero
+    q[:, :, :, 1] = big
+    q[..., 3] = 0
+    db = np.ascontiguousarray(db.reshape(-1)); q = np.ascontiguousarray(q.reshape(-1))
+    words = num_per * 6 * 2 * N
+    got, want = np.zeros(words, dtype=np.uint64), np.zeros(words, dtype=np.uint64)
+    sb.sb200_kernel_log_reset()
+    check(sb.sb200_multiplyQueryByDatabase(got.ctypes.data_as(P64), q.ctypes.data_as(P64), db.ctypes.data_as(P64), dim0, num_per), sb)
+    kernels = kernel_log(sb)
+    assert ("k_scan_spiral_tma" in kernels) == (64 <= dim0 <= 512 and (2 * num_per) % 256 == 0), kernels
+    if (dim0, num_per) == (512, 64):                    # 128 columns, 512 first-dimension ciphertexts: the query slice goes in 16 KiB chunks
+        assert "k_scan_spiral[query slice staged in chunks]" in kernels, kernels
+    oracle.so_multiply_query_by_database(ol.ptr(want), ol.ptr(q), ol.ptr(db), dim0, num_per)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, f"{bad.size} of {want.size} words differ, first at {bad[:5]}"
