@@ -807,6 +807,7 @@ def run_workload(ctx, args, cfg, steps, headline):
     if rank == 0:
         sampler.start()
     # the timed region of `value`: EXACTLY `steps` queries, nothing but the server call inside (one graph launch per query)
+    lib.sb200_kernel_log_reset()
     launches0 = lib.sb200_launch_count()
     t_begin, t_end = ev(), ev()
     barrier()
@@ -818,6 +819,8 @@ def run_workload(ctx, args, cfg, steps, headline):
     launches = lib.sb200_launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
     drv.check(stream)
+    from spiral_b200.lib import kernel_log
+    scan_kernels = sorted(k.strip("()") for k in kernel_log(lib) if "k_scan" in k)       # what the timed queries actually dispatched
     # the same `steps` queries again with four CUDA events per query on the launching stream (stage breakdown, scan duration for
     # the roofline).  The events sit between the stages, so the stages run as separate graphs here: their sum is a few percent
     # above `value`, which has no event inside.
@@ -913,7 +916,9 @@ def run_workload(ctx, args, cfg, steps, headline):
                            "`value` is timed with no event inside the query)",
             "db_gbs_scanned": world * db_bytes_gpu / (scan_max * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": traffic_note, "kernel": drv.kernel, "peak_source": peak_src,
+                         "traffic_source": traffic_note, "kernel": ", ".join(scan_kernels) or drv.kernel, "peak_source": peak_src,
+                         "peak_note": "peak is the measured COPY bandwidth (read + write streams); a read-only stream reaches 7.2-7.4 TB/s on a B200 of this pool "
+                                      "(scripts/micro/pipes.cu, profiles/r02_micro_pipes.txt), so frac can exceed 1 for a scan that only reads",
                          "scan_ms_min_med_max": [scan_ms[0], scan_ms[len(scan_ms) // 2], scan_ms[-1]]},
             "e2e": {"value": e2e_ms / steps, "unit": "ms", "h2d_bytes_per_step": drv.h2d_bytes, "d2h_bytes_per_step": drv.d2h_bytes},
             "gpu_launches": int(launches), "clocks": clocks, "verified": verified,
