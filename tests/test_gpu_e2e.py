@@ -357,11 +357,12 @@ def test_implicit_constant_database_answers_every_index_with_the_constant(sb, or
     s.close()
 
 
-@pytest.mark.parametrize("dim0,num_per", [(64, 128), (128, 256), (512, 128), (32, 128), (64, 64), (512, 64)])
+@pytest.mark.parametrize("dim0,num_per", [(64, 128), (128, 256), (512, 128), (32, 128), (64, 64), (512, 64), (1024, 32), (256, 16), (2048, 16)])
 def test_wide_shard_scan_matches_oracle(sb, oracle, dim0, num_per):
     """multiplyQueryByDatabase (src/spiral.cpp:628-999) at shard widths of 256 database columns and more - cfg1 / cfg5's shapes
-    scaled down in the first dimension: the TMA-ring kernel (k_scan_spiral_tma) where the shape is in its domain (64..512 first-
-    dimension ciphertexts), k_scan_spiral otherwise, both against the oracle on random residues with all-maximal columns and an
+    scaled down in the first dimension - and at the narrow shards of a database spread over several GPUs (32 / 64 / 128 columns):
+    the TMA-ring kernel (k_scan_spiral_tma) where the shape is in its domain (64..1024 first-dimension ciphertexts), the register-
+    streaming kernels otherwise, all against the oracle on random residues with all-maximal columns and an
     all-maximal query row (largest accumulator sums, every fold step)."""
     import ctypes as C
     from spiral_b200.lib import check, kernel_log
@@ -384,9 +385,10 @@ def test_wide_shard_scan_matches_oracle(sb, oracle, dim0, num_per):
     sb.sb200_kernel_log_reset()
     check(sb.sb200_multiplyQueryByDatabase(got.ctypes.data_as(P64), q.ctypes.data_as(P64), db.ctypes.data_as(P64), dim0, num_per), sb)
     kernels = kernel_log(sb)
-    assert ("k_scan_spiral_tma" in kernels) == (64 <= dim0 <= 512 and (2 * num_per) % 256 == 0), kernels
-    if (dim0, num_per) == (512, 64):                    # 128 columns, 512 first-dimension ciphertexts: the query slice goes in 16 KiB chunks
-        assert "k_scan_spiral[query slice staged in chunks]" in kernels, kernels
+    ic = 2 * num_per
+    assert ("k_scan_spiral_tma" in kernels) == (64 <= dim0 <= 1024 and (ic % 256 == 0 or ic in (32, 64, 128))), kernels
+    if (dim0, num_per) == (2048, 16):                   # outside the ring kernel's domain: narrow-shard kernel, query slice in chunks
+        assert any("k_scan_spiral_jsplit" in k for k in kernels), kernels
     oracle.so_multiply_query_by_database(ol.ptr(want), ol.ptr(q), ol.ptr(db), dim0, num_per)
     bad = np.nonzero(got != want)[0]
     assert bad.size == 0, f"{bad.size} of {want.size} words differ, first at {bad[:5]}"
