@@ -716,6 +716,7 @@ def run_workload(ctx, args, cfg, steps, headline):
     wl = WORKLOADS[cfg]
     shape_args = args if headline else argparse.Namespace(workload=cfg, nu1=None, nu2=None, scaling=None)
     nu1, nu2, scaling = workload_shape(shape_args, world)
+    lib.sb200_kernel_log_reset()                             # kernel names are recorded when a launch is issued or CAPTURED: from here on, this workload's
     drv = (SpiralDriver if wl["kind"] == "spiral" else PackDriver)(args, cfg, nu1, nu2, rank, world, local_rank, torch, dist, np)
 
     def ev():
@@ -807,7 +808,6 @@ def run_workload(ctx, args, cfg, steps, headline):
     if rank == 0:
         sampler.start()
     # the timed region of `value`: EXACTLY `steps` queries, nothing but the server call inside (one graph launch per query)
-    lib.sb200_kernel_log_reset()
     launches0 = lib.sb200_launch_count()
     t_begin, t_end = ev(), ev()
     barrier()
