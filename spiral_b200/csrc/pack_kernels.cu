@@ -241,31 +241,34 @@ __global__ void __launch_bounds__(T, 1024 / T) k_scan_pack_wide(uint32_t *__rest
 // a bubble (the generic kernel reduces 32 partial sums through shared memory and two barriers per plane).
 template <int IC, int UNR, int S>                      // S warps share one (plane, z): each takes a contiguous 1/S of its rows
 __global__ void __launch_bounds__(512) k_scan_pack_narrow(uint32_t *__restrict__ out, const uint64_t *__restrict__ query, const uint64_t *__restrict__ db,
-                                                          int JP, size_t plane_words, size_t out_plane_polys, int planes) {
+                                                          int JP, size_t plane_words, size_t out_plane_polys, int planes, int row_stride, int nslab) {
     pdl_prologue();
     extern __shared__ __align__(16) uint4 qs[];        // [JP][2], then (S > 1) the partial sums [warp][IC]
     constexpr int G = 32 / IC;                         // row groups per warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.x;
-    const int W = (int)(blockDim.x >> 5) / S;          // planes per CTA
-    const int plane = blockIdx.y * W + warp / S, split = warp % S;
+    const int W = (int)(blockDim.x >> 5) / S;          // (plane, slab) pairs per CTA
+    // planes wider than 32 columns (a SpiralPack plane shared out over 2 or 4 GPUs: 128 / 64 columns) are cut into nslab slabs of
+    // IC = 32 columns; a warp then owns one (plane, slab, z) and its rows are row_stride apart instead of back to back
+    const int vp = blockIdx.y * W + warp / S, split = warp % S;
+    const int plane = vp / nslab, slab = vp % nslab;
     const uint4 *qg = reinterpret_cast<const uint4 *>(query) + (size_t)z * JP * 2;
     for (int e = tid; e < JP * 2; e += blockDim.x) qs[e] = __ldg(qg + e);
     __syncthreads();
-    const bool live = plane < planes;
+    const bool live = vp < planes * nslab;
     const int g = lane / IC, i = lane % IC;
     const uint32_t c32p = (uint32_t)((1ull << 32) % kP), c32b = (uint32_t)((1ull << 32) % kB);
     uint64_t a00 = 0, a01 = 0, a10 = 0, a11 = 0;
     if (live) {
-        const uint4 *dbz = reinterpret_cast<const uint4 *>(db + plane * plane_words) + ((size_t)z * JP) * IC + lane;     // row jj0 + g, column i
+        const uint4 *dbz = reinterpret_cast<const uint4 *>(db + plane * plane_words) + ((size_t)z * JP) * row_stride + slab * IC + g * row_stride + i;   // row jj0 + g, column i
         const int j_begin = split * (JP / S), j_end = j_begin + JP / S;
         for (int jb = j_begin; jb < j_end; jb += G * 32) {
-            const uint4 *row = dbz + (size_t)jb * IC;
+            const uint4 *row = dbz + (size_t)jb * row_stride;
             const uint4 *qb = qs + (jb + g) * 2;
 #pragma unroll 1
             for (int k0 = 0; k0 < 32; k0 += UNR) {
                 uint4 d[UNR];
 #pragma unroll
-                for (int u = 0; u < UNR; u++) d[u] = ld_stream_u4p(row + (k0 + u) * 32);     // (j0.p, j0.b, j1.p, j1.b) of row jb + k*G + g
+                for (int u = 0; u < UNR; u++) d[u] = ld_stream_u4p(row + (size_t)(k0 + u) * G * row_stride);     // (j0.p, j0.b, j1.p, j1.b) of row jb + k*G + g
 #pragma unroll
                 for (int u = 0; u < UNR; u++) {
                     const uint4 q0 = qb[(k0 + u) * G * 2], q1 = qb[(k0 + u) * G * 2 + 1];
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(512) k_scan_pack_narrow(uint32_t *__restrict__
         }
     }
     if (live && split == 0 && g == 0) {
-        uint32_t *o = out + ((size_t)plane * out_plane_polys + (size_t)i * 2) * 2 * kN + z;
+        uint32_t *o = out + ((size_t)plane * out_plane_polys + (size_t)(slab * IC + i) * 2) * 2 * kN + z;
         o[0] = reduce_u64(r0, 0); o[kN] = reduce_u64(r1, 1);                      // row 0: planes p, b
         o[2 * kN] = reduce_u64(r2, 0); o[3 * kN] = reduce_u64(r3, 1);             // row 1
     }
@@ -312,14 +315,16 @@ void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, 
         launch_pdl((k_scan_pack_wide<1, 256, 8>), dim3(kN, IC / 256, (unsigned)planes), dim3(256), (size_t)JPs * 32, s, out, query, db, JPs, IC, db_plane_words, out_plane_polys);
         return;
     }
-    if (shaped && (IC == 8 || IC == 16 || IC == 32) && JPs % ((32 / IC) * 32) == 0 && (size_t)JPs * 32 <= 32768) {
-        int W = planes <= 8 ? (int)planes : 8;
-        if (planes > 8) { int best = 1 << 30; for (int w = 8; w >= 4; w--) { const int waste = (int)(((planes + w - 1) / w) * w - planes); if (waste < best) { best = waste; W = w; } } }
-        // S warps per (plane, z): twice the loads in flight where the rows allow it (the 32 KiB query slice caps an SM at 6 CTAs)
+    const int ICs = IC > 32 ? 32 : IC, nslab = IC / ICs;               // slab width / slabs per plane (narrow kernel)
+    if (shaped && (IC == 8 || IC == 16 || IC == 32 || IC == 64 || IC == 128) && JPs % ((32 / ICs) * 32) == 0 && (size_t)JPs * 32 <= 32768) {
+        const size_t vplanes = planes * nslab;
+        int W = vplanes <= 8 ? (int)vplanes : 8;
+        if (vplanes > 8) { int best = 1 << 30; for (int w = 8; w >= 4; w--) { const int waste = (int)(((vplanes + w - 1) / w) * w - vplanes); if (waste < best) { best = waste; W = w; } } }
+        // S warps per (plane, slab, z): twice the loads in flight where the rows allow it (the 32 KiB query slice caps an SM at 6 CTAs)
         static const int s_env = [] { const char *e = getenv("SB200_PACK_SCAN_SPLIT"); return e ? atoi(e) : 2; }();
-        const int S = (s_env == 2 && JPs % (2 * (32 / IC) * 32) == 0) ? 2 : 1;
-        const dim3 grid(kN, (unsigned)((planes + W - 1) / W));
-        const size_t smem_n = (size_t)JPs * 32 + (S > 1 ? (size_t)W * S * IC * 16 : 0);
+        const int S = (s_env == 2 && JPs % (2 * (32 / ICs) * 32) == 0) ? 2 : 1;
+        const dim3 grid(kN, (unsigned)((vplanes + W - 1) / W));
+        const size_t smem_n = (size_t)JPs * 32 + (S > 1 ? (size_t)W * S * ICs * 16 : 0);
         static bool attr_n = false;
         if (!attr_n) {
             cudaFuncSetAttribute(k_scan_pack_narrow<8, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
@@ -328,10 +333,10 @@ void launch_scan_pack(uint32_t *out, const uint64_t *query, const uint64_t *db, 
             attr_n = true;
         }
         count_launch();
-#define SB200_NARROW(ICv, Sv) launch_pdl((k_scan_pack_narrow<ICv, 8, Sv>), grid, dim3(32 * W * Sv), smem_n, s, out, query, db, JPs, db_plane_words, out_plane_polys, (int)planes)
-        if (IC == 8)       { if (S == 2) SB200_NARROW(8, 2); else SB200_NARROW(8, 1); }
-        else if (IC == 16) { if (S == 2) SB200_NARROW(16, 2); else SB200_NARROW(16, 1); }
-        else               { if (S == 2) SB200_NARROW(32, 2); else SB200_NARROW(32, 1); }
+#define SB200_NARROW(ICv, Sv) launch_pdl((k_scan_pack_narrow<ICv, 8, Sv>), grid, dim3(32 * W * Sv), smem_n, s, out, query, db, JPs, db_plane_words, out_plane_polys, (int)planes, IC, nslab)
+        if (ICs == 8)       { if (S == 2) SB200_NARROW(8, 2); else SB200_NARROW(8, 1); }
+        else if (ICs == 16) { if (S == 2) SB200_NARROW(16, 2); else SB200_NARROW(16, 1); }
+        else                { if (S == 2) SB200_NARROW(32, 2); else SB200_NARROW(32, 1); }
 #undef SB200_NARROW
         return;
     }

@@ -43,10 +43,11 @@ def build_planes(oracle, prm, rng, dim0, num_per, planes):
     return pts, db
 
 
-@pytest.mark.parametrize("dim0,num_per", [(64, 256), (128, 512), (512, 256), (32, 256), (256, 8), (2048, 8), (512, 16), (64, 32), (128, 8)])
+@pytest.mark.parametrize("dim0,num_per", [(64, 256), (128, 512), (512, 256), (32, 256), (256, 8), (2048, 8), (512, 16), (64, 32), (128, 8),
+                                          (64, 64), (256, 128), (128, 64), (64, 4)])
 def test_shaped_plane_scans_match_oracle(sb, oracle, dim0, num_per):
     """fastMultiplyQueryByDatabaseDim1 through the compile-time-shaped kernels - k_scan_pack_wide at SpiralPack widths (>= 256
-    columns per z-slice), k_scan_pack_narrow (one warp per plane and z) at SpiralStreamPack widths (8 / 16 / 32 columns) - and,
+    columns per z-slice), k_scan_pack_narrow (one warp per plane and z) at SpiralStreamPack widths (8 / 16 / 32 columns, and 64 / 128 as slabs of 32) - and,
     for the shapes outside their domains, the generic one, against the oracle; all-maximal residues in two columns and one query
     row, so the accumulators see their largest sums."""
     rng = np.random.default_rng(dim0 * 7 + num_per)
@@ -72,7 +73,8 @@ def test_shaped_plane_scans_match_oracle(sb, oracle, dim0, num_per):
     if num_per % 256 == 0:
         shaped = "k_scan_pack_wide" if jp % 32 == 0 and jp * 32 <= 32768 else None
     else:
-        shaped = "k_scan_pack_narrow" if jp % ((32 // num_per) * 32) == 0 and jp * 32 <= 32768 else None
+        slab = min(num_per, 32)                          # planes of 64 / 128 columns go as slabs of 32
+        shaped = "k_scan_pack_narrow" if num_per >= 8 and jp % ((32 // slab) * 32) == 0 and jp * 32 <= 32768 else None
     if shaped:
         assert any(shaped in k for k in kernels) and "k_scan_pack" not in kernels, (shaped, kernels)
     else:
