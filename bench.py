@@ -803,6 +803,16 @@ def run_workload(ctx, args, cfg, steps, headline):
     for _ in range(max(args.warmup, 3)):
         step(timed_events=[])
     barrier()
+    if os.environ.get("SB200_BENCH_TRACE"):                  # profiling aid: rank 0's in-graph timeline of one query of this (sharded) workload
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import trace_query
+        if rank == 0:
+            with open(os.environ["SB200_BENCH_TRACE"] + f"_{cfg}_{world}gpu.md", "w") as f:
+                trace_query.trace_steps(lib, lambda: step(timed_events=None), 4, f"{workload_name(cfg, nu1, nu2)}, rank 0 of {world}", f)
+        else:
+            for _ in range(4):
+                step(timed_events=None)
+        barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

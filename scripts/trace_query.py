@@ -65,31 +65,38 @@ def main():
     for _ in range(5):
         srv.process(None, st.cuda_stream, None)
     torch.cuda.synchronize()
+    trace_steps(lib, lambda: srv.process(None, st.cuda_stream, None), a.queries, bench.workload_name(a.workload, nu1, nu2), sys.stdout)
+    srv.close()
+
+
+def trace_steps(lib, step, queries, title, out, sync=None):
+    """Runs `step` `queries` times with the in-graph trace on and prints the LAST query's timeline to `out`."""
+    sync = sync or torch.cuda.synchronize
+    sync()
     assert lib.sb200_trace_enable(4096) == 0
-    for _ in range(a.queries):
-        srv.process(None, st.cuda_stream, None)
-    torch.cuda.synchronize()
+    for _ in range(queries):
+        step()
+    sync()
     buf = np.zeros(4096 * 3, dtype=np.uint64)
     n = lib.sb200_trace_read(buf.ctypes.data, 4096, 1)
     lib.sb200_trace_enable(0)
     rec = buf[:3 * n].reshape(n, 3)
-    per = n // a.queries
-    rec = rec[(a.queries - 1) * per:]                       # the last query
+    per = n // queries
+    rec = rec[(queries - 1) * per:]                         # the last query
     rec = rec[np.argsort(rec[:, 1], kind="stable")]
     t0 = int(rec[0, 1])
-    print(f"# {bench.workload_name(a.workload, nu1, nu2)}: one query, {per} kernels, {(int(rec[-1, 1]) - t0) / 1e3:.1f} us from the first to the last dependency-resolved time")
+    print(f"# {title}: one query, {per} kernels, {(int(rec[-1, 1]) - t0) / 1e3:.1f} us from the first to the last dependency-resolved time", file=out)
     names = kernel_lines()
-    print("| # | kernel | grid | block | scheduled us | ready us | to next ready us | waited us |")
-    print("|---:|---|---|---:|---:|---:|---:|---:|")
+    print("| # | kernel | grid | block | scheduled us | ready us | to next ready us | waited us |", file=out)
+    print("|---:|---|---|---:|---:|---:|---:|---:|", file=out)
     for i, (ts, tr, shape) in enumerate(rec):
         shape = int(shape)
         gx, gy, bx, line = shape & 0xFFFFF, (shape >> 20) & 0xFFFF, (shape >> 36) & 0xFFF, shape >> 48
         if line >= 0xF000:
-            print(f"| {i} | mark {line & 0xFFF} | | | | {(int(tr) - t0) / 1e3:.1f} | | |")
+            print(f"| {i} | mark {line & 0xFFF} | | | | {(int(tr) - t0) / 1e3:.1f} | | |", file=out)
             continue
         nxt = (int(rec[i + 1, 1]) - int(tr)) / 1e3 if i + 1 < len(rec) else 0.0
-        print(f"| {i} | {'/'.join(names.get(line, ['?']))} | ({gx},{gy}) | {bx} | {(int(ts) - t0) / 1e3:.1f} | {(int(tr) - t0) / 1e3:.1f} | {nxt:.1f} | {(int(tr) - int(ts)) / 1e3:.1f} |")
-    srv.close()
+        print(f"| {i} | {'/'.join(names.get(line, ['?']))} | ({gx},{gy}) | {bx} | {(int(ts) - t0) / 1e3:.1f} | {(int(tr) - t0) / 1e3:.1f} | {nxt:.1f} | {(int(tr) - int(ts)) / 1e3:.1f} |", file=out)
 
 
 if __name__ == "__main__":
