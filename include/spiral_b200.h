@@ -327,6 +327,12 @@ int sb200_pack_server_upload_direct_split(sb200_pack_server *srv, const uint64_t
 /* all server stages of the query last uploaded in ONE call (every rank of a sharded server calls it; response on rank 0, in
  * total_resp_dev or the server's own buffer when NULL); marks as sb200_server_process */
 int sb200_pack_server_process(sb200_pack_server *srv, uint64_t *total_resp_dev, void *stream, void *const *marks);
+/* as sb200_server_prepare: build the graphs _process replays without running anything */
+int sb200_pack_server_prepare(sb200_pack_server *srv, uint64_t *total_resp_dev, void *stream);
+/* 1 when the packed-query expansion (coefficientExpansion, src/testing.cpp:40-105) is shared out: a column-sharded server with
+ * connected peers expands only the first-dimension ciphertexts j = rank (mod world) and stores them, reoriented, into every rank's
+ * query buffer over NVLink (the GSW-bit chain stays whole on every rank) */
+int sb200_pack_server_expansion_sharded(const sb200_pack_server *srv);
 size_t sb200_pack_server_db_bytes(const sb200_pack_server *srv);                  /* this shard */
 size_t sb200_pack_server_response_words(const sb200_pack_server *srv);
 

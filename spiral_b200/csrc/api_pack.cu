@@ -145,6 +145,13 @@ struct sb200_pack_server {
     DBuf<int> lists, ct_idx_first, ct_idx_direct, ct_idx_bits, poly_idx_bits;
     DBuf<uint16_t> perms;
     GraphSlot g_convert, g_convert_wire[2], g_fold, g_tail, g_xchg;
+    // sharded expansion (column-sharded servers with connected peers): this rank expands only the ancestors of the first-dimension
+    // ciphertexts j = rank (mod world) - plus the whole odd chain, the GSW bits are few - and k_reorient_dim1_allgather stores its
+    // 2^nu1 / world reoriented ciphertexts into every rank's query buffer (as the Spiral server's ScalToMat does)
+    DBuf<int> lists_sh, ct_idx_first_s;
+    std::vector<int> offs_sh, cnt_sh;
+    bool expand_shard_eligible = false;
+    GraphSlot g_convert_sh[3];
     cudaStream_t own_stream = nullptr;
     // sharding: 0 = second dimension strided (ii = rank mod world of EVERY plane; one exchange, then log2(world) tail folds);
     // 1 = whole planes (plane p lives on rank p mod world: no exchange before the packing; src/testing.cpp:1045-1061 runs
@@ -247,6 +254,27 @@ static int pack_server_create_impl(sb200_pack_server **out, const sb200_params *
     A(s->ct_idx_bits.alloc(nbits ? nbits : 1)); A(s->poly_idx_bits.alloc(nbits ? 2 * nbits : 1));
     if (e != cudaSuccess) { delete s; return fail(SB200_ERR_CUDA, "pack_server_create: device allocation failed: %s", cudaGetErrorString(e)); }
     A(s->lists.up(list.data(), list.size()));
+    if (world > 1 && !s->shard_planes && s->stopround > 0 && s->dim0 % (2 * (size_t)world) == 0 && s->dim0 / world >= 2) {
+        // even output i = 2 j'' of round r is kept when j'' = rank modulo min(world, 2^r) (the ancestors of the leaves j = rank mod
+        // world); odd outputs (the GSW-bit chain) are all kept
+        std::vector<int> ls;
+        s->offs_sh.resize(s->g); s->cnt_sh.resize(s->g);
+        for (size_t r = 0; r < s->g; r++) {
+            s->offs_sh[r] = (int)ls.size();
+            const size_t m = std::min((size_t)world, (size_t)1 << r);
+            for (int k = 0; k < s->cnt[r]; k++) {
+                const int i = list[s->offs[r] + k];
+                if ((i & 1) || ((size_t)(i / 2)) % m == (size_t)rank % m) ls.push_back(i);
+            }
+            s->cnt_sh[r] = (int)ls.size() - s->offs_sh[r];
+        }
+        const size_t cl = s->dim0 / world;
+        std::vector<int> cfs(cl);
+        for (size_t jl = 0; jl < cl; jl++) cfs[jl] = (int)(2 * ((size_t)rank + (size_t)world * jl));
+        A(s->lists_sh.alloc(ls.size())); A(s->lists_sh.up(ls.data(), ls.size()));
+        A(s->ct_idx_first_s.alloc(cl)); A(s->ct_idx_first_s.up(cfs.data(), cl));
+        s->expand_shard_eligible = true;
+    }
     // ciphertext selections: packed query = reorientCiphertextsDim1(..., 2) and regevToSimpleGsw(..., 2, 1) (:1018, :1024);
     // direct upload = the 2^nu1 first-dimension ciphertexts as they arrive
     std::vector<int> cf(s->dim0), cd(s->dim0), cb(nbits), pb(2 * nbits);
@@ -399,7 +427,25 @@ extern "C" int sb200_pack_server_upload_query(sb200_pack_server *s, const uint64
 extern "C" int sb200_pack_server_expand_and_convert(sb200_pack_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!s->have_params) return fail(SB200_ERR_STATE, "pack expand_and_convert: expansion keys / V not set");
+    if (s->world > 1 && s->xchg_connected && s->expand_shard_eligible) {
+        TRY(run_stage(s->g_convert_sh[s->wire_kind], PS(s, stream), s->xchg.p, nullptr, [&](cudaStream_t st) {
+            if (s->wire_kind) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);
+            else launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
+            // store_self: an even output may be processed without its sibling, which would otherwise have stored the base value
+            launch_expand(s->cv.p, s->plan, s->W_left.p, s->W_right.p, s->neg1.p, s->perms.p, s->c0.p, s->c1.p, s->ginv.p, s->lists_sh.p,
+                          s->offs_sh.data(), s->cnt_sh.data(), st, 0, -1, -1, 1);
+            // the GSW conversion first: the all-gather may wait for rank 0's acknowledgement of the previous query
+            launch_regev_to_simple_gsw(s->gsw.p, nullptr, s->cv.p, s->ct_idx_bits.p, s->poly_idx_bits.p, (int)s->prm.nu2, (int)s->prm.t_gsw, s->V.p,
+                                       (int)s->prm.t_conv, s->conv_raw.p, s->conv_ntt.p, st);
+            launch_reorient_dim1_allgather(s->qpeers, s->cv.p, s->ct_idx_first_s.p, s->dim0, (size_t)s->rank, (size_t)s->world, s->dim0 / s->world,
+                                           s->rank, s->world, s->xchg_state.p, s->xchg.p, st);
+        }));
+        s->query_mode = 1;
+        s->query_wait_pending = true;        // the scan waits for every rank's rows of THIS query
+        return SB200_OK;
+    }
     GraphSlot &slot = s->wire_kind ? s->g_convert_wire[s->wire_kind - 1] : s->g_convert;
+    s->query_wait_pending = false;
     return run_stage(slot, PS(s, stream), nullptr, nullptr, [&](cudaStream_t st) {
         if (s->wire_kind) launch_query_from_wire(s->cv.p, s->q_wire.p, s->wire_kind, st);
         else launch_ntt_u64_to_dev(s->cv.p, s->stage.p, 2, st);
@@ -439,7 +485,7 @@ extern "C" int sb200_pack_server_upload_direct_split(sb200_pack_server *s, const
     // GSW ciphertexts first: the all-gather kernel may wait for rank 0's acknowledgement of the previous query, nothing should queue behind it
     if (fd) { TRY(pack_up(s, s->gsw, 0, v_folding_host, fd * 2 * 2 * ell, st)); CU(cudaStreamSynchronize(st)); }
     TRY(pack_up(s, s->cv, 0, v_firstdim_slice_host, jc * 2, st));
-    launch_reorient_dim1_allgather(s->qpeers, s->cv.p, s->dim0, (size_t)s->rank * jc, jc, s->rank, s->world, s->xchg_state.p, s->xchg.p, st);
+    launch_reorient_dim1_allgather(s->qpeers, s->cv.p, nullptr, s->dim0, (size_t)s->rank * jc, 1, jc, s->rank, s->world, s->xchg_state.p, s->xchg.p, st);
     CHECK_LAUNCH();
     s->query_mode = 3;
     s->query_wait_pending = true;        // the next scan waits for every rank's slice of THIS upload (later scans reuse the query)
@@ -449,7 +495,7 @@ extern "C" int sb200_pack_server_upload_direct_split(sb200_pack_server *s, const
 extern "C" int sb200_pack_server_scan(sb200_pack_server *s, void *stream) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     for (size_t p = 0; p < s->planes; p++) if (!pack_plane_loaded(s, p)) return fail(SB200_ERR_STATE, "pack scan: database plane %zu not loaded", p);
-    if (s->query_mode == 3 && s->query_wait_pending) {
+    if (s->query_wait_pending && !tl_prepare_only) {
         launch_query_wait(s->xchg.p, s->world, s->xchg_state.p, s->xchg_state.p + 1, PS(s, stream));
         s->query_wait_pending = false;
     }
@@ -690,6 +736,23 @@ extern "C" int sb200_pack_server_xchg_error(sb200_pack_server *s, void *stream) 
 // all server stages of the query last uploaded (sb200_pack_server_upload_query / _upload_direct / _upload_direct_split) in ONE
 // call, sharded servers included (every rank calls it; the response lands on rank 0).  marks: NULL or four cudaEvent_t recorded
 // before the expansion, before and after the first-dimension scan and at the end.
+// Capture and instantiate the graphs sb200_pack_server_process will replay, without running anything (as sb200_server_prepare):
+// several shards driven from one process on one device must not build graphs while another shard's kernel spins on a flag.
+extern "C" int sb200_pack_server_prepare(sb200_pack_server *s, uint64_t *total_resp_dev, void *stream) {
+    if (!s) return fail(SB200_ERR_ARG, "null server");
+    if (s->world > 1 && !s->xchg_connected) return fail(SB200_ERR_STATE, "pack prepare: sharded server without connected peers");
+    CU(cudaSetDevice(s->device));
+    const int mode = s->query_mode; const bool pending = s->query_wait_pending;
+    tl_prepare_only = true;
+    int rc = s->have_params ? sb200_pack_server_expand_and_convert(s, stream) : SB200_OK;
+    if (!rc) rc = sb200_pack_server_fold_local(s, stream);
+    if (!rc) rc = sb200_pack_server_exchange_and_tail(s, total_resp_dev, stream);
+    tl_prepare_only = false;
+    s->query_mode = mode; s->query_wait_pending = pending;
+    CU(cudaStreamSynchronize(PS(s, stream)));
+    return rc;
+}
+extern "C" int sb200_pack_server_expansion_sharded(const sb200_pack_server *s) { return s && s->world > 1 && s->xchg_connected && s->expand_shard_eligible && s->have_params; }
 extern "C" int sb200_pack_server_process(sb200_pack_server *s, uint64_t *total_resp_dev, void *stream, void *const *marks) {
     if (!s) return fail(SB200_ERR_ARG, "null server");
     if (!s->query_mode) return fail(SB200_ERR_STATE, "pack process: no query uploaded");

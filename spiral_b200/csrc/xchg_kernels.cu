@@ -168,9 +168,11 @@ unsigned int *xchg_arrive_aux_ptr(void *buf) { return &reinterpret_cast<XchgBuf 
 // slice of the first-dimension ciphertexts and stores it into EVERY rank's query buffer, then raises qflags[rank] there;
 // k_query_wait (first kernel of the scan's stream order) waits until all world slices of this epoch have landed.
 struct QueryPeers { uint64_t *query[kXchgMaxWorld]; XchgBuf *xb[kXchgMaxWorld]; };
+// ct_idx (nullable): position in cv of this rank's k-th ciphertext (a sharded EXPANSION keeps the leaves j = rank + world * k of the
+// tree at cv[2 j]; an uploaded slice is simply cv[k]); its row in the query is j_begin + k * j_stride
 __global__ void __launch_bounds__(256) k_reorient_dim1_allgather(const __grid_constant__ QueryPeers peers, const uint32_t *__restrict__ cv,
-                                                                 int dim0, int j_begin, int j_count, int rank, int world,
-                                                                 const unsigned int *epoch, XchgBuf *mine) {
+                                                                 const int *__restrict__ ct_idx, int dim0, int j_begin, int j_stride, int j_count,
+                                                                 int rank, int world, const unsigned int *epoch, XchgBuf *mine) {
     pdl_prologue_no_early_dependents();
     // this query is number e of the exchange sequence; its slices may only overwrite the peers' query buffers once rank 0 has
     // gathered query e - 1 from EVERY rank (ack >= e - 1: all scans of the previous query are over)
@@ -187,14 +189,14 @@ __global__ void __launch_bounds__(256) k_reorient_dim1_allgather(const __grid_co
         ulonglong2 w[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
-            const uint32_t *ct = cv + (size_t)(jl + t) * 2 * 2 * kN;
+            const uint32_t *ct = cv + (size_t)(ct_idx ? ct_idx[jl + t] : jl + t) * 2 * 2 * kN;
             w[t].x = (uint64_t)ct[z] | ((uint64_t)ct[kN + z] << 32);
             w[t].y = (uint64_t)ct[2 * kN + z] | ((uint64_t)ct[3 * kN + z] << 32);
         }
-        const size_t o = (size_t)z * dim0 + j_begin + jl;
+        const size_t o = (size_t)z * dim0 + j_begin + (size_t)jl * j_stride;
         for (int r = 0; r < world; r++) {
             ulonglong2 *q = reinterpret_cast<ulonglong2 *>(peers.query[(rank + r) % world]);      // start with the own copy, spread the peers
-            q[o] = w[0]; q[o + 1] = w[1];
+            q[o] = w[0]; q[o + j_stride] = w[1];
         }
     }
     __threadfence_system();
@@ -212,11 +214,12 @@ __global__ void k_query_wait(XchgBuf *mine, int world, const unsigned int *epoch
     pdl_prologue_no_early_dependents();
     if ((int)threadIdx.x < world && !spin_until_ge(&mine->qflags[threadIdx.x], *epoch + 1)) *error = 3;
 }
-void launch_reorient_dim1_allgather(const QueryPeers &peers, const uint32_t *cv, size_t dim0, size_t j_begin, size_t j_count, int rank, int world,
-                                    const unsigned int *qepoch, void *mine, cudaStream_t s) {
+void launch_reorient_dim1_allgather(const QueryPeers &peers, const uint32_t *cv, const int *ct_idx, size_t dim0, size_t j_begin, size_t j_stride, size_t j_count,
+                                    int rank, int world, const unsigned int *qepoch, void *mine, cudaStream_t s) {
     const size_t n = (size_t)kN * (j_count / 2);
     count_launch();
-    launch_pdl(k_reorient_dim1_allgather, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, peers, cv, (int)dim0, (int)j_begin, (int)j_count, rank, world, qepoch, (XchgBuf *)mine);
+    launch_pdl(k_reorient_dim1_allgather, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, peers, cv, ct_idx, (int)dim0, (int)j_begin, (int)j_stride, (int)j_count,
+               rank, world, qepoch, (XchgBuf *)mine);
 }
 void launch_query_wait(void *mine, int world, const unsigned int *qepoch, unsigned int *error, cudaStream_t s) {
     count_launch();

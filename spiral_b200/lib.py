@@ -135,6 +135,8 @@ def load_library():
         "sb200_pack_server_xchg_error": (C.c_int, [vp, vp]),
         "sb200_pack_server_upload_direct_split": (C.c_int, [vp, vp, vp, vp]),
         "sb200_pack_server_process": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
+        "sb200_pack_server_prepare": (C.c_int, [vp, vp, vp]),
+        "sb200_pack_server_expansion_sharded": (C.c_int, [vp]),
         "sb200_pack_server_upload_query": (C.c_int, [vp, vp, vp]),
         "sb200_pack_server_expand_and_convert": (C.c_int, [vp, vp]),
         "sb200_pack_server_upload_direct": (C.c_int, [vp, vp, vp, vp]),

@@ -280,6 +280,13 @@ class PackServer:
         """All server stages of the uploaded query in one call (sharded servers: every rank calls it)."""
         check(self.lib.sb200_pack_server_process(self.h, resp_ptr, stream, marks), self.lib)
 
+    def prepare(self, resp_ptr=None, stream=None):
+        """Build the CUDA graphs process() replays, without running anything."""
+        check(self.lib.sb200_pack_server_prepare(self.h, resp_ptr, stream), self.lib)
+
+    def expansion_sharded(self):
+        return bool(self.lib.sb200_pack_server_expansion_sharded(self.h))
+
     def enable_tc(self, capacity=16):
         check(self.lib.sb200_pack_server_enable_tc(self.h, capacity), self.lib)
 

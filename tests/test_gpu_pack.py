@@ -217,7 +217,8 @@ def test_pack_device_random_database_is_deterministic_and_in_range(sb):
 
 @pytest.mark.parametrize("cfg,nu1,nu2,mode,world,shard", [
     ("cfg3", 4, 2, "expand", 2, "nu2"), ("cfg3", 3, 2, "expand", 4, "planes"), ("cfg4", 5, 3, "direct", 8, "planes"),
-    ("cfg4", 5, 3, "split", 4, "planes"), ("cfg4", 4, 3, "split", 2, "nu2"), ("cfg1", 4, 1, "expand", 2, "planes"), ("cfg4", 5, 2, "direct", 4, "nu2")])
+    ("cfg4", 5, 3, "split", 4, "planes"), ("cfg4", 4, 3, "split", 2, "nu2"), ("cfg1", 4, 1, "expand", 2, "planes"), ("cfg4", 5, 2, "direct", 4, "nu2"),
+    ("cfg3", 5, 3, "expand", 4, "nu2"), ("cfg1", 5, 3, "expand", 8, "nu2"), ("cfg5", 4, 1, "expand", 2, "nu2")])
 def test_pack_peer_exchange_and_one_call_process(sb, oracle, cfg, nu1, nu2, mode, world, shard):
     """The exchange step inside the product (sb200_pack_server_exchange_and_tail, same peer-memory protocol as the Spiral server),
     both shardings - second dimension (tail folds on rank 0) and whole planes (no fold after the exchange) -, the split direct
@@ -253,6 +254,12 @@ def test_pack_peer_exchange_and_one_call_process(sb, oracle, cfg, nu1, nu2, mode
         srv.xchg_connect_local(shards)
     import torch
     streams = [torch.cuda.Stream() for _ in shards]
+    # column-sharded servers share out the EXPANSION of a packed query too: each expands the first-dimension ciphertexts
+    # j = rank (mod world) and all-gathers them, reoriented, through peer stores
+    for srv in shards:
+        assert srv.expansion_sharded() == (mode == "expand" and shard == "nu2" and dim0 % (2 * world) == 0)
+    for srv, st in zip(shards, streams):                        # every graph exists before any shard's kernel waits for another's
+        srv.prepare(None, st.cuda_stream)
     jc = dim0 // world
     for rep in range(3):                                        # later passes replay the captured graphs and reuse the exchange slots
         query, v_first, v_fold = rnd_ntt(rng, 2), rnd_ntt(rng, dim0 * 2), rnd_ntt(rng, max(fd, 1) * 2 * 2 * ell)
