@@ -646,7 +646,9 @@ class PackDriver:
         self.exchange = ("none (1 GPU)" if world == 1 else
                          (f"plane sharding: peer-memory stores of one folded 32 KiB ciphertext per plane to rank 0 (no fold after the exchange); "
                           f"the direct-upload query is uploaded 1/{world} per rank and all-gathered by the reorientation kernel over NVLink") if self.shard == "planes"
-                         else f"peer-memory stores of {self.planes} surviving 32 KiB ciphertexts per GPU + flags over NVLink, fused into the stream")
+                         else f"peer-memory stores of {self.planes} surviving 32 KiB ciphertexts per GPU + flags over NVLink, fused into the stream"
+                              + ("; the expansion is sharded too: every rank expands 1/N of the first-dimension ciphertexts and its reorientation kernel "
+                                 "stores them into all ranks' query buffers" if self.direct is False and world > 1 else ""))
 
     def planted(self, idx):
         return self.np.stack([planted_record(self.np, idx * 64 + pl, 1, self.p["p_db"])[0] for pl in range(self.planes)])
