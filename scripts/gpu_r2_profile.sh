@@ -9,7 +9,7 @@ cap() { # name kernel-regex bench-args...
 }
 cap scan_cfg1 k_scan_spiral
 cap scan_cfg5 k_scan_spiral --workload cfg5
-cap scan_jsplit_9_5 k_scan_spiral_jsplit --workload cfg5 --nu2 5
+cap scan_shard64_9_5 k_scan_spiral --workload cfg5 --nu2 5
 cap scan_pack_cfg4 k_scan_pack --workload cfg4
 cap scan_pack_cfg3 k_scan_pack --workload cfg3
 ls -la gpurun_out/r2_*.ncu-rep

@@ -16,7 +16,7 @@ SOURCES = ["spiral_b200/csrc/spiral_kernels.cu", "spiral_b200/csrc/scan_tma.cu",
 CAPS = {  # capture -> (json key, description, algorithmic bytes)
     "scan_cfg1": ("dram_bytes_per_launch", "k_scan_spiral_tma, cfg1 ./spiral 8 7 (2 GiB)", 2 << 30),
     "scan_cfg5": ("dram_bytes_per_launch_cfg5_1gpu", "k_scan_spiral_tma, cfg5 ./spiral 9 8 (8 GiB)", 8 << 30),
-    "scan_jsplit_9_5": ("dram_bytes_per_launch_cfg5_8gpu", "k_scan_spiral_jsplit, ./spiral 9 5 = cfg5's 1 GiB shard of an 8-GPU run (64 columns)", 1 << 30),
+    "scan_shard64_9_5": ("dram_bytes_per_launch_cfg5_8gpu", "k_scan_spiral_tma<64>, ./spiral 9 5 = cfg5's 1 GiB shard of an 8-GPU run (64 columns)", 1 << 30),
     "scan_pack_cfg4": ("dram_bytes_per_launch_cfg4_1gpu", "k_scan_pack_narrow, cfg4 ./spiral 11 3 (25 planes x 8 columns, 6.25 GiB)", 25 * 8 * 2048 * (1 << 14)),
     "scan_pack_cfg3": ("dram_bytes_per_launch_cfg3_1gpu", "k_scan_pack_wide, cfg3 ./spiral 10 8 (16 planes x 256 columns, 64 GiB)", 64 << 30),
 }
