@@ -3,15 +3,17 @@
 //
 // Why: k_scan_spiral keeps 24 accumulator registers per thread, so ptxas holds only ~5 of its 8 unrolled 16-byte loads in flight
 // and an SM has ~80 KiB outstanding - 6.0-6.5 TB/s, while a read-only stream with 130 KiB outstanding per SM reaches 7.1-7.3 TB/s
-// on the same GPU (k_scan_pack_wide, scripts/micro/pipes.cu).  Here the bytes in flight are a ring of NS tiles of R database rows
-// (R x 4 KiB) per CTA, filled by one producer lane; the 128 consumer threads read the tiles with conflict-free 128-bit shared
-// loads and run the same 12 MACs per 16 bytes.  Same arithmetic, same results, same output layout as k_scan_spiral.
+// on the same GPU (k_scan_pack_wide, scripts/micro/pipes.cu).  Here the bytes in flight are a ring of NS tiles of 16 KiB per CTA,
+// filled by one producer lane; the 256 consumer threads read the tiles with conflict-free 128-bit shared loads and run the same
+// 12 MACs per 16 bytes.  Same arithmetic, same results, same output layout as k_scan_spiral.
 //
 //   CTA = one z-slice x 256 database columns (or the whole shard when narrower): 8 consumer warps + 1 producer warp
-//   smem = NS x R x 4 KiB tiles | the z-slice of the query (dim0 x 64 B, one bulk copy) | 2 NS + 1 mbarriers
+//   smem = NS x 16 KiB tiles | the z-slice of the query (dim0 x 64 B, one bulk copy) | 2 NS + 1 mbarriers
 // Measured (cfg1 2 GiB / cfg5 8 GiB, scan stage between CUDA events): k_scan_spiral 0.356 / 1.346 ms; this kernel 0.336 / 1.269 ms
-// = 6.39 / 6.77 TB/s.  Tile and ring shapes R x NS in {2,4,8} x {2..6} and U in {1,2} are within 3 % of each other once an SM
-// holds ~100 KiB of tiles; requesting the first tiles before griddepcontrol.wait (the database is constant) bought nothing.
+// = 6.39 / 6.77 TB/s.  Tiles of 2 / 4 / 8 rows, rings of 2..6 slots and 4 or 8 consumer warps are within 3 % of each other once an
+// SM holds ~100 KiB of tiles; requesting the first tiles before griddepcontrol.wait (the database is constant) bought nothing.
+// compute-sanitizer: memcheck clean; racecheck flags every bulk-copy write / shared read pair - it does not model completion by
+// transaction count (mbarrier complete_tx), which is what orders them.
 #include "kernels.cuh"
 
 namespace sb200 {
